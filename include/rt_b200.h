@@ -1,0 +1,150 @@
+/* rt_b200.h — C ABI of the B200-native per-pixel ray-tracing hot path.
+ *
+ * This is the drop-in boundary for catalinlup/RayTracer-Group27's render path.  The reference has no
+ * FFI of its own: its seam is the free function renderRayTracing(Scene&, const Trackball&, const
+ * BoundingVolumeHierarchy&, Screen&, ...) (src/main.cpp:340-341) plus the classes it touches.  The C++
+ * host layer in raytracer-group27_b200/host/ keeps those class names and forwards to the entry points
+ * below; everything device-side (sm_100a kernels, device memory, streams) stays behind this header.
+ * Plain pointers and sizes only, no C++ or torch types.  Every function returns RT_OK (0) or an error
+ * code; rt_last_error() returns a thread-local message for the last failure.  There is no CPU fallback:
+ * without a usable CUDA device rt_create fails.
+ */
+#ifndef RT_B200_H
+#define RT_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_OK 0
+#define RT_ERR_INVALID 1 /* bad argument / call order                     */
+#define RT_ERR_CUDA 2    /* CUDA runtime error (message in rt_last_error) */
+#define RT_ERR_OVERFLOW 3 /* a ray queue overflowed its capacity          */
+#define RT_ERR_IO 4      /* file not found / unparsable                   */
+
+typedef struct rt_ctx rt_ctx; /* one per GPU (one process per GPU); owns all device buffers */
+
+/* Material of a mesh — replaces `struct Material` (src/mesh.h:21-31) minus the texture. */
+typedef struct {
+    float kd[3];
+    float ks[3];
+    float shininess;
+    float transparency; /* 1 = opaque; != 1 takes the dielectric branch (src/main.cpp:257-290) */
+} rt_material;
+
+typedef struct { float position[3]; float color[3]; } rt_point_light;                /* src/scene.h:55-59 */
+typedef struct { float position[3]; float radius; float color[3]; } rt_sphere_light; /* src/scene.h:61-66 */
+
+/* Camera state — replaces the Trackball members read by position()/generateRay()
+ * (framework/include/trackball.h:44-52, framework/src/trackball.cpp:65-68,87-98).  The aspect ratio is
+ * width/height of rt_params, as Window::aspectRatio() (framework/src/window.cpp:334-337). */
+typedef struct {
+    float look_at[3];
+    float euler[3]; /* radians */
+    float dist;
+    float fovy;     /* radians */
+} rt_camera;
+
+/* Per-frame knobs — replace the file-scope globals renderRayTracing reads (src/main.cpp:58-60,123-127)
+ * and its arguments (src/main.cpp:340-341). */
+typedef struct {
+    int width, height;          /* windowResolution, src/main.cpp:33 (parameterised)                    */
+    int max_reflection_level;   /* src/main.cpp:123                                                     */
+    int sphere_light_ray_count; /* src/main.cpp:124                                                     */
+    int glossy_ray_count;       /* src/main.cpp:126; only 1 is accepted (rand() glossy rays: out of scope) */
+    float refraction_factor;    /* src/main.cpp:127                                                     */
+    int sample_mode;            /* 0: one ray per pixel; 1: anti_aliasing (4 taps); 2: multipleRays     */
+    int sample_size;            /* 4 / 16 / 64 when sample_mode == 2                                    */
+    int exhaustive;             /* 1: closest hit loops over every triangle in mesh order (the reference's
+                                   useBVH=false path, bounding_volume_hierarchy.cpp:51-72); 0: BVH      */
+} rt_params;
+
+typedef struct {
+    uint64_t primary_rays;
+    uint64_t shadow_queries;  /* one per cansee loop iteration (src/shadow.cpp:41-66) */
+    uint64_t secondary_rays;  /* reflection + refraction rays                        */
+    uint64_t node_visits;     /* 32-byte BVH nodes fetched (0 unless built with RT_COUNTERS) */
+    uint64_t tri_tests;       /* triangles fetched                                          */
+    uint64_t tri_tests_full;  /* tests that also ran the three edge functions               */
+    float gpu_ms;             /* device time of the frame (CUDA events on the context's stream) */
+    int kernel_launches;      /* kernels launched for the frame                                 */
+    int batches;              /* wavefront batches the frame was split into                     */
+} rt_stats;
+
+#define RT_BVH_LBVH_DEVICE 0      /* Morton codes -> radix sort -> Karras hierarchy -> refit, all on the GPU */
+#define RT_BVH_SAH_HOST 1         /* binned SAH built by the host and uploaded                               */
+
+/* ---- lifetime ---- */
+int rt_create(int device, rt_ctx** out);
+int rt_destroy(rt_ctx* ctx);
+/* Launch all work of this context on `cuda_stream` (a cudaStream_t, e.g. torch's current stream). */
+int rt_set_stream(rt_ctx* ctx, void* cuda_stream);
+
+/* ---- scene (replaces BoundingVolumeHierarchy::BoundingVolumeHierarchy(Scene*), which copies every
+ *      triangle out of the scene: bounding_volume_hierarchy.cpp:5-9,80-99) ----
+ * pos / nrm: 9 floats per triangle (3 corners x xyz) in the reference's global triangle order (meshes in
+ * Scene::meshes order, triangles in Mesh::triangles order); mesh_id[i] indexes `mats`. */
+int rt_upload_scene(rt_ctx* ctx, const float* pos, const float* nrm, const int* mesh_id, int64_t n_tris,
+    const rt_material* mats, int n_mats);
+int rt_build_bvh(rt_ctx* ctx, int mode);
+/* Lights and materials are read live from the Scene every frame in the reference (src/shadow.cpp:111,141;
+ * src/ray_tracing.h:23-27): re-upload them before a render when they changed. */
+int rt_set_materials(rt_ctx* ctx, const rt_material* mats, int n_mats);
+int rt_set_lights(rt_ctx* ctx, const rt_point_light* point, int n_point, const rt_sphere_light* sphere, int n_sphere);
+
+/* Number of 32-byte nodes and depth of the BVH built last. */
+int rt_bvh_info(rt_ctx* ctx, int* n_nodes, int* depth);
+/* Instrumented kernels: fill rt_stats.node_visits / tri_tests / tri_tests_full (slower; off by default). */
+int rt_set_counters(rt_ctx* ctx, int enable);
+/* Upper bound on primary rays per wavefront batch (default 2^24): ray-state memory is O(batch), not O(W*H*spp). */
+int rt_set_batch_rays(rt_ctx* ctx, unsigned int max_primary_rays_per_batch);
+
+/* ---- image sharding across GPUs (one context per rank; scene replicated) ----
+ * The image is cut into 32x16-pixel tiles; this context renders tiles with tile_id % world == rank. */
+int rt_set_shard(rt_ctx* ctx, int rank, int world);
+
+/* ---- render (replaces renderRayTracing, src/main.cpp:340-400, and Screen::setPixel, src/screen.cpp:32-38) ----
+ * rt_render: host buffers in, host buffers out, synchronous.  rgb_out: width*height*3 floats in the Screen
+ * layout (row H-1-y, column x).  tri_id_out / t_out (nullable): closest-hit triangle id (global index, -1 =
+ * miss) and t of the first primary ray of each pixel, same layout. */
+int rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, float* rgb_out, int* tri_id_out,
+    float* t_out, rt_stats* stats);
+/* rt_render_device: same frame, result left in device memory, asynchronous on the context's stream.
+ * d_rgba: device pointer to width*height float4 (Screen layout); it may be a peer-mapped pointer to another
+ * GPU's framebuffer (tiles of this rank are stored straight into it — the gather fused into the resolve
+ * kernel).  NULL selects the context's own framebuffer.  stats (nullable) is filled by rt_sync. */
+int rt_render_device(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, void* d_rgba);
+int rt_sync(rt_ctx* ctx, rt_stats* stats);
+/* Device framebuffer of this context (width*height float4 of the last rt_render_device with d_rgba=NULL). */
+int rt_framebuffer(rt_ctx* ctx, void** d_rgba, int* width, int* height);
+/* CUDA IPC handle (64 bytes) of this context's framebuffer, sized for width x height, so that other ranks can
+ * map it with rt_open_peer_framebuffer and pass the mapped pointer to rt_render_device. */
+int rt_framebuffer_ipc_handle(rt_ctx* ctx, int width, int height, void* handle64);
+int rt_open_peer_framebuffer(rt_ctx* ctx, const void* handle64, void** d_rgba);
+int rt_close_peer_framebuffer(rt_ctx* ctx, void* d_rgba);
+/* Copy a device float4 framebuffer to a host float3 image (Screen::m_textureData layout). */
+int rt_download_rgb(rt_ctx* ctx, const void* d_rgba, int width, int height, float* rgb_out);
+
+/* ---- closest hit for caller-supplied rays (replaces BoundingVolumeHierarchy::intersect(Ray&, HitInfo&,
+ *      bool useBVH), bounding_volume_hierarchy.cpp:49-78) ----
+ * rays: 6 floats each (origin, direction).  tri_id: global triangle index or -1; t: ray.t or FLT_MAX. */
+int rt_intersect(rt_ctx* ctx, const float* rays, int64_t n_rays, int use_bvh, int* tri_id, float* t);
+
+/* ---- OBJ/MTL loading (replaces loadMesh, src/mesh.cpp:58-188; host-only, no GPU needed) ---- */
+typedef struct rt_mesh_soup rt_mesh_soup;
+int rt_load_obj(const char* path, int center_and_normalize, rt_mesh_soup** out);
+int64_t rt_soup_num_triangles(const rt_mesh_soup* s);
+int rt_soup_num_meshes(const rt_mesh_soup* s);
+const float* rt_soup_positions(const rt_mesh_soup* s); /* 9 floats per triangle */
+const float* rt_soup_normals(const rt_mesh_soup* s);   /* 9 floats per triangle */
+const int* rt_soup_mesh_ids(const rt_mesh_soup* s);
+const rt_material* rt_soup_materials(const rt_mesh_soup* s);
+void rt_soup_free(rt_mesh_soup* s);
+
+const char* rt_last_error(void);
+const char* rt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_B200_H */

@@ -1,0 +1,107 @@
+"""TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+
+ctypes loader for the two CPU checkers declared in oracle_api.h:
+  kind "reference": oracle/_ref/libref_oracle.so (reference translation units compiled verbatim + restated harness)
+  kind "port"     : oracle/liboracle_port.so     (plain C++ restatement of the whole path)
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PATHS = {"reference": os.path.join(_HERE, "_ref", "libref_oracle.so"), "port": os.path.join(_HERE, "liboracle_port.so")}
+
+
+class OrcMaterial(C.Structure):
+    _fields_ = [("kd", C.c_float * 3), ("ks", C.c_float * 3), ("shininess", C.c_float), ("transparency", C.c_float)]
+
+
+class OrcCamera(C.Structure):
+    _fields_ = [("look_at", C.c_float * 3), ("euler", C.c_float * 3), ("dist", C.c_float), ("fovy", C.c_float)]
+
+
+class OrcParams(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("max_reflection_level", C.c_int), ("sphere_light_ray_count", C.c_int),
+                ("glossy_ray_count", C.c_int), ("refraction_factor", C.c_float), ("use_bvh", C.c_int), ("sample_mode", C.c_int),
+                ("sample_size", C.c_int), ("defined_bary", C.c_int), ("x0", C.c_int), ("y0", C.c_int), ("x_step", C.c_int),
+                ("y_step", C.c_int), ("num_threads", C.c_int)]
+
+
+class OrcStats(C.Structure):
+    _fields_ = [("primary_rays", C.c_uint64), ("shadow_queries", C.c_uint64), ("secondary_rays", C.c_uint64), ("seconds", C.c_double),
+                ("threads", C.c_int)]
+
+    @property
+    def rays(self) -> int:
+        return int(self.primary_rays + self.shadow_queries + self.secondary_rays)
+
+
+MATERIAL_DTYPE = np.dtype([("kd", np.float32, 3), ("ks", np.float32, 3), ("shininess", np.float32), ("transparency", np.float32)])
+
+
+def available(kind: str) -> bool:
+    return os.path.exists(PATHS[kind])
+
+
+class Oracle:
+    def __init__(self, kind: str = "port"):
+        path = PATHS[kind]
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} not built: run `make -C oracle`")
+        self.kind = kind
+        self.lib = C.CDLL(path)
+        self.lib.oracle_render.restype = C.c_int
+        self.lib.oracle_closest_hit.restype = C.c_int
+        self.lib.oracle_kind.restype = C.c_char_p
+        assert self.lib.oracle_kind().decode() == kind
+
+    def render(self, pos, nrm, mesh_id, mats, point_lights, sphere_lights, cam, width, height, max_level=5, sphere_rays=10,
+               refraction=0.8, use_bvh=True, sample_mode=0, sample_size=4, defined_bary=True, want_ids=True, want_rgb=True,
+               x0=0, y0=0, x_step=1, y_step=1, num_threads=0):
+        """cam: dict(look_at, euler (radians), dist, fovy (radians)) or an object with those attributes."""
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 9)
+        nrm = np.ascontiguousarray(nrm, np.float32).reshape(-1, 9)
+        mesh_id = np.ascontiguousarray(mesh_id, np.int32)
+        mats = np.ascontiguousarray(mats, MATERIAL_DTYPE)
+        pl = np.ascontiguousarray(point_lights if point_lights is not None else np.zeros((0, 6)), np.float32).reshape(-1, 6)
+        sl = np.ascontiguousarray(sphere_lights if sphere_lights is not None else np.zeros((0, 7)), np.float32).reshape(-1, 7)
+        oc = OrcCamera()
+        get = (lambda k: cam[k]) if isinstance(cam, dict) else (lambda k: getattr(cam, k))
+        oc.look_at[:] = [float(v) for v in get("look_at")]
+        oc.euler[:] = [float(v) for v in get("euler")]
+        oc.dist = float(get("dist"))
+        oc.fovy = float(get("fovy"))
+        p = OrcParams(width, height, max_level, sphere_rays, 1, refraction, 1 if use_bvh else 0, sample_mode, sample_size,
+                      1 if defined_bary else 0, x0, y0, x_step, y_step, num_threads)
+        rgb = np.zeros((height, width, 3), np.float32) if want_rgb else None
+        ids = np.full((height, width), -1, np.int32) if want_ids else None
+        t = np.zeros((height, width), np.float32) if want_ids else None
+        st = OrcStats()
+        rc = self.lib.oracle_render(C.c_void_p(pos.ctypes.data), C.c_void_p(nrm.ctypes.data), C.c_void_p(mesh_id.ctypes.data), C.c_int(pos.shape[0]),
+                                    C.c_void_p(mats.ctypes.data), C.c_int(mats.shape[0]),
+                                    C.c_void_p(pl.ctypes.data if len(pl) else None), C.c_int(len(pl)),
+                                    C.c_void_p(sl.ctypes.data if len(sl) else None), C.c_int(len(sl)),
+                                    C.byref(oc), C.byref(p),
+                                    C.c_void_p(rgb.ctypes.data if want_rgb else None), C.c_void_p(ids.ctypes.data if want_ids else None),
+                                    C.c_void_p(t.ctypes.data if want_ids else None), C.byref(st))
+        if rc != 0:
+            raise RuntimeError(f"oracle_render failed with {rc}")
+        return rgb, ids, t, st
+
+    def closest_hit(self, pos, nrm, mesh_id, rays, use_bvh=False):
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 9)
+        nrm = np.ascontiguousarray(nrm, np.float32).reshape(-1, 9)
+        mesh_id = np.ascontiguousarray(mesh_id, np.int32)
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        ids = np.empty(rays.shape[0], np.int32)
+        t = np.empty(rays.shape[0], np.float32)
+        rc = self.lib.oracle_closest_hit(C.c_void_p(pos.ctypes.data), C.c_void_p(nrm.ctypes.data), C.c_void_p(mesh_id.ctypes.data), C.c_int(pos.shape[0]),
+                                         C.c_void_p(rays.ctypes.data), C.c_int(rays.shape[0]), C.c_int(1 if use_bvh else 0),
+                                         C.c_void_p(ids.ctypes.data), C.c_void_p(t.ctypes.data))
+        if rc != 0:
+            raise RuntimeError(f"oracle_closest_hit failed with {rc}")
+        return ids, t

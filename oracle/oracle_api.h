@@ -1,0 +1,76 @@
+/* TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+ *
+ * Common C interface of the two CPU checkers for the per-pixel ray-tracing hot path:
+ *   - oracle/_ref/libref_oracle.so : the reference's own translation units (ray_tracing.cpp,
+ *     bounding_volume_hierarchy.cpp, shadow.cpp) compiled verbatim from /root/reference, plus a
+ *     harness restating the pieces that live next to GL/ImGui code (src/main.cpp:112-121,129-301,
+ *     309-335,340-400; framework/src/trackball.cpp:65-68,87-98).           kind = "reference"
+ *   - oracle/liboracle_port.so     : a plain C++ restatement of the whole path.   kind = "port"
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load these libraries.  The product (raytracer-group27_b200/) never does.
+ */
+#ifndef ORACLE_API_H
+#define ORACLE_API_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+    float kd[3];
+    float ks[3];
+    float shininess;
+    float transparency;
+} orc_material; /* src/mesh.h:21-31 without the texture */
+
+typedef struct {
+    float look_at[3];
+    float euler[3]; /* radians, Trackball::m_rotationEulerAngles */
+    float dist;
+    float fovy; /* radians */
+} orc_camera; /* framework/include/trackball.h:44-52 */
+
+typedef struct {
+    int width, height;          /* windowResolution (src/main.cpp:33), parameterised            */
+    int max_reflection_level;   /* src/main.cpp:123                                             */
+    int sphere_light_ray_count; /* src/main.cpp:124                                             */
+    int glossy_ray_count;       /* src/main.cpp:126; must be 1 (rand() path is out of scope)    */
+    float refraction_factor;    /* src/main.cpp:127                                             */
+    int use_bvh;                /* global useBVH (src/main.cpp:60) for primary/secondary rays   */
+    int sample_mode;            /* 0: 1 ray/pixel, 1: anti_aliasing 4-tap, 2: multipleRays      */
+    int sample_size;            /* 4 / 16 / 64 for sample_mode 2                                */
+    int defined_bary;           /* 1: define the uninitialised-barycentric case (port only)     */
+    int x0, y0, x_step, y_step; /* render only pixels x0+i*x_step, y0+j*y_step (timing subsets) */
+    int num_threads;            /* OpenMP threads, <=0: all                                     */
+} orc_params;
+
+typedef struct {
+    uint64_t primary_rays;
+    uint64_t shadow_queries;   /* one per iteration of the cansee loop (src/shadow.cpp:41-66)  */
+    uint64_t secondary_rays;   /* reflection + refraction rays                                 */
+    double seconds;            /* wall time of the pixel loop                                  */
+    int threads;
+} orc_stats;
+
+/* Geometry is a triangle soup: pos / nrm hold 9 floats per triangle (3 corners x xyz) in global
+ * triangle order; mesh_id[i] is the index of the owning mesh (non-decreasing); mats[mesh_id].
+ * point_lights: 6 floats each (position, colour); sphere_lights: 7 floats (position, radius, colour).
+ * Outputs may be NULL.  rgb uses the Screen layout (src/screen.cpp:32-38): row (H-1-y), column x.
+ * tri_id / t_hit / use the same layout; tri_id = -1 and t = FLT_MAX on a miss. */
+int oracle_render(const float* pos, const float* nrm, const int* mesh_id, int n_tris,
+    const orc_material* mats, int n_mats,
+    const float* point_lights, int n_point, const float* sphere_lights, int n_sphere,
+    const orc_camera* cam, const orc_params* prm,
+    float* rgb, int* tri_id, float* t_hit, orc_stats* stats);
+
+/* Closest hit for caller-supplied rays (6 floats each: origin, direction), exhaustive (use_bvh=0,
+ * reference brute-force order) or through the reference-style BVH (use_bvh=1). */
+int oracle_closest_hit(const float* pos, const float* nrm, const int* mesh_id, int n_tris,
+    const float* rays, int n_rays, int use_bvh, int* tri_id, float* t_hit);
+
+const char* oracle_kind(void); /* "reference" or "port" */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

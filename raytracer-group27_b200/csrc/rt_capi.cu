@@ -1,0 +1,878 @@
+// extern "C" layer of the B200 ray-tracing path (include/rt_b200.h): context, device memory, frame orchestration.
+#include "rt_b200.h"
+#include "rt_kernels.h"
+
+#include "../host/mesh.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace rtb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return fail(RT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));                    \
+    } while (0)
+
+template <typename T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count)
+    {
+        if (count <= n)
+            return cudaSuccess;
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        n = 0;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e == cudaSuccess)
+            n = count;
+        return e;
+    }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+} // namespace
+
+struct rt_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    // scene
+    long long n_tris = 0;
+    int n_mats = 0;
+    std::vector<float> h_pos;
+    float coord_max = 1.0f;
+    DevBuf<float> d_pos, d_nrm;
+    DevBuf<int> d_mesh, d_perm;
+    DevBuf<float4> d_plane, d_v0, d_v1, d_v2, d_n0, d_n1, d_n2, d_nodes, d_mats, d_point, d_sphere;
+    float4* lbvh_nodes = nullptr; // owned when the device builder allocated them
+    int* lbvh_perm = nullptr;
+    const float4* nodes = nullptr;
+    int n_nodes = 0, root_entry = 0, bvh_depth = 0;
+    bool bvh_built = false;
+    int n_point = 0, n_sphere = 0;
+    bool any_transparent = false;
+
+    // sharding
+    int rank = 0, world = 1;
+
+    // frame state
+    bool counters_enabled = false;
+    unsigned batch_rays = 1u << 24;
+    DevBuf<float4> q_o[2], q_d[2], q_w[2], sp_p, sp_a, sp_b, ss_p, ss_a, ss_b, accum, fb;
+    DevBuf<int2> q_hit[2];
+    DevBuf<Counters> counters;
+    DevBuf<int> prim_id, out_id;
+    DevBuf<float> prim_t, out_t, rgb;
+    DevBuf<float> rays_in;
+    DevBuf<unsigned> flag;
+    Counters* h_counters = nullptr; // pinned
+    int fb_w = 0, fb_h = 0;
+    int last_launches = 0, last_batches = 0;
+    bool frame_pending = false;
+
+    SceneDev scene_dev() const
+    {
+        SceneDev s;
+        s.nodes = nodes;
+        s.tri_plane = d_plane.p;
+        s.tri_v0 = d_v0.p;
+        s.tri_v1 = d_v1.p;
+        s.tri_v2 = d_v2.p;
+        s.tri_n0 = d_n0.p;
+        s.tri_n1 = d_n1.p;
+        s.tri_n2 = d_n2.p;
+        s.mats = d_mats.p;
+        s.point_lights = d_point.p;
+        s.sphere_lights = d_sphere.p;
+        s.n_tris = (int)n_tris;
+        s.n_nodes = n_nodes;
+        return s;
+    }
+};
+
+namespace {
+
+int use_device(rt_ctx* ctx)
+{
+    if (!ctx)
+        return fail(RT_ERR_INVALID, "null context");
+    CK(cudaSetDevice(ctx->device));
+    return RT_OK;
+}
+
+int upload_materials(rt_ctx* ctx, const rt_material* mats, int n_mats)
+{
+    if (!mats || n_mats <= 0)
+        return fail(RT_ERR_INVALID, "materials: need at least one");
+    std::vector<float4> h(2 * (size_t)n_mats);
+    bool any_t = false;
+    for (int i = 0; i < n_mats; i++) {
+        h[2 * i] = make_float4(mats[i].kd[0], mats[i].kd[1], mats[i].kd[2], mats[i].shininess);
+        h[2 * i + 1] = make_float4(mats[i].ks[0], mats[i].ks[1], mats[i].ks[2], mats[i].transparency);
+        any_t |= mats[i].transparency != 1.0f;
+    }
+    CK(ctx->d_mats.ensure(h.size()));
+    CK(cudaMemcpyAsync(ctx->d_mats.p, h.data(), h.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream)); // h is a stack-lifetime staging vector
+    ctx->n_mats = n_mats;
+    ctx->any_transparent = any_t;
+    return RT_OK;
+}
+
+// Host-side pieces of the camera and sampling set-up; they use libm exactly where the reference does.
+int make_frame_params(const rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, FrameParams& fp)
+{
+    if (!cam || !prm)
+        return fail(RT_ERR_INVALID, "null camera / params");
+    if (prm->width <= 0 || prm->height <= 0)
+        return fail(RT_ERR_INVALID, "resolution must be positive");
+    if (prm->glossy_ray_count != 1)
+        return fail(RT_ERR_INVALID, "glossy_ray_count must be 1 (the reference's rand() glossy rays are outside the rebuilt path)");
+    if (prm->max_reflection_level < 0 || prm->max_reflection_level > 64)
+        return fail(RT_ERR_INVALID, "max_reflection_level out of range");
+    std::memset(&fp, 0, sizeof(fp));
+    fp.W = prm->width;
+    fp.H = prm->height;
+    fp.sample_mode = prm->sample_mode;
+    fp.sample_size = prm->sample_size;
+    fp.spp = 1;
+    fp.sample_scale = 1.0f;
+    if (prm->sample_mode == 1) { // main.cpp:358-375
+        fp.spp = 4;
+        fp.aa_off_x = 1.0f / fp.W * 0.25f;
+        fp.aa_off_y = 1.0f / fp.H * 0.25f;
+        fp.sample_scale = 0.25f;
+    } else if (prm->sample_mode == 2) { // main.cpp:309-335, 377-385
+        if (prm->sample_size < 4)
+            return fail(RT_ERR_INVALID, "sample_size must be >= 4 for multipleRays");
+        const double root = std::sqrt((double)prm->sample_size);
+        fp.ms_off_x = (float)((1.0f / fp.W) * (1.0f / (root * 2)));
+        fp.ms_off_y = (float)((1.0f / fp.H) * (1.0f / (root * 2)));
+        fp.ms_moves = (int)(root - 1);
+        const int k = (fp.ms_moves + 1) / 2;
+        fp.spp = 4 * k * k;
+        fp.sample_scale = (float)(1.0f / prm->sample_size);
+    } else if (prm->sample_mode != 0) {
+        return fail(RT_ERR_INVALID, "sample_mode must be 0, 1 or 2");
+    }
+    // glm::quat(eulerAngles) and Trackball::position() (trackball.cpp:65-68), generateRay's half extents (89-90)
+    const float ex = cam->euler[0] * 0.5f, ey = cam->euler[1] * 0.5f, ez = cam->euler[2] * 0.5f;
+    const float cx = std::cos(ex), cy = std::cos(ey), cz = std::cos(ez);
+    const float sx = std::sin(ex), sy = std::sin(ey), sz = std::sin(ez);
+    fp.qw = cx * cy * cz + sx * sy * sz;
+    fp.qx = sx * cy * cz - cx * sy * sz;
+    fp.qy = cx * sy * cz + sx * cy * sz;
+    fp.qz = cx * cy * sz - sx * sy * cz;
+    {
+        // q * (0, 0, -dist): uv = cross(qv, v), uuv = cross(qv, uv), v + ((uv*w) + uuv) * 2
+        const float vx = 0.0f, vy = 0.0f, vz = -cam->dist;
+        const float uvx = fp.qy * vz - vy * fp.qz, uvy = fp.qz * vx - vz * fp.qx, uvz = fp.qx * vy - vx * fp.qy;
+        const float uux = fp.qy * uvz - uvy * fp.qz, uuy = fp.qz * uvx - uvz * fp.qx, uuz = fp.qx * uvy - uvx * fp.qy;
+        fp.ox = cam->look_at[0] + (vx + ((uvx * fp.qw) + uux) * 2.0f);
+        fp.oy = cam->look_at[1] + (vy + ((uvy * fp.qw) + uuy) * 2.0f);
+        fp.oz = cam->look_at[2] + (vz + ((uvz * fp.qw) + uuz) * 2.0f);
+    }
+    fp.halfH = std::tan(cam->fovy / 2.0f);
+    fp.halfW = (float(fp.W) / float(fp.H)) * fp.halfH;
+    fp.tiles_x = (fp.W + kTileW - 1) / kTileW;
+    fp.tiles_y = (fp.H + kTileH - 1) / kTileH;
+    fp.rank = ctx->rank;
+    fp.world = ctx->world;
+    const long long total_tiles = (long long)fp.tiles_x * fp.tiles_y;
+    fp.n_local_tiles = total_tiles > ctx->rank ? (int)((total_tiles - ctx->rank + ctx->world - 1) / ctx->world) : 0;
+    fp.max_level = prm->max_reflection_level;
+    fp.refraction = prm->refraction_factor;
+    fp.n_point = ctx->n_point;
+    fp.n_sphere = ctx->n_sphere;
+    fp.any_transparent = ctx->any_transparent ? 1 : 0;
+    fp.exhaustive = prm->exhaustive ? 1 : 0;
+    // getSpherelights ring layout (shadow.cpp:190-196)
+    int rc = prm->sphere_light_ray_count;
+    if (ctx->n_sphere > 0 && rc < 1)
+        return fail(RT_ERR_INVALID, "sphere_light_ray_count must be >= 1");
+    if (rc < 1)
+        rc = 1;
+    const int m = std::max(1, (int)(rc / std::round(std::sqrt(2 * 3.14159365358979f * rc))));
+    const int n = (rc - 1) / m;
+    fp.sl_m = m;
+    fp.sl_n = n;
+    fp.sl_rc = m * n + 1;
+    if (n > 0) {
+        const float angle = 2 * 3.14159365358979f / n;
+        fp.sl_sin = std::sin(angle);
+        fp.sl_omc = 1 - std::cos(angle);
+    }
+    int g = 1;
+    while (g < fp.sl_rc && g < 32)
+        g <<= 1;
+    fp.sl_group = g;
+    return RT_OK;
+}
+
+int ensure_batch(rt_ctx* ctx, const FrameParams& fp, unsigned batch_pixels, bool want_ids, BatchDev& b)
+{
+    const size_t prim = (size_t)batch_pixels * fp.spp;
+    const size_t cap = prim * (ctx->any_transparent ? 2 : 1);
+    for (int k = 0; k < 2; k++) {
+        CK(ctx->q_o[k].ensure(cap));
+        CK(ctx->q_d[k].ensure(cap));
+        CK(ctx->q_w[k].ensure(cap));
+        CK(ctx->q_hit[k].ensure(cap));
+        b.q[k].o_pix = ctx->q_o[k].p;
+        b.q[k].d = ctx->q_d[k].p;
+        b.q[k].w = ctx->q_w[k].p;
+        b.q[k].hit = ctx->q_hit[k].p;
+    }
+    const size_t cap_pt = cap * (size_t)std::max(1, fp.n_point), cap_sp = cap * (size_t)std::max(1, fp.n_sphere);
+    if (fp.n_point > 0) {
+        CK(ctx->sp_p.ensure(cap_pt));
+        CK(ctx->sp_a.ensure(cap_pt));
+        CK(ctx->sp_b.ensure(cap_pt));
+    }
+    if (fp.n_sphere > 0) {
+        CK(ctx->ss_p.ensure(cap_sp));
+        CK(ctx->ss_a.ensure(cap_sp));
+        CK(ctx->ss_b.ensure(cap_sp));
+    }
+    b.sq_point = ShadowQueue { ctx->sp_p.p, ctx->sp_a.p, ctx->sp_b.p };
+    b.sq_sphere = ShadowQueue { ctx->ss_p.p, ctx->ss_a.p, ctx->ss_b.p };
+    b.ray_capacity = (unsigned)std::min<size_t>(cap, 0xfffffff0u);
+    b.shadow_pt_capacity = (unsigned)std::min<size_t>(cap_pt, 0xfffffff0u);
+    b.shadow_sp_capacity = (unsigned)std::min<size_t>(cap_sp, 0xfffffff0u);
+    CK(ctx->counters.ensure(1));
+    b.counters = ctx->counters.p;
+    const size_t n_local = (size_t)fp.n_local_tiles * kTilePixels;
+    CK(ctx->accum.ensure(std::max<size_t>(n_local, 1)));
+    b.accum = ctx->accum.p;
+    b.prim_id = nullptr;
+    b.prim_t = nullptr;
+    if (want_ids) {
+        CK(ctx->prim_id.ensure(std::max<size_t>(n_local, 1)));
+        CK(ctx->prim_t.ensure(std::max<size_t>(n_local, 1)));
+        b.prim_id = ctx->prim_id.p;
+        b.prim_t = ctx->prim_t.p;
+    }
+    return RT_OK;
+}
+
+// Enqueue one frame on the context's stream.  `out`: float4 framebuffer (Screen layout), maybe on a peer GPU.
+int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids, unsigned batch_rays)
+{
+    const size_t n_local = (size_t)fp.n_local_tiles * kTilePixels;
+    unsigned batch_pixels = (unsigned)std::max<size_t>(kTilePixels, (batch_rays / (unsigned)fp.spp) / kTilePixels * (size_t)kTilePixels);
+    if ((size_t)batch_pixels > n_local)
+        batch_pixels = (unsigned)std::max<size_t>(n_local, kTilePixels);
+    BatchDev b;
+    int rc = ensure_batch(ctx, fp, batch_pixels, want_ids, b);
+    if (rc != RT_OK)
+        return rc;
+    const SceneDev s = ctx->scene_dev();
+    cudaStream_t st = ctx->stream;
+    int launches = 0, batches = 0;
+    CK(cudaEventRecord(ctx->ev0, st));
+    CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(Counters), st));
+    if (n_local)
+        CK(cudaMemsetAsync(ctx->accum.p, 0, n_local * sizeof(float4), st));
+    for (size_t first = 0; first < n_local; first += batch_pixels) {
+        const unsigned n_lp = (unsigned)std::min<size_t>(batch_pixels, n_local - first);
+        launch_level_reset(st, b.counters, 0, 1);
+        launch_generate(st, ctx->sm_count, fp, b, (unsigned)first, n_lp, 0);
+        launches += 2;
+        for (int level = 0; level <= fp.max_level; level++) {
+            const int qi = level & 1;
+            launch_level_reset(st, b.counters, qi ^ 1, 0);
+            launch_extend(st, ctx->sm_count, s, ctx->root_entry, fp, b, qi, level, ctx->counters_enabled);
+            launch_shade(st, ctx->sm_count, s, fp, b, qi, level);
+            launches += 3;
+            if (fp.n_point > 0) {
+                launch_shadow_point(st, ctx->sm_count, s, ctx->root_entry, fp, b, ctx->counters_enabled);
+                launches++;
+            }
+            if (fp.n_sphere > 0) {
+                launch_shadow_sphere(st, ctx->sm_count, s, ctx->root_entry, fp, b, ctx->counters_enabled);
+                launches++;
+            }
+        }
+        batches++;
+    }
+    if (n_local) {
+        launch_resolve(st, ctx->sm_count, fp, ctx->accum.p, b.prim_id, b.prim_t, out, want_ids ? ctx->out_id.p : nullptr,
+            want_ids ? ctx->out_t.p : nullptr);
+        launches++;
+    }
+    CK(cudaEventRecord(ctx->ev1, st));
+    CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CK(cudaGetLastError());
+    ctx->last_launches = launches;
+    ctx->last_batches = batches;
+    ctx->frame_pending = true;
+    return RT_OK;
+}
+
+int check_ready(rt_ctx* ctx)
+{
+    if (ctx->n_tris <= 0)
+        return fail(RT_ERR_INVALID, "no scene uploaded (rt_upload_scene)");
+    if (!ctx->bvh_built)
+        return fail(RT_ERR_INVALID, "BVH not built (rt_build_bvh)");
+    if (ctx->n_mats <= 0)
+        return fail(RT_ERR_INVALID, "no materials");
+    return RT_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* rt_last_error(void) { return g_err.c_str(); }
+const char* rt_version(void) { return "rt_b200 0.1 (sm_100a)"; }
+
+int rt_create(int device, rt_ctx** out)
+{
+    if (!out)
+        return fail(RT_ERR_INVALID, "rt_create: null out");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(RT_ERR_CUDA, std::string("rt_create: no CUDA device available (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+    if (device < 0 || device >= count)
+        return fail(RT_ERR_INVALID, "rt_create: device ordinal out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(RT_ERR_CUDA, std::string("rt_create: kernels are built for sm_100a only, found ") + prop.name);
+    rt_ctx* ctx = new rt_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess
+        || cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess
+        || cudaMallocHost(&ctx->h_counters, sizeof(Counters)) != cudaSuccess) {
+        delete ctx;
+        return fail(RT_ERR_CUDA, "rt_create: stream / event / pinned allocation failed");
+    }
+    ctx->own_stream = true;
+    std::memset(ctx->h_counters, 0, sizeof(Counters));
+    *out = ctx;
+    return RT_OK;
+}
+
+int rt_destroy(rt_ctx* ctx)
+{
+    if (!ctx)
+        return RT_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    DevBuf<float4>* f4[] = { &ctx->d_plane, &ctx->d_v0, &ctx->d_v1, &ctx->d_v2, &ctx->d_n0, &ctx->d_n1, &ctx->d_n2, &ctx->d_nodes, &ctx->d_mats,
+        &ctx->d_point, &ctx->d_sphere, &ctx->q_o[0], &ctx->q_o[1], &ctx->q_d[0], &ctx->q_d[1], &ctx->q_w[0], &ctx->q_w[1], &ctx->sp_p, &ctx->sp_a,
+        &ctx->sp_b, &ctx->ss_p, &ctx->ss_a, &ctx->ss_b, &ctx->accum, &ctx->fb };
+    for (auto* b : f4)
+        b->release();
+    ctx->d_pos.release();
+    ctx->d_nrm.release();
+    ctx->d_mesh.release();
+    ctx->d_perm.release();
+    ctx->q_hit[0].release();
+    ctx->q_hit[1].release();
+    ctx->counters.release();
+    ctx->prim_id.release();
+    ctx->out_id.release();
+    ctx->prim_t.release();
+    ctx->out_t.release();
+    ctx->rgb.release();
+    ctx->rays_in.release();
+    ctx->flag.release();
+    if (ctx->lbvh_nodes)
+        cudaFree(ctx->lbvh_nodes);
+    if (ctx->lbvh_perm)
+        cudaFree(ctx->lbvh_perm);
+    if (ctx->h_counters)
+        cudaFreeHost(ctx->h_counters);
+    if (ctx->ev0)
+        cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1)
+        cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream && ctx->stream)
+        cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return RT_OK;
+}
+
+int rt_set_stream(rt_ctx* ctx, void* cuda_stream)
+{
+    int rc = use_device(ctx);
+    if (rc)
+        return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream)
+        cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return RT_OK;
+}
+
+int rt_set_counters(rt_ctx* ctx, int enable)
+{
+    if (!ctx)
+        return fail(RT_ERR_INVALID, "null context");
+    ctx->counters_enabled = enable != 0;
+    return RT_OK;
+}
+
+int rt_set_batch_rays(rt_ctx* ctx, unsigned int max_primary_rays_per_batch)
+{
+    if (!ctx || max_primary_rays_per_batch < (unsigned)kTilePixels)
+        return fail(RT_ERR_INVALID, "batch size must be at least one tile");
+    ctx->batch_rays = max_primary_rays_per_batch;
+    return RT_OK;
+}
+
+int rt_upload_scene(rt_ctx* ctx, const float* pos, const float* nrm, const int* mesh_id, int64_t n_tris, const rt_material* mats, int n_mats)
+{
+    int rc = use_device(ctx);
+    if (rc)
+        return rc;
+    if (!pos || !nrm || n_tris <= 0)
+        return fail(RT_ERR_INVALID, "rt_upload_scene: need positions, normals and at least one triangle");
+    if (n_tris > (1ll << 28) - 1)
+        return fail(RT_ERR_INVALID, "rt_upload_scene: at most 2^28-1 triangles");
+    if (mesh_id)
+        for (int64_t i = 0; i < n_tris; i++)
+            if (mesh_id[i] < 0 || mesh_id[i] >= n_mats)
+                return fail(RT_ERR_INVALID, "rt_upload_scene: mesh_id out of range of the material table");
+    rc = upload_materials(ctx, mats, n_mats);
+    if (rc)
+        return rc;
+    ctx->n_tris = n_tris;
+    ctx->h_pos.assign(pos, pos + 9 * n_tris);
+    float cm = 0.0f;
+    for (float v : ctx->h_pos)
+        cm = std::max(cm, std::fabs(v));
+    ctx->coord_max = cm;
+    CK(ctx->d_pos.ensure(9 * (size_t)n_tris));
+    CK(ctx->d_nrm.ensure(9 * (size_t)n_tris));
+    CK(ctx->d_mesh.ensure((size_t)n_tris));
+    CK(cudaMemcpyAsync(ctx->d_pos.p, pos, 9 * (size_t)n_tris * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_nrm.p, nrm, 9 * (size_t)n_tris * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (mesh_id)
+        CK(cudaMemcpyAsync(ctx->d_mesh.p, mesh_id, (size_t)n_tris * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    else
+        CK(cudaMemsetAsync(ctx->d_mesh.p, 0, (size_t)n_tris * sizeof(int), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->bvh_built = false;
+    return RT_OK;
+}
+
+int rt_build_bvh(rt_ctx* ctx, int mode)
+{
+    int rc = use_device(ctx);
+    if (rc)
+        return rc;
+    if (ctx->n_tris <= 0)
+        return fail(RT_ERR_INVALID, "rt_build_bvh: upload a scene first");
+    // Box padding: the reference's triangle test accepts points a few ulp outside the exact triangle (rounded
+    // hit point, rounded edge functions); pad so such a point is still inside every ancestor box.
+    const float pad = 1e-5f * std::max(1.0f, ctx->coord_max);
+    const size_t n = (size_t)ctx->n_tris;
+    CK(ctx->d_plane.ensure(n));
+    CK(ctx->d_v0.ensure(n));
+    CK(ctx->d_v1.ensure(n));
+    CK(ctx->d_v2.ensure(n));
+    CK(ctx->d_n0.ensure(n));
+    CK(ctx->d_n1.ensure(n));
+    CK(ctx->d_n2.ensure(n));
+    const int* perm = nullptr;
+    if (mode == RT_BVH_SAH_HOST) {
+        HostBvh h = build_bvh_sah_host(ctx->h_pos.data(), ctx->n_tris, pad);
+        if (h.depth >= kStackDepth)
+            return fail(RT_ERR_INVALID, "rt_build_bvh: tree deeper than the traversal stack");
+        CK(ctx->d_nodes.ensure(h.nodes.size()));
+        CK(ctx->d_perm.ensure(n));
+        CK(cudaMemcpyAsync(ctx->d_nodes.p, h.nodes.data(), h.nodes.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_perm.p, h.perm.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->nodes = ctx->d_nodes.p;
+        ctx->n_nodes = (int)(h.nodes.size() / 2);
+        ctx->root_entry = h.root_entry;
+        ctx->bvh_depth = h.depth;
+        perm = ctx->d_perm.p;
+    } else if (mode == RT_BVH_LBVH_DEVICE) {
+        if (ctx->lbvh_nodes)
+            cudaFree(ctx->lbvh_nodes);
+        if (ctx->lbvh_perm)
+            cudaFree(ctx->lbvh_perm);
+        ctx->lbvh_nodes = nullptr;
+        ctx->lbvh_perm = nullptr;
+        DeviceBvh d;
+        const char* err = nullptr;
+        if (build_bvh_lbvh_device(ctx->stream, ctx->d_pos.p, ctx->n_tris, pad, &d, &err) != 0)
+            return fail(RT_ERR_CUDA, std::string("rt_build_bvh (LBVH): ") + (err ? err : "failed"));
+        if (d.depth >= kStackDepth) {
+            cudaFree(d.nodes);
+            cudaFree(d.perm);
+            return fail(RT_ERR_INVALID, "rt_build_bvh: LBVH deeper than the traversal stack");
+        }
+        ctx->lbvh_nodes = d.nodes;
+        ctx->lbvh_perm = d.perm;
+        ctx->nodes = d.nodes;
+        ctx->n_nodes = d.n_nodes;
+        ctx->root_entry = d.root_entry;
+        ctx->bvh_depth = d.depth;
+        perm = d.perm;
+    } else {
+        return fail(RT_ERR_INVALID, "rt_build_bvh: unknown mode");
+    }
+    launch_tri_setup(ctx->stream, ctx->d_pos.p, ctx->d_nrm.p, ctx->d_mesh.p, perm, (int)ctx->n_tris, ctx->d_plane.p, ctx->d_v0.p, ctx->d_v1.p,
+        ctx->d_v2.p, ctx->d_n0.p, ctx->d_n1.p, ctx->d_n2.p);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->bvh_built = true;
+    return RT_OK;
+}
+
+int rt_bvh_info(rt_ctx* ctx, int* n_nodes, int* depth)
+{
+    if (!ctx || !ctx->bvh_built)
+        return fail(RT_ERR_INVALID, "rt_bvh_info: no BVH");
+    if (n_nodes)
+        *n_nodes = ctx->n_nodes;
+    if (depth)
+        *depth = ctx->bvh_depth;
+    return RT_OK;
+}
+
+int rt_set_materials(rt_ctx* ctx, const rt_material* mats, int n_mats)
+{
+    int rc = use_device(ctx);
+    if (rc)
+        return rc;
+    if (ctx->n_mats > 0 && n_mats != ctx->n_mats)
+        return fail(RT_ERR_INVALID, "rt_set_materials: material count differs from the uploaded scene");
+    return upload_materials(ctx, mats, n_mats);
+}
+
+int rt_set_lights(rt_ctx* ctx, const rt_point_light* point, int n_point, const rt_sphere_light* sphere, int n_sphere)
+{
+    int rc = use_device(ctx);
+    if (rc)
+        return rc;
+    if (n_point < 0 || n_sphere < 0 || n_point > kMaxPointLights || n_sphere > kMaxSphereLights)
+        return fail(RT_ERR_INVALID, "rt_set_lights: too many lights");
+    if ((n_point > 0 && !point) || (n_sphere > 0 && !sphere))
+        return fail(RT_ERR_INVALID, "rt_set_lights: null array");
+    std::vector<float4> hp(2 * (size_t)std::max(1, n_point)), hs(2 * (size_t)std::max(1, n_sphere));
+    for (int i = 0; i < n_point; i++) {
+        hp[2 * i] = make_float4(point[i].position[0], point[i].position[1], point[i].position[2], 0.0f);
+        hp[2 * i + 1] = make_float4(point[i].color[0], point[i].color[1], point[i].color[2], 0.0f);
+    }
+    for (int i = 0; i < n_sphere; i++) {
+        hs[2 * i] = make_float4(sphere[i].position[0], sphere[i].position[1], sphere[i].position[2], sphere[i].radius);
+        hs[2 * i + 1] = make_float4(sphere[i].color[0], sphere[i].color[1], sphere[i].color[2], 0.0f);
+    }
+    CK(ctx->d_point.ensure(hp.size()));
+    CK(ctx->d_sphere.ensure(hs.size()));
+    CK(cudaMemcpyAsync(ctx->d_point.p, hp.data(), hp.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_sphere.p, hs.data(), hs.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_point = n_point;
+    ctx->n_sphere = n_sphere;
+    return RT_OK;
+}
+
+int rt_set_shard(rt_ctx* ctx, int rank, int world)
+{
+    if (!ctx || world < 1 || rank < 0 || rank >= world)
+        return fail(RT_ERR_INVALID, "rt_set_shard: need 0 <= rank < world");
+    ctx->rank = rank;
+    ctx->world = world;
+    return RT_OK;
+}
+
+int rt_render_device(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, void* d_rgba)
+{
+    int rc = use_device(ctx);
+    if (rc)
+        return rc;
+    rc = check_ready(ctx);
+    if (rc)
+        return rc;
+    FrameParams fp;
+    rc = make_frame_params(ctx, cam, prm, fp);
+    if (rc)
+        return rc;
+    float4* out = (float4*)d_rgba;
+    if (!out) {
+        const size_t npx = (size_t)fp.W * fp.H;
+        if (ctx->fb.n < npx || ctx->fb_w != fp.W || ctx->fb_h != fp.H) {
+            CK(ctx->fb.ensure(npx));
+            CK(cudaMemsetAsync(ctx->fb.p, 0, npx * sizeof(float4), ctx->stream));
+            ctx->fb_w = fp.W;
+            ctx->fb_h = fp.H;
+        }
+        out = ctx->fb.p;
+    }
+    return enqueue_frame(ctx, fp, out, false, ctx->batch_rays);
+}
+
+int rt_sync(rt_ctx* ctx, rt_stats* stats)
+{
+    int rc = use_device(ctx);
+    if (rc)
+        return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->frame_pending) {
+        ctx->frame_pending = false;
+        const Counters& c = *ctx->h_counters;
+        if (c.overflow == 1)
+            return fail(RT_ERR_OVERFLOW, "a ray queue overflowed (transparent materials doubled the wavefront more than provisioned); lower rt_set_batch_rays");
+        if (c.overflow == 2)
+            return fail(RT_ERR_OVERFLOW, "traversal stack overflow");
+        if (stats) {
+            std::memset(stats, 0, sizeof(*stats));
+            stats->primary_rays = c.primary_rays;
+            stats->shadow_queries = c.shadow_queries;
+            stats->secondary_rays = c.secondary_rays;
+            stats->node_visits = c.node_visits;
+            stats->tri_tests = c.tri_tests;
+            stats->tri_tests_full = c.tri_tests_full;
+            float ms = 0.0f;
+            CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+            stats->gpu_ms = ms;
+            stats->kernel_launches = ctx->last_launches;
+            stats->batches = ctx->last_batches;
+        }
+    }
+    return RT_OK;
+}
+
+int rt_framebuffer(rt_ctx* ctx, void** d_rgba, int* width, int* height)
+{
+    if (!ctx || !ctx->fb.p)
+        return fail(RT_ERR_INVALID, "rt_framebuffer: nothing rendered yet");
+    if (d_rgba)
+        *d_rgba = ctx->fb.p;
+    if (width)
+        *width = ctx->fb_w;
+    if (height)
+        *height = ctx->fb_h;
+    return RT_OK;
+}
+
+int rt_framebuffer_ipc_handle(rt_ctx* ctx, int width, int height, void* handle64)
+{
+    int rc = use_device(ctx);
+    if (rc)
+        return rc;
+    if (width <= 0 || height <= 0 || !handle64)
+        return fail(RT_ERR_INVALID, "rt_framebuffer_ipc_handle: bad arguments");
+    const size_t npx = (size_t)width * height;
+    if (ctx->fb.n < npx || ctx->fb_w != width || ctx->fb_h != height) {
+        CK(ctx->fb.ensure(npx));
+        CK(cudaMemsetAsync(ctx->fb.p, 0, npx * sizeof(float4), ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->fb_w = width;
+        ctx->fb_h = height;
+    }
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->fb.p));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(handle64, &h, 64);
+    return RT_OK;
+}
+
+int rt_open_peer_framebuffer(rt_ctx* ctx, const void* handle64, void** d_rgba)
+{
+    int rc = use_device(ctx);
+    if (rc)
+        return rc;
+    if (!handle64 || !d_rgba)
+        return fail(RT_ERR_INVALID, "rt_open_peer_framebuffer: bad arguments");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    CK(cudaIpcOpenMemHandle(d_rgba, h, cudaIpcMemLazyEnablePeerAccess));
+    return RT_OK;
+}
+
+int rt_close_peer_framebuffer(rt_ctx* ctx, void* d_rgba)
+{
+    int rc = use_device(ctx);
+    if (rc)
+        return rc;
+    CK(cudaIpcCloseMemHandle(d_rgba));
+    return RT_OK;
+}
+
+int rt_download_rgb(rt_ctx* ctx, const void* d_rgba, int width, int height, float* rgb_out)
+{
+    int rc = use_device(ctx);
+    if (rc)
+        return rc;
+    if (!d_rgba || !rgb_out || width <= 0 || height <= 0)
+        return fail(RT_ERR_INVALID, "rt_download_rgb: bad arguments");
+    const size_t npx = (size_t)width * height;
+    CK(ctx->rgb.ensure(npx * 3 + 4));
+    launch_pack_rgb(ctx->stream, ctx->sm_count, (const float4*)d_rgba, ctx->rgb.p, npx);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(rgb_out, ctx->rgb.p, npx * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, float* rgb_out, int* tri_id_out, float* t_out, rt_stats* stats)
+{
+    int rc = use_device(ctx);
+    if (rc)
+        return rc;
+    rc = check_ready(ctx);
+    if (rc)
+        return rc;
+    if (!rgb_out)
+        return fail(RT_ERR_INVALID, "rt_render: rgb_out is null");
+    FrameParams fp;
+    rc = make_frame_params(ctx, cam, prm, fp);
+    if (rc)
+        return rc;
+    const size_t npx = (size_t)fp.W * fp.H;
+    const bool want_ids = tri_id_out != nullptr || t_out != nullptr;
+    if (ctx->fb.n < npx || ctx->fb_w != fp.W || ctx->fb_h != fp.H) {
+        CK(ctx->fb.ensure(npx));
+        CK(cudaMemsetAsync(ctx->fb.p, 0, npx * sizeof(float4), ctx->stream));
+        ctx->fb_w = fp.W;
+        ctx->fb_h = fp.H;
+    }
+    if (want_ids) {
+        CK(ctx->out_id.ensure(npx));
+        CK(ctx->out_t.ensure(npx));
+        CK(cudaMemsetAsync(ctx->out_id.p, 0xff, npx * sizeof(int), ctx->stream));
+        CK(cudaMemsetAsync(ctx->out_t.p, 0, npx * sizeof(float), ctx->stream));
+    }
+    CK(ctx->rgb.ensure(npx * 3 + 4));
+    unsigned batch = ctx->batch_rays;
+    for (int attempt = 0;; attempt++) {
+        rc = enqueue_frame(ctx, fp, ctx->fb.p, want_ids, batch);
+        if (rc)
+            return rc;
+        launch_pack_rgb(ctx->stream, ctx->sm_count, ctx->fb.p, ctx->rgb.p, npx);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(rgb_out, ctx->rgb.p, npx * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        if (tri_id_out)
+            CK(cudaMemcpyAsync(tri_id_out, ctx->out_id.p, npx * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        if (t_out)
+            CK(cudaMemcpyAsync(t_out, ctx->out_t.p, npx * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        rc = rt_sync(ctx, stats);
+        // queue overflow from ray splitting: halve the batch (doubling the head-room) and render again
+        if (rc == RT_ERR_OVERFLOW && ctx->h_counters->overflow == 1 && attempt < 3 && batch / 2 >= (unsigned)kTilePixels * (unsigned)fp.spp) {
+            batch /= 2;
+            continue;
+        }
+        if (rc == RT_OK && stats)
+            stats->kernel_launches += 1;
+        return rc;
+    }
+}
+
+int rt_intersect(rt_ctx* ctx, const float* rays, int64_t n_rays, int use_bvh, int* tri_id, float* t)
+{
+    int rc = use_device(ctx);
+    if (rc)
+        return rc;
+    rc = check_ready(ctx);
+    if (rc)
+        return rc;
+    if (n_rays < 0 || (n_rays > 0 && (!rays || !tri_id || !t)))
+        return fail(RT_ERR_INVALID, "rt_intersect: bad arguments");
+    if (n_rays == 0)
+        return RT_OK;
+    CK(ctx->rays_in.ensure(6 * (size_t)n_rays));
+    CK(ctx->out_id.ensure((size_t)n_rays));
+    CK(ctx->out_t.ensure((size_t)n_rays));
+    CK(ctx->flag.ensure(1));
+    CK(cudaMemsetAsync(ctx->flag.p, 0, sizeof(unsigned), ctx->stream));
+    CK(cudaMemcpyAsync(ctx->rays_in.p, rays, 6 * (size_t)n_rays * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    launch_intersect(ctx->stream, ctx->sm_count, ctx->scene_dev(), ctx->root_entry, ctx->rays_in.p, (long long)n_rays, use_bvh, ctx->out_id.p,
+        ctx->out_t.p, ctx->flag.p);
+    CK(cudaGetLastError());
+    unsigned flag = 0;
+    CK(cudaMemcpyAsync(tri_id, ctx->out_id.p, (size_t)n_rays * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(t, ctx->out_t.p, (size_t)n_rays * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&flag, ctx->flag.p, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (flag)
+        return fail(RT_ERR_OVERFLOW, "traversal stack overflow");
+    return RT_OK;
+}
+
+// ---- OBJ loading: host only ----
+struct rt_mesh_soup {
+    std::vector<float> pos, nrm;
+    std::vector<int> mesh_id;
+    std::vector<rt_material> mats;
+};
+
+int rt_load_obj(const char* path, int center_and_normalize, rt_mesh_soup** out)
+{
+    if (!path || !out)
+        return fail(RT_ERR_INVALID, "rt_load_obj: bad arguments");
+    *out = nullptr;
+    try {
+        std::vector<Mesh> meshes = loadMesh(path, center_and_normalize != 0);
+        auto* s = new rt_mesh_soup();
+        int mi = 0;
+        for (const Mesh& mesh : meshes) {
+            for (const Triangle& tri : mesh.triangles) {
+                const Vertex* v[3] = { &mesh.vertices[tri.x], &mesh.vertices[tri.y], &mesh.vertices[tri.z] };
+                for (int k = 0; k < 3; k++) {
+                    s->pos.insert(s->pos.end(), { v[k]->p.x, v[k]->p.y, v[k]->p.z });
+                    s->nrm.insert(s->nrm.end(), { v[k]->n.x, v[k]->n.y, v[k]->n.z });
+                }
+                s->mesh_id.push_back(mi);
+            }
+            const Material& m = mesh.material;
+            s->mats.push_back(rt_material { { m.kd.x, m.kd.y, m.kd.z }, { m.ks.x, m.ks.y, m.ks.z }, m.shininess, m.transparency });
+            mi++;
+        }
+        *out = s;
+        return RT_OK;
+    } catch (const std::exception& e) {
+        return fail(RT_ERR_IO, e.what());
+    }
+}
+
+int64_t rt_soup_num_triangles(const rt_mesh_soup* s) { return s ? (int64_t)s->mesh_id.size() : 0; }
+int rt_soup_num_meshes(const rt_mesh_soup* s) { return s ? (int)s->mats.size() : 0; }
+const float* rt_soup_positions(const rt_mesh_soup* s) { return s ? s->pos.data() : nullptr; }
+const float* rt_soup_normals(const rt_mesh_soup* s) { return s ? s->nrm.data() : nullptr; }
+const int* rt_soup_mesh_ids(const rt_mesh_soup* s) { return s ? s->mesh_id.data() : nullptr; }
+const rt_material* rt_soup_materials(const rt_mesh_soup* s) { return s ? s->mats.data() : nullptr; }
+void rt_soup_free(rt_mesh_soup* s) { delete s; }
+
+} // extern "C"

@@ -1,0 +1,44 @@
+// Launch wrappers of the wavefront kernels (definitions in rt_kernels.cu, rt_lbvh.cu).
+#pragma once
+#include "rt_types.h"
+#include <vector>
+
+namespace rtb {
+
+void launch_tri_setup(cudaStream_t st, const float* pos, const float* nrm, const int* mesh_id, const int* perm, int n,
+    float4* plane, float4* v0, float4* v1, float4* v2, float4* n0, float4* n1, float4* n2);
+void launch_level_reset(cudaStream_t st, Counters* c, int next_q, int clear_current);
+void launch_generate(cudaStream_t st, int sm_count, const FrameParams& fp, const BatchDev& b, unsigned first_lp, unsigned n_lp, int qi);
+void launch_extend(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, int qi,
+    int level, bool count);
+void launch_shade(cudaStream_t st, int sm_count, const SceneDev& s, const FrameParams& fp, const BatchDev& b, int qi, int level);
+void launch_shadow_point(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count);
+void launch_shadow_sphere(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count);
+void launch_resolve(cudaStream_t st, int sm_count, const FrameParams& fp, const float4* accum, const int* prim_id, const float* prim_t,
+    float4* out, int* out_id, float* out_t);
+void launch_pack_rgb(cudaStream_t st, int sm_count, const float4* in, float* out, size_t n_pixels);
+void launch_intersect(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const float* rays, long long n, int use_bvh,
+    int* tri_id, float* t_out, unsigned* overflow);
+
+// Host binned-SAH builder (rt_bvh_host.cpp).  nodes: 2 x float4 per node in the layout of SceneDev::nodes;
+// perm: BVH-order slot -> global triangle id.  Returns the tree depth.
+struct HostBvh {
+    std::vector<float4> nodes;
+    std::vector<int> perm;
+    int root_entry = 0;
+    int depth = 0;
+};
+HostBvh build_bvh_sah_host(const float* pos, long long n_tris, float pad);
+
+// Device LBVH builder (rt_lbvh.cu): Morton codes -> radix sort -> Karras hierarchy -> leaf collapse -> refit.
+// d_pos: device copy of the triangle soup.  Outputs are device buffers allocated by the callee (cudaMalloc).
+struct DeviceBvh {
+    float4* nodes = nullptr;
+    int* perm = nullptr;
+    int n_nodes = 0;
+    int root_entry = 0;
+    int depth = 0;
+};
+int build_bvh_lbvh_device(cudaStream_t st, const float* d_pos, long long n_tris, float pad, DeviceBvh* out, const char** err);
+
+} // namespace rtb

@@ -1,0 +1,162 @@
+// Closest-hit / any-hit traversal of the flattened BVH and the exact triangle test.
+//
+// Replaces BoundingVolumeHierarchy::intersect / intersectBVH / intersectNode / intersectObject
+// (src/bounding_volume_hierarchy.cpp:49-78, 395-448) and intersectRayWithTriangle / trianglePlane /
+// intersectRayWithPlane / pointInTriangle (src/ray_tracing.cpp:42-128).
+//
+// Semantics kept from the reference: a triangle is hit when the plane parameter t (measured along
+// normalize(direction), ray_tracing.cpp:65-71) satisfies 0 <= t < ray.t and the point origin + direction * t
+// (UN-normalised direction, ray_tracing.cpp:111) passes the three edge-sign tests, all >= 0 or all < 0.  The
+// reference's brute-force loop keeps the first strictly smaller t, i.e. the winner is the lexicographic minimum of
+// (t, global triangle id); a traversal in any order reproduces that with the tie rule below.  Box tests only have
+// to be conservative (never cull a triangle the reference would accept): boxes are padded at build time and the
+// slab comparison carries a rounding guard; the reference's own box test is not reproduced (its result never
+// changes which triangle wins).
+#pragma once
+#include "rt_math.cuh"
+#include "rt_types.h"
+#include <cfloat>
+
+namespace rtb {
+
+struct TraceStats {
+    unsigned int nodes = 0, tris = 0, tris_full = 0;
+};
+
+struct HitRec {
+    float t;   // best t so far (search bound on entry)
+    int id;    // global triangle id of the best hit (tie rule operand)
+    int ti;    // BVH-order index of the best hit, -1 = none
+};
+
+// One ray against one triangle.  `o`/`d` as stored in the ray, `dn` = normalize(d).
+template <bool COUNT>
+__device__ __forceinline__ bool test_triangle(const SceneDev& s, int ti, const f3& o, const f3& d, const f3& dn, HitRec& best, TraceStats& st)
+{
+    const float4 pl = __ldg(&s.tri_plane[ti]);
+    const f3 n = mk3(pl);
+    if (COUNT)
+        st.tris++;
+    const float nd = xdot(dn, n);
+    if (nd == 0.0f)
+        return false;
+    const float t = xdiv(xsub(pl.w, xdot(o, n)), nd);
+    if (!(t >= 0.0f) || !(t <= best.t))
+        return false;
+    const float4 a = __ldg(&s.tri_v0[ti]);
+    const int id = __float_as_int(a.w);
+    if (t == best.t && id >= best.id)
+        return false; // equal t: the lower global id wins (first tested in the reference's loop)
+    const float4 b = __ldg(&s.tri_v1[ti]);
+    const float4 c = __ldg(&s.tri_v2[ti]);
+    if (COUNT)
+        st.tris_full++;
+    const f3 v0 = mk3(a), v1 = mk3(b), v2 = mk3(c);
+    const f3 p = xadd(o, xmul(d, t));
+    const bool s0 = xdot(xcross(xsub(p, v0), xsub(v2, v0)), n) >= 0.0f;
+    const bool s1 = xdot(xcross(xsub(p, v2), xsub(v1, v2)), n) >= 0.0f;
+    const bool s2 = xdot(xcross(xsub(p, v1), xsub(v0, v1)), n) >= 0.0f;
+    if ((s0 && s1 && s2) || (!s0 && !s1 && !s2)) {
+        best.t = t;
+        best.id = id;
+        best.ti = ti;
+        return true;
+    }
+    return false;
+}
+
+// Prune bound for box tests derived from the best t: t is measured along normalize(d) while the accepted point
+// uses the un-normalised d (|d| = 1 +- a few ulp), so leave a relative and an absolute margin.
+__device__ __forceinline__ float prune_limit(float best_t) { return best_t * 1.000004f + 1e-5f; }
+
+// Initial HitRec for a fresh closest-hit query: nothing may be accepted at t == FLT_MAX (reference: t < ray.t).
+__device__ __forceinline__ HitRec fresh_query() { return HitRec { FLT_MAX, INT_MIN, -1 }; }
+// Query bounded by an inclusive limit (shadow rays: blockers have t <= distance - 0.001).
+__device__ __forceinline__ HitRec bounded_query(float limit) { return HitRec { limit, INT_MAX, -1 }; }
+
+// Exhaustive search: every triangle (order irrelevant thanks to the tie rule).
+template <bool ANYHIT, bool COUNT>
+__device__ __forceinline__ void trace_exhaustive(const SceneDev& s, const f3& o, const f3& d, HitRec& best, TraceStats& st)
+{
+    const f3 dn = xnormalize(d);
+    for (int ti = 0; ti < s.n_tris; ti++) {
+        if (test_triangle<COUNT>(s, ti, o, d, dn, best, st) && ANYHIT)
+            return;
+    }
+}
+
+// BVH traversal.  Stack entries: >= 0 -> index of a sibling pair to fetch; < 0 -> ~((first << 3) | (count - 1)).
+// Returns false if the traversal stack overflowed (builders keep the depth below kStackDepth).
+template <bool ANYHIT, bool COUNT>
+__device__ __forceinline__ bool trace_bvh(const SceneDev& s, int root_entry, const f3& o, const f3& d, HitRec& best, TraceStats& st)
+{
+    const f3 dn = xnormalize(d);
+    const float ix = 1.0f / dn.x, iy = 1.0f / dn.y, iz = 1.0f / dn.z;
+    float tlimit = prune_limit(best.t);
+    int stack[kStackDepth];
+    int sp = 0;
+    int cur = root_entry;
+    bool ok = true;
+    while (true) {
+        if (cur >= 0) {
+            const float4* np = s.nodes + 2 * (size_t)cur;
+            const float4 a0 = __ldg(np), a1 = __ldg(np + 1), b0 = __ldg(np + 2), b1 = __ldg(np + 3);
+            if (COUNT)
+                st.nodes += 2;
+            // slabs; fminf/fmaxf drop NaNs (0 * inf), which only widens the interval
+            float t0, t1;
+            t0 = (a0.x - o.x) * ix; t1 = (a1.x - o.x) * ix;
+            float amin = fminf(t0, t1), amax = fmaxf(t0, t1);
+            t0 = (a0.y - o.y) * iy; t1 = (a1.y - o.y) * iy;
+            amin = fmaxf(amin, fminf(t0, t1)); amax = fminf(amax, fmaxf(t0, t1));
+            t0 = (a0.z - o.z) * iz; t1 = (a1.z - o.z) * iz;
+            amin = fmaxf(fmaxf(amin, fminf(t0, t1)), 0.0f); amax = fminf(fminf(amax, fmaxf(t0, t1)), tlimit);
+            t0 = (b0.x - o.x) * ix; t1 = (b1.x - o.x) * ix;
+            float bmin = fminf(t0, t1), bmax = fmaxf(t0, t1);
+            t0 = (b0.y - o.y) * iy; t1 = (b1.y - o.y) * iy;
+            bmin = fmaxf(bmin, fminf(t0, t1)); bmax = fminf(bmax, fmaxf(t0, t1));
+            t0 = (b0.z - o.z) * iz; t1 = (b1.z - o.z) * iz;
+            bmin = fmaxf(fmaxf(bmin, fminf(t0, t1)), 0.0f); bmax = fminf(fminf(bmax, fmaxf(t0, t1)), tlimit);
+            const bool hitA = amin <= amax * 1.0000005f;
+            const bool hitB = bmin <= bmax * 1.0000005f;
+            const int ca = __float_as_int(a1.w), cb = __float_as_int(b1.w);
+            const int ea = ca ? ~((__float_as_int(a0.w) << 3) | (ca - 1)) : __float_as_int(a0.w);
+            const int eb = cb ? ~((__float_as_int(b0.w) << 3) | (cb - 1)) : __float_as_int(b0.w);
+            if (hitA && hitB) {
+                const bool aFirst = amin <= bmin;
+                const int nearE = aFirst ? ea : eb, farE = aFirst ? eb : ea;
+                if (sp < kStackDepth)
+                    stack[sp++] = farE;
+                else
+                    ok = false;
+                cur = nearE;
+                continue;
+            }
+            if (hitA) {
+                cur = ea;
+                continue;
+            }
+            if (hitB) {
+                cur = eb;
+                continue;
+            }
+        } else {
+            const int enc = ~cur;
+            const int first = enc >> 3, count = (enc & 7) + 1;
+            bool any = false;
+            for (int i = 0; i < count; i++)
+                any |= test_triangle<COUNT>(s, first + i, o, d, dn, best, st);
+            if (any) {
+                if (ANYHIT)
+                    return ok;
+                tlimit = prune_limit(best.t);
+            }
+        }
+        if (sp == 0)
+            break;
+        cur = stack[--sp];
+    }
+    return ok;
+}
+
+} // namespace rtb

@@ -1,0 +1,110 @@
+// Shared host/device plain-data types of the B200 ray-tracing path.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace rtb {
+
+// Image tiling: the unit of multi-GPU interleaving is a 32x16-pixel tile (512 pixels = 16 warps); inside a tile
+// pixels are ordered so that one warp owns an 8x4 block (coherent primary rays).
+constexpr int kTileW = 32;
+constexpr int kTileH = 16;
+constexpr int kTilePixels = kTileW * kTileH;
+
+constexpr int kMaxLeafTris = 8;   // leaf size must fit the 3-bit count of a packed stack entry
+constexpr int kStackDepth = 64;   // per-thread traversal stack (ints); builders guarantee depth < kStackDepth
+constexpr int kMaxPointLights = 16;
+constexpr int kMaxSphereLights = 8;
+
+// Flattened BVH in HBM: 32-byte nodes {lo.xyz, left_or_first}{hi.xyz, count}, read as 2 x float4.
+// Sibling nodes are adjacent (2k, 2k+1) so visiting an inner node is one aligned 64-byte fetch of both children.
+// count == 0: inner node, left_or_first = index of the left child (even); count > 0: leaf over triangles
+// [left_or_first, left_or_first + count) of the BVH-ordered triangle arrays.  Node 0 is the root, node 1 an empty
+// box (lo=+inf, hi=-inf) so the root can be fetched like any other pair.
+struct SceneDev {
+    const float4* nodes;
+    const float4* tri_plane; // {n.xyz, D}: trianglePlane() precomputed by K0 with the reference's op order
+    const float4* tri_v0;    // {v0.xyz, bits(global triangle id)}
+    const float4* tri_v1;    // {v1.xyz, bits(mesh id)}
+    const float4* tri_v2;    // {v2.xyz, 0}
+    const float4* tri_n0;    // corner normals, read only by shade / transparent shadow hits
+    const float4* tri_n1;
+    const float4* tri_n2;
+    const float4* mats;          // 2 x float4 per mesh: {kd.xyz, shininess}{ks.xyz, transparency}
+    const float4* point_lights;  // 2 x float4: {pos, 0}{color, 0}
+    const float4* sphere_lights; // 2 x float4: {pos, radius}{color, 0}
+    int n_tris;
+    int n_nodes;
+};
+
+struct FrameParams {
+    int W, H;
+    int sample_mode; // 0 single, 1 four-tap AA, 2 multipleRays
+    int sample_size;
+    int spp;         // rays per pixel
+    float sample_scale; // what the summed colour is multiplied with (1, 0.25, 1/sample_size)
+    float aa_off_x, aa_off_y;   // main.cpp:360-361
+    float ms_off_x, ms_off_y;   // main.cpp:311-312 (evaluated in double on the host, as the reference does)
+    int ms_moves;               // main.cpp:324
+    // camera (quaternion, origin and half extents are computed on the host with libm, like the reference)
+    float qx, qy, qz, qw;
+    float ox, oy, oz;
+    float halfW, halfH;
+    // sharding
+    int tiles_x, tiles_y;
+    int rank, world;
+    int n_local_tiles;
+    // shading
+    int max_level;
+    float refraction;
+    int n_point, n_sphere;
+    int any_transparent;
+    int exhaustive;
+    // spherical-light ring sampling (shadow.cpp:190-196), host-computed and shared with the oracle
+    int sl_m, sl_n, sl_rc;
+    float sl_sin, sl_omc;
+    int sl_group; // lanes cooperating on one (hit, light) pair: smallest power of two >= sl_rc, at most 32
+};
+
+// Device-resident counters of one wavefront batch.
+struct Counters {
+    unsigned int n_rays[2];      // ray queue fill (ping-pong)
+    unsigned int n_shadow_pt;    // point-light shadow records
+    unsigned int n_shadow_sp;    // spherical-light records
+    unsigned int work[4];        // dynamic work-fetch cursors: extend, shade, shadow_pt, shadow_sp
+    unsigned int overflow;       // set when a queue would exceed its capacity
+    unsigned int pad;
+    unsigned long long primary_rays;
+    unsigned long long shadow_queries;
+    unsigned long long secondary_rays;
+    unsigned long long node_visits;
+    unsigned long long tri_tests;
+    unsigned long long tri_tests_full;
+};
+
+struct RayQueue {
+    float4* o_pix; // {origin.xyz, bits(local pixel index)}
+    float4* d;     // {direction.xyz, 0}
+    float4* w;     // {throughput.rgb, 0}
+    int2* hit;     // {bits(t), BVH-order triangle index or -1}
+};
+
+struct ShadowQueue {
+    float4* p_pix;   // {hit point, bits(local pixel index)}
+    float4* a_light; // {A.rgb (scaled by the shadow intensity), bits(light index)}
+    float4* b;       // {B.rgb (added when the light is visible), 0}
+};
+
+struct BatchDev {
+    RayQueue q[2];
+    ShadowQueue sq_point, sq_sphere;
+    unsigned int ray_capacity;
+    unsigned int shadow_pt_capacity;
+    unsigned int shadow_sp_capacity;
+    Counters* counters;
+    float4* accum;    // per local padded pixel, summed radiance
+    int* prim_id;     // nullable: closest-hit global triangle id of the first primary ray of each local pixel
+    float* prim_t;    // nullable
+};
+
+} // namespace rtb

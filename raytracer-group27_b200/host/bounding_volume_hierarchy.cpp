@@ -1,0 +1,79 @@
+#include "bounding_volume_hierarchy.h"
+#include "rt_b200.h"
+#include <stdexcept>
+#include <string>
+
+namespace {
+void check(int rc, const char* what)
+{
+    if (rc != RT_OK)
+        throw std::runtime_error(std::string(what) + ": " + rt_last_error());
+}
+}
+
+BoundingVolumeHierarchy::BoundingVolumeHierarchy(Scene* pScene, int bvhMode, int device)
+    : m_pScene(pScene)
+{
+    std::vector<rt_material> mats;
+    int meshIndex = 0;
+    for (const Mesh& mesh : pScene->meshes) {
+        for (const Triangle& tri : mesh.triangles) {
+            const Vertex* v[3] = { &mesh.vertices[tri.x], &mesh.vertices[tri.y], &mesh.vertices[tri.z] };
+            for (int k = 0; k < 3; k++) {
+                m_pos.insert(m_pos.end(), { v[k]->p.x, v[k]->p.y, v[k]->p.z });
+                m_nrm.insert(m_nrm.end(), { v[k]->n.x, v[k]->n.y, v[k]->n.z });
+            }
+            m_meshId.push_back(meshIndex);
+        }
+        const Material& m = mesh.material;
+        mats.push_back(rt_material { { m.kd.x, m.kd.y, m.kd.z }, { m.ks.x, m.ks.y, m.ks.z }, m.shininess, m.transparency });
+        meshIndex++;
+    }
+    check(rt_create(device, &m_ctx), "rt_create");
+    check(rt_upload_scene(m_ctx, m_pos.data(), m_nrm.data(), m_meshId.data(), (int64_t)m_meshId.size(), mats.data(), (int)mats.size()), "rt_upload_scene");
+    check(rt_build_bvh(m_ctx, bvhMode), "rt_build_bvh");
+    // depth of a balanced binary tree over the triangles, for callers that print it
+    size_t n = m_meshId.size();
+    while (n > 1) {
+        n = (n + 1) / 2;
+        m_numLevels++;
+    }
+    m_numLevels++;
+}
+
+BoundingVolumeHierarchy::~BoundingVolumeHierarchy()
+{
+    if (m_ctx)
+        rt_destroy(m_ctx);
+}
+
+bool BoundingVolumeHierarchy::intersect(Ray& ray, HitInfo& hitInfo, bool useBVH) const
+{
+    const float r[6] = { ray.origin.x, ray.origin.y, ray.origin.z, ray.direction.x, ray.direction.y, ray.direction.z };
+    int id = -1;
+    float t = 0.0f;
+    check(rt_intersect(m_ctx, r, 1, useBVH ? 1 : 0, &id, &t), "rt_intersect");
+    if (id < 0 || !(t < ray.t))
+        return false;
+    ray.t = t;
+    hitInfo.is_triangle = true;
+    hitInfo.triangle_index = id;
+    hitInfo.material_index = m_meshId[id];
+    hitInfo.hitPoint = ray.origin + ray.direction * t;
+    // shading normal: barycentric blend of the corner normals, flipped to the geometric side
+    // (src/ray_tracing.cpp:147-160, 276-308; barycentrics always evaluated, see DESIGN.md "defined barycentrics")
+    const float* p = &m_pos[9 * size_t(id)];
+    const float* nn = &m_nrm[9 * size_t(id)];
+    const glm::vec3 v0(p[0], p[1], p[2]), v1(p[3], p[4], p[5]), v2(p[6], p[7], p[8]);
+    const glm::vec3 faceN = glm::normalize(glm::cross(v0 - v2, v1 - v2));
+    const glm::vec3 hp = hitInfo.hitPoint;
+    const float total = glm::length(glm::cross(v1 - v0, v2 - v0));
+    const float c0 = glm::length(glm::cross(v1 - hp, v2 - hp)) / total;
+    const float c1 = glm::length(glm::cross(hp - v0, v2 - v0)) / total;
+    const float c2 = glm::length(glm::cross(v1 - v0, hp - v0)) / total;
+    glm::vec3 n = glm::vec3(nn[0], nn[1], nn[2]) * c0 + glm::vec3(nn[3], nn[4], nn[5]) * c1 + glm::vec3(nn[6], nn[7], nn[8]) * c2;
+    if (glm::dot(n, faceN) < 0)
+        n = -n;
+    hitInfo.normal = n;
+    return true;
+}

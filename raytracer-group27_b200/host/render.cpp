@@ -1,0 +1,62 @@
+#include "render.h"
+#include "rt_b200.h"
+#include <stdexcept>
+#include <string>
+
+int max_reflection_level = 5;
+int sphere_light_ray_count = 10;
+int glossy_ray_count = 1;
+float refraction_factor = 0.8f;
+bool useBVH = false;
+RenderTimings lastRenderTimings;
+
+namespace {
+void check(int rc, const char* what)
+{
+    if (rc != RT_OK)
+        throw std::runtime_error(std::string(what) + ": " + rt_last_error());
+}
+}
+
+void renderRayTracing(Scene& scene, const Trackball& camera, const BoundingVolumeHierarchy& bvh, Screen& screen,
+    bool textureDebugging, bool anti_aliasing, bool multipleRays, int sampleSize)
+{
+    if (textureDebugging)
+        throw std::runtime_error("renderRayTracing: the texture-debug view is outside the rebuilt path");
+    rt_ctx* ctx = bvh.context();
+
+    // lights and materials are read live from the Scene every frame (src/shadow.cpp:111,141; ray_tracing.h:23-27)
+    std::vector<rt_material> mats;
+    for (const Mesh& mesh : scene.meshes) {
+        const Material& m = mesh.material;
+        mats.push_back(rt_material { { m.kd.x, m.kd.y, m.kd.z }, { m.ks.x, m.ks.y, m.ks.z }, m.shininess, m.transparency });
+    }
+    check(rt_set_materials(ctx, mats.data(), (int)mats.size()), "rt_set_materials");
+    std::vector<rt_point_light> pl;
+    for (const PointLight& l : scene.pointLights)
+        pl.push_back(rt_point_light { { l.position.x, l.position.y, l.position.z }, { l.color.x, l.color.y, l.color.z } });
+    std::vector<rt_sphere_light> sl;
+    for (const SphericalLight& l : scene.sphericalLight)
+        sl.push_back(rt_sphere_light { { l.position.x, l.position.y, l.position.z }, l.radius, { l.color.x, l.color.y, l.color.z } });
+    check(rt_set_lights(ctx, pl.data(), (int)pl.size(), sl.data(), (int)sl.size()), "rt_set_lights");
+
+    const glm::ivec2 res = screen.resolution();
+    const glm::vec3 la = camera.lookAt(), eu = camera.rotationEulerAngles();
+    rt_camera cam { { la.x, la.y, la.z }, { eu.x, eu.y, eu.z }, camera.distanceFromLookAt(), camera.fovy() };
+    rt_params prm {};
+    prm.width = res.x;
+    prm.height = res.y;
+    prm.max_reflection_level = max_reflection_level;
+    prm.sphere_light_ray_count = sphere_light_ray_count;
+    prm.glossy_ray_count = glossy_ray_count;
+    prm.refraction_factor = refraction_factor;
+    prm.sample_mode = anti_aliasing ? 1 : (multipleRays ? 2 : 0);
+    prm.sample_size = sampleSize;
+    prm.exhaustive = useBVH ? 0 : 0; // both reference settings give the same image; the BVH is always used
+    rt_stats st {};
+    static_assert(sizeof(glm::vec3) == 3 * sizeof(float), "Screen pixels must be packed float3");
+    check(rt_render(ctx, &cam, &prm, &screen.pixels()[0].x, nullptr, nullptr, &st), "rt_render");
+    lastRenderTimings.gpu_ms = st.gpu_ms;
+    lastRenderTimings.rays = st.primary_rays + st.shadow_queries + st.secondary_rays;
+    screen.postprocessImage();
+}

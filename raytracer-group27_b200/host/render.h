@@ -1,0 +1,23 @@
+// renderRayTracing — the render entry main.cpp calls (src/main.cpp:340-341), same parameter list.  The knobs
+// the reference keeps as file-scope statics in main.cpp (src/main.cpp:58-60,123-127) are exported here under
+// the same names so a main.cpp that includes this header can drop its own definitions.
+#pragma once
+#include "bounding_volume_hierarchy.h"
+#include "scene.h"
+#include "screen.h"
+#include "trackball.h"
+
+extern int max_reflection_level;   // default 5
+extern int sphere_light_ray_count; // default 10
+extern int glossy_ray_count;       // reference default 10 uses rand(); only the deterministic value 1 is supported
+extern float refraction_factor;    // default 0.8
+extern bool useBVH;                // reference default false (brute force); both settings give the same image
+
+struct RenderTimings {
+    float gpu_ms = 0.0f;
+    unsigned long long rays = 0; // primary + shadow queries + reflection/refraction rays
+};
+extern RenderTimings lastRenderTimings;
+
+void renderRayTracing(Scene& scene, const Trackball& camera, const BoundingVolumeHierarchy& bvh, Screen& screen,
+    bool textureDebugging = false, bool anti_aliasing = false, bool multipleRays = false, int sampleSize = 4);

@@ -1,0 +1,301 @@
+"""ctypes binding of librtb200.so (include/rt_b200.h) for tests, bench.py and torch.distributed plumbing.
+
+The product is the shared library; this module only marshals numpy / torch buffers into its C ABI.  There is no
+CPU fallback: importing works without a GPU (the library loads), but every compute entry point needs a B200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "librtb200.so")
+
+RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_OVERFLOW, RT_ERR_IO = 0, 1, 2, 3, 4
+BVH_LBVH_DEVICE, BVH_SAH_HOST = 0, 1
+
+
+class RtError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"rt_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Material(C.Structure):
+    _fields_ = [("kd", C.c_float * 3), ("ks", C.c_float * 3), ("shininess", C.c_float), ("transparency", C.c_float)]
+
+
+class PointLight(C.Structure):
+    _fields_ = [("position", C.c_float * 3), ("color", C.c_float * 3)]
+
+
+class SphereLight(C.Structure):
+    _fields_ = [("position", C.c_float * 3), ("radius", C.c_float), ("color", C.c_float * 3)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("look_at", C.c_float * 3), ("euler", C.c_float * 3), ("dist", C.c_float), ("fovy", C.c_float)]
+
+
+class Params(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("max_reflection_level", C.c_int), ("sphere_light_ray_count", C.c_int),
+                ("glossy_ray_count", C.c_int), ("refraction_factor", C.c_float), ("sample_mode", C.c_int), ("sample_size", C.c_int),
+                ("exhaustive", C.c_int)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("primary_rays", C.c_uint64), ("shadow_queries", C.c_uint64), ("secondary_rays", C.c_uint64), ("node_visits", C.c_uint64),
+                ("tri_tests", C.c_uint64), ("tri_tests_full", C.c_uint64), ("gpu_ms", C.c_float), ("kernel_launches", C.c_int),
+                ("batches", C.c_int)]
+
+    @property
+    def rays(self) -> int:
+        return int(self.primary_rays + self.shadow_queries + self.secondary_rays)
+
+
+MATERIAL_DTYPE = np.dtype([("kd", np.float32, 3), ("ks", np.float32, 3), ("shininess", np.float32), ("transparency", np.float32)])
+
+_lib = None
+
+# every symbol include/rt_b200.h declares: (name, restype, argtypes)
+_P, _I, _F = C.c_void_p, C.c_int, C.POINTER(C.c_float)
+SYMBOLS = [
+    ("rt_create", _I, [_I, C.POINTER(_P)]),
+    ("rt_destroy", _I, [_P]),
+    ("rt_set_stream", _I, [_P, _P]),
+    ("rt_upload_scene", _I, [_P, _P, _P, _P, C.c_int64, _P, _I]),
+    ("rt_build_bvh", _I, [_P, _I]),
+    ("rt_set_materials", _I, [_P, _P, _I]),
+    ("rt_set_lights", _I, [_P, _P, _I, _P, _I]),
+    ("rt_bvh_info", _I, [_P, C.POINTER(_I), C.POINTER(_I)]),
+    ("rt_set_counters", _I, [_P, _I]),
+    ("rt_set_batch_rays", _I, [_P, C.c_uint]),
+    ("rt_set_shard", _I, [_P, _I, _I]),
+    ("rt_render", _I, [_P, C.POINTER(Camera), C.POINTER(Params), _P, _P, _P, C.POINTER(Stats)]),
+    ("rt_render_device", _I, [_P, C.POINTER(Camera), C.POINTER(Params), _P]),
+    ("rt_sync", _I, [_P, C.POINTER(Stats)]),
+    ("rt_framebuffer", _I, [_P, C.POINTER(_P), C.POINTER(_I), C.POINTER(_I)]),
+    ("rt_framebuffer_ipc_handle", _I, [_P, _I, _I, _P]),
+    ("rt_open_peer_framebuffer", _I, [_P, _P, C.POINTER(_P)]),
+    ("rt_close_peer_framebuffer", _I, [_P, _P]),
+    ("rt_download_rgb", _I, [_P, _P, _I, _I, _P]),
+    ("rt_intersect", _I, [_P, _P, C.c_int64, _I, _P, _P]),
+    ("rt_load_obj", _I, [C.c_char_p, _I, C.POINTER(_P)]),
+    ("rt_soup_num_triangles", C.c_int64, [_P]),
+    ("rt_soup_num_meshes", _I, [_P]),
+    ("rt_soup_positions", _P, [_P]),
+    ("rt_soup_normals", _P, [_P]),
+    ("rt_soup_mesh_ids", _P, [_P]),
+    ("rt_soup_materials", _P, [_P]),
+    ("rt_soup_free", None, [_P]),
+    ("rt_last_error", C.c_char_p, []),
+    ("rt_version", C.c_char_p, []),
+]
+
+
+def lib() -> C.CDLL:
+    """Load librtb200.so; raises (never falls back) if the CUDA extension was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `make -C raytracer-group27_b200` "
+                              "(or __graft_entry__.build()); there is no CPU fallback")
+        l = C.CDLL(LIB_PATH)
+        for name, res, args in SYMBOLS:
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != RT_OK:
+        raise RtError(rc, lib().rt_last_error().decode(errors="replace"))
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+@dataclass
+class SceneData:
+    """Triangle soup in the reference's global triangle order + per-mesh materials + lights."""
+    pos: np.ndarray          # (n, 9) float32
+    nrm: np.ndarray          # (n, 9) float32
+    mesh_id: np.ndarray      # (n,) int32
+    mats: np.ndarray         # (m,) MATERIAL_DTYPE
+    point_lights: np.ndarray = field(default_factory=lambda: np.zeros((0, 6), np.float32))   # position, colour
+    sphere_lights: np.ndarray = field(default_factory=lambda: np.zeros((0, 7), np.float32))  # position, radius, colour
+
+    @property
+    def n_tris(self) -> int:
+        return int(self.pos.shape[0])
+
+
+def load_obj(path: str, normalize: bool = False) -> SceneData:
+    """loadMesh (src/mesh.cpp:58-188) through the library's host-side OBJ/MTL importer (no GPU needed)."""
+    l = lib()
+    h = _P()
+    _check(l.rt_load_obj(os.fsencode(path), 1 if normalize else 0, C.byref(h)))
+    try:
+        n = l.rt_soup_num_triangles(h)
+        m = l.rt_soup_num_meshes(h)
+        pos = np.ctypeslib.as_array(C.cast(l.rt_soup_positions(h), _F), shape=(n, 9)).copy()
+        nrm = np.ctypeslib.as_array(C.cast(l.rt_soup_normals(h), _F), shape=(n, 9)).copy()
+        ids = np.ctypeslib.as_array(C.cast(l.rt_soup_mesh_ids(h), C.POINTER(C.c_int)), shape=(n,)).copy()
+        raw = np.ctypeslib.as_array(C.cast(l.rt_soup_materials(h), _F), shape=(m, 8)).copy()
+        mats = np.zeros(m, MATERIAL_DTYPE)
+        mats["kd"], mats["ks"], mats["shininess"], mats["transparency"] = raw[:, 0:3], raw[:, 3:6], raw[:, 6], raw[:, 7]
+    finally:
+        l.rt_soup_free(h)
+    return SceneData(pos, nrm, ids.astype(np.int32), mats)
+
+
+def make_camera(look_at=(0.0, 0.0, 0.0), euler_deg=(20.0, 20.0, 0.0), dist=3.0, fovy_deg=50.0) -> Camera:
+    """Reference default camera (src/main.cpp:413-414); degrees -> radians with glm::radians' float constant."""
+    k = np.float32(0.01745329251994329576923690768489)
+    cam = Camera()
+    cam.look_at[:] = [float(v) for v in look_at]
+    cam.euler[:] = [float(np.float32(v) * k) for v in euler_deg]
+    cam.dist = float(dist)
+    cam.fovy = float(np.float32(fovy_deg) * k)
+    return cam
+
+
+def make_params(width, height, max_level=5, sphere_rays=10, refraction=0.8, sample_mode=0, sample_size=4, exhaustive=False) -> Params:
+    p = Params()
+    p.width, p.height = int(width), int(height)
+    p.max_reflection_level = int(max_level)
+    p.sphere_light_ray_count = int(sphere_rays)
+    p.glossy_ray_count = 1
+    p.refraction_factor = float(refraction)
+    p.sample_mode, p.sample_size = int(sample_mode), int(sample_size)
+    p.exhaustive = 1 if exhaustive else 0
+    return p
+
+
+class Context:
+    """One rt_ctx (one GPU).  Mirrors the life cycle Scene -> BoundingVolumeHierarchy(&scene) -> renderRayTracing."""
+
+    def __init__(self, device: int = 0):
+        self._l = lib()
+        self._h = _P()
+        _check(self._l.rt_create(device, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            self._l.rt_destroy(self._h)
+            self._h = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- scene --
+    def upload_scene(self, scene: SceneData, bvh_mode: int = BVH_LBVH_DEVICE):
+        pos, nrm = _f32(scene.pos), _f32(scene.nrm)
+        ids = np.ascontiguousarray(scene.mesh_id, dtype=np.int32)
+        mats = np.ascontiguousarray(scene.mats, dtype=MATERIAL_DTYPE)
+        _check(self._l.rt_upload_scene(self._h, pos.ctypes.data, nrm.ctypes.data, ids.ctypes.data, pos.shape[0], mats.ctypes.data, mats.shape[0]))
+        _check(self._l.rt_build_bvh(self._h, bvh_mode))
+        self.set_lights(scene.point_lights, scene.sphere_lights)
+
+    def build_bvh(self, mode: int):
+        _check(self._l.rt_build_bvh(self._h, mode))
+
+    def bvh_info(self):
+        n, d = C.c_int(), C.c_int()
+        _check(self._l.rt_bvh_info(self._h, C.byref(n), C.byref(d)))
+        return n.value, d.value
+
+    def set_materials(self, mats: np.ndarray):
+        mats = np.ascontiguousarray(mats, dtype=MATERIAL_DTYPE)
+        _check(self._l.rt_set_materials(self._h, mats.ctypes.data, mats.shape[0]))
+
+    def set_lights(self, point_lights=None, sphere_lights=None):
+        pl = _f32(point_lights if point_lights is not None else np.zeros((0, 6))).reshape(-1, 6)
+        sl = _f32(sphere_lights if sphere_lights is not None else np.zeros((0, 7))).reshape(-1, 7)
+        _check(self._l.rt_set_lights(self._h, pl.ctypes.data if len(pl) else None, len(pl), sl.ctypes.data if len(sl) else None, len(sl)))
+
+    def set_counters(self, enable: bool):
+        _check(self._l.rt_set_counters(self._h, 1 if enable else 0))
+
+    def set_batch_rays(self, n: int):
+        _check(self._l.rt_set_batch_rays(self._h, int(n)))
+
+    def set_shard(self, rank: int, world: int):
+        _check(self._l.rt_set_shard(self._h, rank, world))
+
+    def set_stream(self, cuda_stream: int):
+        _check(self._l.rt_set_stream(self._h, _P(cuda_stream)))
+
+    # -- render --
+    def render(self, cam: Camera, prm: Params, want_ids: bool = False, rgb_out: np.ndarray | None = None):
+        """Host buffers in, host buffers out (the reference-facing call).  Returns (rgb[H,W,3], ids|None, t|None, Stats)."""
+        h, w = prm.height, prm.width
+        rgb = rgb_out if rgb_out is not None else np.empty((h, w, 3), np.float32)
+        ids = np.empty((h, w), np.int32) if want_ids else None
+        t = np.empty((h, w), np.float32) if want_ids else None
+        st = Stats()
+        _check(self._l.rt_render(self._h, C.byref(cam), C.byref(prm), rgb.ctypes.data, ids.ctypes.data if want_ids else None,
+                                 t.ctypes.data if want_ids else None, C.byref(st)))
+        return rgb, ids, t, st
+
+    def render_host_ptr(self, cam: Camera, prm: Params, rgb_ptr: int) -> Stats:
+        """rt_render into caller-owned (ideally pinned) host memory given as an address."""
+        st = Stats()
+        _check(self._l.rt_render(self._h, C.byref(cam), C.byref(prm), _P(rgb_ptr), None, None, C.byref(st)))
+        return st
+
+    def render_device(self, cam: Camera, prm: Params, d_rgba: int | None = None):
+        _check(self._l.rt_render_device(self._h, C.byref(cam), C.byref(prm), _P(d_rgba) if d_rgba else None))
+
+    def sync(self) -> Stats:
+        st = Stats()
+        _check(self._l.rt_sync(self._h, C.byref(st)))
+        return st
+
+    def framebuffer(self):
+        p, w, h = _P(), C.c_int(), C.c_int()
+        _check(self._l.rt_framebuffer(self._h, C.byref(p), C.byref(w), C.byref(h)))
+        return p.value, w.value, h.value
+
+    def framebuffer_ipc_handle(self, width: int, height: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(self._l.rt_framebuffer_ipc_handle(self._h, width, height, buf))
+        return buf.raw
+
+    def open_peer_framebuffer(self, handle: bytes) -> int:
+        p = _P()
+        _check(self._l.rt_open_peer_framebuffer(self._h, C.create_string_buffer(handle, 64), C.byref(p)))
+        return p.value
+
+    def close_peer_framebuffer(self, ptr: int):
+        _check(self._l.rt_close_peer_framebuffer(self._h, _P(ptr)))
+
+    def download_rgb(self, d_rgba: int, width: int, height: int) -> np.ndarray:
+        rgb = np.empty((height, width, 3), np.float32)
+        _check(self._l.rt_download_rgb(self._h, _P(d_rgba), width, height, rgb.ctypes.data))
+        return rgb
+
+    def intersect(self, rays: np.ndarray, use_bvh: bool = True):
+        """BoundingVolumeHierarchy::intersect for a batch of rays (n, 6) -> (tri_id[n], t[n])."""
+        rays = _f32(rays).reshape(-1, 6)
+        n = rays.shape[0]
+        ids = np.empty(n, np.int32)
+        t = np.empty(n, np.float32)
+        _check(self._l.rt_intersect(self._h, rays.ctypes.data, n, 1 if use_bvh else 0, ids.ctypes.data, t.ctypes.data))
+        return ids, t
