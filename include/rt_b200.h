@@ -96,6 +96,18 @@ int rt_set_lights(rt_ctx* ctx, const rt_point_light* point, int n_point, const r
 int rt_bvh_info(rt_ctx* ctx, int* n_nodes, int* depth);
 /* Instrumented kernels: fill rt_stats.node_visits / tri_tests / tri_tests_full (slower; off by default). */
 int rt_set_counters(rt_ctx* ctx, int enable);
+/* Per-stage device timing of the next frames: CUDA events around every kernel launch (adds a little overhead, so
+ * leave it off for frames whose total time is being measured).  rt_stage_times returns, for the frame completed by
+ * the last rt_sync / rt_render, the summed milliseconds and launch counts of each stage. */
+#define RT_STAGE_GENERATE 0
+#define RT_STAGE_EXTEND 1
+#define RT_STAGE_SHADE 2
+#define RT_STAGE_SHADOW_POINT 3
+#define RT_STAGE_SHADOW_SPHERE 4
+#define RT_STAGE_RESOLVE 5
+#define RT_STAGE_COUNT 6
+int rt_set_stage_timing(rt_ctx* ctx, int enable);
+int rt_stage_times(rt_ctx* ctx, float* ms /* [RT_STAGE_COUNT] */, int* launches /* [RT_STAGE_COUNT] */);
 /* Upper bound on primary rays per wavefront batch (default 2^24): ray-state memory is O(batch), not O(W*H*spp). */
 int rt_set_batch_rays(rt_ctx* ctx, unsigned int max_primary_rays_per_batch);
 

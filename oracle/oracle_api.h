@@ -56,7 +56,8 @@ typedef struct {
  * triangle order; mesh_id[i] is the index of the owning mesh (non-decreasing); mats[mesh_id].
  * point_lights: 6 floats each (position, colour); sphere_lights: 7 floats (position, radius, colour).
  * Outputs may be NULL.  rgb uses the Screen layout (src/screen.cpp:32-38): row (H-1-y), column x.
- * tri_id / t_hit / use the same layout; tri_id = -1 and t = FLT_MAX on a miss. */
+ * tri_id / t_hit use the same layout and describe the FIRST primary ray of the pixel (the pixel-corner ray, or the
+ * first sub-pixel sample when sample_mode != 0); tri_id = -1 and t = FLT_MAX on a miss. */
 int oracle_render(const float* pos, const float* nrm, const int* mesh_id, int n_tris,
     const orc_material* mats, int n_mats,
     const float* point_lights, int n_point, const float* sphere_lights, int n_sphere,

@@ -261,6 +261,7 @@ extern "C" int oracle_render(const float* pos, const float* nrm, const int* mesh
             const glm::vec2 normalizedPixelPos { float(x) / W * 2.0f - 1.0f, float(y) / H * 2.0f - 1.0f };
             const Ray cameraRay = camera.generateRay(normalizedPixelPos);
             glm::vec3 out(0);
+            Ray firstRay = cameraRay; // the ray whose closest hit is reported in tri_id / t_hit: first sample of the pixel
             if (prm->sample_mode == 1) { // main.cpp:358-375
                 float offsetX = 1.0f / W * 0.25f;
                 float offsetY = 1.0f / H * 0.25f;
@@ -270,6 +271,7 @@ extern "C" int oracle_render(const float* pos, const float* nrm, const int* mesh
                 offsets[2] = glm::vec2(normalizedPixelPos.x - offsetX, normalizedPixelPos.y - offsetY);
                 offsets[3] = glm::vec2(normalizedPixelPos.x + offsetX, normalizedPixelPos.y - offsetY);
                 glm::vec3 avgColor(0);
+                firstRay = camera.generateRay(offsets[0]);
                 for (int i = 0; i < 4; i++) {
                     Ray ray = camera.generateRay(offsets[i]);
                     cnt.primary++;
@@ -280,6 +282,8 @@ extern "C" int oracle_render(const float* pos, const float* nrm, const int* mesh
             } else if (prm->sample_mode == 2) { // main.cpp:377-385
                 std::vector<glm::vec2> rayOrigins = getPixelRays(g, normalizedPixelPos, prm->sample_size);
                 glm::vec3 avgColor(0);
+                if (!rayOrigins.empty())
+                    firstRay = camera.generateRay(rayOrigins[0]);
                 for (auto& rayOrigin : rayOrigins) {
                     Ray ray = camera.generateRay(rayOrigin);
                     cnt.primary++;
@@ -299,7 +303,7 @@ extern "C" int oracle_render(const float* pos, const float* nrm, const int* mesh
             }
             if (tri_id || t_hit) {
                 float t;
-                const int id = exhaustiveId(pos, n_tris, cameraRay, t);
+                const int id = exhaustiveId(pos, n_tris, firstRay, t);
                 if (tri_id)
                     tri_id[i] = id;
                 if (t_hit)

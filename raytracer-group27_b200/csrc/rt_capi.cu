@@ -98,6 +98,14 @@ struct rt_ctx {
     int last_launches = 0, last_batches = 0;
     bool frame_pending = false;
 
+    // optional per-stage device timing (events around every launch; off for timed frames)
+    bool stage_timing = false;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_stage; // stage of the launch between ev_pool[2k] and ev_pool[2k+1]
+    size_t ev_used = 0;
+    float stage_ms[RT_STAGE_COUNT] = { 0 };
+    int stage_launches[RT_STAGE_COUNT] = { 0 };
+
     SceneDev scene_dev() const
     {
         SceneDev s;
@@ -283,6 +291,30 @@ int ensure_batch(rt_ctx* ctx, const FrameParams& fp, unsigned batch_pixels, bool
     return RT_OK;
 }
 
+struct StageScope { // brackets one launch with events when stage timing is on
+    rt_ctx* ctx;
+    bool on;
+    StageScope(rt_ctx* c, int stage) : ctx(c), on(c->stage_timing)
+    {
+        if (!on)
+            return;
+        while (ctx->ev_pool.size() < ctx->ev_used + 2) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ctx->ev_pool.push_back(e);
+        }
+        ctx->ev_stage.push_back(stage);
+        cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream);
+    }
+    ~StageScope()
+    {
+        if (!on)
+            return;
+        cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], ctx->stream);
+        ctx->ev_used += 2;
+    }
+};
+
 // Enqueue one frame on the context's stream.  `out`: float4 framebuffer (Screen layout), maybe on a peer GPU.
 int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids, unsigned batch_rays)
 {
@@ -297,6 +329,8 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids
     const SceneDev s = ctx->scene_dev();
     cudaStream_t st = ctx->stream;
     int launches = 0, batches = 0;
+    ctx->ev_used = 0;
+    ctx->ev_stage.clear();
     CK(cudaEventRecord(ctx->ev0, st));
     CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(Counters), st));
     if (n_local)
@@ -304,19 +338,30 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids
     for (size_t first = 0; first < n_local; first += batch_pixels) {
         const unsigned n_lp = (unsigned)std::min<size_t>(batch_pixels, n_local - first);
         launch_level_reset(st, b.counters, 0, 1);
-        launch_generate(st, ctx->sm_count, fp, b, (unsigned)first, n_lp, 0);
+        {
+            StageScope sc(ctx, RT_STAGE_GENERATE);
+            launch_generate(st, ctx->sm_count, fp, b, (unsigned)first, n_lp, 0);
+        }
         launches += 2;
         for (int level = 0; level <= fp.max_level; level++) {
             const int qi = level & 1;
             launch_level_reset(st, b.counters, qi ^ 1, 0);
-            launch_extend(st, ctx->sm_count, s, ctx->root_entry, fp, b, qi, level, ctx->counters_enabled);
-            launch_shade(st, ctx->sm_count, s, fp, b, qi, level);
+            {
+                StageScope sc(ctx, RT_STAGE_EXTEND);
+                launch_extend(st, ctx->sm_count, s, ctx->root_entry, fp, b, qi, level, ctx->counters_enabled);
+            }
+            {
+                StageScope sc(ctx, RT_STAGE_SHADE);
+                launch_shade(st, ctx->sm_count, s, fp, b, qi, level);
+            }
             launches += 3;
             if (fp.n_point > 0) {
+                StageScope sc(ctx, RT_STAGE_SHADOW_POINT);
                 launch_shadow_point(st, ctx->sm_count, s, ctx->root_entry, fp, b, ctx->counters_enabled);
                 launches++;
             }
             if (fp.n_sphere > 0) {
+                StageScope sc(ctx, RT_STAGE_SHADOW_SPHERE);
                 launch_shadow_sphere(st, ctx->sm_count, s, ctx->root_entry, fp, b, ctx->counters_enabled);
                 launches++;
             }
@@ -324,6 +369,7 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids
         batches++;
     }
     if (n_local) {
+        StageScope sc(ctx, RT_STAGE_RESOLVE);
         launch_resolve(st, ctx->sm_count, fp, ctx->accum.p, b.prim_id, b.prim_t, out, want_ids ? ctx->out_id.p : nullptr,
             want_ids ? ctx->out_t.p : nullptr);
         launches++;
@@ -417,6 +463,8 @@ int rt_destroy(rt_ctx* ctx)
         cudaFree(ctx->lbvh_perm);
     if (ctx->h_counters)
         cudaFreeHost(ctx->h_counters);
+    for (cudaEvent_t e : ctx->ev_pool)
+        cudaEventDestroy(e);
     if (ctx->ev0)
         cudaEventDestroy(ctx->ev0);
     if (ctx->ev1)
@@ -445,6 +493,25 @@ int rt_set_counters(rt_ctx* ctx, int enable)
     if (!ctx)
         return fail(RT_ERR_INVALID, "null context");
     ctx->counters_enabled = enable != 0;
+    return RT_OK;
+}
+
+int rt_set_stage_timing(rt_ctx* ctx, int enable)
+{
+    if (!ctx)
+        return fail(RT_ERR_INVALID, "null context");
+    ctx->stage_timing = enable != 0;
+    return RT_OK;
+}
+
+int rt_stage_times(rt_ctx* ctx, float* ms, int* launches)
+{
+    if (!ctx || !ms || !launches)
+        return fail(RT_ERR_INVALID, "rt_stage_times: bad arguments");
+    for (int k = 0; k < RT_STAGE_COUNT; k++) {
+        ms[k] = ctx->stage_ms[k];
+        launches[k] = ctx->stage_launches[k];
+    }
     return RT_OK;
 }
 
@@ -651,6 +718,17 @@ int rt_sync(rt_ctx* ctx, rt_stats* stats)
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->frame_pending) {
         ctx->frame_pending = false;
+        for (int k = 0; k < RT_STAGE_COUNT; k++) {
+            ctx->stage_ms[k] = 0.0f;
+            ctx->stage_launches[k] = 0;
+        }
+        for (size_t k = 0; k + 1 < ctx->ev_used; k += 2) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, ctx->ev_pool[k], ctx->ev_pool[k + 1]) == cudaSuccess) {
+                ctx->stage_ms[ctx->ev_stage[k / 2]] += ms;
+                ctx->stage_launches[ctx->ev_stage[k / 2]]++;
+            }
+        }
         const Counters& c = *ctx->h_counters;
         if (c.overflow == 1)
             return fail(RT_ERR_OVERFLOW, "a ray queue overflowed (transparent materials doubled the wavefront more than provisioned); lower rt_set_batch_rays");

@@ -73,6 +73,8 @@ SYMBOLS = [
     ("rt_bvh_info", _I, [_P, C.POINTER(_I), C.POINTER(_I)]),
     ("rt_set_counters", _I, [_P, _I]),
     ("rt_set_batch_rays", _I, [_P, C.c_uint]),
+    ("rt_set_stage_timing", _I, [_P, _I]),
+    ("rt_stage_times", _I, [_P, _P, _P]),
     ("rt_set_shard", _I, [_P, _I, _I]),
     ("rt_render", _I, [_P, C.POINTER(Camera), C.POINTER(Params), _P, _P, _P, C.POINTER(Stats)]),
     ("rt_render_device", _I, [_P, C.POINTER(Camera), C.POINTER(Params), _P]),
@@ -232,6 +234,18 @@ class Context:
 
     def set_counters(self, enable: bool):
         _check(self._l.rt_set_counters(self._h, 1 if enable else 0))
+
+    STAGES = ("generate", "extend", "shade", "shadow_point", "shadow_sphere", "resolve")
+
+    def set_stage_timing(self, enable: bool):
+        _check(self._l.rt_set_stage_timing(self._h, 1 if enable else 0))
+
+    def stage_times(self) -> dict:
+        """{stage: (ms, launches)} of the frame completed by the last sync()/render()."""
+        ms = (C.c_float * 6)()
+        n = (C.c_int * 6)()
+        _check(self._l.rt_stage_times(self._h, ms, n))
+        return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(self.STAGES)}
 
     def set_batch_rays(self, n: int):
         _check(self._l.rt_set_batch_rays(self._h, int(n)))

@@ -1,0 +1,107 @@
+"""Mint the golden fixtures of tests/golden/*.npz.  Run HERE (the container that has /root/reference):
+
+    make -C oracle && make -C raytracer-group27_b200 && python tests/golden/make_golden.py
+
+The reference ships no tests or golden vectors for the render path, so the pins are minted from
+the reference's own code: each fixture holds the scene exactly as the OBJ importer produced it from
+/root/reference/data (triangle soup, materials), the lights / camera / knobs of the config, and the outputs of
+oracle/_ref/libref_oracle.so — the reference's ray_tracing.cpp, bounding_volume_hierarchy.cpp and shadow.cpp
+compiled verbatim — for that input: per-pixel colour, closest-hit triangle id and t of the primary ray, and ray
+counts.  Scenes whose triangles trip the reference's uninitialised-barycentric bug (teapot, dragon stand-in) take
+their colours from the port with defined barycentrics (ids and t still come from the verbatim code).  Every fixture
+also records whether port and reference agreed bit for bit when it was minted.
+/root/reference does not exist on the GPU box; the tests read only these .npz files.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(ROOT, "raytracer-group27_b200"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import oracle  # noqa: E402
+import rtb200  # noqa: E402
+from rtb200 import standin  # noqa: E402
+
+DATA = "/root/reference/data/"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+CAM = dict(look_at=(0.0, 0.0, 0.0), euler_deg=(20.0, 20.0, 0.0), dist=3.0, fovy_deg=50.0)  # src/main.cpp:413-414
+
+
+def mint(name, sc, w, h, *, max_level, sphere_rays=10, sample_mode=0, sample_size=4, colour_from="reference", cam=CAM):
+    c = rtb200.make_camera(**cam)
+    ref, port = oracle.Oracle("reference"), oracle.Oracle("port")
+    kw = dict(max_level=max_level, sphere_rays=sphere_rays, sample_mode=sample_mode, sample_size=sample_size, use_bvh=True)
+    r_rgb, r_ids, r_t, r_st = ref.render(sc.pos, sc.nrm, sc.mesh_id, sc.mats, sc.point_lights, sc.sphere_lights, c, w, h, **kw)
+    p_rgb, p_ids, p_t, p_st = port.render(sc.pos, sc.nrm, sc.mesh_id, sc.mats, sc.point_lights, sc.sphere_lights, c, w, h, **kw)
+    ids_equal = bool(np.array_equal(r_ids, p_ids))
+    t_equal = bool(np.array_equal(r_t.view(np.int32), p_t.view(np.int32)))
+    rgb_equal = bool(np.array_equal(r_rgb.view(np.int32), p_rgb.view(np.int32)))
+    rgb = r_rgb if colour_from == "reference" else p_rgb
+    st = r_st if colour_from == "reference" else p_st
+    assert ids_equal and t_equal, name
+    if colour_from == "reference":
+        assert rgb_equal, name
+    # exact-t tie census on primary rays: would another triangle give the same t?  (informational)
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"),
+        pos=sc.pos, nrm=sc.nrm, mesh_id=sc.mesh_id, mats=sc.mats, point_lights=sc.point_lights, sphere_lights=sc.sphere_lights,
+        cam_look_at=np.array(cam["look_at"], np.float32), cam_euler_deg=np.array(cam["euler_deg"], np.float32),
+        cam_dist=np.float32(cam["dist"]), cam_fovy_deg=np.float32(cam["fovy_deg"]),
+        width=w, height=h, max_level=max_level, sphere_rays=sphere_rays, sample_mode=sample_mode, sample_size=sample_size,
+        rgb=rgb, ids=r_ids, t=r_t,
+        primary_rays=st.primary_rays, shadow_queries=st.shadow_queries, secondary_rays=st.secondary_rays,
+        colour_from=colour_from, port_equals_reference=np.array([ids_equal, t_equal, rgb_equal]))
+    print(f"{name}: {sc.n_tris} tris {w}x{h} rays={st.rays} port==ref ids/t/rgb={ids_equal}/{t_equal}/{rgb_equal} "
+          f"rgb_maxdiff={np.abs(r_rgb - p_rgb).max():.3g} hit={np.mean(r_ids >= 0):.3f}")
+
+
+def with_lights(sc, point=None, sphere=None):
+    sc.point_lights = np.array(point if point is not None else np.zeros((0, 6)), np.float32).reshape(-1, 6)
+    sc.sphere_lights = np.array(sphere if sphere is not None else np.zeros((0, 7)), np.float32).reshape(-1, 7)
+    return sc
+
+
+def main():
+    cornell = lambda: rtb200.load_obj(DATA + "CornellBox-Mirror-Rotated.obj", True)
+    # C1 at reduced resolution: Cornell, point light (scene.cpp:33), depth 3
+    mint("cornell_c1_256", with_lights(cornell(), point=[[0, 0.58, 0, 1, 1, 1]]), 256, 256, max_level=3)
+    # C4 at reduced resolution: spherical light (scene.cpp:42), 64 samples, depth 5
+    mint("cornell_c4_96", with_lights(cornell(), sphere=[[0, 0.45, 0, 0.1, 1, 1, 1]]), 96, 96, max_level=5, sphere_rays=64)
+    # default sphere_light_ray_count (10 -> m=1, n=9), 4-tap AA, non-square frame
+    mint("cornell_sph10_aa_80x48", with_lights(cornell(), sphere=[[0, 0.45, 0, 0.1, 1, 1, 1]]), 80, 48, max_level=2, sphere_rays=10, sample_mode=1)
+    # multipleRays 16 spp (C5's sampling), ragged frame size (not a multiple of the 32x16 tile)
+    mint("cornell_ms16_70x45", with_lights(cornell(), point=[[0, 0.58, 0, 1, 1, 1]]), 70, 45, max_level=2, sample_mode=2, sample_size=16)
+    # both light kinds, looking from inside the box
+    mint("cornell_inside_128", with_lights(cornell(), point=[[0, 0.3, 0.2, 0.8, 0.7, 0.6]], sphere=[[0.1, 0.45, 0, 0.1, 0.5, 0.5, 1]]), 128, 128,
+         max_level=4, sphere_rays=20, cam=dict(look_at=(0.0, 0.0, 0.0), euler_deg=(5.0, 170.0, 0.0), dist=0.9, fovy_deg=70.0))
+    # Monkey preset: two point lights (scene.cpp:52-57), mirror-ish material
+    mint("monkey_192", with_lights(rtb200.load_obj(DATA + "monkey-rotated.obj", True), point=[[-1, 1, -1, 1, 1, 1], [1, -1, -1, 1, 1, 1]]), 192, 192, max_level=3)
+    # Cube preset (every material transparent: d 0.452632)
+    mint("cube_96", with_lights(rtb200.load_obj(DATA + "cube.obj", False), point=[[-1, 1, -1, 1, 1, 1]]), 96, 96, max_level=3)
+    # SingleTriangle preset: 2 triangles, point + magenta spherical light (scene.cpp:11-16)
+    tr = rtb200.load_obj(DATA + "tr_def.obj", False)
+    tr.mats["kd"] = 1.0
+    mint("tr_def_96", with_lights(tr, point=[[-1, 1, -1, 1, 1, 1]], sphere=[[-2.1, 1.24, -0.51, 0.5, 1, 0, 1]]), 96, 96, max_level=3)
+    # C2 at reduced resolution: teapot, depth 0; colours from the port (defined barycentrics)
+    mint("teapot_c2_256x144", with_lights(rtb200.load_obj(DATA + "teapot.obj", True), point=[[-1, 1, -1, 1, 1, 1]]), 256, 144, max_level=0, colour_from="port")
+    # teapot with reflections (ks 0.2)
+    mint("teapot_d3_128x72", with_lights(rtb200.load_obj(DATA + "teapot.obj", True), point=[[-1, 1, -1, 1, 1, 1]]), 128, 72, max_level=3, colour_from="port")
+    # C3 at reduced resolution on the dragon STAND-IN (data/dragon.obj is absent); geometry is regenerated by
+    # rtb200.standin, only the expected outputs are stored
+    sc = standin.dragon_standin_scene()
+    mint("dragon_standin_c3_160x90", sc, 160, 90, max_level=3, colour_from="port")
+    # drop the 6 MB of geometry from that fixture again: the tests regenerate it and check a checksum instead
+    path = os.path.join(OUT, "dragon_standin_c3_160x90.npz")
+    d = dict(np.load(path))
+    d["pos_sum"] = np.float64(d["pos"].astype(np.float64).sum())
+    d["pos_sha"] = np.frombuffer(__import__("hashlib").sha256(d["pos"].tobytes()).digest(), np.uint8)
+    d["n_tris"] = d["pos"].shape[0]
+    del d["pos"], d["nrm"], d["mesh_id"]
+    np.savez_compressed(path, **d)
+
+
+if __name__ == "__main__":
+    main()

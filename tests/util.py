@@ -1,0 +1,59 @@
+"""Shared helpers of the test-suite: golden fixture loading and comparison metrics."""
+import hashlib
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+GOLDEN_NAMES = ["cornell_c1_256", "cornell_c4_96", "cornell_sph10_aa_80x48", "cornell_ms16_70x45", "cornell_inside_128", "monkey_192",
+                "cube_96", "tr_def_96", "teapot_c2_256x144", "teapot_d3_128x72", "dragon_standin_c3_160x90"]
+
+
+class Golden:
+    def __init__(self, name):
+        import rtb200
+        d = np.load(os.path.join(GOLDEN, name + ".npz"))
+        self.name = name
+        self.d = d
+        self.w, self.h = int(d["width"]), int(d["height"])
+        self.max_level, self.sphere_rays = int(d["max_level"]), int(d["sphere_rays"])
+        self.sample_mode, self.sample_size = int(d["sample_mode"]), int(d["sample_size"])
+        self.rgb, self.ids, self.t = d["rgb"], d["ids"], d["t"]
+        self.counts = (int(d["primary_rays"]), int(d["shadow_queries"]), int(d["secondary_rays"]))
+        self.cam_kw = dict(look_at=tuple(float(v) for v in d["cam_look_at"]), euler_deg=tuple(float(v) for v in d["cam_euler_deg"]),
+                           dist=float(d["cam_dist"]), fovy_deg=float(d["cam_fovy_deg"]))
+        self.geometry_ok = True
+        if "pos" in d:
+            self.scene = rtb200.SceneData(d["pos"], d["nrm"], d["mesh_id"], d["mats"], d["point_lights"], d["sphere_lights"])
+        else:  # dragon stand-in: geometry is regenerated, the fixture only carries a checksum
+            from rtb200 import standin
+            sc = standin.dragon_standin_scene()
+            sc.mats = d["mats"]
+            sc.point_lights, sc.sphere_lights = d["point_lights"], d["sphere_lights"]
+            self.scene = sc
+            self.geometry_ok = hashlib.sha256(np.ascontiguousarray(sc.pos).tobytes()).digest() == bytes(d["pos_sha"])
+
+    def camera(self):
+        import rtb200
+        return rtb200.make_camera(**self.cam_kw)
+
+    def params(self, exhaustive=False):
+        import rtb200
+        return rtb200.make_params(self.w, self.h, self.max_level, self.sphere_rays, 0.8, self.sample_mode, self.sample_size, exhaustive)
+
+    def oracle_render(self, kind="port", **kw):
+        import oracle
+        o = oracle.Oracle(kind)
+        s = self.scene
+        return o.render(s.pos, s.nrm, s.mesh_id, s.mats, s.point_lights, s.sphere_lights, self.camera(), self.w, self.h, max_level=self.max_level,
+                        sphere_rays=self.sphere_rays, sample_mode=self.sample_mode, sample_size=self.sample_size, **kw)
+
+
+def id_mismatch_fraction(a, b):
+    return float(np.mean(a != b))
+
+
+def bits_equal(a, b):
+    return bool(np.array_equal(np.ascontiguousarray(a).view(np.int32), np.ascontiguousarray(b).view(np.int32)))
