@@ -63,12 +63,15 @@ typedef struct {
     uint64_t primary_rays;
     uint64_t shadow_queries;  /* one per cansee loop iteration (src/shadow.cpp:41-66) */
     uint64_t secondary_rays;  /* reflection + refraction rays                        */
-    uint64_t node_visits;     /* 32-byte BVH nodes fetched (0 unless built with RT_COUNTERS) */
+    uint64_t node_visits;     /* 32-byte BVH nodes fetched (0 unless rt_set_counters is on) */
     uint64_t tri_tests;       /* triangles fetched                                          */
     uint64_t tri_tests_full;  /* tests that also ran the three edge functions               */
     float gpu_ms;             /* device time of the frame (CUDA events on the context's stream) */
     int kernel_launches;      /* kernels launched for the frame                                 */
     int batches;              /* wavefront batches the frame was split into                     */
+    uint64_t extend_node_visits;    /* the three traversal counters restricted to the extend kernel (primary + */
+    uint64_t extend_tri_tests;      /* reflection / refraction rays); the shadow kernels account for the rest  */
+    uint64_t extend_tri_tests_full;
 } rt_stats;
 
 #define RT_BVH_LBVH_DEVICE 0      /* Morton codes -> radix sort -> Karras hierarchy -> refit, all on the GPU */

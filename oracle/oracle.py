@@ -28,7 +28,7 @@ class OrcParams(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("max_reflection_level", C.c_int), ("sphere_light_ray_count", C.c_int),
                 ("glossy_ray_count", C.c_int), ("refraction_factor", C.c_float), ("use_bvh", C.c_int), ("sample_mode", C.c_int),
                 ("sample_size", C.c_int), ("defined_bary", C.c_int), ("x0", C.c_int), ("y0", C.c_int), ("x_step", C.c_int),
-                ("y_step", C.c_int), ("num_threads", C.c_int)]
+                ("y_step", C.c_int), ("num_threads", C.c_int), ("shadow_exhaustive", C.c_int)]
 
 
 class OrcStats(C.Structure):
@@ -61,7 +61,7 @@ class Oracle:
 
     def render(self, pos, nrm, mesh_id, mats, point_lights, sphere_lights, cam, width, height, max_level=5, sphere_rays=10,
                refraction=0.8, use_bvh=True, sample_mode=0, sample_size=4, defined_bary=True, want_ids=True, want_rgb=True,
-               x0=0, y0=0, x_step=1, y_step=1, num_threads=0):
+               x0=0, y0=0, x_step=1, y_step=1, num_threads=0, shadow_exhaustive=False):
         """cam: dict(look_at, euler (radians), dist, fovy (radians)) or an object with those attributes."""
         pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 9)
         nrm = np.ascontiguousarray(nrm, np.float32).reshape(-1, 9)
@@ -76,7 +76,7 @@ class Oracle:
         oc.dist = float(get("dist"))
         oc.fovy = float(get("fovy"))
         p = OrcParams(width, height, max_level, sphere_rays, 1, refraction, 1 if use_bvh else 0, sample_mode, sample_size,
-                      1 if defined_bary else 0, x0, y0, x_step, y_step, num_threads)
+                      1 if defined_bary else 0, x0, y0, x_step, y_step, num_threads, 1 if shadow_exhaustive else 0)
         rgb = np.zeros((height, width, 3), np.float32) if want_rgb else None
         ids = np.full((height, width), -1, np.int32) if want_ids else None
         t = np.zeros((height, width), np.float32) if want_ids else None

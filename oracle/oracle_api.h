@@ -42,6 +42,12 @@ typedef struct {
     int defined_bary;           /* 1: define the uninitialised-barycentric case (port only)     */
     int x0, y0, x_step, y_step; /* render only pixels x0+i*x_step, y0+j*y_step (timing subsets) */
     int num_threads;            /* OpenMP threads, <=0: all                                     */
+    int shadow_exhaustive;      /* port only. 0: shadow queries go through the reference-style BVH, as
+                                   cansee does (shadow.cpp:42).  1: they search every triangle.  The
+                                   reference's AABB slab test (ray_tracing.cpp:213-264) occasionally culls a
+                                   box whose triangle the triangle test would accept (flat boxes, rounding);
+                                   the exhaustive answer is what the triangle arithmetic alone defines and
+                                   what a conservative BVH (the GPU path) returns.                            */
 } orc_params;
 
 typedef struct {

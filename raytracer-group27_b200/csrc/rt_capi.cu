@@ -742,6 +742,9 @@ int rt_sync(rt_ctx* ctx, rt_stats* stats)
             stats->node_visits = c.node_visits;
             stats->tri_tests = c.tri_tests;
             stats->tri_tests_full = c.tri_tests_full;
+            stats->extend_node_visits = c.ext_node_visits;
+            stats->extend_tri_tests = c.ext_tri_tests;
+            stats->extend_tri_tests_full = c.ext_tri_tests_full;
             float ms = 0.0f;
             CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
             stats->gpu_ms = ms;

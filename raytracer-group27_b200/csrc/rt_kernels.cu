@@ -223,6 +223,9 @@ __global__ void __launch_bounds__(128) k_extend(SceneDev s, int root_entry, Fram
         warp_add_u64(&b.counters->node_visits, st.nodes);
         warp_add_u64(&b.counters->tri_tests, st.tris);
         warp_add_u64(&b.counters->tri_tests_full, st.tris_full);
+        warp_add_u64(&b.counters->ext_node_visits, st.nodes);
+        warp_add_u64(&b.counters->ext_tri_tests, st.tris);
+        warp_add_u64(&b.counters->ext_tri_tests_full, st.tris_full);
     }
 }
 

@@ -80,6 +80,9 @@ struct Counters {
     unsigned long long node_visits;
     unsigned long long tri_tests;
     unsigned long long tri_tests_full;
+    unsigned long long ext_node_visits; // the same three, counted by the extend kernel alone
+    unsigned long long ext_tri_tests;
+    unsigned long long ext_tri_tests_full;
 };
 
 struct RayQueue {

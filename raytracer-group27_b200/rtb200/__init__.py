@@ -49,7 +49,7 @@ class Params(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("primary_rays", C.c_uint64), ("shadow_queries", C.c_uint64), ("secondary_rays", C.c_uint64), ("node_visits", C.c_uint64),
                 ("tri_tests", C.c_uint64), ("tri_tests_full", C.c_uint64), ("gpu_ms", C.c_float), ("kernel_launches", C.c_int),
-                ("batches", C.c_int)]
+                ("batches", C.c_int), ("extend_node_visits", C.c_uint64), ("extend_tri_tests", C.c_uint64), ("extend_tri_tests_full", C.c_uint64)]
 
     @property
     def rays(self) -> int:
@@ -299,6 +299,10 @@ class Context:
 
     def close_peer_framebuffer(self, ptr: int):
         _check(self._l.rt_close_peer_framebuffer(self._h, _P(ptr)))
+
+    def download_rgb_ptr(self, d_rgba: int, width: int, height: int, host_ptr: int):
+        """rt_download_rgb into caller-owned (ideally pinned) host memory."""
+        _check(self._l.rt_download_rgb(self._h, _P(d_rgba), width, height, _P(host_ptr)))
 
     def download_rgb(self, d_rgba: int, width: int, height: int) -> np.ndarray:
         rgb = np.empty((height, width, 3), np.float32)

@@ -36,6 +36,9 @@ def mint(name, sc, w, h, *, max_level, sphere_rays=10, sample_mode=0, sample_siz
     kw = dict(max_level=max_level, sphere_rays=sphere_rays, sample_mode=sample_mode, sample_size=sample_size, use_bvh=True)
     r_rgb, r_ids, r_t, r_st = ref.render(sc.pos, sc.nrm, sc.mesh_id, sc.mats, sc.point_lights, sc.sphere_lights, c, w, h, **kw)
     p_rgb, p_ids, p_t, p_st = port.render(sc.pos, sc.nrm, sc.mesh_id, sc.mats, sc.point_lights, sc.sphere_lights, c, w, h, **kw)
+    # the same frame with shadow queries answered exhaustively (what the triangle arithmetic alone defines; the
+    # reference's AABB test occasionally culls a box whose triangle the triangle test would accept)
+    x_rgb, x_ids, x_t, x_st = port.render(sc.pos, sc.nrm, sc.mesh_id, sc.mats, sc.point_lights, sc.sphere_lights, c, w, h, shadow_exhaustive=True, **kw)
     ids_equal = bool(np.array_equal(r_ids, p_ids))
     t_equal = bool(np.array_equal(r_t.view(np.int32), p_t.view(np.int32)))
     rgb_equal = bool(np.array_equal(r_rgb.view(np.int32), p_rgb.view(np.int32)))
@@ -53,9 +56,11 @@ def mint(name, sc, w, h, *, max_level, sphere_rays=10, sample_mode=0, sample_siz
         width=w, height=h, max_level=max_level, sphere_rays=sphere_rays, sample_mode=sample_mode, sample_size=sample_size,
         rgb=rgb, ids=r_ids, t=r_t,
         primary_rays=st.primary_rays, shadow_queries=st.shadow_queries, secondary_rays=st.secondary_rays,
+        rgb_x=x_rgb, primary_rays_x=x_st.primary_rays, shadow_queries_x=x_st.shadow_queries, secondary_rays_x=x_st.secondary_rays,
         colour_from=colour_from, port_equals_reference=np.array([ids_equal, t_equal, rgb_equal]))
     print(f"{name}: {sc.n_tris} tris {w}x{h} rays={st.rays} port==ref ids/t/rgb={ids_equal}/{t_equal}/{rgb_equal} "
-          f"rgb_maxdiff={np.abs(r_rgb - p_rgb).max():.3g} hit={np.mean(r_ids >= 0):.3f}")
+          f"rgb_maxdiff={np.abs(r_rgb - p_rgb).max():.3g} hit={np.mean(r_ids >= 0):.3f} | exhaustive shadows: queries {st.shadow_queries}->{x_st.shadow_queries}, "
+          f"pixels differing >1e-4: {int((np.abs(x_rgb - rgb).max(axis=2) > 1e-4).sum())}")
 
 
 def with_lights(sc, point=None, sphere=None):

@@ -17,16 +17,20 @@ ID_BUDGET = 1e-4       # north_star: <= 0.01 % of pixels may differ (edge / vert
 
 
 def _check_against_golden(g, rgb, ids, t, st, what):
-    frac = id_mismatch_fraction(ids, g.ids)
-    assert frac <= ID_BUDGET, f"{what}: {frac * 100:.4f}% of closest-hit ids differ"
-    same = ids == g.ids
-    assert bits_equal(t[same], g.t[same]), f"{what}: t differs on pixels with matching ids"
-    err = np.abs(rgb - g.rgb)
-    # pixels whose primary id differs (tie flips) are excluded from the colour bar and counted above
-    bad = (err.max(axis=2) > COLOUR_TOL) & same
-    assert bad.sum() <= max(1, int(ID_BUDGET * same.size)), f"{what}: {bad.sum()} pixels exceed {COLOUR_TOL} (max err {err[same].max():.3g})"
-    if frac == 0 and bad.sum() == 0:
-        assert (st.primary_rays, st.shadow_queries, st.secondary_rays) == g.counts, f"{what}: ray counts {st.primary_rays, st.shadow_queries, st.secondary_rays} != {g.counts}"
+    # (1) closest-hit ids and t of the primary rays against the reference's own triangle code: bit-exact
+    assert np.array_equal(ids, g.ids), f"{what}: {id_mismatch_fraction(ids, g.ids) * 100:.4f}% of closest-hit ids differ"
+    assert bits_equal(t, g.t), f"{what}: t differs"
+    # (2) colour and ray counts against the oracle with exhaustively answered shadow queries — the semantics a
+    #     conservative BVH has: every pixel within 1e-4, counts identical
+    err_x = np.abs(rgb - g.rgb_x).max(axis=2)
+    assert err_x.max() <= COLOUR_TOL, f"{what}: {(err_x > COLOUR_TOL).sum()} pixels exceed {COLOUR_TOL} vs exhaustive-shadow oracle (max {err_x.max():.3g})"
+    got = (st.primary_rays, st.shadow_queries, st.secondary_rays)
+    assert got == g.counts_x, f"{what}: ray counts {got} != {g.counts_x}"
+    # (3) colour against the reference as it runs (its cansee goes through its own 5-level BVH, whose slab test now
+    #     and then culls a triangle its triangle test would accept): at most 0.01 % of pixels may differ
+    err = np.abs(rgb - g.rgb).max(axis=2)
+    n_bad = int((err > COLOUR_TOL).sum())
+    assert n_bad <= max(1, int(ID_BUDGET * err.size)), f"{what}: {n_bad} pixels exceed {COLOUR_TOL} vs the reference (max {err.max():.3g})"
 
 
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
@@ -57,7 +61,7 @@ def test_dragon_live_oracle(rtb, gpu_ctx):
     cam = rtb.make_camera()
     w, h = 96, 54
     o = oracle.Oracle("port")
-    o_rgb, o_ids, o_t, o_st = o.render(sc.pos, sc.nrm, sc.mesh_id, sc.mats, sc.point_lights, None, cam, w, h, max_level=3)
+    o_rgb, o_ids, o_t, o_st = o.render(sc.pos, sc.nrm, sc.mesh_id, sc.mats, sc.point_lights, None, cam, w, h, max_level=3, shadow_exhaustive=True)
     for mode in (rtb.BVH_LBVH_DEVICE, rtb.BVH_SAH_HOST):
         gpu_ctx.upload_scene(sc, mode)
         rgb, ids, t, st = gpu_ctx.render(cam, rtb.make_params(w, h, 3), want_ids=True)
@@ -76,15 +80,21 @@ def test_intersect_matches_oracle(rtb, gpu_ctx):
     o = rng.normal(size=(n, 3)).astype(np.float32)
     o = 2.5 * o / np.linalg.norm(o, axis=1, keepdims=True)
     target = rng.uniform(-0.6, 0.6, size=(n, 3)).astype(np.float32)
-    d = target - o  # deliberately NOT normalised: t is measured along normalize(d), the hit point uses d
-    rays = np.concatenate([o, d], 1).astype(np.float32)
-    o_ids, o_t = oracle.Oracle("port").closest_hit(g.scene.pos, g.scene.nrm, g.scene.mesh_id, rays, use_bvh=False)
-    for mode in (rtb.BVH_LBVH_DEVICE, rtb.BVH_SAH_HOST):
-        gpu_ctx.upload_scene(g.scene, mode)
-        for use_bvh in (True, False):
-            ids, t = gpu_ctx.intersect(rays, use_bvh)
-            assert np.array_equal(ids, o_ids), f"mode {mode} bvh {use_bvh}: {(ids != o_ids).sum()} ids differ"
-            assert bits_equal(t, o_t)
+    d = target - o
+    unit = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    # Unit directions (|d| = 1 +- ulp, like every ray the renderer makes): BVH and exhaustive search agree with the
+    # oracle.  Un-normalised directions: the reference measures t along normalize(d) but evaluates the hit point
+    # with d itself (ray_tracing.cpp:65,111), so its answer is only reproducible by exhaustive search.
+    for dirs, bvh_modes in ((unit, (True, False)), (d.astype(np.float32), (False,))):
+        rays = np.concatenate([o, dirs], 1).astype(np.float32)
+        o_ids, o_t = oracle.Oracle("port").closest_hit(g.scene.pos, g.scene.nrm, g.scene.mesh_id, rays, use_bvh=False)
+        assert (o_ids >= 0).sum() > 1000
+        for mode in (rtb.BVH_LBVH_DEVICE, rtb.BVH_SAH_HOST):
+            gpu_ctx.upload_scene(g.scene, mode)
+            for use_bvh in bvh_modes:
+                ids, t = gpu_ctx.intersect(rays, use_bvh)
+                assert np.array_equal(ids, o_ids), f"mode {mode} bvh {use_bvh}: {(ids != o_ids).sum()} ids differ"
+                assert bits_equal(t, o_t)
 
 
 def test_full_size_bvh_equals_exhaustive(rtb, gpu_ctx):
@@ -101,7 +111,7 @@ def test_full_size_bvh_equals_exhaustive(rtb, gpu_ctx):
     # downsampled consistency with the 256x256 golden: every 4th pixel corner coincides with a golden pixel corner
     # (pixel x of the 1024 frame has ndc x/1024*2-1 == (x/4)/256*2-1 for x % 4 == 0)
     sub_ids = a[1][3::4, 0::4]  # rows are flipped: row (H-1-y); y % 4 == 0 <=> row index % 4 == 3
-    assert id_mismatch_fraction(sub_ids, g.ids) <= ID_BUDGET
+    assert np.array_equal(sub_ids, g.ids)
 
 
 def test_batched_frame_equals_single_batch(rtb, gpu_ctx):
@@ -140,7 +150,7 @@ def test_sharded_tiles_compose(rtb, gpu_ctx):
     finally:
         gpu_ctx.set_shard(0, 1)
     assert np.abs(acc - full).max() <= 1e-6
-    assert rays == sum(g.counts)
+    assert rays == sum(g.counts_x)
 
 
 def test_errors_are_loud(rtb, gpu_ctx):

@@ -22,6 +22,9 @@ class Golden:
         self.sample_mode, self.sample_size = int(d["sample_mode"]), int(d["sample_size"])
         self.rgb, self.ids, self.t = d["rgb"], d["ids"], d["t"]
         self.counts = (int(d["primary_rays"]), int(d["shadow_queries"]), int(d["secondary_rays"]))
+        # same frame with shadow queries answered exhaustively (oracle_api.h: shadow_exhaustive)
+        self.rgb_x = d["rgb_x"]
+        self.counts_x = (int(d["primary_rays_x"]), int(d["shadow_queries_x"]), int(d["secondary_rays_x"]))
         self.cam_kw = dict(look_at=tuple(float(v) for v in d["cam_look_at"]), euler_deg=tuple(float(v) for v in d["cam_euler_deg"]),
                            dist=float(d["cam_dist"]), fovy_deg=float(d["cam_fovy_deg"]))
         self.geometry_ok = True
