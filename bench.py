@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 ray-tracing path (contract: see the task brief / DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c1|c2|c4]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One step = one frame of the workload (generate -> extend/shade/shadow per bounce -> resolve, plus the tile gather at
+N > 1).  Default workload = BASELINE.json configs[2], the config the metric is quoted on: dragon.obj 3840x2160, one
+point light with hard shadows, reflection depth 3 — on the seeded procedural STAND-IN mesh, because the reference's
+data/dragon.obj is absent (labelled in `data` and `config`).  Rank 0 prints ONE JSON line.
+
+--impl reference times the reference's own CPU implementation of the path (oracle/_ref: its translation units
+compiled verbatim; falls back to the restated port if that library is absent) on the host cores, on a bounded
+strided sample of the same frame.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "raytracer-group27_b200"))
+
+METRIC = "Mrays/s (all ray types), dragon.obj 4K"
+UNIT = "Mrays/s"
+
+WORKLOADS = {
+    # name: (description, width, height, max_level, sphere_rays)
+    "c3": ("dragon.obj (procedural STAND-IN, 86 880 tris) 3840x2160, 1 point light hard shadows, reflection depth 3, 1 spp", 3840, 2160, 3, 10),
+    "c1": ("CornellBox-Mirror-Rotated.obj 1024x1024, 1 point light, hard shadows, reflection depth 3, 1 spp", 1024, 1024, 3, 10),
+    "c2": ("teapot.obj 1920x1080 Phong + hard shadows (depth 0)", 1920, 1080, 0, 10),
+    "c4": ("CornellBox-Mirror-Rotated.obj 2048x2048 spherical-light soft shadows, 64 samples per hit, depth 5", 2048, 2048, 5, 64),
+}
+
+
+def load_workload(name):
+    import rtb200
+    from rtb200 import standin
+    desc, w, h, depth, srays = WORKLOADS[name]
+    if name == "c3":
+        sc = standin.dragon_standin_scene()
+    else:  # geometry of the reference's assets travels inside the golden fixtures (tests/golden/make_golden.py)
+        fixture = {"c1": "cornell_c1_256", "c2": "teapot_c2_256x144", "c4": "cornell_c4_96"}[name]
+        d = np.load(os.path.join(ROOT, "tests", "golden", fixture + ".npz"))
+        sc = rtb200.SceneData(d["pos"], d["nrm"], d["mesh_id"], d["mats"], d["point_lights"], d["sphere_lights"])
+    return desc, sc, rtb200.make_camera(), rtb200.make_params(w, h, depth, srays)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons of one GPU while the timed region runs (NVML, 50 ms period)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.05)
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if one has been summarised."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_reference_sample(sc, cam, prm, target_seconds, threads=0, stride=None):
+    """Time the reference's CPU path on a strided pixel subset of the same frame (all host threads by default)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    kind = "reference" if oracle.available("reference") else "port"
+    o = oracle.Oracle(kind)
+
+    def run(step):
+        _, _, _, st = o.render(sc.pos, sc.nrm, sc.mesh_id, sc.mats, sc.point_lights, sc.sphere_lights, cam, prm.width, prm.height,
+                               max_level=prm.max_reflection_level, sphere_rays=prm.sphere_light_ray_count, use_bvh=True, want_ids=False,
+                               want_rgb=False, x_step=step, y_step=step, num_threads=threads)
+        return st
+    step = stride
+    if step is None:
+        # calibrate on a very sparse subset, then pick the stride that lands near the target time
+        probe_step = max(8, int(round((prm.width * prm.height / 2500.0) ** 0.5)))
+        st = run(probe_step)
+        rate = st.rays / max(st.seconds, 1e-6)
+        rays_per_px = st.rays / max(1, ((prm.width + probe_step - 1) // probe_step) * ((prm.height + probe_step - 1) // probe_step))
+        want_px = max(256.0, target_seconds * rate / max(rays_per_px, 1e-9))
+        step = max(1, int((prm.width * prm.height / want_px) ** 0.5))
+        st = run(step)
+        if st.seconds < 0.5 * target_seconds and step > 1:  # the sparse probe under-estimates the rate: refine once
+            step = max(1, int(step * (st.seconds / target_seconds) ** 0.5))
+    st = run(step)
+    nx, ny = (prm.width + step - 1) // step, (prm.height + step - 1) // step
+    info = {"value": st.rays / st.seconds / 1e6, "unit": UNIT, "cores": int(st.threads), "kind": kind,
+            "sample": f"every {step}th pixel in x and y of the {prm.width}x{prm.height} frame ({nx}x{ny} = {nx * ny} primary rays, {st.rays} rays, "
+                      f"{st.seconds:.2f} s; useBVH=true, glossy_ray_count=1)",
+            "seconds": st.seconds, "rays": int(st.rays), "stride": step}
+    return info
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    desc, sc, cam, prm = load_workload(args.workload)
+    # each step is a bounded sample (about 3 s of CPU work) so K + W steps end within a few minutes
+    infos = []
+    stride = None
+    for i in range(args.warmup + args.steps):
+        info = cpu_reference_sample(sc, cam, prm, target_seconds=3.0, stride=stride)
+        stride = info["stride"]  # calibrated once, then the same subset every step
+        if i >= args.warmup:
+            infos.append(info)
+    rays = sum(i["rays"] for i in infos)
+    secs = sum(i["seconds"] for i in infos)
+    value = rays / secs / 1e6
+    last = infos[-1]
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * secs / len(infos), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (procedural dragon stand-in; data/dragon.obj is absent from the reference tree)" if args.workload == "c3" else "reference asset",
+            "config": {"workload": desc, "sample": last["sample"]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import rtb200
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    desc, sc, cam, prm = load_workload(args.workload)
+    W, H = prm.width, prm.height
+    stream = torch.cuda.Stream()
+    ctx = rtb200.Context(local_rank)
+    ctx.set_stream(stream.cuda_stream)
+    bvh_mode = rtb200.BVH_SAH_HOST if args.bvh == "sah" else rtb200.BVH_LBVH_DEVICE
+    t0 = time.perf_counter()
+    ctx.upload_scene(sc, bvh_mode)
+    build_ms = 1e3 * (time.perf_counter() - t0)
+    ctx.set_shard(rank, world)
+
+    # ---- gather target: rank 0's framebuffer, peer-mapped into the other ranks (stores fused into resolve) ----
+    gather = "none (single GPU)"
+    target = None  # None: the context's own framebuffer
+    fb0 = None
+    if world > 1:
+        gather = "peer_store"
+        handle = [ctx.framebuffer_ipc_handle(W, H) if rank == 0 else None]
+        dist.broadcast_object_list(handle, src=0)
+        ok = torch.ones(1, device="cuda")
+        if rank != 0:
+            try:
+                target = ctx.open_peer_framebuffer(handle[0])
+            except Exception as e:  # IPC unavailable (e.g. no shared IPC namespace): fall back to an NCCL reduction
+                ok.zero_()
+                sys.stderr.write(f"[rank {rank}] peer mapping failed ({e}); falling back to NCCL gather\n")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            gather = "nccl_reduce"
+            target = None
+
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def frame():
+        ctx.render_device(cam, prm, target)
+
+    gathered = torch.empty(W * H * 4, dtype=torch.float32, device="cuda") if world > 1 else None
+
+    def nccl_gather():
+        # fallback gather: non-owned pixels of every rank's framebuffer stay zero, so a sum to rank 0 is the gather
+        ptr, _, _ = ctx.framebuffer()
+        gathered.copy_(_as_tensor(torch, ptr, W * H * 4))
+        dist.reduce(gathered, dst=0, op=dist.ReduceOp.SUM)
+
+    def finish_step():
+        if world > 1 and gather == "nccl_reduce":
+            nccl_gather()
+        st = ctx.sync()
+        if world > 1:
+            dist.barrier()
+        return st
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            frame()
+            finish_step()
+        # ---- timed region: K frames, device time per frame from CUDA events on the launching stream ----
+        sampler = ClockSampler(local_rank)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler.start()
+        wall0 = time.perf_counter()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        stats = []
+        for k in range(args.steps):
+            flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+            ev[k][0].record(stream)
+            frame()
+            if world > 1 and gather == "nccl_reduce":
+                nccl_gather()
+            ev[k][1].record(stream)
+            st = ctx.sync()
+            if world > 1:
+                dist.barrier()
+            stats.append(st)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        wall_ms = 1e3 * (time.perf_counter() - wall0)
+        clocks = sampler.finish()
+    step_ms = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device="cuda")
+    rays = torch.tensor([float(s.rays) for s in stats], dtype=torch.float64, device="cuda")
+    launches = sum(s.kernel_launches for s in stats)
+    if world > 1:
+        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rays, op=dist.ReduceOp.SUM)
+    total_ms = float(step_ms.sum().item())
+    total_rays = float(rays.sum().item())
+    value = total_rays / total_ms / 1e3  # Mrays/s
+
+    # ---- end to end through the reference-facing call: host buffers, copies inside the timed region ----
+    pinned = torch.empty(H * W * 3, dtype=torch.float32).pin_memory()
+    h2d_bytes = sc.mats.nbytes + sc.point_lights.nbytes + sc.sphere_lights.nbytes + 32 + 36  # materials + lights + camera + params
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        ctx.set_materials(sc.mats)                      # the reference re-reads materials and lights every frame
+        ctx.set_lights(sc.point_lights, sc.sphere_lights)
+        if world == 1:
+            return ctx.render_host_ptr(cam, prm, pinned.data_ptr())
+        ctx.render_device(cam, prm, target)
+        st = finish_step()
+        if rank == 0:
+            ptr = gathered.data_ptr() if gather == "nccl_reduce" else ctx.framebuffer()[0]
+            ctx.download_rgb_ptr(ptr, W, H, pinned.data_ptr())
+        return st
+    for _ in range(2):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0 = time.perf_counter()
+    e_rays = 0.0
+    for _ in range(e2e_steps):
+        e_rays += e2e_step().rays
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e_ms = torch.tensor([1e3 * (time.perf_counter() - e0)], dtype=torch.float64, device="cuda")
+    e_r = torch.tensor([e_rays], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e_r, op=dist.ReduceOp.SUM)
+    e2e_value = float(e_r.item()) / float(e_ms.item()) / 1e3
+
+    # ---- roofline of the dominant kernel (separate, untimed passes: stage events, then instrumented counters) ----
+    ctx.set_stage_timing(True)
+    stage_ms = {}
+    for _ in range(3):
+        flush.zero_()
+        frame()
+        finish_step()
+        for k, (ms, n) in ctx.stage_times().items():
+            stage_ms.setdefault(k, []).append((ms, n))
+    ctx.set_stage_timing(False)
+    stage = {k: (float(np.median([m for m, _ in v])), v[0][1]) for k, v in stage_ms.items()}
+    ctx.set_counters(True)
+    frame()
+    c = finish_step()
+    ctx.set_counters(False)
+    roof = roofline(stage, c, prm)
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_reference_sample(sc, cam, prm, target_seconds=15.0)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        st = stats[-1]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (procedural dragon stand-in; data/dragon.obj is absent from the reference tree)" if args.workload == "c3" else "reference asset (from tests/golden)",
+            "config": {"workload": desc, "bvh": args.bvh, "bvh_build_ms": build_ms, "sharding": f"interleaved 32x16 tiles over {world} GPU(s), scene replicated",
+                       "gather": gather, "l2": "flushed between timed steps (512 MiB memset outside the event pair)",
+                       "rays_per_frame": {"primary": int(st.primary_rays), "shadow": int(st.shadow_queries), "secondary": int(st.secondary_rays)} if world == 1 else int(total_rays / args.steps)},
+            "clocks": clocks, "wall_ms_per_step_incl_flush_and_sync": wall_ms / args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(W * H * 3 * 4), "steps": e2e_steps,
+                    "ms_per_step": float(e_ms.item()) / e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        if target:
+            ctx.close_peer_framebuffer(target)
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def _as_tensor(torch, ptr, n_floats):
+    """View raw device memory owned by the C library as a torch tensor (for NCCL plumbing only)."""
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (int(ptr), False), "version": 3}
+    return torch.as_tensor(h, device="cuda")
+
+
+def roofline(stage, c, prm):
+    """Roofline of the dominant kernel.  Algorithmic bytes per ray follow SURVEY §8(d): 32 B per BVH node fetched +
+    64 B per triangle fetched + the ray's own record traffic; flops per ray: 24 per box test, 12 per plane stage,
+    57 per full triangle stage (+ fixed part).  Node / triangle counts are measured by the instrumented kernels."""
+    peak, peak_src = measured_peaks()
+    ext_rays = c.primary_rays + c.secondary_rays
+    sh_rays = c.shadow_queries
+    sh_nodes, sh_tris, sh_full = c.node_visits - c.extend_node_visits, c.tri_tests - c.extend_tri_tests, c.tri_tests_full - c.extend_tri_tests_full
+    kernels = {
+        "extend": dict(ms=stage["extend"][0], launches=stage["extend"][1], rays=ext_rays,
+                       bytes=c.extend_node_visits * 32 + c.extend_tri_tests * 64 + ext_rays * (32 + 8),
+                       flops=c.extend_node_visits * 24 + c.extend_tri_tests * 12 + c.extend_tri_tests_full * 57 + ext_rays * 20),
+        "shadow_point": dict(ms=stage["shadow_point"][0], launches=stage["shadow_point"][1], rays=sh_rays,
+                             bytes=sh_nodes * 32 + sh_tris * 64 + sh_rays * (48 + 12),
+                             flops=sh_nodes * 24 + sh_tris * 12 + sh_full * 57 + sh_rays * 30),
+    }
+    if stage.get("shadow_sphere", (0, 0))[1]:
+        kernels["shadow_sphere"] = dict(kernels.pop("shadow_point"), ms=stage["shadow_sphere"][0], launches=stage["shadow_sphere"][1])
+    name = max(kernels, key=lambda k: kernels[k]["ms"])
+    k = kernels[name]
+    total_ms = sum(v[0] for v in stage.values())
+    achieved = k["bytes"] / max(k["ms"], 1e-9) / 1e6  # GB/s
+    traffic = ncu_traffic().get(name)
+    fp32_nominal = 148 * 128 * 1.965e9  # FP32 instructions/s (non-FMA path: one flop per instruction)
+    return {"bound": "hbm", "kernel": "k_" + name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "peak_source": peak_src, "launches_per_step": k["launches"], "avg_launch_ms": k["ms"] / max(1, k["launches"]),
+            "algorithmic_bytes_per_launch": k["bytes"] / max(1, k["launches"]), "share_of_step": k["ms"] / max(total_ms, 1e-9),
+            "per_ray": {"nodes": (c.node_visits / max(1, c.rays)), "tris": c.tri_tests / max(1, c.rays), "tris_full": c.tri_tests_full / max(1, c.rays)},
+            "stage_ms": {s: round(v[0], 4) for s, v in stage.items()},
+            "fp32": {"achieved_gflops": k["flops"] / max(k["ms"], 1e-9) / 1e6, "nominal_peak_ginst": fp32_nominal / 1e9,
+                     "frac_of_nominal_issue": (k["flops"] / max(k["ms"], 1e-9) * 1e3) / fp32_nominal,
+                     "note": "scene (BVH + triangles ~ 11 MB) is L2-resident: the path is FP32-issue / latency / divergence bound, the HBM fraction is reported as required"}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--bvh", default="sah", choices=["sah", "lbvh"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps == 20 and "--steps" not in " ".join(sys.argv):
+            args.steps = 3
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,18 @@
+"""Minimal single-GPU driver for ncu: uploads the C3 stand-in scene and renders a few frames (no counters, no CPU work)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "raytracer-group27_b200"))
+import rtb200  # noqa: E402
+from rtb200 import standin  # noqa: E402
+
+frames = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+mode = rtb200.BVH_SAH_HOST if (len(sys.argv) < 3 or sys.argv[2] == "sah") else rtb200.BVH_LBVH_DEVICE
+ctx = rtb200.Context(0)
+ctx.upload_scene(standin.dragon_standin_scene(), mode)
+cam, prm = rtb200.make_camera(), rtb200.make_params(3840, 2160, 3)
+for _ in range(frames):
+    ctx.render_device(cam, prm)
+    st = ctx.sync()
+print(f"{frames} frames, last {st.gpu_ms:.3f} ms, {st.rays} rays, {st.rays / st.gpu_ms / 1e3:.1f} Mrays/s")
