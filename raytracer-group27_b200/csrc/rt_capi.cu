@@ -88,6 +88,7 @@ struct rt_ctx {
     unsigned batch_rays = 1u << 24;
     DevBuf<float4> q_o[2], q_d[2], q_w[2], sp_p, sp_a, sp_b, ss_p, ss_a, ss_b, accum, fb;
     DevBuf<int2> q_hit[2];
+    DevBuf<float2> sphere_acc;
     DevBuf<Counters> counters;
     DevBuf<int> prim_id, out_id;
     DevBuf<float> prim_t, out_t, rgb;
@@ -269,7 +270,9 @@ int ensure_batch(rt_ctx* ctx, const FrameParams& fp, unsigned batch_pixels, bool
         CK(ctx->ss_p.ensure(cap_sp));
         CK(ctx->ss_a.ensure(cap_sp));
         CK(ctx->ss_b.ensure(cap_sp));
+        CK(ctx->sphere_acc.ensure(cap_sp));
     }
+    b.sphere_acc = ctx->sphere_acc.p;
     b.sq_point = ShadowQueue { ctx->sp_p.p, ctx->sp_a.p, ctx->sp_b.p };
     b.sq_sphere = ShadowQueue { ctx->ss_p.p, ctx->ss_a.p, ctx->ss_b.p };
     b.ray_capacity = (unsigned)std::min<size_t>(cap, 0xfffffff0u);
@@ -337,22 +340,28 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids
         CK(cudaMemsetAsync(ctx->accum.p, 0, n_local * sizeof(float4), st));
     for (size_t first = 0; first < n_local; first += batch_pixels) {
         const unsigned n_lp = (unsigned)std::min<size_t>(batch_pixels, n_local - first);
-        launch_level_reset(st, b.counters, 0, 1);
-        {
-            StageScope sc(ctx, RT_STAGE_GENERATE);
-            launch_generate(st, ctx->sm_count, fp, b, (unsigned)first, n_lp, 0);
+        // primary rays of this batch: pixels of its tiles that lie inside the image, times samples per pixel
+        unsigned long long n_primary = 0;
+        for (size_t j = first / kTilePixels; j < (first + n_lp) / kTilePixels; j++) {
+            const long long g = (long long)fp.rank + (long long)j * fp.world;
+            const int tx = (int)(g % fp.tiles_x), ty = (int)(g / fp.tiles_x);
+            n_primary += (unsigned long long)std::min(kTileW, fp.W - tx * kTileW) * std::min(kTileH, fp.H - ty * kTileH);
         }
-        launches += 2;
+        n_primary *= (unsigned long long)fp.spp;
         for (int level = 0; level <= fp.max_level; level++) {
             const int qi = level & 1;
-            launch_level_reset(st, b.counters, qi ^ 1, 0);
+            // level 0 has no stored ray queue: K1 generate is fused into extend / shade (rays are a function of the index)
+            if (level == 0)
+                launch_level_reset(st, b.counters, 1, (long long)n_lp * fp.spp, n_primary);
+            else
+                launch_level_reset(st, b.counters, qi ^ 1, -1, 0);
             {
                 StageScope sc(ctx, RT_STAGE_EXTEND);
-                launch_extend(st, ctx->sm_count, s, ctx->root_entry, fp, b, qi, level, ctx->counters_enabled);
+                launch_extend(st, ctx->sm_count, s, ctx->root_entry, fp, b, qi, level, (unsigned)first, ctx->counters_enabled);
             }
             {
                 StageScope sc(ctx, RT_STAGE_SHADE);
-                launch_shade(st, ctx->sm_count, s, fp, b, qi, level);
+                launch_shade(st, ctx->sm_count, s, fp, b, qi, level, (unsigned)first);
             }
             launches += 3;
             if (fp.n_point > 0) {
@@ -363,7 +372,7 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids
             if (fp.n_sphere > 0) {
                 StageScope sc(ctx, RT_STAGE_SHADOW_SPHERE);
                 launch_shadow_sphere(st, ctx->sm_count, s, ctx->root_entry, fp, b, ctx->counters_enabled);
-                launches++;
+                launches += 2;
             }
         }
         batches++;
@@ -455,6 +464,7 @@ int rt_destroy(rt_ctx* ctx)
     ctx->prim_t.release();
     ctx->out_t.release();
     ctx->rgb.release();
+    ctx->sphere_acc.release();
     ctx->rays_in.release();
     ctx->flag.release();
     if (ctx->lbvh_nodes)

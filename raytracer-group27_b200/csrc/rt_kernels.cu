@@ -1,6 +1,6 @@
-// Wavefront kernels of the per-pixel hot path (sm_100a): K0 tri_setup, K1 generate, K2 extend, K3 shade,
-// K4 shadow (point / spherical light), K5 resolve.  See DESIGN.md for the data flow; every kernel cites the
-// reference lines it replaces.
+// Wavefront kernels of the per-pixel hot path (sm_100a): K0 tri_setup, K1 generate (fused into the level-0 extend),
+// K2 extend, K3 shade, K4 shadow (point / spherical light), K5 resolve.  See DESIGN.md for the data flow; every
+// kernel cites the reference lines it replaces.
 #include "rt_kernels.h"
 #include "rt_trace.cuh"
 
@@ -9,39 +9,10 @@ namespace rtb {
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kRefillThreshold = 20;   // traversal loops yield when fewer lanes than this are still busy
+constexpr int kShadeBlock = 256;
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
-
-// Warp-aggregated dynamic work fetch: one atomicAdd per warp hands out 32 consecutive items.
-__device__ __forceinline__ unsigned warp_fetch(unsigned* cursor)
-{
-    unsigned base = 0;
-    if (lane_id() == 0)
-        base = atomicAdd(cursor, 32u);
-    return __shfl_sync(kFull, base, 0);
-}
-
-// Warp-ballot compaction: lanes with `want` get consecutive slots of a queue; one atomicAdd per warp.
-// Must be called by all 32 lanes.  Returns the slot or 0xffffffff (not wanted / queue full -> overflow flagged).
-__device__ __forceinline__ unsigned warp_alloc(unsigned* counter, bool want, unsigned capacity, unsigned* overflow)
-{
-    const unsigned mask = __ballot_sync(kFull, want);
-    if (mask == 0)
-        return 0xffffffffu;
-    const int leader = __ffs(mask) - 1;
-    unsigned base = 0;
-    if (lane_id() == leader)
-        base = atomicAdd(counter, (unsigned)__popc(mask));
-    base = __shfl_sync(kFull, base, leader);
-    if (!want)
-        return 0xffffffffu;
-    const unsigned slot = base + __popc(mask & ((1u << lane_id()) - 1u));
-    if (slot >= capacity) {
-        atomicExch(overflow, 1u);
-        return 0xffffffffu;
-    }
-    return slot;
-}
 
 __device__ __forceinline__ void warp_add_u64(unsigned long long* dst, unsigned v)
 {
@@ -49,6 +20,75 @@ __device__ __forceinline__ void warp_add_u64(unsigned long long* dst, unsigned v
         v += __shfl_xor_sync(kFull, v, o);
     if (lane_id() == 0 && v)
         atomicAdd(dst, (unsigned long long)v);
+}
+
+// Persistent-warp work distribution with per-lane refill: every lane whose ray has finished gets the next unclaimed
+// item; one atomicAdd per warp per refill.  All 32 lanes must call this together.  Returns the item index for a
+// lane that needed one (0xffffffff if none was left); `more` becomes false once the queue is exhausted.
+__device__ __forceinline__ unsigned warp_refill(unsigned* cursor, unsigned n, bool need, bool& more)
+{
+    const unsigned idle = __ballot_sync(kFull, need);
+    unsigned item = 0xffffffffu;
+    if (idle && more) {
+        const int leader = __ffs(idle) - 1;
+        const unsigned cnt = (unsigned)__popc(idle);
+        unsigned base = 0;
+        if (lane_id() == leader)
+            base = atomicAdd(cursor, cnt);
+        base = __shfl_sync(kFull, base, leader);
+        if (need) {
+            const unsigned i = base + (unsigned)__popc(idle & ((1u << lane_id()) - 1u));
+            if (i < n)
+                item = i;
+        }
+        more = base + cnt < n;
+    }
+    return item;
+}
+
+// Block-aggregated queue allocation for NQ queues at once: every thread says whether it wants a slot in each queue;
+// one atomicAdd per queue per block.  Must be called by all threads of the block.  slot[q] = 0xffffffff when nothing
+// was requested or the queue is full (overflow flagged).
+template <int NQ>
+__device__ __forceinline__ void block_alloc(unsigned* const (&counter)[NQ], const bool (&want)[NQ], const unsigned (&capacity)[NQ],
+    unsigned* overflow, unsigned (&slot)[NQ], unsigned (*smem)[kShadeBlock / 32 + 1])
+{
+    const int warp = threadIdx.x >> 5, lane = lane_id(), nw = blockDim.x >> 5;
+    unsigned rank[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+        const unsigned m = __ballot_sync(kFull, want[q]);
+        rank[q] = (unsigned)__popc(m & ((1u << lane) - 1u));
+        if (lane == 0)
+            smem[q][warp] = (unsigned)__popc(m);
+    }
+    __syncthreads();
+    if (threadIdx.x < NQ) {
+        const int q = threadIdx.x;
+        unsigned total = 0;
+        for (int w = 0; w < nw; w++)
+            total += smem[q][w];
+        unsigned base = total ? atomicAdd(counter[q], total) : 0u;
+        for (int w = 0; w < nw; w++) {
+            const unsigned c = smem[q][w];
+            smem[q][w] = base;
+            base += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+        unsigned sl = 0xffffffffu;
+        if (want[q]) {
+            sl = smem[q][warp] + rank[q];
+            if (sl >= capacity[q]) {
+                atomicExch(overflow, 1u);
+                sl = 0xffffffffu;
+            }
+        }
+        slot[q] = sl;
+    }
+    __syncthreads();
 }
 
 // local padded pixel index -> pixel coordinates (tile interleaving across ranks, 8x4 warp blocks inside a tile)
@@ -60,6 +100,37 @@ __device__ __forceinline__ void local_to_pixel(const FrameParams& fp, unsigned l
     const unsigned w = k >> 5, l = k & 31;
     px = (int)(tx * kTileW + (w & 3) * 8 + (l & 7));
     py = (int)(ty * kTileH + (w >> 2) * 4 + (l >> 3));
+}
+
+// K1 generate: pixel -> NDC (src/main.cpp:350-353), sub-pixel sample positions (358-375 / 309-335, 377-385) and
+// Trackball::generateRay (framework/src/trackball.cpp:87-98) for primary ray `idx` of the batch starting at local
+// pixel first_lp.  Returns false for rays of padding pixels outside the image.  tag = (local pixel << 1) | first-sample.
+__device__ __forceinline__ bool generate_ray(const FrameParams& fp, unsigned first_lp, unsigned idx, f3& o, f3& dir, int& tag)
+{
+    const unsigned lp = first_lp + idx / (unsigned)fp.spp;
+    const int sidx = (int)(idx % (unsigned)fp.spp);
+    int px, py;
+    local_to_pixel(fp, lp, px, py);
+    if (px >= fp.W || py >= fp.H)
+        return false;
+    float nx = xsub(xmul(xdiv((float)px, (float)fp.W), 2.0f), 1.0f);
+    float ny = xsub(xmul(xdiv((float)py, (float)fp.H), 2.0f), 1.0f);
+    if (fp.sample_mode == 1) {
+        nx = (sidx & 1) ? xadd(nx, fp.aa_off_x) : xsub(nx, fp.aa_off_x);
+        ny = (sidx & 2) ? xsub(ny, fp.aa_off_y) : xadd(ny, fp.aa_off_y);
+    } else if (fp.sample_mode == 2) {
+        const int k = (fp.ms_moves + 1) / 2; // odd steps 1,3,.. <= moves
+        const int quad = sidx / (k * k), rem = sidx % (k * k);
+        const int sx = 1 + 2 * (rem / k), sy = 1 + 2 * (rem % k);
+        const float sgx = (quad & 1) ? 1.0f : -1.0f, sgy = (quad & 2) ? -1.0f : 1.0f;
+        nx = xadd(nx, xmul(xmul(fp.ms_off_x, sgx), (float)sx));
+        ny = xadd(ny, xmul(xmul(fp.ms_off_y, sgy), (float)sy));
+    }
+    const f3 cam = xnormalize(mk3(xmul(-nx, fp.halfW), xmul(ny, fp.halfH), 1.0f));
+    dir = xquat_rotate(mk3(fp.qx, fp.qy, fp.qz), fp.qw, cam);
+    o = mk3(fp.ox, fp.oy, fp.oz);
+    tag = (int)((lp << 1) | (sidx == 0 ? 1u : 0u));
+    return true;
 }
 
 struct Shading { // what shade and the transparent-shadow branch need at a hit
@@ -100,6 +171,14 @@ __device__ __forceinline__ double schlick(float R0, float c)
     return (double)R0 + (double)(1.0f - R0) * p5;
 }
 
+__device__ __forceinline__ void accumulate(float4* accum, int pix, float r, float g, float bl)
+{
+    float* acc = reinterpret_cast<float*>(&accum[pix]);
+    atomicAdd(acc + 0, r);
+    atomicAdd(acc + 1, g);
+    atomicAdd(acc + 2, bl);
+}
+
 } // namespace
 
 // ---------------------------------------------------------------------------------------------------------
@@ -127,98 +206,80 @@ __global__ void k_tri_setup(const float* __restrict__ pos, const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Reset of the per-level cursors / queue fills (one thread).
-__global__ void k_level_reset(Counters* c, int next_q, int clear_current)
+// Reset of the per-level cursors / queue fills (one thread).  n_current >= 0 sets the fill of the current queue
+// (level 0: the primary rays are generated on the fly, the queue only provides the hit slots).
+__global__ void k_level_reset(Counters* c, int next_q, long long n_current, unsigned long long add_primary)
 {
     c->work[0] = c->work[1] = c->work[2] = c->work[3] = 0;
     c->n_shadow_pt = 0;
     c->n_shadow_sp = 0;
     c->n_rays[next_q] = 0;
-    if (clear_current)
-        c->n_rays[next_q ^ 1] = 0;
+    if (n_current >= 0)
+        c->n_rays[next_q ^ 1] = (unsigned)n_current;
+    c->primary_rays += add_primary;
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K1 generate: pixel -> NDC (src/main.cpp:350-353), sub-pixel sample positions (358-375 / 309-335, 377-385) and
-// Trackball::generateRay (framework/src/trackball.cpp:87-98).  One thread per (pixel, sample) of the batch.
-__global__ void __launch_bounds__(256) k_generate(FrameParams fp, BatchDev b, unsigned first_lp, unsigned n_lp, int qi)
-{
-    const unsigned n = n_lp * (unsigned)fp.spp;
-    const unsigned n_round = (n + 31u) & ~31u;
-    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_round; idx += gridDim.x * blockDim.x) {
-        bool valid = idx < n;
-        unsigned lp = 0;
-        int px = 0, py = 0, sidx = 0;
-        if (valid) {
-            lp = first_lp + idx / (unsigned)fp.spp;
-            sidx = (int)(idx % (unsigned)fp.spp);
-            local_to_pixel(fp, lp, px, py);
-            valid = px < fp.W && py < fp.H;
-        }
-        f3 dir = mk3(0.f, 0.f, 0.f);
-        if (valid) {
-            float nx = xsub(xmul(xdiv((float)px, (float)fp.W), 2.0f), 1.0f);
-            float ny = xsub(xmul(xdiv((float)py, (float)fp.H), 2.0f), 1.0f);
-            if (fp.sample_mode == 1) {
-                nx = (sidx & 1) ? xadd(nx, fp.aa_off_x) : xsub(nx, fp.aa_off_x);
-                ny = (sidx & 2) ? xsub(ny, fp.aa_off_y) : xadd(ny, fp.aa_off_y);
-            } else if (fp.sample_mode == 2) {
-                const int k = (fp.ms_moves + 1) / 2; // odd steps 1,3,.. <= moves
-                const int quad = sidx / (k * k), rem = sidx % (k * k);
-                const int sx = 1 + 2 * (rem / k), sy = 1 + 2 * (rem % k);
-                const float sgx = (quad & 1) ? 1.0f : -1.0f, sgy = (quad & 2) ? -1.0f : 1.0f;
-                nx = xadd(nx, xmul(xmul(fp.ms_off_x, sgx), (float)sx));
-                ny = xadd(ny, xmul(xmul(fp.ms_off_y, sgy), (float)sy));
-            }
-            const f3 cam = xnormalize(mk3(xmul(-nx, fp.halfW), xmul(ny, fp.halfH), 1.0f));
-            dir = xquat_rotate(mk3(fp.qx, fp.qy, fp.qz), fp.qw, cam);
-        }
-        const unsigned slot = warp_alloc(&b.counters->n_rays[qi], valid, b.ray_capacity, &b.counters->overflow);
-        if (slot != 0xffffffffu) {
-            b.q[qi].o_pix[slot] = make_float4(fp.ox, fp.oy, fp.oz, __int_as_float((int)((lp << 1) | (sidx == 0 ? 1u : 0u))));
-            b.q[qi].d[slot] = make_float4(dir.x, dir.y, dir.z, 0.0f);
-            b.q[qi].w[slot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-        }
-        warp_add_u64(&b.counters->primary_rays, valid ? 1u : 0u);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// K2 extend: closest hit of every ray in queue qi (BoundingVolumeHierarchy::intersect,
-// src/bounding_volume_hierarchy.cpp:49-78).  Persistent warps pull 32 rays at a time.
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_extend(SceneDev s, int root_entry, FrameParams fp, BatchDev b, int qi, int level)
+// K2 extend: closest hit of every ray of the level (BoundingVolumeHierarchy::intersect,
+// src/bounding_volume_hierarchy.cpp:49-78).  Persistent warps; a lane whose ray is done immediately pulls the next
+// one (at level 0 it is generated from the pixel index: K1 fused).  Result: hit[i] = {bits(t), BVH-order triangle}.
+template <bool LEVEL0, bool COUNT>
+__global__ void __launch_bounds__(128) k_extend(SceneDev s, int root_entry, FrameParams fp, BatchDev b, int qi, unsigned first_lp)
 {
     const unsigned n = b.counters->n_rays[qi];
+    int stack[kStackDepth];
+    Trav tv;
+    tv.cur = kTravDone;
+    tv.ok = true;
     TraceStats st;
-    while (true) {
-        const unsigned base = warp_fetch(&b.counters->work[0]);
-        if (base >= n)
-            break;
-        const unsigned i = base + lane_id();
-        if (i < n) {
-            const float4 op = b.q[qi].o_pix[i];
-            const float4 dd = b.q[qi].d[i];
-            const f3 o = mk3(op), d = mk3(dd);
-            HitRec best = fresh_query();
-            bool ok = true;
-            if (fp.exhaustive)
-                trace_exhaustive<false, COUNT>(s, o, d, best, st);
-            else
-                ok = trace_bvh<false, COUNT>(s, root_entry, o, d, best, st);
-            if (!ok)
-                atomicExch(&b.counters->overflow, 2u);
-            b.q[qi].hit[i] = make_int2(__float_as_int(best.t), best.ti);
-            if (level == 0 && b.prim_id) {
-                const int tag = __float_as_int(op.w);
-                if (tag & 1) { // first sample of the pixel
-                    b.prim_id[tag >> 1] = best.ti >= 0 ? best.id : -1;
-                    b.prim_t[tag >> 1] = best.t;
+    bool active = false, more = true, ok = true;
+    unsigned my = 0;
+    int tag = 0;
+    for (;;) {
+        const unsigned item = warp_refill(&b.counters->work[0], n, !active, more);
+        if (item != 0xffffffffu) {
+            f3 o, d;
+            bool valid = true;
+            if (LEVEL0) {
+                valid = generate_ray(fp, first_lp, item, o, d, tag);
+            } else {
+                const float4 op = b.q[qi].o_pix[item];
+                const float4 dd = b.q[qi].d[item];
+                o = mk3(op);
+                d = mk3(dd);
+                tag = __float_as_int(op.w);
+            }
+            if (valid) {
+                my = item;
+                active = true;
+                trav_begin(tv, o, d, fresh_query(), root_entry);
+                if (fp.exhaustive) {
+                    trace_exhaustive<false, COUNT>(s, o, d, tv.best, st);
+                    tv.cur = kTravDone;
                 }
+            }
+        }
+        if (!__any_sync(kFull, active)) {
+            if (!more)
+                break;
+            continue;
+        }
+        if (active) {
+            trav_run<false, COUNT>(s, tv, stack, st, more ? kRefillThreshold : 0);
+            if (tv.cur == kTravDone) {
+                ok &= tv.ok;
+                b.q[qi].hit[my] = make_int2(__float_as_int(tv.best.t), tv.best.ti);
+                if (LEVEL0 && b.prim_id && (tag & 1)) { // first sample of the pixel
+                    b.prim_id[tag >> 1] = tv.best.ti >= 0 ? tv.best.id : -1;
+                    b.prim_t[tag >> 1] = tv.best.t;
+                }
+                active = false;
             }
         }
         __syncwarp();
     }
+    if (!ok)
+        atomicExch(&b.counters->overflow, 2u);
     if (COUNT) {
         warp_add_u64(&b.counters->node_visits, st.nodes);
         warp_add_u64(&b.counters->tri_tests, st.tris);
@@ -234,15 +295,16 @@ __global__ void __launch_bounds__(128) k_extend(SceneDev s, int root_entry, Fram
 // getSpherelights (src/shadow.cpp:106-131, 139-226: everything except the cansee calls), calcColor
 // (src/main.cpp:112-121) folded into per-light coefficients, and the spawn of mirror (191-256 with
 // glossy_ray_count == 1 => weight ks*ks) and dielectric (257-290) children with a throughput instead of recursion.
-__global__ void __launch_bounds__(128) k_shade(SceneDev s, FrameParams fp, BatchDev b, int qi, int level)
+// One thread per ray slot; output queues are filled through block-aggregated ballot compaction.
+template <bool LEVEL0>
+__global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams fp, BatchDev b, int qi, int level, unsigned first_lp)
 {
+    __shared__ unsigned smem[3][kShadeBlock / 32 + 1];
     const unsigned n = b.counters->n_rays[qi];
     const int qo = qi ^ 1;
-    while (true) {
-        const unsigned base = warp_fetch(&b.counters->work[1]);
-        if (base >= n)
-            break;
-        const unsigned i = base + lane_id();
+    const unsigned n_round = (n + kShadeBlock - 1) / kShadeBlock * kShadeBlock;
+    unsigned n_secondary = 0;
+    for (unsigned i = blockIdx.x * kShadeBlock + threadIdx.x; i < n_round; i += gridDim.x * kShadeBlock) {
         bool hit = false;
         int pix = 0;
         f3 w = mk3(0, 0, 0), refl = mk3(0, 0, 0), refr = mk3(0, 0, 0), dn = mk3(0, 0, 0), Nn = mk3(0, 0, 0);
@@ -252,15 +314,24 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev s, FrameParams fp, Batch
         sh.mesh = 0;
         float4 m0 = make_float4(0, 0, 0, 0), m1 = make_float4(0, 0, 0, 1);
         if (i < n) {
-            const int2 h = b.q[qi].hit[i];
+            f3 o, d;
+            int tag = 0;
+            bool valid = true;
+            if (LEVEL0)
+                valid = generate_ray(fp, first_lp, i, o, d, tag);
+            const int2 h = valid ? b.q[qi].hit[i] : make_int2(0, -1);
             if (h.y >= 0) {
                 hit = true;
-                const float4 op = b.q[qi].o_pix[i];
-                const float4 dd = b.q[qi].d[i];
-                const float4 ww = b.q[qi].w[i];
-                pix = __float_as_int(op.w) >> 1;
-                w = mk3(ww);
-                const f3 o = mk3(op), d = mk3(dd);
+                if (LEVEL0) {
+                    w = mk3(1.0f, 1.0f, 1.0f);
+                } else {
+                    const float4 op = b.q[qi].o_pix[i];
+                    o = mk3(op);
+                    d = mk3(b.q[qi].d[i]);
+                    w = mk3(b.q[qi].w[i]);
+                    tag = __float_as_int(op.w);
+                }
+                pix = tag >> 1;
                 sh = shading_at(s, h.y, o, d, __int_as_float(h.x));
                 dn = xnormalize(d);
                 Nn = xnormalize(sh.N);
@@ -271,34 +342,6 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev s, FrameParams fp, Batch
         }
         const f3 kd = mk3(m0), ks = mk3(m1);
         const float shininess = m0.w, transparency = m1.w;
-
-        // direct light: one record per light; the shadow kernels add A * intensity + B when the light is visible
-        const int n_lights = fp.n_point + fp.n_sphere;
-        for (int li = 0; li < n_lights; li++) {
-            const bool is_point = li < fp.n_point;
-            const float4* L = is_point ? (s.point_lights + 2 * li) : (s.sphere_lights + 2 * (li - fp.n_point));
-            f3 A = mk3(0, 0, 0), B = mk3(0, 0, 0);
-            if (hit) {
-                const f3 lp = mk3(__ldg(L)), lc = mk3(__ldg(L + 1));
-                const f3 ldir = xnormalize(xsub(lp, sh.p));
-                const float cosNL = fabsf(xdot(Nn, ldir));                         // shadow.cpp:125 / 218
-                const float cosRL = fmaxf(0.0f, xdot(xnormalize(refl), ldir));      // shadow.cpp:126 / 219
-                A = mk3(w.x * kd.x * lc.x * cosNL, w.y * kd.y * lc.y * cosNL, w.z * kd.z * lc.z * cosNL);
-                if (shininess > 0.0f) {
-                    const float sp = powf(cosRL, shininess);
-                    B = mk3(w.x * lc.x * ks.x * sp, w.y * lc.y * ks.y * sp, w.z * lc.z * ks.z * sp);
-                }
-            }
-            ShadowQueue& sq = is_point ? b.sq_point : b.sq_sphere;
-            unsigned* cnt = is_point ? &b.counters->n_shadow_pt : &b.counters->n_shadow_sp;
-            const unsigned cap = is_point ? b.shadow_pt_capacity : b.shadow_sp_capacity;
-            const unsigned slot = warp_alloc(cnt, hit, cap, &b.counters->overflow);
-            if (slot != 0xffffffffu) {
-                sq.p_pix[slot] = make_float4(sh.p.x, sh.p.y, sh.p.z, __int_as_float(pix));
-                sq.a_light[slot] = make_float4(A.x, A.y, A.z, __int_as_float(is_point ? li : li - fp.n_point));
-                sq.b[slot] = make_float4(B.x, B.y, B.z, 0.0f);
-            }
-        }
 
         // children
         bool want0 = false, want1 = false;
@@ -325,92 +368,168 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev s, FrameParams fp, Batch
                 }
             }
         }
-        unsigned slot = warp_alloc(&b.counters->n_rays[qo], want0, b.ray_capacity, &b.counters->overflow);
-        if (slot != 0xffffffffu) {
+        n_secondary += (want0 ? 1u : 0u) + (want1 ? 1u : 0u);
+
+        // one allocation round for: first child ray, point-light records (n_point per hit, contiguous), spherical-light
+        // records (n_sphere per hit); a second round for the refraction child (dielectric hits only)
+        unsigned* const counters[3] = { &b.counters->n_rays[qo], &b.counters->n_shadow_pt, &b.counters->n_shadow_sp };
+        const bool want[3] = { want0, hit && fp.n_point > 0, hit && fp.n_sphere > 0 };
+        const unsigned cap[3] = { b.ray_capacity, b.shadow_pt_capacity / (unsigned)max(fp.n_point, 1), b.shadow_sp_capacity / (unsigned)max(fp.n_sphere, 1) };
+        unsigned slot[3];
+        block_alloc<3>(counters, want, cap, &b.counters->overflow, slot, smem);
+        unsigned slot1 = 0xffffffffu;
+        if (fp.any_transparent) {
+            unsigned* const c1[1] = { &b.counters->n_rays[qo] };
+            const bool w1v[1] = { want1 };
+            const unsigned cap1[1] = { b.ray_capacity };
+            unsigned s1[1];
+            block_alloc<1>(c1, w1v, cap1, &b.counters->overflow, s1, smem);
+            slot1 = s1[0];
+        }
+        if (slot[0] != 0xffffffffu) {
             const f3 o2 = xadd(sh.p, xmul(refl, 0.01f)); // main.cpp:199,286
-            b.q[qo].o_pix[slot] = make_float4(o2.x, o2.y, o2.z, __int_as_float(pix << 1));
-            b.q[qo].d[slot] = make_float4(refl.x, refl.y, refl.z, 0.0f);
-            b.q[qo].w[slot] = make_float4(w0.x, w0.y, w0.z, 0.0f);
+            b.q[qo].o_pix[slot[0]] = make_float4(o2.x, o2.y, o2.z, __int_as_float(pix << 1));
+            b.q[qo].d[slot[0]] = make_float4(refl.x, refl.y, refl.z, 0.0f);
+            b.q[qo].w[slot[0]] = make_float4(w0.x, w0.y, w0.z, 0.0f);
         }
-        slot = warp_alloc(&b.counters->n_rays[qo], want1, b.ray_capacity, &b.counters->overflow);
-        if (slot != 0xffffffffu) {
+        if (slot1 != 0xffffffffu) {
             const f3 o2 = xadd(sh.p, xmul(refr, 0.01f)); // main.cpp:288
-            b.q[qo].o_pix[slot] = make_float4(o2.x, o2.y, o2.z, __int_as_float(pix << 1));
-            b.q[qo].d[slot] = make_float4(refr.x, refr.y, refr.z, 0.0f);
-            b.q[qo].w[slot] = make_float4(w1.x, w1.y, w1.z, 0.0f);
+            b.q[qo].o_pix[slot1] = make_float4(o2.x, o2.y, o2.z, __int_as_float(pix << 1));
+            b.q[qo].d[slot1] = make_float4(refr.x, refr.y, refr.z, 0.0f);
+            b.q[qo].w[slot1] = make_float4(w1.x, w1.y, w1.z, 0.0f);
         }
-        warp_add_u64(&b.counters->secondary_rays, (want0 ? 1u : 0u) + (want1 ? 1u : 0u));
+        // direct light: one record per (hit, light); the shadow kernels add A * intensity + B when the light is visible
+        if (hit) {
+            const int n_lights = fp.n_point + fp.n_sphere;
+            for (int li = 0; li < n_lights; li++) {
+                const bool is_point = li < fp.n_point;
+                const unsigned base = is_point ? slot[1] : slot[2];
+                if (base == 0xffffffffu)
+                    continue;
+                const int lj = is_point ? li : li - fp.n_point;
+                const float4* L = is_point ? (s.point_lights + 2 * lj) : (s.sphere_lights + 2 * lj);
+                const f3 lp = mk3(__ldg(L)), lc = mk3(__ldg(L + 1));
+                const f3 ldir = xnormalize(xsub(lp, sh.p));
+                const float cosNL = fabsf(xdot(Nn, ldir));                         // shadow.cpp:125 / 218
+                const float cosRL = fmaxf(0.0f, xdot(xnormalize(refl), ldir));      // shadow.cpp:126 / 219
+                const f3 A = mk3(w.x * kd.x * lc.x * cosNL, w.y * kd.y * lc.y * cosNL, w.z * kd.z * lc.z * cosNL);
+                f3 B = mk3(0, 0, 0);
+                if (shininess > 0.0f) {
+                    const float sp = powf(cosRL, shininess);
+                    B = mk3(w.x * lc.x * ks.x * sp, w.y * lc.y * ks.y * sp, w.z * lc.z * ks.z * sp);
+                }
+                const ShadowQueue& sq = is_point ? b.sq_point : b.sq_sphere;
+                const unsigned sl = base * (unsigned)(is_point ? fp.n_point : fp.n_sphere) + (unsigned)lj;
+                sq.p_pix[sl] = make_float4(sh.p.x, sh.p.y, sh.p.z, __int_as_float(pix));
+                sq.a_light[sl] = make_float4(A.x, A.y, A.z, __int_as_float(lj));
+                sq.b[sl] = make_float4(B.x, B.y, B.z, 0.0f);
+                if (!is_point)
+                    b.sphere_acc[sl] = make_float2(0.0f, 0.0f);
+            }
+        }
     }
+    warp_add_u64(&b.counters->secondary_rays, n_secondary);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// cansee (src/shadow.cpp:32-69): closest-hit loop from p1 towards p2 with transparent pass-through.  Returns
-// visibility; `intensity` is attenuated by every transparent surface crossed (also when finally blocked, which
-// getSpherelights relies on for its centre sample).  `queries` counts loop iterations.
-template <bool COUNT>
-__device__ __forceinline__ bool cansee(const SceneDev& s, int root_entry, const FrameParams& fp, const f3& p1, const f3& p2,
-    float& intensity, unsigned& queries, TraceStats& st, bool& ok)
+// cansee (src/shadow.cpp:32-69) as a per-lane state machine: closest-hit loop from p1 towards p2 with transparent
+// pass-through.  `intensity` is attenuated by every transparent surface crossed (also when finally blocked, which
+// getSpherelights relies on for its centre sample).
+struct CanSee {
+    f3 o, d;           // current segment origin, unit direction
+    float distance;
+    float intensity;
+};
+
+__device__ __forceinline__ bool cansee_begin(CanSee& cs, const f3& p1, const f3& p2)
 {
     f3 d = xsub(p2, p1);
-    float distance = xlength(d);
-    d = xnormalize(d);
-    f3 o = xadd(p1, xmul(d, 0.0005f));
-    while (distance > 0.0005f) {
-        queries++;
-        // blockers have t <= distance - 2*SHADOW_ERROR_OFFSET; anything farther means "visible" (shadow.cpp:44)
-        HitRec best = bounded_query(xsub(distance, 0.001f));
-        if (fp.exhaustive) {
-            if (fp.any_transparent)
-                trace_exhaustive<false, COUNT>(s, o, d, best, st);
-            else
-                trace_exhaustive<true, COUNT>(s, o, d, best, st);
-        } else {
-            // with opaque materials only, the first blocker found decides (any-hit); otherwise the closest one does
-            if (fp.any_transparent)
-                ok &= trace_bvh<false, COUNT>(s, root_entry, o, d, best, st);
-            else
-                ok &= trace_bvh<true, COUNT>(s, root_entry, o, d, best, st);
-        }
-        if (best.ti < 0)
-            return true;
-        if (!fp.any_transparent)
-            return false;
-        const Shading sh = shading_at(s, best.ti, o, d, best.t);
-        const float R0 = __ldg(&s.mats[2 * sh.mesh + 1]).w;
-        if (R0 == 1.0f)
-            return false;
-        distance = xsub(distance, best.t);                    // shadow.cpp:51
-        o = xadd(sh.p, xmul(d, 0.0005f));                      // shadow.cpp:53
-        const float c = fabsf(xdot(d, sh.N));                  // shadow.cpp:55 (normal not re-normalised)
-        intensity = (float)((double)intensity * (1.0 - schlick(R0, c)));
-    }
-    return true;
+    cs.distance = xlength(d);
+    cs.d = xnormalize(d);
+    cs.o = xadd(p1, xmul(cs.d, 0.0005f));
+    cs.intensity = 1.0f;
+    return cs.distance > 0.0005f; // false: the loop body never runs, the light is visible (shadow.cpp:41,67)
 }
 
-// K4a shadow rays to point lights (getPointLights' cansee call, src/shadow.cpp:120).
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_shadow_point(SceneDev s, int root_entry, FrameParams fp, BatchDev b)
+// Search bound of one loop iteration: blockers have t <= distance - 2*SHADOW_ERROR_OFFSET; a closest hit farther
+// than that means "visible" (shadow.cpp:44), so nothing beyond it needs to be found.
+__device__ __forceinline__ HitRec cansee_query(const CanSee& cs) { return bounded_query(xsub(cs.distance, 0.001f)); }
+
+// After a traversal finished with `best`: 0 = visible, 1 = blocked, 2 = passed a transparent surface, go on.
+__device__ __forceinline__ int cansee_step(const SceneDev& s, const FrameParams& fp, CanSee& cs, const HitRec& best)
 {
-    const unsigned n = b.counters->n_shadow_pt;
+    if (best.ti < 0)
+        return 0;
+    if (!fp.any_transparent)
+        return 1;
+    const Shading sh = shading_at(s, best.ti, cs.o, cs.d, best.t);
+    const float R0 = __ldg(&s.mats[2 * sh.mesh + 1]).w;
+    if (R0 == 1.0f)
+        return 1;
+    cs.distance = xsub(cs.distance, best.t);               // shadow.cpp:51
+    cs.o = xadd(sh.p, xmul(cs.d, 0.0005f));                // shadow.cpp:53
+    const float c = fabsf(xdot(cs.d, sh.N));                // shadow.cpp:55 (normal not re-normalised)
+    cs.intensity = (float)((double)cs.intensity * (1.0 - schlick(R0, c)));
+    return cs.distance > 0.0005f ? 2 : 0;
+}
+
+// Shared body of the two shadow kernels.  Work item j < n_items; item_begin(j, p1, p2) gives the segment to test,
+// item_end(j, visible, intensity) consumes the result.  Persistent warps with per-lane refill, like k_extend.
+template <bool COUNT, typename Begin, typename End>
+__device__ __forceinline__ void shadow_loop(const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, unsigned* cursor,
+    unsigned n_items, Begin item_begin, End item_end)
+{
+    int stack[kStackDepth];
+    Trav tv;
+    tv.cur = kTravDone;
+    tv.ok = true;
     TraceStats st;
-    unsigned queries = 0;
-    bool ok = true;
-    while (true) {
-        const unsigned base = warp_fetch(&b.counters->work[2]);
-        if (base >= n)
-            break;
-        const unsigned i = base + lane_id();
-        if (i < n) {
-            const float4 pp = b.sq_point.p_pix[i];
-            const float4 al = b.sq_point.a_light[i];
-            const f3 lp = mk3(__ldg(&s.point_lights[2 * __float_as_int(al.w)]));
-            float intensity = 1.0f;
-            if (cansee<COUNT>(s, root_entry, fp, mk3(pp), lp, intensity, queries, st, ok)) {
-                const float4 bb = b.sq_point.b[i];
-                float* acc = reinterpret_cast<float*>(&b.accum[__float_as_int(pp.w)]);
-                atomicAdd(acc + 0, al.x * intensity + bb.x);
-                atomicAdd(acc + 1, al.y * intensity + bb.y);
-                atomicAdd(acc + 2, al.z * intensity + bb.z);
+    CanSee cs;
+    bool active = false, more = true, ok = true;
+    unsigned my = 0, queries = 0;
+    for (;;) {
+        const unsigned item = warp_refill(cursor, n_items, !active, more);
+        if (item != 0xffffffffu) {
+            f3 p1, p2;
+            item_begin(item, p1, p2);
+            my = item;
+            if (cansee_begin(cs, p1, p2)) {
+                active = true;
+                queries++;
+                trav_begin(tv, cs.o, cs.d, cansee_query(cs), root_entry);
+            } else {
+                item_end(my, true, 1.0f);
+            }
+        }
+        if (!__any_sync(kFull, active)) {
+            if (!more)
+                break;
+            continue;
+        }
+        if (active) {
+            if (fp.exhaustive) { // reference useBVH=false semantics for tests: loop over every triangle
+                if (fp.any_transparent)
+                    trace_exhaustive<false, COUNT>(s, cs.o, cs.d, tv.best, st);
+                else
+                    trace_exhaustive<true, COUNT>(s, cs.o, cs.d, tv.best, st);
+                tv.cur = kTravDone;
+            } else if (fp.any_transparent) {
+                // a transparent blocker only attenuates: the closest hit decides what happens next
+                trav_run<false, COUNT>(s, tv, stack, st, more ? kRefillThreshold : 0);
+            } else {
+                // opaque materials only: the first blocker found decides (any-hit)
+                trav_run<true, COUNT>(s, tv, stack, st, more ? kRefillThreshold : 0);
+            }
+            if (tv.cur == kTravDone) {
+                ok &= tv.ok;
+                const int r = cansee_step(s, fp, cs, tv.best);
+                if (r == 2) {
+                    queries++;
+                    trav_begin(tv, cs.o, cs.d, cansee_query(cs), root_entry);
+                } else {
+                    item_end(my, r == 0, cs.intensity);
+                    active = false;
+                }
             }
         }
         __syncwarp();
@@ -425,34 +544,50 @@ __global__ void __launch_bounds__(128) k_shadow_point(SceneDev s, int root_entry
     }
 }
 
-// K4b spherical lights (getSpherelights, src/shadow.cpp:139-226): sl_group lanes share one (hit, light) record and
-// split its 1 + m*n samples; sample positions follow the reference's sequential `perp = rotate * perp`.
+// K4a shadow rays to point lights (getPointLights' cansee call, src/shadow.cpp:120).
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_shadow_point(SceneDev s, int root_entry, FrameParams fp, BatchDev b)
+{
+    const unsigned n = b.counters->n_shadow_pt * (unsigned)fp.n_point;
+    shadow_loop<COUNT>(
+        s, root_entry, fp, b, &b.counters->work[2], n,
+        [&](unsigned i, f3& p1, f3& p2) {
+            const float4 pp = b.sq_point.p_pix[i];
+            const float4 al = b.sq_point.a_light[i];
+            p1 = mk3(pp);
+            p2 = mk3(__ldg(&s.point_lights[2 * __float_as_int(al.w)]));
+        },
+        [&](unsigned i, bool visible, float intensity) {
+            if (!visible)
+                return;
+            const float4 pp = b.sq_point.p_pix[i];
+            const float4 al = b.sq_point.a_light[i];
+            const float4 bb = b.sq_point.b[i];
+            accumulate(b.accum, __float_as_int(pp.w), al.x * intensity + bb.x, al.y * intensity + bb.y, al.z * intensity + bb.z);
+        });
+}
+
+// K4b spherical lights (getSpherelights, src/shadow.cpp:139-226).  Work item = (record, sample): sample 0 is the
+// light centre, the others lie on rings of the disc facing the hit point; their positions follow the reference's
+// sequential `perp = rotate * perp`.  Per-record sums go to sphere_acc = {sum of intensities, visible count}.
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_shadow_sphere(SceneDev s, int root_entry, FrameParams fp, BatchDev b)
 {
-    const unsigned n = b.counters->n_shadow_sp;
-    const int G = fp.sl_group;             // lanes per record
-    const unsigned per_warp = 32u / (unsigned)G; // records per warp per fetch
-    TraceStats st;
-    unsigned queries = 0;
-    bool ok = true;
-    while (true) {
-        unsigned base = 0;
-        if (lane_id() == 0)
-            base = atomicAdd(&b.counters->work[3], per_warp);
-        base = __shfl_sync(kFull, base, 0);
-        if (base >= n)
-            break;
-        const unsigned i = base + (unsigned)lane_id() / (unsigned)G;
-        const int sub = lane_id() % G;
-        float sum = 0.0f;
-        int hits = 0;
-        float4 pp = make_float4(0, 0, 0, 0), al = make_float4(0, 0, 0, 0);
-        if (i < n) {
-            pp = b.sq_sphere.p_pix[i];
-            al = b.sq_sphere.a_light[i];
+    const unsigned rc = (unsigned)fp.sl_rc;
+    const unsigned n = b.counters->n_shadow_sp * (unsigned)fp.n_sphere * rc;
+    shadow_loop<COUNT>(
+        s, root_entry, fp, b, &b.counters->work[3], n,
+        [&](unsigned j, f3& p1, f3& p2) {
+            const unsigned rec = j / rc;
+            const int k = (int)(j % rc);
+            const float4 pp = b.sq_sphere.p_pix[rec];
+            const float4 al = b.sq_sphere.a_light[rec];
             const float4 L = __ldg(&s.sphere_lights[2 * __float_as_int(al.w)]);
             const f3 p = mk3(pp), lpos = mk3(L);
+            p1 = p;
+            p2 = lpos; // centre sample (shadow.cpp:148)
+            if (k == 0)
+                return;
             const float radius = L.w;
             f3 d = xnormalize(xsub(lpos, p)); // shadow.cpp:153-155
             f3 notd = d;                       // shadow.cpp:158-166
@@ -463,7 +598,7 @@ __global__ void __launch_bounds__(128) k_shadow_sphere(SceneDev s, int root_entr
                 notd.y = -d.z;
                 notd.z = d.y;
             }
-            const f3 perp0 = xmul(xnormalize(xcross(d, notd)), radius); // shadow.cpp:169
+            f3 perp = xmul(xnormalize(xcross(d, notd)), radius); // shadow.cpp:169
             // rotate = I + C*sin + (C*C)*(1-cos), C columns {0,dz,-dy},{-dz,0,dx},{dy,-dx,0} (shadow.cpp:134-137)
             const float C[3][3] = { { 0.0f, d.z, -d.y }, { -d.z, 0.0f, d.x }, { d.y, -d.x, 0.0f } }; // C[col][row]
             float R[3][3];
@@ -475,53 +610,41 @@ __global__ void __launch_bounds__(128) k_shadow_sphere(SceneDev s, int root_entr
                     const float ident = (col == row) ? 1.0f : 0.0f;
                     R[col][row] = xadd(xadd(ident, xmul(C[col][row], fp.sl_sin)), xmul(cc, fp.sl_omc));
                 }
-            for (int k = sub; k < fp.sl_rc; k += G) {
-                f3 target;
-                if (k == 0) {
-                    target = lpos; // centre sample (shadow.cpp:148)
-                } else {
-                    const int spoke = (k - 1) / fp.sl_m, ring = (k - 1) % fp.sl_m;
-                    f3 perp = perp0;
-                    for (int r = 0; r < spoke; r++) // perp = rotate * perp (shadow.cpp:207)
-                        perp = mk3(xadd(xadd(xmul(R[0][0], perp.x), xmul(R[1][0], perp.y)), xmul(R[2][0], perp.z)),
-                            xadd(xadd(xmul(R[0][1], perp.x), xmul(R[1][1], perp.y)), xmul(R[2][1], perp.z)),
-                            xadd(xadd(xmul(R[0][2], perp.x), xmul(R[1][2], perp.y)), xmul(R[2][2], perp.z)));
-                    const float frac = xdiv((float)(fp.sl_m - ring), (float)fp.sl_m); // (m-j)/(float)m
-                    target = xadd(lpos, xmul(perp, frac));
-                }
-                float intensity = 1.0f;
-                const bool vis = cansee<COUNT>(s, root_entry, fp, p, target, intensity, queries, st, ok);
-                if (k == 0) {
-                    sum += intensity; // intensitySum starts at 1 and carries the centre ray's attenuation (shadow.cpp:145-150)
-                    hits += vis ? 1 : 0;
-                } else if (vis) {
-                    sum += intensity;
-                    hits++;
-                }
-            }
-        }
-        // segmented reduction over the G lanes of a record
-        for (int o = G >> 1; o > 0; o >>= 1) {
-            sum += __shfl_xor_sync(kFull, sum, o);
-            hits += __shfl_xor_sync(kFull, hits, o);
-        }
-        if (i < n && sub == 0 && hits > 0) { // shadow.cpp:212-221
-            const float intensity = sum / (float)fp.sl_rc;
+            const int spoke = (k - 1) / fp.sl_m, ring = (k - 1) % fp.sl_m;
+            for (int r = 0; r < spoke; r++) // perp = rotate * perp (shadow.cpp:207)
+                perp = mk3(xadd(xadd(xmul(R[0][0], perp.x), xmul(R[1][0], perp.y)), xmul(R[2][0], perp.z)),
+                    xadd(xadd(xmul(R[0][1], perp.x), xmul(R[1][1], perp.y)), xmul(R[2][1], perp.z)),
+                    xadd(xadd(xmul(R[0][2], perp.x), xmul(R[1][2], perp.y)), xmul(R[2][2], perp.z)));
+            const float frac = xdiv((float)(fp.sl_m - ring), (float)fp.sl_m); // (m-j)/(float)m
+            p2 = xadd(lpos, xmul(perp, frac));
+        },
+        [&](unsigned j, bool visible, float intensity) {
+            const unsigned rec = j / rc;
+            const bool centre = (j % rc) == 0;
+            // intensitySum starts at 1 and carries the centre ray's attenuation even if that ray ends up blocked
+            // (shadow.cpp:145-150); ring samples count only when visible (shadow.cpp:201-204)
+            float* acc = reinterpret_cast<float*>(&b.sphere_acc[rec]);
+            if (visible || centre)
+                atomicAdd(acc, intensity);
+            if (visible)
+                atomicAdd(acc + 1, 1.0f);
+        });
+}
+
+// K4c: per spherical-light record, Lighting::intensity = intensitySum / rayCount if any sample saw the light
+// (shadow.cpp:212-221), then calcColor's A * intensity + B.
+__global__ void __launch_bounds__(256) k_sphere_finalize(FrameParams fp, BatchDev b)
+{
+    const unsigned n = b.counters->n_shadow_sp * (unsigned)fp.n_sphere;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float2 acc = b.sphere_acc[i];
+        if (acc.y > 0.0f) {
+            const float intensity = acc.x / (float)fp.sl_rc;
+            const float4 pp = b.sq_sphere.p_pix[i];
+            const float4 al = b.sq_sphere.a_light[i];
             const float4 bb = b.sq_sphere.b[i];
-            float* acc = reinterpret_cast<float*>(&b.accum[__float_as_int(pp.w)]);
-            atomicAdd(acc + 0, al.x * intensity + bb.x);
-            atomicAdd(acc + 1, al.y * intensity + bb.y);
-            atomicAdd(acc + 2, al.z * intensity + bb.z);
+            accumulate(b.accum, __float_as_int(pp.w), al.x * intensity + bb.x, al.y * intensity + bb.y, al.z * intensity + bb.z);
         }
-        __syncwarp();
-    }
-    if (!ok)
-        atomicExch(&b.counters->overflow, 2u);
-    warp_add_u64(&b.counters->shadow_queries, queries);
-    if (COUNT) {
-        warp_add_u64(&b.counters->node_visits, st.nodes);
-        warp_add_u64(&b.counters->tri_tests, st.tris);
-        warp_add_u64(&b.counters->tri_tests_full, st.tris_full);
     }
 }
 
@@ -618,30 +741,34 @@ void launch_tri_setup(cudaStream_t st, const float* pos, const float* nrm, const
     k_tri_setup<<<(n + 255) / 256, 256, 0, st>>>(pos, nrm, mesh_id, perm, n, plane, v0, v1, v2, n0, n1, n2);
 }
 
-void launch_level_reset(cudaStream_t st, Counters* c, int next_q, int clear_current)
+void launch_level_reset(cudaStream_t st, Counters* c, int next_q, long long n_current, unsigned long long add_primary)
 {
-    k_level_reset<<<1, 1, 0, st>>>(c, next_q, clear_current);
-}
-
-void launch_generate(cudaStream_t st, int sm_count, const FrameParams& fp, const BatchDev& b, unsigned first_lp, unsigned n_lp, int qi)
-{
-    const long long n = (long long)n_lp * fp.spp;
-    k_generate<<<grid_for(n, 256, sm_count * 8), 256, 0, st>>>(fp, b, first_lp, n_lp, qi);
+    k_level_reset<<<1, 1, 0, st>>>(c, next_q, n_current, add_primary);
 }
 
 void launch_extend(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, int qi,
-    int level, bool count)
+    int level, unsigned first_lp, bool count)
 {
     const int grid = sm_count * 8;
-    if (count)
-        k_extend<true><<<grid, 128, 0, st>>>(s, root_entry, fp, b, qi, level);
-    else
-        k_extend<false><<<grid, 128, 0, st>>>(s, root_entry, fp, b, qi, level);
+    if (level == 0) {
+        if (count)
+            k_extend<true, true><<<grid, 128, 0, st>>>(s, root_entry, fp, b, qi, first_lp);
+        else
+            k_extend<true, false><<<grid, 128, 0, st>>>(s, root_entry, fp, b, qi, first_lp);
+    } else {
+        if (count)
+            k_extend<false, true><<<grid, 128, 0, st>>>(s, root_entry, fp, b, qi, first_lp);
+        else
+            k_extend<false, false><<<grid, 128, 0, st>>>(s, root_entry, fp, b, qi, first_lp);
+    }
 }
 
-void launch_shade(cudaStream_t st, int sm_count, const SceneDev& s, const FrameParams& fp, const BatchDev& b, int qi, int level)
+void launch_shade(cudaStream_t st, int sm_count, const SceneDev& s, const FrameParams& fp, const BatchDev& b, int qi, int level, unsigned first_lp)
 {
-    k_shade<<<sm_count * 8, 128, 0, st>>>(s, fp, b, qi, level);
+    if (level == 0)
+        k_shade<true><<<sm_count * 8, kShadeBlock, 0, st>>>(s, fp, b, qi, level, first_lp);
+    else
+        k_shade<false><<<sm_count * 4, kShadeBlock, 0, st>>>(s, fp, b, qi, level, first_lp);
 }
 
 void launch_shadow_point(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count)
@@ -660,6 +787,7 @@ void launch_shadow_sphere(cudaStream_t st, int sm_count, const SceneDev& s, int 
         k_shadow_sphere<true><<<grid, 128, 0, st>>>(s, root_entry, fp, b);
     else
         k_shadow_sphere<false><<<grid, 128, 0, st>>>(s, root_entry, fp, b);
+    k_sphere_finalize<<<sm_count * 4, 256, 0, st>>>(fp, b);
 }
 
 void launch_resolve(cudaStream_t st, int sm_count, const FrameParams& fp, const float4* accum, const int* prim_id, const float* prim_t,

@@ -11,11 +11,13 @@
 // (t, global triangle id); a traversal in any order reproduces that with the tie rule below.  Box tests only have
 // to be conservative (never cull a triangle the reference would accept): boxes are padded at build time and the
 // slab comparison carries a rounding guard; the reference's own box test is not reproduced (its result never
-// changes which triangle wins).
+// changes which triangle wins).  The BVH assumes |direction| = 1 up to rounding, which holds
+// for every ray the renderer creates; for other rays only the exhaustive search reproduces the reference.
 #pragma once
 #include "rt_math.cuh"
 #include "rt_types.h"
 #include <cfloat>
+#include <climits>
 
 namespace rtb {
 
@@ -85,38 +87,68 @@ __device__ __forceinline__ void trace_exhaustive(const SceneDev& s, const f3& o,
     }
 }
 
-// BVH traversal.  Stack entries: >= 0 -> index of a sibling pair to fetch; < 0 -> ~((first << 3) | (count - 1)).
-// Returns false if the traversal stack overflowed (builders keep the depth below kStackDepth).
-template <bool ANYHIT, bool COUNT>
-__device__ __forceinline__ bool trace_bvh(const SceneDev& s, int root_entry, const f3& o, const f3& d, HitRec& best, TraceStats& st)
+// ---- resumable BVH traversal -------------------------------------------------------------------------------
+// Stack entries: >= 0 -> node index of a sibling pair to fetch; < 0 -> ~((first << 3) | (count - 1)), a leaf.
+constexpr int kTravDone = INT_MIN; // not a valid leaf encoding (triangle count is limited to 2^28 - 2)
+
+struct Trav {
+    f3 o, d, dn;            // ray as stored, and normalize(d)
+    float ix, iy, iz;       // 1 / dn
+    float oix, oiy, oiz;    // o * (1 / dn): slabs are evaluated as fma(box, 1/dn, -o/dn)
+    HitRec best;
+    float tlimit;
+    int cur;                // current entry, kTravDone when the traversal is complete
+    int sp;
+    bool ok;                // false if the stack overflowed
+};
+
+__device__ __forceinline__ void trav_begin(Trav& tv, const f3& o, const f3& d, const HitRec& query, int root_entry)
 {
-    const f3 dn = xnormalize(d);
-    const float ix = 1.0f / dn.x, iy = 1.0f / dn.y, iz = 1.0f / dn.z;
-    float tlimit = prune_limit(best.t);
-    int stack[kStackDepth];
-    int sp = 0;
-    int cur = root_entry;
-    bool ok = true;
-    while (true) {
-        if (cur >= 0) {
-            const float4* np = s.nodes + 2 * (size_t)cur;
+    tv.o = o;
+    tv.d = d;
+    tv.dn = xnormalize(d);
+    // Reciprocal direction, clamped to +-1e30: with an infinite reciprocal (axis-parallel ray) the fused form
+    // box * inf - o * inf is NaN and loses on which side of the origin the slab plane lies; with 1e30 the FMA is exact
+    // before rounding, so the signs survive and the slab covers every finite t when the origin is inside it.
+    tv.ix = fabsf(tv.dn.x) > 1e-30f ? 1.0f / tv.dn.x : copysignf(1e30f, tv.dn.x);
+    tv.iy = fabsf(tv.dn.y) > 1e-30f ? 1.0f / tv.dn.y : copysignf(1e30f, tv.dn.y);
+    tv.iz = fabsf(tv.dn.z) > 1e-30f ? 1.0f / tv.dn.z : copysignf(1e30f, tv.dn.z);
+    tv.oix = o.x * tv.ix;
+    tv.oiy = o.y * tv.iy;
+    tv.oiz = o.z * tv.iz;
+    tv.best = query;
+    tv.tlimit = prune_limit(query.t);
+    tv.cur = root_entry;
+    tv.sp = 0;
+    tv.ok = true;
+}
+
+// Advance the traversal ("while-while": run through inner nodes until a leaf is reached, then test the leaf).
+// Returns when the traversal is complete (tv.cur == kTravDone) or — if min_active > 0 — as soon as fewer than
+// min_active lanes of the warp are still inside this loop, so that the caller can hand new rays to the idle lanes.
+template <bool ANYHIT, bool COUNT>
+__device__ __forceinline__ void trav_run(const SceneDev& s, Trav& tv, int* stack, TraceStats& st, int min_active)
+{
+    while (tv.cur != kTravDone) {
+        while (tv.cur >= 0) {
+            const float4* np = s.nodes + 2 * (size_t)tv.cur;
             const float4 a0 = __ldg(np), a1 = __ldg(np + 1), b0 = __ldg(np + 2), b1 = __ldg(np + 3);
             if (COUNT)
                 st.nodes += 2;
-            // slabs; fminf/fmaxf drop NaNs (0 * inf), which only widens the interval
+            // slabs; fminf/fmaxf drop NaNs (inf - inf for axis-parallel rays), which only widens the interval
             float t0, t1;
-            t0 = (a0.x - o.x) * ix; t1 = (a1.x - o.x) * ix;
+            t0 = fmaf(a0.x, tv.ix, -tv.oix); t1 = fmaf(a1.x, tv.ix, -tv.oix);
             float amin = fminf(t0, t1), amax = fmaxf(t0, t1);
-            t0 = (a0.y - o.y) * iy; t1 = (a1.y - o.y) * iy;
+            t0 = fmaf(a0.y, tv.iy, -tv.oiy); t1 = fmaf(a1.y, tv.iy, -tv.oiy);
             amin = fmaxf(amin, fminf(t0, t1)); amax = fminf(amax, fmaxf(t0, t1));
-            t0 = (a0.z - o.z) * iz; t1 = (a1.z - o.z) * iz;
-            amin = fmaxf(fmaxf(amin, fminf(t0, t1)), 0.0f); amax = fminf(fminf(amax, fmaxf(t0, t1)), tlimit);
-            t0 = (b0.x - o.x) * ix; t1 = (b1.x - o.x) * ix;
+            t0 = fmaf(a0.z, tv.iz, -tv.oiz); t1 = fmaf(a1.z, tv.iz, -tv.oiz);
+            amin = fmaxf(fmaxf(amin, fminf(t0, t1)), 0.0f); amax = fminf(fminf(amax, fmaxf(t0, t1)), tv.tlimit);
+            t0 = fmaf(b0.x, tv.ix, -tv.oix); t1 = fmaf(b1.x, tv.ix, -tv.oix);
             float bmin = fminf(t0, t1), bmax = fmaxf(t0, t1);
-            t0 = (b0.y - o.y) * iy; t1 = (b1.y - o.y) * iy;
+            t0 = fmaf(b0.y, tv.iy, -tv.oiy); t1 = fmaf(b1.y, tv.iy, -tv.oiy);
             bmin = fmaxf(bmin, fminf(t0, t1)); bmax = fminf(bmax, fmaxf(t0, t1));
-            t0 = (b0.z - o.z) * iz; t1 = (b1.z - o.z) * iz;
-            bmin = fmaxf(fmaxf(bmin, fminf(t0, t1)), 0.0f); bmax = fminf(fminf(bmax, fmaxf(t0, t1)), tlimit);
+            t0 = fmaf(b0.z, tv.iz, -tv.oiz); t1 = fmaf(b1.z, tv.iz, -tv.oiz);
+            bmin = fmaxf(fmaxf(bmin, fminf(t0, t1)), 0.0f); bmax = fminf(fminf(bmax, fmaxf(t0, t1)), tv.tlimit);
             const bool hitA = amin <= amax * 1.0000005f;
             const bool hitB = bmin <= bmax * 1.0000005f;
             const int ca = __float_as_int(a1.w), cb = __float_as_int(b1.w);
@@ -124,39 +156,47 @@ __device__ __forceinline__ bool trace_bvh(const SceneDev& s, int root_entry, con
             const int eb = cb ? ~((__float_as_int(b0.w) << 3) | (cb - 1)) : __float_as_int(b0.w);
             if (hitA && hitB) {
                 const bool aFirst = amin <= bmin;
-                const int nearE = aFirst ? ea : eb, farE = aFirst ? eb : ea;
-                if (sp < kStackDepth)
-                    stack[sp++] = farE;
+                if (tv.sp < kStackDepth)
+                    stack[tv.sp++] = aFirst ? eb : ea;
                 else
-                    ok = false;
-                cur = nearE;
-                continue;
+                    tv.ok = false;
+                tv.cur = aFirst ? ea : eb;
+            } else if (hitA) {
+                tv.cur = ea;
+            } else if (hitB) {
+                tv.cur = eb;
+            } else {
+                tv.cur = tv.sp ? stack[--tv.sp] : kTravDone;
             }
-            if (hitA) {
-                cur = ea;
-                continue;
-            }
-            if (hitB) {
-                cur = eb;
-                continue;
-            }
-        } else {
-            const int enc = ~cur;
+        }
+        if (tv.cur != kTravDone) {
+            const int enc = ~tv.cur;
             const int first = enc >> 3, count = (enc & 7) + 1;
             bool any = false;
             for (int i = 0; i < count; i++)
-                any |= test_triangle<COUNT>(s, first + i, o, d, dn, best, st);
+                any |= test_triangle<COUNT>(s, first + i, tv.o, tv.d, tv.dn, tv.best, st);
+            tv.cur = tv.sp ? stack[--tv.sp] : kTravDone;
             if (any) {
                 if (ANYHIT)
-                    return ok;
-                tlimit = prune_limit(best.t);
+                    tv.cur = kTravDone;
+                tv.tlimit = prune_limit(tv.best.t);
             }
         }
-        if (sp == 0)
+        if (min_active > 0 && __popc(__activemask()) < min_active)
             break;
-        cur = stack[--sp];
     }
-    return ok;
+}
+
+// One-shot traversal (no refill): used by rt_intersect and by the rare re-queries.
+template <bool ANYHIT, bool COUNT>
+__device__ __forceinline__ bool trace_bvh(const SceneDev& s, int root_entry, const f3& o, const f3& d, HitRec& best, TraceStats& st)
+{
+    int stack[kStackDepth];
+    Trav tv;
+    trav_begin(tv, o, d, best, root_entry);
+    trav_run<ANYHIT, COUNT>(s, tv, stack, st, 0);
+    best = tv.best;
+    return tv.ok;
 }
 
 } // namespace rtb

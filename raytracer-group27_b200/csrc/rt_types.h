@@ -69,8 +69,8 @@ struct FrameParams {
 // Device-resident counters of one wavefront batch.
 struct Counters {
     unsigned int n_rays[2];      // ray queue fill (ping-pong)
-    unsigned int n_shadow_pt;    // point-light shadow records
-    unsigned int n_shadow_sp;    // spherical-light records
+    unsigned int n_shadow_pt;    // hits with point-light records (n_point consecutive records per hit)
+    unsigned int n_shadow_sp;    // hits with spherical-light records (n_sphere consecutive records per hit)
     unsigned int work[4];        // dynamic work-fetch cursors: extend, shade, shadow_pt, shadow_sp
     unsigned int overflow;       // set when a queue would exceed its capacity
     unsigned int pad;
@@ -105,6 +105,7 @@ struct BatchDev {
     unsigned int shadow_pt_capacity;
     unsigned int shadow_sp_capacity;
     Counters* counters;
+    float2* sphere_acc; // per spherical-light record: {sum of sample intensities, number of visible samples}
     float4* accum;    // per local padded pixel, summed radiance
     int* prim_id;     // nullable: closest-hit global triangle id of the first primary ray of each local pixel
     float* prim_t;    // nullable

@@ -97,6 +97,35 @@ def test_intersect_matches_oracle(rtb, gpu_ctx):
                 assert bits_equal(t, o_t)
 
 
+def test_axis_parallel_and_in_plane_rays(rtb, gpu_ctx):
+    """Rays with exactly zero direction components, some of them travelling inside the plane of a flat face (the cube's
+    faces and the Cornell walls have zero-thickness boxes): the BVH must still return what exhaustive search returns."""
+    import oracle
+    for name in ("cube_96", "cornell_c1_256"):
+        g = Golden(name)
+        lo, hi = g.scene.pos.reshape(-1, 3).min(0), g.scene.pos.reshape(-1, 3).max(0)
+        coords = [np.unique(np.concatenate([np.linspace(lo[a] - 0.25, hi[a] + 0.25, 23), g.scene.pos.reshape(-1, 3)[:, a]])).astype(np.float32) for a in range(3)]
+        rays = []
+        for axis in range(3):
+            u, v = (axis + 1) % 3, (axis + 2) % 3
+            uu, vv = np.meshgrid(coords[u], coords[v], indexing="ij")
+            for sign in (1.0, -1.0):
+                o = np.zeros((uu.size, 3), np.float32)
+                o[:, u], o[:, v] = uu.ravel(), vv.ravel()
+                o[:, axis] = lo[axis] - 1.0 if sign > 0 else hi[axis] + 1.0
+                d = np.zeros_like(o)
+                d[:, axis] = sign
+                rays.append(np.concatenate([o, d], 1))
+        rays = np.concatenate(rays, 0).astype(np.float32)
+        o_ids, o_t = oracle.Oracle("port").closest_hit(g.scene.pos, g.scene.nrm, g.scene.mesh_id, rays, use_bvh=False)
+        assert (o_ids >= 0).sum() > 100
+        for mode in (rtb.BVH_LBVH_DEVICE, rtb.BVH_SAH_HOST):
+            gpu_ctx.upload_scene(g.scene, mode)
+            ids, t = gpu_ctx.intersect(rays, True)
+            assert np.array_equal(ids, o_ids), f"{name} mode {mode}: {(ids != o_ids).sum()} of {len(ids)} ids differ"
+            assert bits_equal(t, o_t)
+
+
 def test_full_size_bvh_equals_exhaustive(rtb, gpu_ctx):
     """Size-independent property at C1's full size (1024x1024, depth 3): the BVH frame equals the exhaustive frame
     bit for bit (ids, t) and to round-off in colour — both use the reference's triangle arithmetic."""

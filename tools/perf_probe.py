@@ -25,6 +25,11 @@ def run(ctx, name, sc, cam, prm, modes=("lbvh", "sah"), reps=5, counters=True):
             ms.append(st.gpu_ms)
         best = min(ms[1:]) if reps > 1 else ms[0]
         line = f"{name:28s} {mode:5s} build {build_s*1e3:8.1f} ms nodes {nodes:9d} depth {depth:3d} | frame {best:9.3f} ms  rays {st.rays:12d}  {st.rays/best/1e3:9.1f} Mrays/s (prim {st.primary_rays} shad {st.shadow_queries} sec {st.secondary_rays}) launches {st.kernel_launches} batches {st.batches}"
+        ctx.set_stage_timing(True)
+        ctx.render_device(cam, prm)
+        ctx.sync()
+        ctx.set_stage_timing(False)
+        line += " | stages ms: " + " ".join(f"{k[:7]}={v[0]:.3f}" for k, v in ctx.stage_times().items() if v[1])
         if counters:
             ctx.set_counters(True)
             ctx.render_device(cam, prm)
