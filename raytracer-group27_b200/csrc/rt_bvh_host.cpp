@@ -62,7 +62,10 @@ void write_node(std::vector<float4>& nodes, int idx, const Box& b, float pad, in
     float4 a, c;
     a.x = b.lo[0] - pad; a.y = b.lo[1] - pad; a.z = b.lo[2] - pad;
     c.x = b.hi[0] + pad; c.y = b.hi[1] + pad; c.z = b.hi[2] + pad;
-    std::memcpy(&a.w, &left_or_first, 4);
+    // lo.w carries the node's traversal-stack entry ready-made: inner node -> index of its left child (the sibling
+    // pair to fetch), leaf -> ~((first << 3) | (count - 1)); hi.w keeps the triangle count (0 = inner)
+    const int entry = count ? ~((left_or_first << 3) | (count - 1)) : left_or_first;
+    std::memcpy(&a.w, &entry, 4);
     std::memcpy(&c.w, &count, 4);
     nodes[2 * (size_t)idx] = a;
     nodes[2 * (size_t)idx + 1] = c;

@@ -9,7 +9,6 @@ namespace rtb {
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kRefillThreshold = 20;   // traversal loops yield when fewer lanes than this are still busy
 constexpr int kShadeBlock = 256;
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
@@ -20,30 +19,6 @@ __device__ __forceinline__ void warp_add_u64(unsigned long long* dst, unsigned v
         v += __shfl_xor_sync(kFull, v, o);
     if (lane_id() == 0 && v)
         atomicAdd(dst, (unsigned long long)v);
-}
-
-// Persistent-warp work distribution with per-lane refill: every lane whose ray has finished gets the next unclaimed
-// item; one atomicAdd per warp per refill.  All 32 lanes must call this together.  Returns the item index for a
-// lane that needed one (0xffffffff if none was left); `more` becomes false once the queue is exhausted.
-__device__ __forceinline__ unsigned warp_refill(unsigned* cursor, unsigned n, bool need, bool& more)
-{
-    const unsigned idle = __ballot_sync(kFull, need);
-    unsigned item = 0xffffffffu;
-    if (idle && more) {
-        const int leader = __ffs(idle) - 1;
-        const unsigned cnt = (unsigned)__popc(idle);
-        unsigned base = 0;
-        if (lane_id() == leader)
-            base = atomicAdd(cursor, cnt);
-        base = __shfl_sync(kFull, base, leader);
-        if (need) {
-            const unsigned i = base + (unsigned)__popc(idle & ((1u << lane_id()) - 1u));
-            if (i < n)
-                item = i;
-        }
-        more = base + cnt < n;
-    }
-    return item;
 }
 
 // Block-aggregated queue allocation for NQ queues at once: every thread says whether it wants a slot in each queue;
@@ -221,65 +196,34 @@ __global__ void k_level_reset(Counters* c, int next_q, long long n_current, unsi
 
 // ---------------------------------------------------------------------------------------------------------
 // K2 extend: closest hit of every ray of the level (BoundingVolumeHierarchy::intersect,
-// src/bounding_volume_hierarchy.cpp:49-78).  Persistent warps; a lane whose ray is done immediately pulls the next
-// one (at level 0 it is generated from the pixel index: K1 fused).  Result: hit[i] = {bits(t), BVH-order triangle}.
+// src/bounding_volume_hierarchy.cpp:49-78) through the warp-synchronous engine of rt_trace.cuh.  At level 0 the ray is
+// generated from the pixel index when a lane picks the item up (K1 fused).  Result: hit[i] = {bits(t), BVH-order triangle}.
 template <bool LEVEL0, bool COUNT>
 __global__ void __launch_bounds__(128) k_extend(SceneDev s, int root_entry, FrameParams fp, BatchDev b, int qi, unsigned first_lp)
 {
     const unsigned n = b.counters->n_rays[qi];
-    int stack[kStackDepth];
-    Trav tv;
-    tv.cur = kTravDone;
-    tv.ok = true;
     TraceStats st;
-    bool active = false, more = true, ok = true;
-    unsigned my = 0;
     int tag = 0;
-    for (;;) {
-        const unsigned item = warp_refill(&b.counters->work[0], n, !active, more);
-        if (item != 0xffffffffu) {
-            f3 o, d;
-            bool valid = true;
-            if (LEVEL0) {
-                valid = generate_ray(fp, first_lp, item, o, d, tag);
-            } else {
-                const float4 op = b.q[qi].o_pix[item];
-                const float4 dd = b.q[qi].d[item];
-                o = mk3(op);
-                d = mk3(dd);
-                tag = __float_as_int(op.w);
+    trace_queue<false, COUNT>(
+        s, root_entry, fp.exhaustive != 0, &b.counters->work[0], n, st,
+        [&](unsigned item, f3& o, f3& d, HitRec& q) {
+            q = fresh_query();
+            if (LEVEL0)
+                return generate_ray(fp, first_lp, item, o, d, tag);
+            const float4 op = b.q[qi].o_pix[item];
+            o = mk3(op);
+            d = mk3(b.q[qi].d[item]);
+            tag = __float_as_int(op.w);
+            return true;
+        },
+        [&](unsigned item, const HitRec& best, f3&, f3&, HitRec&) {
+            b.q[qi].hit[item] = make_int2(__float_as_int(best.t), best.ti);
+            if (LEVEL0 && b.prim_id && (tag & 1)) { // first sample of the pixel
+                b.prim_id[tag >> 1] = best.ti >= 0 ? best.id : -1;
+                b.prim_t[tag >> 1] = best.t;
             }
-            if (valid) {
-                my = item;
-                active = true;
-                trav_begin(tv, o, d, fresh_query(), root_entry);
-                if (fp.exhaustive) {
-                    trace_exhaustive<false, COUNT>(s, o, d, tv.best, st);
-                    tv.cur = kTravDone;
-                }
-            }
-        }
-        if (!__any_sync(kFull, active)) {
-            if (!more)
-                break;
-            continue;
-        }
-        if (active) {
-            trav_run<false, COUNT>(s, tv, stack, st, more ? kRefillThreshold : 0);
-            if (tv.cur == kTravDone) {
-                ok &= tv.ok;
-                b.q[qi].hit[my] = make_int2(__float_as_int(tv.best.t), tv.best.ti);
-                if (LEVEL0 && b.prim_id && (tag & 1)) { // first sample of the pixel
-                    b.prim_id[tag >> 1] = tv.best.ti >= 0 ? tv.best.id : -1;
-                    b.prim_t[tag >> 1] = tv.best.t;
-                }
-                active = false;
-            }
-        }
-        __syncwarp();
-    }
-    if (!ok)
-        atomicExch(&b.counters->overflow, 2u);
+            return false;
+        });
     if (COUNT) {
         warp_add_u64(&b.counters->node_visits, st.nodes);
         warp_add_u64(&b.counters->tri_tests, st.tris);
@@ -474,68 +418,42 @@ __device__ __forceinline__ int cansee_step(const SceneDev& s, const FrameParams&
 }
 
 // Shared body of the two shadow kernels.  Work item j < n_items; item_begin(j, p1, p2) gives the segment to test,
-// item_end(j, visible, intensity) consumes the result.  Persistent warps with per-lane refill, like k_extend.
-template <bool COUNT, typename Begin, typename End>
+// item_end(j, visible, intensity) consumes the result.  Each cansee loop iteration is one traversal of the engine; a
+// transparent blocker makes the lane continue the same item from behind the surface.
+template <bool ANYHIT, bool COUNT, typename Begin, typename End>
 __device__ __forceinline__ void shadow_loop(const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, unsigned* cursor,
     unsigned n_items, Begin item_begin, End item_end)
 {
-    int stack[kStackDepth];
-    Trav tv;
-    tv.cur = kTravDone;
-    tv.ok = true;
     TraceStats st;
     CanSee cs;
-    bool active = false, more = true, ok = true;
-    unsigned my = 0, queries = 0;
-    for (;;) {
-        const unsigned item = warp_refill(cursor, n_items, !active, more);
-        if (item != 0xffffffffu) {
+    unsigned queries = 0;
+    trace_queue<ANYHIT, COUNT>(
+        s, root_entry, fp.exhaustive != 0, cursor, n_items, st,
+        [&](unsigned item, f3& o, f3& d, HitRec& q) {
             f3 p1, p2;
             item_begin(item, p1, p2);
-            my = item;
-            if (cansee_begin(cs, p1, p2)) {
-                active = true;
+            if (!cansee_begin(cs, p1, p2)) {
+                item_end(item, true, 1.0f);
+                return false;
+            }
+            queries++;
+            o = cs.o;
+            d = cs.d;
+            q = cansee_query(cs);
+            return true;
+        },
+        [&](unsigned item, const HitRec& best, f3& o, f3& d, HitRec& q) {
+            const int r = cansee_step(s, fp, cs, best);
+            if (r == 2) {
                 queries++;
-                trav_begin(tv, cs.o, cs.d, cansee_query(cs), root_entry);
-            } else {
-                item_end(my, true, 1.0f);
+                o = cs.o;
+                d = cs.d;
+                q = cansee_query(cs);
+                return true;
             }
-        }
-        if (!__any_sync(kFull, active)) {
-            if (!more)
-                break;
-            continue;
-        }
-        if (active) {
-            if (fp.exhaustive) { // reference useBVH=false semantics for tests: loop over every triangle
-                if (fp.any_transparent)
-                    trace_exhaustive<false, COUNT>(s, cs.o, cs.d, tv.best, st);
-                else
-                    trace_exhaustive<true, COUNT>(s, cs.o, cs.d, tv.best, st);
-                tv.cur = kTravDone;
-            } else if (fp.any_transparent) {
-                // a transparent blocker only attenuates: the closest hit decides what happens next
-                trav_run<false, COUNT>(s, tv, stack, st, more ? kRefillThreshold : 0);
-            } else {
-                // opaque materials only: the first blocker found decides (any-hit)
-                trav_run<true, COUNT>(s, tv, stack, st, more ? kRefillThreshold : 0);
-            }
-            if (tv.cur == kTravDone) {
-                ok &= tv.ok;
-                const int r = cansee_step(s, fp, cs, tv.best);
-                if (r == 2) {
-                    queries++;
-                    trav_begin(tv, cs.o, cs.d, cansee_query(cs), root_entry);
-                } else {
-                    item_end(my, r == 0, cs.intensity);
-                    active = false;
-                }
-            }
-        }
-        __syncwarp();
-    }
-    if (!ok)
-        atomicExch(&b.counters->overflow, 2u);
+            item_end(item, r == 0, cs.intensity);
+            return false;
+        });
     warp_add_u64(&b.counters->shadow_queries, queries);
     if (COUNT) {
         warp_add_u64(&b.counters->node_visits, st.nodes);
@@ -545,11 +463,12 @@ __device__ __forceinline__ void shadow_loop(const SceneDev& s, int root_entry, c
 }
 
 // K4a shadow rays to point lights (getPointLights' cansee call, src/shadow.cpp:120).
-template <bool COUNT>
+// ANYHIT: every material is opaque, so the first blocker found decides; otherwise the closest hit does.
+template <bool ANYHIT, bool COUNT>
 __global__ void __launch_bounds__(128) k_shadow_point(SceneDev s, int root_entry, FrameParams fp, BatchDev b)
 {
     const unsigned n = b.counters->n_shadow_pt * (unsigned)fp.n_point;
-    shadow_loop<COUNT>(
+    shadow_loop<ANYHIT, COUNT>(
         s, root_entry, fp, b, &b.counters->work[2], n,
         [&](unsigned i, f3& p1, f3& p2) {
             const float4 pp = b.sq_point.p_pix[i];
@@ -570,12 +489,12 @@ __global__ void __launch_bounds__(128) k_shadow_point(SceneDev s, int root_entry
 // K4b spherical lights (getSpherelights, src/shadow.cpp:139-226).  Work item = (record, sample): sample 0 is the
 // light centre, the others lie on rings of the disc facing the hit point; their positions follow the reference's
 // sequential `perp = rotate * perp`.  Per-record sums go to sphere_acc = {sum of intensities, visible count}.
-template <bool COUNT>
+template <bool ANYHIT, bool COUNT>
 __global__ void __launch_bounds__(128) k_shadow_sphere(SceneDev s, int root_entry, FrameParams fp, BatchDev b)
 {
     const unsigned rc = (unsigned)fp.sl_rc;
     const unsigned n = b.counters->n_shadow_sp * (unsigned)fp.n_sphere * rc;
-    shadow_loop<COUNT>(
+    shadow_loop<ANYHIT, COUNT>(
         s, root_entry, fp, b, &b.counters->work[3], n,
         [&](unsigned j, f3& p1, f3& p2) {
             const unsigned rec = j / rc;
@@ -711,8 +630,7 @@ __global__ void __launch_bounds__(128) k_intersect(SceneDev s, int root_entry, c
         const f3 d = mk3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
         HitRec best = fresh_query();
         if (use_bvh) {
-            if (!trace_bvh<false, false>(s, root_entry, o, d, best, st))
-                atomicExch(overflow, 2u);
+            trace_bvh<false, false>(s, root_entry, o, d, best, st);
         } else {
             trace_exhaustive<false, false>(s, o, d, best, st);
         }
@@ -774,19 +692,29 @@ void launch_shade(cudaStream_t st, int sm_count, const SceneDev& s, const FrameP
 void launch_shadow_point(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count)
 {
     const int grid = sm_count * 8;
-    if (count)
-        k_shadow_point<true><<<grid, 128, 0, st>>>(s, root_entry, fp, b);
+    const bool anyhit = !fp.any_transparent;
+    if (anyhit && count)
+        k_shadow_point<true, true><<<grid, 128, 0, st>>>(s, root_entry, fp, b);
+    else if (anyhit)
+        k_shadow_point<true, false><<<grid, 128, 0, st>>>(s, root_entry, fp, b);
+    else if (count)
+        k_shadow_point<false, true><<<grid, 128, 0, st>>>(s, root_entry, fp, b);
     else
-        k_shadow_point<false><<<grid, 128, 0, st>>>(s, root_entry, fp, b);
+        k_shadow_point<false, false><<<grid, 128, 0, st>>>(s, root_entry, fp, b);
 }
 
 void launch_shadow_sphere(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count)
 {
     const int grid = sm_count * 8;
-    if (count)
-        k_shadow_sphere<true><<<grid, 128, 0, st>>>(s, root_entry, fp, b);
+    const bool anyhit = !fp.any_transparent;
+    if (anyhit && count)
+        k_shadow_sphere<true, true><<<grid, 128, 0, st>>>(s, root_entry, fp, b);
+    else if (anyhit)
+        k_shadow_sphere<true, false><<<grid, 128, 0, st>>>(s, root_entry, fp, b);
+    else if (count)
+        k_shadow_sphere<false, true><<<grid, 128, 0, st>>>(s, root_entry, fp, b);
     else
-        k_shadow_sphere<false><<<grid, 128, 0, st>>>(s, root_entry, fp, b);
+        k_shadow_sphere<false, false><<<grid, 128, 0, st>>>(s, root_entry, fp, b);
     k_sphere_finalize<<<sm_count * 4, 256, 0, st>>>(fp, b);
 }
 

@@ -181,7 +181,8 @@ __global__ void k_live(const int* __restrict__ first, const int* __restrict__ la
 
 __device__ __forceinline__ void emit_node(float4* nodes, int idx, float4 lo, float4 hi, float pad, int left_or_first, int count)
 {
-    nodes[2 * (size_t)idx] = make_float4(lo.x - pad, lo.y - pad, lo.z - pad, __int_as_float(left_or_first));
+    const int entry = count ? ~((left_or_first << 3) | (count - 1)) : left_or_first; // see rt_types.h
+    nodes[2 * (size_t)idx] = make_float4(lo.x - pad, lo.y - pad, lo.z - pad, __int_as_float(entry));
     nodes[2 * (size_t)idx + 1] = make_float4(hi.x + pad, hi.y + pad, hi.z + pad, __int_as_float(count));
 }
 

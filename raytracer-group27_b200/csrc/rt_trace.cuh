@@ -87,19 +87,21 @@ __device__ __forceinline__ void trace_exhaustive(const SceneDev& s, const f3& o,
     }
 }
 
-// ---- resumable BVH traversal -------------------------------------------------------------------------------
-// Stack entries: >= 0 -> node index of a sibling pair to fetch; < 0 -> ~((first << 3) | (count - 1)), a leaf.
-constexpr int kTravDone = INT_MIN; // not a valid leaf encoding (triangle count is limited to 2^28 - 2)
+// ---- warp-synchronous BVH traversal engine -----------------------------------------------------------------
+// Stack entries (= the `entry` word of a node, rt_types.h): >= 0 -> node index of a sibling pair to fetch;
+// < 0 -> ~((first << 3) | (count - 1)), a leaf.  The builders keep the tree depth below kStackDepth (rt_build_bvh
+// fails otherwise), so the per-lane stack cannot overflow.
+constexpr int kTravDone = INT_MIN;      // not a valid leaf encoding (triangle count is limited to 2^28 - 2)
+constexpr int kRefillThreshold = 20;    // the traversal loop yields for a refill when fewer lanes than this are still busy
 
 struct Trav {
     f3 o, d, dn;            // ray as stored, and normalize(d)
-    float ix, iy, iz;       // 1 / dn
+    float ix, iy, iz;       // 1 / dn (clamped, see trav_begin)
     float oix, oiy, oiz;    // o * (1 / dn): slabs are evaluated as fma(box, 1/dn, -o/dn)
     HitRec best;
     float tlimit;
     int cur;                // current entry, kTravDone when the traversal is complete
     int sp;
-    bool ok;                // false if the stack overflowed
 };
 
 __device__ __forceinline__ void trav_begin(Trav& tv, const f3& o, const f3& d, const HitRec& query, int root_entry)
@@ -120,83 +122,160 @@ __device__ __forceinline__ void trav_begin(Trav& tv, const f3& o, const f3& d, c
     tv.tlimit = prune_limit(query.t);
     tv.cur = root_entry;
     tv.sp = 0;
-    tv.ok = true;
 }
 
-// Advance the traversal ("while-while": run through inner nodes until a leaf is reached, then test the leaf).
-// Returns when the traversal is complete (tv.cur == kTravDone) or — if min_active > 0 — as soon as fewer than
-// min_active lanes of the warp are still inside this loop, so that the caller can hand new rays to the idle lanes.
-template <bool ANYHIT, bool COUNT>
-__device__ __forceinline__ void trav_run(const SceneDev& s, Trav& tv, int* stack, TraceStats& st, int min_active)
+// One node step: fetch the sibling pair `tv.cur` (one aligned 64-byte read), slab-test both boxes, descend into the
+// nearer hit child and push the other one, or pop.
+template <bool COUNT>
+__device__ __forceinline__ void trav_node_step(const SceneDev& s, Trav& tv, int* stack, TraceStats& st)
 {
-    while (tv.cur != kTravDone) {
-        while (tv.cur >= 0) {
-            const float4* np = s.nodes + 2 * (size_t)tv.cur;
-            const float4 a0 = __ldg(np), a1 = __ldg(np + 1), b0 = __ldg(np + 2), b1 = __ldg(np + 3);
-            if (COUNT)
-                st.nodes += 2;
-            // slabs; fminf/fmaxf drop NaNs (inf - inf for axis-parallel rays), which only widens the interval
-            float t0, t1;
-            t0 = fmaf(a0.x, tv.ix, -tv.oix); t1 = fmaf(a1.x, tv.ix, -tv.oix);
-            float amin = fminf(t0, t1), amax = fmaxf(t0, t1);
-            t0 = fmaf(a0.y, tv.iy, -tv.oiy); t1 = fmaf(a1.y, tv.iy, -tv.oiy);
-            amin = fmaxf(amin, fminf(t0, t1)); amax = fminf(amax, fmaxf(t0, t1));
-            t0 = fmaf(a0.z, tv.iz, -tv.oiz); t1 = fmaf(a1.z, tv.iz, -tv.oiz);
-            amin = fmaxf(fmaxf(amin, fminf(t0, t1)), 0.0f); amax = fminf(fminf(amax, fmaxf(t0, t1)), tv.tlimit);
-            t0 = fmaf(b0.x, tv.ix, -tv.oix); t1 = fmaf(b1.x, tv.ix, -tv.oix);
-            float bmin = fminf(t0, t1), bmax = fmaxf(t0, t1);
-            t0 = fmaf(b0.y, tv.iy, -tv.oiy); t1 = fmaf(b1.y, tv.iy, -tv.oiy);
-            bmin = fmaxf(bmin, fminf(t0, t1)); bmax = fminf(bmax, fmaxf(t0, t1));
-            t0 = fmaf(b0.z, tv.iz, -tv.oiz); t1 = fmaf(b1.z, tv.iz, -tv.oiz);
-            bmin = fmaxf(fmaxf(bmin, fminf(t0, t1)), 0.0f); bmax = fminf(fminf(bmax, fmaxf(t0, t1)), tv.tlimit);
-            const bool hitA = amin <= amax * 1.0000005f;
-            const bool hitB = bmin <= bmax * 1.0000005f;
-            const int ca = __float_as_int(a1.w), cb = __float_as_int(b1.w);
-            const int ea = ca ? ~((__float_as_int(a0.w) << 3) | (ca - 1)) : __float_as_int(a0.w);
-            const int eb = cb ? ~((__float_as_int(b0.w) << 3) | (cb - 1)) : __float_as_int(b0.w);
-            if (hitA && hitB) {
-                const bool aFirst = amin <= bmin;
-                if (tv.sp < kStackDepth)
-                    stack[tv.sp++] = aFirst ? eb : ea;
-                else
-                    tv.ok = false;
-                tv.cur = aFirst ? ea : eb;
-            } else if (hitA) {
-                tv.cur = ea;
-            } else if (hitB) {
-                tv.cur = eb;
-            } else {
-                tv.cur = tv.sp ? stack[--tv.sp] : kTravDone;
-            }
-        }
-        if (tv.cur != kTravDone) {
-            const int enc = ~tv.cur;
-            const int first = enc >> 3, count = (enc & 7) + 1;
-            bool any = false;
-            for (int i = 0; i < count; i++)
-                any |= test_triangle<COUNT>(s, first + i, tv.o, tv.d, tv.dn, tv.best, st);
-            tv.cur = tv.sp ? stack[--tv.sp] : kTravDone;
-            if (any) {
-                if (ANYHIT)
-                    tv.cur = kTravDone;
-                tv.tlimit = prune_limit(tv.best.t);
-            }
-        }
-        if (min_active > 0 && __popc(__activemask()) < min_active)
-            break;
+    const float4* np = s.nodes + 2 * (size_t)tv.cur;
+    const float4 a0 = __ldg(np), a1 = __ldg(np + 1), b0 = __ldg(np + 2), b1 = __ldg(np + 3);
+    if (COUNT)
+        st.nodes += 2;
+    // slabs; fminf/fmaxf drop NaNs, which only widens the interval
+    float t0, t1;
+    t0 = fmaf(a0.x, tv.ix, -tv.oix); t1 = fmaf(a1.x, tv.ix, -tv.oix);
+    float amin = fminf(t0, t1), amax = fmaxf(t0, t1);
+    t0 = fmaf(a0.y, tv.iy, -tv.oiy); t1 = fmaf(a1.y, tv.iy, -tv.oiy);
+    amin = fmaxf(amin, fminf(t0, t1)); amax = fminf(amax, fmaxf(t0, t1));
+    t0 = fmaf(a0.z, tv.iz, -tv.oiz); t1 = fmaf(a1.z, tv.iz, -tv.oiz);
+    amin = fmaxf(fmaxf(amin, fminf(t0, t1)), 0.0f); amax = fminf(fminf(amax, fmaxf(t0, t1)), tv.tlimit);
+    t0 = fmaf(b0.x, tv.ix, -tv.oix); t1 = fmaf(b1.x, tv.ix, -tv.oix);
+    float bmin = fminf(t0, t1), bmax = fmaxf(t0, t1);
+    t0 = fmaf(b0.y, tv.iy, -tv.oiy); t1 = fmaf(b1.y, tv.iy, -tv.oiy);
+    bmin = fmaxf(bmin, fminf(t0, t1)); bmax = fminf(bmax, fmaxf(t0, t1));
+    t0 = fmaf(b0.z, tv.iz, -tv.oiz); t1 = fmaf(b1.z, tv.iz, -tv.oiz);
+    bmin = fmaxf(fmaxf(bmin, fminf(t0, t1)), 0.0f); bmax = fminf(fminf(bmax, fmaxf(t0, t1)), tv.tlimit);
+    const bool hitA = amin <= amax * 1.0000005f;
+    const bool hitB = bmin <= bmax * 1.0000005f;
+    const int ea = __float_as_int(a0.w), eb = __float_as_int(b0.w);
+    if (hitA && hitB) {
+        const bool aFirst = amin <= bmin;
+        stack[tv.sp++] = aFirst ? eb : ea;
+        tv.cur = aFirst ? ea : eb;
+    } else if (hitA) {
+        tv.cur = ea;
+    } else if (hitB) {
+        tv.cur = eb;
+    } else {
+        tv.cur = tv.sp ? stack[--tv.sp] : kTravDone;
     }
 }
 
-// One-shot traversal (no refill): used by rt_intersect and by the rare re-queries.
+// Triangle step for the leaf entry in tv.cur; afterwards tv.cur is the next entry from the stack.
 template <bool ANYHIT, bool COUNT>
-__device__ __forceinline__ bool trace_bvh(const SceneDev& s, int root_entry, const f3& o, const f3& d, HitRec& best, TraceStats& st)
+__device__ __forceinline__ void trav_leaf_step(const SceneDev& s, Trav& tv, const int* stack, TraceStats& st)
+{
+    const int enc = ~tv.cur;
+    const int first = enc >> 3, count = (enc & 7) + 1;
+    bool any = false;
+    for (int i = 0; i < count; i++)
+        any |= test_triangle<COUNT>(s, first + i, tv.o, tv.d, tv.dn, tv.best, st);
+    tv.cur = tv.sp ? stack[--tv.sp] : kTravDone;
+    if (any) {
+        tv.tlimit = prune_limit(tv.best.t);
+        if (ANYHIT) // the first blocker decides: drop all remaining work
+            tv.cur = kTravDone;
+    }
+}
+
+// Persistent-warp traversal of a work queue ("while-while" with per-lane refill, after Aila & Laine, "Understanding the
+// Efficiency of Ray Traversal on GPUs", HPG 2009).  Every lane walks inner nodes until it reaches a leaf, then tests the
+// leaf's triangles, and repeats; as soon as fewer than kRefillThreshold lanes are still inside that loop, the warp
+// leaves it and the idle lanes pull new items (one atomicAdd per warp per refill).
+// fetch(item, o, d, query) -> false if the item needs no ray;  finish(item, best, o, d, query) -> true to continue the
+// same item with a new segment (shadow rays passing a transparent surface).
+template <bool ANYHIT, bool COUNT, typename Fetch, typename Finish>
+__device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, bool exhaustive, unsigned* cursor, unsigned n_items,
+    TraceStats& st, Fetch fetch, Finish finish)
+{
+    constexpr unsigned kFullMask = 0xffffffffu;
+    int stack[kStackDepth];
+    Trav tv;
+    tv.cur = kTravDone;
+    tv.sp = 0;
+    bool active = false, more = n_items > 0;
+    unsigned my = 0;
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        // ---- refill: every idle lane takes the next unclaimed item ----
+        const unsigned idle = __ballot_sync(kFullMask, !active);
+        if (idle && more) {
+            const int leader = __ffs(idle) - 1;
+            const unsigned cnt = (unsigned)__popc(idle);
+            unsigned base = 0;
+            if (lane == leader)
+                base = atomicAdd(cursor, cnt);
+            base = __shfl_sync(kFullMask, base, leader);
+            more = base + cnt < n_items;
+            if (!active) {
+                const unsigned item = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
+                if (item < n_items) {
+                    f3 o, d;
+                    HitRec q;
+                    if (fetch(item, o, d, q)) {
+                        my = item;
+                        active = true;
+                        trav_begin(tv, o, d, q, root_entry);
+                        if (exhaustive) { // reference useBVH=false semantics (tests): loop over every triangle
+                            bool again;
+                            do {
+                                trace_exhaustive<ANYHIT, COUNT>(s, tv.o, tv.d, tv.best, st);
+                                again = finish(my, tv.best, o, d, q);
+                                if (again)
+                                    trav_begin(tv, o, d, q, root_entry);
+                            } while (again);
+                            active = false;
+                            tv.cur = kTravDone;
+                        }
+                    }
+                }
+            }
+        }
+        if (!__any_sync(kFullMask, active)) {
+            if (!more)
+                break;
+            continue;
+        }
+        // ---- traverse ----
+        if (active) {
+            const int min_active = more ? kRefillThreshold : 0;
+            while (tv.cur != kTravDone) {
+                while (tv.cur >= 0)
+                    trav_node_step<COUNT>(s, tv, stack, st);
+                if (tv.cur != kTravDone)
+                    trav_leaf_step<ANYHIT, COUNT>(s, tv, stack, st);
+                if (min_active > 0 && __popc(__activemask()) < min_active)
+                    break;
+            }
+            if (tv.cur == kTravDone) {
+                f3 o, d;
+                HitRec q;
+                if (finish(my, tv.best, o, d, q))
+                    trav_begin(tv, o, d, q, root_entry);
+                else
+                    active = false;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// One-shot traversal of a single ray per thread (rt_intersect); lanes are independent here.
+template <bool ANYHIT, bool COUNT>
+__device__ __forceinline__ void trace_bvh(const SceneDev& s, int root_entry, const f3& o, const f3& d, HitRec& best, TraceStats& st)
 {
     int stack[kStackDepth];
     Trav tv;
     trav_begin(tv, o, d, best, root_entry);
-    trav_run<ANYHIT, COUNT>(s, tv, stack, st, 0);
+    while (tv.cur != kTravDone) {
+        if (tv.cur >= 0)
+            trav_node_step<COUNT>(s, tv, stack, st);
+        else
+            trav_leaf_step<ANYHIT, COUNT>(s, tv, stack, st);
+    }
     best = tv.best;
-    return tv.ok;
 }
 
 } // namespace rtb

@@ -16,11 +16,12 @@ constexpr int kStackDepth = 64;   // per-thread traversal stack (ints); builders
 constexpr int kMaxPointLights = 16;
 constexpr int kMaxSphereLights = 8;
 
-// Flattened BVH in HBM: 32-byte nodes {lo.xyz, left_or_first}{hi.xyz, count}, read as 2 x float4.
+// Flattened BVH in HBM: 32-byte nodes {lo.xyz, entry}{hi.xyz, count}, read as 2 x float4.
 // Sibling nodes are adjacent (2k, 2k+1) so visiting an inner node is one aligned 64-byte fetch of both children.
-// count == 0: inner node, left_or_first = index of the left child (even); count > 0: leaf over triangles
-// [left_or_first, left_or_first + count) of the BVH-ordered triangle arrays.  Node 0 is the root, node 1 an empty
-// box (lo=+inf, hi=-inf) so the root can be fetched like any other pair.
+// count == 0: inner node, entry = index of the left child (even, >= 0); count > 0: leaf over triangles
+// [first, first + count) of the BVH-ordered triangle arrays, entry = ~((first << 3) | (count - 1)) (< 0) — i.e.
+// `entry` is exactly what the traversal pushes on its stack.  Node 0 is the root, node 1 a copy of it, so that a
+// root that is itself a leaf can be fetched like any other pair.
 struct SceneDev {
     const float4* nodes;
     const float4* tri_plane; // {n.xyz, D}: trianglePlane() precomputed by K0 with the reference's op order
