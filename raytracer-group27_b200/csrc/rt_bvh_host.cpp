@@ -47,9 +47,15 @@ struct Box {
     }
 };
 
-constexpr int kBins = 16;
+#ifndef RT_SAH_BINS
+#define RT_SAH_BINS 16
+#endif
+#ifndef RT_SAH_TRI_COST
+#define RT_SAH_TRI_COST 1.2f
+#endif
+constexpr int kBins = RT_SAH_BINS;
 constexpr float kTraversalCost = 1.0f;
-constexpr float kTriangleCost = 1.2f;
+constexpr float kTriangleCost = RT_SAH_TRI_COST;
 
 struct Work {
     int node;

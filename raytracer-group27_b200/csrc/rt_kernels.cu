@@ -10,6 +10,12 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kShadeBlock = 256;
+#ifndef RT_TRACE_BLOCK
+#define RT_TRACE_BLOCK 128
+#endif
+#ifndef RT_TRACE_GRID_MULT
+#define RT_TRACE_GRID_MULT 8
+#endif
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
@@ -199,7 +205,7 @@ __global__ void k_level_reset(Counters* c, int next_q, long long n_current, unsi
 // src/bounding_volume_hierarchy.cpp:49-78) through the warp-synchronous engine of rt_trace.cuh.  At level 0 the ray is
 // generated from the pixel index when a lane picks the item up (K1 fused).  Result: hit[i] = {bits(t), BVH-order triangle}.
 template <bool LEVEL0, bool COUNT>
-__global__ void __launch_bounds__(128) k_extend(SceneDev s, int root_entry, FrameParams fp, BatchDev b, int qi, unsigned first_lp)
+__global__ void __launch_bounds__(RT_TRACE_BLOCK) k_extend(SceneDev s, int root_entry, FrameParams fp, BatchDev b, int qi, unsigned first_lp)
 {
     const unsigned n = b.counters->n_rays[qi];
     TraceStats st;
@@ -465,7 +471,7 @@ __device__ __forceinline__ void shadow_loop(const SceneDev& s, int root_entry, c
 // K4a shadow rays to point lights (getPointLights' cansee call, src/shadow.cpp:120).
 // ANYHIT: every material is opaque, so the first blocker found decides; otherwise the closest hit does.
 template <bool ANYHIT, bool COUNT>
-__global__ void __launch_bounds__(128) k_shadow_point(SceneDev s, int root_entry, FrameParams fp, BatchDev b)
+__global__ void __launch_bounds__(RT_TRACE_BLOCK) k_shadow_point(SceneDev s, int root_entry, FrameParams fp, BatchDev b)
 {
     const unsigned n = b.counters->n_shadow_pt * (unsigned)fp.n_point;
     shadow_loop<ANYHIT, COUNT>(
@@ -490,7 +496,7 @@ __global__ void __launch_bounds__(128) k_shadow_point(SceneDev s, int root_entry
 // light centre, the others lie on rings of the disc facing the hit point; their positions follow the reference's
 // sequential `perp = rotate * perp`.  Per-record sums go to sphere_acc = {sum of intensities, visible count}.
 template <bool ANYHIT, bool COUNT>
-__global__ void __launch_bounds__(128) k_shadow_sphere(SceneDev s, int root_entry, FrameParams fp, BatchDev b)
+__global__ void __launch_bounds__(RT_TRACE_BLOCK) k_shadow_sphere(SceneDev s, int root_entry, FrameParams fp, BatchDev b)
 {
     const unsigned rc = (unsigned)fp.sl_rc;
     const unsigned n = b.counters->n_shadow_sp * (unsigned)fp.n_sphere * rc;
@@ -667,17 +673,17 @@ void launch_level_reset(cudaStream_t st, Counters* c, int next_q, long long n_cu
 void launch_extend(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, int qi,
     int level, unsigned first_lp, bool count)
 {
-    const int grid = sm_count * 8;
+    const int grid = sm_count * RT_TRACE_GRID_MULT;
     if (level == 0) {
         if (count)
-            k_extend<true, true><<<grid, 128, 0, st>>>(s, root_entry, fp, b, qi, first_lp);
+            k_extend<true, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b, qi, first_lp);
         else
-            k_extend<true, false><<<grid, 128, 0, st>>>(s, root_entry, fp, b, qi, first_lp);
+            k_extend<true, false><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b, qi, first_lp);
     } else {
         if (count)
-            k_extend<false, true><<<grid, 128, 0, st>>>(s, root_entry, fp, b, qi, first_lp);
+            k_extend<false, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b, qi, first_lp);
         else
-            k_extend<false, false><<<grid, 128, 0, st>>>(s, root_entry, fp, b, qi, first_lp);
+            k_extend<false, false><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b, qi, first_lp);
     }
 }
 
@@ -691,30 +697,30 @@ void launch_shade(cudaStream_t st, int sm_count, const SceneDev& s, const FrameP
 
 void launch_shadow_point(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count)
 {
-    const int grid = sm_count * 8;
+    const int grid = sm_count * RT_TRACE_GRID_MULT;
     const bool anyhit = !fp.any_transparent;
     if (anyhit && count)
-        k_shadow_point<true, true><<<grid, 128, 0, st>>>(s, root_entry, fp, b);
+        k_shadow_point<true, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b);
     else if (anyhit)
-        k_shadow_point<true, false><<<grid, 128, 0, st>>>(s, root_entry, fp, b);
+        k_shadow_point<true, false><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b);
     else if (count)
-        k_shadow_point<false, true><<<grid, 128, 0, st>>>(s, root_entry, fp, b);
+        k_shadow_point<false, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b);
     else
-        k_shadow_point<false, false><<<grid, 128, 0, st>>>(s, root_entry, fp, b);
+        k_shadow_point<false, false><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b);
 }
 
 void launch_shadow_sphere(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count)
 {
-    const int grid = sm_count * 8;
+    const int grid = sm_count * RT_TRACE_GRID_MULT;
     const bool anyhit = !fp.any_transparent;
     if (anyhit && count)
-        k_shadow_sphere<true, true><<<grid, 128, 0, st>>>(s, root_entry, fp, b);
+        k_shadow_sphere<true, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b);
     else if (anyhit)
-        k_shadow_sphere<true, false><<<grid, 128, 0, st>>>(s, root_entry, fp, b);
+        k_shadow_sphere<true, false><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b);
     else if (count)
-        k_shadow_sphere<false, true><<<grid, 128, 0, st>>>(s, root_entry, fp, b);
+        k_shadow_sphere<false, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b);
     else
-        k_shadow_sphere<false, false><<<grid, 128, 0, st>>>(s, root_entry, fp, b);
+        k_shadow_sphere<false, false><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b);
     k_sphere_finalize<<<sm_count * 4, 256, 0, st>>>(fp, b);
 }
 

@@ -92,7 +92,13 @@ __device__ __forceinline__ void trace_exhaustive(const SceneDev& s, const f3& o,
 // < 0 -> ~((first << 3) | (count - 1)), a leaf.  The builders keep the tree depth below kStackDepth (rt_build_bvh
 // fails otherwise), so the per-lane stack cannot overflow.
 constexpr int kTravDone = INT_MIN;      // not a valid leaf encoding (triangle count is limited to 2^28 - 2)
-constexpr int kRefillThreshold = 20;    // the traversal loop yields for a refill when fewer lanes than this are still busy
+#ifndef RT_REFILL_THRESHOLD
+#define RT_REFILL_THRESHOLD 20
+#endif
+#ifndef RT_STACK_TMIN
+#define RT_STACK_TMIN 0
+#endif
+constexpr int kRefillThreshold = RT_REFILL_THRESHOLD; // the traversal loop yields for a refill when fewer lanes than this are still busy
 
 struct Trav {
     f3 o, d, dn;            // ray as stored, and normalize(d)
@@ -124,6 +130,22 @@ __device__ __forceinline__ void trav_begin(Trav& tv, const f3& o, const f3& d, c
     tv.sp = 0;
 }
 
+// Pop the next entry; with RT_STACK_TMIN the entry distance saved at push time lets entries that have fallen behind the
+// current best hit be skipped without fetching them.
+__device__ __forceinline__ int trav_pop(Trav& tv, const int* stack)
+{
+#if RT_STACK_TMIN
+    while (tv.sp) {
+        --tv.sp;
+        if (__int_as_float(stack[2 * tv.sp + 1]) <= tv.tlimit)
+            return stack[2 * tv.sp];
+    }
+    return kTravDone;
+#else
+    return tv.sp ? stack[--tv.sp] : kTravDone;
+#endif
+}
+
 // One node step: fetch the sibling pair `tv.cur` (one aligned 64-byte read), slab-test both boxes, descend into the
 // nearer hit child and push the other one, or pop.
 template <bool COUNT>
@@ -152,14 +174,20 @@ __device__ __forceinline__ void trav_node_step(const SceneDev& s, Trav& tv, int*
     const int ea = __float_as_int(a0.w), eb = __float_as_int(b0.w);
     if (hitA && hitB) {
         const bool aFirst = amin <= bmin;
+#if RT_STACK_TMIN
+        stack[2 * tv.sp] = aFirst ? eb : ea;
+        stack[2 * tv.sp + 1] = __float_as_int(aFirst ? bmin : amin);
+        tv.sp++;
+#else
         stack[tv.sp++] = aFirst ? eb : ea;
+#endif
         tv.cur = aFirst ? ea : eb;
     } else if (hitA) {
         tv.cur = ea;
     } else if (hitB) {
         tv.cur = eb;
     } else {
-        tv.cur = tv.sp ? stack[--tv.sp] : kTravDone;
+        tv.cur = trav_pop(tv, stack);
     }
 }
 
@@ -172,12 +200,9 @@ __device__ __forceinline__ void trav_leaf_step(const SceneDev& s, Trav& tv, cons
     bool any = false;
     for (int i = 0; i < count; i++)
         any |= test_triangle<COUNT>(s, first + i, tv.o, tv.d, tv.dn, tv.best, st);
-    tv.cur = tv.sp ? stack[--tv.sp] : kTravDone;
-    if (any) {
+    if (any)
         tv.tlimit = prune_limit(tv.best.t);
-        if (ANYHIT) // the first blocker decides: drop all remaining work
-            tv.cur = kTravDone;
-    }
+    tv.cur = (ANYHIT && any) ? kTravDone : trav_pop(tv, stack); // any-hit: the first blocker decides
 }
 
 // Persistent-warp traversal of a work queue ("while-while" with per-lane refill, after Aila & Laine, "Understanding the
@@ -191,7 +216,7 @@ __device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, b
     TraceStats& st, Fetch fetch, Finish finish)
 {
     constexpr unsigned kFullMask = 0xffffffffu;
-    int stack[kStackDepth];
+    int stack[kStackDepth * (RT_STACK_TMIN ? 2 : 1)];
     Trav tv;
     tv.cur = kTravDone;
     tv.sp = 0;
@@ -266,7 +291,7 @@ __device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, b
 template <bool ANYHIT, bool COUNT>
 __device__ __forceinline__ void trace_bvh(const SceneDev& s, int root_entry, const f3& o, const f3& d, HitRec& best, TraceStats& st)
 {
-    int stack[kStackDepth];
+    int stack[kStackDepth * (RT_STACK_TMIN ? 2 : 1)];
     Trav tv;
     trav_begin(tv, o, d, best, root_entry);
     while (tv.cur != kTravDone) {

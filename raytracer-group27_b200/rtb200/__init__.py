@@ -12,7 +12,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "librtb200.so")
+LIB_PATH = os.environ.get("RTB200_LIB") or os.path.join(os.path.dirname(_HERE), "librtb200.so")  # override: kernel-variant experiments
 
 RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_OVERFLOW, RT_ERR_IO = 0, 1, 2, 3, 4
 BVH_LBVH_DEVICE, BVH_SAH_HOST = 0, 1
@@ -317,3 +317,25 @@ class Context:
         t = np.empty(n, np.float32)
         _check(self._l.rt_intersect(self._h, rays.ctypes.data, n, 1 if use_bvh else 0, ids.ctypes.data, t.ctypes.data))
         return ids, t
+
+
+# ---- image sharding (host-side mirror of the device mapping in csrc/rt_kernels.cu: local_to_pixel) ----
+TILE_W, TILE_H = 32, 16
+
+
+def tile_grid(width: int, height: int):
+    return (width + TILE_W - 1) // TILE_W, (height + TILE_H - 1) // TILE_H
+
+
+def owner_map(width: int, height: int, world: int) -> np.ndarray:
+    """(H, W) array in the Screen layout (row 0 = top): which rank renders each pixel (tile_id % world)."""
+    tx, ty = tile_grid(width, height)
+    tiles = (np.arange(ty)[:, None] * tx + np.arange(tx)[None, :]) % world
+    full = np.repeat(np.repeat(tiles, TILE_H, 0), TILE_W, 1)[:height, :width]  # indexed [py, px], py = 0 at the bottom
+    return full[::-1].copy()                                                     # Screen::setPixel flips y
+
+
+def local_tile_count(width: int, height: int, rank: int, world: int) -> int:
+    tx, ty = tile_grid(width, height)
+    total = tx * ty
+    return (total - rank + world - 1) // world if total > rank else 0

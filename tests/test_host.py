@@ -1,0 +1,182 @@
+"""CPU tests of the host side: the C-ABI library loads and exports what include/rt_b200.h declares, the OBJ/MTL
+importer, the error behaviour, the tile sharding map, and the C++ drop-in headers (compiled and run without a GPU)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "rt_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rt_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(rtb):
+    lib = rtb.lib()
+    names = declared_functions()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in include/rt_b200.h but not exported"
+    bound = {s[0] for s in rtb.SYMBOLS}
+    assert set(names) <= bound, f"python binding misses {set(names) - bound}"
+    assert lib.rt_version().decode().startswith("rt_b200")
+
+
+def test_no_cpu_fallback_without_gpu(rtb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(rtb.RtError) as e:
+        rtb.Context(0)
+    assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
+
+
+OBJ = """# two objects, three materials, quads, a concave quad, no normals in the second object
+mtllib t.mtl
+o first
+v 0 0 0
+v 1 0 0
+v 1 1 0
+v 0 1 0
+vn 0 0 1
+usemtl red
+f 1//1 2//1 3//1 4//1
+usemtl glass
+f 1//1 3//1 4//1
+o second
+v 0 0 1
+v 2 0 1
+v 0.5 0.5 1
+v 0 2 1
+usemtl red
+f 5 6 7 8
+v 3 3 3
+v 4 3 3
+v 3 4 3
+f 9 10 11
+"""
+MTL = """newmtl red
+Kd 0.8 0.1 0.1
+Ks 0.5 0.5 0.5
+Ns 32
+d 1
+newmtl glass
+Kd 0.1 0.1 0.1
+Tr 0.75
+"""
+
+
+def test_obj_importer(rtb, tmp_path):
+    (tmp_path / "t.obj").write_text(OBJ)
+    (tmp_path / "t.mtl").write_text(MTL)
+    sc = rtb.load_obj(str(tmp_path / "t.obj"))
+    # objects come out last-first (the reference pops assimp's children from a stack); meshes inside an object in order
+    assert list(np.bincount(sc.mesh_id)) == [3, 2, 1]          # second/red: quad + tri; first/red: quad; first/glass: tri
+    assert len(sc.mats) == 3
+    np.testing.assert_allclose(sc.mats["kd"][0], [0.8, 0.1, 0.1])
+    assert sc.mats["shininess"][0] == 32 and sc.mats["transparency"][0] == 1
+    np.testing.assert_allclose(sc.mats["transparency"][2], 0.25)   # Tr 0.75 -> opacity 0.25
+    assert sc.mats["shininess"][2] == 0                            # importer default
+    # the concave quad (corner 2 at (0.5,0.5) is reflex) is fanned from its concave corner: both triangles share it
+    q = sc.pos[:2].reshape(2, 3, 3)
+    assert np.allclose(q[0, 0], [0.5, 0.5, 1]) and np.allclose(q[1, 0], [0.5, 0.5, 1])
+    # generated face normals for the object without vn: unit length, +-z for the planar quad
+    n = sc.nrm[:2].reshape(-1, 3)
+    assert np.allclose(np.abs(n[:, 2]), 1) and np.allclose(n[:, :2], 0)
+    # normals given in the file are kept
+    assert np.allclose(sc.nrm[3].reshape(3, 3), [[0, 0, 1]] * 3)
+    # centre + scale: all corner positions end up inside the unit sphere, the farthest one on it
+    scn = rtb.load_obj(str(tmp_path / "t.obj"), normalize=True)
+    r = np.linalg.norm(scn.pos.reshape(-1, 3), axis=1)
+    assert r.max() == pytest.approx(1.0, abs=1e-6)
+
+
+def test_obj_importer_errors(rtb, tmp_path):
+    with pytest.raises(rtb.RtError) as e:
+        rtb.load_obj(str(tmp_path / "missing.obj"))
+    assert e.value.code == rtb.RT_ERR_IO
+    (tmp_path / "empty.obj").write_text("v 0 0 0\n")
+    with pytest.raises(rtb.RtError):
+        rtb.load_obj(str(tmp_path / "empty.obj"))
+    (tmp_path / "bad.obj").write_text("v 0 0 0\nv 1 0 0\nf 1 2 7\n")
+    with pytest.raises(rtb.RtError):
+        rtb.load_obj(str(tmp_path / "bad.obj"))
+
+
+def test_importer_matches_fixture_geometry(rtb):
+    """Where the reference's data directory is reachable (this container), the importer reproduces the geometry stored in
+    the golden fixtures bit for bit."""
+    data = "/root/reference/data"
+    if not os.path.isdir(data):
+        pytest.skip("reference data not present on this box")
+    from util import Golden
+    for fixture, obj in (("cornell_c1_256", "CornellBox-Mirror-Rotated.obj"), ("monkey_192", "monkey-rotated.obj"), ("teapot_c2_256x144", "teapot.obj")):
+        g = Golden(fixture)
+        sc = rtb.load_obj(os.path.join(data, obj), normalize=True)
+        assert np.array_equal(sc.pos.view(np.int32), g.scene.pos.view(np.int32))
+        assert np.array_equal(sc.mesh_id, g.scene.mesh_id)
+        assert np.array_equal(sc.mats["transparency"], g.scene.mats["transparency"])
+
+
+def test_owner_map_partitions_the_image(rtb):
+    for (w, h, world) in ((3840, 2160, 8), (70, 45, 4), (33, 17, 3), (16, 16, 2)):
+        m = rtb.owner_map(w, h, world)
+        assert m.shape == (h, w) and m.min() >= 0 and m.max() < world
+        tx, ty = rtb.tile_grid(w, h)
+        assert sum(rtb.local_tile_count(w, h, r, world) for r in range(world)) == tx * ty
+        # bottom-left tile belongs to rank 0 (tile id 0), and Screen rows are flipped
+        assert m[h - 1, 0] == 0
+
+
+CPP_TEST = r"""
+#include "scene.h"
+#include "screen.h"
+#include "trackball.h"
+#include <cmath>
+#include <cstdio>
+int main(int argc, char** argv) {
+    Window window{"t", glm::ivec2(64, 32), OpenGLVersion::GL2};
+    Trackball camera{&window, glm::radians(50.0f), 3.0f};
+    camera.setCamera(glm::vec3(0.0f), glm::radians(glm::vec3(20.0f, 20.0f, 0.0f)), 3.0f);
+    const glm::vec3 p = camera.position();
+    if (std::fabs(glm::length(p) - 3.0f) > 1e-5f) return 1;
+    const Ray r = camera.generateRay(glm::vec2(0.0f, 0.0f));
+    // the central ray looks at the look-at point
+    const glm::vec3 to = glm::normalize(glm::vec3(0.0f) - p);
+    if (glm::length(r.direction - to) > 1e-5f) return 2;
+    Screen screen(glm::ivec2(4, 2));
+    screen.clear(glm::vec3(0.0f));
+    screen.setPixel(0, 0, glm::vec3(2.0f, 0.5f, -1.0f));   // bottom-left -> last row, first column
+    if (!(screen.pixels()[4] == glm::vec3(2.0f, 0.5f, -1.0f))) return 3;
+    screen.writeBitmapToFile(argv[1]);
+    Scene scene = loadScene(Cube, argv[2]);
+    if (scene.meshes.size() != 6 || scene.pointLights.size() != 1 || scene.spotLight.size() != 1) return 4;
+    std::printf("%zu meshes\n", scene.meshes.size());
+    return 0;
+}
+"""
+
+
+def test_cpp_host_api_compiles_and_runs(tmp_path):
+    host = os.path.join(ROOT, "raytracer-group27_b200", "host")
+    lib = os.path.join(ROOT, "raytracer-group27_b200")
+    (tmp_path / "t.cpp").write_text(CPP_TEST)
+    (tmp_path / "cube.obj").write_text("mtllib cube.mtl\n" + "".join(f"v {x} {y} {z}\n" for x in (0, 1) for y in (0, 1) for z in (0, 1))
+                                       + "".join(f"g face{i}\nusemtl m{i % 2}\nf {a} {b} {c}\n" for i, (a, b, c) in enumerate([(1, 2, 3), (2, 3, 4), (5, 6, 7), (6, 7, 8), (1, 5, 2), (3, 7, 4)])))
+    (tmp_path / "cube.mtl").write_text("newmtl m0\nKd 1 0 0\nnewmtl m1\nKd 0 1 0\n")
+    exe = tmp_path / "t"
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", f"-I{host}", f"-I{os.path.join(ROOT, 'include')}", str(tmp_path / "t.cpp"), "-o", str(exe),
+                        f"-L{lib}", "-lrtb200", f"-Wl,-rpath,{lib}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), str(tmp_path / "out.bmp"), str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    bmp = (tmp_path / "out.bmp").read_bytes()
+    assert bmp[:2] == b"BM" and len(bmp) == 54 + 4 * 2 * 4
+    # bottom-up BGRA rows: the first stored row is the image's last row, whose first pixel was set to (2, .5, -1) -> clamped (255, 127, 0)
+    assert bmp[54:58] == bytes([0, 127, 255, 255])

@@ -1,0 +1,74 @@
+"""CPU tests of the checker itself: the restated port against the golden vectors minted from the reference's own
+translation units, and (where oracle/_ref was built, i.e. in the container that has /root/reference) against that
+library run live."""
+import numpy as np
+import pytest
+
+from util import GOLDEN_NAMES, Golden, bits_equal
+
+FAST = [n for n in GOLDEN_NAMES if not n.startswith("dragon")]
+
+
+@pytest.mark.parametrize("name", FAST)
+def test_port_reproduces_golden(name):
+    g = Golden(name)
+    rgb, ids, t, st = g.oracle_render("port")
+    assert np.array_equal(ids, g.ids)
+    assert bits_equal(t, g.t)
+    assert bits_equal(rgb, g.rgb), f"max diff {np.abs(rgb - g.rgb).max()}"
+    assert (st.primary_rays, st.shadow_queries, st.secondary_rays) == g.counts
+
+
+@pytest.mark.parametrize("name", ["cube_96", "cornell_sph10_aa_80x48"])
+def test_port_exhaustive_shadow_variant(name):
+    g = Golden(name)
+    rgb, ids, t, st = g.oracle_render("port", shadow_exhaustive=True)
+    assert bits_equal(rgb, g.rgb_x)
+    assert (st.primary_rays, st.shadow_queries, st.secondary_rays) == g.counts_x
+
+
+def test_golden_records_port_reference_agreement():
+    """Every fixture stores whether port == verbatim reference (ids, t, rgb) when it was minted: ids and t always; rgb
+    wherever the reference's colour is defined (scenes that do not trip its uninitialised-barycentric read)."""
+    for name in GOLDEN_NAMES:
+        g = Golden(name)
+        ids_eq, t_eq, rgb_eq = (bool(v) for v in g.d["port_equals_reference"])
+        assert ids_eq and t_eq, name
+        if str(g.d["colour_from"]) == "reference":
+            assert rgb_eq, name
+
+
+def test_port_against_reference_library_live():
+    import oracle
+    if not oracle.available("reference"):
+        pytest.skip("oracle/_ref not built here (needs /root/reference)")
+    g = Golden("cornell_inside_128")
+    a = g.oracle_render("reference")
+    b = g.oracle_render("port")
+    assert np.array_equal(a[1], b[1]) and bits_equal(a[2], b[2]) and bits_equal(a[0], b[0])
+    assert a[3].rays == b[3].rays
+
+
+def test_brute_force_equals_bvh_in_the_oracle():
+    """the reference's useBVH=false and useBVH=true paths give the same frame on the Cornell box."""
+    g = Golden("cornell_c1_256")
+    a = g.oracle_render("port", use_bvh=True)
+    b = g.oracle_render("port", use_bvh=False)
+    assert np.array_equal(a[1], b[1]) and bits_equal(a[2], b[2]) and bits_equal(a[0], b[0])
+
+
+def test_closest_hit_api_and_unnormalised_directions():
+    """t is measured along normalize(d) but the hit point uses d itself (ray_tracing.cpp:65,111): scaling the direction
+    changes the reference's answer, and the oracle must show that quirk."""
+    import oracle
+    g = Golden("monkey_192")
+    rng = np.random.default_rng(1)
+    o = np.tile(np.array([[0.0, 0.0, -3.0]], np.float32), (2000, 1))
+    tgt = rng.uniform(-0.5, 0.5, (2000, 3)).astype(np.float32)
+    d = tgt - o
+    unit = d / np.linalg.norm(d, axis=1, keepdims=True)
+    P = oracle.Oracle("port")
+    ids1, t1 = P.closest_hit(g.scene.pos, g.scene.nrm, g.scene.mesh_id, np.concatenate([o, unit], 1))
+    ids3, t3 = P.closest_hit(g.scene.pos, g.scene.nrm, g.scene.mesh_id, np.concatenate([o, 3 * unit], 1))
+    assert (ids1 >= 0).sum() > 500
+    assert (ids1 != ids3).sum() > 0  # the un-normalised rays land elsewhere
