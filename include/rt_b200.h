@@ -111,6 +111,8 @@ int rt_set_counters(rt_ctx* ctx, int enable);
 #define RT_STAGE_COUNT 6
 int rt_set_stage_timing(rt_ctx* ctx, int enable);
 int rt_stage_times(rt_ctx* ctx, float* ms /* [RT_STAGE_COUNT] */, int* launches /* [RT_STAGE_COUNT] */);
+/* Shadow kernels of bounce level L run on a side stream concurrently with extend / shade of level L+1 (default on). */
+int rt_set_overlap(rt_ctx* ctx, int enable);
 /* Upper bound on primary rays per wavefront batch (default 2^24): ray-state memory is O(batch), not O(W*H*spp). */
 int rt_set_batch_rays(rt_ctx* ctx, unsigned int max_primary_rays_per_batch);
 

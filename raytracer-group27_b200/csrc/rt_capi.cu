@@ -86,9 +86,12 @@ struct rt_ctx {
     // frame state
     bool counters_enabled = false;
     unsigned batch_rays = 1u << 24;
-    DevBuf<float4> q_o[2], q_d[2], q_w[2], sp_p, sp_a, sp_b, ss_p, ss_a, ss_b, accum, fb;
+    DevBuf<float4> q_o[2], q_d[2], q_w[2], sp_p[2], sp_a[2], sp_b[2], ss_p[2], ss_a[2], ss_b[2], accum, fb;
     DevBuf<int2> q_hit[2];
-    DevBuf<float2> sphere_acc;
+    DevBuf<float2> sphere_acc[2];
+    cudaStream_t side = nullptr;          // shadow kernels of level L overlap extend / shade of level L+1
+    cudaEvent_t ev_shade[2] = { nullptr, nullptr }, ev_shadow[2] = { nullptr, nullptr };
+    bool overlap = true;
     DevBuf<Counters> counters;
     DevBuf<int> prim_id, out_id;
     DevBuf<float> prim_t, out_t, rgb;
@@ -246,6 +249,15 @@ int make_frame_params(const rt_ctx* ctx, const rt_camera* cam, const rt_params* 
     return RT_OK;
 }
 
+// Point the batch at the shadow queues / counters of one bounce-level parity.
+void set_parity(rt_ctx* ctx, BatchDev& b, int par)
+{
+    b.par = par;
+    b.sphere_acc = ctx->sphere_acc[par].p;
+    b.sq_point = ShadowQueue { ctx->sp_p[par].p, ctx->sp_a[par].p, ctx->sp_b[par].p };
+    b.sq_sphere = ShadowQueue { ctx->ss_p[par].p, ctx->ss_a[par].p, ctx->ss_b[par].p };
+}
+
 int ensure_batch(rt_ctx* ctx, const FrameParams& fp, unsigned batch_pixels, bool want_ids, BatchDev& b)
 {
     const size_t prim = (size_t)batch_pixels * fp.spp;
@@ -261,20 +273,20 @@ int ensure_batch(rt_ctx* ctx, const FrameParams& fp, unsigned batch_pixels, bool
         b.q[k].hit = ctx->q_hit[k].p;
     }
     const size_t cap_pt = cap * (size_t)std::max(1, fp.n_point), cap_sp = cap * (size_t)std::max(1, fp.n_sphere);
-    if (fp.n_point > 0) {
-        CK(ctx->sp_p.ensure(cap_pt));
-        CK(ctx->sp_a.ensure(cap_pt));
-        CK(ctx->sp_b.ensure(cap_pt));
+    for (int p = 0; p < 2; p++) {
+        if (fp.n_point > 0) {
+            CK(ctx->sp_p[p].ensure(cap_pt));
+            CK(ctx->sp_a[p].ensure(cap_pt));
+            CK(ctx->sp_b[p].ensure(cap_pt));
+        }
+        if (fp.n_sphere > 0) {
+            CK(ctx->ss_p[p].ensure(cap_sp));
+            CK(ctx->ss_a[p].ensure(cap_sp));
+            CK(ctx->ss_b[p].ensure(cap_sp));
+            CK(ctx->sphere_acc[p].ensure(cap_sp));
+        }
     }
-    if (fp.n_sphere > 0) {
-        CK(ctx->ss_p.ensure(cap_sp));
-        CK(ctx->ss_a.ensure(cap_sp));
-        CK(ctx->ss_b.ensure(cap_sp));
-        CK(ctx->sphere_acc.ensure(cap_sp));
-    }
-    b.sphere_acc = ctx->sphere_acc.p;
-    b.sq_point = ShadowQueue { ctx->sp_p.p, ctx->sp_a.p, ctx->sp_b.p };
-    b.sq_sphere = ShadowQueue { ctx->ss_p.p, ctx->ss_a.p, ctx->ss_b.p };
+    set_parity(ctx, b, 0);
     b.ray_capacity = (unsigned)std::min<size_t>(cap, 0xfffffff0u);
     b.shadow_pt_capacity = (unsigned)std::min<size_t>(cap_pt, 0xfffffff0u);
     b.shadow_sp_capacity = (unsigned)std::min<size_t>(cap_sp, 0xfffffff0u);
@@ -297,7 +309,9 @@ int ensure_batch(rt_ctx* ctx, const FrameParams& fp, unsigned batch_pixels, bool
 struct StageScope { // brackets one launch with events when stage timing is on
     rt_ctx* ctx;
     bool on;
-    StageScope(rt_ctx* c, int stage) : ctx(c), on(c->stage_timing)
+    size_t first = 0;
+    cudaStream_t stream;
+    StageScope(rt_ctx* c, int stage, cudaStream_t st) : ctx(c), on(c->stage_timing), stream(st)
     {
         if (!on)
             return;
@@ -307,14 +321,15 @@ struct StageScope { // brackets one launch with events when stage timing is on
             ctx->ev_pool.push_back(e);
         }
         ctx->ev_stage.push_back(stage);
-        cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream);
+        first = ctx->ev_used;
+        ctx->ev_used += 2;
+        cudaEventRecord(ctx->ev_pool[first], stream);
     }
     ~StageScope()
     {
         if (!on)
             return;
-        cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], ctx->stream);
-        ctx->ev_used += 2;
+        cudaEventRecord(ctx->ev_pool[first + 1], stream);
     }
 };
 
@@ -349,36 +364,53 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids
         }
         n_primary *= (unsigned long long)fp.spp;
         for (int level = 0; level <= fp.max_level; level++) {
-            const int qi = level & 1;
+            const int qi = level & 1, par = level & 1;
+            set_parity(ctx, b, par);
+            // the shadow queues of this parity were last read by the shadow kernels of level - 2
+            if (ctx->overlap && level >= 2)
+                CK(cudaStreamWaitEvent(st, ctx->ev_shadow[par], 0));
             // level 0 has no stored ray queue: K1 generate is fused into extend / shade (rays are a function of the index)
             if (level == 0)
-                launch_level_reset(st, b.counters, 1, (long long)n_lp * fp.spp, n_primary);
+                launch_level_reset(st, b.counters, 1, (long long)n_lp * fp.spp, n_primary, par);
             else
-                launch_level_reset(st, b.counters, qi ^ 1, -1, 0);
+                launch_level_reset(st, b.counters, qi ^ 1, -1, 0, par);
             {
-                StageScope sc(ctx, RT_STAGE_EXTEND);
+                StageScope sc(ctx, RT_STAGE_EXTEND, st);
                 launch_extend(st, ctx->sm_count, s, ctx->root_entry, fp, b, qi, level, (unsigned)first, ctx->counters_enabled);
             }
             {
-                StageScope sc(ctx, RT_STAGE_SHADE);
+                StageScope sc(ctx, RT_STAGE_SHADE, st);
                 launch_shade(st, ctx->sm_count, s, fp, b, qi, level, (unsigned)first);
             }
             launches += 3;
+            // shadow rays of this level: on the side stream, concurrently with extend / shade of the next level
+            cudaStream_t ss = ctx->overlap ? ctx->side : st;
+            if (ctx->overlap) {
+                CK(cudaEventRecord(ctx->ev_shade[par], st));
+                CK(cudaStreamWaitEvent(ss, ctx->ev_shade[par], 0));
+            }
             if (fp.n_point > 0) {
-                StageScope sc(ctx, RT_STAGE_SHADOW_POINT);
-                launch_shadow_point(st, ctx->sm_count, s, ctx->root_entry, fp, b, ctx->counters_enabled);
+                StageScope sc(ctx, RT_STAGE_SHADOW_POINT, ss);
+                launch_shadow_point(ss, ctx->sm_count, s, ctx->root_entry, fp, b, ctx->counters_enabled);
                 launches++;
             }
             if (fp.n_sphere > 0) {
-                StageScope sc(ctx, RT_STAGE_SHADOW_SPHERE);
-                launch_shadow_sphere(st, ctx->sm_count, s, ctx->root_entry, fp, b, ctx->counters_enabled);
+                StageScope sc(ctx, RT_STAGE_SHADOW_SPHERE, ss);
+                launch_shadow_sphere(ss, ctx->sm_count, s, ctx->root_entry, fp, b, ctx->counters_enabled);
                 launches += 2;
             }
+            if (ctx->overlap)
+                CK(cudaEventRecord(ctx->ev_shadow[par], ss));
+        }
+        if (ctx->overlap) { // join: everything of this batch is in the accumulators before the next batch / resolve
+            CK(cudaStreamWaitEvent(st, ctx->ev_shadow[0], 0));
+            if (fp.max_level >= 1)
+                CK(cudaStreamWaitEvent(st, ctx->ev_shadow[1], 0));
         }
         batches++;
     }
     if (n_local) {
-        StageScope sc(ctx, RT_STAGE_RESOLVE);
+        StageScope sc(ctx, RT_STAGE_RESOLVE, st);
         launch_resolve(st, ctx->sm_count, fp, ctx->accum.p, b.prim_id, b.prim_t, out, want_ids ? ctx->out_id.p : nullptr,
             want_ids ? ctx->out_t.p : nullptr);
         launches++;
@@ -436,6 +468,14 @@ int rt_create(int device, rt_ctx** out)
         return fail(RT_ERR_CUDA, "rt_create: stream / event / pinned allocation failed");
     }
     ctx->own_stream = true;
+    bool aux_ok = cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) == cudaSuccess;
+    for (int p = 0; p < 2; p++)
+        aux_ok = aux_ok && cudaEventCreateWithFlags(&ctx->ev_shade[p], cudaEventDisableTiming) == cudaSuccess
+            && cudaEventCreateWithFlags(&ctx->ev_shadow[p], cudaEventDisableTiming) == cudaSuccess;
+    if (!aux_ok) {
+        rt_destroy(ctx);
+        return fail(RT_ERR_CUDA, "rt_create: side stream / event creation failed");
+    }
     std::memset(ctx->h_counters, 0, sizeof(Counters));
     *out = ctx;
     return RT_OK;
@@ -448,8 +488,9 @@ int rt_destroy(rt_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     DevBuf<float4>* f4[] = { &ctx->d_plane, &ctx->d_v0, &ctx->d_v1, &ctx->d_v2, &ctx->d_n0, &ctx->d_n1, &ctx->d_n2, &ctx->d_nodes, &ctx->d_mats,
-        &ctx->d_point, &ctx->d_sphere, &ctx->q_o[0], &ctx->q_o[1], &ctx->q_d[0], &ctx->q_d[1], &ctx->q_w[0], &ctx->q_w[1], &ctx->sp_p, &ctx->sp_a,
-        &ctx->sp_b, &ctx->ss_p, &ctx->ss_a, &ctx->ss_b, &ctx->accum, &ctx->fb };
+        &ctx->d_point, &ctx->d_sphere, &ctx->q_o[0], &ctx->q_o[1], &ctx->q_d[0], &ctx->q_d[1], &ctx->q_w[0], &ctx->q_w[1], &ctx->sp_p[0], &ctx->sp_a[0],
+        &ctx->sp_b[0], &ctx->ss_p[0], &ctx->ss_a[0], &ctx->ss_b[0], &ctx->sp_p[1], &ctx->sp_a[1], &ctx->sp_b[1], &ctx->ss_p[1], &ctx->ss_a[1],
+        &ctx->ss_b[1], &ctx->accum, &ctx->fb };
     for (auto* b : f4)
         b->release();
     ctx->d_pos.release();
@@ -464,7 +505,8 @@ int rt_destroy(rt_ctx* ctx)
     ctx->prim_t.release();
     ctx->out_t.release();
     ctx->rgb.release();
-    ctx->sphere_acc.release();
+    ctx->sphere_acc[0].release();
+    ctx->sphere_acc[1].release();
     ctx->rays_in.release();
     ctx->flag.release();
     if (ctx->lbvh_nodes)
@@ -481,6 +523,14 @@ int rt_destroy(rt_ctx* ctx)
         cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream && ctx->stream)
         cudaStreamDestroy(ctx->stream);
+    if (ctx->side)
+        cudaStreamDestroy(ctx->side);
+    for (int p = 0; p < 2; p++) {
+        if (ctx->ev_shade[p])
+            cudaEventDestroy(ctx->ev_shade[p]);
+        if (ctx->ev_shadow[p])
+            cudaEventDestroy(ctx->ev_shadow[p]);
+    }
     delete ctx;
     return RT_OK;
 }
@@ -522,6 +572,14 @@ int rt_stage_times(rt_ctx* ctx, float* ms, int* launches)
         ms[k] = ctx->stage_ms[k];
         launches[k] = ctx->stage_launches[k];
     }
+    return RT_OK;
+}
+
+int rt_set_overlap(rt_ctx* ctx, int enable)
+{
+    if (!ctx)
+        return fail(RT_ERR_INVALID, "null context");
+    ctx->overlap = enable != 0;
     return RT_OK;
 }
 

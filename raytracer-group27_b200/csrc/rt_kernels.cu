@@ -189,11 +189,10 @@ __global__ void k_tri_setup(const float* __restrict__ pos, const float* __restri
 // ---------------------------------------------------------------------------------------------------------
 // Reset of the per-level cursors / queue fills (one thread).  n_current >= 0 sets the fill of the current queue
 // (level 0: the primary rays are generated on the fly, the queue only provides the hit slots).
-__global__ void k_level_reset(Counters* c, int next_q, long long n_current, unsigned long long add_primary)
+__global__ void k_level_reset(Counters* c, int next_q, long long n_current, unsigned long long add_primary, int par)
 {
-    c->work[0] = c->work[1] = c->work[2] = c->work[3] = 0;
-    c->n_shadow_pt = 0;
-    c->n_shadow_sp = 0;
+    c->work[0] = c->work[1] = 0;
+    c->sh[par].n_pt = c->sh[par].n_sp = c->sh[par].work_pt = c->sh[par].work_sp = 0;
     c->n_rays[next_q] = 0;
     if (n_current >= 0)
         c->n_rays[next_q ^ 1] = (unsigned)n_current;
@@ -263,16 +262,27 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
         sh.N = mk3(0, 0, 0);
         sh.mesh = 0;
         float4 m0 = make_float4(0, 0, 0, 0), m1 = make_float4(0, 0, 0, 1);
+        int2 h = make_int2(0, -1);
+        if (i < n) {
+            bool valid = true;
+            if (LEVEL0) { // padding pixels of ragged tiles have no hit record
+                int px, py;
+                local_to_pixel(fp, first_lp + i / (unsigned)fp.spp, px, py);
+                valid = px < fp.W && py < fp.H;
+            }
+            if (valid)
+                h = b.q[qi].hit[i];
+        }
+        // most slots of a level-0 frame are misses: a block without any hit has nothing to allocate
+        if (!__syncthreads_or(h.y >= 0))
+            continue;
         if (i < n) {
             f3 o, d;
             int tag = 0;
-            bool valid = true;
-            if (LEVEL0)
-                valid = generate_ray(fp, first_lp, i, o, d, tag);
-            const int2 h = valid ? b.q[qi].hit[i] : make_int2(0, -1);
             if (h.y >= 0) {
                 hit = true;
                 if (LEVEL0) {
+                    generate_ray(fp, first_lp, i, o, d, tag); // K1 again: the primary ray is a function of the index
                     w = mk3(1.0f, 1.0f, 1.0f);
                 } else {
                     const float4 op = b.q[qi].o_pix[i];
@@ -322,7 +332,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
 
         // one allocation round for: first child ray, point-light records (n_point per hit, contiguous), spherical-light
         // records (n_sphere per hit); a second round for the refraction child (dielectric hits only)
-        unsigned* const counters[3] = { &b.counters->n_rays[qo], &b.counters->n_shadow_pt, &b.counters->n_shadow_sp };
+        unsigned* const counters[3] = { &b.counters->n_rays[qo], &b.counters->sh[b.par].n_pt, &b.counters->sh[b.par].n_sp };
         const bool want[3] = { want0, hit && fp.n_point > 0, hit && fp.n_sphere > 0 };
         const unsigned cap[3] = { b.ray_capacity, b.shadow_pt_capacity / (unsigned)max(fp.n_point, 1), b.shadow_sp_capacity / (unsigned)max(fp.n_sphere, 1) };
         unsigned slot[3];
@@ -473,9 +483,9 @@ __device__ __forceinline__ void shadow_loop(const SceneDev& s, int root_entry, c
 template <bool ANYHIT, bool COUNT>
 __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_shadow_point(SceneDev s, int root_entry, FrameParams fp, BatchDev b)
 {
-    const unsigned n = b.counters->n_shadow_pt * (unsigned)fp.n_point;
+    const unsigned n = b.counters->sh[b.par].n_pt * (unsigned)fp.n_point;
     shadow_loop<ANYHIT, COUNT>(
-        s, root_entry, fp, b, &b.counters->work[2], n,
+        s, root_entry, fp, b, &b.counters->sh[b.par].work_pt, n,
         [&](unsigned i, f3& p1, f3& p2) {
             const float4 pp = b.sq_point.p_pix[i];
             const float4 al = b.sq_point.a_light[i];
@@ -499,9 +509,9 @@ template <bool ANYHIT, bool COUNT>
 __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_shadow_sphere(SceneDev s, int root_entry, FrameParams fp, BatchDev b)
 {
     const unsigned rc = (unsigned)fp.sl_rc;
-    const unsigned n = b.counters->n_shadow_sp * (unsigned)fp.n_sphere * rc;
+    const unsigned n = b.counters->sh[b.par].n_sp * (unsigned)fp.n_sphere * rc;
     shadow_loop<ANYHIT, COUNT>(
-        s, root_entry, fp, b, &b.counters->work[3], n,
+        s, root_entry, fp, b, &b.counters->sh[b.par].work_sp, n,
         [&](unsigned j, f3& p1, f3& p2) {
             const unsigned rec = j / rc;
             const int k = (int)(j % rc);
@@ -560,7 +570,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_shadow_sphere(SceneDev s, in
 // (shadow.cpp:212-221), then calcColor's A * intensity + B.
 __global__ void __launch_bounds__(256) k_sphere_finalize(FrameParams fp, BatchDev b)
 {
-    const unsigned n = b.counters->n_shadow_sp * (unsigned)fp.n_sphere;
+    const unsigned n = b.counters->sh[b.par].n_sp * (unsigned)fp.n_sphere;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float2 acc = b.sphere_acc[i];
         if (acc.y > 0.0f) {
@@ -665,9 +675,9 @@ void launch_tri_setup(cudaStream_t st, const float* pos, const float* nrm, const
     k_tri_setup<<<(n + 255) / 256, 256, 0, st>>>(pos, nrm, mesh_id, perm, n, plane, v0, v1, v2, n0, n1, n2);
 }
 
-void launch_level_reset(cudaStream_t st, Counters* c, int next_q, long long n_current, unsigned long long add_primary)
+void launch_level_reset(cudaStream_t st, Counters* c, int next_q, long long n_current, unsigned long long add_primary, int par)
 {
-    k_level_reset<<<1, 1, 0, st>>>(c, next_q, n_current, add_primary);
+    k_level_reset<<<1, 1, 0, st>>>(c, next_q, n_current, add_primary, par);
 }
 
 void launch_extend(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, int qi,

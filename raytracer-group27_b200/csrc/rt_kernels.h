@@ -9,7 +9,7 @@ void launch_tri_setup(cudaStream_t st, const float* pos, const float* nrm, const
     float4* plane, float4* v0, float4* v1, float4* v2, float4* n0, float4* n1, float4* n2);
 // n_current >= 0: fill of the current ray queue (level 0: primary rays are generated inside extend / shade from the
 // pixel index, the queue only provides the hit slots); add_primary: primary rays of the batch (counted on the host)
-void launch_level_reset(cudaStream_t st, Counters* c, int next_q, long long n_current, unsigned long long add_primary);
+void launch_level_reset(cudaStream_t st, Counters* c, int next_q, long long n_current, unsigned long long add_primary, int par);
 void launch_extend(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, int qi,
     int level, unsigned first_lp, bool count);
 void launch_shade(cudaStream_t st, int sm_count, const SceneDev& s, const FrameParams& fp, const BatchDev& b, int qi, int level, unsigned first_lp);

@@ -223,9 +223,17 @@ __device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, b
     bool active = false, more = n_items > 0;
     unsigned my = 0;
     const int lane = threadIdx.x & 31;
+    // Small queues (deep bounce levels, or one GPU's share of a frame split over many GPUs) cannot fill every lane of
+    // every resident warp; spreading them thinly over ALL warps (fewer rays per warp, more warps busy) hides the
+    // node-fetch latency far better than packing 32 rays into a few warps and leaving most SM warp slots empty.
+    const unsigned total_warps = gridDim.x * (blockDim.x >> 5);
+    const int quota = (int)min(32u, max(1u, (n_items + total_warps - 1) / total_warps));
     for (;;) {
-        // ---- refill: every idle lane takes the next unclaimed item ----
-        const unsigned idle = __ballot_sync(kFullMask, !active);
+        // ---- refill: idle lanes take the next unclaimed items (at most `quota` rays in flight per warp) ----
+        const unsigned idle_all = __ballot_sync(kFullMask, !active);
+        const int room = quota - (32 - __popc(idle_all));
+        // the `room` lowest idle lanes refill
+        const unsigned idle = __ballot_sync(kFullMask, !active && __popc(idle_all & ((1u << lane) - 1u)) < room);
         if (idle && more) {
             const int leader = __ffs(idle) - 1;
             const unsigned cnt = (unsigned)__popc(idle);
@@ -234,7 +242,7 @@ __device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, b
                 base = atomicAdd(cursor, cnt);
             base = __shfl_sync(kFullMask, base, leader);
             more = base + cnt < n_items;
-            if (!active) {
+            if (!active && ((idle >> lane) & 1u)) {
                 const unsigned item = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
                 if (item < n_items) {
                     f3 o, d;
@@ -258,7 +266,7 @@ __device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, b
                 }
             }
         }
-        if (!__any_sync(kFullMask, active)) {
+        if (idle_all == kFullMask && !__any_sync(kFullMask, active)) { // nothing in flight: stop, or fetch again
             if (!more)
                 break;
             continue;

@@ -70,11 +70,17 @@ struct FrameParams {
 // Device-resident counters of one wavefront batch.
 struct Counters {
     unsigned int n_rays[2];      // ray queue fill (ping-pong)
-    unsigned int n_shadow_pt;    // hits with point-light records (n_point consecutive records per hit)
-    unsigned int n_shadow_sp;    // hits with spherical-light records (n_sphere consecutive records per hit)
-    unsigned int work[4];        // dynamic work-fetch cursors: extend, shade, shadow_pt, shadow_sp
+    unsigned int work[2];        // dynamic work-fetch cursors: extend, (spare)
     unsigned int overflow;       // set when a queue would exceed its capacity
     unsigned int pad;
+    // Shadow work is double-buffered by bounce-level parity so that the shadow kernels of level L (side stream) can run
+    // concurrently with extend / shade of level L+1 (main stream).
+    struct Shadow {
+        unsigned int n_pt;       // hits with point-light records (n_point consecutive records per hit)
+        unsigned int n_sp;       // hits with spherical-light records (n_sphere consecutive records per hit)
+        unsigned int work_pt;    // work-fetch cursors of the two shadow kernels
+        unsigned int work_sp;
+    } sh[2];
     unsigned long long primary_rays;
     unsigned long long shadow_queries;
     unsigned long long secondary_rays;
@@ -106,6 +112,7 @@ struct BatchDev {
     unsigned int shadow_pt_capacity;
     unsigned int shadow_sp_capacity;
     Counters* counters;
+    int par;          // bounce-level parity selecting counters->sh[par]; the shadow queue pointers above are set to match
     float2* sphere_acc; // per spherical-light record: {sum of sample intensities, number of visible samples}
     float4* accum;    // per local padded pixel, summed radiance
     int* prim_id;     // nullable: closest-hit global triangle id of the first primary ray of each local pixel
