@@ -313,6 +313,8 @@ def run_gpu(args):
     e2e_value = float(e_r.item()) / float(e_ms.item()) / 1e3
 
     # ---- roofline of the dominant kernel (separate, untimed passes: stage events, then instrumented counters) ----
+    ctx.set_pipeline(1, 1)      # one batch, one stream: every kernel runs alone, so its events time it in isolation
+    ctx.set_overlap(False)
     ctx.set_stage_timing(True)
     stage_ms = {}
     for _ in range(3):
@@ -327,6 +329,8 @@ def run_gpu(args):
     frame()
     c = finish_step()
     ctx.set_counters(False)
+    ctx.set_pipeline(0, 1)
+    ctx.set_overlap(True)
     roof = roofline(stage, c, prm)
 
     line = None

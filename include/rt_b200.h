@@ -113,6 +113,10 @@ int rt_set_stage_timing(rt_ctx* ctx, int enable);
 int rt_stage_times(rt_ctx* ctx, float* ms /* [RT_STAGE_COUNT] */, int* launches /* [RT_STAGE_COUNT] */);
 /* Shadow kernels of bounce level L run on a side stream concurrently with extend / shade of level L+1 (default on). */
 int rt_set_overlap(rt_ctx* ctx, int enable);
+/* Batch pipelining: a frame is cut into about `batches_per_frame` batches (none smaller than min_batch_pixels) that are
+ * processed by `lanes` (1..4) independent sets of queues and streams, `lanes` batches at a time.  With rt_render, each
+ * finished batch (a band of complete image rows) is packed and copied to the host while later batches still render. */
+int rt_set_pipeline(rt_ctx* ctx, int lanes /* 0 = choose automatically (default) */, int batches_per_frame, unsigned int min_batch_pixels);
 /* Upper bound on primary rays per wavefront batch (default 2^24): ray-state memory is O(batch), not O(W*H*spp). */
 int rt_set_batch_rays(rt_ctx* ctx, unsigned int max_primary_rays_per_batch);
 

@@ -86,20 +86,33 @@ struct rt_ctx {
     // frame state
     bool counters_enabled = false;
     unsigned batch_rays = 1u << 24;
-    DevBuf<float4> q_o[2], q_d[2], q_w[2], sp_p[2], sp_a[2], sp_b[2], ss_p[2], ss_a[2], ss_b[2], accum, fb;
-    DevBuf<int2> q_hit[2];
-    DevBuf<float2> sphere_acc[2];
-    cudaStream_t side = nullptr;          // shadow kernels of level L overlap extend / shade of level L+1
-    cudaEvent_t ev_shade[2] = { nullptr, nullptr }, ev_shadow[2] = { nullptr, nullptr };
+    // Pipelined batches: a frame is cut into batches that run concurrently on up to kMaxLanes "lanes".  Each lane owns
+    // its ray / shadow queues, counters, a main stream (extend, shade, resolve, per-batch download) and a side stream
+    // (shadow kernels of level L overlap extend / shade of level L+1).  Tails of one batch's latency-bound deep levels
+    // are filled by other batches' work, and a finished batch's rows travel to the host while the others still render.
+    struct Lane {
+        cudaStream_t main = nullptr, side = nullptr;
+        cudaEvent_t ev_shade[2] = { nullptr, nullptr }, ev_shadow[2] = { nullptr, nullptr }, ev_done = nullptr;
+        DevBuf<float4> q_o[2], q_d[2], q_w[2], sp_p[2], sp_a[2], sp_b[2], ss_p[2], ss_a[2], ss_b[2];
+        DevBuf<int2> q_hit[2];
+        DevBuf<float2> sphere_acc[2];
+        DevBuf<Counters> counters;
+        bool used = false;
+    } lanes[kMaxLanes];
+    int n_lanes = 0;            // 0 = automatic
+    int batches_per_frame = 1;
+    unsigned min_batch_pixels = 1u << 18;
+    cudaEvent_t ev_start = nullptr;
     bool overlap = true;
-    DevBuf<Counters> counters;
+    DevBuf<float4> accum, fb;
     DevBuf<int> prim_id, out_id;
     DevBuf<float> prim_t, out_t, rgb;
     DevBuf<float> rays_in;
     DevBuf<unsigned> flag;
-    Counters* h_counters = nullptr; // pinned
+    Counters* h_counters = nullptr; // pinned, one per lane
     int fb_w = 0, fb_h = 0;
     int last_launches = 0, last_batches = 0;
+    unsigned last_overflow = 0;
     bool frame_pending = false;
 
     // optional per-stage device timing (events around every launch; off for timed frames)
@@ -250,59 +263,54 @@ int make_frame_params(const rt_ctx* ctx, const rt_camera* cam, const rt_params* 
 }
 
 // Point the batch at the shadow queues / counters of one bounce-level parity.
-void set_parity(rt_ctx* ctx, BatchDev& b, int par)
+void set_parity(rt_ctx::Lane& ln, BatchDev& b, int par)
 {
     b.par = par;
-    b.sphere_acc = ctx->sphere_acc[par].p;
-    b.sq_point = ShadowQueue { ctx->sp_p[par].p, ctx->sp_a[par].p, ctx->sp_b[par].p };
-    b.sq_sphere = ShadowQueue { ctx->ss_p[par].p, ctx->ss_a[par].p, ctx->ss_b[par].p };
+    b.sphere_acc = ln.sphere_acc[par].p;
+    b.sq_point = ShadowQueue { ln.sp_p[par].p, ln.sp_a[par].p, ln.sp_b[par].p };
+    b.sq_sphere = ShadowQueue { ln.ss_p[par].p, ln.ss_a[par].p, ln.ss_b[par].p };
 }
 
-int ensure_batch(rt_ctx* ctx, const FrameParams& fp, unsigned batch_pixels, bool want_ids, BatchDev& b)
+// Size one lane's queues for batches of `batch_pixels` pixels and describe them in `b`.
+int ensure_lane(rt_ctx* ctx, rt_ctx::Lane& ln, const FrameParams& fp, unsigned batch_pixels, bool want_ids, BatchDev& b)
 {
     const size_t prim = (size_t)batch_pixels * fp.spp;
     const size_t cap = prim * (ctx->any_transparent ? 2 : 1);
     for (int k = 0; k < 2; k++) {
-        CK(ctx->q_o[k].ensure(cap));
-        CK(ctx->q_d[k].ensure(cap));
-        CK(ctx->q_w[k].ensure(cap));
-        CK(ctx->q_hit[k].ensure(cap));
-        b.q[k].o_pix = ctx->q_o[k].p;
-        b.q[k].d = ctx->q_d[k].p;
-        b.q[k].w = ctx->q_w[k].p;
-        b.q[k].hit = ctx->q_hit[k].p;
+        CK(ln.q_hit[k].ensure(cap));
+        b.q[k].hit = ln.q_hit[k].p;
+        if (fp.max_level > 0) { // level 0 never stores rays (K1 is fused)
+            CK(ln.q_o[k].ensure(cap));
+            CK(ln.q_d[k].ensure(cap));
+            CK(ln.q_w[k].ensure(cap));
+        }
+        b.q[k].o_pix = ln.q_o[k].p;
+        b.q[k].d = ln.q_d[k].p;
+        b.q[k].w = ln.q_w[k].p;
     }
     const size_t cap_pt = cap * (size_t)std::max(1, fp.n_point), cap_sp = cap * (size_t)std::max(1, fp.n_sphere);
     for (int p = 0; p < 2; p++) {
         if (fp.n_point > 0) {
-            CK(ctx->sp_p[p].ensure(cap_pt));
-            CK(ctx->sp_a[p].ensure(cap_pt));
-            CK(ctx->sp_b[p].ensure(cap_pt));
+            CK(ln.sp_p[p].ensure(cap_pt));
+            CK(ln.sp_a[p].ensure(cap_pt));
+            CK(ln.sp_b[p].ensure(cap_pt));
         }
         if (fp.n_sphere > 0) {
-            CK(ctx->ss_p[p].ensure(cap_sp));
-            CK(ctx->ss_a[p].ensure(cap_sp));
-            CK(ctx->ss_b[p].ensure(cap_sp));
-            CK(ctx->sphere_acc[p].ensure(cap_sp));
+            CK(ln.ss_p[p].ensure(cap_sp));
+            CK(ln.ss_a[p].ensure(cap_sp));
+            CK(ln.ss_b[p].ensure(cap_sp));
+            CK(ln.sphere_acc[p].ensure(cap_sp));
         }
     }
-    set_parity(ctx, b, 0);
+    set_parity(ln, b, 0);
     b.ray_capacity = (unsigned)std::min<size_t>(cap, 0xfffffff0u);
     b.shadow_pt_capacity = (unsigned)std::min<size_t>(cap_pt, 0xfffffff0u);
     b.shadow_sp_capacity = (unsigned)std::min<size_t>(cap_sp, 0xfffffff0u);
-    CK(ctx->counters.ensure(1));
-    b.counters = ctx->counters.p;
-    const size_t n_local = (size_t)fp.n_local_tiles * kTilePixels;
-    CK(ctx->accum.ensure(std::max<size_t>(n_local, 1)));
+    CK(ln.counters.ensure(1));
+    b.counters = ln.counters.p;
     b.accum = ctx->accum.p;
-    b.prim_id = nullptr;
-    b.prim_t = nullptr;
-    if (want_ids) {
-        CK(ctx->prim_id.ensure(std::max<size_t>(n_local, 1)));
-        CK(ctx->prim_t.ensure(std::max<size_t>(n_local, 1)));
-        b.prim_id = ctx->prim_id.p;
-        b.prim_t = ctx->prim_t.p;
-    }
+    b.prim_id = want_ids ? ctx->prim_id.p : nullptr;
+    b.prim_t = want_ids ? ctx->prim_t.p : nullptr;
     return RT_OK;
 }
 
@@ -333,27 +341,83 @@ struct StageScope { // brackets one launch with events when stage timing is on
     }
 };
 
-// Enqueue one frame on the context's stream.  `out`: float4 framebuffer (Screen layout), maybe on a peer GPU.
-int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids, unsigned batch_rays)
+// Where rt_render wants the finished rows: packed float3 image on the host (pinned for full PCIe speed).
+struct HostTarget {
+    float* rgb = nullptr;
+};
+
+// Enqueue one frame.  `out`: float4 framebuffer (Screen layout), maybe on a peer GPU.  The frame starts and ends on the
+// context's stream; in between, its batches run on the lanes' own streams.
+int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids, unsigned batch_rays, const HostTarget* host)
 {
     const size_t n_local = (size_t)fp.n_local_tiles * kTilePixels;
-    unsigned batch_pixels = (unsigned)std::max<size_t>(kTilePixels, (batch_rays / (unsigned)fp.spp) / kTilePixels * (size_t)kTilePixels);
-    if ((size_t)batch_pixels > n_local)
-        batch_pixels = (unsigned)std::max<size_t>(n_local, kTilePixels);
-    BatchDev b;
-    int rc = ensure_batch(ctx, fp, batch_pixels, want_ids, b);
-    if (rc != RT_OK)
-        return rc;
+    // batch size: the frame split evenly over the lanes, in whole tile rows when this context owns the whole image (so
+    // that a finished batch is a band of complete image rows), bounded below (tiny batches are all latency) and above
+    // (ray-state memory is O(batch))
+    const size_t unit = (fp.world == 1 ? (size_t)fp.tiles_x : 1) * kTilePixels;
+    // Automatic pipeline shape (rt_set_pipeline(0, ...)), from measurements on C3 (profiles/README.md): every extra
+    // sequential batch costs about 0.4 ms of latency-bound deep levels, so a device-resident frame is cut in two
+    // concurrent halves at most; when rows have to travel to the host, 3 lanes x 2 rounds let the first round's
+    // download overlap the second round's rendering.
+    int lanes_wanted = ctx->n_lanes, batches_auto = ctx->batches_per_frame;
+    if (lanes_wanted <= 0) {
+        const bool big = n_local >= ((size_t)1 << 22);
+        if (host && host->rgb && fp.world == 1) {
+            lanes_wanted = big ? 3 : 1;
+            batches_auto = big ? 6 : 1;
+        } else {
+            lanes_wanted = big ? 2 : 1;
+            batches_auto = big ? 2 : 1;
+        }
+    }
+    lanes_wanted = std::max(1, std::min(lanes_wanted, kMaxLanes));
+    const size_t batches_wanted = (size_t)std::max(1, batches_auto);
+    size_t batch_pixels = (n_local + batches_wanted - 1) / batches_wanted;
+    batch_pixels = std::max<size_t>(batch_pixels, ctx->min_batch_pixels);
+    batch_pixels = (batch_pixels + unit - 1) / unit * unit; // whole tile rows, rounded up: at most batches_wanted batches
+    const size_t cap_pixels = std::max<size_t>(batch_rays / (unsigned)fp.spp, kTilePixels);
+    if (batch_pixels > cap_pixels)
+        batch_pixels = std::max<size_t>(unit, cap_pixels / unit * unit);
+    if (batch_pixels > n_local)
+        batch_pixels = std::max<size_t>(n_local, kTilePixels);
+    const size_t n_batches = n_local ? (n_local + batch_pixels - 1) / batch_pixels : 0;
+    const int n_lanes = (int)std::min<size_t>(lanes_wanted, std::max<size_t>(n_batches, 1));
+
+    CK(ctx->accum.ensure(std::max<size_t>(n_local, 1)));
+    if (want_ids) {
+        CK(ctx->prim_id.ensure(std::max<size_t>(n_local, 1)));
+        CK(ctx->prim_t.ensure(std::max<size_t>(n_local, 1)));
+    }
+    BatchDev bd[kMaxLanes];
+    for (int l = 0; l < n_lanes; l++) {
+        int rc = ensure_lane(ctx, ctx->lanes[l], fp, (unsigned)batch_pixels, want_ids, bd[l]);
+        if (rc != RT_OK)
+            return rc;
+        ctx->lanes[l].used = false;
+    }
+    for (int l = n_lanes; l < kMaxLanes; l++)
+        ctx->lanes[l].used = false;
     const SceneDev s = ctx->scene_dev();
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st0 = ctx->stream;
     int launches = 0, batches = 0;
     ctx->ev_used = 0;
     ctx->ev_stage.clear();
-    CK(cudaEventRecord(ctx->ev0, st));
-    CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(Counters), st));
+    CK(cudaEventRecord(ctx->ev0, st0));
     if (n_local)
-        CK(cudaMemsetAsync(ctx->accum.p, 0, n_local * sizeof(float4), st));
-    for (size_t first = 0; first < n_local; first += batch_pixels) {
+        CK(cudaMemsetAsync(ctx->accum.p, 0, n_local * sizeof(float4), st0));
+    CK(cudaEventRecord(ctx->ev_start, st0));
+    const bool band_download = host && host->rgb && fp.world == 1 && batch_pixels % ((size_t)fp.tiles_x * kTilePixels) == 0;
+
+    for (size_t first = 0; first < n_local; first += batch_pixels, batches++) {
+        const int li = batches % n_lanes;
+        rt_ctx::Lane& ln = ctx->lanes[li];
+        BatchDev& b = bd[li];
+        cudaStream_t st = ln.main;
+        if (!ln.used) {
+            ln.used = true;
+            CK(cudaStreamWaitEvent(st, ctx->ev_start, 0));
+            CK(cudaMemsetAsync(ln.counters.p, 0, sizeof(Counters), st));
+        }
         const unsigned n_lp = (unsigned)std::min<size_t>(batch_pixels, n_local - first);
         // primary rays of this batch: pixels of its tiles that lie inside the image, times samples per pixel
         unsigned long long n_primary = 0;
@@ -365,10 +429,10 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids
         n_primary *= (unsigned long long)fp.spp;
         for (int level = 0; level <= fp.max_level; level++) {
             const int qi = level & 1, par = level & 1;
-            set_parity(ctx, b, par);
+            set_parity(ln, b, par);
             // the shadow queues of this parity were last read by the shadow kernels of level - 2
             if (ctx->overlap && level >= 2)
-                CK(cudaStreamWaitEvent(st, ctx->ev_shadow[par], 0));
+                CK(cudaStreamWaitEvent(st, ln.ev_shadow[par], 0));
             // level 0 has no stored ray queue: K1 generate is fused into extend / shade (rays are a function of the index)
             if (level == 0)
                 launch_level_reset(st, b.counters, 1, (long long)n_lp * fp.spp, n_primary, par);
@@ -384,10 +448,10 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids
             }
             launches += 3;
             // shadow rays of this level: on the side stream, concurrently with extend / shade of the next level
-            cudaStream_t ss = ctx->overlap ? ctx->side : st;
+            cudaStream_t ss = ctx->overlap ? ln.side : st;
             if (ctx->overlap) {
-                CK(cudaEventRecord(ctx->ev_shade[par], st));
-                CK(cudaStreamWaitEvent(ss, ctx->ev_shade[par], 0));
+                CK(cudaEventRecord(ln.ev_shade[par], st));
+                CK(cudaStreamWaitEvent(ss, ln.ev_shade[par], 0));
             }
             if (fp.n_point > 0) {
                 StageScope sc(ctx, RT_STAGE_SHADOW_POINT, ss);
@@ -400,23 +464,43 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids
                 launches += 2;
             }
             if (ctx->overlap)
-                CK(cudaEventRecord(ctx->ev_shadow[par], ss));
+                CK(cudaEventRecord(ln.ev_shadow[par], ss));
         }
-        if (ctx->overlap) { // join: everything of this batch is in the accumulators before the next batch / resolve
-            CK(cudaStreamWaitEvent(st, ctx->ev_shadow[0], 0));
+        if (ctx->overlap) { // join: everything of this batch is in the accumulators before its resolve
+            CK(cudaStreamWaitEvent(st, ln.ev_shadow[0], 0));
             if (fp.max_level >= 1)
-                CK(cudaStreamWaitEvent(st, ctx->ev_shadow[1], 0));
+                CK(cudaStreamWaitEvent(st, ln.ev_shadow[1], 0));
         }
-        batches++;
+        {
+            StageScope sc(ctx, RT_STAGE_RESOLVE, st);
+            launch_resolve(st, ctx->sm_count, fp, (unsigned)first, n_lp, ctx->accum.p, b.prim_id, b.prim_t, out, want_ids ? ctx->out_id.p : nullptr,
+                want_ids ? ctx->out_t.p : nullptr);
+            launches++;
+        }
+        if (band_download) {
+            // this batch is a band of complete image rows: pack it to float3 and send it home while the other lanes render
+            const int ty0 = (int)(first / kTilePixels / fp.tiles_x), ty1 = (int)((first + n_lp) / kTilePixels / fp.tiles_x);
+            const size_t row_lo = (size_t)(fp.H - std::min(fp.H, ty1 * kTileH)), row_hi = (size_t)(fp.H - ty0 * kTileH);
+            const size_t p0 = row_lo * fp.W, p1 = row_hi * fp.W;
+            launch_pack_rgb(st, ctx->sm_count, out, ctx->rgb.p, p0, p1);
+            launches++;
+            CK(cudaMemcpyAsync(host->rgb + 3 * p0, ctx->rgb.p + 3 * p0, (p1 - p0) * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaEventRecord(ln.ev_done, st));
     }
-    if (n_local) {
-        StageScope sc(ctx, RT_STAGE_RESOLVE, st);
-        launch_resolve(st, ctx->sm_count, fp, ctx->accum.p, b.prim_id, b.prim_t, out, want_ids ? ctx->out_id.p : nullptr,
-            want_ids ? ctx->out_t.p : nullptr);
+    for (int l = 0; l < n_lanes; l++)
+        if (ctx->lanes[l].used)
+            CK(cudaStreamWaitEvent(st0, ctx->lanes[l].ev_done, 0));
+    if (host && host->rgb && !band_download && n_local) {
+        const size_t npx = (size_t)fp.W * fp.H;
+        launch_pack_rgb(st0, ctx->sm_count, out, ctx->rgb.p, 0, npx);
         launches++;
+        CK(cudaMemcpyAsync(host->rgb, ctx->rgb.p, npx * 3 * sizeof(float), cudaMemcpyDeviceToHost, st0));
     }
-    CK(cudaEventRecord(ctx->ev1, st));
-    CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->ev1, st0));
+    for (int l = 0; l < n_lanes; l++)
+        if (ctx->lanes[l].used)
+            CK(cudaMemcpyAsync(&ctx->h_counters[l], ctx->lanes[l].counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, st0));
     CK(cudaGetLastError());
     ctx->last_launches = launches;
     ctx->last_batches = batches;
@@ -463,20 +547,26 @@ int rt_create(int device, rt_ctx** out)
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess
         || cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess
-        || cudaMallocHost(&ctx->h_counters, sizeof(Counters)) != cudaSuccess) {
+        || cudaMallocHost(&ctx->h_counters, kMaxLanes * sizeof(Counters)) != cudaSuccess) {
         delete ctx;
         return fail(RT_ERR_CUDA, "rt_create: stream / event / pinned allocation failed");
     }
     ctx->own_stream = true;
-    bool aux_ok = cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) == cudaSuccess;
-    for (int p = 0; p < 2; p++)
-        aux_ok = aux_ok && cudaEventCreateWithFlags(&ctx->ev_shade[p], cudaEventDisableTiming) == cudaSuccess
-            && cudaEventCreateWithFlags(&ctx->ev_shadow[p], cudaEventDisableTiming) == cudaSuccess;
+    bool aux_ok = cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming) == cudaSuccess;
+    for (int l = 0; l < kMaxLanes; l++) {
+        rt_ctx::Lane& ln = ctx->lanes[l];
+        aux_ok = aux_ok && cudaStreamCreateWithFlags(&ln.main, cudaStreamNonBlocking) == cudaSuccess
+            && cudaStreamCreateWithFlags(&ln.side, cudaStreamNonBlocking) == cudaSuccess
+            && cudaEventCreateWithFlags(&ln.ev_done, cudaEventDisableTiming) == cudaSuccess;
+        for (int p = 0; p < 2; p++)
+            aux_ok = aux_ok && cudaEventCreateWithFlags(&ln.ev_shade[p], cudaEventDisableTiming) == cudaSuccess
+                && cudaEventCreateWithFlags(&ln.ev_shadow[p], cudaEventDisableTiming) == cudaSuccess;
+    }
     if (!aux_ok) {
         rt_destroy(ctx);
         return fail(RT_ERR_CUDA, "rt_create: side stream / event creation failed");
     }
-    std::memset(ctx->h_counters, 0, sizeof(Counters));
+    std::memset(ctx->h_counters, 0, kMaxLanes * sizeof(Counters));
     *out = ctx;
     return RT_OK;
 }
@@ -488,25 +578,41 @@ int rt_destroy(rt_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     DevBuf<float4>* f4[] = { &ctx->d_plane, &ctx->d_v0, &ctx->d_v1, &ctx->d_v2, &ctx->d_n0, &ctx->d_n1, &ctx->d_n2, &ctx->d_nodes, &ctx->d_mats,
-        &ctx->d_point, &ctx->d_sphere, &ctx->q_o[0], &ctx->q_o[1], &ctx->q_d[0], &ctx->q_d[1], &ctx->q_w[0], &ctx->q_w[1], &ctx->sp_p[0], &ctx->sp_a[0],
-        &ctx->sp_b[0], &ctx->ss_p[0], &ctx->ss_a[0], &ctx->ss_b[0], &ctx->sp_p[1], &ctx->sp_a[1], &ctx->sp_b[1], &ctx->ss_p[1], &ctx->ss_a[1],
-        &ctx->ss_b[1], &ctx->accum, &ctx->fb };
+        &ctx->d_point, &ctx->d_sphere, &ctx->accum, &ctx->fb };
     for (auto* b : f4)
         b->release();
+    for (int l = 0; l < kMaxLanes; l++) {
+        rt_ctx::Lane& ln = ctx->lanes[l];
+        for (int k = 0; k < 2; k++) {
+            DevBuf<float4>* q[] = { &ln.q_o[k], &ln.q_d[k], &ln.q_w[k], &ln.sp_p[k], &ln.sp_a[k], &ln.sp_b[k], &ln.ss_p[k], &ln.ss_a[k], &ln.ss_b[k] };
+            for (auto* b : q)
+                b->release();
+            ln.q_hit[k].release();
+            ln.sphere_acc[k].release();
+            if (ln.ev_shade[k])
+                cudaEventDestroy(ln.ev_shade[k]);
+            if (ln.ev_shadow[k])
+                cudaEventDestroy(ln.ev_shadow[k]);
+        }
+        ln.counters.release();
+        if (ln.ev_done)
+            cudaEventDestroy(ln.ev_done);
+        if (ln.main)
+            cudaStreamDestroy(ln.main);
+        if (ln.side)
+            cudaStreamDestroy(ln.side);
+    }
+    if (ctx->ev_start)
+        cudaEventDestroy(ctx->ev_start);
     ctx->d_pos.release();
     ctx->d_nrm.release();
     ctx->d_mesh.release();
     ctx->d_perm.release();
-    ctx->q_hit[0].release();
-    ctx->q_hit[1].release();
-    ctx->counters.release();
     ctx->prim_id.release();
     ctx->out_id.release();
     ctx->prim_t.release();
     ctx->out_t.release();
     ctx->rgb.release();
-    ctx->sphere_acc[0].release();
-    ctx->sphere_acc[1].release();
     ctx->rays_in.release();
     ctx->flag.release();
     if (ctx->lbvh_nodes)
@@ -523,14 +629,6 @@ int rt_destroy(rt_ctx* ctx)
         cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream && ctx->stream)
         cudaStreamDestroy(ctx->stream);
-    if (ctx->side)
-        cudaStreamDestroy(ctx->side);
-    for (int p = 0; p < 2; p++) {
-        if (ctx->ev_shade[p])
-            cudaEventDestroy(ctx->ev_shade[p]);
-        if (ctx->ev_shadow[p])
-            cudaEventDestroy(ctx->ev_shadow[p]);
-    }
     delete ctx;
     return RT_OK;
 }
@@ -580,6 +678,16 @@ int rt_set_overlap(rt_ctx* ctx, int enable)
     if (!ctx)
         return fail(RT_ERR_INVALID, "null context");
     ctx->overlap = enable != 0;
+    return RT_OK;
+}
+
+int rt_set_pipeline(rt_ctx* ctx, int lanes, int batches_per_frame, unsigned int min_batch_pixels)
+{
+    if (!ctx || lanes < 0 || lanes > kMaxLanes || (lanes > 0 && batches_per_frame < 1))
+        return fail(RT_ERR_INVALID, "rt_set_pipeline: lanes must be 0 (automatic) or 1..4, batches_per_frame >= 1");
+    ctx->n_lanes = lanes;
+    ctx->batches_per_frame = batches_per_frame;
+    ctx->min_batch_pixels = std::max<unsigned>(min_batch_pixels, (unsigned)kTilePixels);
     return RT_OK;
 }
 
@@ -775,7 +883,7 @@ int rt_render_device(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, vo
         }
         out = ctx->fb.p;
     }
-    return enqueue_frame(ctx, fp, out, false, ctx->batch_rays);
+    return enqueue_frame(ctx, fp, out, false, ctx->batch_rays, nullptr);
 }
 
 int rt_sync(rt_ctx* ctx, rt_stats* stats)
@@ -797,10 +905,27 @@ int rt_sync(rt_ctx* ctx, rt_stats* stats)
                 ctx->stage_launches[ctx->ev_stage[k / 2]]++;
             }
         }
-        const Counters& c = *ctx->h_counters;
+        Counters c; // totals over the lanes used by the frame
+        std::memset(&c, 0, sizeof(c));
+        for (int l = 0; l < kMaxLanes; l++) {
+            if (!ctx->lanes[l].used)
+                continue;
+            const Counters& h = ctx->h_counters[l];
+            c.overflow = std::max(c.overflow, h.overflow);
+            c.primary_rays += h.primary_rays;
+            c.shadow_queries += h.shadow_queries;
+            c.secondary_rays += h.secondary_rays;
+            c.node_visits += h.node_visits;
+            c.tri_tests += h.tri_tests;
+            c.tri_tests_full += h.tri_tests_full;
+            c.ext_node_visits += h.ext_node_visits;
+            c.ext_tri_tests += h.ext_tri_tests;
+            c.ext_tri_tests_full += h.ext_tri_tests_full;
+        }
+        ctx->last_overflow = c.overflow;
         if (c.overflow == 1)
             return fail(RT_ERR_OVERFLOW, "a ray queue overflowed (transparent materials doubled the wavefront more than provisioned); lower rt_set_batch_rays");
-        if (c.overflow == 2)
+        if (c.overflow >= 2)
             return fail(RT_ERR_OVERFLOW, "traversal stack overflow");
         if (stats) {
             std::memset(stats, 0, sizeof(*stats));
@@ -889,7 +1014,7 @@ int rt_download_rgb(rt_ctx* ctx, const void* d_rgba, int width, int height, floa
         return fail(RT_ERR_INVALID, "rt_download_rgb: bad arguments");
     const size_t npx = (size_t)width * height;
     CK(ctx->rgb.ensure(npx * 3 + 4));
-    launch_pack_rgb(ctx->stream, ctx->sm_count, (const float4*)d_rgba, ctx->rgb.p, npx);
+    launch_pack_rgb(ctx->stream, ctx->sm_count, (const float4*)d_rgba, ctx->rgb.p, 0, npx);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(rgb_out, ctx->rgb.p, npx * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -927,24 +1052,21 @@ int rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, float* rg
     CK(ctx->rgb.ensure(npx * 3 + 4));
     unsigned batch = ctx->batch_rays;
     for (int attempt = 0;; attempt++) {
-        rc = enqueue_frame(ctx, fp, ctx->fb.p, want_ids, batch);
+        HostTarget host;
+        host.rgb = rgb_out; // finished bands are packed and copied by the lanes while the rest of the frame renders
+        rc = enqueue_frame(ctx, fp, ctx->fb.p, want_ids, batch, &host);
         if (rc)
             return rc;
-        launch_pack_rgb(ctx->stream, ctx->sm_count, ctx->fb.p, ctx->rgb.p, npx);
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(rgb_out, ctx->rgb.p, npx * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
         if (tri_id_out)
             CK(cudaMemcpyAsync(tri_id_out, ctx->out_id.p, npx * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         if (t_out)
             CK(cudaMemcpyAsync(t_out, ctx->out_t.p, npx * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
         rc = rt_sync(ctx, stats);
         // queue overflow from ray splitting: halve the batch (doubling the head-room) and render again
-        if (rc == RT_ERR_OVERFLOW && ctx->h_counters->overflow == 1 && attempt < 3 && batch / 2 >= (unsigned)kTilePixels * (unsigned)fp.spp) {
+        if (rc == RT_ERR_OVERFLOW && ctx->last_overflow == 1 && attempt < 3 && batch / 2 >= (unsigned)kTilePixels * (unsigned)fp.spp) {
             batch /= 2;
             continue;
         }
-        if (rc == RT_OK && stats)
-            stats->kernel_launches += 1;
         return rc;
     }
 }

@@ -228,7 +228,8 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_extend(SceneDev s, int root_
                 b.prim_t[tag >> 1] = best.t;
             }
             return false;
-        });
+        },
+        LEVEL0 ? 32 : RT_MAX_QUOTA);
     if (COUNT) {
         warp_add_u64(&b.counters->node_visits, st.nodes);
         warp_add_u64(&b.counters->tri_tests, st.tris);
@@ -469,7 +470,8 @@ __device__ __forceinline__ void shadow_loop(const SceneDev& s, int root_entry, c
             }
             item_end(item, r == 0, cs.intensity);
             return false;
-        });
+        },
+        RT_MAX_QUOTA);
     warp_add_u64(&b.counters->shadow_queries, queries);
     if (COUNT) {
         warp_add_u64(&b.counters->node_visits, st.nodes);
@@ -587,11 +589,10 @@ __global__ void __launch_bounds__(256) k_sphere_finalize(FrameParams fp, BatchDe
 // K5 resolve: sample average (src/main.cpp:374,384) and Screen::setPixel's y flip (src/screen.cpp:32-38).  One
 // warp writes one 32-pixel tile row = 512 contiguous bytes of float4; `out` may be a peer-mapped framebuffer of
 // another GPU (the gather of finished tiles fused into this store).
-__global__ void __launch_bounds__(256) k_resolve(FrameParams fp, const float4* __restrict__ accum, const int* __restrict__ prim_id,
-    const float* __restrict__ prim_t, float4* out, int* out_id, float* out_t)
+__global__ void __launch_bounds__(256) k_resolve(FrameParams fp, unsigned first_lp, unsigned n_lp, const float4* __restrict__ accum,
+    const int* __restrict__ prim_id, const float* __restrict__ prim_t, float4* out, int* out_id, float* out_t)
 {
-    const unsigned n = (unsigned)fp.n_local_tiles * kTilePixels;
-    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    for (unsigned idx = first_lp + blockIdx.x * blockDim.x + threadIdx.x; idx < first_lp + n_lp; idx += gridDim.x * blockDim.x) {
         const unsigned j = idx / kTilePixels, k = idx % kTilePixels;
         const unsigned x = k % kTileW, y = k / kTileW; // row-major inside the tile for coalesced stores
         const unsigned g = (unsigned)fp.rank + j * (unsigned)fp.world;
@@ -609,30 +610,27 @@ __global__ void __launch_bounds__(256) k_resolve(FrameParams fp, const float4* _
     }
 }
 
-// float4 framebuffer -> packed float3 (the host Screen's std::vector<glm::vec3>), written as float4 words.
-__global__ void __launch_bounds__(256) k_pack_rgb(const float4* __restrict__ in, float* __restrict__ out, size_t n_pixels)
+// float4 framebuffer -> packed float3 (the host Screen's std::vector<glm::vec3>) for pixels [p0, p1).  One thread packs
+// a group of 4 pixels = 48 bytes = 3 aligned float4 stores; groups cut by the range ends fall back to scalar stores.
+__global__ void __launch_bounds__(256) k_pack_rgb(const float4* __restrict__ in, float* __restrict__ out, size_t p0, size_t p1)
 {
-    const size_t n_words = (n_pixels * 3 + 3) / 4; // float4 words of the packed image
-    for (size_t wi = blockIdx.x * (size_t)blockDim.x + threadIdx.x; wi < n_words; wi += (size_t)gridDim.x * blockDim.x) {
-        float v[4];
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const size_t f = wi * 4 + c;
-            const size_t p = f / 3;
-            const int ch = (int)(f % 3);
-            float val = 0.0f;
-            if (p < n_pixels) {
-                const float4 px = in[p];
-                val = ch == 0 ? px.x : (ch == 1 ? px.y : px.z);
+    const size_t g0 = p0 / 4, g1 = (p1 + 3) / 4;
+    for (size_t g = g0 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < g1; g += (size_t)gridDim.x * blockDim.x) {
+        const size_t p = 4 * g;
+        if (p >= p0 && p + 4 <= p1) {
+            const float4 a = in[p], b = in[p + 1], c = in[p + 2], d = in[p + 3];
+            float4* o = reinterpret_cast<float4*>(out + 3 * p);
+            o[0] = make_float4(a.x, a.y, a.z, b.x);
+            o[1] = make_float4(b.y, b.z, c.x, c.y);
+            o[2] = make_float4(c.z, d.x, d.y, d.z);
+        } else {
+            for (size_t q = (p > p0 ? p : p0); q < p + 4 && q < p1; q++) {
+                const float4 a = in[q];
+                out[3 * q] = a.x;
+                out[3 * q + 1] = a.y;
+                out[3 * q + 2] = a.z;
             }
-            v[c] = val;
         }
-        if (wi * 4 + 3 < n_pixels * 3)
-            reinterpret_cast<float4*>(out)[wi] = make_float4(v[0], v[1], v[2], v[3]);
-        else
-            for (int c = 0; c < 4; c++)
-                if (wi * 4 + c < n_pixels * 3)
-                    out[wi * 4 + c] = v[c];
     }
 }
 
@@ -734,17 +732,19 @@ void launch_shadow_sphere(cudaStream_t st, int sm_count, const SceneDev& s, int 
     k_sphere_finalize<<<sm_count * 4, 256, 0, st>>>(fp, b);
 }
 
-void launch_resolve(cudaStream_t st, int sm_count, const FrameParams& fp, const float4* accum, const int* prim_id, const float* prim_t,
-    float4* out, int* out_id, float* out_t)
+void launch_resolve(cudaStream_t st, int sm_count, const FrameParams& fp, unsigned first_lp, unsigned n_lp, const float4* accum,
+    const int* prim_id, const float* prim_t, float4* out, int* out_id, float* out_t)
 {
-    const long long n = (long long)fp.n_local_tiles * kTilePixels;
-    k_resolve<<<grid_for(n, 256, sm_count * 8), 256, 0, st>>>(fp, accum, prim_id, prim_t, out, out_id, out_t);
+    if (n_lp == 0)
+        return;
+    k_resolve<<<grid_for(n_lp, 256, sm_count * 8), 256, 0, st>>>(fp, first_lp, n_lp, accum, prim_id, prim_t, out, out_id, out_t);
 }
 
-void launch_pack_rgb(cudaStream_t st, int sm_count, const float4* in, float* out, size_t n_pixels)
+void launch_pack_rgb(cudaStream_t st, int sm_count, const float4* in, float* out, size_t p0, size_t p1)
 {
-    const long long n = (long long)((n_pixels * 3 + 3) / 4);
-    k_pack_rgb<<<grid_for(n, 256, sm_count * 8), 256, 0, st>>>(in, out, n_pixels);
+    if (p1 <= p0)
+        return;
+    k_pack_rgb<<<grid_for((long long)((p1 - p0 + 3) / 4 + 1), 256, sm_count * 8), 256, 0, st>>>(in, out, p0, p1);
 }
 
 void launch_intersect(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const float* rays, long long n, int use_bvh,

@@ -15,9 +15,9 @@ void launch_extend(cudaStream_t st, int sm_count, const SceneDev& s, int root_en
 void launch_shade(cudaStream_t st, int sm_count, const SceneDev& s, const FrameParams& fp, const BatchDev& b, int qi, int level, unsigned first_lp);
 void launch_shadow_point(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count);
 void launch_shadow_sphere(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count);
-void launch_resolve(cudaStream_t st, int sm_count, const FrameParams& fp, const float4* accum, const int* prim_id, const float* prim_t,
-    float4* out, int* out_id, float* out_t);
-void launch_pack_rgb(cudaStream_t st, int sm_count, const float4* in, float* out, size_t n_pixels);
+void launch_resolve(cudaStream_t st, int sm_count, const FrameParams& fp, unsigned first_lp, unsigned n_lp, const float4* accum,
+    const int* prim_id, const float* prim_t, float4* out, int* out_id, float* out_t);
+void launch_pack_rgb(cudaStream_t st, int sm_count, const float4* in, float* out, size_t p0, size_t p1);
 void launch_intersect(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const float* rays, long long n, int use_bvh,
     int* tri_id, float* t_out, unsigned* overflow);
 

@@ -213,7 +213,7 @@ __device__ __forceinline__ void trav_leaf_step(const SceneDev& s, Trav& tv, cons
 // same item with a new segment (shadow rays passing a transparent surface).
 template <bool ANYHIT, bool COUNT, typename Fetch, typename Finish>
 __device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, bool exhaustive, unsigned* cursor, unsigned n_items,
-    TraceStats& st, Fetch fetch, Finish finish)
+    TraceStats& st, Fetch fetch, Finish finish, int max_quota = 32)
 {
     constexpr unsigned kFullMask = 0xffffffffu;
     int stack[kStackDepth * (RT_STACK_TMIN ? 2 : 1)];
@@ -227,7 +227,10 @@ __device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, b
     // every resident warp; spreading them thinly over ALL warps (fewer rays per warp, more warps busy) hides the
     // node-fetch latency far better than packing 32 rays into a few warps and leaving most SM warp slots empty.
     const unsigned total_warps = gridDim.x * (blockDim.x >> 5);
-    const int quota = (int)min(32u, max(1u, (n_items + total_warps - 1) / total_warps));
+#ifndef RT_MAX_QUOTA
+#define RT_MAX_QUOTA 32
+#endif
+    const int quota = (int)min((unsigned)max_quota, max(1u, (n_items + total_warps - 1) / total_warps));
     for (;;) {
         // ---- refill: idle lanes take the next unclaimed items (at most `quota` rays in flight per warp) ----
         const unsigned idle_all = __ballot_sync(kFullMask, !active);

@@ -13,6 +13,7 @@ constexpr int kTilePixels = kTileW * kTileH;
 
 constexpr int kMaxLeafTris = 8;   // leaf size must fit the 3-bit count of a packed stack entry
 constexpr int kStackDepth = 64;   // per-thread traversal stack (ints); builders guarantee depth < kStackDepth
+constexpr int kMaxLanes = 4;       // batches of one frame in flight at once (rt_set_pipeline)
 constexpr int kMaxPointLights = 16;
 constexpr int kMaxSphereLights = 8;
 

@@ -74,6 +74,7 @@ SYMBOLS = [
     ("rt_set_counters", _I, [_P, _I]),
     ("rt_set_batch_rays", _I, [_P, C.c_uint]),
     ("rt_set_overlap", _I, [_P, _I]),
+    ("rt_set_pipeline", _I, [_P, _I, _I, C.c_uint]),
     ("rt_set_stage_timing", _I, [_P, _I]),
     ("rt_stage_times", _I, [_P, _P, _P]),
     ("rt_set_shard", _I, [_P, _I, _I]),
@@ -247,6 +248,9 @@ class Context:
         n = (C.c_int * 6)()
         _check(self._l.rt_stage_times(self._h, ms, n))
         return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(self.STAGES)}
+
+    def set_pipeline(self, lanes: int, batches_per_frame: int, min_batch_pixels: int = 1 << 18):
+        _check(self._l.rt_set_pipeline(self._h, lanes, batches_per_frame, min_batch_pixels))
 
     def set_overlap(self, enable: bool):
         _check(self._l.rt_set_overlap(self._h, 1 if enable else 0))
