@@ -76,6 +76,7 @@ typedef struct {
 
 #define RT_BVH_LBVH_DEVICE 0      /* Morton codes -> radix sort -> Karras hierarchy -> refit, all on the GPU */
 #define RT_BVH_SAH_HOST 1         /* binned SAH built by the host and uploaded                               */
+#define RT_BVH_AUTO 2             /* SAH_HOST up to 2^22 triangles, LBVH_DEVICE beyond                        */
 
 /* ---- lifetime ---- */
 int rt_create(int device, rt_ctx** out);

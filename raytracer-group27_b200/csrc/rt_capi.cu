@@ -92,7 +92,7 @@ struct rt_ctx {
     // are filled by other batches' work, and a finished batch's rows travel to the host while the others still render.
     struct Lane {
         cudaStream_t main = nullptr, side = nullptr;
-        cudaEvent_t ev_shade[2] = { nullptr, nullptr }, ev_shadow[2] = { nullptr, nullptr }, ev_done = nullptr;
+        cudaEvent_t ev_shade[2] = { nullptr, nullptr }, ev_shadow[2] = { nullptr, nullptr }, ev_done = nullptr, ev_packed = nullptr;
         DevBuf<float4> q_o[2], q_d[2], q_w[2], sp_p[2], sp_a[2], sp_b[2], ss_p[2], ss_a[2], ss_b[2];
         DevBuf<int2> q_hit[2];
         DevBuf<float2> sphere_acc[2];
@@ -102,7 +102,8 @@ struct rt_ctx {
     int n_lanes = 0;            // 0 = automatic
     int batches_per_frame = 1;
     unsigned min_batch_pixels = 1u << 18;
-    cudaEvent_t ev_start = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_copied = nullptr;
+    cudaStream_t copy = nullptr; // band downloads: must not hold up the next batch on the lane that produced the band
     bool overlap = true;
     DevBuf<float4> accum, fb;
     DevBuf<int> prim_id, out_id;
@@ -357,14 +358,14 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids
     const size_t unit = (fp.world == 1 ? (size_t)fp.tiles_x : 1) * kTilePixels;
     // Automatic pipeline shape (rt_set_pipeline(0, ...)), from measurements on C3 (profiles/README.md): every extra
     // sequential batch costs about 0.4 ms of latency-bound deep levels, so a device-resident frame is cut in two
-    // concurrent halves at most; when rows have to travel to the host, 3 lanes x 2 rounds let the first round's
-    // download overlap the second round's rendering.
+    // concurrent halves at most; when rows have to travel to the host, three bands on two lanes let the first bands'
+    // download overlap the last band's rendering.
     int lanes_wanted = ctx->n_lanes, batches_auto = ctx->batches_per_frame;
     if (lanes_wanted <= 0) {
         const bool big = n_local >= ((size_t)1 << 22);
         if (host && host->rgb && fp.world == 1) {
-            lanes_wanted = big ? 3 : 1;
-            batches_auto = big ? 6 : 1;
+            lanes_wanted = big ? 2 : 1;
+            batches_auto = big ? 3 : 1;
         } else {
             lanes_wanted = big ? 2 : 1;
             batches_auto = big ? 2 : 1;
@@ -484,13 +485,19 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids
             const size_t p0 = row_lo * fp.W, p1 = row_hi * fp.W;
             launch_pack_rgb(st, ctx->sm_count, out, ctx->rgb.p, p0, p1);
             launches++;
-            CK(cudaMemcpyAsync(host->rgb + 3 * p0, ctx->rgb.p + 3 * p0, (p1 - p0) * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(ln.ev_packed, st));
+            CK(cudaStreamWaitEvent(ctx->copy, ln.ev_packed, 0));
+            CK(cudaMemcpyAsync(host->rgb + 3 * p0, ctx->rgb.p + 3 * p0, (p1 - p0) * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy));
         }
         CK(cudaEventRecord(ln.ev_done, st));
     }
     for (int l = 0; l < n_lanes; l++)
         if (ctx->lanes[l].used)
             CK(cudaStreamWaitEvent(st0, ctx->lanes[l].ev_done, 0));
+    if (band_download) {
+        CK(cudaEventRecord(ctx->ev_copied, ctx->copy));
+        CK(cudaStreamWaitEvent(st0, ctx->ev_copied, 0));
+    }
     if (host && host->rgb && !band_download && n_local) {
         const size_t npx = (size_t)fp.W * fp.H;
         launch_pack_rgb(st0, ctx->sm_count, out, ctx->rgb.p, 0, npx);
@@ -552,12 +559,15 @@ int rt_create(int device, rt_ctx** out)
         return fail(RT_ERR_CUDA, "rt_create: stream / event / pinned allocation failed");
     }
     ctx->own_stream = true;
-    bool aux_ok = cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming) == cudaSuccess;
+    bool aux_ok = cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming) == cudaSuccess
+        && cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming) == cudaSuccess
+        && cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking) == cudaSuccess;
     for (int l = 0; l < kMaxLanes; l++) {
         rt_ctx::Lane& ln = ctx->lanes[l];
         aux_ok = aux_ok && cudaStreamCreateWithFlags(&ln.main, cudaStreamNonBlocking) == cudaSuccess
             && cudaStreamCreateWithFlags(&ln.side, cudaStreamNonBlocking) == cudaSuccess
-            && cudaEventCreateWithFlags(&ln.ev_done, cudaEventDisableTiming) == cudaSuccess;
+            && cudaEventCreateWithFlags(&ln.ev_done, cudaEventDisableTiming) == cudaSuccess
+            && cudaEventCreateWithFlags(&ln.ev_packed, cudaEventDisableTiming) == cudaSuccess;
         for (int p = 0; p < 2; p++)
             aux_ok = aux_ok && cudaEventCreateWithFlags(&ln.ev_shade[p], cudaEventDisableTiming) == cudaSuccess
                 && cudaEventCreateWithFlags(&ln.ev_shadow[p], cudaEventDisableTiming) == cudaSuccess;
@@ -597,6 +607,8 @@ int rt_destroy(rt_ctx* ctx)
         ln.counters.release();
         if (ln.ev_done)
             cudaEventDestroy(ln.ev_done);
+        if (ln.ev_packed)
+            cudaEventDestroy(ln.ev_packed);
         if (ln.main)
             cudaStreamDestroy(ln.main);
         if (ln.side)
@@ -604,6 +616,10 @@ int rt_destroy(rt_ctx* ctx)
     }
     if (ctx->ev_start)
         cudaEventDestroy(ctx->ev_start);
+    if (ctx->ev_copied)
+        cudaEventDestroy(ctx->ev_copied);
+    if (ctx->copy)
+        cudaStreamDestroy(ctx->copy);
     ctx->d_pos.release();
     ctx->d_nrm.release();
     ctx->d_mesh.release();
@@ -754,6 +770,8 @@ int rt_build_bvh(rt_ctx* ctx, int mode)
     CK(ctx->d_n1.ensure(n));
     CK(ctx->d_n2.ensure(n));
     const int* perm = nullptr;
+    if (mode == RT_BVH_AUTO) // the host SAH tree traces ~15 % faster but takes ~0.6 us per triangle to build
+        mode = ctx->n_tris <= (1ll << 22) ? RT_BVH_SAH_HOST : RT_BVH_LBVH_DEVICE;
     if (mode == RT_BVH_SAH_HOST) {
         HostBvh h = build_bvh_sah_host(ctx->h_pos.data(), ctx->n_tris, pad);
         if (h.depth >= kStackDepth)

@@ -11,8 +11,8 @@ struct rt_ctx;
 
 class BoundingVolumeHierarchy {
 public:
-    // bvhMode: RT_BVH_LBVH_DEVICE (default) or RT_BVH_SAH_HOST; device: CUDA ordinal
-    explicit BoundingVolumeHierarchy(Scene* pScene, int bvhMode = 0, int device = 0);
+    // bvhMode: RT_BVH_AUTO (default), RT_BVH_LBVH_DEVICE or RT_BVH_SAH_HOST; device: CUDA ordinal
+    explicit BoundingVolumeHierarchy(Scene* pScene, int bvhMode = 2, int device = 0);
     ~BoundingVolumeHierarchy();
     BoundingVolumeHierarchy(const BoundingVolumeHierarchy&) = delete;
     BoundingVolumeHierarchy& operator=(const BoundingVolumeHierarchy&) = delete;
