@@ -16,6 +16,9 @@ constexpr int kShadeBlock = 256;
 #ifndef RT_TRACE_GRID_MULT
 #define RT_TRACE_GRID_MULT 8
 #endif
+#ifndef RT_TRACE_MIN_BLOCKS
+#define RT_TRACE_MIN_BLOCKS 8 // 64 registers per thread: the whole persistent grid (8 blocks per SM) is resident in one wave
+#endif
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
@@ -204,7 +207,7 @@ __global__ void k_level_reset(Counters* c, int next_q, long long n_current, unsi
 // src/bounding_volume_hierarchy.cpp:49-78) through the warp-synchronous engine of rt_trace.cuh.  At level 0 the ray is
 // generated from the pixel index when a lane picks the item up (K1 fused).  Result: hit[i] = {bits(t), BVH-order triangle}.
 template <bool LEVEL0, bool COUNT>
-__global__ void __launch_bounds__(RT_TRACE_BLOCK) k_extend(SceneDev s, int root_entry, FrameParams fp, BatchDev b, int qi, unsigned first_lp)
+__global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_extend(SceneDev s, int root_entry, FrameParams fp, BatchDev b, int qi, unsigned first_lp)
 {
     const unsigned n = b.counters->n_rays[qi];
     TraceStats st;
@@ -483,7 +486,7 @@ __device__ __forceinline__ void shadow_loop(const SceneDev& s, int root_entry, c
 // K4a shadow rays to point lights (getPointLights' cansee call, src/shadow.cpp:120).
 // ANYHIT: every material is opaque, so the first blocker found decides; otherwise the closest hit does.
 template <bool ANYHIT, bool COUNT>
-__global__ void __launch_bounds__(RT_TRACE_BLOCK) k_shadow_point(SceneDev s, int root_entry, FrameParams fp, BatchDev b)
+__global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_shadow_point(SceneDev s, int root_entry, FrameParams fp, BatchDev b)
 {
     const unsigned n = b.counters->sh[b.par].n_pt * (unsigned)fp.n_point;
     shadow_loop<ANYHIT, COUNT>(
@@ -508,7 +511,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_shadow_point(SceneDev s, int
 // light centre, the others lie on rings of the disc facing the hit point; their positions follow the reference's
 // sequential `perp = rotate * perp`.  Per-record sums go to sphere_acc = {sum of intensities, visible count}.
 template <bool ANYHIT, bool COUNT>
-__global__ void __launch_bounds__(RT_TRACE_BLOCK) k_shadow_sphere(SceneDev s, int root_entry, FrameParams fp, BatchDev b)
+__global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_shadow_sphere(SceneDev s, int root_entry, FrameParams fp, BatchDev b)
 {
     const unsigned rc = (unsigned)fp.sl_rc;
     const unsigned n = b.counters->sh[b.par].n_sp * (unsigned)fp.n_sphere * rc;

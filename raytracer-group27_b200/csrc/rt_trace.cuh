@@ -102,8 +102,12 @@ constexpr int kRefillThreshold = RT_REFILL_THRESHOLD; // the traversal loop yiel
 
 struct Trav {
     f3 o, d, dn;            // ray as stored, and normalize(d)
-    float ix, iy, iz;       // 1 / dn (clamped, see trav_begin)
-    float oix, oiy, oiz;    // o * (1 / dn): slabs are evaluated as fma(box, 1/dn, -o/dn)
+    // Slab planes are picked by the sign of the direction, not by min/max: with r = 1/dn (clamped, see trav_begin),
+    // (nl, nh) = (r, 0) if r >= 0 else (0, r), and t_near = fma(lo, nl, fma(hi, nh, -o*r)), t_far = fma(lo, nh, fma(hi, nl, -o*r)).
+    // One of the two products is an exact zero, so these are bit for bit min / max of fma(lo, r, -o*r) and fma(hi, r, -o*r),
+    // but they run on the FP32 FMA pipe instead of the half-rate ALU pipe that FMNMX uses (profiles/README.md, r01d).
+    float nlx, nly, nlz, nhx, nhy, nhz;
+    float oix, oiy, oiz;    // o * r
     HitRec best;
     float tlimit;
     int cur;                // current entry, kTravDone when the traversal is complete
@@ -118,12 +122,15 @@ __device__ __forceinline__ void trav_begin(Trav& tv, const f3& o, const f3& d, c
     // Reciprocal direction, clamped to +-1e30: with an infinite reciprocal (axis-parallel ray) the fused form
     // box * inf - o * inf is NaN and loses on which side of the origin the slab plane lies; with 1e30 the FMA is exact
     // before rounding, so the signs survive and the slab covers every finite t when the origin is inside it.
-    tv.ix = fabsf(tv.dn.x) > 1e-30f ? 1.0f / tv.dn.x : copysignf(1e30f, tv.dn.x);
-    tv.iy = fabsf(tv.dn.y) > 1e-30f ? 1.0f / tv.dn.y : copysignf(1e30f, tv.dn.y);
-    tv.iz = fabsf(tv.dn.z) > 1e-30f ? 1.0f / tv.dn.z : copysignf(1e30f, tv.dn.z);
-    tv.oix = o.x * tv.ix;
-    tv.oiy = o.y * tv.iy;
-    tv.oiz = o.z * tv.iz;
+    const float rx = fabsf(tv.dn.x) > 1e-30f ? 1.0f / tv.dn.x : copysignf(1e30f, tv.dn.x);
+    const float ry = fabsf(tv.dn.y) > 1e-30f ? 1.0f / tv.dn.y : copysignf(1e30f, tv.dn.y);
+    const float rz = fabsf(tv.dn.z) > 1e-30f ? 1.0f / tv.dn.z : copysignf(1e30f, tv.dn.z);
+    tv.nlx = rx >= 0.0f ? rx : 0.0f; tv.nhx = rx >= 0.0f ? 0.0f : rx;
+    tv.nly = ry >= 0.0f ? ry : 0.0f; tv.nhy = ry >= 0.0f ? 0.0f : ry;
+    tv.nlz = rz >= 0.0f ? rz : 0.0f; tv.nhz = rz >= 0.0f ? 0.0f : rz;
+    tv.oix = o.x * rx;
+    tv.oiy = o.y * ry;
+    tv.oiz = o.z * rz;
     tv.best = query;
     tv.tlimit = prune_limit(query.t);
     tv.cur = root_entry;
@@ -155,20 +162,15 @@ __device__ __forceinline__ void trav_node_step(const SceneDev& s, Trav& tv, int*
     const float4 a0 = __ldg(np), a1 = __ldg(np + 1), b0 = __ldg(np + 2), b1 = __ldg(np + 3);
     if (COUNT)
         st.nodes += 2;
-    // slabs; fminf/fmaxf drop NaNs, which only widens the interval
-    float t0, t1;
-    t0 = fmaf(a0.x, tv.ix, -tv.oix); t1 = fmaf(a1.x, tv.ix, -tv.oix);
-    float amin = fminf(t0, t1), amax = fmaxf(t0, t1);
-    t0 = fmaf(a0.y, tv.iy, -tv.oiy); t1 = fmaf(a1.y, tv.iy, -tv.oiy);
-    amin = fmaxf(amin, fminf(t0, t1)); amax = fminf(amax, fmaxf(t0, t1));
-    t0 = fmaf(a0.z, tv.iz, -tv.oiz); t1 = fmaf(a1.z, tv.iz, -tv.oiz);
-    amin = fmaxf(fmaxf(amin, fminf(t0, t1)), 0.0f); amax = fminf(fminf(amax, fmaxf(t0, t1)), tv.tlimit);
-    t0 = fmaf(b0.x, tv.ix, -tv.oix); t1 = fmaf(b1.x, tv.ix, -tv.oix);
-    float bmin = fminf(t0, t1), bmax = fmaxf(t0, t1);
-    t0 = fmaf(b0.y, tv.iy, -tv.oiy); t1 = fmaf(b1.y, tv.iy, -tv.oiy);
-    bmin = fmaxf(bmin, fminf(t0, t1)); bmax = fminf(bmax, fmaxf(t0, t1));
-    t0 = fmaf(b0.z, tv.iz, -tv.oiz); t1 = fmaf(b1.z, tv.iz, -tv.oiz);
-    bmin = fmaxf(fmaxf(bmin, fminf(t0, t1)), 0.0f); bmax = fminf(fminf(bmax, fmaxf(t0, t1)), tv.tlimit);
+    // near / far slab distances of both boxes (all finite: boxes are finite, |r| <= 1e30)
+    const float anx = fmaf(a0.x, tv.nlx, fmaf(a1.x, tv.nhx, -tv.oix)), afx = fmaf(a0.x, tv.nhx, fmaf(a1.x, tv.nlx, -tv.oix));
+    const float any_ = fmaf(a0.y, tv.nly, fmaf(a1.y, tv.nhy, -tv.oiy)), afy = fmaf(a0.y, tv.nhy, fmaf(a1.y, tv.nly, -tv.oiy));
+    const float anz = fmaf(a0.z, tv.nlz, fmaf(a1.z, tv.nhz, -tv.oiz)), afz = fmaf(a0.z, tv.nhz, fmaf(a1.z, tv.nlz, -tv.oiz));
+    const float bnx = fmaf(b0.x, tv.nlx, fmaf(b1.x, tv.nhx, -tv.oix)), bfx = fmaf(b0.x, tv.nhx, fmaf(b1.x, tv.nlx, -tv.oix));
+    const float bny = fmaf(b0.y, tv.nly, fmaf(b1.y, tv.nhy, -tv.oiy)), bfy = fmaf(b0.y, tv.nhy, fmaf(b1.y, tv.nly, -tv.oiy));
+    const float bnz = fmaf(b0.z, tv.nlz, fmaf(b1.z, tv.nhz, -tv.oiz)), bfz = fmaf(b0.z, tv.nhz, fmaf(b1.z, tv.nlz, -tv.oiz));
+    const float amin = fmaxf(fmaxf(fmaxf(anx, any_), anz), 0.0f), amax = fminf(fminf(fminf(afx, afy), afz), tv.tlimit);
+    const float bmin = fmaxf(fmaxf(fmaxf(bnx, bny), bnz), 0.0f), bmax = fminf(fminf(fminf(bfx, bfy), bfz), tv.tlimit);
     const bool hitA = amin <= amax * 1.0000005f;
     const bool hitB = bmin <= bmax * 1.0000005f;
     const int ea = __float_as_int(a0.w), eb = __float_as_int(b0.w);
