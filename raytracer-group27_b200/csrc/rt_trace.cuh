@@ -93,7 +93,7 @@ __device__ __forceinline__ void trace_exhaustive(const SceneDev& s, const f3& o,
 // fails otherwise), so the per-lane stack cannot overflow.
 constexpr int kTravDone = INT_MIN;      // not a valid leaf encoding (triangle count is limited to 2^28 - 2)
 #ifndef RT_REFILL_THRESHOLD
-#define RT_REFILL_THRESHOLD 20
+#define RT_REFILL_THRESHOLD 0 // measured on B200: refilling only when the whole warp is done beats mid-traversal refills (profiles/README.md)
 #endif
 #ifndef RT_STACK_TMIN
 #define RT_STACK_TMIN 0
@@ -193,24 +193,29 @@ __device__ __forceinline__ void trav_node_step(const SceneDev& s, Trav& tv, int*
     }
 }
 
-// Triangle step for the leaf entry in tv.cur; afterwards tv.cur is the next entry from the stack.
+// Test the triangles of leaf entry `leaf`; the walk state (tv.cur, stack) is untouched unless an any-hit query is
+// satisfied, which drops all remaining work.
 template <bool ANYHIT, bool COUNT>
-__device__ __forceinline__ void trav_leaf_step(const SceneDev& s, Trav& tv, const int* stack, TraceStats& st)
+__device__ __forceinline__ void trav_leaf_test(const SceneDev& s, Trav& tv, int leaf, TraceStats& st)
 {
-    const int enc = ~tv.cur;
+    const int enc = ~leaf;
     const int first = enc >> 3, count = (enc & 7) + 1;
     bool any = false;
     for (int i = 0; i < count; i++)
         any |= test_triangle<COUNT>(s, first + i, tv.o, tv.d, tv.dn, tv.best, st);
-    if (any)
+    if (any) {
         tv.tlimit = prune_limit(tv.best.t);
-    tv.cur = (ANYHIT && any) ? kTravDone : trav_pop(tv, stack); // any-hit: the first blocker decides
+        if (ANYHIT) { // the first blocker decides
+            tv.cur = kTravDone;
+            tv.sp = 0;
+        }
+    }
 }
 
-// Persistent-warp traversal of a work queue ("while-while" with per-lane refill, after Aila & Laine, "Understanding the
-// Efficiency of Ray Traversal on GPUs", HPG 2009).  Every lane walks inner nodes until it reaches a leaf, then tests the
-// leaf's triangles, and repeats; as soon as fewer than kRefillThreshold lanes are still inside that loop, the warp
-// leaves it and the idle lanes pull new items (one atomicAdd per warp per refill).
+// Persistent-warp traversal of a work queue (speculative "while-while" with per-lane refill, after Aila & Laine,
+// "Understanding the Efficiency of Ray Traversal on GPUs", HPG 2009).  Every lane walks inner nodes until it reaches a
+// leaf, then tests the leaf's triangles, and repeats; when kRefillThreshold > 0 and fewer lanes than that are still inside
+// the loop, the warp leaves it and the idle lanes pull new items (one atomicAdd per warp per refill).
 // fetch(item, o, d, query) -> false if the item needs no ray;  finish(item, best, o, d, query) -> true to continue the
 // same item with a new segment (shadow rays passing a transparent surface).
 template <bool ANYHIT, bool COUNT, typename Fetch, typename Finish>
@@ -279,11 +284,34 @@ __device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, b
         // ---- traverse ----
         if (active) {
             const int min_active = more ? kRefillThreshold : 0;
-            while (tv.cur != kTravDone) {
-                while (tv.cur >= 0)
+            // Speculative while-while (Aila & Laine): a lane that reaches a leaf parks it and keeps walking nodes until
+            // every lane of the warp that is still walking has found a leaf too; then all parked leaves are tested
+            // together.  Parking only delays pruning; the (t, id) tie rule makes the result order independent.
+            int parked = kTravDone;
+            while (tv.cur != kTravDone || parked != kTravDone) {
+                bool searching = parked == kTravDone;
+                while (tv.cur >= 0) {
                     trav_node_step<COUNT>(s, tv, stack, st);
-                if (tv.cur != kTravDone)
-                    trav_leaf_step<ANYHIT, COUNT>(s, tv, stack, st);
+                    if (tv.cur < 0 && tv.cur != kTravDone && parked == kTravDone) {
+                        parked = tv.cur;
+                        tv.cur = trav_pop(tv, stack);
+                        searching = false;
+                    }
+                    if (!__any_sync(__activemask(), searching))
+                        break;
+                }
+                if (tv.cur < 0 && tv.cur != kTravDone && parked == kTravDone) { // the entry itself was a leaf
+                    parked = tv.cur;
+                    tv.cur = trav_pop(tv, stack);
+                }
+                while (parked != kTravDone) {
+                    trav_leaf_test<ANYHIT, COUNT>(s, tv, parked, st);
+                    parked = kTravDone;
+                    if (tv.cur < 0 && tv.cur != kTravDone) { // the next entry is a leaf as well: test it right away
+                        parked = tv.cur;
+                        tv.cur = trav_pop(tv, stack);
+                    }
+                }
                 if (min_active > 0 && __popc(__activemask()) < min_active)
                     break;
             }
@@ -308,10 +336,13 @@ __device__ __forceinline__ void trace_bvh(const SceneDev& s, int root_entry, con
     Trav tv;
     trav_begin(tv, o, d, best, root_entry);
     while (tv.cur != kTravDone) {
-        if (tv.cur >= 0)
+        if (tv.cur >= 0) {
             trav_node_step<COUNT>(s, tv, stack, st);
-        else
-            trav_leaf_step<ANYHIT, COUNT>(s, tv, stack, st);
+        } else {
+            const int leaf = tv.cur;
+            tv.cur = trav_pop(tv, stack);
+            trav_leaf_test<ANYHIT, COUNT>(s, tv, leaf, st);
+        }
     }
     best = tv.best;
 }
