@@ -760,7 +760,9 @@ int rt_build_bvh(rt_ctx* ctx, int mode)
         return fail(RT_ERR_INVALID, "rt_build_bvh: upload a scene first");
     // Box padding: the reference's triangle test accepts points a few ulp outside the exact triangle (rounded
     // hit point, rounded edge functions); pad so such a point is still inside every ancestor box.
-    const float pad = 1e-5f * std::max(1.0f, ctx->coord_max);
+    // The slack covers rounding of the hit point, eps * (|origin| + t): 4e-5 leaves head-room up to the reference camera's
+    // farthest zoom (distance 100, trackball.cpp:150) on a unit-scale scene.
+    const float pad = 4e-5f * std::max(1.0f, ctx->coord_max);
     const size_t n = (size_t)ctx->n_tris;
     CK(ctx->d_plane.ensure(n));
     CK(ctx->d_v0.ensure(n));

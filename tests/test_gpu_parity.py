@@ -126,6 +126,26 @@ def test_axis_parallel_and_in_plane_rays(rtb, gpu_ctx):
             assert bits_equal(t, o_t)
 
 
+def test_far_and_near_cameras(rtb, gpu_ctx):
+    """Box padding and prune margins are absolute/relative slacks sized for the reference's camera range (distance 0.1 ..
+    100, trackball.cpp:150): the BVH frame must equal the oracle's at both ends."""
+    import oracle
+    g = Golden("monkey_192")
+    o = oracle.Oracle("port")
+    s = g.scene
+    for dist, fov in ((95.0, 1.5), (0.35, 80.0), (12.0, 10.0)):
+        cam = rtb.make_camera(dist=dist, fovy_deg=fov, euler_deg=(35.0, -50.0, 0.0))
+        o_rgb, o_ids, o_t, o_st = o.render(s.pos, s.nrm, s.mesh_id, s.mats, s.point_lights, None, cam, 160, 120, max_level=2, shadow_exhaustive=True)
+        assert (o_ids >= 0).mean() > 0.05
+        for mode in (rtb.BVH_LBVH_DEVICE, rtb.BVH_SAH_HOST):
+            gpu_ctx.upload_scene(s, mode)
+            rgb, ids, t, st = gpu_ctx.render(cam, rtb.make_params(160, 120, 2), want_ids=True)
+            assert np.array_equal(ids, o_ids), f"dist {dist}: {(ids != o_ids).sum()} ids differ"
+            assert bits_equal(t, o_t)
+            assert np.abs(rgb - o_rgb).max() <= COLOUR_TOL
+            assert st.rays == o_st.rays
+
+
 def test_full_size_bvh_equals_exhaustive(rtb, gpu_ctx):
     """Size-independent property at C1's full size (1024x1024, depth 3): the BVH frame equals the exhaustive frame
     bit for bit (ids, t) and to round-off in colour — both use the reference's triangle arithmetic."""
