@@ -35,6 +35,10 @@ typedef struct {
 typedef struct { float position[3]; float color[3]; } rt_point_light;                /* src/scene.h:55-59 */
 typedef struct { float position[3]; float radius; float color[3]; } rt_sphere_light; /* src/scene.h:61-66 */
 
+/* Sphere primitive — replaces `struct Sphere` (src/scene.h:48-53) with its own material; intersected with the
+ * reference's quadratic (src/ray_tracing.cpp:182-209).  A sphere hit is reported as triangle id n_tris + sphere index. */
+typedef struct { float center[3]; float radius; rt_material material; } rt_sphere;
+
 /* Camera state — replaces the Trackball members read by position()/generateRay()
  * (framework/include/trackball.h:44-52, framework/src/trackball.cpp:65-68,87-98).  The aspect ratio is
  * width/height of rt_params, as Window::aspectRatio() (framework/src/window.cpp:334-337). */
@@ -96,6 +100,9 @@ int rt_build_bvh(rt_ctx* ctx, int mode);
 int rt_set_materials(rt_ctx* ctx, const rt_material* mats, int n_mats);
 int rt_set_lights(rt_ctx* ctx, const rt_point_light* point, int n_point, const rt_sphere_light* sphere, int n_sphere);
 
+/* Scene::spheres (src/scene.h:88): read live every frame like the lights; at most 64.  Spheres are tested against every
+ * ray before the triangle BVH is walked (the reference puts them into its BVH leaves, bounding_volume_hierarchy.cpp:283-292). */
+int rt_set_spheres(rt_ctx* ctx, const rt_sphere* spheres, int n_spheres);
 /* Number of 32-byte nodes and depth of the BVH built last. */
 int rt_bvh_info(rt_ctx* ctx, int* n_nodes, int* depth);
 /* Instrumented kernels: fill rt_stats.node_visits / tri_tests / tri_tests_full (slower; off by default). */

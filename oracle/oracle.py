@@ -57,6 +57,7 @@ class Oracle:
         self.lib.oracle_render.restype = C.c_int
         self.lib.oracle_closest_hit.restype = C.c_int
         self.lib.oracle_kind.restype = C.c_char_p
+        self.lib.oracle_set_spheres.restype = None
         assert self.lib.oracle_kind().decode() == kind
 
     def render(self, pos, nrm, mesh_id, mats, point_lights, sphere_lights, cam, width, height, max_level=5, sphere_rays=10,
@@ -91,6 +92,11 @@ class Oracle:
         if rc != 0:
             raise RuntimeError(f"oracle_render failed with {rc}")
         return rgb, ids, t, st
+
+    def set_spheres(self, spheres):
+        """spheres: (n, 12) = centre, radius, kd, ks, shininess, transparency; None / empty clears them."""
+        sp = np.ascontiguousarray(spheres if spheres is not None else np.zeros((0, 12)), np.float32).reshape(-1, 12)
+        self.lib.oracle_set_spheres(C.c_void_p(sp.ctypes.data if len(sp) else None), C.c_int(len(sp)))
 
     def closest_hit(self, pos, nrm, mesh_id, rays, use_bvh=False):
         pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 9)

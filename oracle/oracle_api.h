@@ -75,6 +75,12 @@ int oracle_render(const float* pos, const float* nrm, const int* mesh_id, int n_
 int oracle_closest_hit(const float* pos, const float* nrm, const int* mesh_id, int n_tris,
     const float* rays, int n_rays, int use_bvh, int* tri_id, float* t_hit);
 
+/* Sphere primitives (src/scene.h:48-53, intersectRayWithShape(Sphere) src/ray_tracing.cpp:182-209) used by the following
+ * oracle_render / oracle_closest_hit calls of the same thread group: 12 floats each = centre (3), radius, kd (3), ks (3),
+ * shininess, transparency.  n = 0 clears them.  A sphere that wins the closest-hit query is reported with
+ * tri_id = n_tris + sphere index. */
+void oracle_set_spheres(const float* spheres, int n);
+
 const char* oracle_kind(void); /* "reference" or "port" */
 
 #ifdef __cplusplus

@@ -157,6 +157,25 @@ std::vector<glm::vec2> getPixelRays(const RenderGlobals& g, glm::vec2 pixelCente
     return origins;
 }
 
+std::vector<float> g_spheres; // oracle_set_spheres
+
+void addSpheres(Scene& scene)
+{
+    for (size_t k = 0; k + 11 < g_spheres.size(); k += 12) {
+        const float* f = &g_spheres[k];
+        Material m;
+        m.kd = glm::vec3(f[4], f[5], f[6]);
+        m.ks = glm::vec3(f[7], f[8], f[9]);
+        m.shininess = f[10];
+        m.transparency = f[11];
+        Sphere sp;
+        sp.center = glm::vec3(f[0], f[1], f[2]);
+        sp.radius = f[3];
+        sp.material = m;
+        scene.spheres.push_back(sp);
+    }
+}
+
 Scene sceneFromSoup(const float* pos, const float* nrm, const int* mesh_id, int n_tris, const orc_material* mats, int n_mats)
 {
     Scene scene;
@@ -187,9 +206,9 @@ Scene sceneFromSoup(const float* pos, const float* nrm, const int* mesh_id, int 
     return scene;
 }
 
-// Exhaustive search in the reference's brute-force order (bounding_volume_hierarchy.cpp:51-66) using the
-// verbatim intersectRayWithTriangle; the first strictly smaller t wins, so ties keep the lowest index.
-int exhaustiveId(const float* pos, int n_tris, Ray ray, float& t_out)
+// Exhaustive search in the reference's brute-force order (bounding_volume_hierarchy.cpp:51-72: all triangles, then the
+// spheres) using the verbatim intersection functions; the first strictly smaller t wins, so ties keep the lowest index.
+int exhaustiveId(const float* pos, int n_tris, Ray ray, float& t_out, const Scene* scene = nullptr)
 {
     int best = -1;
     HitInfo hi;
@@ -200,6 +219,10 @@ int exhaustiveId(const float* pos, int n_tris, Ray ray, float& t_out)
         if (intersectRayWithTriangle(v0, v1, v2, ray, hi, 0))
             best = i;
     }
+    if (scene)
+        for (size_t k = 0; k < scene->spheres.size(); k++)
+            if (intersectRayWithShape(scene->spheres[k], ray, hi))
+                best = n_tris + (int)k;
     t_out = ray.t;
     return best;
 }
@@ -208,15 +231,21 @@ int exhaustiveId(const float* pos, int n_tris, Ray ray, float& t_out)
 
 extern "C" const char* oracle_kind(void) { return "reference"; }
 
+extern "C" void oracle_set_spheres(const float* spheres, int n)
+{
+    g_spheres.assign(spheres, spheres + (spheres ? 12 * (size_t)n : 0));
+}
+
 extern "C" int oracle_render(const float* pos, const float* nrm, const int* mesh_id, int n_tris,
     const orc_material* mats, int n_mats,
     const float* point_lights, int n_point, const float* sphere_lights, int n_sphere,
     const orc_camera* cam, const orc_params* prm,
     float* rgb, int* tri_id, float* t_hit, orc_stats* stats)
 {
-    if (!pos || !cam || !prm || prm->width <= 0 || prm->height <= 0 || prm->glossy_ray_count != 1)
+    if ((!pos && n_tris > 0) || !cam || !prm || prm->width <= 0 || prm->height <= 0 || prm->glossy_ray_count != 1)
         return 1;
     Scene scene = sceneFromSoup(pos, nrm, mesh_id, n_tris, mats, n_mats);
+    addSpheres(scene);
     for (int i = 0; i < n_point; i++)
         scene.pointLights.push_back(PointLight { glm::vec3(point_lights[6 * i], point_lights[6 * i + 1], point_lights[6 * i + 2]),
             glm::vec3(point_lights[6 * i + 3], point_lights[6 * i + 4], point_lights[6 * i + 5]) });
@@ -303,7 +332,7 @@ extern "C" int oracle_render(const float* pos, const float* nrm, const int* mesh
             }
             if (tri_id || t_hit) {
                 float t;
-                const int id = exhaustiveId(pos, n_tris, firstRay, t);
+                const int id = exhaustiveId(pos, n_tris, firstRay, t, &scene);
                 if (tri_id)
                     tri_id[i] = id;
                 if (t_hit)
@@ -328,9 +357,10 @@ extern "C" int oracle_render(const float* pos, const float* nrm, const int* mesh
 extern "C" int oracle_closest_hit(const float* pos, const float* nrm, const int* mesh_id, int n_tris,
     const float* rays, int n_rays, int use_bvh, int* tri_id, float* t_hit)
 {
-    if (!pos || !rays)
+    if ((!pos && n_tris > 0) || !rays)
         return 1;
     Scene scene = sceneFromSoup(pos, nrm, mesh_id, n_tris, nullptr, 0);
+    addSpheres(scene);
     BoundingVolumeHierarchy bvh(&scene);
 #pragma omp parallel for schedule(dynamic, 64)
     for (int r = 0; r < n_rays; r++) {
@@ -339,7 +369,7 @@ extern "C" int oracle_closest_hit(const float* pos, const float* nrm, const int*
         ray.direction = glm::vec3(rays[6 * r + 3], rays[6 * r + 4], rays[6 * r + 5]);
         ray.t = std::numeric_limits<float>::max();
         float t;
-        int id = exhaustiveId(pos, n_tris, ray, t);
+        int id = exhaustiveId(pos, n_tris, ray, t, &scene);
         if (use_bvh) {
             Ray rb = ray;
             HitInfo hi;

@@ -78,7 +78,11 @@ struct rt_ctx {
     int n_nodes = 0, root_entry = 0, bvh_depth = 0;
     bool bvh_built = false;
     int n_point = 0, n_sphere = 0;
-    bool any_transparent = false;
+    bool any_transparent = false;          // meshes or spheres
+    bool mats_transparent = false, spheres_transparent = false;
+    DevBuf<float4> d_spheres;
+    int n_spheres = 0;
+    long long user_tris = 0;               // triangles the caller uploaded (0 allowed: a never-hit dummy is traced instead)
 
     // sharding
     int rank = 0, world = 1;
@@ -138,6 +142,9 @@ struct rt_ctx {
         s.mats = d_mats.p;
         s.point_lights = d_point.p;
         s.sphere_lights = d_sphere.p;
+        s.spheres = d_spheres.p;
+        s.n_spheres = n_spheres;
+        s.sphere_id_base = (int)user_tris;
         s.n_tris = (int)n_tris;
         s.n_nodes = n_nodes;
         return s;
@@ -169,7 +176,8 @@ int upload_materials(rt_ctx* ctx, const rt_material* mats, int n_mats)
     CK(cudaMemcpyAsync(ctx->d_mats.p, h.data(), h.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream)); // h is a stack-lifetime staging vector
     ctx->n_mats = n_mats;
-    ctx->any_transparent = any_t;
+    ctx->mats_transparent = any_t;
+    ctx->any_transparent = ctx->mats_transparent || ctx->spheres_transparent;
     return RT_OK;
 }
 
@@ -629,6 +637,7 @@ int rt_destroy(rt_ctx* ctx)
     ctx->prim_t.release();
     ctx->out_t.release();
     ctx->rgb.release();
+    ctx->d_spheres.release();
     ctx->rays_in.release();
     ctx->flag.release();
     if (ctx->lbvh_nodes)
@@ -720,8 +729,22 @@ int rt_upload_scene(rt_ctx* ctx, const float* pos, const float* nrm, const int* 
     int rc = use_device(ctx);
     if (rc)
         return rc;
-    if (!pos || !nrm || n_tris <= 0)
-        return fail(RT_ERR_INVALID, "rt_upload_scene: need positions, normals and at least one triangle");
+    if (n_tris < 0 || (n_tris > 0 && (!pos || !nrm)))
+        return fail(RT_ERR_INVALID, "rt_upload_scene: need positions and normals");
+    // A scene of sphere primitives only (the reference's Spheres preset, src/scene.cpp:80-87) has no triangles: trace one
+    // degenerate triangle (zero area -> NaN plane -> never hit, as in the reference) so the BVH paths stay uniform.
+    static const float zero9[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+    static const rt_material default_mat = { { 0.6f, 0.6f, 0.6f }, { 0, 0, 0 }, 0.0f, 1.0f };
+    ctx->user_tris = n_tris;
+    if (n_tris == 0) {
+        pos = nrm = zero9;
+        mesh_id = nullptr;
+        n_tris = 1;
+        if (!mats || n_mats <= 0) {
+            mats = &default_mat;
+            n_mats = 1;
+        }
+    }
     if (n_tris > (1ll << 28) - 1)
         return fail(RT_ERR_INVALID, "rt_upload_scene: at most 2^28-1 triangles");
     if (mesh_id)
@@ -868,6 +891,31 @@ int rt_set_lights(rt_ctx* ctx, const rt_point_light* point, int n_point, const r
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->n_point = n_point;
     ctx->n_sphere = n_sphere;
+    return RT_OK;
+}
+
+int rt_set_spheres(rt_ctx* ctx, const rt_sphere* spheres, int n_spheres)
+{
+    int rc = use_device(ctx);
+    if (rc)
+        return rc;
+    if (n_spheres < 0 || n_spheres > kMaxSpheres || (n_spheres > 0 && !spheres))
+        return fail(RT_ERR_INVALID, "rt_set_spheres: between 0 and 64 spheres");
+    std::vector<float4> h(3 * (size_t)std::max(1, n_spheres));
+    bool any_t = false;
+    for (int i = 0; i < n_spheres; i++) {
+        const rt_sphere& sp = spheres[i];
+        h[3 * i] = make_float4(sp.center[0], sp.center[1], sp.center[2], sp.radius);
+        h[3 * i + 1] = make_float4(sp.material.kd[0], sp.material.kd[1], sp.material.kd[2], sp.material.shininess);
+        h[3 * i + 2] = make_float4(sp.material.ks[0], sp.material.ks[1], sp.material.ks[2], sp.material.transparency);
+        any_t |= sp.material.transparency != 1.0f;
+    }
+    CK(ctx->d_spheres.ensure(h.size()));
+    CK(cudaMemcpyAsync(ctx->d_spheres.p, h.data(), h.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_spheres = n_spheres;
+    ctx->spheres_transparent = any_t;
+    ctx->any_transparent = ctx->mats_transparent || ctx->spheres_transparent;
     return RT_OK;
 }
 

@@ -119,8 +119,8 @@ __device__ __forceinline__ bool generate_ray(const FrameParams& fp, unsigned fir
 
 struct Shading { // what shade and the transparent-shadow branch need at a hit
     f3 p;      // hit point
-    f3 N;      // interpolated normal, flipped to the geometric side (not normalised)
-    int mesh;
+    f3 N;      // triangle: interpolated normal, flipped to the geometric side (not normalised); sphere: unit normal
+    float4 m0, m1; // material {kd, shininess}{ks, transparency} (HitInfo::getMaterial, src/ray_tracing.h:21-27)
 };
 
 // Hit point and shading normal: src/ray_tracing.cpp:111, 147-160 with barycentricCoordinates (276-308) evaluated
@@ -128,12 +128,21 @@ struct Shading { // what shade and the transparent-shadow branch need at a hit
 // fail).  `o`, `d` are the ray as traced, t its hit parameter.
 __device__ __forceinline__ Shading shading_at(const SceneDev& s, int ti, const f3& o, const f3& d, float t)
 {
+    Shading sh;
+    sh.p = xadd(o, xmul(d, t));
+    if (ti <= -2) { // sphere primitive (src/ray_tracing.cpp:199-204)
+        const int k = -2 - ti;
+        sh.N = xnormalize(xsub(sh.p, mk3(__ldg(&s.spheres[3 * k]))));
+        sh.m0 = __ldg(&s.spheres[3 * k + 1]);
+        sh.m1 = __ldg(&s.spheres[3 * k + 2]);
+        return sh;
+    }
     const float4 pl = __ldg(&s.tri_plane[ti]);
     const float4 a = __ldg(&s.tri_v0[ti]), b = __ldg(&s.tri_v1[ti]), c = __ldg(&s.tri_v2[ti]);
     const f3 v0 = mk3(a), v1 = mk3(b), v2 = mk3(c), fn = mk3(pl);
-    Shading sh;
-    sh.mesh = __float_as_int(b.w);
-    sh.p = xadd(o, xmul(d, t));
+    const int mesh = __float_as_int(b.w);
+    sh.m0 = __ldg(&s.mats[2 * mesh]);
+    sh.m1 = __ldg(&s.mats[2 * mesh + 1]);
     const float total = xlength(xcross(xsub(v1, v0), xsub(v2, v0)));
     const float c0 = xdiv(xlength(xcross(xsub(v1, sh.p), xsub(v2, sh.p))), total);
     const float c1 = xdiv(xlength(xcross(xsub(sh.p, v0), xsub(v2, v0))), total);
@@ -227,7 +236,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_extend(
         [&](unsigned item, const HitRec& best, f3&, f3&, HitRec&) {
             b.q[qi].hit[item] = make_int2(__float_as_int(best.t), best.ti);
             if (LEVEL0 && b.prim_id && (tag & 1)) { // first sample of the pixel
-                b.prim_id[tag >> 1] = best.ti >= 0 ? best.id : -1;
+                b.prim_id[tag >> 1] = best.ti != -1 ? best.id : -1;
                 b.prim_t[tag >> 1] = best.t;
             }
             return false;
@@ -264,8 +273,8 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
         Shading sh;
         sh.p = mk3(0, 0, 0);
         sh.N = mk3(0, 0, 0);
-        sh.mesh = 0;
-        float4 m0 = make_float4(0, 0, 0, 0), m1 = make_float4(0, 0, 0, 1);
+        sh.m0 = make_float4(0, 0, 0, 0);
+        sh.m1 = make_float4(0, 0, 0, 1);
         int2 h = make_int2(0, -1);
         if (i < n) {
             bool valid = true;
@@ -278,12 +287,12 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
                 h = b.q[qi].hit[i];
         }
         // most slots of a level-0 frame are misses: a block without any hit has nothing to allocate
-        if (!__syncthreads_or(h.y >= 0))
+        if (!__syncthreads_or(h.y != -1))
             continue;
         if (i < n) {
             f3 o, d;
             int tag = 0;
-            if (h.y >= 0) {
+            if (h.y != -1) {
                 hit = true;
                 if (LEVEL0) {
                     generate_ray(fp, first_lp, i, o, d, tag); // K1 again: the primary ray is a function of the index
@@ -300,12 +309,10 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
                 dn = xnormalize(d);
                 Nn = xnormalize(sh.N);
                 refl = xreflect(dn, Nn); // main.cpp:141
-                m0 = __ldg(&s.mats[2 * sh.mesh]);
-                m1 = __ldg(&s.mats[2 * sh.mesh + 1]);
             }
         }
-        const f3 kd = mk3(m0), ks = mk3(m1);
-        const float shininess = m0.w, transparency = m1.w;
+        const f3 kd = mk3(sh.m0), ks = mk3(sh.m1);
+        const float shininess = sh.m0.w, transparency = sh.m1.w;
 
         // children
         bool want0 = false, want1 = false;
@@ -422,12 +429,12 @@ __device__ __forceinline__ HitRec cansee_query(const CanSee& cs) { return bounde
 // After a traversal finished with `best`: 0 = visible, 1 = blocked, 2 = passed a transparent surface, go on.
 __device__ __forceinline__ int cansee_step(const SceneDev& s, const FrameParams& fp, CanSee& cs, const HitRec& best)
 {
-    if (best.ti < 0)
+    if (best.ti == -1)
         return 0;
     if (!fp.any_transparent)
         return 1;
     const Shading sh = shading_at(s, best.ti, cs.o, cs.d, best.t);
-    const float R0 = __ldg(&s.mats[2 * sh.mesh + 1]).w;
+    const float R0 = sh.m1.w;
     if (R0 == 1.0f)
         return 1;
     cs.distance = xsub(cs.distance, best.t);               // shadow.cpp:51
@@ -651,7 +658,7 @@ __global__ void __launch_bounds__(128) k_intersect(SceneDev s, int root_entry, c
         } else {
             trace_exhaustive<false, false>(s, o, d, best, st);
         }
-        tri_id[i] = best.ti >= 0 ? best.id : -1;
+        tri_id[i] = best.ti != -1 ? best.id : -1;
         t_out[i] = best.t;
     }
 }

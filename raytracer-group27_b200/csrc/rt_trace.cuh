@@ -27,8 +27,8 @@ struct TraceStats {
 
 struct HitRec {
     float t;   // best t so far (search bound on entry)
-    int id;    // global triangle id of the best hit (tie rule operand)
-    int ti;    // BVH-order index of the best hit, -1 = none
+    int id;    // global id of the best hit (tie rule operand): triangle id, or n_tris + sphere index
+    int ti;    // BVH-order index of the best triangle hit; -1 = none; -2 - k = sphere k
 };
 
 // One ray against one triangle.  `o`/`d` as stored in the ray, `dn` = normalize(d).
@@ -67,6 +67,41 @@ __device__ __forceinline__ bool test_triangle(const SceneDev& s, int ti, const f
     return false;
 }
 
+// Sphere primitives: intersectRayWithShape(const Sphere&, Ray&, HitInfo&) (src/ray_tracing.cpp:182-209).  The reference's
+// glm::pow(float, int) is std::pow and returns double, so the sums of squares and the discriminant are formed in double
+// and rounded to float; x*x of a float is exact in double, so pow(x, 2) is a plain product.  The parameter is along the
+// ray's own (un-normalised) direction.  In the reference's brute-force order spheres come after all triangles and a hit
+// needs t < ray.t strictly: with ids n_tris + k the (t, id) tie rule reproduces that whatever the test order.
+__device__ __forceinline__ bool test_spheres(const SceneDev& s, const f3& o, const f3& d, HitRec& best)
+{
+    bool any = false;
+    for (int k = 0; k < s.n_spheres; k++) {
+        const float4 cr = __ldg(&s.spheres[3 * k]);
+        const f3 m = xsub(o, mk3(cr));
+        const float A = (float)__dadd_rn(__dadd_rn(__dmul_rn(d.x, d.x), __dmul_rn(d.y, d.y)), __dmul_rn(d.z, d.z));
+        const float B = xmul(2.0f, xadd(xadd(xmul(d.x, m.x), xmul(d.y, m.y)), xmul(d.z, m.z)));
+        const float C = (float)__dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(m.x, m.x), __dmul_rn(m.y, m.y)), __dmul_rn(m.z, m.z)), __dmul_rn(cr.w, cr.w));
+        const float disc = (float)__dsub_rn(__dmul_rn(B, B), (double)xmul(xmul(4.0f, A), C));
+        if (!(disc >= 0.0f))
+            continue;
+        const float sq = xsqrt(disc), den = xmul(2.0f, A);
+        float t0 = xdiv(xadd(-B, sq), den), t1 = xdiv(xsub(-B, sq), den);
+        if (t0 < 0.0f)
+            t0 = t1;
+        if (t1 < 0.0f)
+            t1 = t0;
+        const float t = (t1 < t0) ? t1 : t0;
+        const int id = s.sphere_id_base + k;
+        if (!(t > 0.0f) || !(t <= best.t) || (t == best.t && id >= best.id))
+            continue;
+        best.t = t;
+        best.id = id;
+        best.ti = -2 - k;
+        any = true;
+    }
+    return any;
+}
+
 // Prune bound for box tests derived from the best t: t is measured along normalize(d) while the accepted point
 // uses the un-normalised d (|d| = 1 +- a few ulp), so leave a relative and an absolute margin.
 __device__ __forceinline__ float prune_limit(float best_t) { return best_t * 1.000004f + 1e-5f; }
@@ -81,6 +116,8 @@ template <bool ANYHIT, bool COUNT>
 __device__ __forceinline__ void trace_exhaustive(const SceneDev& s, const f3& o, const f3& d, HitRec& best, TraceStats& st)
 {
     const f3 dn = xnormalize(d);
+    if (test_spheres(s, o, d, best) && ANYHIT)
+        return;
     for (int ti = 0; ti < s.n_tris; ti++) {
         if (test_triangle<COUNT>(s, ti, o, d, dn, best, st) && ANYHIT)
             return;
@@ -132,9 +169,18 @@ __device__ __forceinline__ void trav_begin(Trav& tv, const f3& o, const f3& d, c
     tv.oiy = o.y * ry;
     tv.oiz = o.z * rz;
     tv.best = query;
-    tv.tlimit = prune_limit(query.t);
     tv.cur = root_entry;
     tv.sp = 0;
+}
+
+// Start a query: the (few) sphere primitives first — their hit bounds the BVH walk, or ends an any-hit query outright.
+template <bool ANYHIT>
+__device__ __forceinline__ void trav_start(const SceneDev& s, Trav& tv, const f3& o, const f3& d, const HitRec& query, int root_entry)
+{
+    trav_begin(tv, o, d, query, root_entry);
+    if (s.n_spheres > 0 && test_spheres(s, o, d, tv.best) && ANYHIT)
+        tv.cur = kTravDone;
+    tv.tlimit = prune_limit(tv.best.t);
 }
 
 // Pop the next entry; with RT_STACK_TMIN the entry distance saved at push time lets entries that have fallen behind the
@@ -260,17 +306,17 @@ __device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, b
                     if (fetch(item, o, d, q)) {
                         my = item;
                         active = true;
-                        trav_begin(tv, o, d, q, root_entry);
-                        if (exhaustive) { // reference useBVH=false semantics (tests): loop over every triangle
+                        if (exhaustive) { // reference useBVH=false semantics (tests): loop over every primitive
                             bool again;
                             do {
+                                trav_begin(tv, o, d, q, root_entry);
                                 trace_exhaustive<ANYHIT, COUNT>(s, tv.o, tv.d, tv.best, st);
                                 again = finish(my, tv.best, o, d, q);
-                                if (again)
-                                    trav_begin(tv, o, d, q, root_entry);
                             } while (again);
                             active = false;
                             tv.cur = kTravDone;
+                        } else {
+                            trav_start<ANYHIT>(s, tv, o, d, q, root_entry);
                         }
                     }
                 }
@@ -319,7 +365,7 @@ __device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, b
                 f3 o, d;
                 HitRec q;
                 if (finish(my, tv.best, o, d, q))
-                    trav_begin(tv, o, d, q, root_entry);
+                    trav_start<ANYHIT>(s, tv, o, d, q, root_entry);
                 else
                     active = false;
             }
@@ -334,7 +380,7 @@ __device__ __forceinline__ void trace_bvh(const SceneDev& s, int root_entry, con
 {
     int stack[kStackDepth * (RT_STACK_TMIN ? 2 : 1)];
     Trav tv;
-    trav_begin(tv, o, d, best, root_entry);
+    trav_start<ANYHIT>(s, tv, o, d, best, root_entry);
     while (tv.cur != kTravDone) {
         if (tv.cur >= 0) {
             trav_node_step<COUNT>(s, tv, stack, st);

@@ -16,6 +16,7 @@ constexpr int kStackDepth = 64;   // per-thread traversal stack (ints); builders
 constexpr int kMaxLanes = 4;       // batches of one frame in flight at once (rt_set_pipeline)
 constexpr int kMaxPointLights = 16;
 constexpr int kMaxSphereLights = 8;
+constexpr int kMaxSpheres = 64;
 
 // Flattened BVH in HBM: 32-byte nodes {lo.xyz, entry}{hi.xyz, count}, read as 2 x float4.
 // Sibling nodes are adjacent (2k, 2k+1) so visiting an inner node is one aligned 64-byte fetch of both children.
@@ -35,6 +36,9 @@ struct SceneDev {
     const float4* mats;          // 2 x float4 per mesh: {kd.xyz, shininess}{ks.xyz, transparency}
     const float4* point_lights;  // 2 x float4: {pos, 0}{color, 0}
     const float4* sphere_lights; // 2 x float4: {pos, radius}{color, 0}
+    const float4* spheres;       // sphere primitives, 3 x float4: {centre, radius}{kd, shininess}{ks, transparency}
+    int n_spheres;
+    int sphere_id_base;          // global id of sphere 0 = number of triangles the caller uploaded
     int n_tris;
     int n_nodes;
 };

@@ -31,6 +31,13 @@ BoundingVolumeHierarchy::BoundingVolumeHierarchy(Scene* pScene, int bvhMode, int
     }
     check(rt_create(device, &m_ctx), "rt_create");
     check(rt_upload_scene(m_ctx, m_pos.data(), m_nrm.data(), m_meshId.data(), (int64_t)m_meshId.size(), mats.data(), (int)mats.size()), "rt_upload_scene");
+    std::vector<rt_sphere> sp;
+    for (const Sphere& s : pScene->spheres) {
+        const Material& m = s.material;
+        sp.push_back(rt_sphere { { s.center.x, s.center.y, s.center.z }, s.radius,
+            rt_material { { m.kd.x, m.kd.y, m.kd.z }, { m.ks.x, m.ks.y, m.ks.z }, m.shininess, m.transparency } });
+    }
+    check(rt_set_spheres(m_ctx, sp.data(), (int)sp.size()), "rt_set_spheres");
     check(rt_build_bvh(m_ctx, bvhMode), "rt_build_bvh");
     // depth of a balanced binary tree over the triangles, for callers that print it
     size_t n = m_meshId.size();
@@ -56,8 +63,16 @@ bool BoundingVolumeHierarchy::intersect(Ray& ray, HitInfo& hitInfo, bool useBVH)
     if (id < 0 || !(t < ray.t))
         return false;
     ray.t = t;
-    hitInfo.is_triangle = true;
     hitInfo.triangle_index = id;
+    if (id >= (int)m_meshId.size()) { // sphere primitive (src/ray_tracing.cpp:199-204)
+        const Sphere& sp = m_pScene->spheres.at(size_t(id) - m_meshId.size());
+        hitInfo.is_triangle = false;
+        hitInfo.hitPoint = ray.origin + t * ray.direction;
+        hitInfo.normal = glm::normalize(hitInfo.hitPoint - sp.center);
+        hitInfo.sphere_material = sp.material;
+        return true;
+    }
+    hitInfo.is_triangle = true;
     hitInfo.material_index = m_meshId[id];
     hitInfo.hitPoint = ray.origin + ray.direction * t;
     // shading normal: barycentric blend of the corner normals, flipped to the geometric side

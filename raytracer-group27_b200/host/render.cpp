@@ -31,7 +31,8 @@ void renderRayTracing(Scene& scene, const Trackball& camera, const BoundingVolum
         const Material& m = mesh.material;
         mats.push_back(rt_material { { m.kd.x, m.kd.y, m.kd.z }, { m.ks.x, m.ks.y, m.ks.z }, m.shininess, m.transparency });
     }
-    check(rt_set_materials(ctx, mats.data(), (int)mats.size()), "rt_set_materials");
+    if (!mats.empty())
+        check(rt_set_materials(ctx, mats.data(), (int)mats.size()), "rt_set_materials");
     std::vector<rt_point_light> pl;
     for (const PointLight& l : scene.pointLights)
         pl.push_back(rt_point_light { { l.position.x, l.position.y, l.position.z }, { l.color.x, l.color.y, l.color.z } });
@@ -39,6 +40,13 @@ void renderRayTracing(Scene& scene, const Trackball& camera, const BoundingVolum
     for (const SphericalLight& l : scene.sphericalLight)
         sl.push_back(rt_sphere_light { { l.position.x, l.position.y, l.position.z }, l.radius, { l.color.x, l.color.y, l.color.z } });
     check(rt_set_lights(ctx, pl.data(), (int)pl.size(), sl.data(), (int)sl.size()), "rt_set_lights");
+    std::vector<rt_sphere> sp;
+    for (const Sphere& s : scene.spheres) {
+        const Material& m = s.material;
+        sp.push_back(rt_sphere { { s.center.x, s.center.y, s.center.z }, s.radius,
+            rt_material { { m.kd.x, m.kd.y, m.kd.z }, { m.ks.x, m.ks.y, m.ks.z }, m.shininess, m.transparency } });
+    }
+    check(rt_set_spheres(ctx, sp.data(), (int)sp.size()), "rt_set_spheres");
 
     const glm::ivec2 res = screen.resolution();
     const glm::vec3 la = camera.lookAt(), eu = camera.rotationEulerAngles();

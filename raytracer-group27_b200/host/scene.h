@@ -69,7 +69,7 @@ struct PlaneLight {
 
 struct Scene {
     std::vector<Mesh> meshes;
-    std::vector<Sphere> spheres; // kept for API shape; sphere primitives are a "next" row
+    std::vector<Sphere> spheres; // traced (rt_set_spheres), re-read every frame like the lights
 
     std::vector<PointLight> pointLights;
     std::vector<SphericalLight> sphericalLight;

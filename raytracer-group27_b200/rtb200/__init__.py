@@ -70,6 +70,7 @@ SYMBOLS = [
     ("rt_build_bvh", _I, [_P, _I]),
     ("rt_set_materials", _I, [_P, _P, _I]),
     ("rt_set_lights", _I, [_P, _P, _I, _P, _I]),
+    ("rt_set_spheres", _I, [_P, _P, _I]),
     ("rt_bvh_info", _I, [_P, C.POINTER(_I), C.POINTER(_I)]),
     ("rt_set_counters", _I, [_P, _I]),
     ("rt_set_batch_rays", _I, [_P, C.c_uint]),
@@ -134,6 +135,7 @@ class SceneData:
     mats: np.ndarray         # (m,) MATERIAL_DTYPE
     point_lights: np.ndarray = field(default_factory=lambda: np.zeros((0, 6), np.float32))   # position, colour
     sphere_lights: np.ndarray = field(default_factory=lambda: np.zeros((0, 7), np.float32))  # position, radius, colour
+    spheres: np.ndarray = field(default_factory=lambda: np.zeros((0, 12), np.float32))       # centre, radius, kd, ks, shininess, transparency
 
     @property
     def n_tris(self) -> int:
@@ -213,9 +215,12 @@ class Context:
         pos, nrm = _f32(scene.pos), _f32(scene.nrm)
         ids = np.ascontiguousarray(scene.mesh_id, dtype=np.int32)
         mats = np.ascontiguousarray(scene.mats, dtype=MATERIAL_DTYPE)
-        _check(self._l.rt_upload_scene(self._h, pos.ctypes.data, nrm.ctypes.data, ids.ctypes.data, pos.shape[0], mats.ctypes.data, mats.shape[0]))
+        n = pos.shape[0]
+        _check(self._l.rt_upload_scene(self._h, pos.ctypes.data if n else None, nrm.ctypes.data if n else None, ids.ctypes.data if n else None, n,
+                                       mats.ctypes.data if len(mats) else None, mats.shape[0]))
         _check(self._l.rt_build_bvh(self._h, bvh_mode))
         self.set_lights(scene.point_lights, scene.sphere_lights)
+        self.set_spheres(scene.spheres)
 
     def build_bvh(self, mode: int):
         _check(self._l.rt_build_bvh(self._h, mode))
@@ -233,6 +238,11 @@ class Context:
         pl = _f32(point_lights if point_lights is not None else np.zeros((0, 6))).reshape(-1, 6)
         sl = _f32(sphere_lights if sphere_lights is not None else np.zeros((0, 7))).reshape(-1, 7)
         _check(self._l.rt_set_lights(self._h, pl.ctypes.data if len(pl) else None, len(pl), sl.ctypes.data if len(sl) else None, len(sl)))
+
+    def set_spheres(self, spheres=None):
+        """Scene::spheres: (n, 12) rows = centre (3), radius, kd (3), ks (3), shininess, transparency (== rt_sphere)."""
+        sp = _f32(spheres if spheres is not None else np.zeros((0, 12))).reshape(-1, 12)
+        _check(self._l.rt_set_spheres(self._h, sp.ctypes.data if len(sp) else None, len(sp)))
 
     def set_counters(self, enable: bool):
         _check(self._l.rt_set_counters(self._h, 1 if enable else 0))

@@ -33,6 +33,8 @@ CAM = dict(look_at=(0.0, 0.0, 0.0), euler_deg=(20.0, 20.0, 0.0), dist=3.0, fovy_
 def mint(name, sc, w, h, *, max_level, sphere_rays=10, sample_mode=0, sample_size=4, colour_from="reference", cam=CAM):
     c = rtb200.make_camera(**cam)
     ref, port = oracle.Oracle("reference"), oracle.Oracle("port")
+    for o in (ref, port):
+        o.set_spheres(sc.spheres)
     kw = dict(max_level=max_level, sphere_rays=sphere_rays, sample_mode=sample_mode, sample_size=sample_size, use_bvh=True)
     r_rgb, r_ids, r_t, r_st = ref.render(sc.pos, sc.nrm, sc.mesh_id, sc.mats, sc.point_lights, sc.sphere_lights, c, w, h, **kw)
     p_rgb, p_ids, p_t, p_st = port.render(sc.pos, sc.nrm, sc.mesh_id, sc.mats, sc.point_lights, sc.sphere_lights, c, w, h, **kw)
@@ -50,7 +52,7 @@ def mint(name, sc, w, h, *, max_level, sphere_rays=10, sample_mode=0, sample_siz
     # exact-t tie census on primary rays: would another triangle give the same t?  (informational)
     np.savez_compressed(
         os.path.join(OUT, name + ".npz"),
-        pos=sc.pos, nrm=sc.nrm, mesh_id=sc.mesh_id, mats=sc.mats, point_lights=sc.point_lights, sphere_lights=sc.sphere_lights,
+        pos=sc.pos, nrm=sc.nrm, mesh_id=sc.mesh_id, mats=sc.mats, point_lights=sc.point_lights, sphere_lights=sc.sphere_lights, spheres=sc.spheres,
         cam_look_at=np.array(cam["look_at"], np.float32), cam_euler_deg=np.array(cam["euler_deg"], np.float32),
         cam_dist=np.float32(cam["dist"]), cam_fovy_deg=np.float32(cam["fovy_deg"]),
         width=w, height=h, max_level=max_level, sphere_rays=sphere_rays, sample_mode=sample_mode, sample_size=sample_size,
@@ -58,6 +60,8 @@ def mint(name, sc, w, h, *, max_level, sphere_rays=10, sample_mode=0, sample_siz
         primary_rays=st.primary_rays, shadow_queries=st.shadow_queries, secondary_rays=st.secondary_rays,
         rgb_x=x_rgb, primary_rays_x=x_st.primary_rays, shadow_queries_x=x_st.shadow_queries, secondary_rays_x=x_st.secondary_rays,
         colour_from=colour_from, port_equals_reference=np.array([ids_equal, t_equal, rgb_equal]))
+    for o in (ref, port):
+        o.set_spheres(None)
     print(f"{name}: {sc.n_tris} tris {w}x{h} rays={st.rays} port==ref ids/t/rgb={ids_equal}/{t_equal}/{rgb_equal} "
           f"rgb_maxdiff={np.abs(r_rgb - p_rgb).max():.3g} hit={np.mean(r_ids >= 0):.3f} | exhaustive shadows: queries {st.shadow_queries}->{x_st.shadow_queries}, "
           f"pixels differing >1e-4: {int((np.abs(x_rgb - rgb).max(axis=2) > 1e-4).sum())}")
@@ -82,6 +86,16 @@ def main():
     # both light kinds, looking from inside the box
     mint("cornell_inside_128", with_lights(cornell(), point=[[0, 0.3, 0.2, 0.8, 0.7, 0.6]], sphere=[[0.1, 0.45, 0, 0.1, 0.5, 0.5, 1]]), 128, 128,
          max_level=4, sphere_rays=20, cam=dict(look_at=(0.0, 0.0, 0.0), euler_deg=(5.0, 170.0, 0.0), dist=0.9, fovy_deg=70.0))
+    # CornellBox preset exactly as loadScene builds it (scene.cpp:28-35): the box + one transparent sphere + point light
+    cb = with_lights(cornell(), point=[[0, 0.58, 0, 1, 1, 1]])
+    cb.spheres = np.array([[-0.2, 0.15, -0.25, 0.2, 0, 0, 0, 0, 0, 0, 1, 0]], np.float32)
+    mint("cornell_preset_sphere_192", cb, 192, 192, max_level=4)
+    # Spheres preset (scene.cpp:80-87): three opaque spheres, no triangles, a bright point light; plus a mirror sphere
+    sp = rtb200.SceneData(np.zeros((0, 9), np.float32), np.zeros((0, 9), np.float32), np.zeros(0, np.int32), np.zeros(0, rtb200.MATERIAL_DTYPE))
+    sp = with_lights(sp, point=[[3, 0, 3, 15, 15, 15]])
+    sp.spheres = np.array([[3, -2, 10.2, 1.0, .8, .2, .2, 0, 0, 0, 1, 1], [-2, 2, 4, 2.0, .6, .8, .2, 0, 0, 0, 1, 1], [0, 0, 6, .75, .2, .2, .8, 0, 0, 0, 1, 1],
+                           [1.5, 1.0, 5.0, 0.8, .05, .05, .05, .9, .9, .9, 0, 1]], np.float32)
+    mint("spheres_preset_160", sp, 160, 160, max_level=3)
     # Monkey preset: two point lights (scene.cpp:52-57), mirror-ish material
     mint("monkey_192", with_lights(rtb200.load_obj(DATA + "monkey-rotated.obj", True), point=[[-1, 1, -1, 1, 1, 1], [1, -1, -1, 1, 1, 1]]), 192, 192, max_level=3)
     # Cube preset (every material transparent: d 0.452632)

@@ -211,9 +211,16 @@ def test_errors_are_loud(rtb, gpu_ctx):
         gpu_ctx.render(g.camera(), bad)
     with pytest.raises(rtb.RtError):
         gpu_ctx.render(g.camera(), rtb.make_params(0, 10))
-    empty = rtb.SceneData(np.zeros((0, 9), np.float32), np.zeros((0, 9), np.float32), np.zeros(0, np.int32), g.scene.mats)
+    bad_ids = rtb.SceneData(g.scene.pos, g.scene.nrm, g.scene.mesh_id + 5, g.scene.mats)   # mesh ids outside the material table
     with pytest.raises(rtb.RtError):
-        rtb.Context(0).upload_scene(empty)
+        rtb.Context(0).upload_scene(bad_ids)
+    with pytest.raises(rtb.RtError):
+        gpu_ctx.set_spheres(np.zeros((65, 12), np.float32))                                  # more than 64 spheres
+    # a scene without any primitive is legal (the reference renders it black) and must not crash
+    empty = rtb.SceneData(np.zeros((0, 9), np.float32), np.zeros((0, 9), np.float32), np.zeros(0, np.int32), np.zeros(0, rtb.MATERIAL_DTYPE))
+    gpu_ctx.upload_scene(empty)
+    rgb, ids, t, st = gpu_ctx.render(g.camera(), rtb.make_params(64, 48, 2), want_ids=True)
+    assert rgb.max() == 0 and (ids == -1).all() and st.rays == 64 * 48
 
 
 def test_full_size_two_bvhs_agree_c3(rtb, gpu_ctx):

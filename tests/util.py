@@ -7,7 +7,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-GOLDEN_NAMES = ["cornell_c1_256", "cornell_c4_96", "cornell_sph10_aa_80x48", "cornell_ms16_70x45", "cornell_inside_128", "monkey_192",
+GOLDEN_NAMES = ["cornell_preset_sphere_192", "spheres_preset_160", "cornell_c1_256", "cornell_c4_96", "cornell_sph10_aa_80x48", "cornell_ms16_70x45", "cornell_inside_128", "monkey_192",
                 "cube_96", "tr_def_96", "teapot_c2_256x144", "teapot_d3_128x72", "dragon_standin_c3_160x90"]
 
 
@@ -30,6 +30,8 @@ class Golden:
         self.geometry_ok = True
         if "pos" in d:
             self.scene = rtb200.SceneData(d["pos"], d["nrm"], d["mesh_id"], d["mats"], d["point_lights"], d["sphere_lights"])
+            if "spheres" in d:
+                self.scene.spheres = d["spheres"]
         else:  # dragon stand-in: geometry is regenerated, the fixture only carries a checksum
             from rtb200 import standin
             sc = standin.dragon_standin_scene()
@@ -50,6 +52,7 @@ class Golden:
         import oracle
         o = oracle.Oracle(kind)
         s = self.scene
+        o.set_spheres(s.spheres)
         return o.render(s.pos, s.nrm, s.mesh_id, s.mats, s.point_lights, s.sphere_lights, self.camera(), self.w, self.h, max_level=self.max_level,
                         sphere_rays=self.sphere_rays, sample_mode=self.sample_mode, sample_size=self.sample_size, **kw)
 
