@@ -34,6 +34,8 @@ typedef struct {
 
 typedef struct { float position[3]; float color[3]; } rt_point_light;                /* src/scene.h:55-59 */
 typedef struct { float position[3]; float radius; float color[3]; } rt_sphere_light; /* src/scene.h:61-66 */
+typedef struct { float position[3]; float direction[3]; float angle /* degrees */; float color[3]; } rt_spot_light; /* src/scene.h:68-73 */
+typedef struct { float position[3]; float width[3]; float height[3]; float color[3]; } rt_plane_light;               /* src/scene.h:75-83 */
 
 /* Sphere primitive — replaces `struct Sphere` (src/scene.h:48-53) with its own material; intersected with the
  * reference's quadratic (src/ray_tracing.cpp:182-209).  A sphere hit is reported as triangle id n_tris + sphere index. */
@@ -59,8 +61,14 @@ typedef struct {
     float refraction_factor;    /* src/main.cpp:127                                                     */
     int sample_mode;            /* 0: one ray per pixel; 1: anti_aliasing (4 taps); 2: multipleRays     */
     int sample_size;            /* 4 / 16 / 64 when sample_mode == 2                                    */
-    int exhaustive;             /* 1: closest hit loops over every triangle in mesh order (the reference's
-                                   useBVH=false path, bounding_volume_hierarchy.cpp:51-72); 0: BVH      */
+    int use_bvh;                /* the reference's useBVH (src/main.cpp:60).  It never changes WHAT is hit, only which of
+                                   two objects at exactly the same t a camera / reflection ray reports: 1 = the one
+                                   its BVH visits first (bounding_volume_hierarchy.cpp:414-447), 0 = the one earlier
+                                   in mesh order (ibid. 51-72).  Shadow queries always use the BVH order
+                                   (shadow.cpp:42).  The device searches through its own BVH either way.      */
+    int exhaustive;             /* debugging aid: 1 = test every object for every ray instead of walking the device
+                                   BVH (same result, O(n) per ray)                                           */
+    int plane_light_ray_count_1d; /* src/main.cpp:125 (default 3): n x n samples per plane light; values < 2 mean 3 */
 } rt_params;
 
 typedef struct {
@@ -100,6 +108,9 @@ int rt_build_bvh(rt_ctx* ctx, int mode);
 int rt_set_materials(rt_ctx* ctx, const rt_material* mats, int n_mats);
 int rt_set_lights(rt_ctx* ctx, const rt_point_light* point, int n_point, const rt_sphere_light* sphere, int n_sphere);
 
+/* Scene::spotLight / Scene::planeLight (src/scene.h:93-94; getSpotLichts / getPlaneLights, src/shadow.cpp:229-321). */
+int rt_set_spot_lights(rt_ctx* ctx, const rt_spot_light* spot, int n_spot);
+int rt_set_plane_lights(rt_ctx* ctx, const rt_plane_light* plane, int n_plane);
 /* Scene::spheres (src/scene.h:88): read live every frame like the lights; at most 64.  Spheres are tested against every
  * ray before the triangle BVH is walked (the reference puts them into its BVH leaves, bounding_volume_hierarchy.cpp:283-292). */
 int rt_set_spheres(rt_ctx* ctx, const rt_sphere* spheres, int n_spheres);
@@ -116,7 +127,8 @@ int rt_set_counters(rt_ctx* ctx, int enable);
 #define RT_STAGE_SHADOW_POINT 3
 #define RT_STAGE_SHADOW_SPHERE 4
 #define RT_STAGE_RESOLVE 5
-#define RT_STAGE_COUNT 6
+#define RT_STAGE_SHADOW_PLANE 6
+#define RT_STAGE_COUNT 7
 int rt_set_stage_timing(rt_ctx* ctx, int enable);
 int rt_stage_times(rt_ctx* ctx, float* ms /* [RT_STAGE_COUNT] */, int* launches /* [RT_STAGE_COUNT] */);
 /* Shadow kernels of bounce level L run on a side stream concurrently with extend / shade of level L+1 (default on). */

@@ -58,6 +58,7 @@ class Oracle:
         self.lib.oracle_closest_hit.restype = C.c_int
         self.lib.oracle_kind.restype = C.c_char_p
         self.lib.oracle_set_spheres.restype = None
+        self.lib.oracle_set_extra_lights.restype = None
         assert self.lib.oracle_kind().decode() == kind
 
     def render(self, pos, nrm, mesh_id, mats, point_lights, sphere_lights, cam, width, height, max_level=5, sphere_rays=10,
@@ -98,7 +99,15 @@ class Oracle:
         sp = np.ascontiguousarray(spheres if spheres is not None else np.zeros((0, 12)), np.float32).reshape(-1, 12)
         self.lib.oracle_set_spheres(C.c_void_p(sp.ctypes.data if len(sp) else None), C.c_int(len(sp)))
 
+    def set_extra_lights(self, spot=None, plane=None, plane_ray_count_1d=3):
+        """spot: (n, 10) = position, direction, angle (degrees), colour; plane: (n, 12) = position, width, height, colour."""
+        sp = np.ascontiguousarray(spot if spot is not None else np.zeros((0, 10)), np.float32).reshape(-1, 10)
+        pl = np.ascontiguousarray(plane if plane is not None else np.zeros((0, 12)), np.float32).reshape(-1, 12)
+        self.lib.oracle_set_extra_lights(C.c_void_p(sp.ctypes.data if len(sp) else None), C.c_int(len(sp)),
+                                         C.c_void_p(pl.ctypes.data if len(pl) else None), C.c_int(len(pl)), C.c_int(int(plane_ray_count_1d)))
+
     def closest_hit(self, pos, nrm, mesh_id, rays, use_bvh=False):
+        """use_bvh: False/0 every object in id order, True/1 the reference-style BVH, 2 (port) every object in that BVH's visiting order."""
         pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 9)
         nrm = np.ascontiguousarray(nrm, np.float32).reshape(-1, 9)
         mesh_id = np.ascontiguousarray(mesh_id, np.int32)
@@ -106,7 +115,7 @@ class Oracle:
         ids = np.empty(rays.shape[0], np.int32)
         t = np.empty(rays.shape[0], np.float32)
         rc = self.lib.oracle_closest_hit(C.c_void_p(pos.ctypes.data), C.c_void_p(nrm.ctypes.data), C.c_void_p(mesh_id.ctypes.data), C.c_int(pos.shape[0]),
-                                         C.c_void_p(rays.ctypes.data), C.c_int(rays.shape[0]), C.c_int(1 if use_bvh else 0),
+                                         C.c_void_p(rays.ctypes.data), C.c_int(rays.shape[0]), C.c_int(int(use_bvh)),
                                          C.c_void_p(ids.ctypes.data), C.c_void_p(t.ctypes.data))
         if rc != 0:
             raise RuntimeError(f"oracle_closest_hit failed with {rc}")

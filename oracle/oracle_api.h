@@ -42,12 +42,15 @@ typedef struct {
     int defined_bary;           /* 1: define the uninitialised-barycentric case (port only)     */
     int x0, y0, x_step, y_step; /* render only pixels x0+i*x_step, y0+j*y_step (timing subsets) */
     int num_threads;            /* OpenMP threads, <=0: all                                     */
-    int shadow_exhaustive;      /* port only. 0: shadow queries go through the reference-style BVH, as
-                                   cansee does (shadow.cpp:42).  1: they search every triangle.  The
-                                   reference's AABB slab test (ray_tracing.cpp:213-264) occasionally culls a
-                                   box whose triangle the triangle test would accept (flat boxes, rounding);
-                                   the exhaustive answer is what the triangle arithmetic alone defines and
-                                   what a conservative BVH (the GPU path) returns.                            */
+    int shadow_exhaustive;      /* port only. 0: every BVH search runs as in the reference (cansee always uses the
+                                   BVH, shadow.cpp:42; the other rays when use_bvh).  1: those searches test every
+                                   object, in the depth-first order intersectBVH would reach them (so equal t
+                                   resolve to the same object, bvh.cpp:414-447), without the box tests.  The
+                                   reference's AABB slab test (ray_tracing.cpp:213-264) occasionally culls a box
+                                   whose triangle the triangle test would accept (flat boxes, rounding); the
+                                   cull-free answer is what the triangle arithmetic and the visiting order alone
+                                   define and what a conservative BVH (the GPU path) returns.  tri_id then also
+                                   follows the visiting order on equal t (lowest id otherwise).                  */
 } orc_params;
 
 typedef struct {
@@ -71,7 +74,8 @@ int oracle_render(const float* pos, const float* nrm, const int* mesh_id, int n_
     float* rgb, int* tri_id, float* t_hit, orc_stats* stats);
 
 /* Closest hit for caller-supplied rays (6 floats each: origin, direction), exhaustive (use_bvh=0,
- * reference brute-force order) or through the reference-style BVH (use_bvh=1). */
+ * reference brute-force order) or through the reference-style BVH (use_bvh=1); port only: use_bvh=2 = every
+ * object in the BVH's visiting order, no box tests. */
 int oracle_closest_hit(const float* pos, const float* nrm, const int* mesh_id, int n_tris,
     const float* rays, int n_rays, int use_bvh, int* tri_id, float* t_hit);
 
@@ -80,6 +84,11 @@ int oracle_closest_hit(const float* pos, const float* nrm, const int* mesh_id, i
  * shininess, transparency.  n = 0 clears them.  A sphere that wins the closest-hit query is reported with
  * tri_id = n_tris + sphere index. */
 void oracle_set_spheres(const float* spheres, int n);
+
+/* Spot and plane (area) lights (src/scene.h:68-86, getSpotLichts / getPlaneLights src/shadow.cpp:229-321) for the following
+ * oracle_render calls.  spot: 10 floats each = position (3), direction (3), angle in degrees, colour (3).  plane: 12 floats
+ * each = position (3), width (3), height (3), colour (3).  plane_ray_count_1d = plane_light_1D_ray_count (src/main.cpp:125). */
+void oracle_set_extra_lights(const float* spot, int n_spot, const float* plane, int n_plane, int plane_ray_count_1d);
 
 const char* oracle_kind(void); /* "reference" or "port" */
 

@@ -35,6 +35,10 @@ extern thread_local unsigned long long orc_drawray_calls;
 
 namespace {
 
+std::vector<float> g_spheres;       // oracle_set_spheres
+std::vector<float> g_spot, g_plane; // oracle_set_extra_lights
+int g_plane_rays = 3;               // plane_light_1D_ray_count, src/main.cpp:125
+
 struct RenderGlobals { // the file-scope knobs of src/main.cpp:58-60,123-127
     bool useBVH;
     int max_reflection_level;
@@ -103,7 +107,10 @@ glm::vec3 getFinalColor(const RenderGlobals& g, Scene& scene, const BoundingVolu
         color += calcColor(light, matForRendering);
     for (const Lighting& light : getSpherelights(hitInfo, reflect, scene, bvh, g.sphere_light_ray_count))
         color += calcColor(light, matForRendering);
-    // spot and plane lights: empty vectors in every in-scope scene (main.cpp:180-185)
+    for (const Lighting& light : getSpotLichts(hitInfo, reflect, scene, bvh))
+        color += calcColor(light, matForRendering);
+    for (const Lighting& light : getPlaneLights(hitInfo, reflect, scene, bvh, g_plane_rays))
+        color += calcColor(light, matForRendering);
 
     if (level >= g.max_reflection_level)
         return color;
@@ -157,7 +164,7 @@ std::vector<glm::vec2> getPixelRays(const RenderGlobals& g, glm::vec2 pixelCente
     return origins;
 }
 
-std::vector<float> g_spheres; // oracle_set_spheres
+
 
 void addSpheres(Scene& scene)
 {
@@ -231,6 +238,13 @@ int exhaustiveId(const float* pos, int n_tris, Ray ray, float& t_out, const Scen
 
 extern "C" const char* oracle_kind(void) { return "reference"; }
 
+extern "C" void oracle_set_extra_lights(const float* spot, int n_spot, const float* plane, int n_plane, int plane_ray_count_1d)
+{
+    g_spot.assign(spot, spot + (spot ? 10 * (size_t)n_spot : 0));
+    g_plane.assign(plane, plane + (plane ? 12 * (size_t)n_plane : 0));
+    g_plane_rays = plane_ray_count_1d;
+}
+
 extern "C" void oracle_set_spheres(const float* spheres, int n)
 {
     g_spheres.assign(spheres, spheres + (spheres ? 12 * (size_t)n : 0));
@@ -252,6 +266,14 @@ extern "C" int oracle_render(const float* pos, const float* nrm, const int* mesh
     for (int i = 0; i < n_sphere; i++)
         scene.sphericalLight.push_back(SphericalLight { glm::vec3(sphere_lights[7 * i], sphere_lights[7 * i + 1], sphere_lights[7 * i + 2]),
             sphere_lights[7 * i + 3], glm::vec3(sphere_lights[7 * i + 4], sphere_lights[7 * i + 5], sphere_lights[7 * i + 6]) });
+    for (size_t k = 0; k + 9 < g_spot.size(); k += 10) {
+        const float* f = &g_spot[k];
+        scene.spotLight.push_back(SpotLight { glm::vec3(f[0], f[1], f[2]), glm::vec3(f[3], f[4], f[5]), f[6], glm::vec3(f[7], f[8], f[9]) });
+    }
+    for (size_t k = 0; k + 11 < g_plane.size(); k += 12) {
+        const float* f = &g_plane[k];
+        scene.planeLight.push_back(PlaneLight { glm::vec3(f[0], f[1], f[2]), glm::vec3(f[3], f[4], f[5]), glm::vec3(f[6], f[7], f[8]), glm::vec3(f[9], f[10], f[11]) });
+    }
     BoundingVolumeHierarchy bvh(&scene);
 
     RenderGlobals g;

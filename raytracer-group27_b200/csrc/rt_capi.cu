@@ -70,7 +70,8 @@ struct rt_ctx {
     std::vector<float> h_pos;
     float coord_max = 1.0f;
     DevBuf<float> d_pos, d_nrm;
-    DevBuf<int> d_mesh, d_perm;
+    DevBuf<int> d_mesh, d_perm, d_rank;    // d_rank: visiting rank of every object in the reference's BVH (rt_reforder.cu)
+    std::vector<float> h_sphere_centres;   // what d_rank was computed for
     DevBuf<float4> d_plane, d_v0, d_v1, d_v2, d_n0, d_n1, d_n2, d_nodes, d_mats, d_point, d_sphere;
     float4* lbvh_nodes = nullptr; // owned when the device builder allocated them
     int* lbvh_perm = nullptr;
@@ -80,8 +81,10 @@ struct rt_ctx {
     int n_point = 0, n_sphere = 0;
     bool any_transparent = false;          // meshes or spheres
     bool mats_transparent = false, spheres_transparent = false;
-    DevBuf<float4> d_spheres;
+    DevBuf<float4> d_spheres, d_plane_lights;
     int n_spheres = 0;
+    std::vector<float4> h_point, h_spot; // point-like light table = point lights followed by spot lights
+    int n_point_user = 0, n_spot = 0, n_plane = 0;
     long long user_tris = 0;               // triangles the caller uploaded (0 allowed: a never-hit dummy is traced instead)
 
     // sharding
@@ -98,6 +101,7 @@ struct rt_ctx {
         cudaStream_t main = nullptr, side = nullptr;
         cudaEvent_t ev_shade[2] = { nullptr, nullptr }, ev_shadow[2] = { nullptr, nullptr }, ev_done = nullptr, ev_packed = nullptr;
         DevBuf<float4> q_o[2], q_d[2], q_w[2], sp_p[2], sp_a[2], sp_b[2], ss_p[2], ss_a[2], ss_b[2];
+        DevBuf<float4> pl_p[2], pl_a[2], pl_b[2], pl_r[2], pl_acc[2];
         DevBuf<int2> q_hit[2];
         DevBuf<float2> sphere_acc[2];
         DevBuf<Counters> counters;
@@ -142,7 +146,10 @@ struct rt_ctx {
         s.mats = d_mats.p;
         s.point_lights = d_point.p;
         s.sphere_lights = d_sphere.p;
+        s.plane_lights = d_plane_lights.p;
         s.spheres = d_spheres.p;
+        s.sphere_rank = d_rank.p ? d_rank.p + user_tris : nullptr;
+        s.tie_by_id = 0;
         s.n_spheres = n_spheres;
         s.sphere_id_base = (int)user_tris;
         s.n_tris = (int)n_tris;
@@ -246,8 +253,13 @@ int make_frame_params(const rt_ctx* ctx, const rt_camera* cam, const rt_params* 
     fp.refraction = prm->refraction_factor;
     fp.n_point = ctx->n_point;
     fp.n_sphere = ctx->n_sphere;
+    fp.n_plane = ctx->n_plane;
+    fp.pl_rc = prm->plane_light_ray_count_1d >= 2 ? prm->plane_light_ray_count_1d : 3;
+    if (fp.pl_rc > 64)
+        return fail(RT_ERR_INVALID, "plane_light_ray_count_1d must be <= 64");
     fp.any_transparent = ctx->any_transparent ? 1 : 0;
     fp.exhaustive = prm->exhaustive ? 1 : 0;
+    fp.tie_by_id = prm->use_bvh ? 0 : 1;
     // getSpherelights ring layout (shadow.cpp:190-196)
     int rc = prm->sphere_light_ray_count;
     if (ctx->n_sphere > 0 && rc < 1)
@@ -278,6 +290,7 @@ void set_parity(rt_ctx::Lane& ln, BatchDev& b, int par)
     b.sphere_acc = ln.sphere_acc[par].p;
     b.sq_point = ShadowQueue { ln.sp_p[par].p, ln.sp_a[par].p, ln.sp_b[par].p };
     b.sq_sphere = ShadowQueue { ln.ss_p[par].p, ln.ss_a[par].p, ln.ss_b[par].p };
+    b.sq_plane = PlaneQueue { ln.pl_p[par].p, ln.pl_a[par].p, ln.pl_b[par].p, ln.pl_r[par].p, ln.pl_acc[par].p };
 }
 
 // Size one lane's queues for batches of `batch_pixels` pixels and describe them in `b`.
@@ -310,7 +323,16 @@ int ensure_lane(rt_ctx* ctx, rt_ctx::Lane& ln, const FrameParams& fp, unsigned b
             CK(ln.ss_b[p].ensure(cap_sp));
             CK(ln.sphere_acc[p].ensure(cap_sp));
         }
+        if (fp.n_plane > 0) {
+            const size_t cap_pl = cap * (size_t)fp.n_plane;
+            CK(ln.pl_p[p].ensure(cap_pl));
+            CK(ln.pl_a[p].ensure(cap_pl));
+            CK(ln.pl_b[p].ensure(cap_pl));
+            CK(ln.pl_r[p].ensure(cap_pl));
+            CK(ln.pl_acc[p].ensure(cap_pl));
+        }
     }
+    b.plane_capacity = (unsigned)std::min<size_t>(cap * (size_t)std::max(1, fp.n_plane), 0xfffffff0u);
     set_parity(ln, b, 0);
     b.ray_capacity = (unsigned)std::min<size_t>(cap, 0xfffffff0u);
     b.shadow_pt_capacity = (unsigned)std::min<size_t>(cap_pt, 0xfffffff0u);
@@ -449,7 +471,9 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids
                 launch_level_reset(st, b.counters, qi ^ 1, -1, 0, par);
             {
                 StageScope sc(ctx, RT_STAGE_EXTEND, st);
-                launch_extend(st, ctx->sm_count, s, ctx->root_entry, fp, b, qi, level, (unsigned)first, ctx->counters_enabled);
+                SceneDev s_ext = s;
+                s_ext.tie_by_id = fp.tie_by_id; // shadow queries keep the BVH order (shadow.cpp:42)
+                launch_extend(st, ctx->sm_count, s_ext, ctx->root_entry, fp, b, qi, level, (unsigned)first, ctx->counters_enabled);
             }
             {
                 StageScope sc(ctx, RT_STAGE_SHADE, st);
@@ -470,6 +494,11 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids
             if (fp.n_sphere > 0) {
                 StageScope sc(ctx, RT_STAGE_SHADOW_SPHERE, ss);
                 launch_shadow_sphere(ss, ctx->sm_count, s, ctx->root_entry, fp, b, ctx->counters_enabled);
+                launches += 2;
+            }
+            if (fp.n_plane > 0) {
+                StageScope sc(ctx, RT_STAGE_SHADOW_PLANE, ss);
+                launch_shadow_plane(ss, ctx->sm_count, s, ctx->root_entry, fp, b, ctx->counters_enabled);
                 launches += 2;
             }
             if (ctx->overlap)
@@ -531,6 +560,19 @@ int check_ready(rt_ctx* ctx)
         return fail(RT_ERR_INVALID, "BVH not built (rt_build_bvh)");
     if (ctx->n_mats <= 0)
         return fail(RT_ERR_INVALID, "no materials");
+    return RT_OK;
+}
+
+// Tie keys of the triangle slots and spheres = visiting rank in the reference's own BVH over (triangles, spheres).
+int refresh_tie_keys(rt_ctx* ctx)
+{
+    CK(ctx->d_rank.ensure((size_t)ctx->user_tris + kMaxSpheres + 1));
+    const char* err = nullptr;
+    if (reference_visit_rank(ctx->stream, ctx->d_pos.p, ctx->user_tris, ctx->d_spheres.p, ctx->n_spheres, ctx->d_rank.p, &err) != 0)
+        return fail(RT_ERR_CUDA, std::string("reference visiting order: ") + (err ? err : "failed"));
+    launch_apply_tie_keys(ctx->stream, ctx->d_v0.p, ctx->d_v2.p, ctx->d_rank.p, ctx->n_tris, ctx->user_tris);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
     return RT_OK;
 }
 
@@ -602,7 +644,8 @@ int rt_destroy(rt_ctx* ctx)
     for (int l = 0; l < kMaxLanes; l++) {
         rt_ctx::Lane& ln = ctx->lanes[l];
         for (int k = 0; k < 2; k++) {
-            DevBuf<float4>* q[] = { &ln.q_o[k], &ln.q_d[k], &ln.q_w[k], &ln.sp_p[k], &ln.sp_a[k], &ln.sp_b[k], &ln.ss_p[k], &ln.ss_a[k], &ln.ss_b[k] };
+            DevBuf<float4>* q[] = { &ln.q_o[k], &ln.q_d[k], &ln.q_w[k], &ln.sp_p[k], &ln.sp_a[k], &ln.sp_b[k], &ln.ss_p[k], &ln.ss_a[k], &ln.ss_b[k],
+                &ln.pl_p[k], &ln.pl_a[k], &ln.pl_b[k], &ln.pl_r[k], &ln.pl_acc[k] };
             for (auto* b : q)
                 b->release();
             ln.q_hit[k].release();
@@ -632,12 +675,14 @@ int rt_destroy(rt_ctx* ctx)
     ctx->d_nrm.release();
     ctx->d_mesh.release();
     ctx->d_perm.release();
+    ctx->d_rank.release();
     ctx->prim_id.release();
     ctx->out_id.release();
     ctx->prim_t.release();
     ctx->out_t.release();
     ctx->rgb.release();
     ctx->d_spheres.release();
+    ctx->d_plane_lights.release();
     ctx->rays_in.release();
     ctx->flag.release();
     if (ctx->lbvh_nodes)
@@ -840,7 +885,9 @@ int rt_build_bvh(rt_ctx* ctx, int mode)
     launch_tri_setup(ctx->stream, ctx->d_pos.p, ctx->d_nrm.p, ctx->d_mesh.p, perm, (int)ctx->n_tris, ctx->d_plane.p, ctx->d_v0.p, ctx->d_v1.p,
         ctx->d_v2.p, ctx->d_n0.p, ctx->d_n1.p, ctx->d_n2.p);
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(ctx->stream));
+    rc = refresh_tie_keys(ctx);
+    if (rc)
+        return rc;
     ctx->bvh_built = true;
     return RT_OK;
 }
@@ -866,6 +913,20 @@ int rt_set_materials(rt_ctx* ctx, const rt_material* mats, int n_mats)
     return upload_materials(ctx, mats, n_mats);
 }
 
+// Upload the point-like light table: point lights followed by spot lights, 3 x float4 each.
+static int upload_point_like(rt_ctx* ctx)
+{
+    std::vector<float4> h = ctx->h_point;
+    h.insert(h.end(), ctx->h_spot.begin(), ctx->h_spot.end());
+    if (h.empty())
+        h.resize(3);
+    CK(ctx->d_point.ensure(h.size()));
+    CK(cudaMemcpyAsync(ctx->d_point.p, h.data(), h.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_point = ctx->n_point_user + ctx->n_spot;
+    return RT_OK;
+}
+
 int rt_set_lights(rt_ctx* ctx, const rt_point_light* point, int n_point, const rt_sphere_light* sphere, int n_sphere)
 {
     int rc = use_device(ctx);
@@ -875,22 +936,61 @@ int rt_set_lights(rt_ctx* ctx, const rt_point_light* point, int n_point, const r
         return fail(RT_ERR_INVALID, "rt_set_lights: too many lights");
     if ((n_point > 0 && !point) || (n_sphere > 0 && !sphere))
         return fail(RT_ERR_INVALID, "rt_set_lights: null array");
-    std::vector<float4> hp(2 * (size_t)std::max(1, n_point)), hs(2 * (size_t)std::max(1, n_sphere));
+    ctx->h_point.assign(3 * (size_t)n_point, make_float4(0, 0, 0, 0));
     for (int i = 0; i < n_point; i++) {
-        hp[2 * i] = make_float4(point[i].position[0], point[i].position[1], point[i].position[2], 0.0f);
-        hp[2 * i + 1] = make_float4(point[i].color[0], point[i].color[1], point[i].color[2], 0.0f);
+        ctx->h_point[3 * i] = make_float4(point[i].position[0], point[i].position[1], point[i].position[2], 0.0f);
+        ctx->h_point[3 * i + 1] = make_float4(point[i].color[0], point[i].color[1], point[i].color[2], 0.0f);
     }
+    ctx->n_point_user = n_point;
+    std::vector<float4> hs(2 * (size_t)std::max(1, n_sphere));
     for (int i = 0; i < n_sphere; i++) {
         hs[2 * i] = make_float4(sphere[i].position[0], sphere[i].position[1], sphere[i].position[2], sphere[i].radius);
         hs[2 * i + 1] = make_float4(sphere[i].color[0], sphere[i].color[1], sphere[i].color[2], 0.0f);
     }
-    CK(ctx->d_point.ensure(hp.size()));
     CK(ctx->d_sphere.ensure(hs.size()));
-    CK(cudaMemcpyAsync(ctx->d_point.p, hp.data(), hp.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_sphere.p, hs.data(), hs.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->n_point = n_point;
     ctx->n_sphere = n_sphere;
+    return upload_point_like(ctx);
+}
+
+int rt_set_spot_lights(rt_ctx* ctx, const rt_spot_light* spot, int n_spot)
+{
+    int rc = use_device(ctx);
+    if (rc)
+        return rc;
+    if (n_spot < 0 || n_spot > kMaxPointLights || (n_spot > 0 && !spot))
+        return fail(RT_ERR_INVALID, "rt_set_spot_lights: between 0 and 16 spot lights");
+    ctx->h_spot.assign(3 * (size_t)n_spot, make_float4(0, 0, 0, 0));
+    for (int i = 0; i < n_spot; i++) {
+        // cos(radians(angle)) with libm on the host, as the reference evaluates it (shadow.cpp:235)
+        const float cut = std::cos(spot[i].angle * 0.01745329251994329576923690768489f);
+        ctx->h_spot[3 * i] = make_float4(spot[i].position[0], spot[i].position[1], spot[i].position[2], 1.0f);
+        ctx->h_spot[3 * i + 1] = make_float4(spot[i].color[0], spot[i].color[1], spot[i].color[2], cut);
+        ctx->h_spot[3 * i + 2] = make_float4(spot[i].direction[0], spot[i].direction[1], spot[i].direction[2], 0.0f);
+    }
+    ctx->n_spot = n_spot;
+    return upload_point_like(ctx);
+}
+
+int rt_set_plane_lights(rt_ctx* ctx, const rt_plane_light* plane, int n_plane)
+{
+    int rc = use_device(ctx);
+    if (rc)
+        return rc;
+    if (n_plane < 0 || n_plane > kMaxSphereLights || (n_plane > 0 && !plane))
+        return fail(RT_ERR_INVALID, "rt_set_plane_lights: between 0 and 8 plane lights");
+    std::vector<float4> h(4 * (size_t)std::max(1, n_plane));
+    for (int i = 0; i < n_plane; i++) {
+        h[4 * i] = make_float4(plane[i].position[0], plane[i].position[1], plane[i].position[2], 0.0f);
+        h[4 * i + 1] = make_float4(plane[i].width[0], plane[i].width[1], plane[i].width[2], 0.0f);
+        h[4 * i + 2] = make_float4(plane[i].height[0], plane[i].height[1], plane[i].height[2], 0.0f);
+        h[4 * i + 3] = make_float4(plane[i].color[0], plane[i].color[1], plane[i].color[2], 0.0f);
+    }
+    CK(ctx->d_plane_lights.ensure(h.size()));
+    CK(cudaMemcpyAsync(ctx->d_plane_lights.p, h.data(), h.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_plane = n_plane;
     return RT_OK;
 }
 
@@ -913,7 +1013,17 @@ int rt_set_spheres(rt_ctx* ctx, const rt_sphere* spheres, int n_spheres)
     CK(ctx->d_spheres.ensure(h.size()));
     CK(cudaMemcpyAsync(ctx->d_spheres.p, h.data(), h.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<float> centres;
+    for (int i = 0; i < n_spheres; i++)
+        centres.insert(centres.end(), spheres[i].center, spheres[i].center + 3);
+    const bool moved = centres != ctx->h_sphere_centres;
+    ctx->h_sphere_centres = centres;
     ctx->n_spheres = n_spheres;
+    if (moved && ctx->bvh_built) { // the spheres are objects of the reference's BVH: its visiting order changes with them
+        rc = refresh_tie_keys(ctx);
+        if (rc)
+            return rc;
+    }
     ctx->spheres_transparent = any_t;
     ctx->any_transparent = ctx->mats_transparent || ctx->spheres_transparent;
     return RT_OK;
@@ -1157,7 +1267,9 @@ int rt_intersect(rt_ctx* ctx, const float* rays, int64_t n_rays, int use_bvh, in
     CK(ctx->flag.ensure(1));
     CK(cudaMemsetAsync(ctx->flag.p, 0, sizeof(unsigned), ctx->stream));
     CK(cudaMemcpyAsync(ctx->rays_in.p, rays, 6 * (size_t)n_rays * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    launch_intersect(ctx->stream, ctx->sm_count, ctx->scene_dev(), ctx->root_entry, ctx->rays_in.p, (long long)n_rays, use_bvh, ctx->out_id.p,
+    SceneDev s_int = ctx->scene_dev();
+    s_int.tie_by_id = use_bvh ? 0 : 1;
+    launch_intersect(ctx->stream, ctx->sm_count, s_int, ctx->root_entry, ctx->rays_in.p, (long long)n_rays, use_bvh, ctx->out_id.p,
         ctx->out_t.p, ctx->flag.p);
     CK(cudaGetLastError());
     unsigned flag = 0;

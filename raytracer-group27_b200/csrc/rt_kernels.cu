@@ -191,7 +191,7 @@ __global__ void k_tri_setup(const float* __restrict__ pos, const float* __restri
     plane[i] = make_float4(nn.x, nn.y, nn.z, D);
     v0o[i] = make_float4(v0.x, v0.y, v0.z, __int_as_float(g));
     v1o[i] = make_float4(v1.x, v1.y, v1.z, __int_as_float(mesh_id ? mesh_id[g] : 0));
-    v2o[i] = make_float4(v2.x, v2.y, v2.z, 0.0f);
+    v2o[i] = make_float4(v2.x, v2.y, v2.z, __int_as_float(g));
     const float* q = nrm + 9 * (size_t)g;
     n0o[i] = make_float4(q[0], q[1], q[2], 0.0f);
     n1o[i] = make_float4(q[3], q[4], q[5], 0.0f);
@@ -204,7 +204,7 @@ __global__ void k_tri_setup(const float* __restrict__ pos, const float* __restri
 __global__ void k_level_reset(Counters* c, int next_q, long long n_current, unsigned long long add_primary, int par)
 {
     c->work[0] = c->work[1] = 0;
-    c->sh[par].n_pt = c->sh[par].n_sp = c->sh[par].work_pt = c->sh[par].work_sp = 0;
+    c->sh[par].n_pt = c->sh[par].n_sp = c->sh[par].n_pl = c->sh[par].work_pt = c->sh[par].work_sp = c->sh[par].work_pl = 0;
     c->n_rays[next_q] = 0;
     if (n_current >= 0)
         c->n_rays[next_q ^ 1] = (unsigned)n_current;
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_extend(
         [&](unsigned item, const HitRec& best, f3&, f3&, HitRec&) {
             b.q[qi].hit[item] = make_int2(__float_as_int(best.t), best.ti);
             if (LEVEL0 && b.prim_id && (tag & 1)) { // first sample of the pixel
-                b.prim_id[tag >> 1] = best.ti != -1 ? best.id : -1;
+                b.prim_id[tag >> 1] = global_id(s, best);
                 b.prim_t[tag >> 1] = best.t;
             }
             return false;
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_extend(
 template <bool LEVEL0>
 __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams fp, BatchDev b, int qi, int level, unsigned first_lp)
 {
-    __shared__ unsigned smem[3][kShadeBlock / 32 + 1];
+    __shared__ unsigned smem[2][kShadeBlock / 32 + 1];
     const unsigned n = b.counters->n_rays[qi];
     const int qo = qi ^ 1;
     const unsigned n_round = (n + kShadeBlock - 1) / kShadeBlock * kShadeBlock;
@@ -341,13 +341,13 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
         }
         n_secondary += (want0 ? 1u : 0u) + (want1 ? 1u : 0u);
 
-        // one allocation round for: first child ray, point-light records (n_point per hit, contiguous), spherical-light
-        // records (n_sphere per hit); a second round for the refraction child (dielectric hits only)
-        unsigned* const counters[3] = { &b.counters->n_rays[qo], &b.counters->sh[b.par].n_pt, &b.counters->sh[b.par].n_sp };
-        const bool want[3] = { want0, hit && fp.n_point > 0, hit && fp.n_sphere > 0 };
-        const unsigned cap[3] = { b.ray_capacity, b.shadow_pt_capacity / (unsigned)max(fp.n_point, 1), b.shadow_sp_capacity / (unsigned)max(fp.n_sphere, 1) };
-        unsigned slot[3];
-        block_alloc<3>(counters, want, cap, &b.counters->overflow, slot, smem);
+        // one allocation round for: first child ray, spherical-light records (n_sphere per hit, contiguous); a second
+        // round for the refraction child (dielectric hits only)
+        unsigned* const counters[2] = { &b.counters->n_rays[qo], &b.counters->sh[b.par].n_sp };
+        const bool want[2] = { want0, hit && fp.n_sphere > 0 };
+        const unsigned cap[2] = { b.ray_capacity, b.shadow_sp_capacity / (unsigned)max(fp.n_sphere, 1) };
+        unsigned slot[2];
+        block_alloc<2>(counters, want, cap, &b.counters->overflow, slot, smem);
         unsigned slot1 = 0xffffffffu;
         if (fp.any_transparent) {
             unsigned* const c1[1] = { &b.counters->n_rays[qo] };
@@ -369,34 +369,82 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
             b.q[qo].d[slot1] = make_float4(refr.x, refr.y, refr.z, 0.0f);
             b.q[qo].w[slot1] = make_float4(w1.x, w1.y, w1.z, 0.0f);
         }
-        // direct light: one record per (hit, light); the shadow kernels add A * intensity + B when the light is visible
-        if (hit) {
-            const int n_lights = fp.n_point + fp.n_sphere;
-            for (int li = 0; li < n_lights; li++) {
-                const bool is_point = li < fp.n_point;
-                const unsigned base = is_point ? slot[1] : slot[2];
-                if (base == 0xffffffffu)
-                    continue;
-                const int lj = is_point ? li : li - fp.n_point;
-                const float4* L = is_point ? (s.point_lights + 2 * lj) : (s.sphere_lights + 2 * lj);
+        const f3 reflN = xnormalize(refl);
+        // Direct light.  Point and spot lights (getPointLights / getSpotLichts, shadow.cpp:106-131, 229-252): one shadow
+        // record per light, for a spot light only if the hit lies inside its cone; the shadow kernel adds
+        // A * intensity + B when the light is visible (calcColor, main.cpp:112-121).
+        for (int li = 0; li < fp.n_point; li++) {
+            const float4 L0 = __ldg(s.point_lights + 3 * li), L1 = __ldg(s.point_lights + 3 * li + 1);
+            const f3 lp = mk3(L0), lc = mk3(L1);
+            bool lit = hit;
+            if (hit && L0.w != 0.0f) { // spot: dot(normalize(direction), normalize(p - position)) > cos(radians(angle))
+                const f3 sd = mk3(__ldg(s.point_lights + 3 * li + 2));
+                lit = xdot(xnormalize(sd), xnormalize(xsub(sh.p, lp))) > L1.w;
+            }
+            unsigned* const cl[1] = { &b.counters->sh[b.par].n_pt };
+            const bool wl[1] = { lit };
+            const unsigned capl[1] = { b.shadow_pt_capacity };
+            unsigned sl1[1];
+            block_alloc<1>(cl, wl, capl, &b.counters->overflow, sl1, smem);
+            if (sl1[0] == 0xffffffffu)
+                continue;
+            const f3 ldir = xnormalize(xsub(lp, sh.p));
+            const float cosNL = fabsf(xdot(Nn, ldir));                 // shadow.cpp:125 / 245
+            const float cosRL = fmaxf(0.0f, xdot(reflN, ldir));         // shadow.cpp:126 / 246
+            const f3 A = mk3(w.x * kd.x * lc.x * cosNL, w.y * kd.y * lc.y * cosNL, w.z * kd.z * lc.z * cosNL);
+            f3 B = mk3(0, 0, 0);
+            if (shininess > 0.0f) {
+                const float sp = powf(cosRL, shininess);
+                B = mk3(w.x * lc.x * ks.x * sp, w.y * lc.y * ks.y * sp, w.z * lc.z * ks.z * sp);
+            }
+            b.sq_point.p_pix[sl1[0]] = make_float4(sh.p.x, sh.p.y, sh.p.z, __int_as_float(pix));
+            b.sq_point.a_light[sl1[0]] = make_float4(A.x, A.y, A.z, __int_as_float(li));
+            b.sq_point.b[sl1[0]] = make_float4(B.x, B.y, B.z, 0.0f);
+        }
+        // Spherical lights (getSpherelights, shadow.cpp:139-226): one record per light, sampled by k_shadow_sphere.
+        if (hit && slot[1] != 0xffffffffu) {
+            for (int lj = 0; lj < fp.n_sphere; lj++) {
+                const float4* L = s.sphere_lights + 2 * lj;
                 const f3 lp = mk3(__ldg(L)), lc = mk3(__ldg(L + 1));
                 const f3 ldir = xnormalize(xsub(lp, sh.p));
-                const float cosNL = fabsf(xdot(Nn, ldir));                         // shadow.cpp:125 / 218
-                const float cosRL = fmaxf(0.0f, xdot(xnormalize(refl), ldir));      // shadow.cpp:126 / 219
+                const float cosNL = fabsf(xdot(Nn, ldir));             // shadow.cpp:218
+                const float cosRL = fmaxf(0.0f, xdot(reflN, ldir));     // shadow.cpp:219
                 const f3 A = mk3(w.x * kd.x * lc.x * cosNL, w.y * kd.y * lc.y * cosNL, w.z * kd.z * lc.z * cosNL);
                 f3 B = mk3(0, 0, 0);
                 if (shininess > 0.0f) {
                     const float sp = powf(cosRL, shininess);
                     B = mk3(w.x * lc.x * ks.x * sp, w.y * lc.y * ks.y * sp, w.z * lc.z * ks.z * sp);
                 }
-                const ShadowQueue& sq = is_point ? b.sq_point : b.sq_sphere;
-                const unsigned sl = base * (unsigned)(is_point ? fp.n_point : fp.n_sphere) + (unsigned)lj;
-                sq.p_pix[sl] = make_float4(sh.p.x, sh.p.y, sh.p.z, __int_as_float(pix));
-                sq.a_light[sl] = make_float4(A.x, A.y, A.z, __int_as_float(lj));
-                sq.b[sl] = make_float4(B.x, B.y, B.z, 0.0f);
-                if (!is_point)
-                    b.sphere_acc[sl] = make_float2(0.0f, 0.0f);
+                const unsigned sl = slot[1] * (unsigned)fp.n_sphere + (unsigned)lj;
+                b.sq_sphere.p_pix[sl] = make_float4(sh.p.x, sh.p.y, sh.p.z, __int_as_float(pix));
+                b.sq_sphere.a_light[sl] = make_float4(A.x, A.y, A.z, __int_as_float(lj));
+                b.sq_sphere.b[sl] = make_float4(B.x, B.y, B.z, 0.0f);
+                b.sphere_acc[sl] = make_float2(0.0f, 0.0f);
             }
+        }
+        // Plane lights (getPlaneLights, shadow.cpp:255-321): a record for every hit in front of the light; its pl_rc^2
+        // samples are traced by k_shadow_plane, k_plane_finalize turns the sums into a Lighting and calcColor.
+        for (int lj = 0; lj < fp.n_plane; lj++) {
+            const f3 ppos = mk3(__ldg(s.plane_lights + 4 * lj)), pw = mk3(__ldg(s.plane_lights + 4 * lj + 1));
+            const f3 ph = mk3(__ldg(s.plane_lights + 4 * lj + 2)), pc = mk3(__ldg(s.plane_lights + 4 * lj + 3));
+            bool front = false;
+            if (hit) {
+                const f3 nrm = xnormalize(xcross(pw, ph));
+                const f3 centre = xadd(ppos, xmul(xadd(pw, ph), 0.5f)); // position + 0.5f * (width + height)
+                front = xdot(xnormalize(xsub(sh.p, centre)), nrm) > 0.0f;
+            }
+            unsigned* const cl[1] = { &b.counters->sh[b.par].n_pl };
+            const bool wl[1] = { front };
+            const unsigned capl[1] = { b.plane_capacity };
+            unsigned sl1[1];
+            block_alloc<1>(cl, wl, capl, &b.counters->overflow, sl1, smem);
+            if (sl1[0] == 0xffffffffu)
+                continue;
+            b.sq_plane.p_pix[sl1[0]] = make_float4(sh.p.x, sh.p.y, sh.p.z, __int_as_float(pix));
+            b.sq_plane.a_light[sl1[0]] = make_float4(w.x * kd.x * pc.x, w.y * kd.y * pc.y, w.z * kd.z * pc.z, __int_as_float(lj));
+            b.sq_plane.b_shin[sl1[0]] = make_float4(w.x * pc.x * ks.x, w.y * pc.y * ks.y, w.z * pc.z * ks.z, shininess);
+            b.sq_plane.refl[sl1[0]] = make_float4(reflN.x, reflN.y, reflN.z, 0.0f);
+            b.sq_plane.acc[sl1[0]] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
     }
     warp_add_u64(&b.counters->secondary_rays, n_secondary);
@@ -495,14 +543,14 @@ __device__ __forceinline__ void shadow_loop(const SceneDev& s, int root_entry, c
 template <bool ANYHIT, bool COUNT>
 __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_shadow_point(SceneDev s, int root_entry, FrameParams fp, BatchDev b)
 {
-    const unsigned n = b.counters->sh[b.par].n_pt * (unsigned)fp.n_point;
+    const unsigned n = b.counters->sh[b.par].n_pt;
     shadow_loop<ANYHIT, COUNT>(
         s, root_entry, fp, b, &b.counters->sh[b.par].work_pt, n,
         [&](unsigned i, f3& p1, f3& p2) {
             const float4 pp = b.sq_point.p_pix[i];
             const float4 al = b.sq_point.a_light[i];
             p1 = mk3(pp);
-            p2 = mk3(__ldg(&s.point_lights[2 * __float_as_int(al.w)]));
+            p2 = mk3(__ldg(&s.point_lights[3 * __float_as_int(al.w)]));
         },
         [&](unsigned i, bool visible, float intensity) {
             if (!visible)
@@ -595,6 +643,68 @@ __global__ void __launch_bounds__(256) k_sphere_finalize(FrameParams fp, BatchDe
     }
 }
 
+// K4d plane (area) lights (getPlaneLights, src/shadow.cpp:255-321).  Work item = (record, sample): sample (i, j) sits at
+// position + i*dy + j*dx, reached by the reference's sequential `py += dy`, `px += dx`.  Per record the kernel sums the
+// intensities of the visible samples, the terms max(dot(normalize(p - px), normal), 0) / length(p - px), their number, and
+// the largest cosine between the reflection direction and a visible sample.
+template <bool ANYHIT, bool COUNT>
+__global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_shadow_plane(SceneDev s, int root_entry, FrameParams fp, BatchDev b)
+{
+    const unsigned rc = (unsigned)fp.pl_rc, per = rc * rc;
+    const unsigned n = b.counters->sh[b.par].n_pl * per;
+    f3 sample = mk3(0, 0, 0); // position of the sample the lane is tracing
+    shadow_loop<ANYHIT, COUNT>(
+        s, root_entry, fp, b, &b.counters->sh[b.par].work_pl, n,
+        [&](unsigned j, f3& p1, f3& p2) {
+            const unsigned rec = j / per, k = j % per;
+            const int lj = __float_as_int(b.sq_plane.a_light[rec].w);
+            const f3 ppos = mk3(__ldg(s.plane_lights + 4 * lj)), pw = mk3(__ldg(s.plane_lights + 4 * lj + 1)), ph = mk3(__ldg(s.plane_lights + 4 * lj + 2));
+            const float step = xdiv(1.0f, (float)(fp.pl_rc - 1)); // 1.0f / (rayCount1D - 1)
+            const f3 dx = xmul(pw, step), dy = xmul(ph, step);
+            f3 px = ppos;
+            for (unsigned a = 0; a < k / rc; a++)
+                px = xadd(px, dy);
+            for (unsigned a = 0; a < k % rc; a++)
+                px = xadd(px, dx);
+            sample = px;
+            p1 = mk3(b.sq_plane.p_pix[rec]);
+            p2 = px;
+        },
+        [&](unsigned j, bool visible, float intensity) {
+            if (!visible)
+                return;
+            const unsigned rec = j / per;
+            const int lj = __float_as_int(b.sq_plane.a_light[rec].w);
+            const f3 nrm = xnormalize(xcross(mk3(__ldg(s.plane_lights + 4 * lj + 1)), mk3(__ldg(s.plane_lights + 4 * lj + 2))));
+            const f3 p = mk3(b.sq_plane.p_pix[rec]), rn = mk3(b.sq_plane.refl[rec]);
+            const f3 back = xsub(p, sample);
+            const float term = xdiv(fmaxf(xdot(xnormalize(back), nrm), 0.0f), xlength(back));
+            const float cosr = xdot(rn, xnormalize(xsub(sample, p)));
+            float* acc = reinterpret_cast<float*>(&b.sq_plane.acc[rec]);
+            atomicAdd(acc, intensity);
+            atomicAdd(acc + 1, term);
+            atomicAdd(acc + 2, 1.0f);
+            atomicMax(reinterpret_cast<int*>(acc + 3), __float_as_int(fmaxf(cosr, 0.0f))); // maxCosAngle starts at 0
+        });
+}
+
+// K4e: Lighting of a plane light (shadow.cpp:308-318) and calcColor (main.cpp:112-121) with cosLightSurfaceAngle = 1.
+__global__ void __launch_bounds__(256) k_plane_finalize(FrameParams fp, BatchDev b)
+{
+    const unsigned n = b.counters->sh[b.par].n_pl;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 acc = b.sq_plane.acc[i];
+        if (acc.y > 0.0f) {
+            const float intensity = (acc.x / acc.z) * acc.y / (float)(fp.pl_rc * fp.pl_rc);
+            const float4 pp = b.sq_plane.p_pix[i];
+            const float4 al = b.sq_plane.a_light[i];
+            const float4 bs = b.sq_plane.b_shin[i];
+            const float sp = bs.w > 0.0f ? powf(acc.w, bs.w) : 0.0f;
+            accumulate(b.accum, __float_as_int(pp.w), al.x * intensity + bs.x * sp, al.y * intensity + bs.y * sp, al.z * intensity + bs.z * sp);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // K5 resolve: sample average (src/main.cpp:374,384) and Screen::setPixel's y flip (src/screen.cpp:32-38).  One
 // warp writes one 32-pixel tile row = 512 contiguous bytes of float4; `out` may be a peer-mapped framebuffer of
@@ -658,7 +768,7 @@ __global__ void __launch_bounds__(128) k_intersect(SceneDev s, int root_entry, c
         } else {
             trace_exhaustive<false, false>(s, o, d, best, st);
         }
-        tri_id[i] = best.ti != -1 ? best.id : -1;
+        tri_id[i] = global_id(s, best);
         t_out[i] = best.t;
     }
 }
@@ -740,6 +850,21 @@ void launch_shadow_sphere(cudaStream_t st, int sm_count, const SceneDev& s, int 
     else
         k_shadow_sphere<false, false><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b);
     k_sphere_finalize<<<sm_count * 4, 256, 0, st>>>(fp, b);
+}
+
+void launch_shadow_plane(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count)
+{
+    const int grid = sm_count * RT_TRACE_GRID_MULT;
+    const bool anyhit = !fp.any_transparent;
+    if (anyhit && count)
+        k_shadow_plane<true, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b);
+    else if (anyhit)
+        k_shadow_plane<true, false><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b);
+    else if (count)
+        k_shadow_plane<false, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b);
+    else
+        k_shadow_plane<false, false><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b);
+    k_plane_finalize<<<sm_count * 4, 256, 0, st>>>(fp, b);
 }
 
 void launch_resolve(cudaStream_t st, int sm_count, const FrameParams& fp, unsigned first_lp, unsigned n_lp, const float4* accum,

@@ -15,6 +15,7 @@ void launch_extend(cudaStream_t st, int sm_count, const SceneDev& s, int root_en
 void launch_shade(cudaStream_t st, int sm_count, const SceneDev& s, const FrameParams& fp, const BatchDev& b, int qi, int level, unsigned first_lp);
 void launch_shadow_point(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count);
 void launch_shadow_sphere(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count);
+void launch_shadow_plane(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count);
 void launch_resolve(cudaStream_t st, int sm_count, const FrameParams& fp, unsigned first_lp, unsigned n_lp, const float4* accum,
     const int* prim_id, const float* prim_t, float4* out, int* out_id, float* out_t);
 void launch_pack_rgb(cudaStream_t st, int sm_count, const float4* in, float* out, size_t p0, size_t p1);
@@ -41,5 +42,11 @@ struct DeviceBvh {
     int depth = 0;
 };
 int build_bvh_lbvh_device(cudaStream_t st, const float* d_pos, long long n_tris, float pad, DeviceBvh* out, const char** err);
+
+// Visiting rank of every object (triangles 0..n_tris-1, then spheres) in the reference's own BVH (rt_reforder.cu): the tie key
+// of the traversal kernels.  d_spheres: 3 x float4 per sphere ({centre, radius} first).  d_rank: n_tris + n_spheres ints.
+int reference_visit_rank(cudaStream_t st, const float* d_pos, long long n_tris, const float4* d_spheres, int n_spheres, int* d_rank, const char** err);
+// tri_v0[slot].w = rank[global id] for ranked triangles (global id < n_ranked), the id itself otherwise
+void launch_apply_tie_keys(cudaStream_t st, float4* v0, const float4* v2, const int* rank, long long n_slots, long long n_ranked);
 
 } // namespace rtb

@@ -7,8 +7,9 @@
 // Semantics kept from the reference: a triangle is hit when the plane parameter t (measured along
 // normalize(direction), ray_tracing.cpp:65-71) satisfies 0 <= t < ray.t and the point origin + direction * t
 // (UN-normalised direction, ray_tracing.cpp:111) passes the three edge-sign tests, all >= 0 or all < 0.  The
-// reference's brute-force loop keeps the first strictly smaller t, i.e. the winner is the lexicographic minimum of
-// (t, global triangle id); a traversal in any order reproduces that with the tie rule below.  Box tests only have
+// reference keeps the first strictly smaller t, i.e. the winner is the lexicographic minimum of (t, visiting order):
+// the global object id in its brute-force loop (useBVH = false), the depth-first rank of its own BVH otherwise
+// (rt_reforder.cu); a traversal in any order reproduces either with the tie rule below (SceneDev::tie_by_id selects the key).  Box tests only have
 // to be conservative (never cull a triangle the reference would accept): boxes are padded at build time and the
 // slab comparison carries a rounding guard; the reference's own box test is not reproduced (its result never
 // changes which triangle wins).  The BVH assumes |direction| = 1 up to rounding, which holds
@@ -27,7 +28,7 @@ struct TraceStats {
 
 struct HitRec {
     float t;   // best t so far (search bound on entry)
-    int id;    // global id of the best hit (tie rule operand): triangle id, or n_tris + sphere index
+    int key;   // tie key of the best hit: its visiting rank in the reference's BVH, or its global id (tie_by_id searches)
     int ti;    // BVH-order index of the best triangle hit; -1 = none; -2 - k = sphere k
 };
 
@@ -46,11 +47,11 @@ __device__ __forceinline__ bool test_triangle(const SceneDev& s, int ti, const f
     if (!(t >= 0.0f) || !(t <= best.t))
         return false;
     const float4 a = __ldg(&s.tri_v0[ti]);
-    const int id = __float_as_int(a.w);
-    if (t == best.t && id >= best.id)
-        return false; // equal t: the lower global id wins (first tested in the reference's loop)
-    const float4 b = __ldg(&s.tri_v1[ti]);
     const float4 c = __ldg(&s.tri_v2[ti]);
+    const int key = __float_as_int(s.tie_by_id ? c.w : a.w);
+    if (t == best.t && key >= best.key)
+        return false; // equal t: the object the reference visits first wins
+    const float4 b = __ldg(&s.tri_v1[ti]);
     if (COUNT)
         st.tris_full++;
     const f3 v0 = mk3(a), v1 = mk3(b), v2 = mk3(c);
@@ -60,7 +61,7 @@ __device__ __forceinline__ bool test_triangle(const SceneDev& s, int ti, const f
     const bool s2 = xdot(xcross(xsub(p, v1), xsub(v0, v1)), n) >= 0.0f;
     if ((s0 && s1 && s2) || (!s0 && !s1 && !s2)) {
         best.t = t;
-        best.id = id;
+        best.key = key;
         best.ti = ti;
         return true;
     }
@@ -70,8 +71,8 @@ __device__ __forceinline__ bool test_triangle(const SceneDev& s, int ti, const f
 // Sphere primitives: intersectRayWithShape(const Sphere&, Ray&, HitInfo&) (src/ray_tracing.cpp:182-209).  The reference's
 // glm::pow(float, int) is std::pow and returns double, so the sums of squares and the discriminant are formed in double
 // and rounded to float; x*x of a float is exact in double, so pow(x, 2) is a plain product.  The parameter is along the
-// ray's own (un-normalised) direction.  In the reference's brute-force order spheres come after all triangles and a hit
-// needs t < ray.t strictly: with ids n_tris + k the (t, id) tie rule reproduces that whatever the test order.
+// ray's own (un-normalised) direction.  A hit needs t < ray.t strictly; in the reference's brute-force order spheres come
+// after all triangles (ids n_tris + k), in its BVH they are objects like the triangles (sphere_rank).
 __device__ __forceinline__ bool test_spheres(const SceneDev& s, const f3& o, const f3& d, HitRec& best)
 {
     bool any = false;
@@ -91,11 +92,13 @@ __device__ __forceinline__ bool test_spheres(const SceneDev& s, const f3& o, con
         if (t1 < 0.0f)
             t1 = t0;
         const float t = (t1 < t0) ? t1 : t0;
-        const int id = s.sphere_id_base + k;
-        if (!(t > 0.0f) || !(t <= best.t) || (t == best.t && id >= best.id))
+        if (!(t > 0.0f) || !(t <= best.t))
+            continue;
+        const int key = s.tie_by_id ? s.sphere_id_base + k : __ldg(&s.sphere_rank[k]);
+        if (t == best.t && key >= best.key)
             continue;
         best.t = t;
-        best.id = id;
+        best.key = key;
         best.ti = -2 - k;
         any = true;
     }
@@ -111,7 +114,15 @@ __device__ __forceinline__ HitRec fresh_query() { return HitRec { FLT_MAX, INT_M
 // Query bounded by an inclusive limit (shadow rays: blockers have t <= distance - 0.001).
 __device__ __forceinline__ HitRec bounded_query(float limit) { return HitRec { limit, INT_MAX, -1 }; }
 
-// Exhaustive search: every triangle (order irrelevant thanks to the tie rule).
+// Global id of a finished query's winner: triangle id, n_tris + sphere index, or -1.
+__device__ __forceinline__ int global_id(const SceneDev& s, const HitRec& best)
+{
+    if (best.ti >= 0)
+        return __float_as_int(__ldg(&s.tri_v2[best.ti]).w);
+    return best.ti == -1 ? -1 : s.sphere_id_base + (-2 - best.ti);
+}
+
+// Exhaustive search: every object (order irrelevant thanks to the tie rule).
 template <bool ANYHIT, bool COUNT>
 __device__ __forceinline__ void trace_exhaustive(const SceneDev& s, const f3& o, const f3& d, HitRec& best, TraceStats& st)
 {

@@ -27,16 +27,20 @@ constexpr int kMaxSpheres = 64;
 struct SceneDev {
     const float4* nodes;
     const float4* tri_plane; // {n.xyz, D}: trianglePlane() precomputed by K0 with the reference's op order
-    const float4* tri_v0;    // {v0.xyz, bits(global triangle id)}
+    const float4* tri_v0;    // {v0.xyz, bits(tie key: visiting rank in the reference's BVH, rt_reforder.cu)}
     const float4* tri_v1;    // {v1.xyz, bits(mesh id)}
-    const float4* tri_v2;    // {v2.xyz, 0}
+    const float4* tri_v2;    // {v2.xyz, bits(global triangle id)}
     const float4* tri_n0;    // corner normals, read only by shade / transparent shadow hits
     const float4* tri_n1;
     const float4* tri_n2;
     const float4* mats;          // 2 x float4 per mesh: {kd.xyz, shininess}{ks.xyz, transparency}
-    const float4* point_lights;  // 2 x float4: {pos, 0}{color, 0}
+    const float4* point_lights;  // point and spot lights, 3 x float4: {pos, kind 0|1}{color, cos(cut-off)}{spot direction, 0}
+    const float4* plane_lights;  // 4 x float4: {position}{width}{height}{color}
     const float4* sphere_lights; // 2 x float4: {pos, radius}{color, 0}
     const float4* spheres;       // sphere primitives, 3 x float4: {centre, radius}{kd, shininess}{ks, transparency}
+    const int* sphere_rank;      // visiting rank of sphere k in the reference's BVH (tie key, rt_reforder.cu)
+    int tie_by_id;               // tie key of this launch: 0 = visiting rank in the reference's BVH (every BVH search of the reference, i.e. all
+                                 // shadow queries and, with useBVH, the other rays), 1 = global id (its useBVH = false loop)
     int n_spheres;
     int sphere_id_base;          // global id of sphere 0 = number of triangles the caller uploaded
     int n_tris;
@@ -63,9 +67,12 @@ struct FrameParams {
     // shading
     int max_level;
     float refraction;
-    int n_point, n_sphere;
+    int n_point, n_sphere;      // n_point counts point AND spot lights (one shadow segment per light at most)
+    int n_plane;                // plane (area) lights
+    int pl_rc;                  // plane_light_1D_ray_count (src/main.cpp:125): pl_rc x pl_rc samples per plane light
     int any_transparent;
     int exhaustive;
+    int tie_by_id;   // camera / reflection rays: equal t go to the lower global id (useBVH = false) instead of the BVH visiting rank
     // spherical-light ring sampling (shadow.cpp:190-196), host-computed and shared with the oracle
     int sl_m, sl_n, sl_rc;
     float sl_sin, sl_omc;
@@ -81,7 +88,9 @@ struct Counters {
     // Shadow work is double-buffered by bounce-level parity so that the shadow kernels of level L (side stream) can run
     // concurrently with extend / shade of level L+1 (main stream).
     struct Shadow {
-        unsigned int n_pt;       // hits with point-light records (n_point consecutive records per hit)
+        unsigned int n_pt;       // point / spot light shadow records (one per hit and light inside whose cone the hit lies)
+        unsigned int n_pl;       // plane-light records (one per hit in front of the light)
+        unsigned int work_pl;
         unsigned int n_sp;       // hits with spherical-light records (n_sphere consecutive records per hit)
         unsigned int work_pt;    // work-fetch cursors of the two shadow kernels
         unsigned int work_sp;
@@ -110,9 +119,19 @@ struct ShadowQueue {
     float4* b;       // {B.rgb (added when the light is visible), 0}
 };
 
+struct PlaneQueue { // one record per (hit, plane light); the samples of a record share it
+    float4* p_pix;   // {hit point, bits(local pixel index)}
+    float4* a_light; // {throughput * kd * light colour, bits(light index)}
+    float4* b_shin;  // {throughput * light colour * ks, shininess}
+    float4* refl;    // {normalize(reflect direction), 0}
+    float4* acc;     // {sum of intensities, sum of cos/length terms, visible samples, bits(max cos to the reflection)}
+};
+
 struct BatchDev {
     RayQueue q[2];
     ShadowQueue sq_point, sq_sphere;
+    PlaneQueue sq_plane;
+    unsigned int plane_capacity;
     unsigned int ray_capacity;
     unsigned int shadow_pt_capacity;
     unsigned int shadow_sp_capacity;

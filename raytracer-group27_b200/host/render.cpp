@@ -5,6 +5,7 @@
 
 int max_reflection_level = 5;
 int sphere_light_ray_count = 10;
+int plane_light_1D_ray_count = 3;
 int glossy_ray_count = 1;
 float refraction_factor = 0.8f;
 bool useBVH = false;
@@ -40,6 +41,14 @@ void renderRayTracing(Scene& scene, const Trackball& camera, const BoundingVolum
     for (const SphericalLight& l : scene.sphericalLight)
         sl.push_back(rt_sphere_light { { l.position.x, l.position.y, l.position.z }, l.radius, { l.color.x, l.color.y, l.color.z } });
     check(rt_set_lights(ctx, pl.data(), (int)pl.size(), sl.data(), (int)sl.size()), "rt_set_lights");
+    std::vector<rt_spot_light> spots;
+    for (const SpotLight& l : scene.spotLight)
+        spots.push_back(rt_spot_light { { l.position.x, l.position.y, l.position.z }, { l.direction.x, l.direction.y, l.direction.z }, l.angle, { l.color.x, l.color.y, l.color.z } });
+    check(rt_set_spot_lights(ctx, spots.data(), (int)spots.size()), "rt_set_spot_lights");
+    std::vector<rt_plane_light> planes;
+    for (const PlaneLight& l : scene.planeLight)
+        planes.push_back(rt_plane_light { { l.position.x, l.position.y, l.position.z }, { l.width.x, l.width.y, l.width.z }, { l.height.x, l.height.y, l.height.z }, { l.color.x, l.color.y, l.color.z } });
+    check(rt_set_plane_lights(ctx, planes.data(), (int)planes.size()), "rt_set_plane_lights");
     std::vector<rt_sphere> sp;
     for (const Sphere& s : scene.spheres) {
         const Material& m = s.material;
@@ -60,7 +69,9 @@ void renderRayTracing(Scene& scene, const Trackball& camera, const BoundingVolum
     prm.refraction_factor = refraction_factor;
     prm.sample_mode = anti_aliasing ? 1 : (multipleRays ? 2 : 0);
     prm.sample_size = sampleSize;
-    prm.exhaustive = useBVH ? 0 : 0; // both reference settings give the same image; the BVH is always used
+    prm.use_bvh = useBVH ? 1 : 0; // only decides exact-t ties (rt_b200.h); the device BVH is always used
+    prm.exhaustive = 0;
+    prm.plane_light_ray_count_1d = plane_light_1D_ray_count;
     rt_stats st {};
     static_assert(sizeof(glm::vec3) == 3 * sizeof(float), "Screen pixels must be packed float3");
     check(rt_render(ctx, &cam, &prm, &screen.pixels()[0].x, nullptr, nullptr, &st), "rt_render");

@@ -9,6 +9,7 @@
 
 extern int max_reflection_level;   // default 5
 extern int sphere_light_ray_count; // default 10
+extern int plane_light_1D_ray_count; // default 3
 extern int glossy_ray_count;       // reference default 10 uses rand(); only the deterministic value 1 is supported
 extern float refraction_factor;    // default 0.8
 extern bool useBVH;                // reference default false (brute force); both settings give the same image

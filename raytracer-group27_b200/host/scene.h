@@ -73,8 +73,8 @@ struct Scene {
 
     std::vector<PointLight> pointLights;
     std::vector<SphericalLight> sphericalLight;
-    std::vector<PlaneLight> planeLight; // not traced yet
-    std::vector<SpotLight> spotLight;   // not traced yet
+    std::vector<PlaneLight> planeLight;
+    std::vector<SpotLight> spotLight;
 };
 
 // Presets with the reference's light placements (src/scene.cpp:4-150).

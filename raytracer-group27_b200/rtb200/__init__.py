@@ -43,7 +43,7 @@ class Camera(C.Structure):
 class Params(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("max_reflection_level", C.c_int), ("sphere_light_ray_count", C.c_int),
                 ("glossy_ray_count", C.c_int), ("refraction_factor", C.c_float), ("sample_mode", C.c_int), ("sample_size", C.c_int),
-                ("exhaustive", C.c_int)]
+                ("use_bvh", C.c_int), ("exhaustive", C.c_int), ("plane_light_ray_count_1d", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -71,6 +71,8 @@ SYMBOLS = [
     ("rt_set_materials", _I, [_P, _P, _I]),
     ("rt_set_lights", _I, [_P, _P, _I, _P, _I]),
     ("rt_set_spheres", _I, [_P, _P, _I]),
+    ("rt_set_spot_lights", _I, [_P, _P, _I]),
+    ("rt_set_plane_lights", _I, [_P, _P, _I]),
     ("rt_bvh_info", _I, [_P, C.POINTER(_I), C.POINTER(_I)]),
     ("rt_set_counters", _I, [_P, _I]),
     ("rt_set_batch_rays", _I, [_P, C.c_uint]),
@@ -136,6 +138,8 @@ class SceneData:
     point_lights: np.ndarray = field(default_factory=lambda: np.zeros((0, 6), np.float32))   # position, colour
     sphere_lights: np.ndarray = field(default_factory=lambda: np.zeros((0, 7), np.float32))  # position, radius, colour
     spheres: np.ndarray = field(default_factory=lambda: np.zeros((0, 12), np.float32))       # centre, radius, kd, ks, shininess, transparency
+    spot_lights: np.ndarray = field(default_factory=lambda: np.zeros((0, 10), np.float32))   # position, direction, angle (deg), colour
+    plane_lights: np.ndarray = field(default_factory=lambda: np.zeros((0, 12), np.float32))  # position, width, height, colour
 
     @property
     def n_tris(self) -> int:
@@ -172,7 +176,7 @@ def make_camera(look_at=(0.0, 0.0, 0.0), euler_deg=(20.0, 20.0, 0.0), dist=3.0, 
     return cam
 
 
-def make_params(width, height, max_level=5, sphere_rays=10, refraction=0.8, sample_mode=0, sample_size=4, exhaustive=False) -> Params:
+def make_params(width, height, max_level=5, sphere_rays=10, refraction=0.8, sample_mode=0, sample_size=4, exhaustive=False, plane_rays_1d=3, use_bvh=True) -> Params:
     p = Params()
     p.width, p.height = int(width), int(height)
     p.max_reflection_level = int(max_level)
@@ -180,7 +184,9 @@ def make_params(width, height, max_level=5, sphere_rays=10, refraction=0.8, samp
     p.glossy_ray_count = 1
     p.refraction_factor = float(refraction)
     p.sample_mode, p.sample_size = int(sample_mode), int(sample_size)
+    p.use_bvh = 1 if use_bvh else 0
     p.exhaustive = 1 if exhaustive else 0
+    p.plane_light_ray_count_1d = int(plane_rays_1d)
     return p
 
 
@@ -221,6 +227,8 @@ class Context:
         _check(self._l.rt_build_bvh(self._h, bvh_mode))
         self.set_lights(scene.point_lights, scene.sphere_lights)
         self.set_spheres(scene.spheres)
+        self.set_spot_lights(scene.spot_lights)
+        self.set_plane_lights(scene.plane_lights)
 
     def build_bvh(self, mode: int):
         _check(self._l.rt_build_bvh(self._h, mode))
@@ -244,18 +252,26 @@ class Context:
         sp = _f32(spheres if spheres is not None else np.zeros((0, 12))).reshape(-1, 12)
         _check(self._l.rt_set_spheres(self._h, sp.ctypes.data if len(sp) else None, len(sp)))
 
+    def set_spot_lights(self, spot=None):
+        sp = _f32(spot if spot is not None else np.zeros((0, 10))).reshape(-1, 10)
+        _check(self._l.rt_set_spot_lights(self._h, sp.ctypes.data if len(sp) else None, len(sp)))
+
+    def set_plane_lights(self, plane=None):
+        pl = _f32(plane if plane is not None else np.zeros((0, 12))).reshape(-1, 12)
+        _check(self._l.rt_set_plane_lights(self._h, pl.ctypes.data if len(pl) else None, len(pl)))
+
     def set_counters(self, enable: bool):
         _check(self._l.rt_set_counters(self._h, 1 if enable else 0))
 
-    STAGES = ("generate", "extend", "shade", "shadow_point", "shadow_sphere", "resolve")
+    STAGES = ("generate", "extend", "shade", "shadow_point", "shadow_sphere", "resolve", "shadow_plane")
 
     def set_stage_timing(self, enable: bool):
         _check(self._l.rt_set_stage_timing(self._h, 1 if enable else 0))
 
     def stage_times(self) -> dict:
         """{stage: (ms, launches)} of the frame completed by the last sync()/render()."""
-        ms = (C.c_float * 6)()
-        n = (C.c_int * 6)()
+        ms = (C.c_float * 7)()
+        n = (C.c_int * 7)()
         _check(self._l.rt_stage_times(self._h, ms, n))
         return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(self.STAGES)}
 

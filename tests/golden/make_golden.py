@@ -30,16 +30,18 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 CAM = dict(look_at=(0.0, 0.0, 0.0), euler_deg=(20.0, 20.0, 0.0), dist=3.0, fovy_deg=50.0)  # src/main.cpp:413-414
 
 
-def mint(name, sc, w, h, *, max_level, sphere_rays=10, sample_mode=0, sample_size=4, colour_from="reference", cam=CAM):
+def mint(name, sc, w, h, *, max_level, sphere_rays=10, sample_mode=0, sample_size=4, colour_from="reference", cam=CAM, plane_rays_1d=3):
     c = rtb200.make_camera(**cam)
     ref, port = oracle.Oracle("reference"), oracle.Oracle("port")
     for o in (ref, port):
         o.set_spheres(sc.spheres)
+        o.set_extra_lights(sc.spot_lights, sc.plane_lights, plane_rays_1d)
     kw = dict(max_level=max_level, sphere_rays=sphere_rays, sample_mode=sample_mode, sample_size=sample_size, use_bvh=True)
     r_rgb, r_ids, r_t, r_st = ref.render(sc.pos, sc.nrm, sc.mesh_id, sc.mats, sc.point_lights, sc.sphere_lights, c, w, h, **kw)
     p_rgb, p_ids, p_t, p_st = port.render(sc.pos, sc.nrm, sc.mesh_id, sc.mats, sc.point_lights, sc.sphere_lights, c, w, h, **kw)
-    # the same frame with shadow queries answered exhaustively (what the triangle arithmetic alone defines; the
-    # reference's AABB test occasionally culls a box whose triangle the triangle test would accept)
+    # the same frame with every BVH search made cull-free: all objects tested in the BVH's own visiting order (what the
+    # triangle arithmetic and that order alone define; the reference's AABB test occasionally culls a box whose triangle
+    # the triangle test would accept).  ids_x: winners of the primary rays with exact-t ties resolved by that order.
     x_rgb, x_ids, x_t, x_st = port.render(sc.pos, sc.nrm, sc.mesh_id, sc.mats, sc.point_lights, sc.sphere_lights, c, w, h, shadow_exhaustive=True, **kw)
     ids_equal = bool(np.array_equal(r_ids, p_ids))
     t_equal = bool(np.array_equal(r_t.view(np.int32), p_t.view(np.int32)))
@@ -47,24 +49,27 @@ def mint(name, sc, w, h, *, max_level, sphere_rays=10, sample_mode=0, sample_siz
     rgb = r_rgb if colour_from == "reference" else p_rgb
     st = r_st if colour_from == "reference" else p_st
     assert ids_equal and t_equal, name
+    assert np.array_equal(x_t.view(np.int32), r_t.view(np.int32)), name
     if colour_from == "reference":
         assert rgb_equal, name
     # exact-t tie census on primary rays: would another triangle give the same t?  (informational)
     np.savez_compressed(
         os.path.join(OUT, name + ".npz"),
         pos=sc.pos, nrm=sc.nrm, mesh_id=sc.mesh_id, mats=sc.mats, point_lights=sc.point_lights, sphere_lights=sc.sphere_lights, spheres=sc.spheres,
+        spot_lights=sc.spot_lights, plane_lights=sc.plane_lights, plane_rays_1d=plane_rays_1d,
         cam_look_at=np.array(cam["look_at"], np.float32), cam_euler_deg=np.array(cam["euler_deg"], np.float32),
         cam_dist=np.float32(cam["dist"]), cam_fovy_deg=np.float32(cam["fovy_deg"]),
         width=w, height=h, max_level=max_level, sphere_rays=sphere_rays, sample_mode=sample_mode, sample_size=sample_size,
-        rgb=rgb, ids=r_ids, t=r_t,
+        rgb=rgb, ids=r_ids, t=r_t, ids_x=x_ids,
         primary_rays=st.primary_rays, shadow_queries=st.shadow_queries, secondary_rays=st.secondary_rays,
         rgb_x=x_rgb, primary_rays_x=x_st.primary_rays, shadow_queries_x=x_st.shadow_queries, secondary_rays_x=x_st.secondary_rays,
         colour_from=colour_from, port_equals_reference=np.array([ids_equal, t_equal, rgb_equal]))
     for o in (ref, port):
         o.set_spheres(None)
+        o.set_extra_lights(None, None, 3)
     print(f"{name}: {sc.n_tris} tris {w}x{h} rays={st.rays} port==ref ids/t/rgb={ids_equal}/{t_equal}/{rgb_equal} "
           f"rgb_maxdiff={np.abs(r_rgb - p_rgb).max():.3g} hit={np.mean(r_ids >= 0):.3f} | exhaustive shadows: queries {st.shadow_queries}->{x_st.shadow_queries}, "
-          f"pixels differing >1e-4: {int((np.abs(x_rgb - rgb).max(axis=2) > 1e-4).sum())}")
+          f"pixels differing >1e-4: {int((np.abs(x_rgb - rgb).max(axis=2) > 1e-4).sum())}, tie pixels (visiting order != id order): {int((x_ids != r_ids).sum())}")
 
 
 def with_lights(sc, point=None, sphere=None):
@@ -96,6 +101,34 @@ def main():
     sp.spheres = np.array([[3, -2, 10.2, 1.0, .8, .2, .2, 0, 0, 0, 1, 1], [-2, 2, 4, 2.0, .6, .8, .2, 0, 0, 0, 1, 1], [0, 0, 6, .75, .2, .2, .8, 0, 0, 0, 1, 1],
                            [1.5, 1.0, 5.0, 0.8, .05, .05, .05, .9, .9, .9, 0, 1]], np.float32)
     mint("spheres_preset_160", sp, 160, 160, max_level=3)
+    # CornellBoxPlaneLight preset (scene.cpp:44-50): one plane light, 3 x 3 samples; and a denser 4 x 4 variant from inside
+    cp = with_lights(cornell())
+    cp.plane_lights = np.array([[-0.1, 0.63, -0.1, 0.15, -0.05, 0, 0, 0, 0.2, 1, 1, 1]], np.float32)
+    mint("cornell_planelight_160", cp, 160, 160, max_level=3)
+    cp2 = with_lights(cornell(), point=[[0.2, 0.2, 0.3, 0.3, 0.3, 0.3]])
+    cp2.plane_lights = np.array([[-0.1, 0.63, -0.1, 0.15, -0.05, 0, 0, 0, 0.2, 1, 0.9, 0.8]], np.float32)
+    mint("cornell_planelight_inside_96", cp2, 96, 96, max_level=2, plane_rays_1d=4, cam=dict(look_at=(0.0, 0.0, 0.0), euler_deg=(5.0, 170.0, 0.0), dist=0.9, fovy_deg=70.0))
+    # Cube preset exactly as loadScene builds it (scene.cpp:18-26): point light + spot light, all faces transparent
+    cu = with_lights(rtb200.load_obj(DATA + "cube.obj", False), point=[[-1, 1, -1, 1, 1, 1]])
+    cu.spot_lights = np.array([[-1.2, -1, -1, 1, 1.2, 1, 10, 1, 1, 1]], np.float32)
+    mint("cube_preset_spot_128", cu, 128, 128, max_level=3)
+    # a narrow spot on the monkey: most hits fall outside the cone
+    ms = with_lights(rtb200.load_obj(DATA + "monkey-rotated.obj", True))
+    ms.spot_lights = np.array([[-1.5, 1.0, -2.0, 1.5, -0.9, 2.0, 12, 1, 0.8, 0.6], [1.0, 1.5, -1.5, -1.0, -1.4, 1.5, 25, 0.2, 0.3, 0.9]], np.float32)
+    mint("monkey_spots_128", ms, 128, 128, max_level=2)
+    # z-fighting: two coplanar overlapping triangles (exact ties in t over the whole overlap) whose order in the reference's
+    # BVH (sorted by centroid y: the green one first) is the reverse of their order in the mesh list (the red one first).
+    # The green one is transparent, the red one opaque, so shadow rays (always through the BVH) and primary rays (useBVH)
+    # both depend on who wins the tie; a mirror floor adds secondary rays that meet the pair from below
+    zpos = np.array([[-1, -0.5, 0, 1, -0.5, 0, 0, 1.5, 0], [-1, -1, 0, 1, -1, 0, 0, 0.8, 0], [-3, -1.2, -3, 0, -1.2, 3, 3, -1.2, -3]], np.float32)
+    znrm = np.array([[0, 0, 1] * 3, [0, 0, 1] * 3, [0, 1, 0] * 3], np.float32)
+    zm = np.zeros(3, rtb200.MATERIAL_DTYPE)
+    zm["kd"] = [[0.8, 0.1, 0.1], [0.1, 0.8, 0.1], [0.3, 0.3, 0.6]]
+    zm["ks"] = [[0, 0, 0], [0, 0, 0], [0.5, 0.5, 0.5]]
+    zm["shininess"] = [0, 0, 8]
+    zm["transparency"] = [1.0, 0.5, 1.0]
+    zf = with_lights(rtb200.SceneData(zpos, znrm, np.arange(3, dtype=np.int32), zm), point=[[0.3, 2, 2.5, 1, 1, 1], [0.3, 2, -2.5, 0.7, 0.7, 0.7]])
+    mint("zfight_96", zf, 96, 96, max_level=2)
     # Monkey preset: two point lights (scene.cpp:52-57), mirror-ish material
     mint("monkey_192", with_lights(rtb200.load_obj(DATA + "monkey-rotated.obj", True), point=[[-1, 1, -1, 1, 1, 1], [1, -1, -1, 1, 1, 1]]), 192, 192, max_level=3)
     # Cube preset (every material transparent: d 0.452632)

@@ -7,8 +7,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-GOLDEN_NAMES = ["cornell_preset_sphere_192", "spheres_preset_160", "cornell_c1_256", "cornell_c4_96", "cornell_sph10_aa_80x48", "cornell_ms16_70x45", "cornell_inside_128", "monkey_192",
-                "cube_96", "tr_def_96", "teapot_c2_256x144", "teapot_d3_128x72", "dragon_standin_c3_160x90"]
+GOLDEN_NAMES = ["cornell_planelight_160", "cornell_planelight_inside_96", "cube_preset_spot_128", "monkey_spots_128", "cornell_preset_sphere_192", "spheres_preset_160", "cornell_c1_256", "cornell_c4_96", "cornell_sph10_aa_80x48", "cornell_ms16_70x45", "cornell_inside_128", "monkey_192",
+                "cube_96", "zfight_96", "tr_def_96", "teapot_c2_256x144", "teapot_d3_128x72", "dragon_standin_c3_160x90"]
 
 
 class Golden:
@@ -20,7 +20,11 @@ class Golden:
         self.w, self.h = int(d["width"]), int(d["height"])
         self.max_level, self.sphere_rays = int(d["max_level"]), int(d["sphere_rays"])
         self.sample_mode, self.sample_size = int(d["sample_mode"]), int(d["sample_size"])
+        self.plane_rays_1d = int(d["plane_rays_1d"]) if "plane_rays_1d" in d else 3
         self.rgb, self.ids, self.t = d["rgb"], d["ids"], d["t"]
+        # closest-hit ids with exact-t ties resolved by the visiting order of the reference's BVH (what its useBVH=true
+        # search returns when no box test culls); self.ids resolves them by global id (its useBVH=false loop)
+        self.ids_x = d["ids_x"]
         self.counts = (int(d["primary_rays"]), int(d["shadow_queries"]), int(d["secondary_rays"]))
         # same frame with shadow queries answered exhaustively (oracle_api.h: shadow_exhaustive)
         self.rgb_x = d["rgb_x"]
@@ -32,6 +36,8 @@ class Golden:
             self.scene = rtb200.SceneData(d["pos"], d["nrm"], d["mesh_id"], d["mats"], d["point_lights"], d["sphere_lights"])
             if "spheres" in d:
                 self.scene.spheres = d["spheres"]
+            if "spot_lights" in d:
+                self.scene.spot_lights, self.scene.plane_lights = d["spot_lights"], d["plane_lights"]
         else:  # dragon stand-in: geometry is regenerated, the fixture only carries a checksum
             from rtb200 import standin
             sc = standin.dragon_standin_scene()
@@ -44,15 +50,16 @@ class Golden:
         import rtb200
         return rtb200.make_camera(**self.cam_kw)
 
-    def params(self, exhaustive=False):
+    def params(self, exhaustive=False, use_bvh=True):
         import rtb200
-        return rtb200.make_params(self.w, self.h, self.max_level, self.sphere_rays, 0.8, self.sample_mode, self.sample_size, exhaustive)
+        return rtb200.make_params(self.w, self.h, self.max_level, self.sphere_rays, 0.8, self.sample_mode, self.sample_size, exhaustive, self.plane_rays_1d, use_bvh)
 
     def oracle_render(self, kind="port", **kw):
         import oracle
         o = oracle.Oracle(kind)
         s = self.scene
         o.set_spheres(s.spheres)
+        o.set_extra_lights(s.spot_lights, s.plane_lights, self.plane_rays_1d)
         return o.render(s.pos, s.nrm, s.mesh_id, s.mats, s.point_lights, s.sphere_lights, self.camera(), self.w, self.h, max_level=self.max_level,
                         sphere_rays=self.sphere_rays, sample_mode=self.sample_mode, sample_size=self.sample_size, **kw)
 
