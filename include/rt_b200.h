@@ -108,6 +108,42 @@ int rt_build_bvh(rt_ctx* ctx, int mode);
 int rt_set_materials(rt_ctx* ctx, const rt_material* mats, int n_mats);
 int rt_set_lights(rt_ctx* ctx, const rt_point_light* point, int n_point, const rt_sphere_light* sphere, int n_sphere);
 
+/* Screen post-processing: the step renderRayTracing ends with (screen.postprocessImage(), src/main.cpp:397-398), and the
+ * bloom + 8-bit conversion of Screen::writeBitmapToFile (src/screen.cpp:40-53).  Fields = Screen's private settings
+ * (src/screen.h:84-101) as its setters leave them (src/screen.cpp:172-223). */
+#define RT_FILTER_NONE 0              /* FilteringOption, src/screen.h:17-26 */
+#define RT_FILTER_BLOOM 1
+#define RT_FILTER_BLOOM_REINHARD 2
+#define RT_FILTER_BLOOM_EXPOSURE 3
+#define RT_FILTER_ONLY_LIGHT 4
+#define RT_FILTER_ONLY_LIGHT_KERNEL 5
+#define RT_KERNEL_BOX 0               /* Kernel, src/screen.h:28-31 */
+#define RT_KERNEL_GAUSSIAN 1
+typedef struct {
+    int filtering_option;   /* RT_FILTER_* (default NONE)                                                     */
+    int kernel;             /* RT_KERNEL_* (default BOX)                                                      */
+    int kernel_repetitions; /* setKernelNumRepetitions: values < 1 mean 1                                     */
+    int filter_size;        /* setFilterSize (default 5): taps run over [-size, size]^2; at most 64           */
+    float sigma;            /* setSigma (default 2): values < 0.001 mean 0.001                                */
+    float exposure;         /* setExposure (default 0.5)                                                      */
+    int gamma_correction;   /* enableGammaCorrection (default off)                                            */
+    float gamma;            /* setGammaValue (default 2.2)                                                    */
+    int bloom_live;         /* setBloomFilterLive (default off): postprocessImage blooms only when set        */
+} rt_post_params;
+
+/* Post-processing applied by every following rt_render / rt_render_device at the end of the frame, on the device,
+ * before the rows travel to the host (what renderRayTracing does with the Screen it renders into).  NULL switches it
+ * off.  Frames sharded over several GPUs (rt_set_shard) are not post-processed: the bloom needs the gathered image, so
+ * rank 0 calls rt_postprocess_device on its framebuffer after the ranks have met. */
+int rt_set_postprocess(rt_ctx* ctx, const rt_post_params* post);
+/* Screen::postprocessImage (via_write_bitmap = 0) or writeBitmapToFile's bloom + conversion (via_write_bitmap = 1) on
+ * an image in host memory: rgb = W*H*3 floats in the Screen layout, processed in place; rgba8 (may be NULL) receives
+ * the W*H*4 bytes the reference hands to its BMP encoder. */
+int rt_postprocess(rt_ctx* ctx, const rt_post_params* post, float* rgb, int width, int height, int via_write_bitmap, unsigned char* rgba8);
+/* The same on a device-resident float4 image (NULL = the context's own framebuffer), asynchronous on the context's
+ * stream; bloom_live and gamma_correction are honoured as in postprocessImage. */
+int rt_postprocess_device(rt_ctx* ctx, const rt_post_params* post, void* d_rgba, int width, int height);
+
 /* Scene::spotLight / Scene::planeLight (src/scene.h:93-94; getSpotLichts / getPlaneLights, src/shadow.cpp:229-321). */
 int rt_set_spot_lights(rt_ctx* ctx, const rt_spot_light* spot, int n_spot);
 int rt_set_plane_lights(rt_ctx* ctx, const rt_plane_light* plane, int n_plane);
@@ -128,7 +164,8 @@ int rt_set_counters(rt_ctx* ctx, int enable);
 #define RT_STAGE_SHADOW_SPHERE 4
 #define RT_STAGE_RESOLVE 5
 #define RT_STAGE_SHADOW_PLANE 6
-#define RT_STAGE_COUNT 7
+#define RT_STAGE_POST 7
+#define RT_STAGE_COUNT 8
 int rt_set_stage_timing(rt_ctx* ctx, int enable);
 int rt_stage_times(rt_ctx* ctx, float* ms /* [RT_STAGE_COUNT] */, int* launches /* [RT_STAGE_COUNT] */);
 /* Shadow kernels of bounce level L run on a side stream concurrently with extend / shade of level L+1 (default on). */

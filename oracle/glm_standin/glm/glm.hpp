@@ -27,6 +27,7 @@ using std::pow;   // glm's func_exponential.inl does `using std::pow;` for scala
 using std::sqrt;  // likewise `using std::sqrt;`
 using std::sin;
 using std::cos;
+using std::exp;   // func_exponential.inl: `using std::exp;` for scalars (src/screen.cpp:325,363)
 
 typedef int length_t;
 
@@ -70,12 +71,14 @@ template <typename T> struct tvec4 {
     constexpr explicit tvec4(T v) : x(v), y(v), z(v), w(v) {}
     constexpr tvec4(T a, T b, T c, T d) : x(a), y(b), z(c), w(d) {}
     constexpr tvec4(const tvec3<T>& v, T d) : x(v.x), y(v.y), z(v.z), w(d) {}
+    template <typename U> constexpr explicit tvec4(const tvec4<U>& o) : x(static_cast<T>(o.x)), y(static_cast<T>(o.y)), z(static_cast<T>(o.z)), w(static_cast<T>(o.w)) {}
 };
 template <typename T> constexpr tvec3<T>::tvec3(const tvec4<T>& o) : x(o.x), y(o.y), z(o.z) {}
 
 typedef tvec2<float> vec2;
 typedef tvec3<float> vec3;
 typedef tvec4<float> vec4;
+typedef tvec4<unsigned char> u8vec4; // src/screen.cpp:44-49: glm::u8vec4(glm::vec4 * 255.0f) converts per component with static_cast
 typedef tvec2<int> ivec2;
 typedef tvec3<unsigned int> uvec3;
 typedef tvec3<bool> bvec3;
@@ -98,14 +101,20 @@ inline vec3 operator-(const vec3& a) { return vec3(-a.x, -a.y, -a.z); }
 inline bool operator==(const vec3& a, const vec3& b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
 inline bool operator!=(const vec3& a, const vec3& b) { return !(a == b); }
 
+inline vec4 operator*(const vec4& a, float s) { return vec4(a.x * s, a.y * s, a.z * s, a.w * s); }
+
 // ---- common ----
 inline float abs(float v) { return std::fabs(v); }
 inline float min(float a, float b) { return (b < a) ? b : a; }
 inline float max(float a, float b) { return (a < b) ? b : a; }
+inline int min(int a, int b) { return (b < a) ? b : a; }
+inline int max(int a, int b) { return (a < b) ? b : a; }
 inline vec3 min(const vec3& a, const vec3& b) { return vec3(min(a.x, b.x), min(a.y, b.y), min(a.z, b.z)); }
 inline vec3 max(const vec3& a, const vec3& b) { return vec3(max(a.x, b.x), max(a.y, b.y), max(a.z, b.z)); }
 inline float clamp(float v, float lo, float hi) { return min(max(v, lo), hi); }
 inline vec3 clamp(const vec3& v, float lo, float hi) { return vec3(clamp(v.x, lo, hi), clamp(v.y, lo, hi), clamp(v.z, lo, hi)); }
+inline vec3 clamp(const vec3& v, const vec3& lo, const vec3& hi) { return min(max(v, lo), hi); }
+inline vec3 exp(const vec3& v) { return vec3(std::exp(v.x), std::exp(v.y), std::exp(v.z)); }
 inline float radians(float deg) { return deg * 0.01745329251994329576923690768489f; }
 inline vec3 radians(const vec3& d) { return vec3(radians(d.x), radians(d.y), radians(d.z)); }
 inline vec3 pow(const vec3& b, const vec3& e) { return vec3(std::pow(b.x, e.x), std::pow(b.y, e.y), std::pow(b.z, e.z)); }

@@ -40,6 +40,15 @@ class OrcStats(C.Structure):
         return int(self.primary_rays + self.shadow_queries + self.secondary_rays)
 
 
+class OrcPost(C.Structure):
+    _fields_ = [("filtering_option", C.c_int), ("kernel", C.c_int), ("kernel_repetitions", C.c_int), ("filter_size", C.c_int),
+                ("sigma", C.c_float), ("exposure", C.c_float), ("gamma_correction", C.c_int), ("gamma", C.c_float), ("bloom_live", C.c_int)]
+
+
+# FilteringOption / Kernel of src/screen.h:17-31
+FILTER_NONE, FILTER_BLOOM, FILTER_BLOOM_REINHARD, FILTER_BLOOM_EXPOSURE, FILTER_ONLY_LIGHT, FILTER_ONLY_LIGHT_KERNEL = range(6)
+KERNEL_BOX, KERNEL_GAUSSIAN = 0, 1
+
 MATERIAL_DTYPE = np.dtype([("kd", np.float32, 3), ("ks", np.float32, 3), ("shininess", np.float32), ("transparency", np.float32)])
 
 
@@ -105,6 +114,22 @@ class Oracle:
         pl = np.ascontiguousarray(plane if plane is not None else np.zeros((0, 12)), np.float32).reshape(-1, 12)
         self.lib.oracle_set_extra_lights(C.c_void_p(sp.ctypes.data if len(sp) else None), C.c_int(len(sp)),
                                          C.c_void_p(pl.ctypes.data if len(pl) else None), C.c_int(len(pl)), C.c_int(int(plane_ray_count_1d)))
+
+    def postprocess(self, rgb, filtering_option=FILTER_NONE, kernel=KERNEL_BOX, kernel_repetitions=1, filter_size=5, sigma=2.0, exposure=0.5,
+                    gamma_correction=False, gamma=2.2, bloom_live=True, via_write_bitmap=False):
+        """Screen::postprocessImage (or the bloom + 8-bit conversion of writeBitmapToFile) on an (H, W, 3) float image in the
+        Screen layout.  Returns the processed image, plus the RGBA8 rows when via_write_bitmap."""
+        img = np.array(rgb, np.float32, order="C", copy=True)
+        h, w = img.shape[:2]
+        p = OrcPost(int(filtering_option), int(kernel), int(kernel_repetitions), int(filter_size), float(sigma), float(exposure),
+                    1 if gamma_correction else 0, float(gamma), 1 if bloom_live else 0)
+        rgba = np.zeros((h, w, 4), np.uint8)
+        self.lib.oracle_postprocess.restype = C.c_int
+        rc = self.lib.oracle_postprocess(C.c_void_p(img.ctypes.data), C.c_int(w), C.c_int(h), C.byref(p), C.c_int(1 if via_write_bitmap else 0),
+                                         C.c_void_p(rgba.ctypes.data))
+        if rc != 0:
+            raise RuntimeError(f"oracle_postprocess failed with {rc}")
+        return (img, rgba) if via_write_bitmap else img
 
     def closest_hit(self, pos, nrm, mesh_id, rays, use_bvh=False):
         """use_bvh: False/0 every object in id order, True/1 the reference-style BVH, 2 (port) every object in that BVH's visiting order."""

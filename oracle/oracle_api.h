@@ -90,6 +90,25 @@ void oracle_set_spheres(const float* spheres, int n);
  * each = position (3), width (3), height (3), colour (3).  plane_ray_count_1d = plane_light_1D_ray_count (src/main.cpp:125). */
 void oracle_set_extra_lights(const float* spot, int n_spot, const float* plane, int n_plane, int plane_ray_count_1d);
 
+/* Screen post-processing, the step renderRayTracing ends with (src/main.cpp:397-398; src/screen.cpp:56-69, 226-395). */
+typedef struct {
+    int filtering_option;   /* FilteringOption (src/screen.h:17-26): 0 None, 1 Bloom, 2 BloomWithReinhardHdr, 3 BloomWithExposureHdr,
+                               4 OnlyLight, 5 OnlyLightWithKernel                                                                 */
+    int kernel;             /* Kernel (src/screen.h:28-31): 0 box, 1 Gaussian                                                    */
+    int kernel_repetitions; /* setKernelNumRepetitions (max(1, n))                                                               */
+    int filter_size;        /* setFilterSize: taps run over [-size, size]^2                                                      */
+    float sigma;            /* setSigma (max(0.001, s))                                                                          */
+    float exposure;         /* setExposure                                                                                       */
+    int gamma_correction;   /* enableGammaCorrection                                                                             */
+    float gamma;            /* setGammaValue                                                                                     */
+    int bloom_live;         /* setBloomFilterLive: postprocessImage applies the bloom only when set                              */
+} orc_post;
+
+/* rgb: W*H*3 floats in the Screen layout, processed in place.  via_write_bitmap = 0: Screen::postprocessImage();
+ * 1: what Screen::writeBitmapToFile does before writing (bloom whatever bloom_live says, no gamma) and, if rgba8 != NULL,
+ * the W*H*4 bytes it hands to the BMP encoder (clamp to [0,1], * 255, truncate; alpha 255). */
+int oracle_postprocess(float* rgb, int w, int h, const orc_post* p, int via_write_bitmap, unsigned char* rgba8);
+
 const char* oracle_kind(void); /* "reference" or "port" */
 
 #ifdef __cplusplus

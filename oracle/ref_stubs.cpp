@@ -11,3 +11,13 @@ thread_local unsigned long long orc_drawray_calls = 0;
 
 void drawRay(const Ray&, const glm::vec3&) { orc_drawray_calls++; }
 void drawAABB(const AxisAlignedBox&, DrawMode, const glm::vec3&, float) {}
+
+// Screen::writeBitmapToFile's sink (see gl_standin/stb_image_write.h): keep the rows instead of writing a file.
+#include <vector>
+extern thread_local std::vector<unsigned char> orc_bmp_rows;
+extern "C" int stbi_write_bmp(char const*, int w, int h, int comp, const void* data)
+{
+    const unsigned char* b = static_cast<const unsigned char*>(data);
+    orc_bmp_rows.assign(b, b + (size_t)w * h * comp);
+    return 1;
+}

@@ -114,6 +114,13 @@ struct rt_ctx {
     cudaStream_t copy = nullptr; // band downloads: must not hold up the next batch on the lane that produced the band
     bool overlap = true;
     DevBuf<float4> accum, fb;
+    DevBuf<float4> post_img, post_a, post_b; // post-processing: host image staging, light image ping-pong
+    DevBuf<float> post_weights;
+    int post_weights_f = -1;
+    float post_weights_sigma = 0.0f;
+    DevBuf<unsigned char> post_rgba8;
+    bool post_on = false;
+    rt_post_params post {};
     DevBuf<int> prim_id, out_id;
     DevBuf<float> prim_t, out_t, rgb;
     DevBuf<float> rays_in;
@@ -372,6 +379,106 @@ struct StageScope { // brackets one launch with events when stage timing is on
     }
 };
 
+
+// Screen's setters clamp two of the settings (src/screen.cpp:191-194, 213-216); setFilterSize does not (219-223).
+rt_post_params normalised_post(const rt_post_params& in)
+{
+    rt_post_params p = in;
+    p.kernel_repetitions = std::max(1, p.kernel_repetitions);
+    p.sigma = std::max(0.001f, p.sigma);
+    return p;
+}
+
+bool post_has_effect(const rt_post_params& p) { return (p.bloom_live && p.filtering_option != RT_FILTER_NONE) || p.gamma_correction; }
+
+int check_post(const rt_post_params* p)
+{
+    if (!p)
+        return fail(RT_ERR_INVALID, "post-processing: null settings");
+    if (p->filtering_option < RT_FILTER_NONE || p->filtering_option > RT_FILTER_ONLY_LIGHT_KERNEL || (p->kernel != RT_KERNEL_BOX && p->kernel != RT_KERNEL_GAUSSIAN))
+        return fail(RT_ERR_INVALID, "post-processing: unknown filtering option or kernel");
+    if (p->filter_size > 64)
+        return fail(RT_ERR_INVALID, "post-processing: filter_size above 64");
+    return RT_OK;
+}
+
+// Weight table of the Gaussian kernel for the settings in use; uploaded outside frames (blocks on the context's stream).
+// gaussianFunction (src/screen.cpp:324-326): (1 / (sigma * sigma * 2 * M_PI)) * glm::exp(-(x*x + y*y) / (2 * sigma * sigma)) with the
+// reference's own `#define M_PI 3.1415926535893238` (src/screen.cpp:13): double prefactor, float exp (this host's libm, the
+// one the CPU reference would call), rounded to float on return.
+int ensure_post_weights(rt_ctx* ctx, const rt_post_params& p)
+{
+    const int f = p.filter_size;
+    if (p.kernel != RT_KERNEL_GAUSSIAN || f < 0 || p.filtering_option == RT_FILTER_NONE || p.filtering_option == RT_FILTER_ONLY_LIGHT)
+        return RT_OK;
+    if (ctx->post_weights_f == f && ctx->post_weights_sigma == p.sigma && ctx->post_weights.p)
+        return RT_OK;
+    const int side = 2 * f + 1;
+    std::vector<float> wts((size_t)side * side);
+    const float sigma = p.sigma;
+    for (int i = -f; i <= f; i++)
+        for (int j = -f; j <= f; j++) {
+            const float x = (float)i, y = (float)j;
+            wts[(size_t)(i + f) * side + (j + f)] = (float)((1 / (sigma * sigma * 2 * 3.1415926535893238)) * std::exp(-(x * x + y * y) / (2 * sigma * sigma)));
+        }
+    CK(cudaStreamSynchronize(ctx->stream)); // an earlier frame may still read the old table
+    CK(ctx->post_weights.ensure(wts.size()));
+    CK(cudaMemcpyAsync(ctx->post_weights.p, wts.data(), wts.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->post_weights_f = f;
+    ctx->post_weights_sigma = p.sigma;
+    return RT_OK;
+}
+
+// Screen::applyBloomEffect (src/screen.cpp:226-268) on a device image, in place.
+int enqueue_bloom(rt_ctx* ctx, cudaStream_t st, float4* img, int w, int h, const rt_post_params& p, int& launches)
+{
+    if (p.filtering_option == RT_FILTER_NONE)
+        return RT_OK;
+    const size_t n = (size_t)w * h;
+    CK(ctx->post_a.ensure(n));
+    CK(ctx->post_b.ensure(n));
+    const int f = p.filter_size;
+    const bool gauss = p.kernel == RT_KERNEL_GAUSSIAN;
+    float4 *light = ctx->post_a.p, *other = ctx->post_b.p;
+    launch_post_light(st, ctx->sm_count, img, light, n);
+    launches++;
+    if (p.filtering_option == RT_FILTER_ONLY_LIGHT) {
+        CK(cudaMemcpyAsync(img, light, n * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+        return RT_OK;
+    }
+    const int reps = p.filtering_option == RT_FILTER_ONLY_LIGHT_KERNEL ? 1 : p.kernel_repetitions;
+    for (int r = 0; r < reps; r++) {
+        launch_post_blur(st, light, other, w, h, f, gauss, ctx->post_weights.p);
+        launches++;
+        std::swap(light, other);
+    }
+    if (p.filtering_option == RT_FILTER_ONLY_LIGHT_KERNEL) {
+        CK(cudaMemcpyAsync(img, light, n * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+        return RT_OK;
+    }
+    launch_post_combine(st, ctx->sm_count, img, light, n, p.filtering_option, p.exposure);
+    launches++;
+    return RT_OK;
+}
+
+// Screen::postprocessImage (src/screen.cpp:56-69) on a device image, in place.
+int enqueue_postprocess(rt_ctx* ctx, cudaStream_t st, float4* img, int w, int h, const rt_post_params& p, int& launches)
+{
+    StageScope sc(ctx, RT_STAGE_POST, st);
+    if (p.bloom_live) {
+        int rc = enqueue_bloom(ctx, st, img, w, h, p, launches);
+        if (rc)
+            return rc;
+    }
+    if (p.gamma_correction) {
+        launch_post_gamma(st, ctx->sm_count, img, (size_t)w * h, 1.0f / p.gamma);
+        launches++;
+    }
+    CK(cudaGetLastError());
+    return RT_OK;
+}
+
 // Where rt_render wants the finished rows: packed float3 image on the host (pinned for full PCIe speed).
 struct HostTarget {
     float* rgb = nullptr;
@@ -393,7 +500,7 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids
     int lanes_wanted = ctx->n_lanes, batches_auto = ctx->batches_per_frame;
     if (lanes_wanted <= 0) {
         const bool big = n_local >= ((size_t)1 << 22);
-        if (host && host->rgb && fp.world == 1) {
+        if (host && host->rgb && fp.world == 1 && !(ctx->post_on && post_has_effect(ctx->post))) {
             lanes_wanted = big ? 2 : 1;
             batches_auto = big ? 3 : 1;
         } else {
@@ -437,7 +544,9 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids
     if (n_local)
         CK(cudaMemsetAsync(ctx->accum.p, 0, n_local * sizeof(float4), st0));
     CK(cudaEventRecord(ctx->ev_start, st0));
-    const bool band_download = host && host->rgb && fp.world == 1 && batch_pixels % ((size_t)fp.tiles_x * kTilePixels) == 0;
+    // post-processing (bloom) needs the whole image: it runs after the last batch, so rows cannot leave band by band
+    const bool post = ctx->post_on && fp.world == 1 && post_has_effect(ctx->post) && n_local;
+    const bool band_download = host && host->rgb && fp.world == 1 && !post && batch_pixels % ((size_t)fp.tiles_x * kTilePixels) == 0;
 
     for (size_t first = 0; first < n_local; first += batch_pixels, batches++) {
         const int li = batches % n_lanes;
@@ -534,6 +643,11 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids
     if (band_download) {
         CK(cudaEventRecord(ctx->ev_copied, ctx->copy));
         CK(cudaStreamWaitEvent(st0, ctx->ev_copied, 0));
+    }
+    if (post) {
+        int rc = enqueue_postprocess(ctx, st0, out, fp.W, fp.H, ctx->post, launches);
+        if (rc)
+            return rc;
     }
     if (host && host->rgb && !band_download && n_local) {
         const size_t npx = (size_t)fp.W * fp.H;
@@ -638,7 +752,9 @@ int rt_destroy(rt_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     DevBuf<float4>* f4[] = { &ctx->d_plane, &ctx->d_v0, &ctx->d_v1, &ctx->d_v2, &ctx->d_n0, &ctx->d_n1, &ctx->d_n2, &ctx->d_nodes, &ctx->d_mats,
-        &ctx->d_point, &ctx->d_sphere, &ctx->accum, &ctx->fb };
+        &ctx->d_point, &ctx->d_sphere, &ctx->accum, &ctx->fb, &ctx->post_img, &ctx->post_a, &ctx->post_b };
+    ctx->post_weights.release();
+    ctx->post_rgba8.release();
     for (auto* b : f4)
         b->release();
     for (int l = 0; l < kMaxLanes; l++) {
@@ -1247,6 +1363,96 @@ int rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, float* rg
         }
         return rc;
     }
+}
+
+int rt_set_postprocess(rt_ctx* ctx, const rt_post_params* post)
+{
+    if (!ctx)
+        return fail(RT_ERR_INVALID, "null context");
+    if (!post) {
+        ctx->post_on = false;
+        return RT_OK;
+    }
+    int rc = check_post(post);
+    if (rc)
+        return rc;
+    rc = use_device(ctx);
+    if (rc)
+        return rc;
+    ctx->post = normalised_post(*post);
+    ctx->post_on = true;
+    return ensure_post_weights(ctx, ctx->post);
+}
+
+int rt_postprocess_device(rt_ctx* ctx, const rt_post_params* post, void* d_rgba, int width, int height)
+{
+    int rc = use_device(ctx);
+    if (rc)
+        return rc;
+    rc = check_post(post);
+    if (rc)
+        return rc;
+    float4* img = (float4*)d_rgba;
+    if (!img) {
+        if (!ctx->fb.p || ctx->fb_w != width || ctx->fb_h != height)
+            return fail(RT_ERR_INVALID, "rt_postprocess_device: the context holds no framebuffer of that size");
+        img = ctx->fb.p;
+    }
+    if (width <= 0 || height <= 0)
+        return fail(RT_ERR_INVALID, "rt_postprocess_device: empty image");
+    int launches = 0;
+    const rt_post_params p = normalised_post(*post);
+    rc = ensure_post_weights(ctx, p);
+    if (rc)
+        return rc;
+    const bool timing = ctx->stage_timing;
+    ctx->stage_timing = false; // stage events belong to frames (rt_sync reads them back)
+    rc = enqueue_postprocess(ctx, ctx->stream, img, width, height, p, launches);
+    ctx->stage_timing = timing;
+    return rc;
+}
+
+int rt_postprocess(rt_ctx* ctx, const rt_post_params* post, float* rgb, int width, int height, int via_write_bitmap, unsigned char* rgba8)
+{
+    int rc = use_device(ctx);
+    if (rc)
+        return rc;
+    rc = check_post(post);
+    if (rc)
+        return rc;
+    if (!rgb || width <= 0 || height <= 0)
+        return fail(RT_ERR_INVALID, "rt_postprocess: need an image");
+    const size_t n = (size_t)width * height;
+    CK(ctx->rgb.ensure(n * 3 + 4));
+    CK(ctx->post_img.ensure(n));
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->rgb.p, rgb, n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    launch_unpack_rgb(st, ctx->sm_count, ctx->rgb.p, ctx->post_img.p, n);
+    const rt_post_params p = normalised_post(*post);
+    rc = ensure_post_weights(ctx, p);
+    if (rc)
+        return rc;
+    int launches = 0;
+    const bool timing = ctx->stage_timing;
+    ctx->stage_timing = false;
+    if (via_write_bitmap) { // writeBitmapToFile (src/screen.cpp:40-53): bloom whatever bloom_live says, no gamma
+        rc = enqueue_bloom(ctx, st, ctx->post_img.p, width, height, p, launches);
+        if (rc == RT_OK && rgba8) {
+            CK(ctx->post_rgba8.ensure(n * 4));
+            launch_post_rgba8(st, ctx->sm_count, ctx->post_img.p, ctx->post_rgba8.p, n);
+            CK(cudaMemcpyAsync(rgba8, ctx->post_rgba8.p, n * 4, cudaMemcpyDeviceToHost, st));
+        }
+    } else {
+        rc = enqueue_postprocess(ctx, st, ctx->post_img.p, width, height, p, launches);
+    }
+    ctx->stage_timing = timing;
+    if (rc)
+        return rc;
+    launch_pack_rgb(st, ctx->sm_count, ctx->post_img.p, ctx->rgb.p, 0, n);
+    CK(cudaMemcpyAsync(rgb, ctx->rgb.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    return RT_OK;
 }
 
 int rt_intersect(rt_ctx* ctx, const float* rays, int64_t n_rays, int use_bvh, int* tri_id, float* t)

@@ -43,6 +43,14 @@ struct DeviceBvh {
 };
 int build_bvh_lbvh_device(cudaStream_t st, const float* d_pos, long long n_tris, float pad, DeviceBvh* out, const char** err);
 
+// Screen post-processing (rt_post.cu): float4 images in the Screen layout.  option / gauss follow rt_b200.h's RT_FILTER_* / RT_KERNEL_*.
+void launch_post_light(cudaStream_t st, int sm_count, const float4* img, float4* light, size_t n);
+void launch_post_blur(cudaStream_t st, const float4* src, float4* dst, int w, int h, int f, bool gauss, const float* weights);
+void launch_post_combine(cudaStream_t st, int sm_count, float4* img, const float4* light, size_t n, int option, float exposure);
+void launch_post_gamma(cudaStream_t st, int sm_count, float4* img, size_t n, float e);
+void launch_post_rgba8(cudaStream_t st, int sm_count, const float4* img, unsigned char* out, size_t n);
+void launch_unpack_rgb(cudaStream_t st, int sm_count, const float* in, float4* out, size_t n);
+
 // Visiting rank of every object (triangles 0..n_tris-1, then spheres) in the reference's own BVH (rt_reforder.cu): the tie key
 // of the traversal kernels.  d_spheres: 3 x float4 per sphere ({centre, radius} first).  d_rank: n_tris + n_spheres ints.
 int reference_visit_rank(cudaStream_t st, const float* d_pos, long long n_tris, const float4* d_spheres, int n_spheres, int* d_rank, const char** err);

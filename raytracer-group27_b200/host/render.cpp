@@ -74,8 +74,9 @@ void renderRayTracing(Scene& scene, const Trackball& camera, const BoundingVolum
     prm.plane_light_ray_count_1d = plane_light_1D_ray_count;
     rt_stats st {};
     static_assert(sizeof(glm::vec3) == 3 * sizeof(float), "Screen pixels must be packed float3");
+    // screen.postprocessImage() (src/main.cpp:397-398) runs on the device at the end of the frame, before the rows come home
+    check(rt_set_postprocess(ctx, &screen.postSettings()), "rt_set_postprocess");
     check(rt_render(ctx, &cam, &prm, &screen.pixels()[0].x, nullptr, nullptr, &st), "rt_render");
     lastRenderTimings.gpu_ms = st.gpu_ms;
     lastRenderTimings.rays = st.primary_rays + st.shadow_queries + st.secondary_rays;
-    screen.postprocessImage();
 }

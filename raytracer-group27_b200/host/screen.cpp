@@ -3,6 +3,7 @@
 #include <cstdint>
 #include <fstream>
 #include <stdexcept>
+#include <string>
 
 Screen::Screen(const glm::ivec2& resolution)
     : m_resolution(resolution), m_textureData(size_t(resolution.x) * size_t(resolution.y), glm::vec3(0.0f))
@@ -18,15 +19,39 @@ void Screen::setPixel(int x, int y, const glm::vec3& color)
 }
 
 namespace {
+// Screen has no link to a BoundingVolumeHierarchy, so its own post-processing calls share one lazily created context.
+rt_ctx* postContext()
+{
+    static rt_ctx* ctx = nullptr;
+    if (!ctx && rt_create(0, &ctx) != RT_OK)
+        throw std::runtime_error(std::string("Screen: ") + rt_last_error());
+    return ctx;
+}
+}
+
+void Screen::postprocessImage()
+{
+    if (!((m_post.bloom_live && m_post.filtering_option != RT_FILTER_NONE) || m_post.gamma_correction) || m_textureData.empty())
+        return;
+    static_assert(sizeof(glm::vec3) == 3 * sizeof(float), "Screen pixels must be packed float3");
+    if (rt_postprocess(postContext(), &m_post, &m_textureData[0].x, m_resolution.x, m_resolution.y, 0, nullptr) != RT_OK)
+        throw std::runtime_error(std::string("Screen::postprocessImage: ") + rt_last_error());
+}
+
+namespace {
 void put32(std::ofstream& f, uint32_t v) { f.write(reinterpret_cast<const char*>(&v), 4); }
 void put16(std::ofstream& f, uint16_t v) { f.write(reinterpret_cast<const char*>(&v), 2); }
 }
 
-// The reference hands RGBA8 rows (top row first) to stbi_write_bmp with comp=4 (src/screen.cpp:44-52).  stb is
-// not vendored; this writes an equivalent uncompressed 32-bit BMP (BGRA, bottom-up rows).
+// The reference applies the bloom to its pixels (whether or not it is live, src/screen.cpp:42), then hands RGBA8 rows (top
+// row first) to stbi_write_bmp with comp=4 (src/screen.cpp:44-52).  stb is not vendored; this writes an equivalent
+// uncompressed 32-bit BMP (BGRA, bottom-up rows).
 void Screen::writeBitmapToFile(const std::filesystem::path& filePath)
 {
     const int w = m_resolution.x, h = m_resolution.y;
+    if (m_post.filtering_option != RT_FILTER_NONE && !m_textureData.empty()
+        && rt_postprocess(postContext(), &m_post, &m_textureData[0].x, w, h, 1, nullptr) != RT_OK)
+        throw std::runtime_error(std::string("Screen::writeBitmapToFile: ") + rt_last_error());
     std::ofstream f(filePath, std::ios::binary);
     if (!f)
         throw std::runtime_error("Screen::writeBitmapToFile: cannot open " + filePath.string());

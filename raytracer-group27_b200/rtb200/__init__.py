@@ -62,6 +62,23 @@ _lib = None
 
 # every symbol include/rt_b200.h declares: (name, restype, argtypes)
 _P, _I, _F = C.c_void_p, C.c_int, C.POINTER(C.c_float)
+class PostParams(C.Structure):
+    """rt_post_params: Screen's bloom / tone-mapping / gamma settings (include/rt_b200.h)."""
+    _fields_ = [("filtering_option", C.c_int), ("kernel", C.c_int), ("kernel_repetitions", C.c_int), ("filter_size", C.c_int),
+                ("sigma", C.c_float), ("exposure", C.c_float), ("gamma_correction", C.c_int), ("gamma", C.c_float), ("bloom_live", C.c_int)]
+
+
+FILTER_NONE, FILTER_BLOOM, FILTER_BLOOM_REINHARD, FILTER_BLOOM_EXPOSURE, FILTER_ONLY_LIGHT, FILTER_ONLY_LIGHT_KERNEL = range(6)
+KERNEL_BOX, KERNEL_GAUSSIAN = 0, 1
+
+
+def make_post(filtering_option=FILTER_NONE, kernel=KERNEL_BOX, kernel_repetitions=1, filter_size=5, sigma=2.0, exposure=0.5,
+              gamma_correction=False, gamma=2.2, bloom_live=True) -> PostParams:
+    """Defaults are Screen's (src/screen.h:84-101), except bloom_live, which postprocessImage needs to bloom at all."""
+    return PostParams(int(filtering_option), int(kernel), int(kernel_repetitions), int(filter_size), float(sigma), float(exposure),
+                      1 if gamma_correction else 0, float(gamma), 1 if bloom_live else 0)
+
+
 SYMBOLS = [
     ("rt_create", _I, [_I, C.POINTER(_P)]),
     ("rt_destroy", _I, [_P]),
@@ -73,6 +90,9 @@ SYMBOLS = [
     ("rt_set_spheres", _I, [_P, _P, _I]),
     ("rt_set_spot_lights", _I, [_P, _P, _I]),
     ("rt_set_plane_lights", _I, [_P, _P, _I]),
+    ("rt_set_postprocess", _I, [_P, C.POINTER(PostParams)]),
+    ("rt_postprocess", _I, [_P, C.POINTER(PostParams), _P, _I, _I, _I, _P]),
+    ("rt_postprocess_device", _I, [_P, C.POINTER(PostParams), _P, _I, _I]),
     ("rt_bvh_info", _I, [_P, C.POINTER(_I), C.POINTER(_I)]),
     ("rt_set_counters", _I, [_P, _I]),
     ("rt_set_batch_rays", _I, [_P, C.c_uint]),
@@ -260,18 +280,33 @@ class Context:
         pl = _f32(plane if plane is not None else np.zeros((0, 12))).reshape(-1, 12)
         _check(self._l.rt_set_plane_lights(self._h, pl.ctypes.data if len(pl) else None, len(pl)))
 
+    def set_postprocess(self, post: "PostParams | None"):
+        """Post-processing applied on the device at the end of every following frame (None: off)."""
+        _check(self._l.rt_set_postprocess(self._h, C.byref(post) if post is not None else None))
+
+    def postprocess(self, rgb, post: "PostParams", via_write_bitmap=False):
+        """Screen::postprocessImage (or writeBitmapToFile's bloom + 8-bit conversion) on a host image (H, W, 3)."""
+        img = np.array(rgb, np.float32, order="C", copy=True)
+        h, w = img.shape[:2]
+        rgba = np.zeros((h, w, 4), np.uint8)
+        _check(self._l.rt_postprocess(self._h, C.byref(post), img.ctypes.data, w, h, 1 if via_write_bitmap else 0, rgba.ctypes.data if via_write_bitmap else None))
+        return (img, rgba) if via_write_bitmap else img
+
+    def postprocess_device(self, post: "PostParams", width: int, height: int, d_rgba=None):
+        _check(self._l.rt_postprocess_device(self._h, C.byref(post), d_rgba, int(width), int(height)))
+
     def set_counters(self, enable: bool):
         _check(self._l.rt_set_counters(self._h, 1 if enable else 0))
 
-    STAGES = ("generate", "extend", "shade", "shadow_point", "shadow_sphere", "resolve", "shadow_plane")
+    STAGES = ("generate", "extend", "shade", "shadow_point", "shadow_sphere", "resolve", "shadow_plane", "post")
 
     def set_stage_timing(self, enable: bool):
         _check(self._l.rt_set_stage_timing(self._h, 1 if enable else 0))
 
     def stage_times(self) -> dict:
         """{stage: (ms, launches)} of the frame completed by the last sync()/render()."""
-        ms = (C.c_float * 7)()
-        n = (C.c_int * 7)()
+        ms = (C.c_float * len(self.STAGES))()
+        n = (C.c_int * len(self.STAGES))()
         _check(self._l.rt_stage_times(self._h, ms, n))
         return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(self.STAGES)}
 

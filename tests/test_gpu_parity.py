@@ -330,6 +330,17 @@ int main(int argc, char** argv) {
     HitInfo hi;
     const bool hit = bvh.intersect(r, hi, true);
     std::printf("%d %d %.9g %llu\n", hit ? 1 : 0, hi.triangle_index, r.t, lastRenderTimings.rays);
+    // second frame: a light bright enough to bloom, Screen configured through the reference's setters (main.cpp:560-640)
+    scene.pointLights[0].color = glm::vec3(6.0f);
+    screen.setBloomFilter(FilteringOption::BloomWithReinhardHdr);
+    screen.setKernel(Kernel::GaussianKernel);
+    screen.setFilterSize(3);
+    screen.setSigma(1.5f);
+    screen.setBloomFilterLive(true);
+    renderRayTracing(scene, camera, bvh, screen);    // ends with the post-processing (main.cpp:397-398)
+    std::ofstream f2(argv[3], std::ios::binary);
+    f2.write(reinterpret_cast<const char*>(screen.pixels().data()), sizeof(glm::vec3) * screen.pixels().size());
+    screen.writeBitmapToFile(argv[4]);                // blooms the pixels once more, then writes 8-bit BGRA (screen.cpp:40-53)
     return 0;
 }
 """
@@ -358,7 +369,7 @@ def test_cpp_drop_in_renders_the_same_frame(rtb, gpu_ctx, tmp_path):
     r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", f"-I{host}", f"-I{os.path.join(root, 'include')}", str(tmp_path / "r.cpp"), "-o", str(exe),
                         f"-L{lib}", "-lrtb200", f"-Wl,-rpath,{lib}"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    r = subprocess.run([str(exe), str(tmp_path), str(tmp_path / "frame.bin")], capture_output=True, text=True)
+    r = subprocess.run([str(exe), str(tmp_path), str(tmp_path / "frame.bin"), str(tmp_path / "frame2.bin"), str(tmp_path / "render.bmp")], capture_output=True, text=True)
     assert r.returncode == 0, (r.stdout, r.stderr)
     cpp = np.fromfile(tmp_path / "frame.bin", np.float32).reshape(256, 256, 3)
     sc = rtb.load_obj(str(tmp_path / "custom.obj"))
@@ -372,3 +383,19 @@ def test_cpp_drop_in_renders_the_same_frame(rtb, gpu_ctx, tmp_path):
     assert int(tri) == ids[127, 128] and int(hit) == int(ids[127, 128] >= 0)
     assert np.float32(tt) == t[127, 128]
     assert int(rays) == st.rays
+    # second frame: post-processed on the device inside renderRayTracing; the BMP is the doubly bloomed frame, clamped and truncated
+    import oracle
+    port = oracle.Oracle("port")
+    sc.point_lights = np.array([[-1, 1, -1, 6, 6, 6]], np.float32)
+    gpu_ctx.upload_scene(sc, rtb.BVH_LBVH_DEVICE)
+    bright, _, _, _ = gpu_ctx.render(rtb.make_camera(), rtb.make_params(256, 256, 3), want_ids=True)
+    cfg = dict(filtering_option=2, kernel=1, filter_size=3, sigma=1.5)
+    want = port.postprocess(bright, **cfg)
+    cpp2 = np.fromfile(tmp_path / "frame2.bin", np.float32).reshape(256, 256, 3)
+    assert np.abs(want - bright).max() > 0.05          # the bloom did something
+    assert np.abs(cpp2 - want).max() <= 1e-6
+    _, rgba = port.postprocess(cpp2, via_write_bitmap=True, **cfg)
+    bmp = np.fromfile(tmp_path / "render.bmp", np.uint8)
+    assert bmp[:2].tobytes() == b"BM" and len(bmp) == 54 + 256 * 256 * 4
+    px = bmp[54:].reshape(256, 256, 4)[::-1]           # bottom-up rows, BGRA
+    assert np.array_equal(px[..., [2, 1, 0, 3]], rgba)

@@ -100,3 +100,32 @@ def test_closest_hit_api_and_unnormalised_directions():
     ids3, t3 = P.closest_hit(g.scene.pos, g.scene.nrm, g.scene.mesh_id, np.concatenate([o, 3 * unit], 1))
     assert (ids1 >= 0).sum() > 500
     assert (ids1 != ids3).sum() > 0  # the un-normalised rays land elsewhere
+
+
+def test_port_reproduces_screen_postprocessing_golden():
+    """tests/golden/post_screen_56x40.npz holds what the reference's own Screen (src/screen.cpp, verbatim) makes of one
+    HDR image under 11 settings, through postprocessImage and through writeBitmapToFile: the port must match bit for bit."""
+    import os
+    import oracle
+    from util import GOLDEN, POST_CONFIGS
+    d = np.load(os.path.join(GOLDEN, "post_screen_56x40.npz"))
+    port = oracle.Oracle("port")
+    for k, cfg in enumerate(POST_CONFIGS):
+        a = port.postprocess(d["img"], **cfg)
+        b, rgba = port.postprocess(d["img"], via_write_bitmap=True, **cfg)
+        assert bits_equal(a, d[f"post_{k}"]), cfg
+        assert bits_equal(b, d[f"bmp_{k}"]) and np.array_equal(rgba, d[f"rgba_{k}"]), cfg
+
+
+def test_port_postprocessing_against_reference_library_live():
+    import oracle
+    if not oracle.available("reference"):
+        pytest.skip("oracle/_ref not built here (needs /root/reference)")
+    from util import POST_CONFIGS
+    rng = np.random.default_rng(11)
+    img = (rng.random((33, 47, 3), dtype=np.float32) * 3.0).astype(np.float32)
+    ref, port = oracle.Oracle("reference"), oracle.Oracle("port")
+    for cfg in POST_CONFIGS:
+        assert bits_equal(ref.postprocess(img, **cfg), port.postprocess(img, **cfg)), cfg
+        (a, ra), (b, rb) = ref.postprocess(img, via_write_bitmap=True, **cfg), port.postprocess(img, via_write_bitmap=True, **cfg)
+        assert bits_equal(a, b) and np.array_equal(ra, rb), cfg

@@ -11,6 +11,26 @@ GOLDEN_NAMES = ["cornell_planelight_160", "cornell_planelight_inside_96", "cube_
                 "cube_96", "zfight_96", "tr_def_96", "teapot_c2_256x144", "teapot_d3_128x72", "dragon_standin_c3_160x90"]
 
 
+# Screen settings exercised by the post-processing fixture (tests/golden/make_golden_post.py) and the GPU tests; keyword
+# names are those of oracle.Oracle.postprocess.  filtering_option: 0 None, 1 Bloom, 2 +Reinhard, 3 +Exposure, 4 OnlyLight,
+# 5 OnlyLightWithKernel; kernel: 0 box, 1 Gaussian.
+POST_CONFIGS = [
+    dict(filtering_option=1),                                                        # Screen's defaults with the bloom on
+    dict(filtering_option=2, kernel=1),                                              # Gaussian, sigma 2, size 5
+    dict(filtering_option=3, kernel_repetitions=3, filter_size=2, exposure=0.8),
+    dict(filtering_option=2, kernel=1, sigma=0.7, filter_size=3, gamma_correction=True, gamma=1.8),
+    dict(filtering_option=4),
+    dict(filtering_option=5, kernel=1, kernel_repetitions=4),                        # repetitions are ignored by this option
+    dict(filtering_option=1, filter_size=0),                                         # single tap
+    dict(filtering_option=1, filter_size=20),                                        # wider than the staged tile path
+    dict(filtering_option=2, bloom_live=False, gamma_correction=True),               # gamma only (postprocessImage), bloom only (BMP)
+    dict(filtering_option=0, gamma_correction=True, gamma=2.2),
+    dict(filtering_option=1, kernel_repetitions=0, sigma=0.0, kernel=1, filter_size=1),  # setter clamps: 1 repetition, sigma 0.001
+]
+# settings whose arithmetic is +, *, / and comparisons only: bit-exact on the device; the others involve exp / pow
+POST_EXACT = [k for k, c in enumerate(POST_CONFIGS) if c["filtering_option"] != 3 and not c.get("gamma_correction")]
+
+
 class Golden:
     def __init__(self, name):
         import rtb200
