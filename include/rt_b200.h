@@ -108,6 +108,32 @@ int rt_build_bvh(rt_ctx* ctx, int mode);
 int rt_set_materials(rt_ctx* ctx, const rt_material* mats, int n_mats);
 int rt_set_lights(rt_ctx* ctx, const rt_point_light* point, int n_point, const rt_sphere_light* sphere, int n_sphere);
 
+/* Diffuse textures: Material::kdTexture (src/mesh.h:29), Vertex::texCoord (src/mesh.h:18) and the texture branch of
+ * getFinalColor (src/main.cpp:155-171) with Image::getPixel (src/image.cpp:75-108). */
+#define RT_TEX_NEAREST 0   /* TextureFiltering::NearestNeighbor, src/image.h:24-31                                  */
+#define RT_TEX_BILINEAR 1  /* TextureFiltering::Bilinear.  The three mip-mapped modes are refused: their level comes  */
+                           /* from Ray::dD_dx / dD_dy, which the reference initialises from members constructed       */
+                           /* later (framework/include/ray.h:19-28) — there is no defined answer to reproduce.        */
+#define RT_OOB_BORDER 0    /* OutOfBoundsRule, src/image.h:18-22 */
+#define RT_OOB_CLAMP 1
+#define RT_OOB_REPEAT 2
+typedef struct {
+    int width, height;
+    const float* rgb;      /* width*height*3 floats, top row first: Image::m_pixels, i.e. byte / 255.0f (src/image.cpp:57-59) */
+} rt_texture;
+typedef struct {
+    int filtering;                          /* textureFiltering, src/main.cpp:54 */
+    int out_of_bounds_x, out_of_bounds_y;   /* outOfBoundsRuleX / Y, src/main.cpp:55-56 */
+    float border_color[3];                  /* textureBorderColor, src/main.cpp:57 */
+} rt_texture_params;
+/* Texture coordinates of the uploaded triangles: 6 floats per triangle (u, v of its three corners), global order.
+ * NULL: all zero (what loadMesh stores for meshes without them, src/mesh.cpp:113-117).  Call after rt_upload_scene. */
+int rt_set_texcoords(rt_ctx* ctx, const float* uv);
+/* The scene's textures and, per material (mesh), which one it uses (-1: none).  n_textures = 0 removes them. */
+int rt_set_textures(rt_ctx* ctx, const rt_texture* textures, int n_textures, const int* material_texture, int n_materials);
+/* useTextures (src/main.cpp:58) and its knobs for the following frames; NULL = off (the reference's default). */
+int rt_set_texturing(rt_ctx* ctx, const rt_texture_params* params);
+
 /* Screen post-processing: the step renderRayTracing ends with (screen.postprocessImage(), src/main.cpp:397-398), and the
  * bloom + 8-bit conversion of Screen::writeBitmapToFile (src/screen.cpp:40-53).  Fields = Screen's private settings
  * (src/screen.h:84-101) as its setters leave them (src/screen.cpp:172-223). */
@@ -217,6 +243,10 @@ const float* rt_soup_positions(const rt_mesh_soup* s); /* 9 floats per triangle 
 const float* rt_soup_normals(const rt_mesh_soup* s);   /* 9 floats per triangle */
 const int* rt_soup_mesh_ids(const rt_mesh_soup* s);
 const rt_material* rt_soup_materials(const rt_mesh_soup* s);
+const float* rt_soup_texcoords(const rt_mesh_soup* s);          /* 6 floats per triangle: Vertex::texCoord of its corners        */
+int rt_soup_num_textures(const rt_mesh_soup* s);                /* distinct map_Kd files that could be decoded (PNG)             */
+const rt_texture* rt_soup_textures(const rt_mesh_soup* s);
+const int* rt_soup_material_textures(const rt_mesh_soup* s);    /* per mesh: index into rt_soup_textures or -1 (Material::kdTexture) */
 void rt_soup_free(rt_mesh_soup* s);
 
 const char* rt_last_error(void);

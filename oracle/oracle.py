@@ -40,6 +40,15 @@ class OrcStats(C.Structure):
         return int(self.primary_rays + self.shadow_queries + self.secondary_rays)
 
 
+class OrcTexture(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("rgb", C.c_void_p)]
+
+
+# TextureFiltering (the two without a mip level) and OutOfBoundsRule of src/image.h:18-31
+TEX_NEAREST, TEX_BILINEAR = 0, 1
+OOB_BORDER, OOB_CLAMP, OOB_REPEAT = 0, 1, 2
+
+
 class OrcPost(C.Structure):
     _fields_ = [("filtering_option", C.c_int), ("kernel", C.c_int), ("kernel_repetitions", C.c_int), ("filter_size", C.c_int),
                 ("sigma", C.c_float), ("exposure", C.c_float), ("gamma_correction", C.c_int), ("gamma", C.c_float), ("bloom_live", C.c_int)]
@@ -114,6 +123,21 @@ class Oracle:
         pl = np.ascontiguousarray(plane if plane is not None else np.zeros((0, 12)), np.float32).reshape(-1, 12)
         self.lib.oracle_set_extra_lights(C.c_void_p(sp.ctypes.data if len(sp) else None), C.c_int(len(sp)),
                                          C.c_void_p(pl.ctypes.data if len(pl) else None), C.c_int(len(pl)), C.c_int(int(plane_ray_count_1d)))
+
+    def set_textures(self, tri_uv=None, textures=None, mesh_tex=None, filtering=TEX_NEAREST, oob_x=OOB_BORDER, oob_y=OOB_BORDER, border=(0, 0, 0)):
+        """Diffuse textures for the following render() calls (None / no textures: off).  tri_uv (n_tris, 6); textures: list of
+        (H, W, 3) uint8 arrays, top row first; mesh_tex: texture index per mesh or -1."""
+        self.lib.oracle_set_textures.restype = None
+        if tri_uv is None or not textures:
+            self.lib.oracle_set_textures(None, 0, None, 0, None, 0, 0, 0, 0, 0, None)
+            return
+        uv = np.ascontiguousarray(tri_uv, np.float32).reshape(-1, 6)
+        imgs = [np.ascontiguousarray(t, np.uint8) for t in textures]
+        arr = (OrcTexture * len(imgs))(*[OrcTexture(t.shape[1], t.shape[0], t.ctypes.data) for t in imgs])
+        mt = np.ascontiguousarray(mesh_tex, np.int32)
+        b = np.ascontiguousarray(border, np.float32)
+        self.lib.oracle_set_textures(C.c_void_p(uv.ctypes.data), C.c_int(uv.shape[0]), arr, C.c_int(len(imgs)), C.c_void_p(mt.ctypes.data), C.c_int(len(mt)),
+                                     C.c_int(1), C.c_int(int(filtering)), C.c_int(int(oob_x)), C.c_int(int(oob_y)), C.c_void_p(b.ctypes.data))
 
     def postprocess(self, rgb, filtering_option=FILTER_NONE, kernel=KERNEL_BOX, kernel_repetitions=1, filter_size=5, sigma=2.0, exposure=0.5,
                     gamma_correction=False, gamma=2.2, bloom_live=True, via_write_bitmap=False):

@@ -90,6 +90,20 @@ void oracle_set_spheres(const float* spheres, int n);
  * each = position (3), width (3), height (3), colour (3).  plane_ray_count_1d = plane_light_1D_ray_count (src/main.cpp:125). */
 void oracle_set_extra_lights(const float* spot, int n_spot, const float* plane, int n_plane, int plane_ray_count_1d);
 
+/* Diffuse textures (src/image.cpp; getFinalColor's texture branch, src/main.cpp:155-171; texture coordinates interpolated in
+ * intersectRayWithTriangleWithInterpolation, src/ray_tracing.cpp:166-169) for the following oracle_render calls.
+ * tri_uv: 6 floats per triangle (u, v of its three corners) in global triangle order.  textures: 8-bit RGB rows, top row first
+ * (what stbi_load hands to Image::Image, which divides by 255).  mesh_tex[m]: texture of mesh m or -1.
+ * filtering: TextureFiltering (src/image.h:24-31) 0 NearestNeighbor, 1 Bilinear — the mip-mapped modes take their level from
+ * ray differentials that the reference initialises from not-yet-constructed members (framework/include/ray.h:19-28) and are
+ * not offered.  oob_x / oob_y: OutOfBoundsRule (src/image.h:18-22) 0 Border, 1 Clamp, 2 Repeat.  use_textures = 0 clears. */
+typedef struct {
+    int width, height;
+    const unsigned char* rgb;
+} orc_texture;
+void oracle_set_textures(const float* tri_uv, int n_tris, const orc_texture* textures, int n_textures, const int* mesh_tex, int n_meshes,
+    int use_textures, int filtering, int oob_x, int oob_y, const float* border_rgb);
+
 /* Screen post-processing, the step renderRayTracing ends with (src/main.cpp:397-398; src/screen.cpp:56-69, 226-395). */
 typedef struct {
     int filtering_option;   /* FilteringOption (src/screen.h:17-26): 0 None, 1 Bloom, 2 BloomWithReinhardHdr, 3 BloomWithExposureHdr,

@@ -11,8 +11,9 @@
 //   getPixelRays                           src/main.cpp:309-335
 //   renderRayTracing                       src/main.cpp:340-400
 //   Screen::setPixel                       src/screen.cpp:32-38
-// Textures (useTextures=false, main.cpp:58) and ray differentials (no colour effect with textures
-// off, main.cpp:137) are left out.  Builds oracle/_ref/libref_oracle.so, kind "reference".
+// Diffuse textures go through the reference's own Image class (src/image.cpp, also compiled verbatim) for the two
+// filters that do not need a mip level; ray differentials (main.cpp:137) only feed that level and are left out.
+// Builds oracle/_ref/libref_oracle.so, kind "reference".
 #include "bounding_volume_hierarchy.h"
 #include "ray_tracing.h"
 #include "shadow.h"
@@ -22,8 +23,11 @@
 #include <array>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
+#include <filesystem>
 #include <limits>
+#include <string>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -34,6 +38,22 @@
 extern thread_local unsigned long long orc_drawray_calls;
 
 namespace {
+
+} // namespace
+struct OrcRegisteredTexture { // shared with the stbi_load stand-in (ref_stubs.cpp)
+    int w, h;
+    std::vector<unsigned char> rgb;
+};
+extern std::vector<OrcRegisteredTexture> orc_registered_textures;
+namespace {
+
+std::vector<float> g_tex_uv;        // oracle_set_textures: 6 floats per triangle
+std::vector<int> g_mesh_tex;
+std::vector<std::string> g_tex_files; // placeholder files whose names carry the registry index
+bool g_use_textures = false;        // useTextures, src/main.cpp:58
+TextureFiltering g_tex_filtering = TextureFiltering::NearestNeighbor; // main.cpp:54
+OutOfBoundsRule g_oob_x = OutOfBoundsRule::Border, g_oob_y = OutOfBoundsRule::Border; // main.cpp:55-56
+glm::vec3 g_tex_border(0);          // main.cpp:57
 
 std::vector<float> g_spheres;       // oracle_set_spheres
 std::vector<float> g_spot, g_plane; // oracle_set_extra_lights
@@ -102,6 +122,16 @@ glm::vec3 getFinalColor(const RenderGlobals& g, Scene& scene, const BoundingVolu
     matForRendering.ks = originalMaterial.ks;
     matForRendering.shininess = originalMaterial.shininess;
     matForRendering.transparency = originalMaterial.transparency;
+
+    if (g_use_textures && hitInfo.is_triangle && originalMaterial.kdTexture) { // main.cpp:155-171
+        Image& texture = originalMaterial.kdTexture.value();
+        texture.setBorderColor(g_tex_border);
+        texture.setOutOfBoundsRuleX(g_oob_x);
+        texture.setOutOfBoundsRuleY(g_oob_y);
+        texture.setTextureFilteringMethod(g_tex_filtering);
+        const float lod = 0.0f; // computeLevelOfDetails: unused by NearestNeighbor / Bilinear (src/image.cpp:96-99)
+        matForRendering.kd = texture.getPixel(hitInfo.texCoord, lod);
+    }
 
     for (const Lighting& light : getPointLights(hitInfo, reflect, scene, bvh))
         color += calcColor(light, matForRendering);
@@ -198,6 +228,9 @@ Scene sceneFromSoup(const float* pos, const float* nrm, const int* mesh_id, int 
             mat.kd = glm::vec3(1.0f);
         }
     }
+    for (int m = 0; m < (int)scene.meshes.size() && m < (int)g_mesh_tex.size(); m++)
+        if (g_mesh_tex[m] >= 0 && g_mesh_tex[m] < (int)g_tex_files.size())
+            scene.meshes[m].material.kdTexture = Image(g_tex_files[g_mesh_tex[m]]); // Image::Image -> stbi_load stand-in
     for (int i = 0; i < n_tris; i++) {
         Mesh& mesh = scene.meshes[mesh_id ? mesh_id[i] : 0];
         const unsigned base = (unsigned)mesh.vertices.size();
@@ -205,7 +238,7 @@ Scene sceneFromSoup(const float* pos, const float* nrm, const int* mesh_id, int 
             Vertex v;
             v.p = glm::vec3(pos[9 * i + 3 * k], pos[9 * i + 3 * k + 1], pos[9 * i + 3 * k + 2]);
             v.n = nrm ? glm::vec3(nrm[9 * i + 3 * k], nrm[9 * i + 3 * k + 1], nrm[9 * i + 3 * k + 2]) : glm::vec3(0, 0, 1);
-            v.texCoord = glm::vec2(0.0f);
+            v.texCoord = g_tex_uv.size() == 6 * (size_t)n_tris ? glm::vec2(g_tex_uv[6 * i + 2 * k], g_tex_uv[6 * i + 2 * k + 1]) : glm::vec2(0.0f);
             mesh.vertices.push_back(v);
         }
         mesh.triangles.emplace_back(base, base + 1, base + 2);
@@ -248,6 +281,30 @@ extern "C" void oracle_set_extra_lights(const float* spot, int n_spot, const flo
 extern "C" void oracle_set_spheres(const float* spheres, int n)
 {
     g_spheres.assign(spheres, spheres + (spheres ? 12 * (size_t)n : 0));
+}
+
+extern "C" void oracle_set_textures(const float* tri_uv, int n_tris, const orc_texture* textures, int n_textures, const int* mesh_tex, int n_meshes,
+    int use_textures, int filtering, int oob_x, int oob_y, const float* border_rgb)
+{
+    g_use_textures = use_textures != 0;
+    g_tex_uv.assign(tri_uv, tri_uv + (tri_uv && use_textures ? 6 * (size_t)n_tris : 0));
+    g_mesh_tex.assign(mesh_tex, mesh_tex + (mesh_tex && use_textures ? n_meshes : 0));
+    orc_registered_textures.clear();
+    g_tex_files.clear();
+    for (int k = 0; use_textures && k < n_textures; k++) {
+        orc_registered_textures.push_back({ textures[k].width, textures[k].height,
+            std::vector<unsigned char>(textures[k].rgb, textures[k].rgb + 3 * (size_t)textures[k].width * textures[k].height) });
+        // Image::Image insists on an existing file (src/image.cpp:38-41): an empty placeholder whose name carries the index
+        const std::string name = (std::filesystem::temp_directory_path() / ("orc_texture_" + std::to_string(k))).string();
+        std::FILE* f = std::fopen(name.c_str(), "wb");
+        if (f)
+            std::fclose(f);
+        g_tex_files.push_back(name);
+    }
+    g_tex_filtering = filtering == 1 ? TextureFiltering::Bilinear : TextureFiltering::NearestNeighbor;
+    g_oob_x = (OutOfBoundsRule)oob_x;
+    g_oob_y = (OutOfBoundsRule)oob_y;
+    g_tex_border = border_rgb ? glm::vec3(border_rgb[0], border_rgb[1], border_rgb[2]) : glm::vec3(0);
 }
 
 extern "C" int oracle_render(const float* pos, const float* nrm, const int* mesh_id, int n_tris,

@@ -21,3 +21,29 @@ extern "C" int stbi_write_bmp(char const*, int w, int h, int comp, const void* d
     orc_bmp_rows.assign(b, b + (size_t)w * h * comp);
     return 1;
 }
+
+// Image::Image's source of texels (see gl_standin/stb_image.h).  The registry is filled by oracle_set_textures.
+#include <cstdlib>
+#include <cstring>
+#include <string>
+struct OrcRegisteredTexture {
+    int w, h;
+    std::vector<unsigned char> rgb;
+};
+std::vector<OrcRegisteredTexture> orc_registered_textures;
+extern "C" unsigned char* stbi_load(char const* filename, int* x, int* y, int* channels_in_file, int)
+{
+    const std::string name(filename);
+    const size_t us = name.find_last_of('_');
+    const int k = us == std::string::npos ? -1 : std::atoi(name.c_str() + us + 1);
+    if (k < 0 || k >= (int)orc_registered_textures.size())
+        return nullptr;
+    const OrcRegisteredTexture& t = orc_registered_textures[k];
+    *x = t.w;
+    *y = t.h;
+    *channels_in_file = 3;
+    unsigned char* p = static_cast<unsigned char*>(std::malloc(t.rgb.size()));
+    std::memcpy(p, t.rgb.data(), t.rgb.size());
+    return p;
+}
+extern "C" void stbi_image_free(void* p) { std::free(p); }

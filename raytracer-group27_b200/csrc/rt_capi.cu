@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <filesystem>
 #include <string>
 #include <vector>
 
@@ -82,6 +83,15 @@ struct rt_ctx {
     bool any_transparent = false;          // meshes or spheres
     bool mats_transparent = false, spheres_transparent = false;
     DevBuf<float4> d_spheres, d_plane_lights;
+    // diffuse textures (rt_set_texcoords / rt_set_textures / rt_set_texturing)
+    DevBuf<float4> d_tex_texels;
+    DevBuf<int4> d_tex_table;
+    DevBuf<int> d_mat_tex;
+    DevBuf<float2> d_uv;
+    bool have_uv = false;
+    int n_textures = 0;
+    bool tex_on = false;
+    rt_texture_params tex_params {};
     int n_spheres = 0;
     std::vector<float4> h_point, h_spot; // point-like light table = point lights followed by spot lights
     int n_point_user = 0, n_spot = 0, n_plane = 0;
@@ -155,6 +165,10 @@ struct rt_ctx {
         s.sphere_lights = d_sphere.p;
         s.plane_lights = d_plane_lights.p;
         s.spheres = d_spheres.p;
+        s.tex_texels = d_tex_texels.p;
+        s.tex_table = d_tex_table.p;
+        s.mat_tex = d_mat_tex.p;
+        s.tri_uv = have_uv ? d_uv.p : nullptr;
         s.sphere_rank = d_rank.p ? d_rank.p + user_tris : nullptr;
         s.tie_by_id = 0;
         s.n_spheres = n_spheres;
@@ -267,6 +281,13 @@ int make_frame_params(const rt_ctx* ctx, const rt_camera* cam, const rt_params* 
     fp.any_transparent = ctx->any_transparent ? 1 : 0;
     fp.exhaustive = prm->exhaustive ? 1 : 0;
     fp.tie_by_id = prm->use_bvh ? 0 : 1;
+    fp.tex_on = ctx->tex_on && ctx->n_textures > 0 && ctx->d_mat_tex.p ? 1 : 0;
+    fp.tex_filter = ctx->tex_params.filtering;
+    fp.tex_oob_x = ctx->tex_params.out_of_bounds_x;
+    fp.tex_oob_y = ctx->tex_params.out_of_bounds_y;
+    fp.tex_border_r = ctx->tex_params.border_color[0];
+    fp.tex_border_g = ctx->tex_params.border_color[1];
+    fp.tex_border_b = ctx->tex_params.border_color[2];
     // getSpherelights ring layout (shadow.cpp:190-196)
     int rc = prm->sphere_light_ray_count;
     if (ctx->n_sphere > 0 && rc < 1)
@@ -798,6 +819,10 @@ int rt_destroy(rt_ctx* ctx)
     ctx->out_t.release();
     ctx->rgb.release();
     ctx->d_spheres.release();
+    ctx->d_tex_texels.release();
+    ctx->d_tex_table.release();
+    ctx->d_mat_tex.release();
+    ctx->d_uv.release();
     ctx->d_plane_lights.release();
     ctx->rays_in.release();
     ctx->flag.release();
@@ -932,6 +957,8 @@ int rt_upload_scene(rt_ctx* ctx, const float* pos, const float* nrm, const int* 
         CK(cudaMemsetAsync(ctx->d_mesh.p, 0, (size_t)n_tris * sizeof(int), ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->bvh_built = false;
+    ctx->have_uv = false; // texture coordinates and texture bindings belong to the previous scene
+    ctx->n_textures = 0;
     return RT_OK;
 }
 
@@ -1365,6 +1392,86 @@ int rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, float* rg
     }
 }
 
+int rt_set_texcoords(rt_ctx* ctx, const float* uv)
+{
+    int rc = use_device(ctx);
+    if (rc)
+        return rc;
+    if (ctx->n_tris <= 0)
+        return fail(RT_ERR_INVALID, "rt_set_texcoords: upload a scene first");
+    if (!uv || ctx->user_tris == 0) {
+        ctx->have_uv = false;
+        return RT_OK;
+    }
+    CK(ctx->d_uv.ensure(3 * (size_t)ctx->user_tris));
+    CK(cudaMemcpyAsync(ctx->d_uv.p, uv, 6 * (size_t)ctx->user_tris * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_uv = true;
+    return RT_OK;
+}
+
+int rt_set_textures(rt_ctx* ctx, const rt_texture* textures, int n_textures, const int* material_texture, int n_materials)
+{
+    int rc = use_device(ctx);
+    if (rc)
+        return rc;
+    if (n_textures < 0 || (n_textures > 0 && (!textures || !material_texture)))
+        return fail(RT_ERR_INVALID, "rt_set_textures: need textures and one texture index per material");
+    if (n_textures == 0) {
+        ctx->n_textures = 0;
+        return RT_OK;
+    }
+    if (n_materials != ctx->n_mats)
+        return fail(RT_ERR_INVALID, "rt_set_textures: material count differs from the uploaded scene");
+    std::vector<int4> table((size_t)n_textures);
+    size_t total = 0;
+    for (int k = 0; k < n_textures; k++) {
+        if (textures[k].width <= 0 || textures[k].height <= 0 || !textures[k].rgb)
+            return fail(RT_ERR_INVALID, "rt_set_textures: empty texture");
+        if (total + (size_t)textures[k].width * textures[k].height > 0x7fffffffu)
+            return fail(RT_ERR_INVALID, "rt_set_textures: more than 2^31 texels");
+        table[k] = make_int4((int)total, textures[k].width, textures[k].height, 0);
+        total += (size_t)textures[k].width * textures[k].height;
+    }
+    for (int m = 0; m < n_materials; m++)
+        if (material_texture[m] < -1 || material_texture[m] >= n_textures)
+            return fail(RT_ERR_INVALID, "rt_set_textures: texture index out of range");
+    std::vector<float4> texels(total);
+    for (int k = 0; k < n_textures; k++) {
+        const size_t n = (size_t)textures[k].width * textures[k].height;
+        for (size_t i = 0; i < n; i++)
+            texels[table[k].x + i] = make_float4(textures[k].rgb[3 * i], textures[k].rgb[3 * i + 1], textures[k].rgb[3 * i + 2], 0.0f);
+    }
+    CK(cudaStreamSynchronize(ctx->stream)); // an earlier frame may still sample the old texels
+    CK(ctx->d_tex_texels.ensure(total));
+    CK(ctx->d_tex_table.ensure((size_t)n_textures));
+    CK(ctx->d_mat_tex.ensure((size_t)n_materials));
+    CK(cudaMemcpyAsync(ctx->d_tex_texels.p, texels.data(), total * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_tex_table.p, table.data(), table.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_mat_tex.p, material_texture, (size_t)n_materials * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_textures = n_textures;
+    return RT_OK;
+}
+
+int rt_set_texturing(rt_ctx* ctx, const rt_texture_params* p)
+{
+    if (!ctx)
+        return fail(RT_ERR_INVALID, "null context");
+    if (!p) {
+        ctx->tex_on = false;
+        return RT_OK;
+    }
+    if (p->filtering != RT_TEX_NEAREST && p->filtering != RT_TEX_BILINEAR)
+        return fail(RT_ERR_INVALID, "rt_set_texturing: only the NearestNeighbor and Bilinear filters are offered (the mip-mapped ones take their level from "
+                                    "ray differentials the reference leaves uninitialised)");
+    if (p->out_of_bounds_x < RT_OOB_BORDER || p->out_of_bounds_x > RT_OOB_REPEAT || p->out_of_bounds_y < RT_OOB_BORDER || p->out_of_bounds_y > RT_OOB_REPEAT)
+        return fail(RT_ERR_INVALID, "rt_set_texturing: unknown out-of-bounds rule");
+    ctx->tex_params = *p;
+    ctx->tex_on = true;
+    return RT_OK;
+}
+
 int rt_set_postprocess(rt_ctx* ctx, const rt_post_params* post)
 {
     if (!ctx)
@@ -1490,9 +1597,12 @@ int rt_intersect(rt_ctx* ctx, const float* rays, int64_t n_rays, int use_bvh, in
 
 // ---- OBJ loading: host only ----
 struct rt_mesh_soup {
-    std::vector<float> pos, nrm;
+    std::vector<float> pos, nrm, uv;
     std::vector<int> mesh_id;
     std::vector<rt_material> mats;
+    std::vector<int> mat_tex;                 // texture of each mesh, -1 = none
+    std::vector<std::vector<float>> texels;   // one per distinct texture file
+    std::vector<rt_texture> textures;         // views of `texels`
 };
 
 int rt_load_obj(const char* path, int center_and_normalize, rt_mesh_soup** out)
@@ -1503,6 +1613,7 @@ int rt_load_obj(const char* path, int center_and_normalize, rt_mesh_soup** out)
     try {
         std::vector<Mesh> meshes = loadMesh(path, center_and_normalize != 0);
         auto* s = new rt_mesh_soup();
+        std::vector<std::filesystem::path> texture_paths;
         int mi = 0;
         for (const Mesh& mesh : meshes) {
             for (const Triangle& tri : mesh.triangles) {
@@ -1510,13 +1621,34 @@ int rt_load_obj(const char* path, int center_and_normalize, rt_mesh_soup** out)
                 for (int k = 0; k < 3; k++) {
                     s->pos.insert(s->pos.end(), { v[k]->p.x, v[k]->p.y, v[k]->p.z });
                     s->nrm.insert(s->nrm.end(), { v[k]->n.x, v[k]->n.y, v[k]->n.z });
+                    s->uv.insert(s->uv.end(), { v[k]->texCoord.x, v[k]->texCoord.y });
                 }
                 s->mesh_id.push_back(mi);
             }
             const Material& m = mesh.material;
             s->mats.push_back(rt_material { { m.kd.x, m.kd.y, m.kd.z }, { m.ks.x, m.ks.y, m.ks.z }, m.shininess, m.transparency });
+            int tex = -1;
+            if (m.kdTexture) { // one entry per distinct file
+                const Image& img = *m.kdTexture;
+                for (size_t k = 0; k < texture_paths.size() && tex < 0; k++)
+                    if (texture_paths[k] == img.path())
+                        tex = (int)k;
+                if (tex < 0) {
+                    tex = (int)texture_paths.size();
+                    texture_paths.push_back(img.path());
+                    std::vector<float> t;
+                    t.reserve(img.pixels().size() * 3);
+                    for (const glm::vec3& c : img.pixels())
+                        t.insert(t.end(), { c.x, c.y, c.z });
+                    s->texels.push_back(std::move(t));
+                    s->textures.push_back(rt_texture { img.width(), img.height(), nullptr });
+                }
+            }
+            s->mat_tex.push_back(tex);
             mi++;
         }
+        for (size_t k = 0; k < s->textures.size(); k++)
+            s->textures[k].rgb = s->texels[k].data();
         *out = s;
         return RT_OK;
     } catch (const std::exception& e) {
@@ -1530,6 +1662,10 @@ const float* rt_soup_positions(const rt_mesh_soup* s) { return s ? s->pos.data()
 const float* rt_soup_normals(const rt_mesh_soup* s) { return s ? s->nrm.data() : nullptr; }
 const int* rt_soup_mesh_ids(const rt_mesh_soup* s) { return s ? s->mesh_id.data() : nullptr; }
 const rt_material* rt_soup_materials(const rt_mesh_soup* s) { return s ? s->mats.data() : nullptr; }
+const float* rt_soup_texcoords(const rt_mesh_soup* s) { return s ? s->uv.data() : nullptr; }
+int rt_soup_num_textures(const rt_mesh_soup* s) { return s ? (int)s->textures.size() : 0; }
+const rt_texture* rt_soup_textures(const rt_mesh_soup* s) { return s ? s->textures.data() : nullptr; }
+const int* rt_soup_material_textures(const rt_mesh_soup* s) { return s ? s->mat_tex.data() : nullptr; }
 void rt_soup_free(rt_mesh_soup* s) { delete s; }
 
 } // extern "C"

@@ -121,6 +121,8 @@ struct Shading { // what shade and the transparent-shadow branch need at a hit
     f3 p;      // hit point
     f3 N;      // triangle: interpolated normal, flipped to the geometric side (not normalised); sphere: unit normal
     float4 m0, m1; // material {kd, shininess}{ks, transparency} (HitInfo::getMaterial, src/ray_tracing.h:21-27)
+    float c0, c1, c2; // barycentric weights of a triangle hit (interpolateProperty, src/ray_tracing.cpp:313-316)
+    int mesh, gid;    // mesh (material) index and global triangle id of a triangle hit; -1 for spheres
 };
 
 // Hit point and shading normal: src/ray_tracing.cpp:111, 147-160 with barycentricCoordinates (276-308) evaluated
@@ -135,6 +137,8 @@ __device__ __forceinline__ Shading shading_at(const SceneDev& s, int ti, const f
         sh.N = xnormalize(xsub(sh.p, mk3(__ldg(&s.spheres[3 * k]))));
         sh.m0 = __ldg(&s.spheres[3 * k + 1]);
         sh.m1 = __ldg(&s.spheres[3 * k + 2]);
+        sh.c0 = sh.c1 = sh.c2 = 0.0f;
+        sh.mesh = sh.gid = -1;
         return sh;
     }
     const float4 pl = __ldg(&s.tri_plane[ti]);
@@ -152,7 +156,82 @@ __device__ __forceinline__ Shading shading_at(const SceneDev& s, int ti, const f
     if (xdot(N, fn) < 0.0f)
         N = xneg(N);
     sh.N = N;
+    sh.c0 = c0;
+    sh.c1 = c1;
+    sh.c2 = c2;
+    sh.mesh = mesh;
+    sh.gid = __float_as_int(c.w);
     return sh;
+}
+
+// Image::getPixel for the NearestNeighbor and Bilinear filters (src/image.cpp:75-108) with the out-of-bounds rules
+// (110-198), toImageCoordinates (118-131: rows start at the top), nearestNeighbor (217-246), bilinearInterpolation (249-268)
+// and linearInterpolation (366-375), operation for operation.
+__device__ __forceinline__ bool tex_out_of_bounds(float c) { return c < 0.0f || c > 1.0f; }
+
+__device__ __forceinline__ float tex_rule(float c, int rule)
+{
+    if (rule == 1)
+        return c > 1.0f ? 1.0f : (c < 0.0f ? 0.0f : c);
+    if (rule == 2)
+        return tex_out_of_bounds(c) ? xsub(c, floorf(c)) : c;
+    return c;
+}
+
+__device__ __forceinline__ f3 tex_lerp(float low, float high, const f3& cl, const f3& ch, float p)
+{
+    if ((double)fabsf(xsub(high, low)) < 1e-6)
+        return cl;
+    const float c = xdiv(xsub(p, low), xsub(high, low));
+    return xadd(xmul(cl, xsub(1.0f, c)), xmul(ch, c));
+}
+
+__device__ __forceinline__ f3 sample_texture(const SceneDev& s, const FrameParams& fp, int tex, float u, float v)
+{
+    const f3 border = mk3(fp.tex_border_r, fp.tex_border_g, fp.tex_border_b);
+    if (fp.tex_oob_x == 0 && tex_out_of_bounds(u))
+        return border;
+    if (fp.tex_oob_y == 0 && tex_out_of_bounds(v))
+        return border;
+    u = tex_rule(u, fp.tex_oob_x);
+    v = tex_rule(v, fp.tex_oob_y);
+    const int4 tb = __ldg(&s.tex_table[tex]);
+    const unsigned w = (unsigned)tb.y, h = (unsigned)tb.z;
+    const float4* px = s.tex_texels + tb.x;
+    const float ix = xmul(u, (float)(w - 1u)), iy = xmul(xsub(1.0f, v), (float)(h - 1u));
+    if (fp.tex_filter == 0) {
+        unsigned x = (unsigned)roundf(ix), y = (unsigned)roundf(iy);
+        if (x >= w)
+            x = w - 1u;
+        if (y >= h)
+            y = h - 1u;
+        return mk3(__ldg(&px[(size_t)y * w + x]));
+    }
+    const float xl = floorf(ix), xh = ceilf(ix), yl = floorf(iy), yh = ceilf(iy);
+    const f3 ll = mk3(__ldg(&px[(size_t)(unsigned)yl * w + (unsigned)xl])), lr = mk3(__ldg(&px[(size_t)(unsigned)yl * w + (unsigned)xh]));
+    const f3 hl = mk3(__ldg(&px[(size_t)(unsigned)yh * w + (unsigned)xl])), hr = mk3(__ldg(&px[(size_t)(unsigned)yh * w + (unsigned)xh]));
+    const f3 low = tex_lerp(xl, xh, ll, lr, ix), high = tex_lerp(xl, xh, hl, hr, ix);
+    return tex_lerp(yl, yh, low, high, iy);
+}
+
+// kd of a hit: the material's, or its texture at the interpolated texture coordinate (getFinalColor, src/main.cpp:155-171)
+__device__ __forceinline__ f3 diffuse_colour(const SceneDev& s, const FrameParams& fp, const Shading& sh)
+{
+    if (fp.tex_on && sh.mesh >= 0) {
+        const int tex = __ldg(&s.mat_tex[sh.mesh]);
+        if (tex >= 0) {
+            float2 t0 = make_float2(0.0f, 0.0f), t1 = t0, t2 = t0;
+            if (s.tri_uv) {
+                t0 = __ldg(&s.tri_uv[3 * (size_t)sh.gid]);
+                t1 = __ldg(&s.tri_uv[3 * (size_t)sh.gid + 1]);
+                t2 = __ldg(&s.tri_uv[3 * (size_t)sh.gid + 2]);
+            }
+            const float u = xadd(xadd(xmul(t0.x, sh.c0), xmul(t1.x, sh.c1)), xmul(t2.x, sh.c2));
+            const float v = xadd(xadd(xmul(t0.y, sh.c0), xmul(t1.y, sh.c1)), xmul(t2.y, sh.c2));
+            return sample_texture(s, fp, tex, u, v);
+        }
+    }
+    return mk3(sh.m0);
 }
 
 // Schlick term of the reference, evaluated in double like `R0 + (1 - R0) * std::pow(1 - c, 5)` with float c, R0
@@ -311,7 +390,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
                 refl = xreflect(dn, Nn); // main.cpp:141
             }
         }
-        const f3 kd = mk3(sh.m0), ks = mk3(sh.m1);
+        const f3 kd = hit ? diffuse_colour(s, fp, sh) : mk3(sh.m0), ks = mk3(sh.m1);
         const float shininess = sh.m0.w, transparency = sh.m1.w;
 
         // children

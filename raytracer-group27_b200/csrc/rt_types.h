@@ -38,6 +38,11 @@ struct SceneDev {
     const float4* plane_lights;  // 4 x float4: {position}{width}{height}{color}
     const float4* sphere_lights; // 2 x float4: {pos, radius}{color, 0}
     const float4* spheres;       // sphere primitives, 3 x float4: {centre, radius}{kd, shininess}{ks, transparency}
+    // diffuse textures (src/image.cpp): texels of all textures back to back, top row first; table {first texel, width, height, 0}
+    const float4* tex_texels;
+    const int4* tex_table;
+    const int* mat_tex;          // texture of material (mesh) m, or -1
+    const float2* tri_uv;        // Vertex::texCoord of the three corners of global triangle g at [3g .. 3g+2]; null = all zero
     const int* sphere_rank;      // visiting rank of sphere k in the reference's BVH (tie key, rt_reforder.cu)
     int tie_by_id;               // tie key of this launch: 0 = visiting rank in the reference's BVH (every BVH search of the reference, i.e. all
                                  // shadow queries and, with useBVH, the other rays), 1 = global id (its useBVH = false loop)
@@ -72,6 +77,9 @@ struct FrameParams {
     int pl_rc;                  // plane_light_1D_ray_count (src/main.cpp:125): pl_rc x pl_rc samples per plane light
     int any_transparent;
     int exhaustive;
+    // diffuse textures: useTextures and the knobs of src/main.cpp:54-58
+    int tex_on, tex_filter, tex_oob_x, tex_oob_y;
+    float tex_border_r, tex_border_g, tex_border_b;
     int tie_by_id;   // camera / reflection rays: equal t go to the lower global id (useBVH = false) instead of the BVH visiting rank
     // spherical-light ring sampling (shadow.cpp:190-196), host-computed and shared with the oracle
     int sl_m, sl_n, sl_rc;

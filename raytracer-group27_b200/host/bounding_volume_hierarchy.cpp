@@ -15,6 +15,9 @@ BoundingVolumeHierarchy::BoundingVolumeHierarchy(Scene* pScene, int bvhMode, int
     : m_pScene(pScene)
 {
     std::vector<rt_material> mats;
+    std::vector<float> uv;                 // Vertex::texCoord of every corner
+    std::vector<const Image*> images;      // distinct Material::kdTexture objects, by file
+    std::vector<int> matTex;
     int meshIndex = 0;
     for (const Mesh& mesh : pScene->meshes) {
         for (const Triangle& tri : mesh.triangles) {
@@ -22,15 +25,38 @@ BoundingVolumeHierarchy::BoundingVolumeHierarchy(Scene* pScene, int bvhMode, int
             for (int k = 0; k < 3; k++) {
                 m_pos.insert(m_pos.end(), { v[k]->p.x, v[k]->p.y, v[k]->p.z });
                 m_nrm.insert(m_nrm.end(), { v[k]->n.x, v[k]->n.y, v[k]->n.z });
+                uv.insert(uv.end(), { v[k]->texCoord.x, v[k]->texCoord.y });
             }
             m_meshId.push_back(meshIndex);
         }
         const Material& m = mesh.material;
         mats.push_back(rt_material { { m.kd.x, m.kd.y, m.kd.z }, { m.ks.x, m.ks.y, m.ks.z }, m.shininess, m.transparency });
+        int tex = -1;
+        if (m.kdTexture) {
+            for (size_t k = 0; k < images.size() && tex < 0; k++)
+                if (images[k]->path() == m.kdTexture->path())
+                    tex = (int)k;
+            if (tex < 0) {
+                tex = (int)images.size();
+                images.push_back(&*m.kdTexture);
+            }
+        }
+        matTex.push_back(tex);
         meshIndex++;
     }
     check(rt_create(device, &m_ctx), "rt_create");
     check(rt_upload_scene(m_ctx, m_pos.data(), m_nrm.data(), m_meshId.data(), (int64_t)m_meshId.size(), mats.data(), (int)mats.size()), "rt_upload_scene");
+    // textures travel with the geometry (they are loaded by loadMesh, src/mesh.cpp:138-145); whether they are used is a
+    // per-frame knob (useTextures, render.h)
+    if (!m_meshId.empty())
+        check(rt_set_texcoords(m_ctx, uv.data()), "rt_set_texcoords");
+    if (!images.empty()) {
+        std::vector<rt_texture> tex;
+        static_assert(sizeof(glm::vec3) == 3 * sizeof(float), "texels must be packed float3");
+        for (const Image* img : images)
+            tex.push_back(rt_texture { img->width(), img->height(), &img->pixels()[0].x });
+        check(rt_set_textures(m_ctx, tex.data(), (int)tex.size(), matTex.data(), (int)matTex.size()), "rt_set_textures");
+    }
     std::vector<rt_sphere> sp;
     for (const Sphere& s : pScene->spheres) {
         const Material& m = s.material;

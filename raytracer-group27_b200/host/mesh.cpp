@@ -18,6 +18,7 @@
 //     never sets them keeps kd 0.6, ks 0, shininess 0, transparency 1 (src/mesh.cpp:144-147 reads those keys).
 // Number parsing uses strtof (correctly rounded).
 #include "mesh.h"
+#include <iostream>
 
 #include <algorithm>
 #include <cmath>
@@ -326,8 +327,16 @@ std::vector<Mesh> loadMesh(const std::filesystem::path& file, bool normalize)
             mesh.material.ks = m.ks;
             mesh.material.shininess = m.shininess;
             mesh.material.transparency = m.opacity;
-            if (!m.mapKd.empty())
-                mesh.material.kdTexture = Image(std::filesystem::absolute(file).parent_path() / m.mapKd);
+            if (!m.mapKd.empty()) {
+                // The reference lets Image::Image's exception end the program (src/mesh.cpp:140-145).  Here a texture that
+                // is missing or cannot be decoded is reported and the material keeps its kd: the reference snapshot itself
+                // lacks some of the files its MTLs name, and the geometry of those scenes is still wanted.
+                try {
+                    mesh.material.kdTexture = Image(std::filesystem::absolute(file).parent_path() / m.mapKd);
+                } catch (const ImageError& e) {
+                    std::cerr << e.what() << std::endl;
+                }
+            }
             out.push_back(std::move(mesh));
         }
     }

@@ -9,6 +9,11 @@ int plane_light_1D_ray_count = 3;
 int glossy_ray_count = 1;
 float refraction_factor = 0.8f;
 bool useBVH = false;
+TextureFiltering textureFiltering { TextureFiltering::NearestNeighbor };
+OutOfBoundsRule outOfBoundsRuleX { OutOfBoundsRule::Border };
+OutOfBoundsRule outOfBoundsRuleY { OutOfBoundsRule::Border };
+glm::vec3 textureBorderColor(0);
+bool useTextures = false;
 RenderTimings lastRenderTimings;
 
 namespace {
@@ -74,6 +79,14 @@ void renderRayTracing(Scene& scene, const Trackball& camera, const BoundingVolum
     prm.plane_light_ray_count_1d = plane_light_1D_ray_count;
     rt_stats st {};
     static_assert(sizeof(glm::vec3) == 3 * sizeof(float), "Screen pixels must be packed float3");
+    // the texture branch of getFinalColor (src/main.cpp:155-171) with the knobs main.cpp sets on the Image before sampling it
+    if (useTextures) {
+        rt_texture_params tp { static_cast<int>(textureFiltering), static_cast<int>(outOfBoundsRuleX), static_cast<int>(outOfBoundsRuleY),
+            { textureBorderColor.x, textureBorderColor.y, textureBorderColor.z } };
+        check(rt_set_texturing(ctx, &tp), "rt_set_texturing");
+    } else {
+        check(rt_set_texturing(ctx, nullptr), "rt_set_texturing");
+    }
     // screen.postprocessImage() (src/main.cpp:397-398) runs on the device at the end of the frame, before the rows come home
     check(rt_set_postprocess(ctx, &screen.postSettings()), "rt_set_postprocess");
     check(rt_render(ctx, &cam, &prm, &screen.pixels()[0].x, nullptr, nullptr, &st), "rt_render");

@@ -12,7 +12,12 @@ extern int sphere_light_ray_count; // default 10
 extern int plane_light_1D_ray_count; // default 3
 extern int glossy_ray_count;       // reference default 10 uses rand(); only the deterministic value 1 is supported
 extern float refraction_factor;    // default 0.8
-extern bool useBVH;                // reference default false (brute force); both settings give the same image
+extern bool useBVH;                // reference default false: which of two objects at exactly the same t is reported (rt_b200.h)
+// texture knobs (src/main.cpp:54-58)
+extern TextureFiltering textureFiltering;  // default NearestNeighbor; the mip-mapped modes are refused (rt_b200.h)
+extern OutOfBoundsRule outOfBoundsRuleX, outOfBoundsRuleY; // default Border
+extern glm::vec3 textureBorderColor;       // default black
+extern bool useTextures;                   // default false
 
 struct RenderTimings {
     float gpu_ms = 0.0f;

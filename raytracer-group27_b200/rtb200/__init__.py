@@ -62,6 +62,18 @@ _lib = None
 
 # every symbol include/rt_b200.h declares: (name, restype, argtypes)
 _P, _I, _F = C.c_void_p, C.c_int, C.POINTER(C.c_float)
+class Texture(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("rgb", C.c_void_p)]
+
+
+class TextureParams(C.Structure):
+    _fields_ = [("filtering", C.c_int), ("out_of_bounds_x", C.c_int), ("out_of_bounds_y", C.c_int), ("border_color", C.c_float * 3)]
+
+
+TEX_NEAREST, TEX_BILINEAR = 0, 1
+OOB_BORDER, OOB_CLAMP, OOB_REPEAT = 0, 1, 2
+
+
 class PostParams(C.Structure):
     """rt_post_params: Screen's bloom / tone-mapping / gamma settings (include/rt_b200.h)."""
     _fields_ = [("filtering_option", C.c_int), ("kernel", C.c_int), ("kernel_repetitions", C.c_int), ("filter_size", C.c_int),
@@ -90,6 +102,9 @@ SYMBOLS = [
     ("rt_set_spheres", _I, [_P, _P, _I]),
     ("rt_set_spot_lights", _I, [_P, _P, _I]),
     ("rt_set_plane_lights", _I, [_P, _P, _I]),
+    ("rt_set_texcoords", _I, [_P, _P]),
+    ("rt_set_textures", _I, [_P, C.POINTER(Texture), _I, _P, _I]),
+    ("rt_set_texturing", _I, [_P, C.POINTER(TextureParams)]),
     ("rt_set_postprocess", _I, [_P, C.POINTER(PostParams)]),
     ("rt_postprocess", _I, [_P, C.POINTER(PostParams), _P, _I, _I, _I, _P]),
     ("rt_postprocess_device", _I, [_P, C.POINTER(PostParams), _P, _I, _I]),
@@ -116,6 +131,10 @@ SYMBOLS = [
     ("rt_soup_positions", _P, [_P]),
     ("rt_soup_normals", _P, [_P]),
     ("rt_soup_mesh_ids", _P, [_P]),
+    ("rt_soup_texcoords", _P, [_P]),
+    ("rt_soup_num_textures", _I, [_P]),
+    ("rt_soup_textures", _P, [_P]),
+    ("rt_soup_material_textures", _P, [_P]),
     ("rt_soup_materials", _P, [_P]),
     ("rt_soup_free", None, [_P]),
     ("rt_last_error", C.c_char_p, []),
@@ -160,6 +179,9 @@ class SceneData:
     spheres: np.ndarray = field(default_factory=lambda: np.zeros((0, 12), np.float32))       # centre, radius, kd, ks, shininess, transparency
     spot_lights: np.ndarray = field(default_factory=lambda: np.zeros((0, 10), np.float32))   # position, direction, angle (deg), colour
     plane_lights: np.ndarray = field(default_factory=lambda: np.zeros((0, 12), np.float32))  # position, width, height, colour
+    uv: "np.ndarray | None" = None           # (n, 6) float32: texture coordinates of the three corners
+    textures: list = field(default_factory=list)   # (H, W, 3) uint8 images (top row first), as stbi_load delivers them
+    mesh_tex: "np.ndarray | None" = None     # (m,) int32: texture of each mesh, -1 = none
 
     @property
     def n_tris(self) -> int:
@@ -180,9 +202,20 @@ def load_obj(path: str, normalize: bool = False) -> SceneData:
         raw = np.ctypeslib.as_array(C.cast(l.rt_soup_materials(h), _F), shape=(m, 8)).copy()
         mats = np.zeros(m, MATERIAL_DTYPE)
         mats["kd"], mats["ks"], mats["shininess"], mats["transparency"] = raw[:, 0:3], raw[:, 3:6], raw[:, 6], raw[:, 7]
+        uv = np.ctypeslib.as_array(C.cast(l.rt_soup_texcoords(h), _F), shape=(n, 6)).copy()
+        nt = l.rt_soup_num_textures(h)
+        mesh_tex = np.ctypeslib.as_array(C.cast(l.rt_soup_material_textures(h), C.POINTER(C.c_int)), shape=(m,)).copy().astype(np.int32)
+        textures = []
+        tex_arr = C.cast(l.rt_soup_textures(h), C.POINTER(Texture))
+        for k in range(nt):
+            t = tex_arr[k]
+            texels = np.ctypeslib.as_array(C.cast(t.rgb, _F), shape=(t.height, t.width, 3))
+            textures.append(np.rint(texels * 255.0).astype(np.uint8))   # texels are byte / 255.0f: back to the file's bytes
     finally:
         l.rt_soup_free(h)
-    return SceneData(pos, nrm, ids.astype(np.int32), mats)
+    sc = SceneData(pos, nrm, ids.astype(np.int32), mats)
+    sc.uv, sc.textures, sc.mesh_tex = uv, textures, mesh_tex
+    return sc
 
 
 def make_camera(look_at=(0.0, 0.0, 0.0), euler_deg=(20.0, 20.0, 0.0), dist=3.0, fovy_deg=50.0) -> Camera:
@@ -249,6 +282,33 @@ class Context:
         self.set_spheres(scene.spheres)
         self.set_spot_lights(scene.spot_lights)
         self.set_plane_lights(scene.plane_lights)
+        self.set_texcoords(scene.uv)
+        self.set_textures(scene.textures, scene.mesh_tex)
+
+    def set_texcoords(self, uv=None):
+        if uv is None:
+            _check(self._l.rt_set_texcoords(self._h, None))
+            return
+        uv = _f32(uv).reshape(-1, 6)
+        _check(self._l.rt_set_texcoords(self._h, uv.ctypes.data))
+
+    def set_textures(self, textures=None, mesh_tex=None):
+        """textures: (H, W, 3) uint8 images, converted like Image::Image (byte / 255.0f, src/image.cpp:57-59)."""
+        if not textures:
+            _check(self._l.rt_set_textures(self._h, None, 0, None, 0))
+            return
+        texels = [np.ascontiguousarray(np.asarray(t, np.uint8).astype(np.float32) / np.float32(255.0)) for t in textures]
+        arr = (Texture * len(texels))(*[Texture(t.shape[1], t.shape[0], t.ctypes.data) for t in texels])
+        mt = np.ascontiguousarray(mesh_tex, np.int32)
+        _check(self._l.rt_set_textures(self._h, arr, len(texels), mt.ctypes.data, len(mt)))
+
+    def set_texturing(self, filtering=None, oob_x=OOB_BORDER, oob_y=OOB_BORDER, border=(0.0, 0.0, 0.0)):
+        """useTextures and its knobs (src/main.cpp:54-58) for the following frames; filtering=None switches textures off."""
+        if filtering is None:
+            _check(self._l.rt_set_texturing(self._h, None))
+            return
+        p = TextureParams(int(filtering), int(oob_x), int(oob_y), (C.c_float * 3)(*[float(v) for v in border]))
+        _check(self._l.rt_set_texturing(self._h, C.byref(p)))
 
     def build_bvh(self, mode: int):
         _check(self._l.rt_build_bvh(self._h, mode))

@@ -30,12 +30,17 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 CAM = dict(look_at=(0.0, 0.0, 0.0), euler_deg=(20.0, 20.0, 0.0), dist=3.0, fovy_deg=50.0)  # src/main.cpp:413-414
 
 
-def mint(name, sc, w, h, *, max_level, sphere_rays=10, sample_mode=0, sample_size=4, colour_from="reference", cam=CAM, plane_rays_1d=3):
+def mint(name, sc, w, h, *, max_level, sphere_rays=10, sample_mode=0, sample_size=4, colour_from="reference", cam=CAM, plane_rays_1d=3, tex=None):
+    """tex: dict(filtering, oob_x, oob_y, border) = useTextures on with these knobs (the scene carries uv / textures / mesh_tex)."""
     c = rtb200.make_camera(**cam)
     ref, port = oracle.Oracle("reference"), oracle.Oracle("port")
     for o in (ref, port):
         o.set_spheres(sc.spheres)
         o.set_extra_lights(sc.spot_lights, sc.plane_lights, plane_rays_1d)
+        if tex:
+            o.set_textures(sc.uv, sc.textures, sc.mesh_tex, tex["filtering"], tex["oob_x"], tex["oob_y"], tex["border"])
+        else:
+            o.set_textures()
     kw = dict(max_level=max_level, sphere_rays=sphere_rays, sample_mode=sample_mode, sample_size=sample_size, use_bvh=True)
     r_rgb, r_ids, r_t, r_st = ref.render(sc.pos, sc.nrm, sc.mesh_id, sc.mats, sc.point_lights, sc.sphere_lights, c, w, h, **kw)
     p_rgb, p_ids, p_t, p_st = port.render(sc.pos, sc.nrm, sc.mesh_id, sc.mats, sc.point_lights, sc.sphere_lights, c, w, h, **kw)
@@ -63,8 +68,11 @@ def mint(name, sc, w, h, *, max_level, sphere_rays=10, sample_mode=0, sample_siz
         rgb=rgb, ids=r_ids, t=r_t, ids_x=x_ids,
         primary_rays=st.primary_rays, shadow_queries=st.shadow_queries, secondary_rays=st.secondary_rays,
         rgb_x=x_rgb, primary_rays_x=x_st.primary_rays, shadow_queries_x=x_st.shadow_queries, secondary_rays_x=x_st.secondary_rays,
-        colour_from=colour_from, port_equals_reference=np.array([ids_equal, t_equal, rgb_equal]))
+        colour_from=colour_from, port_equals_reference=np.array([ids_equal, t_equal, rgb_equal]),
+        **(dict(uv=sc.uv, mesh_tex=sc.mesh_tex, n_textures=len(sc.textures), tex_filtering=tex["filtering"], tex_oob_x=tex["oob_x"], tex_oob_y=tex["oob_y"],
+                tex_border=np.array(tex["border"], np.float32), **{f"texture_{k}": t for k, t in enumerate(sc.textures)}) if tex else {}))
     for o in (ref, port):
+        o.set_textures()
         o.set_spheres(None)
         o.set_extra_lights(None, None, 3)
     print(f"{name}: {sc.n_tris} tris {w}x{h} rays={st.rays} port==ref ids/t/rgb={ids_equal}/{t_equal}/{rgb_equal} "
@@ -75,6 +83,25 @@ def mint(name, sc, w, h, *, max_level, sphere_rays=10, sample_mode=0, sample_siz
 def with_lights(sc, point=None, sphere=None):
     sc.point_lights = np.array(point if point is not None else np.zeros((0, 6)), np.float32).reshape(-1, 6)
     sc.sphere_lights = np.array(sphere if sphere is not None else np.zeros((0, 7)), np.float32).reshape(-1, 7)
+    return sc
+
+
+def textured_scene():
+    quad = np.array([[-1.5, -0.6, -1.5, 1.5, -0.6, -1.5, 1.5, -0.6, 1.5], [-1.5, -0.6, -1.5, 1.5, -0.6, 1.5, -1.5, -0.6, 1.5]], np.float32)
+    quv = np.array([[-0.5, -0.5, 1.5, -0.5, 1.5, 1.5], [-0.5, -0.5, 1.5, 1.5, -0.5, 1.5]], np.float32)
+    cube = rtb200.load_obj(DATA + "cube.obj", False)
+    pos = np.concatenate([quad, cube.pos * np.float32(0.4)])
+    nrm = np.concatenate([np.tile([0, 1, 0], (2, 3)).astype(np.float32), cube.nrm])
+    mesh_id = np.concatenate([np.zeros(2, np.int32), cube.mesh_id + 1]).astype(np.int32)
+    mats = np.zeros(1 + len(cube.mats), rtb200.MATERIAL_DTYPE)
+    mats["kd"], mats["transparency"] = 0.7, 1
+    mats["ks"][0], mats["shininess"][0] = 0.3, 5      # the floor mirrors a little: textured hits of reflection rays
+    sc = with_lights(rtb200.SceneData(pos, nrm, mesh_id, mats), point=[[-1, 1, -1, 1, 1, 1]])
+    rng = np.random.default_rng(2)
+    sc.uv = np.concatenate([quv, rng.random((12, 6)).astype(np.float32)])
+    sc.textures = [np.linspace(0, 255, 7 * 5 * 3).reshape(5, 7, 3).astype(np.uint8),
+                   ((np.indices((16, 16)).sum(0) % 2)[..., None] * np.array([245, 190, 30]) + 10).astype(np.uint8)]
+    sc.mesh_tex = np.array([0, 1, -1, 1, -1, 0, 1], np.int32)
     return sc
 
 
@@ -133,6 +160,11 @@ def main():
     # and one transparent material in AndreasScene; geometry through the restated importer
     for nm, fn, w_, h_, lvl in (("andreas_160x120", "AndreasScene.obj", 160, 120, 2), ("catalin_128x96", "CatalinScene.obj", 128, 96, 1), ("mike_128x96", "MikeScene.obj", 128, 96, 1)):
         mint(nm, with_lights(rtb200.load_obj(DATA + fn, True), point=[[-1, 1, -1, 1, 1, 1]]), w_, h_, max_level=lvl, colour_from="port")
+    # textures: a floor quad whose texture coordinates run from -0.5 to 1.5 (every out-of-bounds rule matters) under a cube
+    # with random coordinates; a 7x5 gradient and a 16x16 checker; both filters that need no mip level, four rule pairs
+    for nm, filt, ox, oy in (("tex_nearest_border_96x80", 0, 0, 0), ("tex_bilinear_clamp_repeat_96x80", 1, 1, 2), ("tex_nearest_repeat_clamp_96x80", 0, 2, 1),
+                             ("tex_bilinear_repeat_96x80", 1, 2, 2)):
+        mint(nm, textured_scene(), 96, 80, max_level=2, tex=dict(filtering=filt, oob_x=ox, oob_y=oy, border=(0.2, 0.1, 0.4)))
     # Monkey preset: two point lights (scene.cpp:52-57), mirror-ish material
     mint("monkey_192", with_lights(rtb200.load_obj(DATA + "monkey-rotated.obj", True), point=[[-1, 1, -1, 1, 1, 1], [1, -1, -1, 1, 1, 1]]), 192, 192, max_level=3)
     # Cube preset (every material transparent: d 0.452632)

@@ -46,7 +46,11 @@ def test_golden(rtb, gpu_ctx, name, bvh):
     if not g.geometry_ok:
         pytest.skip("stand-in geometry differs on this host's numpy; covered by test_dragon_live_oracle")
     gpu_ctx.upload_scene(g.scene, rtb.BVH_LBVH_DEVICE if bvh == "lbvh" else rtb.BVH_SAH_HOST)
-    rgb, ids, t, st = gpu_ctx.render(g.camera(), g.params(), want_ids=True)
+    gpu_ctx.set_texturing(**g.tex) if g.tex else gpu_ctx.set_texturing(None)
+    try:
+        rgb, ids, t, st = gpu_ctx.render(g.camera(), g.params(), want_ids=True)
+    finally:
+        gpu_ctx.set_texturing(None)
     _check_against_golden(g, rgb, ids, t, st, f"{name}/{bvh}")
 
 
@@ -341,6 +345,16 @@ int main(int argc, char** argv) {
     std::ofstream f2(argv[3], std::ios::binary);
     f2.write(reinterpret_cast<const char*>(screen.pixels().data()), sizeof(glm::vec3) * screen.pixels().size());
     screen.writeBitmapToFile(argv[4]);                // blooms the pixels once more, then writes 8-bit BGRA (screen.cpp:40-53)
+    // third frame: textures on (the "Use Textures" panel of main.cpp:598-610), bilinear, repeat in x, clamp in y
+    screen.setBloomFilter(FilteringOption::None);
+    scene.pointLights[0].color = glm::vec3(1.0f);
+    useTextures = true;
+    textureFiltering = TextureFiltering::Bilinear;
+    outOfBoundsRuleX = OutOfBoundsRule::Repeat;
+    outOfBoundsRuleY = OutOfBoundsRule::Clamp;
+    renderRayTracing(scene, camera, bvh, screen);
+    std::ofstream f3(argv[5], std::ios::binary);
+    f3.write(reinterpret_cast<const char*>(screen.pixels().data()), sizeof(glm::vec3) * screen.pixels().size());
     return 0;
 }
 """
@@ -357,19 +371,23 @@ def test_cpp_drop_in_renders_the_same_frame(rtb, gpu_ctx, tmp_path):
     obj = ["mtllib custom.mtl", "o box"]
     v = [(x, y, z) for x in (-0.5, 0.5) for y in (-0.5, 0.5) for z in (-0.5, 0.5)]
     obj += [f"v {a} {b} {c}" for a, b, c in v]
+    obj += ["vt 0 0", "vt 1 0", "vt 1 1", "vt 0 1", "vt 2.5 -0.5", "vt -1 2"]
     faces = [(1, 2, 4, 3), (5, 7, 8, 6), (1, 5, 6, 2), (3, 4, 8, 7), (1, 3, 7, 5), (2, 6, 8, 4)]
     for i, f in enumerate(faces):
         obj.append(f"usemtl m{i % 2}")
-        obj.append("f " + " ".join(str(k) for k in f))
-    obj += ["o floor", "v -2 -0.6 -2", "v 2 -0.6 -2", "v 2 -0.6 2", "v -2 -0.6 2", "usemtl m0", "f 9 10 11 12"]
+        obj.append("f " + " ".join(f"{k}/{t}" for k, t in zip(f, (1, 2, 3, 4))))
+    obj += ["o floor", "v -2 -0.6 -2", "v 2 -0.6 -2", "v 2 -0.6 2", "v -2 -0.6 2", "usemtl m0", "f 9/5 10/2 11/6 12/4"]
     (tmp_path / "custom.obj").write_text("\n".join(obj) + "\n")
-    (tmp_path / "custom.mtl").write_text("newmtl m0\nKd 0.7 0.6 0.5\nKs 0.4 0.4 0.4\nNs 20\nnewmtl m1\nKd 0.2 0.5 0.8\nKs 0 0 0\nNs 5\n")
+    (tmp_path / "custom.mtl").write_text("newmtl m0\nKd 0.7 0.6 0.5\nKs 0.4 0.4 0.4\nNs 20\nmap_Kd tiles.png\nnewmtl m1\nKd 0.2 0.5 0.8\nKs 0 0 0\nNs 5\n")
+    from util import write_png
+    write_png(tmp_path / "tiles.png", np.random.default_rng(8).integers(0, 256, (8, 8, 3)), 2)
     (tmp_path / "r.cpp").write_text(CPP_RENDER)
     exe = tmp_path / "r"
     r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", f"-I{host}", f"-I{os.path.join(root, 'include')}", str(tmp_path / "r.cpp"), "-o", str(exe),
                         f"-L{lib}", "-lrtb200", f"-Wl,-rpath,{lib}"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    r = subprocess.run([str(exe), str(tmp_path), str(tmp_path / "frame.bin"), str(tmp_path / "frame2.bin"), str(tmp_path / "render.bmp")], capture_output=True, text=True)
+    r = subprocess.run([str(exe), str(tmp_path), str(tmp_path / "frame.bin"), str(tmp_path / "frame2.bin"), str(tmp_path / "render.bmp"),
+                        str(tmp_path / "frame3.bin")], capture_output=True, text=True)
     assert r.returncode == 0, (r.stdout, r.stderr)
     cpp = np.fromfile(tmp_path / "frame.bin", np.float32).reshape(256, 256, 3)
     sc = rtb.load_obj(str(tmp_path / "custom.obj"))
@@ -399,3 +417,21 @@ def test_cpp_drop_in_renders_the_same_frame(rtb, gpu_ctx, tmp_path):
     assert bmp[:2].tobytes() == b"BM" and len(bmp) == 54 + 256 * 256 * 4
     px = bmp[54:].reshape(256, 256, 4)[::-1]           # bottom-up rows, BGRA
     assert np.array_equal(px[..., [2, 1, 0, 3]], rgba)
+    # third frame: the OBJ's texture (map_Kd, decoded by the host importer) through the device sampler, against the CPU port
+    assert len(sc.textures) == 1 and sc.textures[0].shape == (8, 8, 3) and list(sc.mesh_tex).count(0) >= 1
+    sc.point_lights = np.array([[-1, 1, -1, 1, 1, 1]], np.float32)
+    gpu_ctx.upload_scene(sc, rtb.BVH_LBVH_DEVICE)
+    gpu_ctx.set_texturing(rtb.TEX_BILINEAR, rtb.OOB_REPEAT, rtb.OOB_CLAMP)
+    try:
+        tex_py, _, _, _ = gpu_ctx.render(rtb.make_camera(), rtb.make_params(256, 256, 3), want_ids=True)
+    finally:
+        gpu_ctx.set_texturing(None)
+    cpp3 = np.fromfile(tmp_path / "frame3.bin", np.float32).reshape(256, 256, 3)
+    assert np.abs(cpp3 - tex_py).max() <= 1e-6
+    assert np.abs(cpp3 - cpp).max() > 0.1               # the texture is visible
+    port.set_textures(sc.uv, sc.textures, sc.mesh_tex, oracle.TEX_BILINEAR, oracle.OOB_REPEAT, oracle.OOB_CLAMP)
+    try:
+        o_rgb, _, _, _ = port.render(sc.pos, sc.nrm, sc.mesh_id, sc.mats, sc.point_lights, None, rtb.make_camera(), 256, 256, max_level=3, shadow_exhaustive=True)
+    finally:
+        port.set_textures()
+    assert np.abs(cpp3 - o_rgb).max() <= COLOUR_TOL

@@ -227,3 +227,52 @@ def test_importer_on_every_reference_obj(rtb):
         assert np.all((np.abs(nn - 1) < 1e-3) | (nn == 0) | ~np.isfinite(nn)), f"{n}: normals are not unit length"
         scn = rtb.load_obj(os.path.join(data, n), normalize=True)
         assert np.linalg.norm(scn.pos.reshape(-1, 3), axis=1).max() == pytest.approx(1.0, abs=2e-6), n
+
+
+TEX_OBJ = """mtllib t.mtl
+v 0 0 0
+v 1 0 0
+v 0 1 0
+vt 0.25 0.5
+vt 1.5 -0.25
+vt 0 1
+usemtl m
+f 1/1 2/2 3/3
+"""
+
+
+def _load_textured(rtb, tmp_path, png_name):
+    (tmp_path / "t.obj").write_text(TEX_OBJ)
+    (tmp_path / "t.mtl").write_text(f"newmtl m\nKd 1 1 1\nmap_Kd {png_name}\n")
+    return rtb.load_obj(str(tmp_path / "t.obj"))
+
+
+def test_png_textures_decode_like_the_reference_image_reader(rtb, tmp_path):
+    """Image::Image asks its image reader for 8-bit RGB (src/image.cpp:45): palette entries expanded, 16-bit samples reduced to
+    their high byte, alpha dropped; files with fewer than 3 channels are refused (src/image.cpp:47-50).  Every scanline filter
+    type and split IDAT chunks are covered by the writer."""
+    from util import write_png
+    rng = np.random.default_rng(4)
+    rgb = rng.integers(0, 256, (13, 9, 3))
+    write_png(tmp_path / "rgb8.png", rgb, 2)
+    sc = _load_textured(rtb, tmp_path, "rgb8.png")
+    assert np.array_equal(sc.textures[0], rgb) and list(sc.mesh_tex) == [0]
+    np.testing.assert_array_equal(sc.uv, [[0.25, 0.5, 1.5, -0.25, 0, 1]])        # vt kept as written (no v flip)
+    rgba = rng.integers(0, 256, (6, 11, 4))
+    write_png(tmp_path / "rgba8.png", rgba, 6)
+    assert np.array_equal(_load_textured(rtb, tmp_path, "rgba8.png").textures[0], rgba[..., :3])
+    rgb16 = rng.integers(0, 65536, (5, 4, 3))
+    write_png(tmp_path / "rgb16.png", rgb16, 2, depth=16)
+    assert np.array_equal(_load_textured(rtb, tmp_path, "rgb16.png").textures[0], rgb16 >> 8)
+    for depth in (1, 2, 4, 8):
+        pal = rng.integers(0, 256, (1 << depth, 3))
+        idx = rng.integers(0, 1 << depth, (7, 10, 1))
+        write_png(tmp_path / f"pal{depth}.png", idx, 3, depth=depth, palette=pal)
+        assert np.array_equal(_load_textured(rtb, tmp_path, f"pal{depth}.png").textures[0], pal[idx[..., 0]]), depth
+    # grey: one channel -> refused like the reference does; loadMesh reports it and keeps the material's kd
+    write_png(tmp_path / "grey.png", rng.integers(0, 256, (4, 4, 1)), 0)
+    sc = _load_textured(rtb, tmp_path, "grey.png")
+    assert sc.textures == [] and list(sc.mesh_tex) == [-1]
+    # a file the MTL names but that is not there (the reference snapshot lacks two of its texture blobs)
+    sc = _load_textured(rtb, tmp_path, "nowhere.png")
+    assert sc.textures == [] and sc.n_tris == 1

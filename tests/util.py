@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 GOLDEN_NAMES = ["cornell_planelight_160", "cornell_planelight_inside_96", "cube_preset_spot_128", "monkey_spots_128", "cornell_preset_sphere_192", "spheres_preset_160", "cornell_c1_256", "cornell_c4_96", "cornell_sph10_aa_80x48", "cornell_ms16_70x45", "cornell_inside_128", "monkey_192",
-                "cube_96", "zfight_96", "andreas_160x120", "catalin_128x96", "mike_128x96", "tr_def_96", "teapot_c2_256x144", "teapot_d3_128x72", "dragon_standin_c3_160x90"]
+                "cube_96", "zfight_96", "tex_nearest_border_96x80", "tex_bilinear_clamp_repeat_96x80", "tex_nearest_repeat_clamp_96x80", "tex_bilinear_repeat_96x80", "andreas_160x120", "catalin_128x96", "mike_128x96", "tr_def_96", "teapot_c2_256x144", "teapot_d3_128x72", "dragon_standin_c3_160x90"]
 
 
 # Screen settings exercised by the post-processing fixture (tests/golden/make_golden_post.py) and the GPU tests; keyword
@@ -52,12 +52,17 @@ class Golden:
         self.cam_kw = dict(look_at=tuple(float(v) for v in d["cam_look_at"]), euler_deg=tuple(float(v) for v in d["cam_euler_deg"]),
                            dist=float(d["cam_dist"]), fovy_deg=float(d["cam_fovy_deg"]))
         self.geometry_ok = True
+        # useTextures and its knobs (None: textures off, the reference's default)
+        self.tex = dict(filtering=int(d["tex_filtering"]), oob_x=int(d["tex_oob_x"]), oob_y=int(d["tex_oob_y"]), border=tuple(float(v) for v in d["tex_border"])) if "tex_filtering" in d else None
         if "pos" in d:
             self.scene = rtb200.SceneData(d["pos"], d["nrm"], d["mesh_id"], d["mats"], d["point_lights"], d["sphere_lights"])
             if "spheres" in d:
                 self.scene.spheres = d["spheres"]
             if "spot_lights" in d:
                 self.scene.spot_lights, self.scene.plane_lights = d["spot_lights"], d["plane_lights"]
+            if "uv" in d:
+                self.scene.uv, self.scene.mesh_tex = d["uv"], d["mesh_tex"]
+                self.scene.textures = [d[f"texture_{k}"] for k in range(int(d["n_textures"]))]
         else:  # dragon stand-in: geometry is regenerated, the fixture only carries a checksum
             from rtb200 import standin
             sc = standin.dragon_standin_scene()
@@ -80,6 +85,10 @@ class Golden:
         s = self.scene
         o.set_spheres(s.spheres)
         o.set_extra_lights(s.spot_lights, s.plane_lights, self.plane_rays_1d)
+        if self.tex:
+            o.set_textures(s.uv, s.textures, s.mesh_tex, self.tex["filtering"], self.tex["oob_x"], self.tex["oob_y"], self.tex["border"])
+        else:
+            o.set_textures()
         return o.render(s.pos, s.nrm, s.mesh_id, s.mats, s.point_lights, s.sphere_lights, self.camera(), self.w, self.h, max_level=self.max_level,
                         sphere_rays=self.sphere_rays, sample_mode=self.sample_mode, sample_size=self.sample_size, **kw)
 
@@ -90,3 +99,55 @@ def id_mismatch_fraction(a, b):
 
 def bits_equal(a, b):
     return bool(np.array_equal(np.ascontiguousarray(a).view(np.int32), np.ascontiguousarray(b).view(np.int32)))
+
+
+def write_png(path, samples, ctype, depth=8, palette=None, trns=False):
+    """Minimal PNG writer for importer tests: `samples` is (H, W, S) integers with S samples per pixel of `depth` bits
+    (palette indices for ctype 3); scanlines cycle through the five PNG filter types so the reader's unfiltering is exercised."""
+    import struct
+    import zlib
+    samples = np.asarray(samples)
+    h, w, s = samples.shape
+    if depth == 16:
+        row_bytes = np.stack([samples >> 8, samples & 255], axis=-1).reshape(h, -1).astype(np.uint8)
+    elif depth == 8:
+        row_bytes = samples.reshape(h, -1).astype(np.uint8)
+    else:
+        bits = ((samples.reshape(h, -1)[..., None] >> np.arange(depth - 1, -1, -1)) & 1).reshape(h, -1).astype(np.uint8)
+        pad = (-bits.shape[1]) % 8
+        row_bytes = np.packbits(np.pad(bits, ((0, 0), (0, pad))), axis=1)
+    bpp = max(1, s * depth // 8)
+    raw = bytearray()
+    prev = np.zeros(row_bytes.shape[1], np.int32)
+    for y in range(h):
+        cur = row_bytes[y].astype(np.int32)
+        ft = y % 5
+        a = np.concatenate([np.zeros(bpp, np.int32), cur[:-bpp]]) if len(cur) > bpp else np.zeros_like(cur)
+        c = np.concatenate([np.zeros(bpp, np.int32), prev[:-bpp]]) if len(cur) > bpp else np.zeros_like(cur)
+        if ft == 0:
+            pred = 0
+        elif ft == 1:
+            pred = a
+        elif ft == 2:
+            pred = prev
+        elif ft == 3:
+            pred = (a + prev) // 2
+        else:
+            p = a + prev - c
+            pa, pb, pc = np.abs(p - a), np.abs(p - prev), np.abs(p - c)
+            pred = np.where((pa <= pb) & (pa <= pc), a, np.where(pb <= pc, prev, c))
+        raw.append(ft)
+        raw += bytes(((cur - pred) & 255).astype(np.uint8))
+        prev = cur
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xffffffff)
+    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 0))
+    if palette is not None:
+        out += chunk(b"PLTE", bytes(np.asarray(palette, np.uint8).reshape(-1)))
+    if trns:
+        out += chunk(b"tRNS", bytes([0, 255]))
+    comp = zlib.compress(bytes(raw), 6)
+    out += chunk(b"IDAT", comp[: len(comp) // 2]) + chunk(b"IDAT", comp[len(comp) // 2:]) + chunk(b"IEND", b"")
+    with open(path, "wb") as f:
+        f.write(out)
