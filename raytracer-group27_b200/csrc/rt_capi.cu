@@ -1,6 +1,9 @@
 // extern "C" layer of the B200 ray-tracing path (include/rt_b200.h): context, device memory, frame orchestration.
 #include "rt_b200.h"
 #include "rt_kernels.h"
+#ifndef RT_BVH_WIDE
+#define RT_BVH_WIDE 0
+#endif
 
 #include "../host/mesh.h"
 
@@ -76,6 +79,7 @@ struct rt_ctx {
     DevBuf<float4> d_plane, d_v0, d_v1, d_v2, d_n0, d_n1, d_n2, d_nodes, d_mats, d_point, d_sphere;
     float4* lbvh_nodes = nullptr; // owned when the device builder allocated them
     int* lbvh_perm = nullptr;
+    float4* wide_nodes = nullptr; // 4-wide tree collapsed from the builder's binary one (RT_BVH_WIDE builds)
     const float4* nodes = nullptr;
     int n_nodes = 0, root_entry = 0, bvh_depth = 0;
     bool bvh_built = false;
@@ -830,6 +834,8 @@ int rt_destroy(rt_ctx* ctx)
         cudaFree(ctx->lbvh_nodes);
     if (ctx->lbvh_perm)
         cudaFree(ctx->lbvh_perm);
+    if (ctx->wide_nodes)
+        cudaFree(ctx->wide_nodes);
     if (ctx->h_counters)
         cudaFreeHost(ctx->h_counters);
     for (cudaEvent_t e : ctx->ev_pool)
@@ -1025,6 +1031,33 @@ int rt_build_bvh(rt_ctx* ctx, int mode)
     } else {
         return fail(RT_ERR_INVALID, "rt_build_bvh: unknown mode");
     }
+#if RT_BVH_WIDE
+    {
+        if (ctx->wide_nodes)
+            cudaFree(ctx->wide_nodes);
+        ctx->wide_nodes = nullptr;
+        WideBvh w;
+        const char* err = nullptr;
+        if (collapse_bvh_wide_device(ctx->stream, ctx->nodes, ctx->n_nodes, ctx->root_entry, &w, &err) != 0)
+            return fail(RT_ERR_CUDA, std::string("rt_build_bvh (4-wide collapse): ") + (err ? err : "failed"));
+        if (3 * w.depth + 1 >= kStackDepth) { // a node step pushes up to three entries
+            cudaFree(w.nodes);
+            return fail(RT_ERR_INVALID, "rt_build_bvh: 4-wide tree deeper than the traversal stack");
+        }
+        ctx->wide_nodes = w.nodes;
+        if (w.nodes) {
+            ctx->nodes = w.nodes;
+            ctx->n_nodes = w.n_nodes;
+            ctx->bvh_depth = w.depth;
+        }
+        ctx->root_entry = w.root_entry;
+        // the binary tree is no longer needed
+        if (ctx->lbvh_nodes) {
+            cudaFree(ctx->lbvh_nodes);
+            ctx->lbvh_nodes = nullptr;
+        }
+    }
+#endif
     launch_tri_setup(ctx->stream, ctx->d_pos.p, ctx->d_nrm.p, ctx->d_mesh.p, perm, (int)ctx->n_tris, ctx->d_plane.p, ctx->d_v0.p, ctx->d_v1.p,
         ctx->d_v2.p, ctx->d_n0.p, ctx->d_n1.p, ctx->d_n2.p);
     CK(cudaGetLastError());

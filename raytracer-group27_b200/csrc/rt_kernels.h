@@ -51,6 +51,15 @@ void launch_post_gamma(cudaStream_t st, int sm_count, float4* img, size_t n, flo
 void launch_post_rgba8(cudaStream_t st, int sm_count, const float4* img, unsigned char* out, size_t n);
 void launch_unpack_rgb(cudaStream_t st, int sm_count, const float* in, float4* out, size_t n);
 
+// 4-wide BVH collapsed from the binary one (rt_wide.cu).  nodes: 8 x float4 per node; allocated by the callee (cudaMalloc).
+struct WideBvh {
+    float4* nodes = nullptr;
+    int n_nodes = 0;
+    int root_entry = 0; // node index, or the leaf encoding when the whole scene is one leaf
+    int depth = 0;
+};
+int collapse_bvh_wide_device(cudaStream_t st, const float4* d_nodes2, int n_nodes2, int root_entry2, WideBvh* out, const char** err);
+
 // Visiting rank of every object (triangles 0..n_tris-1, then spheres) in the reference's own BVH (rt_reforder.cu): the tie key
 // of the traversal kernels.  d_spheres: 3 x float4 per sphere ({centre, radius} first).  d_rank: n_tris + n_spheres ints.
 int reference_visit_rank(cudaStream_t st, const float* d_pos, long long n_tris, const float4* d_spheres, int n_spheres, int* d_rank, const char** err);

@@ -210,9 +210,72 @@ __device__ __forceinline__ int trav_pop(Trav& tv, const int* stack)
 #endif
 }
 
+#ifndef RT_BVH_WIDE
+#define RT_BVH_WIDE 0
+#endif
+
+#if RT_BVH_WIDE
+// One node step of the 4-wide tree (rt_wide.cu): fetch the 128-byte node `tv.cur`, slab-test its four boxes, go on with the
+// nearest hit child and push the others, farthest first; or pop.  An any-hit query does not care about the order.
+template <bool ANYHIT, bool COUNT>
+__device__ __forceinline__ void trav_node_step(const SceneDev& s, Trav& tv, int* stack, TraceStats& st)
+{
+    const float4* np = s.nodes + 8 * (size_t)tv.cur;
+    const float4 lx = __ldg(np), ly = __ldg(np + 1), lz = __ldg(np + 2), hx = __ldg(np + 3), hy = __ldg(np + 4), hz = __ldg(np + 5);
+    const float4 eb = __ldg(np + 6);
+    if (COUNT)
+        st.nodes += 4;
+    float key[4];
+    int e[4] = { __float_as_int(eb.x), __float_as_int(eb.y), __float_as_int(eb.z), __float_as_int(eb.w) };
+    int n = 0;
+#define RT_SLAB4(k, c)                                                                                                                  \
+    {                                                                                                                                   \
+        const float nx = fmaf(lx.c, tv.nlx, fmaf(hx.c, tv.nhx, -tv.oix)), fx = fmaf(lx.c, tv.nhx, fmaf(hx.c, tv.nlx, -tv.oix));           \
+        const float ny = fmaf(ly.c, tv.nly, fmaf(hy.c, tv.nhy, -tv.oiy)), fy = fmaf(ly.c, tv.nhy, fmaf(hy.c, tv.nly, -tv.oiy));           \
+        const float nz = fmaf(lz.c, tv.nlz, fmaf(hz.c, tv.nhz, -tv.oiz)), fz = fmaf(lz.c, tv.nhz, fmaf(hz.c, tv.nlz, -tv.oiz));           \
+        const float tn = fmaxf(fmaxf(fmaxf(nx, ny), nz), 0.0f), tf = fminf(fminf(fminf(fx, fy), fz), tv.tlimit);                        \
+        const bool hit = tn <= tf * 1.0000005f;                                                                                         \
+        key[k] = hit ? tn : INFINITY;                                                                                                   \
+        n += hit ? 1 : 0;                                                                                                               \
+    }
+    RT_SLAB4(0, x)
+    RT_SLAB4(1, y)
+    RT_SLAB4(2, z)
+    RT_SLAB4(3, w)
+#undef RT_SLAB4
+    if (n == 0) {
+        tv.cur = trav_pop(tv, stack);
+        return;
+    }
+    // sort the four (key, entry) pairs by key; missed boxes carry +inf and end up behind the hits
+#define RT_CSWAP(a, b)                          \
+    {                                           \
+        const bool sw = key[b] < key[a];        \
+        const float ka = key[a], kb = key[b];   \
+        const int ea = e[a], eb_ = e[b];        \
+        key[a] = sw ? kb : ka;                  \
+        key[b] = sw ? ka : kb;                  \
+        e[a] = sw ? eb_ : ea;                   \
+        e[b] = sw ? ea : eb_;                   \
+    }
+    RT_CSWAP(0, 1)
+    RT_CSWAP(2, 3)
+    RT_CSWAP(0, 2)
+    RT_CSWAP(1, 3)
+    RT_CSWAP(1, 2)
+#undef RT_CSWAP
+    if (n > 3)
+        stack[tv.sp++] = e[3];
+    if (n > 2)
+        stack[tv.sp++] = e[2];
+    if (n > 1)
+        stack[tv.sp++] = e[1];
+    tv.cur = e[0];
+}
+#else
 // One node step: fetch the sibling pair `tv.cur` (one aligned 64-byte read), slab-test both boxes, descend into the
 // nearer hit child and push the other one, or pop.
-template <bool COUNT>
+template <bool ANYHIT, bool COUNT>
 __device__ __forceinline__ void trav_node_step(const SceneDev& s, Trav& tv, int* stack, TraceStats& st)
 {
     const float4* np = s.nodes + 2 * (size_t)tv.cur;
@@ -249,6 +312,7 @@ __device__ __forceinline__ void trav_node_step(const SceneDev& s, Trav& tv, int*
         tv.cur = trav_pop(tv, stack);
     }
 }
+#endif
 
 // Test the triangles of leaf entry `leaf`; the walk state (tv.cur, stack) is untouched unless an any-hit query is
 // satisfied, which drops all remaining work.
@@ -348,7 +412,7 @@ __device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, b
             while (tv.cur != kTravDone || parked != kTravDone) {
                 bool searching = parked == kTravDone;
                 while (tv.cur >= 0) {
-                    trav_node_step<COUNT>(s, tv, stack, st);
+                    trav_node_step<ANYHIT, COUNT>(s, tv, stack, st);
                     if (tv.cur < 0 && tv.cur != kTravDone && parked == kTravDone) {
                         parked = tv.cur;
                         tv.cur = trav_pop(tv, stack);
@@ -394,7 +458,7 @@ __device__ __forceinline__ void trace_bvh(const SceneDev& s, int root_entry, con
     trav_start<ANYHIT>(s, tv, o, d, best, root_entry);
     while (tv.cur != kTravDone) {
         if (tv.cur >= 0) {
-            trav_node_step<COUNT>(s, tv, stack, st);
+            trav_node_step<ANYHIT, COUNT>(s, tv, stack, st);
         } else {
             const int leaf = tv.cur;
             tv.cur = trav_pop(tv, stack);
