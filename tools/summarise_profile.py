@@ -15,8 +15,11 @@ ki, vi, gi, bi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index(
 out = [f"# {tag}: ncu --metrics gpu__time_duration.sum --clock-control none, tools/profile_frame.py 3 (C3 stand-in 3840x2160 depth 3, SAH BVH, one batch per frame)",
        "# per-launch device time in us (cold-cache, serialised: compare SHARES)", "id,kernel,grid,block,us"]
 agg, tot = collections.OrderedDict(), 0.0
+FRAME_KERNELS = ("k_level_reset", "k_extend", "k_shade", "k_shadow", "k_sphere_finalize", "k_plane_finalize", "k_resolve", "k_pack_rgb", "k_post")
 for r in rows[1:]:
     n = r[ki].split("(")[0].replace("void ", "").replace("rtb::", "")
+    if not n.startswith(FRAME_KERNELS):   # scene upload / BVH build / tie-key kernels run once, before the frames
+        continue
     v = float(r[vi].replace(",", "")) / 1e3
     out.append(f"{r[0]},{n},{r[gi].strip()},{r[bi].strip()},{v:.1f}")
     agg.setdefault(n, [0.0, 0])
