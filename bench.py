@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200 ray-tracing path (contract: see the task brief / DESIGN.md §Measurement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c1|c2|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c1|c2|c4|c5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 One step = one frame of the workload (generate -> extend/shade/shadow per bounce -> resolve, plus the tile gather at
@@ -36,6 +36,7 @@ WORKLOADS = {
     "c1": ("CornellBox-Mirror-Rotated.obj 1024x1024, 1 point light, hard shadows, reflection depth 3, 1 spp", 1024, 1024, 3, 10),
     "c2": ("teapot.obj 1920x1080 Phong + hard shadows (depth 0)", 1920, 1080, 0, 10),
     "c4": ("CornellBox-Mirror-Rotated.obj 2048x2048 spherical-light soft shadows, 64 samples per hit, depth 5", 2048, 2048, 5, 64),
+    "c5": ("8x8x8 lattice of the dragon STAND-IN flattened to one mesh (44.5 M tris), 7680x4320, multipleRays 16 spp, 1 point light, reflection depth 3", 7680, 4320, 3, 10),
 }
 
 
@@ -45,6 +46,8 @@ def load_workload(name):
     desc, w, h, depth, srays = WORKLOADS[name]
     if name == "c3":
         sc = standin.dragon_standin_scene()
+    elif name == "c5":  # BASELINE.json configs[4]; device LBVH (a host SAH build of 44.5 M triangles takes half a minute)
+        return desc, standin.dragon_lattice_scene(), rtb200.make_camera(), rtb200.make_params(w, h, depth, srays, sample_mode=2, sample_size=16)
     else:  # geometry of the reference's assets travels inside the golden fixtures (tests/golden/make_golden.py)
         fixture = {"c1": "cornell_c1_256", "c2": "teapot_c2_256x144", "c4": "cornell_c4_96"}[name]
         d = np.load(os.path.join(ROOT, "tests", "golden", fixture + ".npz"))
@@ -191,6 +194,8 @@ def run_gpu(args):
     stream = torch.cuda.Stream()
     ctx = rtb200.Context(local_rank)
     ctx.set_stream(stream.cuda_stream)
+    if args.workload == "c5":
+        args.bvh, args.no_cpu_baseline = "lbvh", True   # the CPU reference needs ~10 GB and seconds per ray on this mesh
     bvh_mode = rtb200.BVH_SAH_HOST if args.bvh == "sah" else rtb200.BVH_LBVH_DEVICE
     t0 = time.perf_counter()
     ctx.upload_scene(sc, bvh_mode)
@@ -331,7 +336,7 @@ def run_gpu(args):
     ctx.set_counters(False)
     ctx.set_pipeline(0, 1)
     ctx.set_overlap(True)
-    roof = roofline(stage, c, prm)
+    roof = roofline(stage, c, prm, args.workload)
 
     line = None
     if rank == 0:
@@ -343,7 +348,7 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic (procedural dragon stand-in; data/dragon.obj is absent from the reference tree)" if args.workload == "c3" else "reference asset (from tests/golden)",
+            "data": "synthetic (procedural dragon stand-in; data/dragon.obj is absent from the reference tree)" if args.workload in ("c3", "c5") else "reference asset (from tests/golden)",
             "config": {"workload": desc, "bvh": args.bvh, "bvh_build_ms": build_ms, "sharding": f"interleaved 32x16 tiles over {world} GPU(s), scene replicated",
                        "gather": gather, "l2": "flushed between timed steps (512 MiB memset outside the event pair)",
                        "rays_per_frame": {"primary": int(st.primary_rays), "shadow": int(st.shadow_queries), "secondary": int(st.secondary_rays)} if world == 1 else int(total_rays / args.steps)},
@@ -373,7 +378,7 @@ def _as_tensor(torch, ptr, n_floats):
     return torch.as_tensor(h, device="cuda")
 
 
-def roofline(stage, c, prm):
+def roofline(stage, c, prm, workload="c3"):
     """Roofline of the dominant kernel.  Algorithmic bytes per ray follow SURVEY §8(d): 32 B per BVH node fetched +
     64 B per triangle fetched + the ray's own record traffic; flops per ray: 24 per box test, 12 per plane stage,
     57 per full triangle stage (+ fixed part).  Node / triangle counts are measured by the instrumented kernels."""
@@ -395,7 +400,7 @@ def roofline(stage, c, prm):
     k = kernels[name]
     total_ms = sum(v[0] for v in stage.values())
     achieved = k["bytes"] / max(k["ms"], 1e-9) / 1e6  # GB/s
-    traffic = ncu_traffic().get(name)
+    traffic = ncu_traffic().get(name) if workload == "c3" else None  # the committed ncu capture is of the C3 frame
     fp32_nominal = 148 * 128 * 1.965e9  # FP32 instructions/s (non-FMA path: one flop per instruction)
     return {"bound": "hbm", "kernel": "k_" + name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "peak_source": peak_src, "launches_per_step": k["launches"], "avg_launch_ms": k["ms"] / max(1, k["launches"]),
