@@ -520,14 +520,14 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids
     const size_t unit = (fp.world == 1 ? (size_t)fp.tiles_x : 1) * kTilePixels;
     // Automatic pipeline shape (rt_set_pipeline(0, ...)), from measurements on C3 (profiles/README.md): every extra
     // sequential batch costs about 0.4 ms of latency-bound deep levels, so a device-resident frame is cut in two
-    // concurrent halves at most; when rows have to travel to the host, three bands on two lanes let the first bands'
-    // download overlap the last band's rendering.
+    // concurrent halves at most; when rows have to travel to the host, six bands on three lanes let the first bands'
+    // download overlap the later bands' rendering (C3 through rt_render: 1x1 4.10, 2x3 3.55, 3x6 3.48, 4x8 3.72 ms).
     int lanes_wanted = ctx->n_lanes, batches_auto = ctx->batches_per_frame;
     if (lanes_wanted <= 0) {
         const bool big = n_local >= ((size_t)1 << 22);
         if (host && host->rgb && fp.world == 1 && !(ctx->post_on && post_has_effect(ctx->post))) {
-            lanes_wanted = big ? 2 : 1;
-            batches_auto = big ? 3 : 1;
+            lanes_wanted = big ? 3 : 1;
+            batches_auto = big ? 6 : 1;
         } else {
             lanes_wanted = big ? 2 : 1;
             batches_auto = big ? 2 : 1;
