@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_extend(
 // (src/main.cpp:112-121) folded into per-light coefficients, and the spawn of mirror (191-256 with
 // glossy_ray_count == 1 => weight ks*ks) and dielectric (257-290) children with a throughput instead of recursion.
 // One thread per ray slot; output queues are filled through block-aggregated ballot compaction.
-template <bool LEVEL0>
+template <bool LEVEL0, bool TEXTURED>
 __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams fp, BatchDev b, int qi, int level, unsigned first_lp)
 {
     __shared__ unsigned smem[2][kShadeBlock / 32 + 1];
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
                 refl = xreflect(dn, Nn); // main.cpp:141
             }
         }
-        const f3 kd = hit ? diffuse_colour(s, fp, sh) : mk3(sh.m0), ks = mk3(sh.m1);
+        const f3 kd = (TEXTURED && hit) ? diffuse_colour(s, fp, sh) : mk3(sh.m0), ks = mk3(sh.m1);
         const float shininess = sh.m0.w, transparency = sh.m1.w;
 
         // children
@@ -896,10 +896,18 @@ void launch_extend(cudaStream_t st, int sm_count, const SceneDev& s, int root_en
 
 void launch_shade(cudaStream_t st, int sm_count, const SceneDev& s, const FrameParams& fp, const BatchDev& b, int qi, int level, unsigned first_lp)
 {
-    if (level == 0)
-        k_shade<true><<<sm_count * 8, kShadeBlock, 0, st>>>(s, fp, b, qi, level, first_lp);
-    else
-        k_shade<false><<<sm_count * 4, kShadeBlock, 0, st>>>(s, fp, b, qi, level, first_lp);
+    // the texture branch (diffuse_colour) is compiled out of the kernels used when useTextures is off
+    if (level == 0) {
+        if (fp.tex_on)
+            k_shade<true, true><<<sm_count * 8, kShadeBlock, 0, st>>>(s, fp, b, qi, level, first_lp);
+        else
+            k_shade<true, false><<<sm_count * 8, kShadeBlock, 0, st>>>(s, fp, b, qi, level, first_lp);
+    } else {
+        if (fp.tex_on)
+            k_shade<false, true><<<sm_count * 4, kShadeBlock, 0, st>>>(s, fp, b, qi, level, first_lp);
+        else
+            k_shade<false, false><<<sm_count * 4, kShadeBlock, 0, st>>>(s, fp, b, qi, level, first_lp);
+    }
 }
 
 void launch_shadow_point(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count)
