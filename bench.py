@@ -273,6 +273,8 @@ def run_gpu(args):
         wall_ms = 1e3 * (time.perf_counter() - wall0)
         clocks = sampler.finish()
     step_ms = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device="cuda")
+    if os.environ.get("RTB200_BENCH_VERBOSE"):
+        sys.stderr.write(f"[rank {rank}] mean device ms per step {float(step_ms.mean().item()):.3f}, rays per step {stats[-1].rays}\n")
     rays = torch.tensor([float(s.rays) for s in stats], dtype=torch.float64, device="cuda")
     launches = sum(s.kernel_launches for s in stats)
     if world > 1:
