@@ -1,4 +1,5 @@
 #include "screen.h"
+#include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdint>
 #include <fstream>
@@ -19,12 +20,18 @@ void Screen::setPixel(int x, int y, const glm::vec3& color)
 }
 
 namespace {
-// Screen has no link to a BoundingVolumeHierarchy, so its own post-processing calls share one lazily created context.
+// Screen has no link to a BoundingVolumeHierarchy, so its own post-processing calls share one lazily created context,
+// on the CUDA device that is current for the calling thread at that moment (device 0 unless the caller chose another).
 rt_ctx* postContext()
 {
     static rt_ctx* ctx = nullptr;
-    if (!ctx && rt_create(0, &ctx) != RT_OK)
-        throw std::runtime_error(std::string("Screen: ") + rt_last_error());
+    if (!ctx) {
+        int device = 0;
+        if (cudaGetDevice(&device) != cudaSuccess)
+            device = 0;
+        if (rt_create(device, &ctx) != RT_OK)
+            throw std::runtime_error(std::string("Screen: ") + rt_last_error());
+    }
     return ctx;
 }
 }
