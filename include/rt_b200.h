@@ -57,7 +57,10 @@ typedef struct {
     int width, height;          /* windowResolution, src/main.cpp:33 (parameterised)                    */
     int max_reflection_level;   /* src/main.cpp:123                                                     */
     int sphere_light_ray_count; /* src/main.cpp:124                                                     */
-    int glossy_ray_count;       /* src/main.cpp:126; only 1 is accepted (rand() glossy rays: out of scope) */
+    int glossy_ray_count;       /* src/main.cpp:126, 1..40.  1: mirror ray only — the setting every parity bar is
+                                   defined on.  > 1: glossy rays (main.cpp:204-250) whose directions come from a
+                                   DEFINED counter-based stream (csrc/rt_kernels.cu, path_uniform): the reference
+                                   draws them from rand(), shared by its threads, and has no reproducible answer */
     float refraction_factor;    /* src/main.cpp:127                                                     */
     int sample_mode;            /* 0: one ray per pixel; 1: anti_aliasing (4 taps); 2: multipleRays     */
     int sample_size;            /* 4 / 16 / 64 when sample_mode == 2                                    */

@@ -81,7 +81,7 @@ class Oracle:
 
     def render(self, pos, nrm, mesh_id, mats, point_lights, sphere_lights, cam, width, height, max_level=5, sphere_rays=10,
                refraction=0.8, use_bvh=True, sample_mode=0, sample_size=4, defined_bary=True, want_ids=True, want_rgb=True,
-               x0=0, y0=0, x_step=1, y_step=1, num_threads=0, shadow_exhaustive=False):
+               x0=0, y0=0, x_step=1, y_step=1, num_threads=0, shadow_exhaustive=False, glossy_rays=1):
         """cam: dict(look_at, euler (radians), dist, fovy (radians)) or an object with those attributes."""
         pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 9)
         nrm = np.ascontiguousarray(nrm, np.float32).reshape(-1, 9)
@@ -95,7 +95,7 @@ class Oracle:
         oc.euler[:] = [float(v) for v in get("euler")]
         oc.dist = float(get("dist"))
         oc.fovy = float(get("fovy"))
-        p = OrcParams(width, height, max_level, sphere_rays, 1, refraction, 1 if use_bvh else 0, sample_mode, sample_size,
+        p = OrcParams(width, height, max_level, sphere_rays, int(glossy_rays), refraction, 1 if use_bvh else 0, sample_mode, sample_size,
                       1 if defined_bary else 0, x0, y0, x_step, y_step, num_threads, 1 if shadow_exhaustive else 0)
         rgb = np.zeros((height, width, 3), np.float32) if want_rgb else None
         ids = np.full((height, width), -1, np.int32) if want_ids else None

@@ -34,7 +34,10 @@ typedef struct {
     int width, height;          /* windowResolution (src/main.cpp:33), parameterised            */
     int max_reflection_level;   /* src/main.cpp:123                                             */
     int sphere_light_ray_count; /* src/main.cpp:124                                             */
-    int glossy_ray_count;       /* src/main.cpp:126; must be 1 (rand() path is out of scope)    */
+    int glossy_ray_count;       /* src/main.cpp:126.  1: mirror ray only.  > 1 (port only; the reference kind
+                                   refuses): glossy rays with the DEFINED random stream of oracle_port.cpp —
+                                   the reference draws from rand() shared by its threads and has no
+                                   reproducible answer there                                                  */
     float refraction_factor;    /* src/main.cpp:127                                             */
     int use_bvh;                /* global useBVH (src/main.cpp:60) for primary/secondary rays   */
     int sample_mode;            /* 0: 1 ray/pixel, 1: anti_aliasing 4-tap, 2: multipleRays      */

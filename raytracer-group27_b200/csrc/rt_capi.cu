@@ -87,6 +87,7 @@ struct rt_ctx {
     bool any_transparent = false;          // meshes or spheres
     bool mats_transparent = false, spheres_transparent = false;
     DevBuf<float4> d_spheres, d_plane_lights;
+    DevBuf<float> d_mat_glossy, d_sphere_glossy; // glossy cone half-width per material / sphere primitive (glossy_cone)
     // diffuse textures (rt_set_texcoords / rt_set_textures / rt_set_texturing)
     DevBuf<float4> d_tex_texels;
     DevBuf<int4> d_tex_table;
@@ -169,6 +170,8 @@ struct rt_ctx {
         s.sphere_lights = d_sphere.p;
         s.plane_lights = d_plane_lights.p;
         s.spheres = d_spheres.p;
+        s.mat_glossy_d = d_mat_glossy.p;
+        s.sphere_glossy_d = d_sphere_glossy.p;
         s.tex_texels = d_tex_texels.p;
         s.tex_table = d_tex_table.p;
         s.mat_tex = d_mat_tex.p;
@@ -193,18 +196,31 @@ int use_device(rt_ctx* ctx)
     return RT_OK;
 }
 
+// Half-width of the glossy cone, `d` of src/main.cpp:224: std::pow(0.5f, -1 / shininess) * std::sqrt(1 - std::pow(0.5, 2 / shininess)),
+// float pow, double pow and sqrt, product rounded to float — evaluated here with the host's libm, as the CPU reference would.
+float glossy_cone(float shininess)
+{
+    if (shininess == 0.0f)
+        return 0.0f; // never read: the reference skips the glossy branch for shininess 0 (main.cpp:204)
+    return (float)(std::pow(0.5f, -1 / (float)shininess) * std::sqrt(1 - std::pow(0.5, 2 / (float)shininess)));
+}
+
 int upload_materials(rt_ctx* ctx, const rt_material* mats, int n_mats)
 {
     if (!mats || n_mats <= 0)
         return fail(RT_ERR_INVALID, "materials: need at least one");
     std::vector<float4> h(2 * (size_t)n_mats);
+    std::vector<float> gd((size_t)n_mats);
     bool any_t = false;
     for (int i = 0; i < n_mats; i++) {
         h[2 * i] = make_float4(mats[i].kd[0], mats[i].kd[1], mats[i].kd[2], mats[i].shininess);
         h[2 * i + 1] = make_float4(mats[i].ks[0], mats[i].ks[1], mats[i].ks[2], mats[i].transparency);
+        gd[i] = glossy_cone(mats[i].shininess);
         any_t |= mats[i].transparency != 1.0f;
     }
     CK(ctx->d_mats.ensure(h.size()));
+    CK(ctx->d_mat_glossy.ensure(gd.size()));
+    CK(cudaMemcpyAsync(ctx->d_mat_glossy.p, gd.data(), gd.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_mats.p, h.data(), h.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream)); // h is a stack-lifetime staging vector
     ctx->n_mats = n_mats;
@@ -220,8 +236,8 @@ int make_frame_params(const rt_ctx* ctx, const rt_camera* cam, const rt_params* 
         return fail(RT_ERR_INVALID, "null camera / params");
     if (prm->width <= 0 || prm->height <= 0)
         return fail(RT_ERR_INVALID, "resolution must be positive");
-    if (prm->glossy_ray_count != 1)
-        return fail(RT_ERR_INVALID, "glossy_ray_count must be 1 (the reference's rand() glossy rays are outside the rebuilt path)");
+    if (prm->glossy_ray_count < 1 || prm->glossy_ray_count > 40) // the reference's slider range (main.cpp:530)
+        return fail(RT_ERR_INVALID, "glossy_ray_count must be between 1 and 40");
     if (prm->max_reflection_level < 0 || prm->max_reflection_level > 64)
         return fail(RT_ERR_INVALID, "max_reflection_level out of range");
     std::memset(&fp, 0, sizeof(fp));
@@ -285,6 +301,7 @@ int make_frame_params(const rt_ctx* ctx, const rt_camera* cam, const rt_params* 
     fp.any_transparent = ctx->any_transparent ? 1 : 0;
     fp.exhaustive = prm->exhaustive ? 1 : 0;
     fp.tie_by_id = prm->use_bvh ? 0 : 1;
+    fp.glossy = prm->glossy_ray_count;
     fp.tex_on = ctx->tex_on && ctx->n_textures > 0 && ctx->d_mat_tex.p ? 1 : 0;
     fp.tex_filter = ctx->tex_params.filtering;
     fp.tex_oob_x = ctx->tex_params.out_of_bounds_x;
@@ -329,7 +346,9 @@ void set_parity(rt_ctx::Lane& ln, BatchDev& b, int par)
 int ensure_lane(rt_ctx* ctx, rt_ctx::Lane& ln, const FrameParams& fp, unsigned batch_pixels, bool want_ids, BatchDev& b)
 {
     const size_t prim = (size_t)batch_pixels * fp.spp;
-    const size_t cap = prim * (ctx->any_transparent ? 2 : 1);
+    // head-room of the ray queues: a dielectric hit spawns two rays, a glossy one up to glossy_ray_count; deeper levels can
+    // still outgrow it, rt_render then halves the batch and retries (RT_ERR_OVERFLOW)
+    const size_t cap = prim * (ctx->any_transparent ? 2 : 1) * (size_t)std::min(std::max(fp.glossy, 1), 8);
     for (int k = 0; k < 2; k++) {
         CK(ln.q_hit[k].ensure(cap));
         b.q[k].hit = ln.q_hit[k].p;
@@ -823,6 +842,8 @@ int rt_destroy(rt_ctx* ctx)
     ctx->out_t.release();
     ctx->rgb.release();
     ctx->d_spheres.release();
+    ctx->d_mat_glossy.release();
+    ctx->d_sphere_glossy.release();
     ctx->d_tex_texels.release();
     ctx->d_tex_table.release();
     ctx->d_mat_tex.release();
@@ -1186,6 +1207,11 @@ int rt_set_spheres(rt_ctx* ctx, const rt_sphere* spheres, int n_spheres)
         h[3 * i + 2] = make_float4(sp.material.ks[0], sp.material.ks[1], sp.material.ks[2], sp.material.transparency);
         any_t |= sp.material.transparency != 1.0f;
     }
+    std::vector<float> gd((size_t)std::max(1, n_spheres), 0.0f);
+    for (int i = 0; i < n_spheres; i++)
+        gd[i] = glossy_cone(spheres[i].material.shininess);
+    CK(ctx->d_sphere_glossy.ensure(gd.size()));
+    CK(cudaMemcpyAsync(ctx->d_sphere_glossy.p, gd.data(), gd.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx->d_spheres.ensure(h.size()));
     CK(cudaMemcpyAsync(ctx->d_spheres.p, h.data(), h.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -331,6 +331,27 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_extend(
     }
 }
 
+// Glossy rays (src/main.cpp:204-250).  The reference draws their directions from rand(), one stream shared by all of its
+// OpenMP threads, so it has no reproducible answer for glossy_ray_count > 1; the rebuilt path defines the stream: every ray
+// carries a 32-bit path id (primary ray: mix(pixel index y * W + x, sample index); child: mix(parent id, child index) with
+// mirror / reflection child 0, glossy child i = i, refraction child 0x4000), and uniform j of attempt a for glossy child i
+// at a hit is the top 24 bits of mix(mix(mix(path, i), a), j) over 2^24.  The CPU port (oracle/oracle_port.cpp) restates
+// the same integer arithmetic; parity for this feature is device == port, there is no reference run to pin it on.
+__device__ __forceinline__ unsigned path_mix(unsigned a, unsigned b)
+{
+    unsigned h = (a * 0x9E3779B1u) ^ (b + 0x7F4A7C15u + (a << 6) + (a >> 2));
+    h ^= h >> 16;
+    h *= 0x85EBCA6Bu;
+    h ^= h >> 13;
+    h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return h;
+}
+__device__ __forceinline__ float path_uniform(unsigned path, unsigned child, unsigned attempt, unsigned j)
+{
+    return (float)(path_mix(path_mix(path_mix(path, child), attempt), j) >> 8) * (1.0f / 16777216.0f);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // K3 shade: getFinalColor without the recursion (src/main.cpp:129-190), light set-up of getPointLights /
 // getSpherelights (src/shadow.cpp:106-131, 139-226: everything except the cansee calls), calcColor
@@ -348,6 +369,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
     for (unsigned i = blockIdx.x * kShadeBlock + threadIdx.x; i < n_round; i += gridDim.x * kShadeBlock) {
         bool hit = false;
         int pix = 0;
+        unsigned path = 0; // path id of the ray (glossy random stream; 0 and unused when glossy_ray_count is 1)
         f3 w = mk3(0, 0, 0), refl = mk3(0, 0, 0), refr = mk3(0, 0, 0), dn = mk3(0, 0, 0), Nn = mk3(0, 0, 0);
         Shading sh;
         sh.p = mk3(0, 0, 0);
@@ -376,12 +398,19 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
                 if (LEVEL0) {
                     generate_ray(fp, first_lp, i, o, d, tag); // K1 again: the primary ray is a function of the index
                     w = mk3(1.0f, 1.0f, 1.0f);
+                    if (fp.glossy > 1) {
+                        int px, py;
+                        local_to_pixel(fp, first_lp + i / (unsigned)fp.spp, px, py);
+                        path = path_mix((unsigned)(py * fp.W + px), i % (unsigned)fp.spp);
+                    }
                 } else {
                     const float4 op = b.q[qi].o_pix[i];
+                    const float4 dq = b.q[qi].d[i];
                     o = mk3(op);
-                    d = mk3(b.q[qi].d[i]);
+                    d = mk3(dq);
                     w = mk3(b.q[qi].w[i]);
                     tag = __float_as_int(op.w);
+                    path = (unsigned)__float_as_int(dq.w);
                 }
                 pix = tag >> 1;
                 sh = shading_at(s, h.y, o, d, __int_as_float(h.x));
@@ -394,13 +423,18 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
         const float shininess = sh.m0.w, transparency = sh.m1.w;
 
         // children
-        bool want0 = false, want1 = false;
+        bool want0 = false, want1 = false, glossy_here = false;
         f3 w0 = mk3(0, 0, 0), w1 = mk3(0, 0, 0);
         if (hit && level < fp.max_level) { // main.cpp:187
             if (transparency == 1.0f) {
                 if (ks.x > 0.0f || ks.y > 0.0f || ks.z > 0.0f) { // main.cpp:194
                     want0 = true;
                     w0 = mk3(w.x * ks.x * ks.x, w.y * ks.y * ks.y, w.z * ks.z * ks.z);
+                    if (shininess != 0.0f && fp.glossy > 1) { // color += ks * reflectColor / glossy_ray_count, main.cpp:250
+                        const float g = (float)fp.glossy;
+                        w0 = mk3(w0.x / g, w0.y / g, w0.z / g);
+                        glossy_here = true;
+                    }
                 }
             } else { // main.cpp:257-290
                 const float r = fp.refraction;
@@ -439,14 +473,68 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
         if (slot[0] != 0xffffffffu) {
             const f3 o2 = xadd(sh.p, xmul(refl, 0.01f)); // main.cpp:199,286
             b.q[qo].o_pix[slot[0]] = make_float4(o2.x, o2.y, o2.z, __int_as_float(pix << 1));
-            b.q[qo].d[slot[0]] = make_float4(refl.x, refl.y, refl.z, 0.0f);
+            b.q[qo].d[slot[0]] = make_float4(refl.x, refl.y, refl.z, __int_as_float((int)path_mix(path, 0u)));
             b.q[qo].w[slot[0]] = make_float4(w0.x, w0.y, w0.z, 0.0f);
         }
         if (slot1 != 0xffffffffu) {
             const f3 o2 = xadd(sh.p, xmul(refr, 0.01f)); // main.cpp:288
             b.q[qo].o_pix[slot1] = make_float4(o2.x, o2.y, o2.z, __int_as_float(pix << 1));
-            b.q[qo].d[slot1] = make_float4(refr.x, refr.y, refr.z, 0.0f);
+            b.q[qo].d[slot1] = make_float4(refr.x, refr.y, refr.z, __int_as_float((int)path_mix(path, 0x4000u)));
             b.q[qo].w[slot1] = make_float4(w1.x, w1.y, w1.z, 0.0f);
+        }
+        // Glossy rays (main.cpp:207-249), glossy_ray_count - 1 candidates around the mirror direction with the defined
+        // random stream; one block-wide allocation round per candidate (all threads take part, few have one).
+        if (fp.glossy > 1) {
+            f3 pr1 = mk3(0, 0, 0), pr2 = mk3(0, 0, 0);
+            float dev = 0.0f;
+            if (glossy_here) {
+                f3 notr = refl; // a vector that is not in line with reflect, main.cpp:211-219
+                if (refl.x != 0.0f) {
+                    notr.y = -refl.x;
+                    notr.x = refl.y;
+                } else {
+                    notr.y = -refl.z;
+                    notr.z = refl.y;
+                }
+                pr1 = xcross(refl, notr);
+                pr2 = xcross(refl, pr1);
+                dev = sh.mesh >= 0 ? __ldg(&s.mat_glossy_d[sh.mesh]) : __ldg(&s.sphere_glossy_d[-2 - h.y]); // main.cpp:224, from the host's libm
+            }
+            for (int gi = 1; gi < fp.glossy; gi++) {
+                f3 shine = mk3(0, 0, 0);
+                bool cast = false;
+                if (glossy_here) {
+                    int loopcount = 0;
+                    unsigned attempt = 0;
+                    do {
+                        float a, bb;
+                        do {
+                            a = path_uniform(path, (unsigned)gi, attempt, 0u);
+                            bb = path_uniform(path, (unsigned)gi, attempt, 1u);
+                            attempt++;
+                        } while (a == 0.0f && bb == 0.0f);
+                        a = xmul(xsub(xmul(2.0f, a), 1.0f), dev);
+                        bb = xmul(xsub(xmul(2.0f, bb), 1.0f), dev);
+                        shine = xnormalize(xadd(xadd(refl, xmul(pr1, a)), xmul(pr2, bb)));
+                        loopcount++;
+                    } while (xdot(shine, sh.N) <= 0.0f && loopcount < fp.glossy / 4);
+                    cast = xdot(shine, sh.N) > 0.0f;
+                }
+                unsigned* const cg[1] = { &b.counters->n_rays[qo] };
+                const bool wg[1] = { cast };
+                const unsigned capg[1] = { b.ray_capacity };
+                unsigned sg[1];
+                block_alloc<1>(cg, wg, capg, &b.counters->overflow, sg, smem);
+                if (cast)
+                    n_secondary++;
+                if (sg[0] == 0xffffffffu)
+                    continue;
+                const float wgt = fmaxf(powf(xdot(refl, shine), shininess), 0.0f) / (float)fp.glossy; // main.cpp:245,250
+                const f3 o2 = xadd(sh.p, xmul(shine, 0.01f));
+                b.q[qo].o_pix[sg[0]] = make_float4(o2.x, o2.y, o2.z, __int_as_float(pix << 1));
+                b.q[qo].d[sg[0]] = make_float4(shine.x, shine.y, shine.z, __int_as_float((int)path_mix(path, (unsigned)gi)));
+                b.q[qo].w[sg[0]] = make_float4(w.x * ks.x * wgt, w.y * ks.y * wgt, w.z * ks.z * wgt, 0.0f);
+            }
         }
         const f3 reflN = xnormalize(refl);
         // Direct light.  Point and spot lights (getPointLights / getSpotLichts, shadow.cpp:106-131, 229-252): one shadow

@@ -43,6 +43,9 @@ struct SceneDev {
     const int4* tex_table;
     const int* mat_tex;          // texture of material (mesh) m, or -1
     const float2* tri_uv;        // Vertex::texCoord of the three corners of global triangle g at [3g .. 3g+2]; null = all zero
+    // glossy rays: the cone half-width d of main.cpp:224, evaluated on the host per material / per sphere primitive
+    const float* mat_glossy_d;
+    const float* sphere_glossy_d;
     const int* sphere_rank;      // visiting rank of sphere k in the reference's BVH (tie key, rt_reforder.cu)
     int tie_by_id;               // tie key of this launch: 0 = visiting rank in the reference's BVH (every BVH search of the reference, i.e. all
                                  // shadow queries and, with useBVH, the other rays), 1 = global id (its useBVH = false loop)
@@ -80,6 +83,7 @@ struct FrameParams {
     // diffuse textures: useTextures and the knobs of src/main.cpp:54-58
     int tex_on, tex_filter, tex_oob_x, tex_oob_y;
     float tex_border_r, tex_border_g, tex_border_b;
+    int glossy;      // glossy_ray_count (src/main.cpp:126): 1 = mirror ray only
     int tie_by_id;   // camera / reflection rays: equal t go to the lower global id (useBVH = false) instead of the BVH visiting rank
     // spherical-light ring sampling (shadow.cpp:190-196), host-computed and shared with the oracle
     int sl_m, sl_n, sl_rc;

@@ -10,7 +10,7 @@
 extern int max_reflection_level;   // default 5
 extern int sphere_light_ray_count; // default 10
 extern int plane_light_1D_ray_count; // default 3
-extern int glossy_ray_count;       // reference default 10 uses rand(); only the deterministic value 1 is supported
+extern int glossy_ray_count;       // default 1 here (mirror ray only; the reference's 10 draws from rand()); > 1 uses the defined stream of rt_b200.h
 extern float refraction_factor;    // default 0.8
 extern bool useBVH;                // reference default false: which of two objects at exactly the same t is reported (rt_b200.h)
 // texture knobs (src/main.cpp:54-58)

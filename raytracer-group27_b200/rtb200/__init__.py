@@ -229,12 +229,12 @@ def make_camera(look_at=(0.0, 0.0, 0.0), euler_deg=(20.0, 20.0, 0.0), dist=3.0, 
     return cam
 
 
-def make_params(width, height, max_level=5, sphere_rays=10, refraction=0.8, sample_mode=0, sample_size=4, exhaustive=False, plane_rays_1d=3, use_bvh=True) -> Params:
+def make_params(width, height, max_level=5, sphere_rays=10, refraction=0.8, sample_mode=0, sample_size=4, exhaustive=False, plane_rays_1d=3, use_bvh=True, glossy_rays=1) -> Params:
     p = Params()
     p.width, p.height = int(width), int(height)
     p.max_reflection_level = int(max_level)
     p.sphere_light_ray_count = int(sphere_rays)
-    p.glossy_ray_count = 1
+    p.glossy_ray_count = int(glossy_rays)
     p.refraction_factor = float(refraction)
     p.sample_mode, p.sample_size = int(sample_mode), int(sample_size)
     p.use_bvh = 1 if use_bvh else 0
