@@ -358,7 +358,8 @@ __device__ __forceinline__ float path_uniform(unsigned path, unsigned child, uns
 // (src/main.cpp:112-121) folded into per-light coefficients, and the spawn of mirror (191-256 with
 // glossy_ray_count == 1 => weight ks*ks) and dielectric (257-290) children with a throughput instead of recursion.
 // One thread per ray slot; output queues are filled through block-aggregated ballot compaction.
-template <bool LEVEL0, bool TEXTURED>
+// EXTRAS: the texture branch and the glossy rays are compiled in (frames that use neither run the leaner kernels)
+template <bool LEVEL0, bool EXTRAS>
 __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams fp, BatchDev b, int qi, int level, unsigned first_lp)
 {
     __shared__ unsigned smem[2][kShadeBlock / 32 + 1];
@@ -398,7 +399,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
                 if (LEVEL0) {
                     generate_ray(fp, first_lp, i, o, d, tag); // K1 again: the primary ray is a function of the index
                     w = mk3(1.0f, 1.0f, 1.0f);
-                    if (fp.glossy > 1) {
+                    if (EXTRAS && fp.glossy > 1) {
                         int px, py;
                         local_to_pixel(fp, first_lp + i / (unsigned)fp.spp, px, py);
                         path = path_mix((unsigned)(py * fp.W + px), i % (unsigned)fp.spp);
@@ -419,7 +420,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
                 refl = xreflect(dn, Nn); // main.cpp:141
             }
         }
-        const f3 kd = (TEXTURED && hit) ? diffuse_colour(s, fp, sh) : mk3(sh.m0), ks = mk3(sh.m1);
+        const f3 kd = (EXTRAS && hit) ? diffuse_colour(s, fp, sh) : mk3(sh.m0), ks = mk3(sh.m1);
         const float shininess = sh.m0.w, transparency = sh.m1.w;
 
         // children
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
                 if (ks.x > 0.0f || ks.y > 0.0f || ks.z > 0.0f) { // main.cpp:194
                     want0 = true;
                     w0 = mk3(w.x * ks.x * ks.x, w.y * ks.y * ks.y, w.z * ks.z * ks.z);
-                    if (shininess != 0.0f && fp.glossy > 1) { // color += ks * reflectColor / glossy_ray_count, main.cpp:250
+                    if (EXTRAS && shininess != 0.0f && fp.glossy > 1) { // color += ks * reflectColor / glossy_ray_count, main.cpp:250
                         const float g = (float)fp.glossy;
                         w0 = mk3(w0.x / g, w0.y / g, w0.z / g);
                         glossy_here = true;
@@ -484,7 +485,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
         }
         // Glossy rays (main.cpp:207-249), glossy_ray_count - 1 candidates around the mirror direction with the defined
         // random stream; one block-wide allocation round per candidate (all threads take part, few have one).
-        if (fp.glossy > 1) {
+        if (EXTRAS && fp.glossy > 1) {
             f3 pr1 = mk3(0, 0, 0), pr2 = mk3(0, 0, 0);
             float dev = 0.0f;
             if (glossy_here) {
@@ -984,14 +985,15 @@ void launch_extend(cudaStream_t st, int sm_count, const SceneDev& s, int root_en
 
 void launch_shade(cudaStream_t st, int sm_count, const SceneDev& s, const FrameParams& fp, const BatchDev& b, int qi, int level, unsigned first_lp)
 {
-    // the texture branch (diffuse_colour) is compiled out of the kernels used when useTextures is off
+    // the texture branch (diffuse_colour) and the glossy rays are compiled out of the kernels used by frames without them
+    const bool extras = fp.tex_on || fp.glossy > 1;
     if (level == 0) {
-        if (fp.tex_on)
+        if (extras)
             k_shade<true, true><<<sm_count * 8, kShadeBlock, 0, st>>>(s, fp, b, qi, level, first_lp);
         else
             k_shade<true, false><<<sm_count * 8, kShadeBlock, 0, st>>>(s, fp, b, qi, level, first_lp);
     } else {
-        if (fp.tex_on)
+        if (extras)
             k_shade<false, true><<<sm_count * 4, kShadeBlock, 0, st>>>(s, fp, b, qi, level, first_lp);
         else
             k_shade<false, false><<<sm_count * 4, kShadeBlock, 0, st>>>(s, fp, b, qi, level, first_lp);
