@@ -113,10 +113,15 @@ int rt_set_lights(rt_ctx* ctx, const rt_point_light* point, int n_point, const r
 
 /* Diffuse textures: Material::kdTexture (src/mesh.h:29), Vertex::texCoord (src/mesh.h:18) and the texture branch of
  * getFinalColor (src/main.cpp:155-171) with Image::getPixel (src/image.cpp:75-108). */
-#define RT_TEX_NEAREST 0   /* TextureFiltering::NearestNeighbor, src/image.h:24-31                                  */
-#define RT_TEX_BILINEAR 1  /* TextureFiltering::Bilinear.  The three mip-mapped modes are refused: their level comes  */
-                           /* from Ray::dD_dx / dD_dy, which the reference initialises from members constructed       */
-                           /* later (framework/include/ray.h:19-28) — there is no defined answer to reproduce.        */
+#define RT_TEX_NEAREST 0   /* TextureFiltering (src/image.h:24-31): NearestNeighbor                                   */
+#define RT_TEX_BILINEAR 1  /* Bilinear                                                                                 */
+#define RT_TEX_MIP_NEAREST 2    /* MipMappingNearestLevelNearestNeighbor | The level of detail of these three comes    */
+#define RT_TEX_MIP_BILINEAR 3   /* MipMappingNearestLevelBilinear        | from Ray::dD_dx / dD_dy, which the reference */
+#define RT_TEX_TRILINEAR 4      /* Trilinear                             | initialises from members constructed later  */
+                           /* (framework/include/ray.h:19-28): whatever the stack held.  Here it is DEFINED as 0, the     */
+                           /* value of that expression when those members read as zero: textures with a mip pyramid       */
+                           /* (square, power of two) are sampled at level 0, the others answer white (Trilinear: black),  */
+                           /* exactly as Image::getPixel does for lod = 0 (src/image.cpp:270-330, 506-538).               */
 #define RT_OOB_BORDER 0    /* OutOfBoundsRule, src/image.h:18-22 */
 #define RT_OOB_CLAMP 1
 #define RT_OOB_REPEAT 2

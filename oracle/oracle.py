@@ -45,7 +45,7 @@ class OrcTexture(C.Structure):
 
 
 # TextureFiltering (the two without a mip level) and OutOfBoundsRule of src/image.h:18-31
-TEX_NEAREST, TEX_BILINEAR = 0, 1
+TEX_NEAREST, TEX_BILINEAR, TEX_MIP_NEAREST, TEX_MIP_BILINEAR, TEX_TRILINEAR = range(5)
 OOB_BORDER, OOB_CLAMP, OOB_REPEAT = 0, 1, 2
 
 

@@ -97,9 +97,10 @@ void oracle_set_extra_lights(const float* spot, int n_spot, const float* plane, 
  * intersectRayWithTriangleWithInterpolation, src/ray_tracing.cpp:166-169) for the following oracle_render calls.
  * tri_uv: 6 floats per triangle (u, v of its three corners) in global triangle order.  textures: 8-bit RGB rows, top row first
  * (what stbi_load hands to Image::Image, which divides by 255).  mesh_tex[m]: texture of mesh m or -1.
- * filtering: TextureFiltering (src/image.h:24-31) 0 NearestNeighbor, 1 Bilinear — the mip-mapped modes take their level from
- * ray differentials that the reference initialises from not-yet-constructed members (framework/include/ray.h:19-28) and are
- * not offered.  oob_x / oob_y: OutOfBoundsRule (src/image.h:18-22) 0 Border, 1 Clamp, 2 Repeat.  use_textures = 0 clears. */
+ * filtering: TextureFiltering (src/image.h:24-31) 0 NearestNeighbor, 1 Bilinear, 2 MipMappingNearestLevelNearestNeighbor,
+ * 3 MipMappingNearestLevelBilinear, 4 Trilinear.  The mip-mapped modes take their level from ray differentials that the reference
+ * initialises from not-yet-constructed members (framework/include/ray.h:19-28), i.e. from whatever the stack held; both checkers
+ * sample them at level of detail 0, the value that expression has when those members read as zero.  oob_x / oob_y: OutOfBoundsRule (src/image.h:18-22) 0 Border, 1 Clamp, 2 Repeat.  use_textures = 0 clears. */
 typedef struct {
     int width, height;
     const unsigned char* rgb;

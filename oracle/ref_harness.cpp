@@ -129,7 +129,10 @@ glm::vec3 getFinalColor(const RenderGlobals& g, Scene& scene, const BoundingVolu
         texture.setOutOfBoundsRuleX(g_oob_x);
         texture.setOutOfBoundsRuleY(g_oob_y);
         texture.setTextureFilteringMethod(g_tex_filtering);
-        const float lod = 0.0f; // computeLevelOfDetails: unused by NearestNeighbor / Bilinear (src/image.cpp:96-99)
+        // computeLevelOfDetails (src/ray_differentials.cpp:121-139) works on Ray::dD_dx / dD_dy, which the reference initialises from
+        // members constructed after them (framework/include/ray.h:19-28): its value is whatever the stack held.  Defined here as 0 —
+        // what the expression gives when those members read as zero; NearestNeighbor / Bilinear do not use it at all.
+        const float lod = 0.0f;
         matForRendering.kd = texture.getPixel(hitInfo.texCoord, lod);
     }
 
@@ -301,7 +304,7 @@ extern "C" void oracle_set_textures(const float* tri_uv, int n_tris, const orc_t
             std::fclose(f);
         g_tex_files.push_back(name);
     }
-    g_tex_filtering = filtering == 1 ? TextureFiltering::Bilinear : TextureFiltering::NearestNeighbor;
+    g_tex_filtering = (TextureFiltering)filtering; // 2..4: the mip-mapped filters, sampled at lod 0 (see oracle_api.h)
     g_oob_x = (OutOfBoundsRule)oob_x;
     g_oob_y = (OutOfBoundsRule)oob_y;
     g_tex_border = border_rgb ? glm::vec3(border_rgb[0], border_rgb[1], border_rgb[2]) : glm::vec3(0);

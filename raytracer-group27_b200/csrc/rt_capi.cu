@@ -1489,7 +1489,8 @@ int rt_set_textures(rt_ctx* ctx, const rt_texture* textures, int n_textures, con
             return fail(RT_ERR_INVALID, "rt_set_textures: empty texture");
         if (total + (size_t)textures[k].width * textures[k].height > 0x7fffffffu)
             return fail(RT_ERR_INVALID, "rt_set_textures: more than 2^31 texels");
-        table[k] = make_int4((int)total, textures[k].width, textures[k].height, 0);
+        const int tw = textures[k].width, th = textures[k].height; // Image::canUseMipmapping, src/image.cpp:411-413
+        table[k] = make_int4((int)total, tw, th, (((th & (th - 1)) == 0) && ((tw & (tw - 1)) == 0) && tw == th) ? 1 : 0);
         total += (size_t)textures[k].width * textures[k].height;
     }
     for (int m = 0; m < n_materials; m++)
@@ -1521,9 +1522,8 @@ int rt_set_texturing(rt_ctx* ctx, const rt_texture_params* p)
         ctx->tex_on = false;
         return RT_OK;
     }
-    if (p->filtering != RT_TEX_NEAREST && p->filtering != RT_TEX_BILINEAR)
-        return fail(RT_ERR_INVALID, "rt_set_texturing: only the NearestNeighbor and Bilinear filters are offered (the mip-mapped ones take their level from "
-                                    "ray differentials the reference leaves uninitialised)");
+    if (p->filtering < RT_TEX_NEAREST || p->filtering > RT_TEX_TRILINEAR)
+        return fail(RT_ERR_INVALID, "rt_set_texturing: unknown filtering method");
     if (p->out_of_bounds_x < RT_OOB_BORDER || p->out_of_bounds_x > RT_OOB_REPEAT || p->out_of_bounds_y < RT_OOB_BORDER || p->out_of_bounds_y > RT_OOB_REPEAT)
         return fail(RT_ERR_INVALID, "rt_set_texturing: unknown out-of-bounds rule");
     ctx->tex_params = *p;

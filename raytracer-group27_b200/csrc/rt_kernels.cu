@@ -198,8 +198,12 @@ __device__ __forceinline__ f3 sample_texture(const SceneDev& s, const FrameParam
     const int4 tb = __ldg(&s.tex_table[tex]);
     const unsigned w = (unsigned)tb.y, h = (unsigned)tb.z;
     const float4* px = s.tex_texels + tb.x;
+    // Mip-mapped filters (2, 3, 4) at level of detail 0, see rt_b200.h: no pyramid (the texture is not a square power of two,
+    // src/image.cpp:411-413) -> white, Trilinear black (270-330); otherwise level 0 with the nearest / bilinear sample.
+    if (fp.tex_filter >= 2 && tb.w == 0)
+        return fp.tex_filter == 4 ? mk3(0.0f, 0.0f, 0.0f) : mk3(1.0f, 1.0f, 1.0f);
     const float ix = xmul(u, (float)(w - 1u)), iy = xmul(xsub(1.0f, v), (float)(h - 1u));
-    if (fp.tex_filter == 0) {
+    if (fp.tex_filter == 0 || fp.tex_filter == 2) {
         unsigned x = (unsigned)roundf(ix), y = (unsigned)roundf(iy);
         if (x >= w)
             x = w - 1u;

@@ -38,7 +38,7 @@ struct SceneDev {
     const float4* plane_lights;  // 4 x float4: {position}{width}{height}{color}
     const float4* sphere_lights; // 2 x float4: {pos, radius}{color, 0}
     const float4* spheres;       // sphere primitives, 3 x float4: {centre, radius}{kd, shininess}{ks, transparency}
-    // diffuse textures (src/image.cpp): texels of all textures back to back, top row first; table {first texel, width, height, 0}
+    // diffuse textures (src/image.cpp): texels of all textures back to back, top row first; table {first texel, width, height, 1 if it has a mip pyramid}
     const float4* tex_texels;
     const int4* tex_table;
     const int* mat_tex;          // texture of material (mesh) m, or -1

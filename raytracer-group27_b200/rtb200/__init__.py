@@ -70,7 +70,7 @@ class TextureParams(C.Structure):
     _fields_ = [("filtering", C.c_int), ("out_of_bounds_x", C.c_int), ("out_of_bounds_y", C.c_int), ("border_color", C.c_float * 3)]
 
 
-TEX_NEAREST, TEX_BILINEAR = 0, 1
+TEX_NEAREST, TEX_BILINEAR, TEX_MIP_NEAREST, TEX_MIP_BILINEAR, TEX_TRILINEAR = range(5)
 OOB_BORDER, OOB_CLAMP, OOB_REPEAT = 0, 1, 2
 
 

@@ -163,7 +163,10 @@ def main():
     # textures: a floor quad whose texture coordinates run from -0.5 to 1.5 (every out-of-bounds rule matters) under a cube
     # with random coordinates; a 7x5 gradient and a 16x16 checker; both filters that need no mip level, four rule pairs
     for nm, filt, ox, oy in (("tex_nearest_border_96x80", 0, 0, 0), ("tex_bilinear_clamp_repeat_96x80", 1, 1, 2), ("tex_nearest_repeat_clamp_96x80", 0, 2, 1),
-                             ("tex_bilinear_repeat_96x80", 1, 2, 2)):
+                             ("tex_bilinear_repeat_96x80", 1, 2, 2),
+                             # the mip-mapped filters at the defined level of detail 0 (oracle_api.h): the 16x16 checker has a
+                             # pyramid and is sampled at level 0, the 7x5 gradient has none and answers white / black
+                             ("tex_mipnearest_repeat_96x80", 2, 2, 2), ("tex_mipbilinear_clamp_96x80", 3, 1, 1), ("tex_trilinear_repeat_clamp_96x80", 4, 2, 1)):
         mint(nm, textured_scene(), 96, 80, max_level=2, tex=dict(filtering=filt, oob_x=ox, oob_y=oy, border=(0.2, 0.1, 0.4)))
     # Monkey preset: two point lights (scene.cpp:52-57), mirror-ish material
     mint("monkey_192", with_lights(rtb200.load_obj(DATA + "monkey-rotated.obj", True), point=[[-1, 1, -1, 1, 1, 1], [1, -1, -1, 1, 1, 1]]), 192, 192, max_level=3)
