@@ -72,6 +72,10 @@ typedef struct {
     int exhaustive;             /* debugging aid: 1 = test every object for every ray instead of walking the device
                                    BVH (same result, O(n) per ray)                                           */
     int plane_light_ray_count_1d; /* src/main.cpp:125 (default 3): n x n samples per plane light; values < 2 mean 3 */
+    int texture_debug;          /* renderRayTracing's textureDebugging argument (src/main.cpp:75-106, 355-356): every pixel
+                                   shows the texture colour of what its corner ray hits — white where the material has no
+                                   texture, black on a miss — without lighting, sampling modes or bounces; it reads the
+                                   textures and the knobs of rt_set_texturing even when texturing is off for rendering   */
 } rt_params;
 
 typedef struct {
@@ -139,7 +143,9 @@ typedef struct {
 int rt_set_texcoords(rt_ctx* ctx, const float* uv);
 /* The scene's textures and, per material (mesh), which one it uses (-1: none).  n_textures = 0 removes them. */
 int rt_set_textures(rt_ctx* ctx, const rt_texture* textures, int n_textures, const int* material_texture, int n_materials);
-/* useTextures (src/main.cpp:58) and its knobs for the following frames; NULL = off (the reference's default). */
+/* useTextures (src/main.cpp:58) and its knobs for the following frames; NULL = off and the knobs back at the reference's
+ * defaults (nearest neighbour, border, black).  A texture-debug frame (rt_params.texture_debug) samples with these knobs
+ * whether useTextures is on or not, as getFinalColorNoRayTracingJustTextures does (src/main.cpp:75-106). */
 int rt_set_texturing(rt_ctx* ctx, const rt_texture_params* params);
 
 /* Screen post-processing: the step renderRayTracing ends with (screen.postprocessImage(), src/main.cpp:397-398), and the

@@ -28,7 +28,7 @@ class OrcParams(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("max_reflection_level", C.c_int), ("sphere_light_ray_count", C.c_int),
                 ("glossy_ray_count", C.c_int), ("refraction_factor", C.c_float), ("use_bvh", C.c_int), ("sample_mode", C.c_int),
                 ("sample_size", C.c_int), ("defined_bary", C.c_int), ("x0", C.c_int), ("y0", C.c_int), ("x_step", C.c_int),
-                ("y_step", C.c_int), ("num_threads", C.c_int), ("shadow_exhaustive", C.c_int)]
+                ("y_step", C.c_int), ("num_threads", C.c_int), ("shadow_exhaustive", C.c_int), ("texture_debug", C.c_int)]
 
 
 class OrcStats(C.Structure):
@@ -81,7 +81,7 @@ class Oracle:
 
     def render(self, pos, nrm, mesh_id, mats, point_lights, sphere_lights, cam, width, height, max_level=5, sphere_rays=10,
                refraction=0.8, use_bvh=True, sample_mode=0, sample_size=4, defined_bary=True, want_ids=True, want_rgb=True,
-               x0=0, y0=0, x_step=1, y_step=1, num_threads=0, shadow_exhaustive=False, glossy_rays=1):
+               x0=0, y0=0, x_step=1, y_step=1, num_threads=0, shadow_exhaustive=False, glossy_rays=1, texture_debug=False):
         """cam: dict(look_at, euler (radians), dist, fovy (radians)) or an object with those attributes."""
         pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 9)
         nrm = np.ascontiguousarray(nrm, np.float32).reshape(-1, 9)
@@ -96,7 +96,7 @@ class Oracle:
         oc.dist = float(get("dist"))
         oc.fovy = float(get("fovy"))
         p = OrcParams(width, height, max_level, sphere_rays, int(glossy_rays), refraction, 1 if use_bvh else 0, sample_mode, sample_size,
-                      1 if defined_bary else 0, x0, y0, x_step, y_step, num_threads, 1 if shadow_exhaustive else 0)
+                      1 if defined_bary else 0, x0, y0, x_step, y_step, num_threads, 1 if shadow_exhaustive else 0, 1 if texture_debug else 0)
         rgb = np.zeros((height, width, 3), np.float32) if want_rgb else None
         ids = np.full((height, width), -1, np.int32) if want_ids else None
         t = np.zeros((height, width), np.float32) if want_ids else None
@@ -124,7 +124,8 @@ class Oracle:
         self.lib.oracle_set_extra_lights(C.c_void_p(sp.ctypes.data if len(sp) else None), C.c_int(len(sp)),
                                          C.c_void_p(pl.ctypes.data if len(pl) else None), C.c_int(len(pl)), C.c_int(int(plane_ray_count_1d)))
 
-    def set_textures(self, tri_uv=None, textures=None, mesh_tex=None, filtering=TEX_NEAREST, oob_x=OOB_BORDER, oob_y=OOB_BORDER, border=(0, 0, 0)):
+    def set_textures(self, tri_uv=None, textures=None, mesh_tex=None, filtering=TEX_NEAREST, oob_x=OOB_BORDER, oob_y=OOB_BORDER, border=(0, 0, 0),
+                     use_textures=True):
         """Diffuse textures for the following render() calls (None / no textures: off).  tri_uv (n_tris, 6); textures: list of
         (H, W, 3) uint8 arrays, top row first; mesh_tex: texture index per mesh or -1."""
         self.lib.oracle_set_textures.restype = None
@@ -137,7 +138,7 @@ class Oracle:
         mt = np.ascontiguousarray(mesh_tex, np.int32)
         b = np.ascontiguousarray(border, np.float32)
         self.lib.oracle_set_textures(C.c_void_p(uv.ctypes.data), C.c_int(uv.shape[0]), arr, C.c_int(len(imgs)), C.c_void_p(mt.ctypes.data), C.c_int(len(mt)),
-                                     C.c_int(1), C.c_int(int(filtering)), C.c_int(int(oob_x)), C.c_int(int(oob_y)), C.c_void_p(b.ctypes.data))
+                                     C.c_int(1 if use_textures else 0), C.c_int(int(filtering)), C.c_int(int(oob_x)), C.c_int(int(oob_y)), C.c_void_p(b.ctypes.data))
 
     def postprocess(self, rgb, filtering_option=FILTER_NONE, kernel=KERNEL_BOX, kernel_repetitions=1, filter_size=5, sigma=2.0, exposure=0.5,
                     gamma_correction=False, gamma=2.2, bloom_live=True, via_write_bitmap=False):

@@ -54,6 +54,9 @@ typedef struct {
                                    cull-free answer is what the triangle arithmetic and the visiting order alone
                                    define and what a conservative BVH (the GPU path) returns.  tri_id then also
                                    follows the visiting order on equal t (lowest id otherwise).                  */
+    int texture_debug;          /* renderRayTracing's textureDebugging argument (src/main.cpp:75-106, 355-356): every pixel shows
+                                   the texture colour of what its corner ray hits (white where the material has no texture,
+                                   black on a miss), no lighting; textures as set by oracle_set_textures, whatever use_textures */
 } orc_params;
 
 typedef struct {
@@ -100,7 +103,8 @@ void oracle_set_extra_lights(const float* spot, int n_spot, const float* plane, 
  * filtering: TextureFiltering (src/image.h:24-31) 0 NearestNeighbor, 1 Bilinear, 2 MipMappingNearestLevelNearestNeighbor,
  * 3 MipMappingNearestLevelBilinear, 4 Trilinear.  The mip-mapped modes take their level from ray differentials that the reference
  * initialises from not-yet-constructed members (framework/include/ray.h:19-28), i.e. from whatever the stack held; both checkers
- * sample them at level of detail 0, the value that expression has when those members read as zero.  oob_x / oob_y: OutOfBoundsRule (src/image.h:18-22) 0 Border, 1 Clamp, 2 Repeat.  use_textures = 0 clears. */
+ * sample them at level of detail 0, the value that expression has when those members read as zero.  oob_x / oob_y: OutOfBoundsRule (src/image.h:18-22) 0 Border, 1 Clamp, 2 Repeat.  use_textures is main.cpp's useTextures (the
+ * materials keep their textures either way, the texture-debug view reads them regardless); n_textures = 0 removes them. */
 typedef struct {
     int width, height;
     const unsigned char* rgb;

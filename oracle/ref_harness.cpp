@@ -106,6 +106,25 @@ glm::vec3 calcColor(const Lighting& light, const Material& material) // main.cpp
     return diffuse + spec;
 }
 
+glm::vec3 getFinalColorNoRayTracingJustTextures(const RenderGlobals& g, Scene& scene, const BoundingVolumeHierarchy& bvh, Ray ray) // main.cpp:75-106
+{
+    HitInfo hitInfo;
+    if (bvh.intersect(ray, hitInfo, g.useBVH)) {
+        Material& mat = hitInfo.getMaterial(scene);
+        if (mat.kdTexture) {
+            Image& texture = mat.kdTexture.value();
+            texture.setBorderColor(g_tex_border);
+            texture.setOutOfBoundsRuleX(g_oob_x);
+            texture.setOutOfBoundsRuleY(g_oob_y);
+            texture.setTextureFilteringMethod(g_tex_filtering);
+            const float lod = 0.0f; // computeLevelOfDetails: defined as 0, see getFinalColor below
+            return texture.getPixel(hitInfo.texCoord, lod);
+        }
+        return glm::vec3(1);
+    }
+    return glm::vec3(0);
+}
+
 glm::vec3 getFinalColor(const RenderGlobals& g, Scene& scene, const BoundingVolumeHierarchy& bvh, Ray ray, int level,
     Counters& cnt) // main.cpp:129-301
 {
@@ -290,11 +309,11 @@ extern "C" void oracle_set_textures(const float* tri_uv, int n_tris, const orc_t
     int use_textures, int filtering, int oob_x, int oob_y, const float* border_rgb)
 {
     g_use_textures = use_textures != 0;
-    g_tex_uv.assign(tri_uv, tri_uv + (tri_uv && use_textures ? 6 * (size_t)n_tris : 0));
-    g_mesh_tex.assign(mesh_tex, mesh_tex + (mesh_tex && use_textures ? n_meshes : 0));
+    g_tex_uv.assign(tri_uv, tri_uv + (tri_uv ? 6 * (size_t)n_tris : 0));
+    g_mesh_tex.assign(mesh_tex, mesh_tex + (mesh_tex ? n_meshes : 0));
     orc_registered_textures.clear();
     g_tex_files.clear();
-    for (int k = 0; use_textures && k < n_textures; k++) {
+    for (int k = 0; textures && k < n_textures; k++) {
         orc_registered_textures.push_back({ textures[k].width, textures[k].height,
             std::vector<unsigned char>(textures[k].rgb, textures[k].rgb + 3 * (size_t)textures[k].width * textures[k].height) });
         // Image::Image insists on an existing file (src/image.cpp:38-41): an empty placeholder whose name carries the index
@@ -373,7 +392,10 @@ extern "C" int oracle_render(const float* pos, const float* nrm, const int* mesh
             const Ray cameraRay = camera.generateRay(normalizedPixelPos);
             glm::vec3 out(0);
             Ray firstRay = cameraRay; // the ray whose closest hit is reported in tri_id / t_hit: first sample of the pixel
-            if (prm->sample_mode == 1) { // main.cpp:358-375
+            if (prm->texture_debug) { // main.cpp:355-356
+                cnt.primary++;
+                out = getFinalColorNoRayTracingJustTextures(g, scene, bvh, cameraRay);
+            } else if (prm->sample_mode == 1) { // main.cpp:358-375
                 float offsetX = 1.0f / W * 0.25f;
                 float offsetY = 1.0f / H * 0.25f;
                 std::array<glm::vec2, 4> offsets;

@@ -302,7 +302,18 @@ int make_frame_params(const rt_ctx* ctx, const rt_camera* cam, const rt_params* 
     fp.exhaustive = prm->exhaustive ? 1 : 0;
     fp.tie_by_id = prm->use_bvh ? 0 : 1;
     fp.glossy = prm->glossy_ray_count;
-    fp.tex_on = ctx->tex_on && ctx->n_textures > 0 && ctx->d_mat_tex.p ? 1 : 0;
+    fp.tex_available = ctx->n_textures > 0 && ctx->d_mat_tex.p ? 1 : 0;
+    fp.tex_on = ctx->tex_on && fp.tex_available ? 1 : 0;
+    fp.tex_debug = prm->texture_debug ? 1 : 0;
+    if (fp.tex_debug) { // one corner ray per pixel, no lights, no bounces (main.cpp:355-356)
+        fp.sample_mode = 0;
+        fp.spp = 1;
+        fp.sample_scale = 1.0f;
+        fp.max_level = 0;
+        fp.n_point = fp.n_sphere = fp.n_plane = 0;
+        fp.glossy = 1;
+        fp.tex_on = 0;
+    }
     fp.tex_filter = ctx->tex_params.filtering;
     fp.tex_oob_x = ctx->tex_params.out_of_bounds_x;
     fp.tex_oob_y = ctx->tex_params.out_of_bounds_y;
@@ -1520,6 +1531,7 @@ int rt_set_texturing(rt_ctx* ctx, const rt_texture_params* p)
         return fail(RT_ERR_INVALID, "null context");
     if (!p) {
         ctx->tex_on = false;
+        ctx->tex_params = rt_texture_params {}; // the reference's defaults (src/main.cpp:54-57): nearest, border, black
         return RT_OK;
     }
     if (p->filtering < RT_TEX_NEAREST || p->filtering > RT_TEX_TRILINEAR)

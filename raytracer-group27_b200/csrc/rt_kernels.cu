@@ -219,9 +219,9 @@ __device__ __forceinline__ f3 sample_texture(const SceneDev& s, const FrameParam
 }
 
 // kd of a hit: the material's, or its texture at the interpolated texture coordinate (getFinalColor, src/main.cpp:155-171)
-__device__ __forceinline__ f3 diffuse_colour(const SceneDev& s, const FrameParams& fp, const Shading& sh)
+__device__ __forceinline__ f3 diffuse_colour(const SceneDev& s, const FrameParams& fp, const Shading& sh, bool force = false)
 {
-    if (fp.tex_on && sh.mesh >= 0) {
+    if ((fp.tex_on || force) && sh.mesh >= 0) {
         const int tex = __ldg(&s.mat_tex[sh.mesh]);
         if (tex >= 0) {
             float2 t0 = make_float2(0.0f, 0.0f), t1 = t0, t2 = t0;
@@ -423,6 +423,15 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
                 Nn = xnormalize(sh.N);
                 refl = xreflect(dn, Nn); // main.cpp:141
             }
+        }
+        if (EXTRAS && fp.tex_debug) { // getFinalColorNoRayTracingJustTextures (main.cpp:75-106): the texel, or white without a texture
+            if (hit) {
+                f3 c = mk3(1.0f, 1.0f, 1.0f);
+                if (fp.tex_available && sh.mesh >= 0 && __ldg(&s.mat_tex[sh.mesh]) >= 0)
+                    c = diffuse_colour(s, fp, sh, true);
+                accumulate(b.accum, pix, c.x, c.y, c.z);
+            }
+            continue;
         }
         const f3 kd = (EXTRAS && hit) ? diffuse_colour(s, fp, sh) : mk3(sh.m0), ks = mk3(sh.m1);
         const float shininess = sh.m0.w, transparency = sh.m1.w;
@@ -990,7 +999,7 @@ void launch_extend(cudaStream_t st, int sm_count, const SceneDev& s, int root_en
 void launch_shade(cudaStream_t st, int sm_count, const SceneDev& s, const FrameParams& fp, const BatchDev& b, int qi, int level, unsigned first_lp)
 {
     // the texture branch (diffuse_colour) and the glossy rays are compiled out of the kernels used by frames without them
-    const bool extras = fp.tex_on || fp.glossy > 1;
+    const bool extras = fp.tex_on || fp.glossy > 1 || fp.tex_debug;
     if (level == 0) {
         if (extras)
             k_shade<true, true><<<sm_count * 8, kShadeBlock, 0, st>>>(s, fp, b, qi, level, first_lp);

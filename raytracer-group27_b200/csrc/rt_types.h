@@ -82,6 +82,8 @@ struct FrameParams {
     int exhaustive;
     // diffuse textures: useTextures and the knobs of src/main.cpp:54-58
     int tex_on, tex_filter, tex_oob_x, tex_oob_y;
+    int tex_debug;      // texture-debug view (rt_params.texture_debug)
+    int tex_available;  // the context holds textures (rt_set_textures)
     float tex_border_r, tex_border_g, tex_border_b;
     int glossy;      // glossy_ray_count (src/main.cpp:126): 1 = mirror ray only
     int tie_by_id;   // camera / reflection rays: equal t go to the lower global id (useBVH = false) instead of the BVH visiting rank

@@ -27,8 +27,6 @@ void check(int rc, const char* what)
 void renderRayTracing(Scene& scene, const Trackball& camera, const BoundingVolumeHierarchy& bvh, Screen& screen,
     bool textureDebugging, bool anti_aliasing, bool multipleRays, int sampleSize)
 {
-    if (textureDebugging)
-        throw std::runtime_error("renderRayTracing: the texture-debug view is outside the rebuilt path");
     rt_ctx* ctx = bvh.context();
 
     // lights and materials are read live from the Scene every frame (src/shadow.cpp:111,141; ray_tracing.h:23-27)
@@ -77,10 +75,12 @@ void renderRayTracing(Scene& scene, const Trackball& camera, const BoundingVolum
     prm.use_bvh = useBVH ? 1 : 0; // only decides exact-t ties (rt_b200.h); the device BVH is always used
     prm.exhaustive = 0;
     prm.plane_light_ray_count_1d = plane_light_1D_ray_count;
+    prm.texture_debug = textureDebugging ? 1 : 0; // src/main.cpp:355-356: one corner ray per pixel, its texel, nothing else
     rt_stats st {};
     static_assert(sizeof(glm::vec3) == 3 * sizeof(float), "Screen pixels must be packed float3");
     // the texture branch of getFinalColor (src/main.cpp:155-171) with the knobs main.cpp sets on the Image before sampling it
-    if (useTextures) {
+    // (the texture-debug view applies the same knobs whether useTextures is set or not, src/main.cpp:81-86)
+    if (useTextures || textureDebugging) {
         rt_texture_params tp { static_cast<int>(textureFiltering), static_cast<int>(outOfBoundsRuleX), static_cast<int>(outOfBoundsRuleY),
             { textureBorderColor.x, textureBorderColor.y, textureBorderColor.z } };
         check(rt_set_texturing(ctx, &tp), "rt_set_texturing");

@@ -14,7 +14,7 @@ extern int glossy_ray_count;       // default 1 here (mirror ray only; the refer
 extern float refraction_factor;    // default 0.8
 extern bool useBVH;                // reference default false: which of two objects at exactly the same t is reported (rt_b200.h)
 // texture knobs (src/main.cpp:54-58)
-extern TextureFiltering textureFiltering;  // default NearestNeighbor; the mip-mapped modes are refused (rt_b200.h)
+extern TextureFiltering textureFiltering;  // default NearestNeighbor; the mip-mapped modes sample level of detail 0 (rt_b200.h)
 extern OutOfBoundsRule outOfBoundsRuleX, outOfBoundsRuleY; // default Border
 extern glm::vec3 textureBorderColor;       // default black
 extern bool useTextures;                   // default false

@@ -43,7 +43,7 @@ class Camera(C.Structure):
 class Params(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("max_reflection_level", C.c_int), ("sphere_light_ray_count", C.c_int),
                 ("glossy_ray_count", C.c_int), ("refraction_factor", C.c_float), ("sample_mode", C.c_int), ("sample_size", C.c_int),
-                ("use_bvh", C.c_int), ("exhaustive", C.c_int), ("plane_light_ray_count_1d", C.c_int)]
+                ("use_bvh", C.c_int), ("exhaustive", C.c_int), ("plane_light_ray_count_1d", C.c_int), ("texture_debug", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -229,7 +229,7 @@ def make_camera(look_at=(0.0, 0.0, 0.0), euler_deg=(20.0, 20.0, 0.0), dist=3.0, 
     return cam
 
 
-def make_params(width, height, max_level=5, sphere_rays=10, refraction=0.8, sample_mode=0, sample_size=4, exhaustive=False, plane_rays_1d=3, use_bvh=True, glossy_rays=1) -> Params:
+def make_params(width, height, max_level=5, sphere_rays=10, refraction=0.8, sample_mode=0, sample_size=4, exhaustive=False, plane_rays_1d=3, use_bvh=True, glossy_rays=1, texture_debug=False) -> Params:
     p = Params()
     p.width, p.height = int(width), int(height)
     p.max_reflection_level = int(max_level)
@@ -240,6 +240,7 @@ def make_params(width, height, max_level=5, sphere_rays=10, refraction=0.8, samp
     p.use_bvh = 1 if use_bvh else 0
     p.exhaustive = 1 if exhaustive else 0
     p.plane_light_ray_count_1d = int(plane_rays_1d)
+    p.texture_debug = 1 if texture_debug else 0
     return p
 
 
@@ -303,7 +304,8 @@ class Context:
         _check(self._l.rt_set_textures(self._h, arr, len(texels), mt.ctypes.data, len(mt)))
 
     def set_texturing(self, filtering=None, oob_x=OOB_BORDER, oob_y=OOB_BORDER, border=(0.0, 0.0, 0.0)):
-        """useTextures and its knobs (src/main.cpp:54-58) for the following frames; filtering=None switches textures off."""
+        """useTextures and its knobs (src/main.cpp:54-58) for the following frames; filtering=None switches textures off (the
+        texture-debug view then samples with the reference's default knobs)."""
         if filtering is None:
             _check(self._l.rt_set_texturing(self._h, None))
             return

@@ -30,18 +30,19 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 CAM = dict(look_at=(0.0, 0.0, 0.0), euler_deg=(20.0, 20.0, 0.0), dist=3.0, fovy_deg=50.0)  # src/main.cpp:413-414
 
 
-def mint(name, sc, w, h, *, max_level, sphere_rays=10, sample_mode=0, sample_size=4, colour_from="reference", cam=CAM, plane_rays_1d=3, tex=None):
-    """tex: dict(filtering, oob_x, oob_y, border) = useTextures on with these knobs (the scene carries uv / textures / mesh_tex)."""
+def mint(name, sc, w, h, *, max_level, sphere_rays=10, sample_mode=0, sample_size=4, colour_from="reference", cam=CAM, plane_rays_1d=3, tex=None, texture_debug=False):
+    """tex: dict(filtering, oob_x, oob_y, border) = useTextures on with these knobs (the scene carries uv / textures / mesh_tex);
+    texture_debug: renderRayTracing's textureDebugging view (main.cpp:355-356), useTextures off, the knobs of `tex` still apply."""
     c = rtb200.make_camera(**cam)
     ref, port = oracle.Oracle("reference"), oracle.Oracle("port")
     for o in (ref, port):
         o.set_spheres(sc.spheres)
         o.set_extra_lights(sc.spot_lights, sc.plane_lights, plane_rays_1d)
         if tex:
-            o.set_textures(sc.uv, sc.textures, sc.mesh_tex, tex["filtering"], tex["oob_x"], tex["oob_y"], tex["border"])
+            o.set_textures(sc.uv, sc.textures, sc.mesh_tex, tex["filtering"], tex["oob_x"], tex["oob_y"], tex["border"], use_textures=not texture_debug)
         else:
             o.set_textures()
-    kw = dict(max_level=max_level, sphere_rays=sphere_rays, sample_mode=sample_mode, sample_size=sample_size, use_bvh=True)
+    kw = dict(max_level=max_level, sphere_rays=sphere_rays, sample_mode=sample_mode, sample_size=sample_size, use_bvh=True, texture_debug=texture_debug)
     r_rgb, r_ids, r_t, r_st = ref.render(sc.pos, sc.nrm, sc.mesh_id, sc.mats, sc.point_lights, sc.sphere_lights, c, w, h, **kw)
     p_rgb, p_ids, p_t, p_st = port.render(sc.pos, sc.nrm, sc.mesh_id, sc.mats, sc.point_lights, sc.sphere_lights, c, w, h, **kw)
     # the same frame with every BVH search made cull-free: all objects tested in the BVH's own visiting order (what the
@@ -70,7 +71,7 @@ def mint(name, sc, w, h, *, max_level, sphere_rays=10, sample_mode=0, sample_siz
         rgb_x=x_rgb, primary_rays_x=x_st.primary_rays, shadow_queries_x=x_st.shadow_queries, secondary_rays_x=x_st.secondary_rays,
         colour_from=colour_from, port_equals_reference=np.array([ids_equal, t_equal, rgb_equal]),
         **(dict(uv=sc.uv, mesh_tex=sc.mesh_tex, n_textures=len(sc.textures), tex_filtering=tex["filtering"], tex_oob_x=tex["oob_x"], tex_oob_y=tex["oob_y"],
-                tex_border=np.array(tex["border"], np.float32), **{f"texture_{k}": t for k, t in enumerate(sc.textures)}) if tex else {}))
+                tex_border=np.array(tex["border"], np.float32), texture_debug=int(texture_debug), **{f"texture_{k}": t for k, t in enumerate(sc.textures)}) if tex else {}))
     for o in (ref, port):
         o.set_textures()
         o.set_spheres(None)
@@ -168,6 +169,8 @@ def main():
                              # pyramid and is sampled at level 0, the 7x5 gradient has none and answers white / black
                              ("tex_mipnearest_repeat_96x80", 2, 2, 2), ("tex_mipbilinear_clamp_96x80", 3, 1, 1), ("tex_trilinear_repeat_clamp_96x80", 4, 2, 1)):
         mint(nm, textured_scene(), 96, 80, max_level=2, tex=dict(filtering=filt, oob_x=ox, oob_y=oy, border=(0.2, 0.1, 0.4)))
+    # renderRayTracing(..., textureDebugging = true) (main.cpp:355-356): texel of the corner ray's hit, white without a texture
+    mint("texdebug_bilinear_repeat_clamp_96x80", textured_scene(), 96, 80, max_level=2, tex=dict(filtering=1, oob_x=2, oob_y=1, border=(0.2, 0.1, 0.4)), texture_debug=True)
     # Monkey preset: two point lights (scene.cpp:52-57), mirror-ish material
     mint("monkey_192", with_lights(rtb200.load_obj(DATA + "monkey-rotated.obj", True), point=[[-1, 1, -1, 1, 1, 1], [1, -1, -1, 1, 1, 1]]), 192, 192, max_level=3)
     # Cube preset (every material transparent: d 0.452632)

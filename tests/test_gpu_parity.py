@@ -383,6 +383,11 @@ int main(int argc, char** argv) {
     renderRayTracing(scene, camera, bvh, screen);
     std::ofstream f3(argv[5], std::ios::binary);
     f3.write(reinterpret_cast<const char*>(screen.pixels().data()), sizeof(glm::vec3) * screen.pixels().size());
+    // fourth frame: the texture-debug view (main.cpp:753-757), useTextures off again, the same knobs
+    useTextures = false;
+    renderRayTracing(scene, camera, bvh, screen, true);
+    std::ofstream f4(argv[6], std::ios::binary);
+    f4.write(reinterpret_cast<const char*>(screen.pixels().data()), sizeof(glm::vec3) * screen.pixels().size());
     return 0;
 }
 """
@@ -415,7 +420,7 @@ def test_cpp_drop_in_renders_the_same_frame(rtb, gpu_ctx, tmp_path):
                         f"-L{lib}", "-lrtb200", f"-Wl,-rpath,{lib}"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe), str(tmp_path), str(tmp_path / "frame.bin"), str(tmp_path / "frame2.bin"), str(tmp_path / "render.bmp"),
-                        str(tmp_path / "frame3.bin")], capture_output=True, text=True)
+                        str(tmp_path / "frame3.bin"), str(tmp_path / "frame4.bin")], capture_output=True, text=True)
     assert r.returncode == 0, (r.stdout, r.stderr)
     cpp = np.fromfile(tmp_path / "frame.bin", np.float32).reshape(256, 256, 3)
     sc = rtb.load_obj(str(tmp_path / "custom.obj"))
@@ -463,3 +468,12 @@ def test_cpp_drop_in_renders_the_same_frame(rtb, gpu_ctx, tmp_path):
     finally:
         port.set_textures()
     assert np.abs(cpp3 - o_rgb).max() <= COLOUR_TOL
+    # fourth frame: renderRayTracing(..., textureDebugging = true): texels only, white where the material has no texture
+    port.set_textures(sc.uv, sc.textures, sc.mesh_tex, oracle.TEX_BILINEAR, oracle.OOB_REPEAT, oracle.OOB_CLAMP, use_textures=False)
+    try:
+        d_rgb, d_ids, _, d_st = port.render(sc.pos, sc.nrm, sc.mesh_id, sc.mats, sc.point_lights, None, rtb.make_camera(), 256, 256, max_level=3, texture_debug=True)
+    finally:
+        port.set_textures()
+    cpp4 = np.fromfile(tmp_path / "frame4.bin", np.float32).reshape(256, 256, 3)
+    assert np.abs(cpp4 - d_rgb).max() <= 1e-6
+    assert (cpp4[d_ids < 0] == 0).all() and (cpp4.reshape(-1, 3) == 1).all(axis=1).sum() > 100 and d_st.shadow_queries == 0

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 GOLDEN_NAMES = ["cornell_planelight_160", "cornell_planelight_inside_96", "cube_preset_spot_128", "monkey_spots_128", "cornell_preset_sphere_192", "spheres_preset_160", "cornell_c1_256", "cornell_c4_96", "cornell_sph10_aa_80x48", "cornell_ms16_70x45", "cornell_inside_128", "monkey_192",
-                "cube_96", "zfight_96", "tex_nearest_border_96x80", "tex_bilinear_clamp_repeat_96x80", "tex_nearest_repeat_clamp_96x80", "tex_bilinear_repeat_96x80", "tex_mipnearest_repeat_96x80", "tex_mipbilinear_clamp_96x80", "tex_trilinear_repeat_clamp_96x80", "andreas_160x120", "catalin_128x96", "mike_128x96", "tr_def_96", "teapot_c2_256x144", "teapot_d3_128x72", "dragon_standin_c3_160x90"]
+                "cube_96", "zfight_96", "tex_nearest_border_96x80", "tex_bilinear_clamp_repeat_96x80", "tex_nearest_repeat_clamp_96x80", "tex_bilinear_repeat_96x80", "tex_mipnearest_repeat_96x80", "tex_mipbilinear_clamp_96x80", "tex_trilinear_repeat_clamp_96x80", "texdebug_bilinear_repeat_clamp_96x80", "andreas_160x120", "catalin_128x96", "mike_128x96", "tr_def_96", "teapot_c2_256x144", "teapot_d3_128x72", "dragon_standin_c3_160x90"]
 
 
 # Screen settings exercised by the post-processing fixture (tests/golden/make_golden_post.py) and the GPU tests; keyword
@@ -54,6 +54,8 @@ class Golden:
         self.geometry_ok = True
         # useTextures and its knobs (None: textures off, the reference's default)
         self.tex = dict(filtering=int(d["tex_filtering"]), oob_x=int(d["tex_oob_x"]), oob_y=int(d["tex_oob_y"]), border=tuple(float(v) for v in d["tex_border"])) if "tex_filtering" in d else None
+        # renderRayTracing's textureDebugging view (main.cpp:355-356): useTextures off, the knobs above still apply
+        self.texture_debug = bool(int(d["texture_debug"])) if "texture_debug" in d else False
         if "pos" in d:
             self.scene = rtb200.SceneData(d["pos"], d["nrm"], d["mesh_id"], d["mats"], d["point_lights"], d["sphere_lights"])
             if "spheres" in d:
@@ -77,7 +79,7 @@ class Golden:
 
     def params(self, exhaustive=False, use_bvh=True):
         import rtb200
-        return rtb200.make_params(self.w, self.h, self.max_level, self.sphere_rays, 0.8, self.sample_mode, self.sample_size, exhaustive, self.plane_rays_1d, use_bvh)
+        return rtb200.make_params(self.w, self.h, self.max_level, self.sphere_rays, 0.8, self.sample_mode, self.sample_size, exhaustive, self.plane_rays_1d, use_bvh, texture_debug=self.texture_debug)
 
     def oracle_render(self, kind="port", **kw):
         import oracle
@@ -86,11 +88,11 @@ class Golden:
         o.set_spheres(s.spheres)
         o.set_extra_lights(s.spot_lights, s.plane_lights, self.plane_rays_1d)
         if self.tex:
-            o.set_textures(s.uv, s.textures, s.mesh_tex, self.tex["filtering"], self.tex["oob_x"], self.tex["oob_y"], self.tex["border"])
+            o.set_textures(s.uv, s.textures, s.mesh_tex, self.tex["filtering"], self.tex["oob_x"], self.tex["oob_y"], self.tex["border"], use_textures=not self.texture_debug)
         else:
             o.set_textures()
         return o.render(s.pos, s.nrm, s.mesh_id, s.mats, s.point_lights, s.sphere_lights, self.camera(), self.w, self.h, max_level=self.max_level,
-                        sphere_rays=self.sphere_rays, sample_mode=self.sample_mode, sample_size=self.sample_size, **kw)
+                        sphere_rays=self.sphere_rays, sample_mode=self.sample_mode, sample_size=self.sample_size, texture_debug=self.texture_debug, **kw)
 
 
 def id_mismatch_fraction(a, b):
