@@ -8,11 +8,13 @@
 #include "../host/mesh.h"
 
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <filesystem>
 #include <string>
+#include <cstdlib>
 #include <vector>
 
 using namespace rtb;
@@ -95,6 +97,10 @@ struct rt_ctx {
     DevBuf<float2> d_uv;
     bool have_uv = false;
     int n_textures = 0;
+    bool band_order_outer_first = true; // host-path frames: outer bands first (RTB200_BAND_ORDER=0: top to bottom)
+    bool trace_bands = false;           // RTB200_TRACE_BANDS=1 (developer): print when every band was rendered / had left
+    std::vector<cudaEvent_t> trace_ev;
+    std::vector<std::string> trace_what;
     bool tex_on = false;
     rt_texture_params tex_params {};
     int n_spheres = 0;
@@ -541,8 +547,11 @@ struct HostTarget {
 
 // Enqueue one frame.  `out`: float4 framebuffer (Screen layout), maybe on a peer GPU.  The frame starts and ends on the
 // context's stream; in between, its batches run on the lanes' own streams.
-int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids, unsigned batch_rays, const HostTarget* host)
+constexpr int kBandGridMult = 4;
+
+int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_ids, unsigned batch_rays, const HostTarget* host)
 {
+    FrameParams fp = fp_in;
     const size_t n_local = (size_t)fp.n_local_tiles * kTilePixels;
     // batch size: the frame split evenly over the lanes, in whole tile rows when this context owns the whole image (so
     // that a finished batch is a band of complete image rows), bounded below (tiny batches are all latency) and above
@@ -573,7 +582,28 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids
         batch_pixels = std::max<size_t>(unit, cap_pixels / unit * unit);
     if (batch_pixels > n_local)
         batch_pixels = std::max<size_t>(n_local, kTilePixels);
-    const size_t n_batches = n_local ? (n_local + batch_pixels - 1) / batch_pixels : 0;
+    // post-processing (bloom) needs the whole image: it runs after the last batch, so rows cannot leave band by band
+    const bool post = ctx->post_on && fp.world == 1 && post_has_effect(ctx->post) && n_local;
+    const bool band_download = host && host->rgb && fp.world == 1 && !post && batch_pixels % ((size_t)fp.tiles_x * kTilePixels) == 0;
+    // several lanes render bands side by side: traversal grids of 4 blocks per SM leave room for another lane's kernel
+    // (C3 through rt_render, 3 lanes x 6 bands: 3.40 ms with 8 blocks per SM, 3.17 with 4, 3.16 with 3)
+    fp.trace_grid_mult = band_download && lanes_wanted > 1 ? kBandGridMult : 0;
+    // The batches of the frame: {first local pixel, pixels}.  Bands that travel to the host go from the outside in (top,
+    // bottom, second from the top, ...): the camera looks at the scene, so the outer bands are mostly background, finish
+    // early and keep the copy engine busy while the expensive middle of the image renders (profiles/README.md, host path).
+    std::vector<std::pair<size_t, size_t>> plan;
+    for (size_t first = 0; first < n_local; first += batch_pixels)
+        plan.push_back({ first, std::min(batch_pixels, n_local - first) });
+    if (band_download && ctx->band_order_outer_first) {
+        std::vector<std::pair<size_t, size_t>> outer;
+        for (size_t lo = 0, hi = plan.size(); lo < hi;) {
+            outer.push_back(plan[--hi]);
+            if (lo < hi)
+                outer.push_back(plan[lo++]);
+        }
+        plan.swap(outer);
+    }
+    const size_t n_batches = plan.size();
     const int n_lanes = (int)std::min<size_t>(lanes_wanted, std::max<size_t>(n_batches, 1));
 
     CK(ctx->accum.ensure(std::max<size_t>(n_local, 1)));
@@ -599,11 +629,9 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids
     if (n_local)
         CK(cudaMemsetAsync(ctx->accum.p, 0, n_local * sizeof(float4), st0));
     CK(cudaEventRecord(ctx->ev_start, st0));
-    // post-processing (bloom) needs the whole image: it runs after the last batch, so rows cannot leave band by band
-    const bool post = ctx->post_on && fp.world == 1 && post_has_effect(ctx->post) && n_local;
-    const bool band_download = host && host->rgb && fp.world == 1 && !post && batch_pixels % ((size_t)fp.tiles_x * kTilePixels) == 0;
 
-    for (size_t first = 0; first < n_local; first += batch_pixels, batches++) {
+    for (size_t bi = 0; bi < plan.size(); bi++, batches++) {
+        const size_t first = plan[bi].first;
         const int li = batches % n_lanes;
         rt_ctx::Lane& ln = ctx->lanes[li];
         BatchDev& b = bd[li];
@@ -613,7 +641,7 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids
             CK(cudaStreamWaitEvent(st, ctx->ev_start, 0));
             CK(cudaMemsetAsync(ln.counters.p, 0, sizeof(Counters), st));
         }
-        const unsigned n_lp = (unsigned)std::min<size_t>(batch_pixels, n_local - first);
+        const unsigned n_lp = (unsigned)plan[bi].second;
         // primary rays of this batch: pixels of its tiles that lie inside the image, times samples per pixel
         unsigned long long n_primary = 0;
         for (size_t j = first / kTilePixels; j < (first + n_lp) / kTilePixels; j++) {
@@ -688,7 +716,18 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp, float4* out, bool want_ids
             launches++;
             CK(cudaEventRecord(ln.ev_packed, st));
             CK(cudaStreamWaitEvent(ctx->copy, ln.ev_packed, 0));
+            auto trace = [&](cudaStream_t on, const char* what) {
+                if (!ctx->trace_bands)
+                    return;
+                cudaEvent_t e;
+                cudaEventCreate(&e);
+                cudaEventRecord(e, on);
+                ctx->trace_ev.push_back(e);
+                ctx->trace_what.push_back(std::string(what) + " band " + std::to_string(bi) + " lane " + std::to_string(li) + " rows " + std::to_string(row_lo) + ".." + std::to_string(row_hi));
+            };
+            trace(st, "packed");
             CK(cudaMemcpyAsync(host->rgb + 3 * p0, ctx->rgb.p + 3 * p0, (p1 - p0) * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy));
+            trace(ctx->copy, "copied");
         }
         CK(cudaEventRecord(ln.ev_done, st));
     }
@@ -778,6 +817,10 @@ int rt_create(int device, rt_ctx** out)
         return fail(RT_ERR_CUDA, "rt_create: stream / event / pinned allocation failed");
     }
     ctx->own_stream = true;
+    if (const char* e = std::getenv("RTB200_BAND_ORDER")) // developer knob for A/B timing: 0 = bands top to bottom
+        ctx->band_order_outer_first = e[0] != '0';
+    if (const char* e = std::getenv("RTB200_TRACE_BANDS"))
+        ctx->trace_bands = e[0] == '1';
     bool aux_ok = cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming) == cudaSuccess
         && cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming) == cudaSuccess
         && cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking) == cudaSuccess;
@@ -1295,6 +1338,16 @@ int rt_sync(rt_ctx* ctx, rt_stats* stats)
                 ctx->stage_ms[ctx->ev_stage[k / 2]] += ms;
                 ctx->stage_launches[ctx->ev_stage[k / 2]]++;
             }
+        }
+        if (ctx->trace_bands) {
+            for (size_t k = 0; k < ctx->trace_ev.size(); k++) {
+                float ms = 0.0f;
+                cudaEventElapsedTime(&ms, ctx->ev0, ctx->trace_ev[k]);
+                std::fprintf(stderr, "[bands] %7.3f ms %s\n", ms, ctx->trace_what[k].c_str());
+                cudaEventDestroy(ctx->trace_ev[k]);
+            }
+            ctx->trace_ev.clear();
+            ctx->trace_what.clear();
         }
         Counters c; // totals over the lanes used by the frame
         std::memset(&c, 0, sizeof(c));

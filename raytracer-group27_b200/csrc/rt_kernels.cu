@@ -3,6 +3,7 @@
 // kernel cites the reference lines it replaces.
 #include "rt_kernels.h"
 #include "rt_trace.cuh"
+#include <cstdlib>
 
 namespace rtb {
 
@@ -974,6 +975,19 @@ void launch_tri_setup(cudaStream_t st, const float* pos, const float* nrm, const
     k_tri_setup<<<(n + 255) / 256, 256, 0, st>>>(pos, nrm, mesh_id, perm, n, plane, v0, v1, v2, n0, n1, n2);
 }
 
+// Blocks per SM of the persistent traversal kernels: 8 fill the SM (64 registers x 128 threads); frames whose bands are
+// rendered by several lanes at once ask for fewer, so that kernels of different lanes are resident side by side instead of
+// queueing behind each other (rt_capi.cu, enqueue_frame).  RTB200_GRID_MULT overrides both for experiments.
+static int trace_grid_mult(const FrameParams& fp)
+{
+    static const int forced = [] {
+        const char* e = std::getenv("RTB200_GRID_MULT");
+        const int v = e ? std::atoi(e) : 0;
+        return v >= 1 && v <= 16 ? v : 0;
+    }();
+    return forced ? forced : (fp.trace_grid_mult > 0 ? fp.trace_grid_mult : RT_TRACE_GRID_MULT);
+}
+
 void launch_level_reset(cudaStream_t st, Counters* c, int next_q, long long n_current, unsigned long long add_primary, int par)
 {
     k_level_reset<<<1, 1, 0, st>>>(c, next_q, n_current, add_primary, par);
@@ -982,7 +996,7 @@ void launch_level_reset(cudaStream_t st, Counters* c, int next_q, long long n_cu
 void launch_extend(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, int qi,
     int level, unsigned first_lp, bool count)
 {
-    const int grid = sm_count * RT_TRACE_GRID_MULT;
+    const int grid = sm_count * trace_grid_mult(fp);
     if (level == 0) {
         if (count)
             k_extend<true, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b, qi, first_lp);
@@ -1015,7 +1029,7 @@ void launch_shade(cudaStream_t st, int sm_count, const SceneDev& s, const FrameP
 
 void launch_shadow_point(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count)
 {
-    const int grid = sm_count * RT_TRACE_GRID_MULT;
+    const int grid = sm_count * trace_grid_mult(fp);
     const bool anyhit = !fp.any_transparent;
     if (anyhit && count)
         k_shadow_point<true, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b);
@@ -1029,7 +1043,7 @@ void launch_shadow_point(cudaStream_t st, int sm_count, const SceneDev& s, int r
 
 void launch_shadow_sphere(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count)
 {
-    const int grid = sm_count * RT_TRACE_GRID_MULT;
+    const int grid = sm_count * trace_grid_mult(fp);
     const bool anyhit = !fp.any_transparent;
     if (anyhit && count)
         k_shadow_sphere<true, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b);
@@ -1044,7 +1058,7 @@ void launch_shadow_sphere(cudaStream_t st, int sm_count, const SceneDev& s, int 
 
 void launch_shadow_plane(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count)
 {
-    const int grid = sm_count * RT_TRACE_GRID_MULT;
+    const int grid = sm_count * trace_grid_mult(fp);
     const bool anyhit = !fp.any_transparent;
     if (anyhit && count)
         k_shadow_plane<true, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b);

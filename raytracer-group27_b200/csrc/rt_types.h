@@ -91,6 +91,7 @@ struct FrameParams {
     int sl_m, sl_n, sl_rc;
     float sl_sin, sl_omc;
     int sl_group; // lanes cooperating on one (hit, light) pair: smallest power of two >= sl_rc, at most 32
+    int trace_grid_mult; // host side only: blocks per SM of the traversal kernels of this frame (0: the default, rt_kernels.cu)
 };
 
 // Device-resident counters of one wavefront batch.

@@ -477,3 +477,34 @@ def test_cpp_drop_in_renders_the_same_frame(rtb, gpu_ctx, tmp_path):
     cpp4 = np.fromfile(tmp_path / "frame4.bin", np.float32).reshape(256, 256, 3)
     assert np.abs(cpp4 - d_rgb).max() <= 1e-6
     assert (cpp4[d_ids < 0] == 0).all() and (cpp4.reshape(-1, 3) == 1).all(axis=1).sum() > 100 and d_st.shadow_queries == 0
+
+
+def test_host_bands_do_not_depend_on_their_order(rtb, monkeypatch):
+    """rt_render cuts a large frame into bands that leave for the host one by one, rendered from the outside in by several lanes
+    with smaller traversal grids.  The frame must not depend on any of that: bands top to bottom with full grids, the default,
+    and one single batch give the same ids, t, ray counts and (up to the order of the float atomics) pixels."""
+    g = Golden("cornell_c1_256")
+    w, h = 640, 512          # 32 tile rows
+    frames = {}
+    for name, env, shape in (("one batch", {}, (1, 1)), ("top to bottom", {"RTB200_BAND_ORDER": "0", "RTB200_GRID_MULT": "8"}, (3, 4)), ("default", {}, (3, 4)),
+                             ("seven bands", {}, (4, 7))):
+        for k in ("RTB200_BAND_ORDER", "RTB200_GRID_MULT"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ctx = rtb.Context(0)
+        try:
+            ctx.upload_scene(g.scene, rtb.BVH_SAH_HOST)
+            ctx.set_pipeline(shape[0], shape[1], 1 << 12)
+            rgb, ids, t, st = ctx.render(g.camera(), rtb.make_params(w, h, 3), want_ids=True)
+            frames[name] = (rgb, ids, t, (st.primary_rays, st.shadow_queries, st.secondary_rays), st.batches)
+        finally:
+            ctx.close()
+    ref = frames["one batch"]
+    assert (ref[1] >= 0).any() and ref[3][0] == w * h and ref[4] == 1
+    for name in ("top to bottom", "default", "seven bands"):
+        got = frames[name]
+        assert got[4] == (7 if name == "seven bands" else 4), name
+        assert np.array_equal(got[1], ref[1]) and bits_equal(got[2], ref[2]), name
+        assert np.abs(got[0] - ref[0]).max() <= 1e-6, name
+        assert got[3] == ref[3], name

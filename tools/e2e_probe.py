@@ -14,7 +14,7 @@ sc = standin.dragon_standin_scene()
 ctx.upload_scene(sc, rtb200.BVH_SAH_HOST)
 cam, prm = rtb200.make_camera(), rtb200.make_params(3840, 2160, 3)
 pinned = torch.empty(3840 * 2160 * 3, dtype=torch.float32).pin_memory()
-for shape in ((0, 0), (3, 6), (2, 3), (3, 5), (4, 6), (3, 4)):
+for shape in [tuple(int(v) for v in a.split('x')) for a in sys.argv[1:]] or [(0, 0)]:
     ctx.set_pipeline(*shape)
     wall, dev, setup = [], [], []
     for _ in range(12):
