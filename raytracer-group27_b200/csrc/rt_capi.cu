@@ -75,6 +75,9 @@ struct rt_ctx {
     int n_mats = 0;
     std::vector<float> h_pos;
     float coord_max = 1.0f;
+    float tri_lo[3] = { 0, 0, 0 }, tri_hi[3] = { 0, 0, 0 }; // bounds of the uploaded triangle corners
+    std::vector<float> h_sphere_radii;
+    bool cull_primary = true;           // RTB200_CULL_PRIMARY=0 (developer): trace every primary ray
     DevBuf<float> d_pos, d_nrm;
     DevBuf<int> d_mesh, d_perm, d_rank;    // d_rank: visiting rank of every object in the reference's BVH (rt_reforder.cu)
     std::vector<float> h_sphere_centres;   // what d_rank was computed for
@@ -236,6 +239,56 @@ int upload_materials(rt_ctx* ctx, const rt_material* mats, int n_mats)
 }
 
 // Host-side pieces of the camera and sampling set-up; they use libm exactly where the reference does.
+// Pixel rectangle outside of which no camera ray can meet the scene: the eight corners of the scene's bounding box (triangle
+// corners and sphere primitives; the exact geometry, which the padded BVH boxes contain) taken through the inverse of
+// generate_ray's mapping (rt_kernels.cu: pixel -> NDC -> normalize(-nx * halfW, ny * halfH, 1) rotated by q), widened by
+// three pixels for the sub-pixel sample offsets (< 1 pixel) and the float rounding of the device's ray set-up.  A corner
+// beside or behind the eye, or non-finite input, leaves the whole image.
+void visible_pixel_rect(const rt_ctx* ctx, FrameParams& fp)
+{
+    fp.vis_x0 = fp.vis_y0 = 0;
+    fp.vis_x1 = fp.W;
+    fp.vis_y1 = fp.H;
+    if (!ctx->cull_primary || fp.exhaustive)
+        return;
+    double lo[3], hi[3];
+    for (int a = 0; a < 3; a++) {
+        lo[a] = ctx->tri_lo[a];
+        hi[a] = ctx->tri_hi[a];
+    }
+    for (size_t k = 0; k < ctx->h_sphere_radii.size() && k < (size_t)ctx->n_spheres; k++)
+        for (int a = 0; a < 3; a++) {
+            const double r = std::fabs((double)ctx->h_sphere_radii[k]);
+            lo[a] = std::min(lo[a], (double)ctx->h_sphere_centres[3 * k + a] - r);
+            hi[a] = std::max(hi[a], (double)ctx->h_sphere_centres[3 * k + a] + r);
+        }
+    double nx_min = 1e300, nx_max = -1e300, ny_min = 1e300, ny_max = -1e300;
+    const double qx = -fp.qx, qy = -fp.qy, qz = -fp.qz, qw = fp.qw; // inverse rotation: world -> camera
+    for (int c = 0; c < 8; c++) {
+        const double vx = ((c & 1) ? hi[0] : lo[0]) - fp.ox, vy = ((c & 2) ? hi[1] : lo[1]) - fp.oy, vz = ((c & 4) ? hi[2] : lo[2]) - fp.oz;
+        if (!std::isfinite(vx) || !std::isfinite(vy) || !std::isfinite(vz))
+            return;
+        const double uvx = qy * vz - vy * qz, uvy = qz * vx - vz * qx, uvz = qx * vy - vx * qy;
+        const double uux = qy * uvz - uvy * qz, uuy = qz * uvx - uvz * qx, uuz = qx * uvy - uvx * qy;
+        const double cx = vx + (uvx * qw + uux) * 2.0, cy = vy + (uvy * qw + uuy) * 2.0, cz = vz + (uvz * qw + uuz) * 2.0;
+        if (!(cz > 1e-3 * std::max(1.0, std::fabs(vx) + std::fabs(vy) + std::fabs(vz)))) // beside or behind the eye: the projection says nothing
+            return;
+        const double nx = -cx / cz / (double)fp.halfW, ny = cy / cz / (double)fp.halfH;
+        nx_min = std::min(nx_min, nx);
+        nx_max = std::max(nx_max, nx);
+        ny_min = std::min(ny_min, ny);
+        ny_max = std::max(ny_max, ny);
+    }
+    const double x0 = std::floor((nx_min + 1.0) * 0.5 * fp.W) - 3.0, x1 = std::ceil((nx_max + 1.0) * 0.5 * fp.W) + 4.0;
+    const double y0 = std::floor((ny_min + 1.0) * 0.5 * fp.H) - 3.0, y1 = std::ceil((ny_max + 1.0) * 0.5 * fp.H) + 4.0;
+    if (!std::isfinite(x0) || !std::isfinite(x1) || !std::isfinite(y0) || !std::isfinite(y1))
+        return;
+    fp.vis_x0 = (int)std::min((double)fp.W, std::max(0.0, x0));
+    fp.vis_x1 = (int)std::min((double)fp.W, std::max((double)fp.vis_x0, x1));
+    fp.vis_y0 = (int)std::min((double)fp.H, std::max(0.0, y0));
+    fp.vis_y1 = (int)std::min((double)fp.H, std::max((double)fp.vis_y0, y1));
+}
+
 int make_frame_params(const rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, FrameParams& fp)
 {
     if (!cam || !prm)
@@ -346,6 +399,7 @@ int make_frame_params(const rt_ctx* ctx, const rt_camera* cam, const rt_params* 
     while (g < fp.sl_rc && g < 32)
         g <<= 1;
     fp.sl_group = g;
+    visible_pixel_rect(ctx, fp);
     return RT_OK;
 }
 
@@ -819,6 +873,8 @@ int rt_create(int device, rt_ctx** out)
     ctx->own_stream = true;
     if (const char* e = std::getenv("RTB200_BAND_ORDER")) // developer knob for A/B timing: 0 = bands top to bottom
         ctx->band_order_outer_first = e[0] != '0';
+    if (const char* e = std::getenv("RTB200_CULL_PRIMARY"))
+        ctx->cull_primary = e[0] != '0';
     if (const char* e = std::getenv("RTB200_TRACE_BANDS"))
         ctx->trace_bands = e[0] == '1';
     bool aux_ok = cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming) == cudaSuccess
@@ -1027,6 +1083,17 @@ int rt_upload_scene(rt_ctx* ctx, const float* pos, const float* nrm, const int* 
     for (float v : ctx->h_pos)
         cm = std::max(cm, std::fabs(v));
     ctx->coord_max = cm;
+    for (int a = 0; a < 3; a++) {
+        ctx->tri_lo[a] = FLT_MAX;
+        ctx->tri_hi[a] = -FLT_MAX;
+    }
+    for (size_t i = 0; i < ctx->h_pos.size(); i++) { // NaN corners bound nothing (a triangle with one is never hit)
+        const float v = ctx->h_pos[i];
+        if (v < ctx->tri_lo[i % 3])
+            ctx->tri_lo[i % 3] = v;
+        if (v > ctx->tri_hi[i % 3])
+            ctx->tri_hi[i % 3] = v;
+    }
     CK(ctx->d_pos.ensure(9 * (size_t)n_tris));
     CK(ctx->d_nrm.ensure(9 * (size_t)n_tris));
     CK(ctx->d_mesh.ensure((size_t)n_tris));
@@ -1274,6 +1341,9 @@ int rt_set_spheres(rt_ctx* ctx, const rt_sphere* spheres, int n_spheres)
         centres.insert(centres.end(), spheres[i].center, spheres[i].center + 3);
     const bool moved = centres != ctx->h_sphere_centres;
     ctx->h_sphere_centres = centres;
+    ctx->h_sphere_radii.clear();
+    for (int i = 0; i < n_spheres; i++)
+        ctx->h_sphere_radii.push_back(spheres[i].radius);
     ctx->n_spheres = n_spheres;
     if (moved && ctx->bvh_built) { // the spheres are objects of the reference's BVH: its visiting order changes with them
         rc = refresh_tie_keys(ctx);

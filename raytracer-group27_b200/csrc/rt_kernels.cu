@@ -87,16 +87,22 @@ __device__ __forceinline__ void local_to_pixel(const FrameParams& fp, unsigned l
     py = (int)(ty * kTileH + (w >> 2) * 4 + (l >> 3));
 }
 
+// false: the camera rays of this pixel cannot meet the scene (or the pixel is padding outside the image)
+__device__ __forceinline__ bool pixel_sees_scene(const FrameParams& fp, int px, int py)
+{
+    return px >= fp.vis_x0 && px < fp.vis_x1 && py >= fp.vis_y0 && py < fp.vis_y1;
+}
+
 // K1 generate: pixel -> NDC (src/main.cpp:350-353), sub-pixel sample positions (358-375 / 309-335, 377-385) and
 // Trackball::generateRay (framework/src/trackball.cpp:87-98) for primary ray `idx` of the batch starting at local
-// pixel first_lp.  Returns false for rays of padding pixels outside the image.  tag = (local pixel << 1) | first-sample.
+// pixel first_lp.  Returns false for rays of padding pixels outside the image and of pixels that cannot see the scene.  tag = (local pixel << 1) | first-sample.
 __device__ __forceinline__ bool generate_ray(const FrameParams& fp, unsigned first_lp, unsigned idx, f3& o, f3& dir, int& tag)
 {
     const unsigned lp = first_lp + idx / (unsigned)fp.spp;
     const int sidx = (int)(idx % (unsigned)fp.spp);
     int px, py;
     local_to_pixel(fp, lp, px, py);
-    if (px >= fp.W || py >= fp.H)
+    if (!pixel_sees_scene(fp, px, py))
         return false;
     float nx = xsub(xmul(xdiv((float)px, (float)fp.W), 2.0f), 1.0f);
     float ny = xsub(xmul(xdiv((float)py, (float)fp.H), 2.0f), 1.0f);
@@ -388,7 +394,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
             if (LEVEL0) { // padding pixels of ragged tiles have no hit record
                 int px, py;
                 local_to_pixel(fp, first_lp + i / (unsigned)fp.spp, px, py);
-                valid = px < fp.W && py < fp.H;
+                valid = pixel_sees_scene(fp, px, py);
             }
             if (valid)
                 h = b.q[qi].hit[i];
@@ -906,8 +912,9 @@ __global__ void __launch_bounds__(256) k_resolve(FrameParams fp, unsigned first_
         const size_t o = (size_t)(fp.H - 1 - py) * fp.W + px;
         out[o] = make_float4(a.x * fp.sample_scale, a.y * fp.sample_scale, a.z * fp.sample_scale, 1.0f);
         if (out_id) {
-            out_id[o] = prim_id[lp];
-            out_t[o] = prim_t[lp];
+            const bool traced = pixel_sees_scene(fp, px, py);
+            out_id[o] = traced ? prim_id[lp] : -1;
+            out_t[o] = traced ? prim_t[lp] : FLT_MAX;
         }
     }
 }

@@ -91,6 +91,9 @@ struct FrameParams {
     int sl_m, sl_n, sl_rc;
     float sl_sin, sl_omc;
     int sl_group; // lanes cooperating on one (hit, light) pair: smallest power of two >= sl_rc, at most 32
+    // Pixels [vis_x0, vis_x1) x [vis_y0, vis_y1) are the only ones whose camera rays can meet the scene (projection of its
+    // bounding box, rt_capi.cu); the other primary rays are misses without being traced.  Whole image when unknown.
+    int vis_x0, vis_x1, vis_y0, vis_y1;
     int trace_grid_mult; // host side only: blocks per SM of the traversal kernels of this frame (0: the default, rt_kernels.cu)
 };
 
