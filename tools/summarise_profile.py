@@ -49,6 +49,6 @@ for n, r, w in zip(vals["Kernel Name"], vals["dram__bytes_read.sum"], vals["dram
     k = "extend" if "k_extend" in n else "shadow_point" if "k_shadow_point" in n else "shade"
     per.setdefault(k, []).append(float(r) * mul[ur] + float(w) * mul[uw])
 tr = {k: sum(v) / len(v) for k, v in per.items()}
-tr["_note"] = f"dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the captured launches (bounce levels 0-1 of frame 2), ncu --set full, profiles/{tag}_extend_shade_shadow_raw.csv"
+tr["_note"] = f"dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the captured launches (all bounce levels of frame 2), ncu --set full, profiles/{tag}_extend_shade_shadow_raw.csv"
 json.dump(tr, open(os.path.join(dst, "traffic.json"), "w"), indent=1)
 print(tr)
