@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -606,6 +607,7 @@ constexpr int kBandGridMult = 4;
 int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_ids, unsigned batch_rays, const HostTarget* host)
 {
     FrameParams fp = fp_in;
+    const auto host_t0 = std::chrono::steady_clock::now();
     const size_t n_local = (size_t)fp.n_local_tiles * kTilePixels;
     // batch size: the frame split evenly over the lanes, in whole tile rows when this context owns the whole image (so
     // that a finished batch is a band of complete image rows), bounded below (tiny batches are all latency) and above
@@ -811,6 +813,9 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
     ctx->last_launches = launches;
     ctx->last_batches = batches;
     ctx->frame_pending = true;
+    if (ctx->trace_bands)
+        std::fprintf(stderr, "[bands] host: %d launches of %d batches enqueued in %.3f ms\n", launches, batches,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count());
     return RT_OK;
 }
 
