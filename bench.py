@@ -289,11 +289,51 @@ def run_gpu(args):
     h2d_bytes = sc.mats.nbytes + sc.point_lights.nbytes + sc.sphere_lights.nbytes + 32 + 36  # materials + lights + camera + params
     e2e_steps = max(3, min(args.steps, 10))
 
+    # N > 1: the host image is one shared-memory segment that every rank registers with CUDA (page-locked, mapped); each rank
+    # stores the tiles it owns straight into it over its own PCIe link (rt_render_shard) and a barrier ends the step.  If the
+    # segment cannot be shared or registered, rank 0 downloads the gathered device frame instead.
+    shared, shared_ptr, e2e_path = None, 0, "rt_render (bands leave while later bands render)"
+    if world > 1:
+        from multiprocessing import shared_memory
+        nbytes = H * W * 3 * 4
+        ok = torch.ones(1, device="cuda")
+        try:
+            name = [None]
+            if rank == 0:
+                shared = shared_memory.SharedMemory(create=True, size=nbytes)
+                name[0] = shared.name
+            dist.broadcast_object_list(name, src=0)
+            if rank != 0:
+                shared = shared_memory.SharedMemory(name=name[0])
+                try:  # the creator unlinks it; Python < 3.13 would have every attaching process try as well
+                    from multiprocessing import resource_tracker
+                    resource_tracker.unregister(shared._name, "shared_memory")
+                except Exception:
+                    pass
+            view = np.ndarray((H * W * 3,), dtype=np.float32, buffer=shared.buf)
+            if rank == 0:
+                view[:] = 0.0
+            shared_ptr = view.ctypes.data
+            err = torch.cuda.cudart().cudaHostRegister(shared_ptr, nbytes, 1 | 2)  # portable | mapped
+            if int(err) != 0:
+                raise RuntimeError(f"cudaHostRegister: {err}")
+        except Exception as e:
+            ok.zero_()
+            sys.stderr.write(f"[rank {rank}] shared host image unavailable ({e}); rank 0 downloads the gathered frame\n")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            shared_ptr = 0
+        e2e_path = "rt_render_shard (every rank stores its tiles into one shared page-locked host image)" if shared_ptr else "rt_render_device + gather + rank 0 downloads"
+
     def e2e_step():
         ctx.set_materials(sc.mats)                      # the reference re-reads materials and lights every frame
         ctx.set_lights(sc.point_lights, sc.sphere_lights)
         if world == 1:
             return ctx.render_host_ptr(cam, prm, pinned.data_ptr())
+        if shared_ptr:
+            st = ctx.render_shard_host(cam, prm, shared_ptr)
+            dist.barrier()
+            return st
         ctx.render_device(cam, prm, target)
         st = finish_step()
         if rank == 0:
@@ -318,6 +358,21 @@ def run_gpu(args):
         dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(e_r, op=dist.ReduceOp.SUM)
     e2e_value = float(e_r.item()) / float(e_ms.item()) / 1e3
+    if world > 1 and shared_ptr:
+        # the shared host image must be the frame the device-side gather produces
+        ctx.render_device(cam, prm, target)
+        finish_step()
+        if rank == 0:
+            ctx.download_rgb_ptr(gathered.data_ptr() if gather == "nccl_reduce" else ctx.framebuffer()[0], W, H, pinned.data_ptr())
+            diff = float(np.abs(np.ndarray((H * W * 3,), dtype=np.float32, buffer=shared.buf) - pinned.numpy()).max())
+            if not diff <= 1e-6:
+                raise RuntimeError(f"shared host image differs from the gathered frame by {diff}")
+        dist.barrier()
+        torch.cuda.cudart().cudaHostUnregister(shared_ptr)
+    if shared is not None:
+        shared.close()
+        if rank == 0:
+            shared.unlink()
 
     # ---- roofline of the dominant kernel (separate, untimed passes: stage events, then instrumented counters) ----
     ctx.set_pipeline(1, 1)      # one batch, one stream: every kernel runs alone, so its events time it in isolation
@@ -355,8 +410,8 @@ def run_gpu(args):
                        "gather": gather, "l2": "flushed between timed steps (512 MiB memset outside the event pair)",
                        "rays_per_frame": {"primary": int(st.primary_rays), "shadow": int(st.shadow_queries), "secondary": int(st.secondary_rays)} if world == 1 else int(total_rays / args.steps)},
             "clocks": clocks, "wall_ms_per_step_incl_flush_and_sync": wall_ms / args.steps,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(W * H * 3 * 4), "steps": e2e_steps,
-                    "ms_per_step": float(e_ms.item()) / e2e_steps},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes) * world, "d2h_bytes_per_step": int(W * H * 3 * 4), "steps": e2e_steps,
+                    "ms_per_step": float(e_ms.item()) / e2e_steps, "path": e2e_path},
             "gpu_launches": int(launches),
             "roofline": roof,
         }

@@ -233,6 +233,13 @@ int rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, float* rg
  * kernel).  NULL selects the context's own framebuffer.  stats (nullable) is filled by rt_sync. */
 int rt_render_device(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, void* d_rgba);
 int rt_sync(rt_ctx* ctx, rt_stats* stats);
+/* rt_render_shard: rt_render for a sharded context (rt_set_shard), synchronous.  rgb_host_mapped is the WHOLE image's
+ * packed float3 buffer (Screen layout, width*height*3 floats) in page-locked host memory that is mapped into this
+ * context's device (cudaHostRegister with cudaHostRegisterMapped | cudaHostRegisterPortable, or cudaHostAlloc): typically
+ * a shared-memory segment that every rank's process registers.  The frame's last kernel stores the pixels of the tiles
+ * this rank owns straight into it — no staging copy, every GPU over its own PCIe link — and touches nothing else, so after
+ * all ranks have returned the buffer holds the frame renderRayTracing would have left in Screen::m_textureData. */
+int rt_render_shard(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, float* rgb_host_mapped, rt_stats* stats);
 /* Device framebuffer of this context (width*height float4 of the last rt_render_device with d_rgba=NULL). */
 int rt_framebuffer(rt_ctx* ctx, void** d_rgba, int* width, int* height);
 /* CUDA IPC handle (64 bytes) of this context's framebuffer, sized for width x height, so that other ranks can

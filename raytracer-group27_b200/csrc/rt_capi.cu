@@ -598,6 +598,9 @@ int enqueue_postprocess(rt_ctx* ctx, cudaStream_t st, float4* img, int w, int h,
 // Where rt_render wants the finished rows: packed float3 image on the host (pinned for full PCIe speed).
 struct HostTarget {
     float* rgb = nullptr;
+    // rt_render_shard: the whole image's packed float3 buffer in page-locked host memory as THIS device sees it; the
+    // frame's last kernel stores the pixels of this rank's tiles into it (no staging copy)
+    float* mapped_rgb = nullptr;
 };
 
 // Enqueue one frame.  `out`: float4 framebuffer (Screen layout), maybe on a peer GPU.  The frame starts and ends on the
@@ -798,6 +801,10 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
         int rc = enqueue_postprocess(ctx, st0, out, fp.W, fp.H, ctx->post, launches);
         if (rc)
             return rc;
+    }
+    if (host && host->mapped_rgb && n_local) {
+        launch_pack_rgb_tiles(st0, ctx->sm_count, fp, out, host->mapped_rgb);
+        launches++;
     }
     if (host && host->rgb && !band_download && n_local) {
         const size_t npx = (size_t)fp.W * fp.H;
@@ -1393,6 +1400,49 @@ int rt_render_device(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, vo
         out = ctx->fb.p;
     }
     return enqueue_frame(ctx, fp, out, false, ctx->batch_rays, nullptr);
+}
+
+int rt_render_shard(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, float* rgb_host_mapped, rt_stats* stats)
+{
+    int rc = use_device(ctx);
+    if (rc)
+        return rc;
+    rc = check_ready(ctx);
+    if (rc)
+        return rc;
+    if (!rgb_host_mapped)
+        return fail(RT_ERR_INVALID, "rt_render_shard: rgb_host_mapped is null");
+    cudaPointerAttributes attr {};
+    if (cudaPointerGetAttributes(&attr, rgb_host_mapped) != cudaSuccess || !attr.devicePointer
+        || (attr.type != cudaMemoryTypeHost && attr.type != cudaMemoryTypeManaged && attr.type != cudaMemoryTypeDevice)) {
+        cudaGetLastError();
+        return fail(RT_ERR_INVALID, "rt_render_shard: the buffer must be page-locked host memory mapped into the device (cudaHostRegister / cudaHostAlloc)");
+    }
+    FrameParams fp;
+    rc = make_frame_params(ctx, cam, prm, fp);
+    if (rc)
+        return rc;
+    const size_t npx = (size_t)fp.W * fp.H;
+    if (ctx->fb.n < npx || ctx->fb_w != fp.W || ctx->fb_h != fp.H) {
+        CK(ctx->fb.ensure(npx));
+        CK(cudaMemsetAsync(ctx->fb.p, 0, npx * sizeof(float4), ctx->stream));
+        ctx->fb_w = fp.W;
+        ctx->fb_h = fp.H;
+    }
+    unsigned batch = ctx->batch_rays;
+    for (int attempt = 0;; attempt++) {
+        HostTarget host;
+        host.mapped_rgb = static_cast<float*>(attr.devicePointer);
+        rc = enqueue_frame(ctx, fp, ctx->fb.p, false, batch, &host);
+        if (rc)
+            return rc;
+        rc = rt_sync(ctx, stats);
+        if (rc == RT_ERR_OVERFLOW && ctx->last_overflow == 1 && attempt < 3 && batch / 2 >= (unsigned)kTilePixels * (unsigned)fp.spp) {
+            batch /= 2;
+            continue;
+        }
+        return rc;
+    }
 }
 
 int rt_sync(rt_ctx* ctx, rt_stats* stats)

@@ -943,6 +943,42 @@ __global__ void __launch_bounds__(256) k_pack_rgb(const float4* __restrict__ in,
     }
 }
 
+// The pixels of the tiles this rank owns, float4 framebuffer -> packed float3 in `out` (the whole image's buffer, Screen
+// layout).  `out` may be page-locked host memory mapped into the device (rt_render_shard): the stores then cross PCIe
+// directly, every rank over its own link, so they have to be whole lines: one warp takes one tile row (32 pixels), stages
+// its 96 floats in shared memory and 24 lanes write them as float4, 384 contiguous bytes per store instruction (the first
+// version, three 16-byte stores 48 bytes apart per thread, reached 8.6 GB/s over PCIe).  Rows cut by the image's right edge
+// or not 16-byte aligned fall back to scalar stores.
+__global__ void __launch_bounds__(256) k_pack_rgb_tiles(FrameParams fp, const float4* __restrict__ in, float* __restrict__ out)
+{
+    __shared__ __align__(16) float stage[8][3 * kTileW];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const size_t n_rows = (size_t)fp.n_local_tiles * kTileH;
+    for (size_t r = (size_t)blockIdx.x * 8 + wib; r < n_rows; r += (size_t)gridDim.x * 8) {
+        const unsigned j = (unsigned)(r / kTileH), y = (unsigned)(r % kTileH);
+        const unsigned g = (unsigned)fp.rank + j * (unsigned)fp.world;
+        const int px0 = (int)((g % (unsigned)fp.tiles_x) * kTileW), py = (int)((g / (unsigned)fp.tiles_x) * kTileH + y);
+        if (py >= fp.H)
+            continue;
+        const size_t p0 = (size_t)(fp.H - 1 - py) * fp.W + px0;
+        const bool inside = px0 + lane < fp.W;
+        const float4 a = inside ? in[p0 + lane] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (px0 + (int)kTileW <= fp.W && ((3 * p0) & 3) == 0) {
+            stage[wib][3 * lane] = a.x;
+            stage[wib][3 * lane + 1] = a.y;
+            stage[wib][3 * lane + 2] = a.z;
+            __syncwarp();
+            if (lane < 3 * (int)kTileW / 4)
+                reinterpret_cast<float4*>(out + 3 * p0)[lane] = reinterpret_cast<const float4*>(stage[wib])[lane];
+            __syncwarp();
+        } else if (inside) {
+            out[3 * (p0 + lane)] = a.x;
+            out[3 * (p0 + lane) + 1] = a.y;
+            out[3 * (p0 + lane) + 2] = a.z;
+        }
+    }
+}
+
 // Closest hit for caller-supplied rays (rt_intersect).
 __global__ void __launch_bounds__(128) k_intersect(SceneDev s, int root_entry, const float* __restrict__ rays, long long n, int use_bvh,
     int* tri_id, float* t_out, unsigned* overflow)
@@ -1091,6 +1127,13 @@ void launch_pack_rgb(cudaStream_t st, int sm_count, const float4* in, float* out
     if (p1 <= p0)
         return;
     k_pack_rgb<<<grid_for((long long)((p1 - p0 + 3) / 4 + 1), 256, sm_count * 8), 256, 0, st>>>(in, out, p0, p1);
+}
+
+void launch_pack_rgb_tiles(cudaStream_t st, int sm_count, const FrameParams& fp, const float4* in, float* out)
+{
+    if (fp.n_local_tiles <= 0)
+        return;
+    k_pack_rgb_tiles<<<grid_for((long long)fp.n_local_tiles * kTileH * 32, 256, sm_count * 8), 256, 0, st>>>(fp, in, out);
 }
 
 void launch_intersect(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const float* rays, long long n, int use_bvh,

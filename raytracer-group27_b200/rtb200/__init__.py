@@ -118,6 +118,7 @@ SYMBOLS = [
     ("rt_set_shard", _I, [_P, _I, _I]),
     ("rt_render", _I, [_P, C.POINTER(Camera), C.POINTER(Params), _P, _P, _P, C.POINTER(Stats)]),
     ("rt_render_device", _I, [_P, C.POINTER(Camera), C.POINTER(Params), _P]),
+    ("rt_render_shard", _I, [_P, C.POINTER(Camera), C.POINTER(Params), _P, C.POINTER(Stats)]),
     ("rt_sync", _I, [_P, C.POINTER(Stats)]),
     ("rt_framebuffer", _I, [_P, C.POINTER(_P), C.POINTER(_I), C.POINTER(_I)]),
     ("rt_framebuffer_ipc_handle", _I, [_P, _I, _I, _P]),
@@ -403,6 +404,12 @@ class Context:
         """rt_render into caller-owned (ideally pinned) host memory given as an address."""
         st = Stats()
         _check(self._l.rt_render(self._h, C.byref(cam), C.byref(prm), _P(rgb_ptr), None, None, C.byref(st)))
+        return st
+
+    def render_shard_host(self, cam: Camera, prm: Params, rgb_mapped_ptr: int) -> Stats:
+        """rt_render_shard: this rank's tiles stored straight into the whole image's page-locked, device-mapped host buffer."""
+        st = Stats()
+        _check(self._l.rt_render_shard(self._h, C.byref(cam), C.byref(prm), _P(rgb_mapped_ptr), C.byref(st)))
         return st
 
     def render_device(self, cam: Camera, prm: Params, d_rgba: int | None = None):

@@ -508,3 +508,45 @@ def test_host_bands_do_not_depend_on_their_order(rtb, monkeypatch):
         assert np.array_equal(got[1], ref[1]) and bits_equal(got[2], ref[2]), name
         assert np.abs(got[0] - ref[0]).max() <= 1e-6, name
         assert got[3] == ref[3], name
+
+
+def test_render_shard_fills_a_shared_host_image(rtb):
+    """rt_render_shard: every rank stores the tiles it owns straight into one page-locked host image (in a multi-process job a
+    shared-memory segment each rank registers; here three contexts on one GPU and one pinned buffer).  Untouched pixels keep
+    what they held, the union is bit for bit the frame one context renders on its own, ray counts add up, and pageable memory
+    is refused."""
+    import torch
+    g = Golden("cornell_c1_256")
+    w, h = 200, 150      # ragged tiles, and a row pitch (2400 bytes) that allows the 16-byte stores only on every other row group
+    cam, prm = g.camera(), rtb.make_params(w, h, 3)
+    whole = rtb.Context(0)
+    try:
+        whole.upload_scene(g.scene, rtb.BVH_SAH_HOST)
+        want, _, _, st_whole = whole.render(cam, prm)
+    finally:
+        whole.close()
+    image = torch.full((h, w, 3), -7.0, dtype=torch.float32).pin_memory()
+    world, counts = 3, [0, 0, 0]
+    for rank in range(world):
+        ctx = rtb.Context(0)
+        try:
+            ctx.upload_scene(g.scene, rtb.BVH_SAH_HOST)
+            ctx.set_shard(rank, world)
+            before = image.numpy().copy()
+            st = ctx.render_shard_host(cam, prm, image.data_ptr())
+            after = image.numpy()
+            changed = (after != before).any(axis=2)
+            # only pixels of this rank's 32x16 tiles may change (Screen rows are flipped: row r holds y = h - 1 - r)
+            ys, xs = np.nonzero(changed)
+            tiles = ((h - 1 - ys) // 16) * ((w + 31) // 32) + xs // 32
+            assert len(ys) > 0 and (tiles % world == rank).all()
+            for k, v in enumerate((st.primary_rays, st.shadow_queries, st.secondary_rays)):
+                counts[k] += v
+            with pytest.raises(rtb.RtError):
+                ctx.render_shard_host(cam, prm, np.zeros((h, w, 3), np.float32).ctypes.data)   # pageable memory
+        finally:
+            ctx.close()
+    got = image.numpy()
+    assert (got != -7.0).all()
+    assert np.abs(got - want).max() <= 1e-6
+    assert tuple(counts) == (st_whole.primary_rays, st_whole.shadow_queries, st_whole.secondary_rays)
