@@ -188,6 +188,9 @@ def run_gpu(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # NCCL_DEBUG=VERSION makes NCCL print its version on STDOUT, next to the one JSON line this script owes the driver
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     desc, sc, cam, prm = load_workload(args.workload)
     W, H = prm.width, prm.height
