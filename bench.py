@@ -295,7 +295,7 @@ def run_gpu(args):
     # N > 1: the host image is one shared-memory segment that every rank registers with CUDA (page-locked, mapped); each rank
     # stores the tiles it owns straight into it over its own PCIe link (rt_render_shard) and a barrier ends the step.  If the
     # segment cannot be shared or registered, rank 0 downloads the gathered device frame instead.
-    shared, shared_ptr, e2e_path = None, 0, "rt_render (bands leave while later bands render)"
+    shared, shared_ptr, e2e_path = None, 0, "rt_render into page-locked memory (kernels store the frame themselves: background rows during the frame, rows with hits when their batch is resolved)"
     if world > 1:
         from multiprocessing import shared_memory
         nbytes = H * W * 3 * 4

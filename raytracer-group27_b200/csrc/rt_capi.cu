@@ -148,6 +148,9 @@ struct rt_ctx {
     rt_post_params post {};
     DevBuf<int> prim_id, out_id;
     DevBuf<float> prim_t, out_t, rgb;
+    DevBuf<unsigned char> row_flags;    // per 32-pixel tile row: some camera ray hit (k_row_flags)
+    double store_gbs = 0.0;             // rate the paced background stores hold: 85 % of the measured device-to-host copy rate
+    bool zero_copy_host = true;         // RTB200_ZERO_COPY=0 (developer): rt_render always stages bands through the copy engine
     DevBuf<float> rays_in;
     DevBuf<unsigned> flag;
     Counters* h_counters = nullptr; // pinned, one per lane
@@ -601,6 +604,9 @@ struct HostTarget {
     // rt_render_shard: the whole image's packed float3 buffer in page-locked host memory as THIS device sees it; the
     // frame's last kernel stores the pixels of this rank's tiles into it (no staging copy)
     float* mapped_rgb = nullptr;
+    // rt_render with one sample per pixel into such a buffer: tile rows whose camera rays all missed are final (black) after
+    // level 0 and are stored while the other levels are traced; the rows with hits follow when their batch is resolved
+    bool early_background = false;
 };
 
 // Enqueue one frame.  `out`: float4 framebuffer (Screen layout), maybe on a peer GPU.  The frame starts and ends on the
@@ -644,6 +650,18 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
     // post-processing (bloom) needs the whole image: it runs after the last batch, so rows cannot leave band by band
     const bool post = ctx->post_on && fp.world == 1 && post_has_effect(ctx->post) && n_local;
     const bool band_download = host && host->rgb && fp.world == 1 && !post && batch_pixels % ((size_t)fp.tiles_x * kTilePixels) == 0;
+    auto trace_at = [&](cudaStream_t on, const std::string& what) {
+        if (!ctx->trace_bands)
+            return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, on);
+        ctx->trace_ev.push_back(e);
+        ctx->trace_what.push_back(what);
+    };
+    const bool early_bg = host && host->mapped_rgb && host->early_background && fp.world == 1 && fp.spp == 1 && !post && n_local;
+    if (early_bg)
+        CK(ctx->row_flags.ensure(n_local / kTilePixels * kTileH));
     // several lanes render bands side by side: traversal grids of 4 blocks per SM leave room for another lane's kernel
     // (C3 through rt_render, 3 lanes x 6 bands: 3.40 ms with 8 blocks per SM, 3.17 with 4, 3.16 with 3)
     fp.trace_grid_mult = band_download && lanes_wanted > 1 ? kBandGridMult : 0;
@@ -689,6 +707,12 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
         CK(cudaMemsetAsync(ctx->accum.p, 0, n_local * sizeof(float4), st0));
     CK(cudaEventRecord(ctx->ev_start, st0));
 
+    if (early_bg) { // rows outside the scene's projection: on their way before the first ray is traced
+        CK(cudaStreamWaitEvent(ctx->copy, ctx->ev_start, 0));
+        launch_host_background(ctx->copy, ctx->sm_count, fp, 0, (unsigned)fp.n_local_tiles, nullptr, host->mapped_rgb, ctx->store_gbs);
+        launches++;
+        trace_at(ctx->copy, "rows outside the scene's projection stored");
+    }
     for (size_t bi = 0; bi < plan.size(); bi++, batches++) {
         const size_t first = plan[bi].first;
         const int li = batches % n_lanes;
@@ -725,6 +749,16 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
                 SceneDev s_ext = s;
                 s_ext.tie_by_id = fp.tie_by_id; // shadow queries keep the BVH order (shadow.cpp:42)
                 launch_extend(st, ctx->sm_count, s_ext, ctx->root_entry, fp, b, qi, level, (unsigned)first, ctx->counters_enabled);
+            }
+            if (early_bg && level == 0) {
+                // rows of pure background leave for the host now, on the copy stream, next to everything that follows
+                launch_row_flags(st, ctx->sm_count, fp, (unsigned)first, n_lp, b.q[0].hit, ctx->row_flags.p);
+                CK(cudaEventRecord(ln.ev_packed, st));
+                CK(cudaStreamWaitEvent(ctx->copy, ln.ev_packed, 0));
+                trace_at(ctx->copy, "level-0 extend done, batch " + std::to_string(bi));
+                launch_host_background(ctx->copy, ctx->sm_count, fp, (unsigned)(first / kTilePixels), n_lp / kTilePixels, ctx->row_flags.p, host->mapped_rgb, ctx->store_gbs);
+                trace_at(ctx->copy, "background rows stored, batch " + std::to_string(bi));
+                launches += 2;
             }
             {
                 StageScope sc(ctx, RT_STAGE_SHADE, st);
@@ -766,6 +800,12 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
                 want_ids ? ctx->out_t.p : nullptr);
             launches++;
         }
+        if (early_bg) { // the rows of this batch that were hit: straight into the host image
+            trace_at(st, "resolved, batch " + std::to_string(bi));
+            launch_pack_rgb_tiles(st, ctx->sm_count, fp, (unsigned)(first / kTilePixels), n_lp / kTilePixels, ctx->row_flags.p, out, host->mapped_rgb);
+            launches++;
+            trace_at(st, "rows with hits stored, batch " + std::to_string(bi));
+        }
         if (band_download) {
             // this batch is a band of complete image rows: pack it to float3 and send it home while the other lanes render
             const int ty0 = (int)(first / kTilePixels / fp.tiles_x), ty1 = (int)((first + n_lp) / kTilePixels / fp.tiles_x);
@@ -802,8 +842,11 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
         if (rc)
             return rc;
     }
-    if (host && host->mapped_rgb && n_local) {
-        launch_pack_rgb_tiles(st0, ctx->sm_count, fp, out, host->mapped_rgb);
+    if (early_bg) {
+        CK(cudaEventRecord(ctx->ev_copied, ctx->copy));
+        CK(cudaStreamWaitEvent(st0, ctx->ev_copied, 0));
+    } else if (host && host->mapped_rgb && n_local) {
+        launch_pack_rgb_tiles(st0, ctx->sm_count, fp, 0, (unsigned)fp.n_local_tiles, nullptr, out, host->mapped_rgb);
         launches++;
     }
     if (host && host->rgb && !band_download && n_local) {
@@ -885,6 +928,8 @@ int rt_create(int device, rt_ctx** out)
     ctx->own_stream = true;
     if (const char* e = std::getenv("RTB200_BAND_ORDER")) // developer knob for A/B timing: 0 = bands top to bottom
         ctx->band_order_outer_first = e[0] != '0';
+    if (const char* e = std::getenv("RTB200_ZERO_COPY"))
+        ctx->zero_copy_host = e[0] != '0';
     if (const char* e = std::getenv("RTB200_CULL_PRIMARY"))
         ctx->cull_primary = e[0] != '0';
     if (const char* e = std::getenv("RTB200_TRACE_BANDS"))
@@ -1590,6 +1635,37 @@ int rt_download_rgb(rt_ctx* ctx, const void* d_rgba, int width, int height, floa
     return RT_OK;
 }
 
+// Device-to-host rate of this context's link, once: a 16 MB copy into page-locked memory, best of three.
+static int measure_store_rate(rt_ctx* ctx)
+{
+    if (ctx->store_gbs > 0.0)
+        return RT_OK;
+    const size_t bytes = (size_t)16 << 20;
+    void* h = nullptr;
+    DevBuf<unsigned char> d;
+    CK(d.ensure(bytes));
+    if (cudaMallocHost(&h, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        d.release();
+        ctx->store_gbs = 20.0;
+        return RT_OK;
+    }
+    float best = 1e30f;
+    for (int k = 0; k < 3; k++) {
+        cudaEventRecord(ctx->ev0, ctx->stream);
+        cudaMemcpyAsync(h, d.p, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess && ms > 0.0f)
+            best = std::min(best, ms);
+    }
+    cudaFreeHost(h);
+    d.release();
+    ctx->store_gbs = best < 1e29f ? 0.85 * (double)bytes / (best * 1e6) : 20.0;
+    return RT_OK;
+}
+
 int rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, float* rgb_out, int* tri_id_out, float* t_out, rt_stats* stats)
 {
     int rc = use_device(ctx);
@@ -1620,9 +1696,27 @@ int rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, float* rg
     }
     CK(ctx->rgb.ensure(npx * 3 + 4));
     unsigned batch = ctx->batch_rays;
+    // Page-locked memory that this device can address (cudaHostAlloc / cudaHostRegister): the kernels store the frame into it
+    // themselves and the background rows leave right after level 0 (HostTarget); otherwise bands go through the copy engine.
+    float* mapped = nullptr;
+    if (ctx->zero_copy_host && fp.world == 1 && fp.spp == 1 && !(ctx->post_on && post_has_effect(ctx->post))) {
+        cudaPointerAttributes attr {};
+        if (cudaPointerGetAttributes(&attr, rgb_out) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+            mapped = static_cast<float*>(attr.devicePointer);
+        cudaGetLastError();
+        if (mapped) {
+            rc = measure_store_rate(ctx);
+            if (rc)
+                return rc;
+        }
+    }
     for (int attempt = 0;; attempt++) {
         HostTarget host;
-        host.rgb = rgb_out; // finished bands are packed and copied by the lanes while the rest of the frame renders
+        if (mapped) {
+            host.mapped_rgb = mapped;
+            host.early_background = true;
+        } else
+            host.rgb = rgb_out; // finished bands are packed and copied by the lanes while the rest of the frame renders
         rc = enqueue_frame(ctx, fp, ctx->fb.p, want_ids, batch, &host);
         if (rc)
             return rc;

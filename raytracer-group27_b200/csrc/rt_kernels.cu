@@ -3,6 +3,7 @@
 // kernel cites the reference lines it replaces.
 #include "rt_kernels.h"
 #include "rt_trace.cuh"
+#include <algorithm>
 #include <cstdlib>
 
 namespace rtb {
@@ -949,13 +950,16 @@ __global__ void __launch_bounds__(256) k_pack_rgb(const float4* __restrict__ in,
 // its 96 floats in shared memory and 24 lanes write them as float4, 384 contiguous bytes per store instruction (the first
 // version, three 16-byte stores 48 bytes apart per thread, reached 8.6 GB/s over PCIe).  Rows cut by the image's right edge
 // or not 16-byte aligned fall back to scalar stores.
-__global__ void __launch_bounds__(256) k_pack_rgb_tiles(FrameParams fp, const float4* __restrict__ in, float* __restrict__ out)
+__global__ void __launch_bounds__(256) k_pack_rgb_tiles(FrameParams fp, unsigned tile0, unsigned n_tiles, const unsigned char* __restrict__ flags,
+    const float4* __restrict__ in, float* __restrict__ out)
 {
     __shared__ __align__(16) float stage[8][3 * kTileW];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const size_t n_rows = (size_t)fp.n_local_tiles * kTileH;
+    const size_t n_rows = (size_t)n_tiles * kTileH;
     for (size_t r = (size_t)blockIdx.x * 8 + wib; r < n_rows; r += (size_t)gridDim.x * 8) {
-        const unsigned j = (unsigned)(r / kTileH), y = (unsigned)(r % kTileH);
+        const unsigned j = tile0 + (unsigned)(r / kTileH), y = (unsigned)(r % kTileH);
+        if (flags && !flags[(size_t)j * kTileH + y]) // rt_render, rows of background: already on the host (k_host_background)
+            continue;
         const unsigned g = (unsigned)fp.rank + j * (unsigned)fp.world;
         const int px0 = (int)((g % (unsigned)fp.tiles_x) * kTileW), py = (int)((g / (unsigned)fp.tiles_x) * kTileH + y);
         if (py >= fp.H)
@@ -975,6 +979,73 @@ __global__ void __launch_bounds__(256) k_pack_rgb_tiles(FrameParams fp, const fl
             out[3 * (p0 + lane)] = a.x;
             out[3 * (p0 + lane) + 1] = a.y;
             out[3 * (p0 + lane) + 2] = a.z;
+        }
+    }
+}
+
+// rt_render into a device-mapped host image, one sample per pixel: which 32-pixel tile rows of the batch contain a pixel
+// whose camera ray hit something.  The others are background — black, and final as soon as level 0 has been traced.
+// One warp per tile row; flags[tile * kTileH + row] = 1 if any of its pixels was hit.
+__global__ void __launch_bounds__(256) k_row_flags(FrameParams fp, unsigned first_lp, unsigned n_lp, const int2* __restrict__ hit, unsigned char* __restrict__ flags)
+{
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned tile0 = first_lp / kTilePixels;
+    const size_t n_rows = (size_t)(n_lp / kTilePixels) * kTileH;
+    for (size_t r = (size_t)blockIdx.x * 8 + wib; r < n_rows; r += (size_t)gridDim.x * 8) {
+        const unsigned jl = (unsigned)(r / kTileH), y = (unsigned)(r % kTileH);
+        const unsigned g = (unsigned)fp.rank + (tile0 + jl) * (unsigned)fp.world;
+        const int px = (int)((g % (unsigned)fp.tiles_x) * kTileW) + lane, py = (int)((g / (unsigned)fp.tiles_x) * kTileH + y);
+        const unsigned k = ((((y >> 2) * 4 + ((unsigned)lane >> 3)) << 5) + ((y & 3) << 3) + ((unsigned)lane & 7)); // slot of pixel (lane, y) in its tile
+        const bool was_hit = pixel_sees_scene(fp, px, py) && hit[(size_t)jl * kTilePixels + k].y != -1;
+        const bool any = __any_sync(0xffffffffu, was_hit);
+        if (lane == 0)
+            flags[(size_t)(tile0 + jl) * kTileH + y] = any ? 1 : 0;
+    }
+}
+
+// The background rows of the batch (k_row_flags) go to the host image at once, as zeros, while the rest of the frame is
+// still being traced: 384 contiguous bytes per warp store over PCIe.  The kernel is PACED: left alone, its warps queue stores
+// as fast as the LSU takes them, the path to system memory backs up into L2 and the traversal kernels running beside it take
+// 70 % longer.  Every warp therefore sends its k-th row no earlier than k * period_ns after it started (%globaltimer), with the
+// period chosen so that all warps together stay just below what PCIe carries away: nothing queues, the warps sleep in between.
+// flags == nullptr: the rows that lie outside the scene's projection altogether (known before anything is traced); otherwise the
+// other rows whose flag says that no camera ray hit anything.
+__global__ void __launch_bounds__(256) k_host_background(FrameParams fp, unsigned tile0, unsigned n_tiles, const unsigned char* __restrict__ flags, float* __restrict__ out,
+    unsigned period_ns)
+{
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const size_t n_rows = (size_t)n_tiles * kTileH;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    unsigned sent = 0;
+    for (size_t r = (size_t)blockIdx.x * 8 + wib; r < n_rows; r += (size_t)gridDim.x * 8) {
+        const unsigned j = tile0 + (unsigned)(r / kTileH), y = (unsigned)(r % kTileH);
+        if (flags && flags[(size_t)j * kTileH + y])
+            continue;
+        const unsigned g = (unsigned)fp.rank + j * (unsigned)fp.world;
+        const int px0 = (int)((g % (unsigned)fp.tiles_x) * kTileW), py = (int)((g / (unsigned)fp.tiles_x) * kTileH + y);
+        if (py >= fp.H)
+            continue;
+        const bool outside = py < fp.vis_y0 || py >= fp.vis_y1 || px0 + (int)kTileW <= fp.vis_x0 || px0 >= fp.vis_x1;
+        if (outside != (flags == nullptr))
+            continue;
+        for (;;) { // wait for this warp's slot
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            const long long wait = (long long)(t0 + (unsigned long long)sent * period_ns) - (long long)now;
+            if (wait <= 0)
+                break;
+            __nanosleep((unsigned)min(wait, 20000ll));
+        }
+        sent++;
+        const size_t p0 = (size_t)(fp.H - 1 - py) * fp.W + px0;
+        if (px0 + (int)kTileW <= fp.W && ((3 * p0) & 3) == 0) {
+            if (lane < 3 * (int)kTileW / 4)
+                reinterpret_cast<float4*>(out + 3 * p0)[lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        } else if (px0 + lane < fp.W) {
+            out[3 * (p0 + lane)] = 0.0f;
+            out[3 * (p0 + lane) + 1] = 0.0f;
+            out[3 * (p0 + lane) + 2] = 0.0f;
         }
     }
 }
@@ -1129,11 +1200,41 @@ void launch_pack_rgb(cudaStream_t st, int sm_count, const float4* in, float* out
     k_pack_rgb<<<grid_for((long long)((p1 - p0 + 3) / 4 + 1), 256, sm_count * 8), 256, 0, st>>>(in, out, p0, p1);
 }
 
-void launch_pack_rgb_tiles(cudaStream_t st, int sm_count, const FrameParams& fp, const float4* in, float* out)
+void launch_pack_rgb_tiles(cudaStream_t st, int sm_count, const FrameParams& fp, unsigned tile0, unsigned n_tiles, const unsigned char* flags,
+    const float4* in, float* out)
 {
-    if (fp.n_local_tiles <= 0)
+    if (n_tiles == 0)
         return;
-    k_pack_rgb_tiles<<<grid_for((long long)fp.n_local_tiles * kTileH * 32, 256, sm_count * 8), 256, 0, st>>>(fp, in, out);
+    k_pack_rgb_tiles<<<grid_for((long long)n_tiles * kTileH * 32, 256, sm_count * 8), 256, 0, st>>>(fp, tile0, n_tiles, flags, in, out);
+}
+
+void launch_row_flags(cudaStream_t st, int sm_count, const FrameParams& fp, unsigned first_lp, unsigned n_lp, const int2* hit, unsigned char* flags)
+{
+    if (n_lp < (unsigned)kTilePixels)
+        return;
+    k_row_flags<<<grid_for((long long)(n_lp / kTilePixels) * kTileH * 32, 256, sm_count * 8), 256, 0, st>>>(fp, first_lp, n_lp, hit, flags);
+}
+
+// One block on every other SM; the pacing period follows from the number of warps and the rate to hold (`gbs`: a little under what
+// the link carries, measured by the caller; RTB200_BG_GBS / RTB200_BG_BLOCKS override for experiments).
+void launch_host_background(cudaStream_t st, int sm_count, const FrameParams& fp, unsigned tile0, unsigned n_tiles, const unsigned char* flags, float* out,
+    double gbs)
+{
+    if (n_tiles == 0)
+        return;
+    static const int blocks_env = [] {
+        const char* e = std::getenv("RTB200_BG_BLOCKS");
+        return e ? std::atoi(e) : 0;
+    }();
+    static const double gbs_env = [] {
+        const char* e = std::getenv("RTB200_BG_GBS");
+        return e ? std::atof(e) : 0.0;
+    }();
+    if (gbs_env > 0.0)
+        gbs = gbs_env;
+    const int grid = grid_for((long long)n_tiles * kTileH * 32, 256, blocks_env > 0 ? blocks_env : std::max(1, sm_count / 2));
+    const double period = (double)grid * 8.0 * (3.0 * kTileW * 4.0) / std::max(gbs, 1.0); // ns between two rows of one warp
+    k_host_background<<<grid, 256, 0, st>>>(fp, tile0, n_tiles, flags, out, (unsigned)std::max(1.0, period));
 }
 
 void launch_intersect(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const float* rays, long long n, int use_bvh,

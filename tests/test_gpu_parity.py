@@ -550,3 +550,29 @@ def test_render_shard_fills_a_shared_host_image(rtb):
     assert (got != -7.0).all()
     assert np.abs(got - want).max() <= 1e-6
     assert tuple(counts) == (st_whole.primary_rays, st_whole.shadow_queries, st_whole.secondary_rays)
+
+
+@pytest.mark.parametrize("size,shape", [((640, 512), (2, 2)), ((200, 150), (1, 1)), ((1000, 333), (3, 5))])
+def test_render_into_pinned_host_memory_equals_pageable(rtb, size, shape):
+    """rt_render into page-locked memory stores the frame from the kernels themselves (background rows right after level 0, the
+    rows with hits when their batch is resolved); into pageable memory it stages bands through the copy engine.  Same frame
+    either way, every pixel written (the buffer starts as garbage), ids and ray counts equal."""
+    import torch
+    g = Golden("cornell_c1_256")
+    w, h = size
+    ctx = rtb.Context(0)
+    try:
+        ctx.upload_scene(g.scene, rtb.BVH_SAH_HOST)
+        ctx.set_pipeline(shape[0], shape[1], 1 << 12)
+        for cam in (rtb.make_camera(dist=4.5), g.camera(), rtb.make_camera(euler_deg=(70.0, 200.0, 0.0), dist=6.0)):
+            prm = rtb.make_params(w, h, 3)
+            want, ids, t, st = ctx.render(cam, prm, want_ids=True)
+            pinned = torch.full((h, w, 3), float("nan"), dtype=torch.float32).pin_memory()
+            st2 = ctx.render_host_ptr(cam, prm, pinned.data_ptr())
+            got = pinned.numpy()
+            assert np.isfinite(got).all()
+            assert np.abs(got - want).max() <= 1e-6
+            assert (got[ids < 0] == 0).all() and (got[ids >= 0].sum(axis=1) > 0).any()
+            assert (st2.primary_rays, st2.shadow_queries, st2.secondary_rays) == (st.primary_rays, st.shadow_queries, st.secondary_rays)
+    finally:
+        ctx.close()
