@@ -171,7 +171,7 @@ def run_reference(args):
             "config": {"workload": desc, "sample": last["sample"]},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     return 0
 
 
@@ -420,7 +420,7 @@ def run_gpu(args):
         }
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         if target:
             ctx.close_peer_framebuffer(target)
@@ -472,7 +472,30 @@ def roofline(stage, c, prm, workload="c3"):
                      "note": "scene (BVH + triangles ~ 11 MB) is L2-resident: the path is FP32-issue / latency / divergence bound, the HBM fraction is reported as required"}}
 
 
+_REAL_STDOUT = None
+
+
+def _own_stdout():
+    """Libraries below (NCCL prints its version line) write to file descriptor 1; the driver expects ONE JSON line there.  Point fd 1
+    at stderr for the rest of the run and keep the real stdout for that line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _own_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

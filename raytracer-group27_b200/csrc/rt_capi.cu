@@ -659,7 +659,7 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
         ctx->trace_ev.push_back(e);
         ctx->trace_what.push_back(what);
     };
-    const bool early_bg = host && host->mapped_rgb && host->early_background && fp.world == 1 && fp.spp == 1 && !post && n_local;
+    const bool early_bg = host && host->mapped_rgb && host->early_background && fp.spp == 1 && !post && n_local;
     if (early_bg)
         CK(ctx->row_flags.ensure(n_local / kTilePixels * kTileH));
     // several lanes render bands side by side: traversal grids of 4 blocks per SM leave room for another lane's kernel
@@ -1447,6 +1447,37 @@ int rt_render_device(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, vo
     return enqueue_frame(ctx, fp, out, false, ctx->batch_rays, nullptr);
 }
 
+// Device-to-host rate of this context's link, once: a 16 MB copy into page-locked memory, best of three.
+static int measure_store_rate(rt_ctx* ctx)
+{
+    if (ctx->store_gbs > 0.0)
+        return RT_OK;
+    const size_t bytes = (size_t)16 << 20;
+    void* h = nullptr;
+    DevBuf<unsigned char> d;
+    CK(d.ensure(bytes));
+    if (cudaMallocHost(&h, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        d.release();
+        ctx->store_gbs = 20.0;
+        return RT_OK;
+    }
+    float best = 1e30f;
+    for (int k = 0; k < 3; k++) {
+        cudaEventRecord(ctx->ev0, ctx->stream);
+        cudaMemcpyAsync(h, d.p, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess && ms > 0.0f)
+            best = std::min(best, ms);
+    }
+    cudaFreeHost(h);
+    d.release();
+    ctx->store_gbs = best < 1e29f ? 0.85 * (double)bytes / (best * 1e6) : 20.0;
+    return RT_OK;
+}
+
 int rt_render_shard(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, float* rgb_host_mapped, rt_stats* stats)
 {
     int rc = use_device(ctx);
@@ -1467,6 +1498,9 @@ int rt_render_shard(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, flo
     rc = make_frame_params(ctx, cam, prm, fp);
     if (rc)
         return rc;
+    rc = measure_store_rate(ctx);
+    if (rc)
+        return rc;
     const size_t npx = (size_t)fp.W * fp.H;
     if (ctx->fb.n < npx || ctx->fb_w != fp.W || ctx->fb_h != fp.H) {
         CK(ctx->fb.ensure(npx));
@@ -1478,6 +1512,7 @@ int rt_render_shard(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, flo
     for (int attempt = 0;; attempt++) {
         HostTarget host;
         host.mapped_rgb = static_cast<float*>(attr.devicePointer);
+        host.early_background = ctx->zero_copy_host; // (a frame with several samples per pixel is stored when it is complete)
         rc = enqueue_frame(ctx, fp, ctx->fb.p, false, batch, &host);
         if (rc)
             return rc;
@@ -1632,37 +1667,6 @@ int rt_download_rgb(rt_ctx* ctx, const void* d_rgba, int width, int height, floa
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(rgb_out, ctx->rgb.p, npx * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    return RT_OK;
-}
-
-// Device-to-host rate of this context's link, once: a 16 MB copy into page-locked memory, best of three.
-static int measure_store_rate(rt_ctx* ctx)
-{
-    if (ctx->store_gbs > 0.0)
-        return RT_OK;
-    const size_t bytes = (size_t)16 << 20;
-    void* h = nullptr;
-    DevBuf<unsigned char> d;
-    CK(d.ensure(bytes));
-    if (cudaMallocHost(&h, bytes) != cudaSuccess) {
-        cudaGetLastError();
-        d.release();
-        ctx->store_gbs = 20.0;
-        return RT_OK;
-    }
-    float best = 1e30f;
-    for (int k = 0; k < 3; k++) {
-        cudaEventRecord(ctx->ev0, ctx->stream);
-        cudaMemcpyAsync(h, d.p, bytes, cudaMemcpyDeviceToHost, ctx->stream);
-        cudaEventRecord(ctx->ev1, ctx->stream);
-        cudaStreamSynchronize(ctx->stream);
-        float ms = 0.0f;
-        if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess && ms > 0.0f)
-            best = std::min(best, ms);
-    }
-    cudaFreeHost(h);
-    d.release();
-    ctx->store_gbs = best < 1e29f ? 0.85 * (double)bytes / (best * 1e6) : 20.0;
     return RT_OK;
 }
 
