@@ -9,6 +9,17 @@
 Screen::Screen(const glm::ivec2& resolution)
     : m_resolution(resolution), m_textureData(size_t(resolution.x) * size_t(resolution.y), glm::vec3(0.0f))
 {
+    if (!m_textureData.empty()) {
+        m_pageLocked = cudaHostRegister(m_textureData.data(), m_textureData.size() * sizeof(glm::vec3), cudaHostRegisterPortable | cudaHostRegisterMapped) == cudaSuccess;
+        if (!m_pageLocked)
+            cudaGetLastError(); // no device (or no permission to lock pages): the frame then arrives through staged copies
+    }
+}
+
+Screen::~Screen()
+{
+    if (m_pageLocked && cudaHostUnregister(m_textureData.data()) != cudaSuccess)
+        cudaGetLastError();
 }
 
 void Screen::clear(const glm::vec3& color) { std::fill(m_textureData.begin(), m_textureData.end(), color); }

@@ -42,9 +42,16 @@ public:
     [[nodiscard]] std::vector<glm::vec3>& pixels() { return m_textureData; }
     [[nodiscard]] const std::vector<glm::vec3>& pixels() const { return m_textureData; }
 
+    // The pixel storage is page-locked and mapped into the CUDA devices while the Screen lives (when there is a device), so that
+    // renderRayTracing's kernels can store the frame into it themselves (rt_render, rt_b200.h); hence no copies of a Screen.
+    ~Screen();
+    Screen(const Screen&) = delete;
+    Screen& operator=(const Screen&) = delete;
+
 private:
     glm::ivec2 m_resolution;
     std::vector<glm::vec3> m_textureData;
+    bool m_pageLocked = false;
     // defaults of src/screen.h:84-101: no bloom, box kernel applied once, size 5, sigma 2, exposure 0.5, gamma 2.2 off
     rt_post_params m_post { RT_FILTER_NONE, RT_KERNEL_BOX, 1, 5, 2.0f, 0.5f, 0, 2.2f, 0 };
 };
