@@ -223,7 +223,9 @@ int rt_set_shard(rt_ctx* ctx, int rank, int world);
 
 /* ---- render (replaces renderRayTracing, src/main.cpp:340-400, and Screen::setPixel, src/screen.cpp:32-38) ----
  * rt_render: host buffers in, host buffers out, synchronous.  rgb_out: width*height*3 floats in the Screen
- * layout (row H-1-y, column x).  tri_id_out / t_out (nullable): closest-hit triangle id (global index, -1 =
+ * layout (row H-1-y, column x).  Any host memory will do; page-locked memory (cudaHostAlloc / cudaHostRegister, which
+ * host/screen.cpp does for the Screen's pixels) is the fast path: the kernels then store the frame into it themselves, rows of
+ * background while the frame is still being traced, instead of staging bands through the copy engine.  tri_id_out / t_out (nullable): closest-hit triangle id (global index, -1 =
  * miss) and t of the first primary ray of each pixel, same layout. */
 int rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, float* rgb_out, int* tri_id_out,
     float* t_out, rt_stats* stats);
