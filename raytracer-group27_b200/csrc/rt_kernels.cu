@@ -1216,7 +1216,7 @@ void launch_row_flags(cudaStream_t st, int sm_count, const FrameParams& fp, unsi
 }
 
 // One block on every other SM; the pacing period follows from the number of warps and the rate to hold (`gbs`: a little under what
-// the link carries, measured by the caller; RTB200_BG_GBS / RTB200_BG_BLOCKS override for experiments).
+// the link carries, measured by the caller, and this rank's share of what the host absorbs; RTB200_BG_GBS / RTB200_BG_BLOCKS override for experiments).
 void launch_host_background(cudaStream_t st, int sm_count, const FrameParams& fp, unsigned tile0, unsigned n_tiles, const unsigned char* flags, float* out,
     double gbs)
 {
@@ -1230,6 +1230,15 @@ void launch_host_background(cudaStream_t st, int sm_count, const FrameParams& fp
         const char* e = std::getenv("RTB200_BG_GBS");
         return e ? std::atof(e) : 0.0;
     }();
+    // All ranks of a sharded frame store into the same host memory at once, and the host takes in only so much: 8 ranks at
+    // 46 GB/s each back up again (C3 end to end 1.75 ms), at 12 GB/s each they do not (1.21 ms).  RTB200_HOST_GBS: what the host
+    // is assumed to absorb in total.
+    static const double host_gbs = [] {
+        const char* e = std::getenv("RTB200_HOST_GBS");
+        const double v = e ? std::atof(e) : 0.0;
+        return v > 0.0 ? v : 100.0;
+    }();
+    gbs = std::min(gbs, host_gbs / std::max(1, fp.world));
     if (gbs_env > 0.0)
         gbs = gbs_env;
     const int grid = grid_for((long long)n_tiles * kTileH * 32, 256, blocks_env > 0 ? blocks_env : std::max(1, sm_count / 2));
