@@ -1,3 +1,4 @@
+# Developer tool (GPU box): the end-of-round bench line, launch list and ncu --set full capture behind profiles/r01g_*.
 set -x
 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_r01g.json 2> gpurun_out/bench_r01g.err
 python tools/profile_frame.py 3 > gpurun_out/r01g_plain.log 2>&1 && \
