@@ -252,6 +252,12 @@ int rt_close_peer_framebuffer(rt_ctx* ctx, void* d_rgba);
 /* Copy a device float4 framebuffer to a host float3 image (Screen::m_textureData layout). */
 int rt_download_rgb(rt_ctx* ctx, const void* d_rgba, int width, int height, float* rgb_out);
 
+/* Host-only (no GPU needed): the pixel rectangle [rect[0], rect[1]) x [rect[2], rect[3]) (x, then y counted from the bottom as in
+ * src/main.cpp:350-353) outside of which no camera ray of a width x height frame can meet the box [lo, hi].  rt_render uses it
+ * with the scene's bounds to answer those primary rays as misses without tracing them; exported so that its conservativeness can
+ * be tested where there is no device. */
+int rt_visible_rect(const rt_camera* cam, int width, int height, const float lo[3], const float hi[3], int rect[4]);
+
 /* ---- closest hit for caller-supplied rays (replaces BoundingVolumeHierarchy::intersect(Ray&, HitInfo&,
  *      bool useBVH), bounding_volume_hierarchy.cpp:49-78) ----
  * rays: 6 floats each (origin, direction).  tri_id: global triangle index or -1; t: ray.t or FLT_MAX. */

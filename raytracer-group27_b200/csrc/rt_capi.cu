@@ -243,29 +243,40 @@ int upload_materials(rt_ctx* ctx, const rt_material* mats, int n_mats)
 }
 
 // Host-side pieces of the camera and sampling set-up; they use libm exactly where the reference does.
-// Pixel rectangle outside of which no camera ray can meet the scene: the eight corners of the scene's bounding box (triangle
-// corners and sphere primitives; the exact geometry, which the padded BVH boxes contain) taken through the inverse of
-// generate_ray's mapping (rt_kernels.cu: pixel -> NDC -> normalize(-nx * halfW, ny * halfH, 1) rotated by q), widened by
-// three pixels for the sub-pixel sample offsets (< 1 pixel) and the float rounding of the device's ray set-up.  A corner
-// beside or behind the eye, or non-finite input, leaves the whole image.
-void visible_pixel_rect(const rt_ctx* ctx, FrameParams& fp)
+// Camera of the frame (fp.W, fp.H set): glm::quat(eulerAngles) and Trackball::position() (trackball.cpp:65-68), generateRay's half
+// extents (89-90), with the host's libm exactly as the reference evaluates them.
+void camera_to_frame(const rt_camera* cam, FrameParams& fp)
+{
+    const float ex = cam->euler[0] * 0.5f, ey = cam->euler[1] * 0.5f, ez = cam->euler[2] * 0.5f;
+    const float cx = std::cos(ex), cy = std::cos(ey), cz = std::cos(ez);
+    const float sx = std::sin(ex), sy = std::sin(ey), sz = std::sin(ez);
+    fp.qw = cx * cy * cz + sx * sy * sz;
+    fp.qx = sx * cy * cz - cx * sy * sz;
+    fp.qy = cx * sy * cz + sx * cy * sz;
+    fp.qz = cx * cy * sz - sx * sy * cz;
+    {
+        // q * (0, 0, -dist): uv = cross(qv, v), uuv = cross(qv, uv), v + ((uv*w) + uuv) * 2
+        const float vx = 0.0f, vy = 0.0f, vz = -cam->dist;
+        const float uvx = fp.qy * vz - vy * fp.qz, uvy = fp.qz * vx - vz * fp.qx, uvz = fp.qx * vy - vx * fp.qy;
+        const float uux = fp.qy * uvz - uvy * fp.qz, uuy = fp.qz * uvx - uvz * fp.qx, uuz = fp.qx * uvy - uvx * fp.qy;
+        fp.ox = cam->look_at[0] + (vx + ((uvx * fp.qw) + uux) * 2.0f);
+        fp.oy = cam->look_at[1] + (vy + ((uvy * fp.qw) + uuy) * 2.0f);
+        fp.oz = cam->look_at[2] + (vz + ((uvz * fp.qw) + uuz) * 2.0f);
+    }
+    fp.halfH = std::tan(cam->fovy / 2.0f);
+    fp.halfW = (float(fp.W) / float(fp.H)) * fp.halfH;
+}
+
+// Pixel rectangle outside of which no camera ray can meet the box [lo, hi]: its eight corners taken through the inverse of
+// generate_ray's mapping (rt_kernels.cu: pixel -> NDC -> normalize(-nx * halfW, ny * halfH, 1) rotated by q), widened by three
+// pixels for the sub-pixel sample offsets (< 1 pixel) and the float rounding of the device's ray set-up.  A corner beside or
+// behind the eye, or non-finite input, leaves the whole image.  (The projection of a convex body in front of the eye is the
+// hull of its projected corners, so their bounding rectangle contains it.)
+void box_pixel_rect(const double lo[3], const double hi[3], FrameParams& fp)
 {
     fp.vis_x0 = fp.vis_y0 = 0;
     fp.vis_x1 = fp.W;
     fp.vis_y1 = fp.H;
-    if (!ctx->cull_primary || fp.exhaustive)
-        return;
-    double lo[3], hi[3];
-    for (int a = 0; a < 3; a++) {
-        lo[a] = ctx->tri_lo[a];
-        hi[a] = ctx->tri_hi[a];
-    }
-    for (size_t k = 0; k < ctx->h_sphere_radii.size() && k < (size_t)ctx->n_spheres; k++)
-        for (int a = 0; a < 3; a++) {
-            const double r = std::fabs((double)ctx->h_sphere_radii[k]);
-            lo[a] = std::min(lo[a], (double)ctx->h_sphere_centres[3 * k + a] - r);
-            hi[a] = std::max(hi[a], (double)ctx->h_sphere_centres[3 * k + a] + r);
-        }
     double nx_min = 1e300, nx_max = -1e300, ny_min = 1e300, ny_max = -1e300;
     const double qx = -fp.qx, qy = -fp.qy, qz = -fp.qz, qw = fp.qw; // inverse rotation: world -> camera
     for (int c = 0; c < 8; c++) {
@@ -291,6 +302,29 @@ void visible_pixel_rect(const rt_ctx* ctx, FrameParams& fp)
     fp.vis_x1 = (int)std::min((double)fp.W, std::max((double)fp.vis_x0, x1));
     fp.vis_y0 = (int)std::min((double)fp.H, std::max(0.0, y0));
     fp.vis_y1 = (int)std::min((double)fp.H, std::max((double)fp.vis_y0, y1));
+}
+
+// The rectangle for this context's scene: bounds of the triangle corners and the sphere primitives (the exact geometry, which the
+// padded BVH boxes contain).  Whole image for the exhaustive search, which the full-size tests compare against.
+void visible_pixel_rect(const rt_ctx* ctx, FrameParams& fp)
+{
+    fp.vis_x0 = fp.vis_y0 = 0;
+    fp.vis_x1 = fp.W;
+    fp.vis_y1 = fp.H;
+    if (!ctx->cull_primary || fp.exhaustive)
+        return;
+    double lo[3], hi[3];
+    for (int a = 0; a < 3; a++) {
+        lo[a] = ctx->tri_lo[a];
+        hi[a] = ctx->tri_hi[a];
+    }
+    for (size_t k = 0; k < ctx->h_sphere_radii.size() && k < (size_t)ctx->n_spheres; k++)
+        for (int a = 0; a < 3; a++) {
+            const double r = std::fabs((double)ctx->h_sphere_radii[k]);
+            lo[a] = std::min(lo[a], (double)ctx->h_sphere_centres[3 * k + a] - r);
+            hi[a] = std::max(hi[a], (double)ctx->h_sphere_centres[3 * k + a] + r);
+        }
+    box_pixel_rect(lo, hi, fp);
 }
 
 int make_frame_params(const rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, FrameParams& fp)
@@ -328,25 +362,7 @@ int make_frame_params(const rt_ctx* ctx, const rt_camera* cam, const rt_params* 
     } else if (prm->sample_mode != 0) {
         return fail(RT_ERR_INVALID, "sample_mode must be 0, 1 or 2");
     }
-    // glm::quat(eulerAngles) and Trackball::position() (trackball.cpp:65-68), generateRay's half extents (89-90)
-    const float ex = cam->euler[0] * 0.5f, ey = cam->euler[1] * 0.5f, ez = cam->euler[2] * 0.5f;
-    const float cx = std::cos(ex), cy = std::cos(ey), cz = std::cos(ez);
-    const float sx = std::sin(ex), sy = std::sin(ey), sz = std::sin(ez);
-    fp.qw = cx * cy * cz + sx * sy * sz;
-    fp.qx = sx * cy * cz - cx * sy * sz;
-    fp.qy = cx * sy * cz + sx * cy * sz;
-    fp.qz = cx * cy * sz - sx * sy * cz;
-    {
-        // q * (0, 0, -dist): uv = cross(qv, v), uuv = cross(qv, uv), v + ((uv*w) + uuv) * 2
-        const float vx = 0.0f, vy = 0.0f, vz = -cam->dist;
-        const float uvx = fp.qy * vz - vy * fp.qz, uvy = fp.qz * vx - vz * fp.qx, uvz = fp.qx * vy - vx * fp.qy;
-        const float uux = fp.qy * uvz - uvy * fp.qz, uuy = fp.qz * uvx - uvz * fp.qx, uuz = fp.qx * uvy - uvx * fp.qy;
-        fp.ox = cam->look_at[0] + (vx + ((uvx * fp.qw) + uux) * 2.0f);
-        fp.oy = cam->look_at[1] + (vy + ((uvy * fp.qw) + uuy) * 2.0f);
-        fp.oz = cam->look_at[2] + (vz + ((uvz * fp.qw) + uuz) * 2.0f);
-    }
-    fp.halfH = std::tan(cam->fovy / 2.0f);
-    fp.halfW = (float(fp.W) / float(fp.H)) * fp.halfH;
+    camera_to_frame(cam, fp);
     fp.tiles_x = (fp.W + kTileW - 1) / kTileW;
     fp.tiles_y = (fp.H + kTileH - 1) / kTileH;
     fp.rank = ctx->rank;
@@ -1445,6 +1461,24 @@ int rt_render_device(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, vo
         out = ctx->fb.p;
     }
     return enqueue_frame(ctx, fp, out, false, ctx->batch_rays, nullptr);
+}
+
+int rt_visible_rect(const rt_camera* cam, int width, int height, const float lo[3], const float hi[3], int rect[4])
+{
+    if (!cam || !lo || !hi || !rect || width <= 0 || height <= 0)
+        return fail(RT_ERR_INVALID, "rt_visible_rect: null argument or empty image");
+    FrameParams fp;
+    std::memset(&fp, 0, sizeof(fp));
+    fp.W = width;
+    fp.H = height;
+    camera_to_frame(cam, fp);
+    const double l[3] = { lo[0], lo[1], lo[2] }, h[3] = { hi[0], hi[1], hi[2] };
+    box_pixel_rect(l, h, fp);
+    rect[0] = fp.vis_x0;
+    rect[1] = fp.vis_x1;
+    rect[2] = fp.vis_y0;
+    rect[3] = fp.vis_y1;
+    return RT_OK;
 }
 
 // Device-to-host rate of this context's link, once: a 16 MB copy into page-locked memory, best of three.

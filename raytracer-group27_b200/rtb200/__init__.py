@@ -118,6 +118,7 @@ SYMBOLS = [
     ("rt_set_shard", _I, [_P, _I, _I]),
     ("rt_render", _I, [_P, C.POINTER(Camera), C.POINTER(Params), _P, _P, _P, C.POINTER(Stats)]),
     ("rt_render_device", _I, [_P, C.POINTER(Camera), C.POINTER(Params), _P]),
+    ("rt_visible_rect", _I, [C.POINTER(Camera), C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     ("rt_render_shard", _I, [_P, C.POINTER(Camera), C.POINTER(Params), _P, C.POINTER(Stats)]),
     ("rt_sync", _I, [_P, C.POINTER(Stats)]),
     ("rt_framebuffer", _I, [_P, C.POINTER(_P), C.POINTER(_I), C.POINTER(_I)]),
@@ -228,6 +229,15 @@ def make_camera(look_at=(0.0, 0.0, 0.0), euler_deg=(20.0, 20.0, 0.0), dist=3.0, 
     cam.dist = float(dist)
     cam.fovy = float(np.float32(fovy_deg) * k)
     return cam
+
+
+def visible_rect(cam: Camera, width: int, height: int, lo, hi):
+    """rt_visible_rect: (x0, x1, y0, y1), half-open, y from the bottom."""
+    l = (C.c_float * 3)(*[float(v) for v in lo])
+    h = (C.c_float * 3)(*[float(v) for v in hi])
+    r = (C.c_int * 4)()
+    _check(lib().rt_visible_rect(C.byref(cam), int(width), int(height), l, h, r))
+    return tuple(r)
 
 
 def make_params(width, height, max_level=5, sphere_rays=10, refraction=0.8, sample_mode=0, sample_size=4, exhaustive=False, plane_rays_1d=3, use_bvh=True, glossy_rays=1, texture_debug=False) -> Params:

@@ -276,3 +276,61 @@ def test_png_textures_decode_like_the_reference_image_reader(rtb, tmp_path):
     # a file the MTL names but that is not there (the reference snapshot lacks two of its texture blobs)
     sc = _load_textured(rtb, tmp_path, "nowhere.png")
     assert sc.textures == [] and sc.n_tris == 1
+
+
+def test_visible_rect_never_culls_a_ray_that_meets_the_box(rtb):
+    """rt_visible_rect (the rectangle rt_render uses to answer primary rays as misses without tracing them) must be
+    conservative: for random cameras and boxes, no camera ray of a pixel outside the rectangle — at the pixel corner or at any
+    sub-pixel sample position (offsets below one pixel) — meets the box; and the rectangle is not trivially the whole image."""
+    rng = np.random.default_rng(11)
+
+    def rays(cam, w, h, px, py):  # Trackball::generateRay (framework/src/trackball.cpp:87-98) in float64
+        ex, ey, ez = (0.5 * float(v) for v in cam.euler)
+        cx, cy, cz, sx, sy, sz = np.cos(ex), np.cos(ey), np.cos(ez), np.sin(ex), np.sin(ey), np.sin(ez)
+        qw, qv = cx * cy * cz + sx * sy * sz, np.array([sx * cy * cz - cx * sy * sz, cx * sy * cz + sx * cy * sz, cx * cy * sz - sx * sy * cz])
+
+        def rot(v):
+            uv = np.cross(qv, v)
+            return v + (uv * qw + np.cross(qv, uv)) * 2.0
+        o = np.array(cam.look_at, np.float64) + rot(np.array([0.0, 0.0, -float(cam.dist)]))
+        half_h = np.tan(float(cam.fovy) / 2.0)
+        half_w = w / h * half_h
+        nx, ny = px / w * 2.0 - 1.0, py / h * 2.0 - 1.0
+        c = np.stack([-nx * half_w, ny * half_h, np.ones_like(nx)], axis=-1)
+        c /= np.linalg.norm(c, axis=-1, keepdims=True)
+        return o, rot(c)
+
+    def hits(o, d, lo, hi):  # slab test, origin outside or inside, t >= 0
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t0, t1 = (lo - o) / d, (hi - o) / d
+        tn, tf = np.minimum(t0, t1).max(axis=-1), np.maximum(t0, t1).min(axis=-1)
+        return (tn <= tf) & (tf >= 0)
+
+    culled_something = 0
+    for trial in range(60):
+        w, h = int(rng.integers(40, 400)), int(rng.integers(40, 300))
+        centre = rng.uniform(-1.5, 1.5, 3)
+        half = rng.uniform(0.01, 1.2, 3)
+        lo, hi = centre - half, centre + half
+        cam = rtb.make_camera(look_at=tuple(rng.uniform(-0.5, 0.5, 3)), euler_deg=tuple(rng.uniform(-180, 180, 3) * (1, 1, 0.2)),
+                              dist=float(rng.uniform(0.3, 8.0)), fovy_deg=float(rng.uniform(20, 100)))
+        x0, x1, y0, y1 = rtb.visible_rect(cam, w, h, lo, hi)
+        assert 0 <= x0 <= x1 <= w and 0 <= y0 <= y1 <= h
+        py, px = np.mgrid[0:h, 0:w]
+        outside = (px < x0) | (px >= x1) | (py < y0) | (py >= y1)
+        culled_something += int(outside.any())
+        if not outside.any():
+            continue
+        for dx in (-0.9, 0.0, 0.9):
+            for dy in (-0.9, 0.0, 0.9):
+                o, d = rays(cam, w, h, px[outside] + dx, py[outside] + dy)
+                assert not hits(o, d, lo, hi).any(), (trial, dx, dy)
+        # and it is tight to a few pixels: the rays of the rectangle's four edges (3 pixels further in) do meet the box somewhere
+        if x1 - x0 > 12 and y1 - y0 > 12 and x0 > 0 and x1 < w and y0 > 0 and y1 < h:
+            ys, xs = np.mgrid[y0:y1, x0:x1]
+            o, d = rays(cam, w, h, xs.astype(np.float64), ys.astype(np.float64))
+            m = hits(o, d, lo, hi)
+            assert m[:, :8].any() and m[:, -8:].any() and m[:8, :].any() and m[-8:, :].any(), trial
+    assert culled_something >= 20
+    # a corner behind the eye: the whole image
+    assert rtb.visible_rect(rtb.make_camera(dist=0.5), 64, 48, (-1, -1, -1), (1, 1, 1)) == (0, 64, 0, 48)
