@@ -300,12 +300,20 @@ def run_gpu(args):
         from multiprocessing import shared_memory
         nbytes = H * W * 3 * 4
         ok = torch.ones(1, device="cuda")
-        try:
-            name = [None]
-            if rank == 0:
+        name = [None]
+        if rank == 0:
+            try:
+                vfs = os.statvfs("/dev/shm")   # a segment larger than the tmpfs would end in SIGBUS on first touch, not in an exception
+                if vfs.f_bavail * vfs.f_frsize < nbytes + (16 << 20):
+                    raise RuntimeError("/dev/shm is too small for the frame")
                 shared = shared_memory.SharedMemory(create=True, size=nbytes)
                 name[0] = shared.name
-            dist.broadcast_object_list(name, src=0)
+            except Exception as e:
+                sys.stderr.write(f"[rank 0] no shared-memory segment ({e})\n")
+        dist.broadcast_object_list(name, src=0)    # every rank gets here, whatever happened on rank 0
+        try:
+            if name[0] is None:
+                raise RuntimeError("rank 0 could not create the segment")
             if rank != 0:
                 shared = shared_memory.SharedMemory(name=name[0])
                 try:  # the creator unlinks it; Python < 3.13 would have every attaching process try as well
