@@ -620,7 +620,7 @@ struct HostTarget {
     // rt_render_shard: the whole image's packed float3 buffer in page-locked host memory as THIS device sees it; the
     // frame's last kernel stores the pixels of this rank's tiles into it (no staging copy)
     float* mapped_rgb = nullptr;
-    // rt_render with one sample per pixel into such a buffer: tile rows whose camera rays all missed are final (black) after
+    // rt_render into such a buffer: tile rows whose camera rays all missed are final (black) after
     // level 0 and are stored while the other levels are traced; the rows with hits follow when their batch is resolved
     bool early_background = false;
 };
@@ -675,7 +675,7 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
         ctx->trace_ev.push_back(e);
         ctx->trace_what.push_back(what);
     };
-    const bool early_bg = host && host->mapped_rgb && host->early_background && fp.spp == 1 && !post && n_local;
+    const bool early_bg = host && host->mapped_rgb && host->early_background && !post && n_local;
     if (early_bg)
         CK(ctx->row_flags.ensure(n_local / kTilePixels * kTileH));
     // several lanes render bands side by side: traversal grids of 4 blocks per SM leave room for another lane's kernel
@@ -1546,7 +1546,7 @@ int rt_render_shard(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, flo
     for (int attempt = 0;; attempt++) {
         HostTarget host;
         host.mapped_rgb = static_cast<float*>(attr.devicePointer);
-        host.early_background = ctx->zero_copy_host; // (a frame with several samples per pixel is stored when it is complete)
+        host.early_background = ctx->zero_copy_host && fp.spp == 1; // (a frame with several samples per pixel is stored when it is complete)
         rc = enqueue_frame(ctx, fp, ctx->fb.p, false, batch, &host);
         if (rc)
             return rc;
@@ -1736,8 +1736,12 @@ int rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, float* rg
     unsigned batch = ctx->batch_rays;
     // Page-locked memory that this device can address (cudaHostAlloc / cudaHostRegister): the kernels store the frame into it
     // themselves and the background rows leave right after level 0 (HostTarget); otherwise bands go through the copy engine.
+    // Frames with several samples per pixel take that path when they fit the batches the lanes render side by side (the rows with
+    // hits are stored unpaced when a batch is resolved, which must not run next to a later batch's traversal for long).
     float* mapped = nullptr;
-    if (ctx->zero_copy_host && fp.world == 1 && fp.spp == 1 && !(ctx->post_on && post_has_effect(ctx->post))) {
+    const bool big = npx >= ((size_t)1 << 22);
+    const bool fits = fp.spp == 1 || (ctx->n_lanes <= 0 && npx * (size_t)fp.spp <= (big ? 2 : 1) * (size_t)ctx->batch_rays);
+    if (ctx->zero_copy_host && fp.world == 1 && fits && !(ctx->post_on && post_has_effect(ctx->post))) {
         cudaPointerAttributes attr {};
         if (cudaPointerGetAttributes(&attr, rgb_out) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
             mapped = static_cast<float*>(attr.devicePointer);

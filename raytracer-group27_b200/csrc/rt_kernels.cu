@@ -983,8 +983,8 @@ __global__ void __launch_bounds__(256) k_pack_rgb_tiles(FrameParams fp, unsigned
     }
 }
 
-// rt_render into a device-mapped host image, one sample per pixel: which 32-pixel tile rows of the batch contain a pixel
-// whose camera ray hit something.  The others are background — black, and final as soon as level 0 has been traced.
+// rt_render into a device-mapped host image: which 32-pixel tile rows of the batch contain a pixel one of whose camera rays
+// hit something.  The others are background — black, and final as soon as level 0 has been traced.
 // One warp per tile row; flags[tile * kTileH + row] = 1 if any of its pixels was hit.
 __global__ void __launch_bounds__(256) k_row_flags(FrameParams fp, unsigned first_lp, unsigned n_lp, const int2* __restrict__ hit, unsigned char* __restrict__ flags)
 {
@@ -996,7 +996,12 @@ __global__ void __launch_bounds__(256) k_row_flags(FrameParams fp, unsigned firs
         const unsigned g = (unsigned)fp.rank + (tile0 + jl) * (unsigned)fp.world;
         const int px = (int)((g % (unsigned)fp.tiles_x) * kTileW) + lane, py = (int)((g / (unsigned)fp.tiles_x) * kTileH + y);
         const unsigned k = ((((y >> 2) * 4 + ((unsigned)lane >> 3)) << 5) + ((y & 3) << 3) + ((unsigned)lane & 7)); // slot of pixel (lane, y) in its tile
-        const bool was_hit = pixel_sees_scene(fp, px, py) && hit[(size_t)jl * kTilePixels + k].y != -1;
+        bool was_hit = false;
+        if (pixel_sees_scene(fp, px, py)) {
+            const int2* h = hit + ((size_t)jl * kTilePixels + k) * (size_t)fp.spp; // the samples of a pixel are neighbours in the queue
+            for (int sidx = 0; sidx < fp.spp; sidx++)
+                was_hit |= h[sidx].y != -1;
+        }
         const bool any = __any_sync(0xffffffffu, was_hit);
         if (lane == 0)
             flags[(size_t)(tile0 + jl) * kTileH + y] = any ? 1 : 0;

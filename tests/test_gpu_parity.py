@@ -564,15 +564,21 @@ def test_render_into_pinned_host_memory_equals_pageable(rtb, size, shape):
     try:
         ctx.upload_scene(g.scene, rtb.BVH_SAH_HOST)
         ctx.set_pipeline(shape[0], shape[1], 1 << 12)
-        for cam in (rtb.make_camera(dist=4.5), g.camera(), rtb.make_camera(euler_deg=(70.0, 200.0, 0.0), dist=6.0)):
-            prm = rtb.make_params(w, h, 3)
+        for k, cam in enumerate((rtb.make_camera(dist=4.5), g.camera(), rtb.make_camera(euler_deg=(70.0, 200.0, 0.0), dist=6.0))):
+            # one sample per pixel, and (automatic pipeline only) the 4-tap and 16-sample modes: a pixel is background when all its samples miss
+            mode = (0, 1, 2)[k] if shape == (1, 1) else 0
+            if mode:
+                ctx.set_pipeline(0, 1)
+            prm = rtb.make_params(w, h, 3, sample_mode=mode, sample_size=16)
             want, ids, t, st = ctx.render(cam, prm, want_ids=True)
             pinned = torch.full((h, w, 3), float("nan"), dtype=torch.float32).pin_memory()
             st2 = ctx.render_host_ptr(cam, prm, pinned.data_ptr())
             got = pinned.numpy()
             assert np.isfinite(got).all()
             assert np.abs(got - want).max() <= 1e-6
-            assert (got[ids < 0] == 0).all() and (got[ids >= 0].sum(axis=1) > 0).any()
+            assert (got[ids >= 0].sum(axis=1) > 0).any()
+            if mode == 0:   # (with several samples the ids are those of the pixel's first sample only)
+                assert (got[ids < 0] == 0).all()
             assert (st2.primary_rays, st2.shadow_queries, st2.secondary_rays) == (st.primary_rays, st.shadow_queries, st.secondary_rays)
     finally:
         ctx.close()
