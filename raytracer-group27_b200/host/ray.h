@@ -6,7 +6,6 @@
 #include <limits>
 
 struct Ray {
-    glm::vec3 origin { 0.0f };
-    glm::vec3 direction { 0.0f, 0.0f, -1.0f };
-    float t { std::numeric_limits<float>::max() };
+    glm::vec3 origin { 0.0f }, direction { 0.0f, 0.0f, -1.0f };
+    float t { std::numeric_limits<float>::max() }; // closest hit so far along normalize(direction); max = nothing hit
 };
