@@ -334,3 +334,20 @@ def test_visible_rect_never_culls_a_ray_that_meets_the_box(rtb):
     assert culled_something >= 20
     # a corner behind the eye: the whole image
     assert rtb.visible_rect(rtb.make_camera(dist=0.5), 64, 48, (-1, -1, -1), (1, 1, 1)) == (0, 64, 0, 48)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the reference's own CPU code on the host cores; the one place besides the tests that runs the
+    oracle) owes the driver exactly ONE line on stdout, a JSON object with the contract's keys; everything else goes to stderr."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "Mrays/s" and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "sample" in d["config"] and d["gpu_launches"] == 0
