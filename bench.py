@@ -121,6 +121,9 @@ def cpu_reference_sample(sc, cam, prm, target_seconds, threads=0, stride=None):
     import oracle
     kind = "reference" if oracle.available("reference") else "port"
     o = oracle.Oracle(kind)
+    if threads <= 0:
+        # every core this process may use — said explicitly, because torchrun exports OMP_NUM_THREADS=1 to its workers
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
     def run(step):
         _, _, _, st = o.render(sc.pos, sc.nrm, sc.mesh_id, sc.mats, sc.point_lights, sc.sphere_lights, cam, prm.width, prm.height,
