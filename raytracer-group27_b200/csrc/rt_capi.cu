@@ -172,12 +172,20 @@ struct rt_ctx {
         SceneDev s;
         s.nodes = nodes;
         s.tri_plane = d_plane.p;
-        s.tri_v0 = d_v0.p;
-        s.tri_v1 = d_v1.p;
-        s.tri_v2 = d_v2.p;
         s.tri_n0 = d_n0.p;
-        s.tri_n1 = d_n1.p;
-        s.tri_n2 = d_n2.p;
+        if (RT_TRI_AOS) { // one 64-byte record per triangle in d_plane / d_n0
+            s.tri_v0 = d_plane.p + 1;
+            s.tri_v1 = d_plane.p + 2;
+            s.tri_v2 = d_plane.p + 3;
+            s.tri_n1 = d_n0.p + 1;
+            s.tri_n2 = d_n0.p + 2;
+        } else {
+            s.tri_v0 = d_v0.p;
+            s.tri_v1 = d_v1.p;
+            s.tri_v2 = d_v2.p;
+            s.tri_n1 = d_n1.p;
+            s.tri_n2 = d_n2.p;
+        }
         s.mats = d_mats.p;
         s.point_lights = d_point.p;
         s.sphere_lights = d_sphere.p;
@@ -903,7 +911,10 @@ int refresh_tie_keys(rt_ctx* ctx)
     const char* err = nullptr;
     if (reference_visit_rank(ctx->stream, ctx->d_pos.p, ctx->user_tris, ctx->d_spheres.p, ctx->n_spheres, ctx->d_rank.p, &err) != 0)
         return fail(RT_ERR_CUDA, std::string("reference visiting order: ") + (err ? err : "failed"));
-    launch_apply_tie_keys(ctx->stream, ctx->d_v0.p, ctx->d_v2.p, ctx->d_rank.p, ctx->n_tris, ctx->user_tris);
+    {
+        const SceneDev sd = ctx->scene_dev();
+        launch_apply_tie_keys(ctx->stream, const_cast<float4*>(sd.tri_v0), sd.tri_v2, ctx->d_rank.p, ctx->n_tris, ctx->user_tris);
+    }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
     return RT_OK;
@@ -1196,13 +1207,15 @@ int rt_build_bvh(rt_ctx* ctx, int mode)
     // farthest zoom (distance 100, trackball.cpp:150) on a unit-scale scene.
     const float pad = 4e-5f * std::max(1.0f, ctx->coord_max);
     const size_t n = (size_t)ctx->n_tris;
-    CK(ctx->d_plane.ensure(n));
-    CK(ctx->d_v0.ensure(n));
-    CK(ctx->d_v1.ensure(n));
-    CK(ctx->d_v2.ensure(n));
-    CK(ctx->d_n0.ensure(n));
-    CK(ctx->d_n1.ensure(n));
-    CK(ctx->d_n2.ensure(n));
+    CK(ctx->d_plane.ensure(n * kTriStride));
+    CK(ctx->d_n0.ensure(n * kTriStride));
+    if (!RT_TRI_AOS) {
+        CK(ctx->d_v0.ensure(n));
+        CK(ctx->d_v1.ensure(n));
+        CK(ctx->d_v2.ensure(n));
+        CK(ctx->d_n1.ensure(n));
+        CK(ctx->d_n2.ensure(n));
+    }
     const int* perm = nullptr;
     if (mode == RT_BVH_AUTO) // the host SAH tree traces ~15 % faster but takes ~0.6 us per triangle to build
         mode = ctx->n_tris <= (1ll << 22) ? RT_BVH_SAH_HOST : RT_BVH_LBVH_DEVICE;
@@ -1273,8 +1286,12 @@ int rt_build_bvh(rt_ctx* ctx, int mode)
         }
     }
 #endif
-    launch_tri_setup(ctx->stream, ctx->d_pos.p, ctx->d_nrm.p, ctx->d_mesh.p, perm, (int)ctx->n_tris, ctx->d_plane.p, ctx->d_v0.p, ctx->d_v1.p,
-        ctx->d_v2.p, ctx->d_n0.p, ctx->d_n1.p, ctx->d_n2.p);
+    {
+        const SceneDev sd = ctx->scene_dev();
+        auto w = [](const float4* p) { return const_cast<float4*>(p); };
+        launch_tri_setup(ctx->stream, ctx->d_pos.p, ctx->d_nrm.p, ctx->d_mesh.p, perm, (int)ctx->n_tris, w(sd.tri_plane), w(sd.tri_v0), w(sd.tri_v1),
+            w(sd.tri_v2), w(sd.tri_n0), w(sd.tri_n1), w(sd.tri_n2));
+    }
     CK(cudaGetLastError());
     rc = refresh_tie_keys(ctx);
     if (rc)
@@ -1576,6 +1593,12 @@ int rt_sync(rt_ctx* ctx, rt_stats* stats)
             if (cudaEventElapsedTime(&ms, ctx->ev_pool[k], ctx->ev_pool[k + 1]) == cudaSuccess) {
                 ctx->stage_ms[ctx->ev_stage[k / 2]] += ms;
                 ctx->stage_launches[ctx->ev_stage[k / 2]]++;
+                static const bool timeline = std::getenv("RTB200_TRACE_LAUNCHES") != nullptr; // developer: when every timed launch began
+                if (timeline) {
+                    float t0 = 0.0f;
+                    cudaEventElapsedTime(&t0, ctx->ev0, ctx->ev_pool[k]);
+                    std::fprintf(stderr, "[launch] stage %d  begin %7.3f ms  took %7.3f ms\n", ctx->ev_stage[k / 2], t0, ms);
+                }
             }
         }
         if (ctx->trace_bands) {

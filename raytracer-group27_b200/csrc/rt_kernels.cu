@@ -12,8 +12,8 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kShadeBlock = 256;
-#ifndef RT_TRACE_BLOCK
-#define RT_TRACE_BLOCK 128
+#ifndef RT_STATIC_L0
+#define RT_STATIC_L0 0
 #endif
 #ifndef RT_TRACE_GRID_MULT
 #define RT_TRACE_GRID_MULT 8
@@ -149,8 +149,8 @@ __device__ __forceinline__ Shading shading_at(const SceneDev& s, int ti, const f
         sh.mesh = sh.gid = -1;
         return sh;
     }
-    const float4 pl = __ldg(&s.tri_plane[ti]);
-    const float4 a = __ldg(&s.tri_v0[ti]), b = __ldg(&s.tri_v1[ti]), c = __ldg(&s.tri_v2[ti]);
+    const float4 pl = __ldg(&s.tri_plane[kTriStride * ti]);
+    const float4 a = __ldg(&s.tri_v0[kTriStride * ti]), b = __ldg(&s.tri_v1[kTriStride * ti]), c = __ldg(&s.tri_v2[kTriStride * ti]);
     const f3 v0 = mk3(a), v1 = mk3(b), v2 = mk3(c), fn = mk3(pl);
     const int mesh = __float_as_int(b.w);
     sh.m0 = __ldg(&s.mats[2 * mesh]);
@@ -159,7 +159,7 @@ __device__ __forceinline__ Shading shading_at(const SceneDev& s, int ti, const f
     const float c0 = xdiv(xlength(xcross(xsub(v1, sh.p), xsub(v2, sh.p))), total);
     const float c1 = xdiv(xlength(xcross(xsub(sh.p, v0), xsub(v2, v0))), total);
     const float c2 = xdiv(xlength(xcross(xsub(v1, v0), xsub(sh.p, v0))), total);
-    const f3 n0 = mk3(__ldg(&s.tri_n0[ti])), n1 = mk3(__ldg(&s.tri_n1[ti])), n2 = mk3(__ldg(&s.tri_n2[ti]));
+    const f3 n0 = mk3(__ldg(&s.tri_n0[kTriStride * ti])), n1 = mk3(__ldg(&s.tri_n1[kTriStride * ti])), n2 = mk3(__ldg(&s.tri_n2[kTriStride * ti]));
     f3 N = xadd(xadd(xmul(n0, c0), xmul(n1, c1)), xmul(n2, c2));
     if (xdot(N, fn) < 0.0f)
         N = xneg(N);
@@ -279,14 +279,15 @@ __global__ void k_tri_setup(const float* __restrict__ pos, const float* __restri
     const f3 v0 = mk3(p[0], p[1], p[2]), v1 = mk3(p[3], p[4], p[5]), v2 = mk3(p[6], p[7], p[8]);
     const f3 nn = xnormalize(xcross(xsub(v0, v2), xsub(v1, v2)));
     const float D = xdot(nn, v0);
-    plane[i] = make_float4(nn.x, nn.y, nn.z, D);
-    v0o[i] = make_float4(v0.x, v0.y, v0.z, __int_as_float(g));
-    v1o[i] = make_float4(v1.x, v1.y, v1.z, __int_as_float(mesh_id ? mesh_id[g] : 0));
-    v2o[i] = make_float4(v2.x, v2.y, v2.z, __int_as_float(g));
+    const size_t o = (size_t)kTriStride * i;
+    plane[o] = make_float4(nn.x, nn.y, nn.z, D);
+    v0o[o] = make_float4(v0.x, v0.y, v0.z, __int_as_float(g));
+    v1o[o] = make_float4(v1.x, v1.y, v1.z, __int_as_float(mesh_id ? mesh_id[g] : 0));
+    v2o[o] = make_float4(v2.x, v2.y, v2.z, __int_as_float(g));
     const float* q = nrm + 9 * (size_t)g;
-    n0o[i] = make_float4(q[0], q[1], q[2], 0.0f);
-    n1o[i] = make_float4(q[3], q[4], q[5], 0.0f);
-    n2o[i] = make_float4(q[6], q[7], q[8], 0.0f);
+    n0o[o] = make_float4(q[0], q[1], q[2], 0.0f);
+    n1o[o] = make_float4(q[3], q[4], q[5], 0.0f);
+    n2o[o] = make_float4(q[6], q[7], q[8], 0.0f);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_extend(
     const unsigned n = b.counters->n_rays[qi];
     TraceStats st;
     int tag = 0;
-    trace_queue<false, COUNT>(
+    trace_queue<false, COUNT, LEVEL0 && RT_STATIC_L0>(
         s, root_entry, fp.exhaustive != 0, &b.counters->work[0], n, st,
         [&](unsigned item, f3& o, f3& d, HitRec& q) {
             q = fresh_query();
@@ -707,6 +708,10 @@ __device__ __forceinline__ void shadow_loop(const SceneDev& s, int root_entry, c
             return true;
         },
         [&](unsigned item, const HitRec& best, f3& o, f3& d, HitRec& q) {
+            if (ANYHIT) { // every material is opaque (the launcher's condition for ANYHIT): the first blocker decides, no segment state to keep
+                item_end(item, best.ti == -1, 1.0f);
+                return false;
+            }
             const int r = cansee_step(s, fp, cs, best);
             if (r == 2) {
                 queries++;

@@ -79,8 +79,8 @@ __global__ void k_apply_tie_keys(float4* v0, const float4* __restrict__ v2, cons
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_slots)
         return;
-    const int g = __float_as_int(v2[i].w);
-    v0[i].w = __int_as_float(g < n_ranked ? rank[g] : g);
+    const int g = __float_as_int(v2[kTriStride * i].w);
+    v0[kTriStride * i].w = __int_as_float(g < n_ranked ? rank[g] : g);
 }
 
 } // namespace

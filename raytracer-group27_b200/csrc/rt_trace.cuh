@@ -32,11 +32,16 @@ struct HitRec {
     int ti;    // BVH-order index of the best triangle hit; -1 = none; -2 - k = sphere k
 };
 
-// One ray against one triangle.  `o`/`d` as stored in the ray, `dn` = normalize(d).
+// One ray against one triangle.  `o`/`d` as stored in the ray, `dn` = normalize(d); `pl` = the triangle's plane record.
+#ifndef RT_TRI_EAGER_V1
+#define RT_TRI_EAGER_V1 0 // 1: fetch v1 together with v0 / v2 instead of after the tie check (one round trip less per full test)
+#endif
+#ifndef RT_LEAF_PREFETCH
+#define RT_LEAF_PREFETCH 0 // 1: the plane of the leaf's next triangle is requested before the current one is tested
+#endif
 template <bool COUNT>
-__device__ __forceinline__ bool test_triangle(const SceneDev& s, int ti, const f3& o, const f3& d, const f3& dn, HitRec& best, TraceStats& st)
+__device__ __forceinline__ bool test_triangle(const SceneDev& s, int ti, const float4& pl, const f3& o, const f3& d, const f3& dn, HitRec& best, TraceStats& st)
 {
-    const float4 pl = __ldg(&s.tri_plane[ti]);
     const f3 n = mk3(pl);
     if (COUNT)
         st.tris++;
@@ -46,12 +51,17 @@ __device__ __forceinline__ bool test_triangle(const SceneDev& s, int ti, const f
     const float t = xdiv(xsub(pl.w, xdot(o, n)), nd);
     if (!(t >= 0.0f) || !(t <= best.t))
         return false;
-    const float4 a = __ldg(&s.tri_v0[ti]);
-    const float4 c = __ldg(&s.tri_v2[ti]);
+    const float4 a = __ldg(&s.tri_v0[kTriStride * ti]);
+    const float4 c = __ldg(&s.tri_v2[kTriStride * ti]);
+#if RT_TRI_EAGER_V1
+    const float4 b = __ldg(&s.tri_v1[kTriStride * ti]);
+#endif
     const int key = __float_as_int(s.tie_by_id ? c.w : a.w);
     if (t == best.t && key >= best.key)
         return false; // equal t: the object the reference visits first wins
-    const float4 b = __ldg(&s.tri_v1[ti]);
+#if !RT_TRI_EAGER_V1
+    const float4 b = __ldg(&s.tri_v1[kTriStride * ti]);
+#endif
     if (COUNT)
         st.tris_full++;
     const f3 v0 = mk3(a), v1 = mk3(b), v2 = mk3(c);
@@ -66,6 +76,11 @@ __device__ __forceinline__ bool test_triangle(const SceneDev& s, int ti, const f
         return true;
     }
     return false;
+}
+template <bool COUNT>
+__device__ __forceinline__ bool test_triangle(const SceneDev& s, int ti, const f3& o, const f3& d, const f3& dn, HitRec& best, TraceStats& st)
+{
+    return test_triangle<COUNT>(s, ti, __ldg(&s.tri_plane[kTriStride * ti]), o, d, dn, best, st);
 }
 
 // Sphere primitives: intersectRayWithShape(const Sphere&, Ray&, HitInfo&) (src/ray_tracing.cpp:182-209).  The reference's
@@ -118,7 +133,7 @@ __device__ __forceinline__ HitRec bounded_query(float limit) { return HitRec { l
 __device__ __forceinline__ int global_id(const SceneDev& s, const HitRec& best)
 {
     if (best.ti >= 0)
-        return __float_as_int(__ldg(&s.tri_v2[best.ti]).w);
+        return __float_as_int(__ldg(&s.tri_v2[kTriStride * best.ti]).w);
     return best.ti == -1 ? -1 : s.sphere_id_base + (-2 - best.ti);
 }
 
@@ -194,9 +209,66 @@ __device__ __forceinline__ void trav_start(const SceneDev& s, Trav& tv, const f3
     tv.tlimit = prune_limit(tv.best.t);
 }
 
+// Per-thread traversal stack.  RT_SMEM_STACK > 0: the first RT_SMEM_STACK entries live in shared memory (one column per thread,
+// entry i of thread t at [i][t]: conflict-free), deeper ones spill to local memory; 0: all of it in local memory.
+#ifndef RT_TRACE_BLOCK
+#define RT_TRACE_BLOCK 128
+#endif
+#ifndef RT_SMEM_STACK
+#define RT_SMEM_STACK 0
+#endif
+constexpr int kStackWords = kStackDepth * (RT_STACK_TMIN ? 2 : 1);
+struct TravStack {
+#if RT_SMEM_STACK > 0
+    int* sh; // this thread's column of the block's shared array
+    int lo[kStackWords > RT_SMEM_STACK ? kStackWords - RT_SMEM_STACK : 1];
+    __device__ __forceinline__ int operator[](int i) const { return i < RT_SMEM_STACK ? sh[i * RT_TRACE_BLOCK] : lo[i - RT_SMEM_STACK]; }
+    __device__ __forceinline__ void put(int i, int v)
+    {
+        if (i < RT_SMEM_STACK)
+            sh[i * RT_TRACE_BLOCK] = v;
+        else
+            lo[i - RT_SMEM_STACK] = v;
+    }
+#else
+    int lo[kStackWords];
+    __device__ __forceinline__ int operator[](int i) const { return lo[i]; }
+    __device__ __forceinline__ void put(int i, int v) { lo[i] = v; }
+#endif
+};
+// Binds the shared part of the stack; must be called by every thread of a block of at most RT_TRACE_BLOCK threads.
+__device__ __forceinline__ void trav_stack_init(TravStack& st)
+{
+#if RT_SMEM_STACK > 0
+    __shared__ int s_stack[RT_SMEM_STACK][RT_TRACE_BLOCK];
+    st.sh = &s_stack[0][threadIdx.x];
+#endif
+}
+
+// Fetch of one sibling pair = 64 aligned bytes.  RT_LDG256: two 256-bit loads (LDG.E.ENL2.256, sm_100) instead of four 128-bit ones.
+#ifndef RT_LDG256
+#define RT_LDG256 0
+#endif
+__device__ __forceinline__ void load_node_pair(const float4* np, float4& a0, float4& a1, float4& b0, float4& b1)
+{
+#if RT_LDG256
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a0.x), "=f"(a0.y), "=f"(a0.z), "=f"(a0.w), "=f"(a1.x), "=f"(a1.y), "=f"(a1.z), "=f"(a1.w)
+                 : "l"(np));
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w), "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w)
+                 : "l"(np + 2));
+#else
+    a0 = __ldg(np);
+    a1 = __ldg(np + 1);
+    b0 = __ldg(np + 2);
+    b1 = __ldg(np + 3);
+#endif
+}
+
 // Pop the next entry; with RT_STACK_TMIN the entry distance saved at push time lets entries that have fallen behind the
 // current best hit be skipped without fetching them.
-__device__ __forceinline__ int trav_pop(Trav& tv, const int* stack)
+__device__ __forceinline__ int trav_pop(Trav& tv, const TravStack& stack)
 {
 #if RT_STACK_TMIN
     while (tv.sp) {
@@ -218,7 +290,7 @@ __device__ __forceinline__ int trav_pop(Trav& tv, const int* stack)
 // One node step of the 4-wide tree (rt_wide.cu): fetch the 128-byte node `tv.cur`, slab-test its four boxes, go on with the
 // nearest hit child and push the others, farthest first; or pop.  An any-hit query does not care about the order.
 template <bool ANYHIT, bool COUNT>
-__device__ __forceinline__ void trav_node_step(const SceneDev& s, Trav& tv, int* stack, TraceStats& st)
+__device__ __forceinline__ void trav_node_step(const SceneDev& s, Trav& tv, TravStack& stack, TraceStats& st)
 {
     const float4* np = s.nodes + 8 * (size_t)tv.cur;
     const float4 lx = __ldg(np), ly = __ldg(np + 1), lz = __ldg(np + 2), hx = __ldg(np + 3), hy = __ldg(np + 4), hz = __ldg(np + 5);
@@ -265,21 +337,22 @@ __device__ __forceinline__ void trav_node_step(const SceneDev& s, Trav& tv, int*
     RT_CSWAP(1, 2)
 #undef RT_CSWAP
     if (n > 3)
-        stack[tv.sp++] = e[3];
+        stack.put(tv.sp++, e[3]);
     if (n > 2)
-        stack[tv.sp++] = e[2];
+        stack.put(tv.sp++, e[2]);
     if (n > 1)
-        stack[tv.sp++] = e[1];
+        stack.put(tv.sp++, e[1]);
     tv.cur = e[0];
 }
 #else
 // One node step: fetch the sibling pair `tv.cur` (one aligned 64-byte read), slab-test both boxes, descend into the
 // nearer hit child and push the other one, or pop.
 template <bool ANYHIT, bool COUNT>
-__device__ __forceinline__ void trav_node_step(const SceneDev& s, Trav& tv, int* stack, TraceStats& st)
+__device__ __forceinline__ void trav_node_step(const SceneDev& s, Trav& tv, TravStack& stack, TraceStats& st)
 {
     const float4* np = s.nodes + 2 * (size_t)tv.cur;
-    const float4 a0 = __ldg(np), a1 = __ldg(np + 1), b0 = __ldg(np + 2), b1 = __ldg(np + 3);
+    float4 a0, a1, b0, b1;
+    load_node_pair(np, a0, a1, b0, b1);
     if (COUNT)
         st.nodes += 2;
     // near / far slab distances of both boxes (all finite: boxes are finite, |r| <= 1e30)
@@ -297,11 +370,11 @@ __device__ __forceinline__ void trav_node_step(const SceneDev& s, Trav& tv, int*
     if (hitA && hitB) {
         const bool aFirst = amin <= bmin;
 #if RT_STACK_TMIN
-        stack[2 * tv.sp] = aFirst ? eb : ea;
-        stack[2 * tv.sp + 1] = __float_as_int(aFirst ? bmin : amin);
+        stack.put(2 * tv.sp, aFirst ? eb : ea);
+        stack.put(2 * tv.sp + 1, __float_as_int(aFirst ? bmin : amin));
         tv.sp++;
 #else
-        stack[tv.sp++] = aFirst ? eb : ea;
+        stack.put(tv.sp++, aFirst ? eb : ea);
 #endif
         tv.cur = aFirst ? ea : eb;
     } else if (hitA) {
@@ -322,8 +395,18 @@ __device__ __forceinline__ void trav_leaf_test(const SceneDev& s, Trav& tv, int 
     const int enc = ~leaf;
     const int first = enc >> 3, count = (enc & 7) + 1;
     bool any = false;
+#if RT_LEAF_PREFETCH
+    float4 pl = __ldg(&s.tri_plane[kTriStride * first]);
+    for (int i = 0; i < count; i++) {
+        const float4 cur = pl;
+        if (i + 1 < count)
+            pl = __ldg(&s.tri_plane[kTriStride * (first + i + 1)]);
+        any |= test_triangle<COUNT>(s, first + i, cur, tv.o, tv.d, tv.dn, tv.best, st);
+    }
+#else
     for (int i = 0; i < count; i++)
         any |= test_triangle<COUNT>(s, first + i, tv.o, tv.d, tv.dn, tv.best, st);
+#endif
     if (any) {
         tv.tlimit = prune_limit(tv.best.t);
         if (ANYHIT) { // the first blocker decides
@@ -339,12 +422,16 @@ __device__ __forceinline__ void trav_leaf_test(const SceneDev& s, Trav& tv, int 
 // the loop, the warp leaves it and the idle lanes pull new items (one atomicAdd per warp per refill).
 // fetch(item, o, d, query) -> false if the item needs no ray;  finish(item, best, o, d, query) -> true to continue the
 // same item with a new segment (shadow rays passing a transparent surface).
-template <bool ANYHIT, bool COUNT, typename Fetch, typename Finish>
+// STATIC: no work cursor — warp w takes items [(k * total_warps + w) * 32, + 32) for k = 0, 1, ...; only for queues whose items never
+// continue (finish() returns false), so that a warp refills with all 32 lanes idle.  Level-0 extend uses it: a 4K frame would
+// otherwise issue 260 K same-address atomics, which L2 serialises at about 1 ns each.
+template <bool ANYHIT, bool COUNT, bool STATIC = false, typename Fetch, typename Finish>
 __device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, bool exhaustive, unsigned* cursor, unsigned n_items,
     TraceStats& st, Fetch fetch, Finish finish, int max_quota = 32)
 {
     constexpr unsigned kFullMask = 0xffffffffu;
-    int stack[kStackDepth * (RT_STACK_TMIN ? 2 : 1)];
+    TravStack stack;
+    trav_stack_init(stack);
     Trav tv;
     tv.cur = kTravDone;
     tv.sp = 0;
@@ -358,7 +445,10 @@ __device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, b
 #ifndef RT_MAX_QUOTA
 #define RT_MAX_QUOTA 32
 #endif
-    const int quota = (int)min((unsigned)max_quota, max(1u, (n_items + total_warps - 1) / total_warps));
+    const int quota = STATIC ? 32 : (int)min((unsigned)max_quota, max(1u, (n_items + total_warps - 1) / total_warps));
+    unsigned static_next = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u;
+    if (STATIC)
+        more = static_next < n_items;
     for (;;) {
         // ---- refill: idle lanes take the next unclaimed items (at most `quota` rays in flight per warp) ----
         const unsigned idle_all = __ballot_sync(kFullMask, !active);
@@ -369,10 +459,16 @@ __device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, b
             const int leader = __ffs(idle) - 1;
             const unsigned cnt = (unsigned)__popc(idle);
             unsigned base = 0;
-            if (lane == leader)
-                base = atomicAdd(cursor, cnt);
-            base = __shfl_sync(kFullMask, base, leader);
-            more = base + cnt < n_items;
+            if (STATIC) {
+                base = static_next;
+                static_next += total_warps * 32u;
+                more = static_next < n_items;
+            } else {
+                if (lane == leader)
+                    base = atomicAdd(cursor, cnt);
+                base = __shfl_sync(kFullMask, base, leader);
+                more = base + cnt < n_items;
+            }
             if (!active && ((idle >> lane) & 1u)) {
                 const unsigned item = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
                 if (item < n_items) {
@@ -453,7 +549,8 @@ __device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, b
 template <bool ANYHIT, bool COUNT>
 __device__ __forceinline__ void trace_bvh(const SceneDev& s, int root_entry, const f3& o, const f3& d, HitRec& best, TraceStats& st)
 {
-    int stack[kStackDepth * (RT_STACK_TMIN ? 2 : 1)];
+    TravStack stack;
+    trav_stack_init(stack);
     Trav tv;
     trav_start<ANYHIT>(s, tv, o, d, best, root_entry);
     while (tv.cur != kTravDone) {

@@ -11,6 +11,14 @@ constexpr int kTileW = 32;
 constexpr int kTileH = 16;
 constexpr int kTilePixels = kTileW * kTileH;
 
+// Triangle records.  RT_TRI_AOS = 1: one 64-byte record {plane, v0, v1, v2} per triangle (and {n0, n1, n2, -} for the corner
+// normals), so that everything a triangle test reads sits in one cache line; 0: four separate float4 arrays.  The pointers
+// of SceneDev address element 0 of each member either way; element ti of a member is at [kTriStride * ti].
+#ifndef RT_TRI_AOS
+#define RT_TRI_AOS 1
+#endif
+constexpr int kTriStride = RT_TRI_AOS ? 4 : 1;
+
 constexpr int kMaxLeafTris = 8;   // leaf size must fit the 3-bit count of a packed stack entry
 constexpr int kStackDepth = 64;   // per-thread traversal stack (ints); builders guarantee depth < kStackDepth
 constexpr int kMaxLanes = 4;       // batches of one frame in flight at once (rt_set_pipeline)

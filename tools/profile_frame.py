@@ -12,6 +12,7 @@ mode = rtb200.BVH_SAH_HOST if (len(sys.argv) < 3 or sys.argv[2] == "sah") else r
 ctx = rtb200.Context(0)
 ctx.upload_scene(standin.dragon_standin_scene(), mode)
 cam, prm = rtb200.make_camera(), rtb200.make_params(3840, 2160, 3)
+ctx.set_shard(0, int(os.environ.get("RTB200_PROFILE_WORLD", "1")))  # > 1: rank 0's share of the frame split over that many ranks
 if os.environ.get("RTB200_ONE_BATCH", "1") == "1":
     ctx.set_pipeline(1, 1)  # one batch per frame: one launch of every kernel per bounce level (ncu serialises anyway)
 for _ in range(frames):
