@@ -91,6 +91,10 @@ typedef struct {
     uint64_t extend_node_visits;    /* the three traversal counters restricted to the extend kernel (primary + */
     uint64_t extend_tri_tests;      /* reflection / refraction rays); the shadow kernels account for the rest  */
     uint64_t extend_tri_tests_full;
+    uint64_t traced_primary_rays;   /* primary rays that walked the BVH: those of pixels inside the projection of the scene's bounding
+                                       box; the others are counted in primary_rays (the reference casts them) but answered as misses */
+    uint64_t gather_bytes;          /* bytes this rank stored into a framebuffer that is not its own (rt_render_device with a
+                                       caller-supplied / peer-mapped d_rgba): float4 pixels of its tiles, or of their rows with hits only */
 } rt_stats;
 
 #define RT_BVH_LBVH_DEVICE 0      /* Morton codes -> radix sort -> Karras hierarchy -> refit, all on the GPU */
@@ -208,6 +212,9 @@ int rt_set_counters(rt_ctx* ctx, int enable);
 #define RT_STAGE_COUNT 8
 int rt_set_stage_timing(rt_ctx* ctx, int enable);
 int rt_stage_times(rt_ctx* ctx, float* ms /* [RT_STAGE_COUNT] */, int* launches /* [RT_STAGE_COUNT] */);
+/* Measurement aid (bench.py's roofline): the rate at which this device issues un-fused FP32 multiplies and adds — the instruction
+ * mix of the path's parity-critical geometry code — in 1e9 lane-instructions per second, from a microbenchmark kernel (best of 3). */
+int rt_measure_fp32_peak(rt_ctx* ctx, double* ginst_per_s);
 /* Shadow kernels of bounce level L run on a side stream concurrently with extend / shade of level L+1 (default on). */
 int rt_set_overlap(rt_ctx* ctx, int enable);
 /* Batch pipelining: a frame is cut into about `batches_per_frame` batches (none smaller than min_batch_pixels) that are
@@ -244,10 +251,22 @@ int rt_sync(rt_ctx* ctx, rt_stats* stats);
 int rt_render_shard(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, float* rgb_host_mapped, rt_stats* stats);
 /* Device framebuffer of this context (width*height float4 of the last rt_render_device with d_rgba=NULL). */
 int rt_framebuffer(rt_ctx* ctx, void** d_rgba, int* width, int* height);
-/* CUDA IPC handle (64 bytes) of this context's framebuffer, sized for width x height, so that other ranks can
- * map it with rt_open_peer_framebuffer and pass the mapped pointer to rt_render_device. */
+/* The gather — the one collective of a sharded frame: finished tiles land in the framebuffer of the ROOT rank, stored there by the
+ * other ranks' resolve kernels over NVLink.
+ *   root:  rt_framebuffer_ipc_handle exports its framebuffer for width x height (CUDA IPC handle, 64 bytes) and makes the context the
+ *          gather root: its rt_render_device(..., NULL) calls with world > 1 are GATHER FRAMES.
+ *   peers: rt_open_peer_framebuffer maps the handle (another process), or rt_set_gather_target takes the root's rt_framebuffer
+ *          pointer as it stood right after the export (same process, peer access enabled by the caller); their
+ *          rt_render_device(..., that pointer) calls with world > 1 are gather frames too.
+ * Gather frames store only what has to travel.  The exported allocation holds two images used by alternate frames; while frame k
+ * is rendered into one, the root fills the other with the background colour, so a peer leaves out every 32-pixel tile row none of
+ * whose camera rays hit anything (C3: 16 % of the rows are stored).  What this asks of the callers, and what every per-frame
+ * job loop does anyway: all ranks render the same sequence of gather frames, and a barrier (after rt_sync on every rank)
+ * separates consecutive frames.  rt_framebuffer on the root returns the image of the last frame.  rt_stats.gather_bytes
+ * reports what a peer stored. */
 int rt_framebuffer_ipc_handle(rt_ctx* ctx, int width, int height, void* handle64);
 int rt_open_peer_framebuffer(rt_ctx* ctx, const void* handle64, void** d_rgba);
+int rt_set_gather_target(rt_ctx* ctx, void* d_rgba);
 int rt_close_peer_framebuffer(rt_ctx* ctx, void* d_rgba);
 /* Copy a device float4 framebuffer to a host float3 image (Screen::m_textureData layout). */
 int rt_download_rgb(rt_ctx* ctx, const void* d_rgba, int width, int height, float* rgb_out);

@@ -155,7 +155,21 @@ struct rt_ctx {
     DevBuf<unsigned> flag;
     Counters* h_counters = nullptr; // pinned, one per lane
     int fb_w = 0, fb_h = 0;
+    // Gather frames of a sharded job (rt_framebuffer_ipc_handle / rt_open_peer_framebuffer): the root's framebuffer has two halves
+    // used by alternate frames; while frame k is rendered into half k & 1 the root fills the other half with the background colour,
+    // and the barrier that ends frame k orders that fill before the peers' stores of frame k + 1 — which can therefore leave out
+    // every tile row without a hit.
+    bool gather_root = false;        // this context's framebuffer was exported
+    void* peer_base = nullptr;       // the root's framebuffer as mapped into this process
+    unsigned long long gather_frames = 0; // gather frames rendered so far (every rank counts the same sequence)
+    float4* fb_last = nullptr;       // where the last frame rendered into the own framebuffer lives (rt_framebuffer)
+    int fb_last_w = 0, fb_last_h = 0;
+    DevBuf<float4> fb_plain;         // gather root: framebuffer of its frames that are not gather frames
+    int fb_plain_w = 0, fb_plain_h = 0;
     int last_launches = 0, last_batches = 0;
+    unsigned long long last_traced_primary = 0;
+    int last_gather_mode = 0;        // 0: frame stayed in this context's memory; 1: every pixel of its tiles stored into a foreign buffer; 2: rows with hits only
+    size_t last_local_pixels = 0;
     unsigned last_overflow = 0;
     bool frame_pending = false;
 
@@ -624,6 +638,11 @@ int enqueue_postprocess(rt_ctx* ctx, cudaStream_t st, float4* img, int w, int h,
 
 // Where rt_render wants the finished rows: packed float3 image on the host (pinned for full PCIe speed).
 struct HostTarget {
+    // gather frames: `sparse` — store only tile rows with hits (peer ranks); `prefill` — background fill of that buffer while the frame renders (root)
+    bool sparse = false;
+    bool foreign = false; // the framebuffer is not this context's (caller-supplied device pointer, maybe on a peer GPU)
+    float4* prefill = nullptr;
+    size_t prefill_n = 0;
     float* rgb = nullptr;
     // rt_render_shard: the whole image's packed float3 buffer in page-locked host memory as THIS device sees it; the
     // frame's last kernel stores the pixels of this rank's tiles into it (no staging copy)
@@ -684,7 +703,8 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
         ctx->trace_what.push_back(what);
     };
     const bool early_bg = host && host->mapped_rgb && host->early_background && !post && n_local;
-    if (early_bg)
+    const bool sparse = host && host->sparse && !early_bg && n_local;
+    if (early_bg || sparse)
         CK(ctx->row_flags.ensure(n_local / kTilePixels * kTileH));
     // several lanes render bands side by side: traversal grids of 4 blocks per SM leave room for another lane's kernel
     // (C3 through rt_render, 3 lanes x 6 bands: 3.40 ms with 8 blocks per SM, 3.17 with 4, 3.16 with 3)
@@ -724,6 +744,7 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
     const SceneDev s = ctx->scene_dev();
     cudaStream_t st0 = ctx->stream;
     int launches = 0, batches = 0;
+    unsigned long long traced_primary = 0;
     ctx->ev_used = 0;
     ctx->ev_stage.clear();
     CK(cudaEventRecord(ctx->ev0, st0));
@@ -731,6 +752,12 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
         CK(cudaMemsetAsync(ctx->accum.p, 0, n_local * sizeof(float4), st0));
     CK(cudaEventRecord(ctx->ev_start, st0));
 
+    const bool prefill = host && host->prefill && host->prefill_n;
+    if (prefill) { // gather root: the other half of the framebuffer becomes background for the next frame
+        CK(cudaStreamWaitEvent(ctx->copy, ctx->ev_start, 0));
+        launch_fill_background(ctx->copy, ctx->sm_count, host->prefill, host->prefill_n);
+        launches++;
+    }
     if (early_bg) { // rows outside the scene's projection: on their way before the first ray is traced
         CK(cudaStreamWaitEvent(ctx->copy, ctx->ev_start, 0));
         launch_host_background(ctx->copy, ctx->sm_count, fp, 0, (unsigned)fp.n_local_tiles, nullptr, host->mapped_rgb, ctx->store_gbs);
@@ -750,13 +777,19 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
         }
         const unsigned n_lp = (unsigned)plan[bi].second;
         // primary rays of this batch: pixels of its tiles that lie inside the image, times samples per pixel
-        unsigned long long n_primary = 0;
+        unsigned long long n_primary = 0, n_traced = 0;
         for (size_t j = first / kTilePixels; j < (first + n_lp) / kTilePixels; j++) {
             const long long g = (long long)fp.rank + (long long)j * fp.world;
             const int tx = (int)(g % fp.tiles_x), ty = (int)(g / fp.tiles_x);
             n_primary += (unsigned long long)std::min(kTileW, fp.W - tx * kTileW) * std::min(kTileH, fp.H - ty * kTileH);
+            // the ones that walk the BVH: pixels of the tile inside the scene's projection (pixel_sees_scene)
+            const int x0 = std::max(tx * kTileW, fp.vis_x0), x1 = std::min(std::min((tx + 1) * kTileW, fp.W), fp.vis_x1);
+            const int y0 = std::max(ty * kTileH, fp.vis_y0), y1 = std::min(std::min((ty + 1) * kTileH, fp.H), fp.vis_y1);
+            if (x1 > x0 && y1 > y0)
+                n_traced += (unsigned long long)(x1 - x0) * (y1 - y0);
         }
         n_primary *= (unsigned long long)fp.spp;
+        traced_primary += n_traced * (unsigned long long)fp.spp;
         for (int level = 0; level <= fp.max_level; level++) {
             const int qi = level & 1, par = level & 1;
             set_parity(ln, b, par);
@@ -774,9 +807,13 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
                 s_ext.tie_by_id = fp.tie_by_id; // shadow queries keep the BVH order (shadow.cpp:42)
                 launch_extend(st, ctx->sm_count, s_ext, ctx->root_entry, fp, b, qi, level, (unsigned)first, ctx->counters_enabled);
             }
+            if (sparse && level == 0) { // which tile rows of this batch hold a hit: the others are not stored (k_resolve)
+                launch_row_flags(st, ctx->sm_count, fp, (unsigned)first, n_lp, b.q[0].hit, ctx->row_flags.p, &b.counters->flagged_rows);
+                launches++;
+            }
             if (early_bg && level == 0) {
                 // rows of pure background leave for the host now, on the copy stream, next to everything that follows
-                launch_row_flags(st, ctx->sm_count, fp, (unsigned)first, n_lp, b.q[0].hit, ctx->row_flags.p);
+                launch_row_flags(st, ctx->sm_count, fp, (unsigned)first, n_lp, b.q[0].hit, ctx->row_flags.p, &b.counters->flagged_rows);
                 CK(cudaEventRecord(ln.ev_packed, st));
                 CK(cudaStreamWaitEvent(ctx->copy, ln.ev_packed, 0));
                 trace_at(ctx->copy, "level-0 extend done, batch " + std::to_string(bi));
@@ -821,7 +858,7 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
         {
             StageScope sc(ctx, RT_STAGE_RESOLVE, st);
             launch_resolve(st, ctx->sm_count, fp, (unsigned)first, n_lp, ctx->accum.p, b.prim_id, b.prim_t, out, want_ids ? ctx->out_id.p : nullptr,
-                want_ids ? ctx->out_t.p : nullptr);
+                want_ids ? ctx->out_t.p : nullptr, sparse ? ctx->row_flags.p : nullptr);
             launches++;
         }
         if (early_bg) { // the rows of this batch that were hit: straight into the host image
@@ -866,9 +903,11 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
         if (rc)
             return rc;
     }
-    if (early_bg) {
+    if (early_bg || prefill) {
         CK(cudaEventRecord(ctx->ev_copied, ctx->copy));
         CK(cudaStreamWaitEvent(st0, ctx->ev_copied, 0));
+    }
+    if (early_bg) {
     } else if (host && host->mapped_rgb && n_local) {
         launch_pack_rgb_tiles(st0, ctx->sm_count, fp, 0, (unsigned)fp.n_local_tiles, nullptr, out, host->mapped_rgb);
         launches++;
@@ -886,10 +925,41 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
     CK(cudaGetLastError());
     ctx->last_launches = launches;
     ctx->last_batches = batches;
+    ctx->last_traced_primary = traced_primary;
+    ctx->last_gather_mode = sparse ? 2 : (host && host->foreign ? 1 : 0);
+    ctx->last_local_pixels = n_local;
     ctx->frame_pending = true;
     if (ctx->trace_bands)
         std::fprintf(stderr, "[bands] host: %d launches of %d batches enqueued in %.3f ms\n", launches, batches,
             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count());
+    return RT_OK;
+}
+
+// Framebuffer of a frame that is not a gather frame: the context's own, except on a gather root, whose two exported halves only
+// gather frames may touch (peers rely on their background fill) — such a context renders everything else into a separate buffer.
+int plain_framebuffer(rt_ctx* ctx, const FrameParams& fp, float4** out)
+{
+    const size_t npx = (size_t)fp.W * fp.H;
+    if (ctx->gather_root) {
+        if (ctx->fb_plain.n < npx || ctx->fb_plain_w != fp.W || ctx->fb_plain_h != fp.H) {
+            CK(ctx->fb_plain.ensure(npx));
+            CK(cudaMemsetAsync(ctx->fb_plain.p, 0, npx * sizeof(float4), ctx->stream));
+            ctx->fb_plain_w = fp.W;
+            ctx->fb_plain_h = fp.H;
+        }
+        *out = ctx->fb_plain.p;
+    } else {
+        if (ctx->fb.n < npx || ctx->fb_w != fp.W || ctx->fb_h != fp.H) {
+            CK(ctx->fb.ensure(npx));
+            CK(cudaMemsetAsync(ctx->fb.p, 0, npx * sizeof(float4), ctx->stream));
+            ctx->fb_w = fp.W;
+            ctx->fb_h = fp.H;
+        }
+        *out = ctx->fb.p;
+    }
+    ctx->fb_last = *out;
+    ctx->fb_last_w = fp.W;
+    ctx->fb_last_h = fp.H;
     return RT_OK;
 }
 
@@ -1045,6 +1115,8 @@ int rt_destroy(rt_ctx* ctx)
     ctx->d_plane_lights.release();
     ctx->rays_in.release();
     ctx->flag.release();
+    ctx->row_flags.release();
+    ctx->fb_plain.release();
     if (ctx->lbvh_nodes)
         cudaFree(ctx->lbvh_nodes);
     if (ctx->lbvh_perm)
@@ -1102,6 +1174,30 @@ int rt_stage_times(rt_ctx* ctx, float* ms, int* launches)
         ms[k] = ctx->stage_ms[k];
         launches[k] = ctx->stage_launches[k];
     }
+    return RT_OK;
+}
+
+int rt_measure_fp32_peak(rt_ctx* ctx, double* ginst_per_s)
+{
+    int rc = use_device(ctx);
+    if (rc)
+        return rc;
+    if (!ginst_per_s)
+        return fail(RT_ERR_INVALID, "rt_measure_fp32_peak: null argument");
+    CK(ctx->rays_in.ensure((size_t)ctx->sm_count * 8 * 256));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) { // first launches warm the clocks up; the best of the rest counts
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        const double n = launch_fp32_peak(ctx->stream, ctx->sm_count, ctx->rays_in.p, 8192);
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.0f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        if (rep >= 2 && ms > 0.0f)
+            best = std::max(best, n / (ms * 1e-3) / 1e9);
+    }
+    *ginst_per_s = best;
     return RT_OK;
 }
 
@@ -1207,6 +1303,10 @@ int rt_build_bvh(rt_ctx* ctx, int mode)
     // farthest zoom (distance 100, trackball.cpp:150) on a unit-scale scene.
     const float pad = 4e-5f * std::max(1.0f, ctx->coord_max);
     const size_t n = (size_t)ctx->n_tris;
+    // a build that fails half-way must not leave the previous tree's (possibly freed) nodes behind a `built` flag
+    ctx->bvh_built = false;
+    ctx->nodes = nullptr;
+    ctx->n_nodes = 0;
     CK(ctx->d_plane.ensure(n * kTriStride));
     CK(ctx->d_n0.ensure(n * kTriStride));
     if (!RT_TRI_AOS) {
@@ -1429,11 +1529,12 @@ int rt_set_spheres(rt_ctx* ctx, const rt_sphere* spheres, int n_spheres)
     std::vector<float> centres;
     for (int i = 0; i < n_spheres; i++)
         centres.insert(centres.end(), spheres[i].center, spheres[i].center + 3);
-    const bool moved = centres != ctx->h_sphere_centres;
-    ctx->h_sphere_centres = centres;
-    ctx->h_sphere_radii.clear();
+    std::vector<float> radii;
     for (int i = 0; i < n_spheres; i++)
-        ctx->h_sphere_radii.push_back(spheres[i].radius);
+        radii.push_back(spheres[i].radius);
+    const bool moved = centres != ctx->h_sphere_centres || radii != ctx->h_sphere_radii; // (the rank depends on the centres only; radii for good measure)
+    ctx->h_sphere_centres = centres;
+    ctx->h_sphere_radii = radii;
     ctx->n_spheres = n_spheres;
     if (moved && ctx->bvh_built) { // the spheres are objects of the reference's BVH: its visiting order changes with them
         rc = refresh_tie_keys(ctx);
@@ -1467,17 +1568,34 @@ int rt_render_device(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, vo
     if (rc)
         return rc;
     float4* out = (float4*)d_rgba;
+    const size_t npx = (size_t)fp.W * fp.H;
+    HostTarget gt;
+    bool gather = false;
     if (!out) {
-        const size_t npx = (size_t)fp.W * fp.H;
-        if (ctx->fb.n < npx || ctx->fb_w != fp.W || ctx->fb_h != fp.H) {
-            CK(ctx->fb.ensure(npx));
-            CK(cudaMemsetAsync(ctx->fb.p, 0, npx * sizeof(float4), ctx->stream));
-            ctx->fb_w = fp.W;
-            ctx->fb_h = fp.H;
+        if (ctx->gather_root && fp.world > 1 && ctx->fb_w == fp.W && ctx->fb_h == fp.H) {
+            // gather frame on the root: this frame's half, and the background fill of the other one
+            const unsigned half = (unsigned)(ctx->gather_frames & 1);
+            out = ctx->fb.p + half * npx;
+            gt.prefill = ctx->fb.p + (half ^ 1) * npx;
+            gt.prefill_n = npx;
+            gather = true;
+            ctx->fb_last = out;
+            ctx->fb_last_w = fp.W;
+            ctx->fb_last_h = fp.H;
+        } else {
+            rc = plain_framebuffer(ctx, fp, &out);
+            if (rc)
+                return rc;
         }
-        out = ctx->fb.p;
+    } else if (d_rgba == ctx->peer_base && fp.world > 1) { // gather frame on a peer: rows with hits only, into this frame's half
+        out += (ctx->gather_frames & 1) * npx;
+        gt.sparse = true;
+        gather = true;
     }
-    return enqueue_frame(ctx, fp, out, false, ctx->batch_rays, nullptr);
+    if (gather)
+        ctx->gather_frames++;
+    gt.foreign = d_rgba != nullptr;
+    return enqueue_frame(ctx, fp, out, false, ctx->batch_rays, &gt);
 }
 
 int rt_visible_rect(const rt_camera* cam, int width, int height, const float lo[3], const float hi[3], int rect[4])
@@ -1552,19 +1670,16 @@ int rt_render_shard(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, flo
     rc = measure_store_rate(ctx);
     if (rc)
         return rc;
-    const size_t npx = (size_t)fp.W * fp.H;
-    if (ctx->fb.n < npx || ctx->fb_w != fp.W || ctx->fb_h != fp.H) {
-        CK(ctx->fb.ensure(npx));
-        CK(cudaMemsetAsync(ctx->fb.p, 0, npx * sizeof(float4), ctx->stream));
-        ctx->fb_w = fp.W;
-        ctx->fb_h = fp.H;
-    }
+    float4* fb = nullptr;
+    rc = plain_framebuffer(ctx, fp, &fb);
+    if (rc)
+        return rc;
     unsigned batch = ctx->batch_rays;
     for (int attempt = 0;; attempt++) {
         HostTarget host;
         host.mapped_rgb = static_cast<float*>(attr.devicePointer);
         host.early_background = ctx->zero_copy_host && fp.spp == 1; // (a frame with several samples per pixel is stored when it is complete)
-        rc = enqueue_frame(ctx, fp, ctx->fb.p, false, batch, &host);
+        rc = enqueue_frame(ctx, fp, fb, false, batch, &host);
         if (rc)
             return rc;
         rc = rt_sync(ctx, stats);
@@ -1621,6 +1736,7 @@ int rt_sync(rt_ctx* ctx, rt_stats* stats)
             c.primary_rays += h.primary_rays;
             c.shadow_queries += h.shadow_queries;
             c.secondary_rays += h.secondary_rays;
+            c.flagged_rows += h.flagged_rows;
             c.node_visits += h.node_visits;
             c.tri_tests += h.tri_tests;
             c.tri_tests_full += h.tri_tests_full;
@@ -1649,6 +1765,10 @@ int rt_sync(rt_ctx* ctx, rt_stats* stats)
             stats->gpu_ms = ms;
             stats->kernel_launches = ctx->last_launches;
             stats->batches = ctx->last_batches;
+            stats->traced_primary_rays = ctx->last_traced_primary;
+            stats->gather_bytes = ctx->last_gather_mode == 2 ? (uint64_t)c.flagged_rows * kTileW * sizeof(float4)
+                : ctx->last_gather_mode == 1                  ? (uint64_t)ctx->last_local_pixels * sizeof(float4)
+                                                              : 0;
         }
     }
     return RT_OK;
@@ -1656,14 +1776,14 @@ int rt_sync(rt_ctx* ctx, rt_stats* stats)
 
 int rt_framebuffer(rt_ctx* ctx, void** d_rgba, int* width, int* height)
 {
-    if (!ctx || !ctx->fb.p)
+    if (!ctx || !ctx->fb_last)
         return fail(RT_ERR_INVALID, "rt_framebuffer: nothing rendered yet");
     if (d_rgba)
-        *d_rgba = ctx->fb.p;
+        *d_rgba = ctx->fb_last;
     if (width)
-        *width = ctx->fb_w;
+        *width = ctx->fb_last_w;
     if (height)
-        *height = ctx->fb_h;
+        *height = ctx->fb_last_h;
     return RT_OK;
 }
 
@@ -1674,14 +1794,21 @@ int rt_framebuffer_ipc_handle(rt_ctx* ctx, int width, int height, void* handle64
         return rc;
     if (width <= 0 || height <= 0 || !handle64)
         return fail(RT_ERR_INVALID, "rt_framebuffer_ipc_handle: bad arguments");
+    // two halves for alternate gather frames, both background to begin with (see rt_ctx::gather_root)
     const size_t npx = (size_t)width * height;
-    if (ctx->fb.n < npx || ctx->fb_w != width || ctx->fb_h != height) {
-        CK(ctx->fb.ensure(npx));
-        CK(cudaMemsetAsync(ctx->fb.p, 0, npx * sizeof(float4), ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->fb.n < 2 * npx || ctx->fb_w != width || ctx->fb_h != height || !ctx->gather_root) {
+        CK(ctx->fb.ensure(2 * npx));
         ctx->fb_w = width;
         ctx->fb_h = height;
     }
+    launch_fill_background(ctx->stream, ctx->sm_count, ctx->fb.p, 2 * npx);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->gather_root = true;
+    ctx->gather_frames = 0;
+    ctx->fb_last = ctx->fb.p;
+    ctx->fb_last_w = width;
+    ctx->fb_last_h = height;
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, ctx->fb.p));
     static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
@@ -1699,6 +1826,17 @@ int rt_open_peer_framebuffer(rt_ctx* ctx, const void* handle64, void** d_rgba)
     cudaIpcMemHandle_t h;
     std::memcpy(&h, handle64, 64);
     CK(cudaIpcOpenMemHandle(d_rgba, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peer_base = *d_rgba;
+    ctx->gather_frames = 0;
+    return RT_OK;
+}
+
+int rt_set_gather_target(rt_ctx* ctx, void* d_rgba)
+{
+    if (!ctx)
+        return fail(RT_ERR_INVALID, "null context");
+    ctx->peer_base = d_rgba;
+    ctx->gather_frames = 0;
     return RT_OK;
 }
 
@@ -1708,6 +1846,8 @@ int rt_close_peer_framebuffer(rt_ctx* ctx, void* d_rgba)
     if (rc)
         return rc;
     CK(cudaIpcCloseMemHandle(d_rgba));
+    if (d_rgba == ctx->peer_base)
+        ctx->peer_base = nullptr;
     return RT_OK;
 }
 
@@ -1743,12 +1883,10 @@ int rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, float* rg
         return rc;
     const size_t npx = (size_t)fp.W * fp.H;
     const bool want_ids = tri_id_out != nullptr || t_out != nullptr;
-    if (ctx->fb.n < npx || ctx->fb_w != fp.W || ctx->fb_h != fp.H) {
-        CK(ctx->fb.ensure(npx));
-        CK(cudaMemsetAsync(ctx->fb.p, 0, npx * sizeof(float4), ctx->stream));
-        ctx->fb_w = fp.W;
-        ctx->fb_h = fp.H;
-    }
+    float4* fb = nullptr;
+    rc = plain_framebuffer(ctx, fp, &fb);
+    if (rc)
+        return rc;
     if (want_ids) {
         CK(ctx->out_id.ensure(npx));
         CK(ctx->out_t.ensure(npx));
@@ -1782,7 +1920,7 @@ int rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, float* rg
             host.early_background = true;
         } else
             host.rgb = rgb_out; // finished bands are packed and copied by the lanes while the rest of the frame renders
-        rc = enqueue_frame(ctx, fp, ctx->fb.p, want_ids, batch, &host);
+        rc = enqueue_frame(ctx, fp, fb, want_ids, batch, &host);
         if (rc)
             return rc;
         if (tri_id_out)
@@ -1909,9 +2047,9 @@ int rt_postprocess_device(rt_ctx* ctx, const rt_post_params* post, void* d_rgba,
         return rc;
     float4* img = (float4*)d_rgba;
     if (!img) {
-        if (!ctx->fb.p || ctx->fb_w != width || ctx->fb_h != height)
+        if (!ctx->fb_last || ctx->fb_last_w != width || ctx->fb_last_h != height)
             return fail(RT_ERR_INVALID, "rt_postprocess_device: the context holds no framebuffer of that size");
-        img = ctx->fb.p;
+        img = ctx->fb_last;
     }
     if (width <= 0 || height <= 0)
         return fail(RT_ERR_INVALID, "rt_postprocess_device: empty image");

@@ -903,12 +903,16 @@ __global__ void __launch_bounds__(256) k_plane_finalize(FrameParams fp, BatchDev
 // K5 resolve: sample average (src/main.cpp:374,384) and Screen::setPixel's y flip (src/screen.cpp:32-38).  One
 // warp writes one 32-pixel tile row = 512 contiguous bytes of float4; `out` may be a peer-mapped framebuffer of
 // another GPU (the gather of finished tiles fused into this store).
+// row_flags (nullable, k_row_flags): sparse gather — tile rows none of whose camera rays hit anything are not stored; the gather
+// root has pre-filled them with the background colour (rt_capi.cu, gather frames).
 __global__ void __launch_bounds__(256) k_resolve(FrameParams fp, unsigned first_lp, unsigned n_lp, const float4* __restrict__ accum,
-    const int* __restrict__ prim_id, const float* __restrict__ prim_t, float4* out, int* out_id, float* out_t)
+    const int* __restrict__ prim_id, const float* __restrict__ prim_t, float4* out, int* out_id, float* out_t, const unsigned char* __restrict__ row_flags)
 {
     for (unsigned idx = first_lp + blockIdx.x * blockDim.x + threadIdx.x; idx < first_lp + n_lp; idx += gridDim.x * blockDim.x) {
         const unsigned j = idx / kTilePixels, k = idx % kTilePixels;
         const unsigned x = k % kTileW, y = k / kTileW; // row-major inside the tile for coalesced stores
+        if (row_flags && !row_flags[(size_t)j * kTileH + y])
+            continue;
         const unsigned g = (unsigned)fp.rank + j * (unsigned)fp.world;
         const int px = (int)((g % (unsigned)fp.tiles_x) * kTileW + x), py = (int)((g / (unsigned)fp.tiles_x) * kTileH + y);
         if (px >= fp.W || py >= fp.H)
@@ -991,8 +995,14 @@ __global__ void __launch_bounds__(256) k_pack_rgb_tiles(FrameParams fp, unsigned
 // rt_render into a device-mapped host image: which 32-pixel tile rows of the batch contain a pixel one of whose camera rays
 // hit something.  The others are background — black, and final as soon as level 0 has been traced.
 // One warp per tile row; flags[tile * kTileH + row] = 1 if any of its pixels was hit.
-__global__ void __launch_bounds__(256) k_row_flags(FrameParams fp, unsigned first_lp, unsigned n_lp, const int2* __restrict__ hit, unsigned char* __restrict__ flags)
+__global__ void __launch_bounds__(256) k_row_flags(FrameParams fp, unsigned first_lp, unsigned n_lp, const int2* __restrict__ hit, unsigned char* __restrict__ flags,
+    unsigned* n_flagged)
 {
+    __shared__ unsigned s_flagged;
+    if (threadIdx.x == 0)
+        s_flagged = 0;
+    __syncthreads();
+    unsigned mine = 0;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned tile0 = first_lp / kTilePixels;
     const size_t n_rows = (size_t)(n_lp / kTilePixels) * kTileH;
@@ -1008,9 +1018,16 @@ __global__ void __launch_bounds__(256) k_row_flags(FrameParams fp, unsigned firs
                 was_hit |= h[sidx].y != -1;
         }
         const bool any = __any_sync(0xffffffffu, was_hit);
-        if (lane == 0)
+        if (lane == 0) {
             flags[(size_t)(tile0 + jl) * kTileH + y] = any ? 1 : 0;
+            mine += any ? 1u : 0u;
+        }
     }
+    if (lane == 0 && mine)
+        atomicAdd(&s_flagged, mine);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_flagged && n_flagged)
+        atomicAdd(n_flagged, s_flagged);
 }
 
 // The background rows of the batch (k_row_flags) go to the host image at once, as zeros, while the rest of the frame is
@@ -1058,6 +1075,31 @@ __global__ void __launch_bounds__(256) k_host_background(FrameParams fp, unsigne
             out[3 * (p0 + lane) + 2] = 0.0f;
         }
     }
+}
+
+// FP32 issue-rate microbenchmark (rt_measure_fp32_peak): the geometry code of this path is un-fused FMUL / FADD (rt_math.cuh), which
+// cannot reach the FFMA peak; this kernel measures what the chip issues for exactly that instruction mix — 8 independent chains per
+// thread, alternating __fmul_rn / __fadd_rn, nothing else in the loop.  16 * iters FP32 instructions per thread.
+__global__ void __launch_bounds__(256) k_fp32_peak(float* out, int iters, float a, float b)
+{
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.0f, x2 = x0 + 2.0f, x3 = x0 + 3.0f, x4 = x0 + 4.0f, x5 = x0 + 5.0f, x6 = x0 + 6.0f, x7 = x0 + 7.0f;
+#pragma unroll 4
+    for (int i = 0; i < iters; i++) {
+        x0 = __fmul_rn(x0, a); x1 = __fmul_rn(x1, a); x2 = __fmul_rn(x2, a); x3 = __fmul_rn(x3, a);
+        x4 = __fmul_rn(x4, a); x5 = __fmul_rn(x5, a); x6 = __fmul_rn(x6, a); x7 = __fmul_rn(x7, a);
+        x0 = __fadd_rn(x0, b); x1 = __fadd_rn(x1, b); x2 = __fadd_rn(x2, b); x3 = __fadd_rn(x3, b);
+        x4 = __fadd_rn(x4, b); x5 = __fadd_rn(x5, b); x6 = __fadd_rn(x6, b); x7 = __fadd_rn(x7, b);
+    }
+    const float r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (r == 12345.678f) // never true for the arguments used; keeps the chains alive
+        out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+double launch_fp32_peak(cudaStream_t st, int sm_count, float* scratch, int iters)
+{
+    const int grid = sm_count * 8;
+    k_fp32_peak<<<grid, 256, 0, st>>>(scratch, iters, 0.999f, 0.001f);
+    return (double)grid * 256.0 * 16.0 * iters; // FP32 instructions (per lane) of the launch
 }
 
 // Closest hit for caller-supplied rays (rt_intersect).
@@ -1196,11 +1238,24 @@ void launch_shadow_plane(cudaStream_t st, int sm_count, const SceneDev& s, int r
 }
 
 void launch_resolve(cudaStream_t st, int sm_count, const FrameParams& fp, unsigned first_lp, unsigned n_lp, const float4* accum,
-    const int* prim_id, const float* prim_t, float4* out, int* out_id, float* out_t)
+    const int* prim_id, const float* prim_t, float4* out, int* out_id, float* out_t, const unsigned char* row_flags)
 {
     if (n_lp == 0)
         return;
-    k_resolve<<<grid_for(n_lp, 256, sm_count * 8), 256, 0, st>>>(fp, first_lp, n_lp, accum, prim_id, prim_t, out, out_id, out_t);
+    k_resolve<<<grid_for(n_lp, 256, sm_count * 8), 256, 0, st>>>(fp, first_lp, n_lp, accum, prim_id, prim_t, out, out_id, out_t, row_flags);
+}
+
+// Background fill of a gather target: every pixel (0, 0, 0, 1), what k_resolve stores for a pixel without a hit.
+__global__ void __launch_bounds__(256) k_fill_background(float4* __restrict__ out, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+}
+
+void launch_fill_background(cudaStream_t st, int sm_count, float4* out, size_t n)
+{
+    if (n)
+        k_fill_background<<<grid_for((long long)n, 256, sm_count * 4), 256, 0, st>>>(out, n);
 }
 
 void launch_pack_rgb(cudaStream_t st, int sm_count, const float4* in, float* out, size_t p0, size_t p1)
@@ -1218,11 +1273,12 @@ void launch_pack_rgb_tiles(cudaStream_t st, int sm_count, const FrameParams& fp,
     k_pack_rgb_tiles<<<grid_for((long long)n_tiles * kTileH * 32, 256, sm_count * 8), 256, 0, st>>>(fp, tile0, n_tiles, flags, in, out);
 }
 
-void launch_row_flags(cudaStream_t st, int sm_count, const FrameParams& fp, unsigned first_lp, unsigned n_lp, const int2* hit, unsigned char* flags)
+void launch_row_flags(cudaStream_t st, int sm_count, const FrameParams& fp, unsigned first_lp, unsigned n_lp, const int2* hit, unsigned char* flags,
+    unsigned* n_flagged)
 {
     if (n_lp < (unsigned)kTilePixels)
         return;
-    k_row_flags<<<grid_for((long long)(n_lp / kTilePixels) * kTileH * 32, 256, sm_count * 8), 256, 0, st>>>(fp, first_lp, n_lp, hit, flags);
+    k_row_flags<<<grid_for((long long)(n_lp / kTilePixels) * kTileH * 32, 256, sm_count * 8), 256, 0, st>>>(fp, first_lp, n_lp, hit, flags, n_flagged);
 }
 
 // One block on every other SM; the pacing period follows from the number of warps and the rate to hold (`gbs`: a little under what

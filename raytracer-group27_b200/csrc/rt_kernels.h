@@ -17,13 +17,17 @@ void launch_shadow_point(cudaStream_t st, int sm_count, const SceneDev& s, int r
 void launch_shadow_sphere(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count);
 void launch_shadow_plane(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count);
 void launch_resolve(cudaStream_t st, int sm_count, const FrameParams& fp, unsigned first_lp, unsigned n_lp, const float4* accum,
-    const int* prim_id, const float* prim_t, float4* out, int* out_id, float* out_t);
+    const int* prim_id, const float* prim_t, float4* out, int* out_id, float* out_t, const unsigned char* row_flags = nullptr);
+void launch_fill_background(cudaStream_t st, int sm_count, float4* out, size_t n);
 void launch_pack_rgb(cudaStream_t st, int sm_count, const float4* in, float* out, size_t p0, size_t p1);
 void launch_pack_rgb_tiles(cudaStream_t st, int sm_count, const FrameParams& fp, unsigned tile0, unsigned n_tiles, const unsigned char* flags,
     const float4* in, float* out);
-void launch_row_flags(cudaStream_t st, int sm_count, const FrameParams& fp, unsigned first_lp, unsigned n_lp, const int2* hit, unsigned char* flags);
+void launch_row_flags(cudaStream_t st, int sm_count, const FrameParams& fp, unsigned first_lp, unsigned n_lp, const int2* hit, unsigned char* flags,
+    unsigned* n_flagged);
 void launch_host_background(cudaStream_t st, int sm_count, const FrameParams& fp, unsigned tile0, unsigned n_tiles, const unsigned char* flags, float* out,
     double gbs);
+// FMUL / FADD issue-rate microbenchmark; returns the number of FP32 lane-instructions the launch executes.  scratch: >= sm_count * 8 * 256 floats.
+double launch_fp32_peak(cudaStream_t st, int sm_count, float* scratch, int iters);
 void launch_intersect(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const float* rays, long long n, int use_bvh,
     int* tri_id, float* t_out, unsigned* overflow);
 

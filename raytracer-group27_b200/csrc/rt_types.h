@@ -110,7 +110,7 @@ struct Counters {
     unsigned int n_rays[2];      // ray queue fill (ping-pong)
     unsigned int work[2];        // dynamic work-fetch cursors: extend, (spare)
     unsigned int overflow;       // set when a queue would exceed its capacity
-    unsigned int pad;
+    unsigned int flagged_rows;   // tile rows with a hit counted by k_row_flags (frames that store rows selectively)
     // Shadow work is double-buffered by bounce-level parity so that the shadow kernels of level L (side stream) can run
     // concurrently with extend / shade of level L+1 (main stream).
     struct Shadow {

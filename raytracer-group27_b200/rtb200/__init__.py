@@ -49,7 +49,13 @@ class Params(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("primary_rays", C.c_uint64), ("shadow_queries", C.c_uint64), ("secondary_rays", C.c_uint64), ("node_visits", C.c_uint64),
                 ("tri_tests", C.c_uint64), ("tri_tests_full", C.c_uint64), ("gpu_ms", C.c_float), ("kernel_launches", C.c_int),
-                ("batches", C.c_int), ("extend_node_visits", C.c_uint64), ("extend_tri_tests", C.c_uint64), ("extend_tri_tests_full", C.c_uint64)]
+                ("batches", C.c_int), ("extend_node_visits", C.c_uint64), ("extend_tri_tests", C.c_uint64), ("extend_tri_tests_full", C.c_uint64),
+                ("traced_primary_rays", C.c_uint64), ("gather_bytes", C.c_uint64)]
+
+    @property
+    def traced_rays(self) -> int:
+        """Rays that walked the BVH: everything but the primary rays of pixels outside the scene's projection."""
+        return int(self.traced_primary_rays + self.shadow_queries + self.secondary_rays)
 
     @property
     def rays(self) -> int:
@@ -112,6 +118,7 @@ SYMBOLS = [
     ("rt_set_counters", _I, [_P, _I]),
     ("rt_set_batch_rays", _I, [_P, C.c_uint]),
     ("rt_set_overlap", _I, [_P, _I]),
+    ("rt_measure_fp32_peak", _I, [_P, C.POINTER(C.c_double)]),
     ("rt_set_pipeline", _I, [_P, _I, _I, C.c_uint]),
     ("rt_set_stage_timing", _I, [_P, _I]),
     ("rt_stage_times", _I, [_P, _P, _P]),
@@ -124,6 +131,7 @@ SYMBOLS = [
     ("rt_framebuffer", _I, [_P, C.POINTER(_P), C.POINTER(_I), C.POINTER(_I)]),
     ("rt_framebuffer_ipc_handle", _I, [_P, _I, _I, _P]),
     ("rt_open_peer_framebuffer", _I, [_P, _P, C.POINTER(_P)]),
+    ("rt_set_gather_target", _I, [_P, _P]),
     ("rt_close_peer_framebuffer", _I, [_P, _P]),
     ("rt_download_rgb", _I, [_P, _P, _I, _I, _P]),
     ("rt_intersect", _I, [_P, _P, C.c_int64, _I, _P, _P]),
@@ -386,6 +394,12 @@ class Context:
     def set_pipeline(self, lanes: int, batches_per_frame: int, min_batch_pixels: int = 1 << 18):
         _check(self._l.rt_set_pipeline(self._h, lanes, batches_per_frame, min_batch_pixels))
 
+    def measure_fp32_peak(self) -> float:
+        """Un-fused FMUL / FADD issue rate of this device in 1e9 lane-instructions per second (microbenchmark)."""
+        v = C.c_double(0.0)
+        _check(self._l.rt_measure_fp32_peak(self._h, C.byref(v)))
+        return float(v.value)
+
     def set_overlap(self, enable: bool):
         _check(self._l.rt_set_overlap(self._h, 1 if enable else 0))
 
@@ -444,6 +458,10 @@ class Context:
         p = _P()
         _check(self._l.rt_open_peer_framebuffer(self._h, C.create_string_buffer(handle, 64), C.byref(p)))
         return p.value
+
+    def set_gather_target(self, ptr: int):
+        """Same-process form of open_peer_framebuffer: `ptr` = the root's framebuffer() pointer right after its export."""
+        _check(self._l.rt_set_gather_target(self._h, _P(ptr)))
 
     def close_peer_framebuffer(self, ptr: int):
         _check(self._l.rt_close_peer_framebuffer(self._h, _P(ptr)))

@@ -350,4 +350,18 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "Mrays/s" and d["higher_is_better"] is True and d["n_gpus"] == 1
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"] and "sample" in d["config"] and d["gpu_launches"] == 0
+    assert d["gpu_launches"] == 0
+    # the job description has the GPU arm's keys (the sample lives under cpu_baseline), and the product library stays out of this arm
+    assert set(d["config"]) == {"workload", "bvh", "sharding", "gather", "l2"} and "sample" in d["cpu_baseline"]
+    assert d["native_libraries_loaded"] and all(p.startswith("oracle" + os.sep) for p in d["native_libraries_loaded"]), d["native_libraries_loaded"]
+
+
+def test_reference_arm_scene_equals_the_importers(rtb):
+    """oracle/standin_np.py (numpy reader + centerAndScaleToUnitMesh, used by bench.py's reference arm so that it need not load
+    the product library) gives bit for bit the arrays the product's OBJ importer gives for the stand-in."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import standin_np
+    from rtb200 import standin
+    a, b = standin_np.dragon_standin_scene(), standin.dragon_standin_scene()
+    assert np.array_equal(a.pos, b.pos) and np.array_equal(a.nrm, b.nrm) and np.array_equal(a.mesh_id, b.mesh_id)
+    assert a.mats.tobytes() == np.ascontiguousarray(b.mats).tobytes() and np.array_equal(a.point_lights, b.point_lights)
