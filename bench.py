@@ -402,6 +402,27 @@ def run_gpu(args):
             shared_ptr = 0
         e2e_path = "rt_render_shard (every rank stores its tiles into one shared page-locked host image)" if shared_ptr else "rt_render_device + gather + rank 0 downloads"
 
+    host_store_gbs = None
+    if world > 1 and shared_ptr:
+        # What one rank's link carries while ALL ranks store into host memory (GPUs behind one PCIe switch share its uplink; the
+        # host's ingest rate is finite): measured, not assumed — every rank copies 64 MiB device-to-host at the same moment, 6 times.
+        probe_d = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+        probe_h = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+        torch.cuda.synchronize()
+        rates = []
+        for k in range(6):
+            dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            probe_h.copy_(probe_d, non_blocking=True)
+            b.record()
+            b.synchronize()
+            if k >= 2:
+                rates.append(probe_d.numel() / (a.elapsed_time(b) * 1e6))
+        host_store_gbs = float(np.median(rates))
+        ctx.set_host_store_rate(host_store_gbs)
+        del probe_d, probe_h
+
     def e2e_step():
         ctx.set_materials(sc.mats)                      # the reference re-reads materials and lights every frame
         ctx.set_lights(sc.point_lights, sc.sphere_lights)
@@ -505,7 +526,8 @@ def run_gpu(args):
             "config": job_config(args, desc, world, gather),
             "clocks": clocks, "wall_ms_per_step_incl_flush_and_sync": wall_ms / args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes) * world, "d2h_bytes_per_step": int(W * H * 3 * 4), "steps": e2e_steps,
-                    "ms_per_step": float(e_ms.item()) / e2e_steps, "path": e2e_path},
+                    "ms_per_step": float(e_ms.item()) / e2e_steps, "path": e2e_path,
+                    "host_store_gbs_per_rank_all_ranks_copying": host_store_gbs},
             "gpu_launches": int(launches),
             "roofline": roof,
             "extra": {

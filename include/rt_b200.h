@@ -249,6 +249,12 @@ int rt_sync(rt_ctx* ctx, rt_stats* stats);
  * this rank owns straight into it — no staging copy, every GPU over its own PCIe link — and touches nothing else, so after
  * all ranks have returned the buffer holds the frame renderRayTracing would have left in Screen::m_textureData. */
 int rt_render_shard(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, float* rgb_host_mapped, rt_stats* stats);
+/* The rows of background leave for the host while the frame is still traced, paced to just under what the link carries (stores that
+ * back up into L2 slow the traversal kernels down).  One context measures its own link; what a link carries while ALL ranks of a
+ * job store into the same host memory depends on the box (shared PCIe switches, the host's ingest rate) and only the job can measure
+ * it: every rank copies device-to-host at the same time and hands its rate in GB/s to its context.  0 = back to the built-in
+ * assumption min(own link, 100 GB/s / world). */
+int rt_set_host_store_rate(rt_ctx* ctx, double gbs);
 /* Device framebuffer of this context (width*height float4 of the last rt_render_device with d_rgba=NULL). */
 int rt_framebuffer(rt_ctx* ctx, void** d_rgba, int* width, int* height);
 /* The gather — the one collective of a sharded frame: finished tiles land in the framebuffer of the ROOT rank, stored there by the

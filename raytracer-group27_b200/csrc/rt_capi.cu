@@ -150,6 +150,9 @@ struct rt_ctx {
     DevBuf<float> prim_t, out_t, rgb;
     DevBuf<unsigned char> row_flags;    // per 32-pixel tile row: some camera ray hit (k_row_flags)
     double store_gbs = 0.0;             // rate the paced background stores hold: 85 % of the measured device-to-host copy rate
+    double queue_scale = 1.0;           // RTB200_QUEUE_SCALE (tests): shrinks the queues' head-room to provoke the overflow path
+    unsigned headroom_shift = 0;        // doublings of the head-room asked for by the overflow retry of rt_render / rt_render_shard
+    double shared_store_gbs = 0.0;      // rt_set_host_store_rate: what this rank's link carries while every rank of the job stores into host memory
     bool zero_copy_host = true;         // RTB200_ZERO_COPY=0 (developer): rt_render always stages bands through the copy engine
     DevBuf<float> rays_in;
     DevBuf<unsigned> flag;
@@ -455,13 +458,18 @@ void set_parity(rt_ctx::Lane& ln, BatchDev& b, int par)
     b.sq_plane = PlaneQueue { ln.pl_p[par].p, ln.pl_a[par].p, ln.pl_b[par].p, ln.pl_r[par].p, ln.pl_acc[par].p };
 }
 
+// Rays a primary ray can turn into at the next level: two at a dielectric hit, glossy_ray_count at a glossy one (main.cpp:204-290).
+size_t queue_multiplier(const rt_ctx* ctx, const FrameParams& fp) { return (size_t)(ctx->any_transparent ? 2 : 1) * (size_t)std::max(fp.glossy, 1); }
+
 // Size one lane's queues for batches of `batch_pixels` pixels and describe them in `b`.
 int ensure_lane(rt_ctx* ctx, rt_ctx::Lane& ln, const FrameParams& fp, unsigned batch_pixels, bool want_ids, BatchDev& b)
 {
     const size_t prim = (size_t)batch_pixels * fp.spp;
-    // head-room of the ray queues: a dielectric hit spawns two rays, a glossy one up to glossy_ray_count; deeper levels can
-    // still outgrow it, rt_render then halves the batch and retries (RT_ERR_OVERFLOW)
-    const size_t cap = prim * (ctx->any_transparent ? 2 : 1) * (size_t)std::min(std::max(fp.glossy, 1), 8);
+    // head-room of the ray queues: a dielectric hit spawns two rays, a glossy one up to glossy_ray_count (queue_multiplier); deeper
+    // levels of dielectric-heavy views can still outgrow it: the frame then ends with RT_ERR_OVERFLOW, and rt_render / rt_render_shard
+    // render it again with twice the head-room per attempt (ctx->headroom_shift) on half the batch
+    const size_t cap = std::max<size_t>((size_t)kTilePixels,
+        (size_t)((double)(prim * queue_multiplier(ctx, fp)) * ctx->queue_scale * (double)(1u << ctx->headroom_shift)));
     for (int k = 0; k < 2; k++) {
         CK(ln.q_hit[k].ensure(cap));
         b.q[k].hit = ln.q_hit[k].p;
@@ -685,7 +693,8 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
     size_t batch_pixels = (n_local + batches_wanted - 1) / batches_wanted;
     batch_pixels = std::max<size_t>(batch_pixels, ctx->min_batch_pixels);
     batch_pixels = (batch_pixels + unit - 1) / unit * unit; // whole tile rows, rounded up: at most batches_wanted batches
-    const size_t cap_pixels = std::max<size_t>(batch_rays / (unsigned)fp.spp, kTilePixels);
+    // rt_set_batch_rays bounds the rays of one batch IN FLIGHT: primary rays times what each can turn into at the next level
+    const size_t cap_pixels = std::max<size_t>(batch_rays / ((size_t)fp.spp * queue_multiplier(ctx, fp)) * (ctx->any_transparent ? 2 : 1), kTilePixels);
     if (batch_pixels > cap_pixels)
         batch_pixels = std::max<size_t>(unit, cap_pixels / unit * unit);
     if (batch_pixels > n_local)
@@ -760,7 +769,7 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
     }
     if (early_bg) { // rows outside the scene's projection: on their way before the first ray is traced
         CK(cudaStreamWaitEvent(ctx->copy, ctx->ev_start, 0));
-        launch_host_background(ctx->copy, ctx->sm_count, fp, 0, (unsigned)fp.n_local_tiles, nullptr, host->mapped_rgb, ctx->store_gbs);
+        launch_host_background(ctx->copy, ctx->sm_count, fp, 0, (unsigned)fp.n_local_tiles, nullptr, host->mapped_rgb, ctx->shared_store_gbs > 0.0 ? 0.85 * ctx->shared_store_gbs : ctx->store_gbs, ctx->shared_store_gbs > 0.0);
         launches++;
         trace_at(ctx->copy, "rows outside the scene's projection stored");
     }
@@ -817,7 +826,7 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
                 CK(cudaEventRecord(ln.ev_packed, st));
                 CK(cudaStreamWaitEvent(ctx->copy, ln.ev_packed, 0));
                 trace_at(ctx->copy, "level-0 extend done, batch " + std::to_string(bi));
-                launch_host_background(ctx->copy, ctx->sm_count, fp, (unsigned)(first / kTilePixels), n_lp / kTilePixels, ctx->row_flags.p, host->mapped_rgb, ctx->store_gbs);
+                launch_host_background(ctx->copy, ctx->sm_count, fp, (unsigned)(first / kTilePixels), n_lp / kTilePixels, ctx->row_flags.p, host->mapped_rgb, ctx->shared_store_gbs > 0.0 ? 0.85 * ctx->shared_store_gbs : ctx->store_gbs, ctx->shared_store_gbs > 0.0);
                 trace_at(ctx->copy, "background rows stored, batch " + std::to_string(bi));
                 launches += 2;
             }
@@ -1031,6 +1040,11 @@ int rt_create(int device, rt_ctx** out)
         ctx->cull_primary = e[0] != '0';
     if (const char* e = std::getenv("RTB200_TRACE_BANDS"))
         ctx->trace_bands = e[0] == '1';
+    if (const char* e = std::getenv("RTB200_QUEUE_SCALE")) {
+        const double v = std::atof(e);
+        if (v > 0.0 && v <= 1.0)
+            ctx->queue_scale = v;
+    }
     bool aux_ok = cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming) == cudaSuccess
         && cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming) == cudaSuccess
         && cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking) == cudaSuccess;
@@ -1647,6 +1661,14 @@ static int measure_store_rate(rt_ctx* ctx)
     return RT_OK;
 }
 
+int rt_set_host_store_rate(rt_ctx* ctx, double gbs)
+{
+    if (!ctx || !(gbs >= 0.0))
+        return fail(RT_ERR_INVALID, "rt_set_host_store_rate: need a context and a rate >= 0");
+    ctx->shared_store_gbs = gbs;
+    return RT_OK;
+}
+
 int rt_render_shard(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, float* rgb_host_mapped, rt_stats* stats)
 {
     int rc = use_device(ctx);
@@ -1683,10 +1705,14 @@ int rt_render_shard(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, flo
         if (rc)
             return rc;
         rc = rt_sync(ctx, stats);
-        if (rc == RT_ERR_OVERFLOW && ctx->last_overflow == 1 && attempt < 3 && batch / 2 >= (unsigned)kTilePixels * (unsigned)fp.spp) {
-            batch /= 2;
+        // queue overflow from ray splitting: twice the head-room per primary ray, on half the batch where the batch can shrink
+        if (rc == RT_ERR_OVERFLOW && ctx->last_overflow == 1 && attempt < 6) {
+            ctx->headroom_shift++;
+            if (batch / 2 >= (unsigned)kTilePixels * (unsigned)fp.spp)
+                batch /= 2;
             continue;
         }
+        ctx->headroom_shift = 0;
         return rc;
     }
 }
@@ -1928,11 +1954,14 @@ int rt_render(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, float* rg
         if (t_out)
             CK(cudaMemcpyAsync(t_out, ctx->out_t.p, npx * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
         rc = rt_sync(ctx, stats);
-        // queue overflow from ray splitting: halve the batch (doubling the head-room) and render again
-        if (rc == RT_ERR_OVERFLOW && ctx->last_overflow == 1 && attempt < 3 && batch / 2 >= (unsigned)kTilePixels * (unsigned)fp.spp) {
-            batch /= 2;
+        // queue overflow from ray splitting: twice the head-room per primary ray, on half the batch where the batch can shrink
+        if (rc == RT_ERR_OVERFLOW && ctx->last_overflow == 1 && attempt < 6) {
+            ctx->headroom_shift++;
+            if (batch / 2 >= (unsigned)kTilePixels * (unsigned)fp.spp)
+                batch /= 2;
             continue;
         }
+        ctx->headroom_shift = 0;
         return rc;
     }
 }

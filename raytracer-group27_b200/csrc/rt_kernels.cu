@@ -77,6 +77,9 @@ __device__ __forceinline__ void block_alloc(unsigned* const (&counter)[NQ], cons
     __syncthreads();
 }
 
+// The batch's overflow flag, one answer per warp (it may rise while a kernel of the side stream is starting up).
+__device__ __forceinline__ bool batch_overflowed(const BatchDev& b) { return __shfl_sync(kFull, b.counters->overflow, 0) != 0u; }
+
 // local padded pixel index -> pixel coordinates (tile interleaving across ranks, 8x4 warp blocks inside a tile)
 __device__ __forceinline__ void local_to_pixel(const FrameParams& fp, unsigned lp, int& px, int& py)
 {
@@ -310,7 +313,11 @@ __global__ void k_level_reset(Counters* c, int next_q, long long n_current, unsi
 template <bool LEVEL0, bool COUNT>
 __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_extend(SceneDev s, int root_entry, FrameParams fp, BatchDev b, int qi, unsigned first_lp)
 {
-    const unsigned n = b.counters->n_rays[qi];
+    // a queue that overflowed holds `capacity` items (block_alloc rejects the rest but still counts them); once the flag is up
+    // the rest of the batch is skipped, rt_sync reports RT_ERR_OVERFLOW and the caller renders again with more head-room
+    if (batch_overflowed(b))
+        return;
+    const unsigned n = min(b.counters->n_rays[qi], b.ray_capacity);
     TraceStats st;
     int tag = 0;
     trace_queue<false, COUNT, LEVEL0 && RT_STATIC_L0>(
@@ -376,7 +383,13 @@ template <bool LEVEL0, bool EXTRAS>
 __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams fp, BatchDev b, int qi, int level, unsigned first_lp)
 {
     __shared__ unsigned smem[2][kShadeBlock / 32 + 1];
-    const unsigned n = b.counters->n_rays[qi];
+    __shared__ unsigned s_overflow;
+    if (threadIdx.x == 0)
+        s_overflow = b.counters->overflow; // read once per block: the flag may rise while the kernel runs, the barriers below need one answer
+    __syncthreads();
+    if (s_overflow)
+        return;
+    const unsigned n = min(b.counters->n_rays[qi], b.ray_capacity);
     const int qo = qi ^ 1;
     const unsigned n_round = (n + kShadeBlock - 1) / kShadeBlock * kShadeBlock;
     unsigned n_secondary = 0;
@@ -737,7 +750,9 @@ __device__ __forceinline__ void shadow_loop(const SceneDev& s, int root_entry, c
 template <bool ANYHIT, bool COUNT>
 __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_shadow_point(SceneDev s, int root_entry, FrameParams fp, BatchDev b)
 {
-    const unsigned n = b.counters->sh[b.par].n_pt;
+    if (batch_overflowed(b))
+        return;
+    const unsigned n = min(b.counters->sh[b.par].n_pt, b.shadow_pt_capacity);
     shadow_loop<ANYHIT, COUNT>(
         s, root_entry, fp, b, &b.counters->sh[b.par].work_pt, n,
         [&](unsigned i, f3& p1, f3& p2) {
@@ -762,8 +777,10 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_shadow_
 template <bool ANYHIT, bool COUNT>
 __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_shadow_sphere(SceneDev s, int root_entry, FrameParams fp, BatchDev b)
 {
+    if (batch_overflowed(b))
+        return;
     const unsigned rc = (unsigned)fp.sl_rc;
-    const unsigned n = b.counters->sh[b.par].n_sp * (unsigned)fp.n_sphere * rc;
+    const unsigned n = min(b.counters->sh[b.par].n_sp, b.shadow_sp_capacity / (unsigned)max(fp.n_sphere, 1)) * (unsigned)fp.n_sphere * rc;
     shadow_loop<ANYHIT, COUNT>(
         s, root_entry, fp, b, &b.counters->sh[b.par].work_sp, n,
         [&](unsigned j, f3& p1, f3& p2) {
@@ -824,7 +841,9 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_shadow_
 // (shadow.cpp:212-221), then calcColor's A * intensity + B.
 __global__ void __launch_bounds__(256) k_sphere_finalize(FrameParams fp, BatchDev b)
 {
-    const unsigned n = b.counters->sh[b.par].n_sp * (unsigned)fp.n_sphere;
+    if (batch_overflowed(b))
+        return;
+    const unsigned n = min(b.counters->sh[b.par].n_sp, b.shadow_sp_capacity / (unsigned)max(fp.n_sphere, 1)) * (unsigned)fp.n_sphere;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float2 acc = b.sphere_acc[i];
         if (acc.y > 0.0f) {
@@ -844,8 +863,10 @@ __global__ void __launch_bounds__(256) k_sphere_finalize(FrameParams fp, BatchDe
 template <bool ANYHIT, bool COUNT>
 __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_shadow_plane(SceneDev s, int root_entry, FrameParams fp, BatchDev b)
 {
+    if (batch_overflowed(b))
+        return;
     const unsigned rc = (unsigned)fp.pl_rc, per = rc * rc;
-    const unsigned n = b.counters->sh[b.par].n_pl * per;
+    const unsigned n = min(b.counters->sh[b.par].n_pl, b.plane_capacity) * per;
     f3 sample = mk3(0, 0, 0); // position of the sample the lane is tracing
     shadow_loop<ANYHIT, COUNT>(
         s, root_entry, fp, b, &b.counters->sh[b.par].work_pl, n,
@@ -885,7 +906,9 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_shadow_
 // K4e: Lighting of a plane light (shadow.cpp:308-318) and calcColor (main.cpp:112-121) with cosLightSurfaceAngle = 1.
 __global__ void __launch_bounds__(256) k_plane_finalize(FrameParams fp, BatchDev b)
 {
-    const unsigned n = b.counters->sh[b.par].n_pl;
+    if (batch_overflowed(b))
+        return;
+    const unsigned n = min(b.counters->sh[b.par].n_pl, b.plane_capacity);
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 acc = b.sq_plane.acc[i];
         if (acc.y > 0.0f) {
@@ -1282,9 +1305,10 @@ void launch_row_flags(cudaStream_t st, int sm_count, const FrameParams& fp, unsi
 }
 
 // One block on every other SM; the pacing period follows from the number of warps and the rate to hold (`gbs`: a little under what
-// the link carries, measured by the caller, and this rank's share of what the host absorbs; RTB200_BG_GBS / RTB200_BG_BLOCKS override for experiments).
+// the link carries, measured by the caller — with every rank of a sharded job storing at once when gbs_is_shared_rate, else alone, and then capped by this
+// rank's share of what the host is assumed to absorb; RTB200_BG_GBS / RTB200_BG_BLOCKS override for experiments).
 void launch_host_background(cudaStream_t st, int sm_count, const FrameParams& fp, unsigned tile0, unsigned n_tiles, const unsigned char* flags, float* out,
-    double gbs)
+    double gbs, bool gbs_is_shared_rate)
 {
     if (n_tiles == 0)
         return;
@@ -1304,7 +1328,8 @@ void launch_host_background(cudaStream_t st, int sm_count, const FrameParams& fp
         const double v = e ? std::atof(e) : 0.0;
         return v > 0.0 ? v : 100.0;
     }();
-    gbs = std::min(gbs, host_gbs / std::max(1, fp.world));
+    if (!gbs_is_shared_rate) // no measurement with all ranks storing at once (rt_set_host_store_rate): assume
+        gbs = std::min(gbs, host_gbs / std::max(1, fp.world));
     if (gbs_env > 0.0)
         gbs = gbs_env;
     const int grid = grid_for((long long)n_tiles * kTileH * 32, 256, blocks_env > 0 ? blocks_env : std::max(1, sm_count / 2));

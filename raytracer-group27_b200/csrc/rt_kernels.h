@@ -25,7 +25,7 @@ void launch_pack_rgb_tiles(cudaStream_t st, int sm_count, const FrameParams& fp,
 void launch_row_flags(cudaStream_t st, int sm_count, const FrameParams& fp, unsigned first_lp, unsigned n_lp, const int2* hit, unsigned char* flags,
     unsigned* n_flagged);
 void launch_host_background(cudaStream_t st, int sm_count, const FrameParams& fp, unsigned tile0, unsigned n_tiles, const unsigned char* flags, float* out,
-    double gbs);
+    double gbs, bool gbs_is_shared_rate);
 // FMUL / FADD issue-rate microbenchmark; returns the number of FP32 lane-instructions the launch executes.  scratch: >= sm_count * 8 * 256 floats.
 double launch_fp32_peak(cudaStream_t st, int sm_count, float* scratch, int iters);
 void launch_intersect(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const float* rays, long long n, int use_bvh,

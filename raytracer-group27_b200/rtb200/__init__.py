@@ -132,6 +132,7 @@ SYMBOLS = [
     ("rt_framebuffer_ipc_handle", _I, [_P, _I, _I, _P]),
     ("rt_open_peer_framebuffer", _I, [_P, _P, C.POINTER(_P)]),
     ("rt_set_gather_target", _I, [_P, _P]),
+    ("rt_set_host_store_rate", _I, [_P, C.c_double]),
     ("rt_close_peer_framebuffer", _I, [_P, _P]),
     ("rt_download_rgb", _I, [_P, _P, _I, _I, _P]),
     ("rt_intersect", _I, [_P, _P, C.c_int64, _I, _P, _P]),
@@ -458,6 +459,10 @@ class Context:
         p = _P()
         _check(self._l.rt_open_peer_framebuffer(self._h, C.create_string_buffer(handle, 64), C.byref(p)))
         return p.value
+
+    def set_host_store_rate(self, gbs: float):
+        """Device-to-host rate of this rank's link measured while every rank of the job copies at once (GB/s); 0 = built-in assumption."""
+        _check(self._l.rt_set_host_store_rate(self._h, float(gbs)))
 
     def set_gather_target(self, ptr: int):
         """Same-process form of open_peer_framebuffer: `ptr` = the root's framebuffer() pointer right after its export."""

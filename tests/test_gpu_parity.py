@@ -304,6 +304,38 @@ def test_gather_frames_store_only_rows_with_hits(rtb, gpu_ctx):
     assert np.abs(gpu_ctx.download_rgb(ptr, w, h) - want["a"]).max() <= 1e-6
 
 
+def test_queue_overflow_is_clean_and_retried(rtb, gpu_ctx):
+    """A wavefront queue that overflows (views dominated by dielectrics or glossy surfaces can outgrow any fixed head-room) must end
+    the frame with RT_ERR_OVERFLOW and nothing else: consumers clamp their item counts to the queues' capacities and the rest of
+    the batch is skipped.  The device-resident call reports it; rt_render renders again with twice the head-room per attempt and
+    returns the frame.  RTB200_QUEUE_SCALE (read at context creation) shrinks the head-room to provoke it."""
+    import os
+    g = Golden("cornell_c1_256")
+    cam, prm = g.camera(), g.params()
+    gpu_ctx.upload_scene(g.scene, rtb.BVH_SAH_HOST)
+    want = gpu_ctx.render(cam, prm, want_ids=True)
+    os.environ["RTB200_QUEUE_SCALE"] = "0.05"
+    try:
+        small = rtb.Context(0)
+    finally:
+        del os.environ["RTB200_QUEUE_SCALE"]
+    try:
+        small.upload_scene(g.scene, rtb.BVH_SAH_HOST)
+        for _ in range(2):   # twice: the context stays usable
+            small.render_device(cam, prm)
+            with pytest.raises(rtb.RtError, match="overflow"):
+                small.sync()
+        rgb, ids, t, st = small.render(cam, prm, want_ids=True)
+        assert np.array_equal(ids, want[1]) and bits_equal(t, want[2])
+        assert np.abs(rgb - want[0]).max() <= 1e-6
+        assert (st.primary_rays, st.shadow_queries, st.secondary_rays) == (want[3].primary_rays, want[3].shadow_queries, want[3].secondary_rays)
+        # glossy_ray_count at the reference's default of 10 (main.cpp:126) renders as well: the queues are sized from it
+        glossy = small.render(cam, rtb.make_params(96, 96, 3, glossy_rays=10))
+        assert glossy[3].secondary_rays > want[3].secondary_rays * (96 * 96) / (g.w * g.h)
+    finally:
+        small.close()
+
+
 def test_errors_are_loud(rtb, gpu_ctx):
     g = Golden("tr_def_96")
     gpu_ctx.upload_scene(g.scene)
