@@ -471,7 +471,7 @@ int ensure_lane(rt_ctx* ctx, rt_ctx::Lane& ln, const FrameParams& fp, unsigned b
     const size_t cap = std::max<size_t>((size_t)kTilePixels,
         (size_t)((double)(prim * queue_multiplier(ctx, fp)) * ctx->queue_scale * (double)(1u << ctx->headroom_shift)));
     for (int k = 0; k < 2; k++) {
-        CK(ln.q_hit[k].ensure(cap));
+        CK(ln.q_hit[k].ensure(std::max(cap, prim))); // level 0 keeps a hit slot per primary ray whatever the head-room of the later levels
         b.q[k].hit = ln.q_hit[k].p;
         if (fp.max_level > 0) { // level 0 never stores rays (K1 is fused)
             CK(ln.q_o[k].ensure(cap));

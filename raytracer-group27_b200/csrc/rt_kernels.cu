@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_extend(
     // the rest of the batch is skipped, rt_sync reports RT_ERR_OVERFLOW and the caller renders again with more head-room
     if (batch_overflowed(b))
         return;
-    const unsigned n = min(b.counters->n_rays[qi], b.ray_capacity);
+    const unsigned n = LEVEL0 ? b.counters->n_rays[qi] : min(b.counters->n_rays[qi], b.ray_capacity); // (level 0: the batch's primary rays, set by the host)
     TraceStats st;
     int tag = 0;
     trace_queue<false, COUNT, LEVEL0 && RT_STATIC_L0>(
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
     __syncthreads();
     if (s_overflow)
         return;
-    const unsigned n = min(b.counters->n_rays[qi], b.ray_capacity);
+    const unsigned n = LEVEL0 ? b.counters->n_rays[qi] : min(b.counters->n_rays[qi], b.ray_capacity);
     const int qo = qi ^ 1;
     const unsigned n_round = (n + kShadeBlock - 1) / kShadeBlock * kShadeBlock;
     unsigned n_secondary = 0;
