@@ -391,9 +391,8 @@ def run_gpu(args):
             if rank == 0:
                 view[:] = 0.0
             shared_ptr = view.ctypes.data
-            err = torch.cuda.cudart().cudaHostRegister(shared_ptr, nbytes, 1 | 2)  # portable | mapped
-            if int(err) != 0:
-                raise RuntimeError(f"cudaHostRegister: {err}")
+            if rtb200.lib().rt_host_register(shared_ptr, nbytes) != 0:  # page-locked, mapped into the device
+                raise RuntimeError("rt_host_register: " + rtb200.lib().rt_last_error().decode())
         except Exception as e:
             ok.zero_()
             sys.stderr.write(f"[rank {rank}] shared host image unavailable ({e}); rank 0 downloads the gathered frame\n")
@@ -466,7 +465,7 @@ def run_gpu(args):
             if not diff <= 1e-6:
                 raise RuntimeError(f"shared host image differs from the gathered frame by {diff}")
         dist.barrier()
-        torch.cuda.cudart().cudaHostUnregister(shared_ptr)
+        rtb200.lib().rt_host_unregister(shared_ptr)
     if shared is not None:
         shared.close()
         if rank == 0:

@@ -11,6 +11,7 @@
  */
 #ifndef RT_B200_H
 #define RT_B200_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -249,6 +250,13 @@ int rt_sync(rt_ctx* ctx, rt_stats* stats);
  * this rank owns straight into it — no staging copy, every GPU over its own PCIe link — and touches nothing else, so after
  * all ranks have returned the buffer holds the frame renderRayTracing would have left in Screen::m_textureData. */
 int rt_render_shard(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, float* rgb_host_mapped, rt_stats* stats);
+/* Host memory of the caller as rt_render's fast path wants it: page-locked and mapped into every device (what host/screen.cpp does
+ * for the Screen's pixels, so that nothing above this header calls the CUDA runtime).  rt_host_register fails without a device or
+ * without the permission to lock pages; the caller then simply keeps pageable memory.  rt_current_device: the calling thread's
+ * current CUDA device (0 when there is none). */
+int rt_host_register(void* p, size_t bytes);
+int rt_host_unregister(void* p);
+int rt_current_device(void);
 /* The rows of background leave for the host while the frame is still traced, paced to just under what the link carries (stores that
  * back up into L2 slow the traversal kernels down).  One context measures its own link; what a link carries while ALL ranks of a
  * job store into the same host memory depends on the box (shared PCIe switches, the host's ingest rate) and only the job can measure

@@ -445,6 +445,11 @@ int make_frame_params(const rt_ctx* ctx, const rt_camera* cam, const rt_params* 
         g <<= 1;
     fp.sl_group = g;
     visible_pixel_rect(ctx, fp);
+    static const int min_quota_env = [] { // developer knob for A/B timing
+        const char* e = std::getenv("RTB200_MIN_QUOTA");
+        return e ? std::max(1, std::min(32, std::atoi(e))) : 0;
+    }();
+    fp.min_quota = min_quota_env > 0 ? min_quota_env : 1;
     return RT_OK;
 }
 
@@ -1661,6 +1666,35 @@ static int measure_store_rate(rt_ctx* ctx)
     return RT_OK;
 }
 
+int rt_host_register(void* p, size_t bytes)
+{
+    if (!p || !bytes)
+        return fail(RT_ERR_INVALID, "rt_host_register: empty range");
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(RT_ERR_CUDA, std::string("rt_host_register: ") + cudaGetErrorString(e));
+    }
+    return RT_OK;
+}
+
+int rt_host_unregister(void* p)
+{
+    if (p && cudaHostUnregister(p) != cudaSuccess)
+        cudaGetLastError();
+    return RT_OK;
+}
+
+int rt_current_device(void)
+{
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess) {
+        cudaGetLastError();
+        device = 0;
+    }
+    return device;
+}
+
 int rt_set_host_store_rate(rt_ctx* ctx, double gbs)
 {
     if (!ctx || !(gbs >= 0.0))
@@ -1769,7 +1803,11 @@ int rt_sync(rt_ctx* ctx, rt_stats* stats)
             c.ext_node_visits += h.ext_node_visits;
             c.ext_tri_tests += h.ext_tri_tests;
             c.ext_tri_tests_full += h.ext_tri_tests_full;
+            c.max_ray_nodes = std::max(c.max_ray_nodes, h.max_ray_nodes);
+            c.max_ray_tris = std::max(c.max_ray_tris, h.max_ray_tris);
         }
+        if (ctx->counters_enabled && std::getenv("RTB200_TRACE_LAUNCHES"))
+            std::fprintf(stderr, "[counters] longest query: %u boxes, %u triangles\n", c.max_ray_nodes, c.max_ray_tris);
         ctx->last_overflow = c.overflow;
         if (c.overflow == 1)
             return fail(RT_ERR_OVERFLOW, "a ray queue overflowed (transparent materials doubled the wavefront more than provisioned); lower rt_set_batch_rays");

@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_extend(
             }
             return false;
         },
-        LEVEL0 ? 32 : RT_MAX_QUOTA);
+        LEVEL0 ? 32 : RT_MAX_QUOTA, max(fp.min_quota, 1));
     if (COUNT) {
         warp_add_u64(&b.counters->node_visits, st.nodes);
         warp_add_u64(&b.counters->tri_tests, st.tris);
@@ -348,6 +348,8 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_extend(
         warp_add_u64(&b.counters->ext_node_visits, st.nodes);
         warp_add_u64(&b.counters->ext_tri_tests, st.tris);
         warp_add_u64(&b.counters->ext_tri_tests_full, st.tris_full);
+        atomicMax(&b.counters->max_ray_nodes, st.max_ray_nodes);
+        atomicMax(&b.counters->max_ray_tris, st.max_ray_tris);
     }
 }
 
@@ -736,12 +738,14 @@ __device__ __forceinline__ void shadow_loop(const SceneDev& s, int root_entry, c
             item_end(item, r == 0, cs.intensity);
             return false;
         },
-        RT_MAX_QUOTA);
+        RT_MAX_QUOTA, max(fp.min_quota, 1));
     warp_add_u64(&b.counters->shadow_queries, queries);
     if (COUNT) {
         warp_add_u64(&b.counters->node_visits, st.nodes);
         warp_add_u64(&b.counters->tri_tests, st.tris);
         warp_add_u64(&b.counters->tri_tests_full, st.tris_full);
+        atomicMax(&b.counters->max_ray_nodes, st.max_ray_nodes);
+        atomicMax(&b.counters->max_ray_tris, st.max_ray_tris);
     }
 }
 

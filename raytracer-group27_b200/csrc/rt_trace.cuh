@@ -24,6 +24,14 @@ namespace rtb {
 
 struct TraceStats {
     unsigned int nodes = 0, tris = 0, tris_full = 0;
+    unsigned int ray_start_nodes = 0, ray_start_tris = 0; // counters when the lane's current query began (instrumented builds)
+    unsigned int max_ray_nodes = 0, max_ray_tris = 0;     // most boxes / triangles any one query of this lane touched
+    __device__ __forceinline__ void query_begins() { ray_start_nodes = nodes; ray_start_tris = tris; }
+    __device__ __forceinline__ void query_ends()
+    {
+        max_ray_nodes = max(max_ray_nodes, nodes - ray_start_nodes);
+        max_ray_tris = max(max_ray_tris, tris - ray_start_tris);
+    }
 };
 
 struct HitRec {
@@ -427,7 +435,7 @@ __device__ __forceinline__ void trav_leaf_test(const SceneDev& s, Trav& tv, int 
 // otherwise issue 260 K same-address atomics, which L2 serialises at about 1 ns each.
 template <bool ANYHIT, bool COUNT, bool STATIC = false, typename Fetch, typename Finish>
 __device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, bool exhaustive, unsigned* cursor, unsigned n_items,
-    TraceStats& st, Fetch fetch, Finish finish, int max_quota = 32)
+    TraceStats& st, Fetch fetch, Finish finish, int max_quota = 32, int min_quota = 1)
 {
     constexpr unsigned kFullMask = 0xffffffffu;
     TravStack stack;
@@ -445,7 +453,7 @@ __device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, b
 #ifndef RT_MAX_QUOTA
 #define RT_MAX_QUOTA 32
 #endif
-    const int quota = STATIC ? 32 : (int)min((unsigned)max_quota, max(1u, (n_items + total_warps - 1) / total_warps));
+    const int quota = STATIC ? 32 : (int)min((unsigned)max_quota, max((unsigned)min_quota, (n_items + total_warps - 1) / total_warps));
     unsigned static_next = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u;
     if (STATIC)
         more = static_next < n_items;
@@ -487,6 +495,8 @@ __device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, b
                             active = false;
                             tv.cur = kTravDone;
                         } else {
+                            if (COUNT)
+                                st.query_begins();
                             trav_start<ANYHIT>(s, tv, o, d, q, root_entry);
                         }
                     }
@@ -535,9 +545,13 @@ __device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, b
             if (tv.cur == kTravDone) {
                 f3 o, d;
                 HitRec q;
-                if (finish(my, tv.best, o, d, q))
+                if (COUNT)
+                    st.query_ends();
+                if (finish(my, tv.best, o, d, q)) {
+                    if (COUNT)
+                        st.query_begins();
                     trav_start<ANYHIT>(s, tv, o, d, q, root_entry);
-                else
+                } else
                     active = false;
             }
         }

@@ -102,6 +102,7 @@ struct FrameParams {
     // Pixels [vis_x0, vis_x1) x [vis_y0, vis_y1) are the only ones whose camera rays can meet the scene (projection of its
     // bounding box, rt_capi.cu); the other primary rays are misses without being traced.  Whole image when unknown.
     int vis_x0, vis_x1, vis_y0, vis_y1;
+    int min_quota;       // fewest rays a warp of the traversal kernels takes per refill (small queues: fewer, fuller warps)
     int trace_grid_mult; // host side only: blocks per SM of the traversal kernels of this frame (0: the default, rt_kernels.cu)
 };
 
@@ -130,6 +131,7 @@ struct Counters {
     unsigned long long ext_node_visits; // the same three, counted by the extend kernel alone
     unsigned long long ext_tri_tests;
     unsigned long long ext_tri_tests_full;
+    unsigned int max_ray_nodes, max_ray_tris; // instrumented builds: most boxes / triangles one query touched
 };
 
 struct RayQueue {

@@ -1,5 +1,4 @@
 #include "screen.h"
-#include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdint>
 #include <fstream>
@@ -10,16 +9,16 @@ Screen::Screen(const glm::ivec2& resolution)
     : m_resolution(resolution), m_textureData(size_t(resolution.x) * size_t(resolution.y), glm::vec3(0.0f))
 {
     if (!m_textureData.empty()) {
-        m_pageLocked = cudaHostRegister(m_textureData.data(), m_textureData.size() * sizeof(glm::vec3), cudaHostRegisterPortable | cudaHostRegisterMapped) == cudaSuccess;
-        if (!m_pageLocked)
-            cudaGetLastError(); // no device (or no permission to lock pages): the frame then arrives through staged copies
+        // page-locked and device-mapped pixels are rt_render's fast path; without a device (or the permission to lock pages) the
+        // frame arrives through staged copies instead
+        m_pageLocked = rt_host_register(m_textureData.data(), m_textureData.size() * sizeof(glm::vec3)) == RT_OK;
     }
 }
 
 Screen::~Screen()
 {
-    if (m_pageLocked && cudaHostUnregister(m_textureData.data()) != cudaSuccess)
-        cudaGetLastError();
+    if (m_pageLocked)
+        rt_host_unregister(m_textureData.data());
 }
 
 void Screen::clear(const glm::vec3& color) { std::fill(m_textureData.begin(), m_textureData.end(), color); }
@@ -37,10 +36,7 @@ rt_ctx* postContext()
 {
     static rt_ctx* ctx = nullptr;
     if (!ctx) {
-        int device = 0;
-        if (cudaGetDevice(&device) != cudaSuccess)
-            device = 0;
-        if (rt_create(device, &ctx) != RT_OK)
+        if (rt_create(rt_current_device(), &ctx) != RT_OK)
             throw std::runtime_error(std::string("Screen: ") + rt_last_error());
     }
     return ctx;

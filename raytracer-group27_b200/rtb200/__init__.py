@@ -133,6 +133,9 @@ SYMBOLS = [
     ("rt_open_peer_framebuffer", _I, [_P, _P, C.POINTER(_P)]),
     ("rt_set_gather_target", _I, [_P, _P]),
     ("rt_set_host_store_rate", _I, [_P, C.c_double]),
+    ("rt_host_register", _I, [_P, C.c_size_t]),
+    ("rt_host_unregister", _I, [_P]),
+    ("rt_current_device", _I, []),
     ("rt_close_peer_framebuffer", _I, [_P, _P]),
     ("rt_download_rgb", _I, [_P, _P, _I, _I, _P]),
     ("rt_intersect", _I, [_P, _P, C.c_int64, _I, _P, _P]),
