@@ -27,6 +27,7 @@ using std::pow;   // glm's func_exponential.inl does `using std::pow;` for scala
 using std::sqrt;  // likewise `using std::sqrt;`
 using std::sin;
 using std::cos;
+using std::log2;  // func_exponential.inl with GLM_HAS_CXX11_STL: `using std::log2;` (src/ray_differentials.cpp:138)
 using std::exp;   // func_exponential.inl: `using std::exp;` for scalars (src/screen.cpp:325,363)
 
 typedef int length_t;
@@ -129,6 +130,11 @@ inline float dot(const vec3& a, const vec3& b) {
 inline vec3 cross(const vec3& x, const vec3& y) {
     return vec3(x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y);
 }
+inline float dot(const vec2& a, const vec2& b) {
+    const vec2 tmp(a.x * b.x, a.y * b.y);
+    return tmp.x + tmp.y;
+}
+inline float length(const vec2& v) { return std::sqrt(dot(v, v)); }
 inline float inversesqrt(float x) { return 1.0f / std::sqrt(x); }
 inline float length(const vec3& v) { return std::sqrt(dot(v, v)); }
 inline vec3 normalize(const vec3& v) { return v * inversesqrt(dot(v, v)); }

@@ -11,10 +11,19 @@
 //   getPixelRays                           src/main.cpp:309-335
 //   renderRayTracing                       src/main.cpp:340-400
 //   Screen::setPixel                       src/screen.cpp:32-38
-// Diffuse textures go through the reference's own Image class (src/image.cpp, also compiled verbatim) for the two
-// filters that do not need a mip level; ray differentials (main.cpp:137) only feed that level and are left out.
+// Diffuse textures go through the reference's own Image class (src/image.cpp, also compiled verbatim), with all five
+// filters; the level of detail of the mip-mapped ones comes from the reference's own ray differentials
+// (src/ray_differentials.cpp, compiled verbatim too: tranfer_and_reflect_ray_differentials, transfer_ray_differentials,
+// computeLevelOfDetails, called where main.cpp:83,137,168 call them).  One thing had to be DEFINED: Ray's default member
+// initialisers of dD_dx / dD_dy read the members `right` and `up`, which are declared — hence constructed — after them
+// (framework/include/ray.h:19-28): undefined behaviour, whatever the stack held.  defineDifferentials() below gives every
+// ray the values that code evidently means: the declared right = (1,0,0), up = (0,-1,0), evaluated with the direction the
+// ray had when its defaults ran — (0,0,-1) for a default-constructed ray that generateRay fills in afterwards
+// (trackball.cpp:92-95), the given direction for the aggregate-initialised reflection / refraction rays (main.cpp:199,286,288).
+// Child rays do not inherit differentials in the reference (they are fresh objects), so neither do they here.
 // Builds oracle/_ref/libref_oracle.so, kind "reference".
 #include "bounding_volume_hierarchy.h"
+#include "ray_differentials.h"
 #include "ray_tracing.h"
 #include "shadow.h"
 
@@ -32,6 +41,24 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+
+// The defined initial state of a ray's differentials (see the header comment): ray.h:19-28 with right / up as declared.
+static void defineDifferentials(Ray& ray, const glm::vec3& directionWhenConstructed)
+{
+    ray.right = glm::vec3(1, 0, 0);
+    ray.up = glm::vec3(0, -1, 0);
+    const glm::vec3 direction = directionWhenConstructed;
+    ray.dD_dx = (glm::dot(direction, direction) * ray.right - glm::dot(direction, ray.right) * direction) / glm::pow(glm::dot(direction, direction), 1.5f);
+    ray.dD_dy = (glm::dot(direction, direction) * ray.up - glm::dot(direction, ray.up) * direction) / glm::pow(glm::dot(direction, direction), 1.5f);
+    ray.dP_dx = glm::vec3(0);
+    ray.dP_dy = glm::vec3(0);
+}
+static Ray childRay(const glm::vec3& origin, const glm::vec3& direction) // `Ray r = { origin, direction };`
+{
+    Ray ray = { origin, direction };
+    defineDifferentials(ray, direction);
+    return ray;
+}
 
 // counters bumped by the drawRay stub (oracle/ref_stubs.cpp): every iteration of the reference's
 // cansee loop ends in exactly one drawRay call (src/shadow.cpp:45,49,62).
@@ -86,6 +113,7 @@ struct HeadlessTrackball { // framework/include/trackball.h:44-52 without the Wi
         const glm::vec3 cameraSpaceDirection = glm::normalize(
             glm::vec3(-pixel.x * halfScreenPlaceWidth, pixel.y * halfScreenPlaceHeight, 1.0f));
         Ray ray;
+        defineDifferentials(ray, glm::vec3(0.0f, 0.0f, -1.0f)); // the defaults ran on the default direction
         ray.origin = position();
         ray.direction = glm::quat(m_rotationEulerAngles) * cameraSpaceDirection;
         ray.t = std::numeric_limits<float>::max();
@@ -110,6 +138,7 @@ glm::vec3 getFinalColorNoRayTracingJustTextures(const RenderGlobals& g, Scene& s
 {
     HitInfo hitInfo;
     if (bvh.intersect(ray, hitInfo, g.useBVH)) {
+        transfer_ray_differentials(ray, hitInfo.normal); // main.cpp:83
         Material& mat = hitInfo.getMaterial(scene);
         if (mat.kdTexture) {
             Image& texture = mat.kdTexture.value();
@@ -117,7 +146,7 @@ glm::vec3 getFinalColorNoRayTracingJustTextures(const RenderGlobals& g, Scene& s
             texture.setOutOfBoundsRuleX(g_oob_x);
             texture.setOutOfBoundsRuleY(g_oob_y);
             texture.setTextureFilteringMethod(g_tex_filtering);
-            const float lod = 0.0f; // computeLevelOfDetails: defined as 0, see getFinalColor below
+            const float lod = computeLevelOfDetails(ray, hitInfo); // main.cpp:99
             return texture.getPixel(hitInfo.texCoord, lod);
         }
         return glm::vec3(1);
@@ -131,6 +160,8 @@ glm::vec3 getFinalColor(const RenderGlobals& g, Scene& scene, const BoundingVolu
     HitInfo hitInfo;
     if (!bvh.intersect(ray, hitInfo, g.useBVH))
         return glm::vec3(0.0f);
+
+    tranfer_and_reflect_ray_differentials(ray, hitInfo); // main.cpp:137
 
     glm::vec3 color(0);
     glm::vec3 reflect = glm::reflect(glm::normalize(ray.direction), glm::normalize(hitInfo.normal));
@@ -148,10 +179,7 @@ glm::vec3 getFinalColor(const RenderGlobals& g, Scene& scene, const BoundingVolu
         texture.setOutOfBoundsRuleX(g_oob_x);
         texture.setOutOfBoundsRuleY(g_oob_y);
         texture.setTextureFilteringMethod(g_tex_filtering);
-        // computeLevelOfDetails (src/ray_differentials.cpp:121-139) works on Ray::dD_dx / dD_dy, which the reference initialises from
-        // members constructed after them (framework/include/ray.h:19-28): its value is whatever the stack held.  Defined here as 0 —
-        // what the expression gives when those members read as zero; NearestNeighbor / Bilinear do not use it at all.
-        const float lod = 0.0f;
+        const float lod = computeLevelOfDetails(ray, hitInfo); // main.cpp:168
         matForRendering.kd = texture.getPixel(hitInfo.texCoord, lod);
     }
 
@@ -170,7 +198,7 @@ glm::vec3 getFinalColor(const RenderGlobals& g, Scene& scene, const BoundingVolu
     if (matForRendering.transparency == 1.0f) {
         if (matForRendering.ks.x > 0 || matForRendering.ks.y > 0 || matForRendering.ks.z > 0) {
             glm::vec3 reflectColor = glm::vec3(0);
-            Ray refRay = { hitInfo.hitPoint + 0.01f * reflect, reflect };
+            Ray refRay = childRay(hitInfo.hitPoint + 0.01f * reflect, reflect);
             cnt.secondary++;
             reflectColor += matForRendering.ks * getFinalColor(g, scene, bvh, refRay, level + 1, cnt);
             if (matForRendering.shininess != 0) {
@@ -191,10 +219,10 @@ glm::vec3 getFinalColor(const RenderGlobals& g, Scene& scene, const BoundingVolu
         float reflectionChance = R0 + (1 - R0) * (std::pow(1 - c, 5));
         float refractionChance = 1 - reflectionChance;
         cnt.secondary++;
-        color += reflectionChance * getFinalColor(g, scene, bvh, { hitInfo.hitPoint + 0.01f * reflect, reflect }, level + 1, cnt);
+        color += reflectionChance * getFinalColor(g, scene, bvh, childRay(hitInfo.hitPoint + 0.01f * reflect, reflect), level + 1, cnt);
         if (r * r * (1 - c * c) <= 1.0f) {
             cnt.secondary++;
-            color += refractionChance * getFinalColor(g, scene, bvh, { hitInfo.hitPoint + 0.01f * refract, refract }, level + 1, cnt);
+            color += refractionChance * getFinalColor(g, scene, bvh, childRay(hitInfo.hitPoint + 0.01f * refract, refract), level + 1, cnt);
         }
     }
     return color;

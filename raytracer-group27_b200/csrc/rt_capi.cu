@@ -2042,9 +2042,21 @@ int rt_set_textures(rt_ctx* ctx, const rt_texture* textures, int n_textures, con
             return fail(RT_ERR_INVALID, "rt_set_textures: empty texture");
         if (total + (size_t)textures[k].width * textures[k].height > 0x7fffffffu)
             return fail(RT_ERR_INVALID, "rt_set_textures: more than 2^31 texels");
-        const int tw = textures[k].width, th = textures[k].height; // Image::canUseMipmapping, src/image.cpp:411-413
-        table[k] = make_int4((int)total, tw, th, (((th & (th - 1)) == 0) && ((tw & (tw - 1)) == 0) && tw == th) ? 1 : 0);
-        total += (size_t)textures[k].width * textures[k].height;
+        // a square power-of-two texture gets a mip pyramid down to 1 x 1 (Image::canUseMipmapping / initMipmap, src/image.cpp:400-430):
+        // its levels follow level 0 back to back; table.w = number of levels, 0 = no pyramid
+        const int tw = textures[k].width, th = textures[k].height;
+        const bool pyramid = ((th & (th - 1)) == 0) && ((tw & (tw - 1)) == 0) && tw == th;
+        int levels = 0;
+        size_t texels_k = (size_t)tw * th;
+        if (pyramid) {
+            levels = 1;
+            for (int w = tw; w > 1; w /= 2, levels++)
+                texels_k += (size_t)(w / 2) * (w / 2);
+        }
+        table[k] = make_int4((int)total, tw, th, levels);
+        total += texels_k;
+        if (total > 0x7fffffffu)
+            return fail(RT_ERR_INVALID, "rt_set_textures: more than 2^31 texels");
     }
     for (int m = 0; m < n_materials; m++)
         if (material_texture[m] < -1 || material_texture[m] >= n_textures)
@@ -2054,6 +2066,20 @@ int rt_set_textures(rt_ctx* ctx, const rt_texture* textures, int n_textures, con
         const size_t n = (size_t)textures[k].width * textures[k].height;
         for (size_t i = 0; i < n; i++)
             texels[table[k].x + i] = make_float4(textures[k].rgb[3 * i], textures[k].rgb[3 * i + 1], textures[k].rgb[3 * i + 2], 0.0f);
+        // getReducedResolutionTexture (src/image.cpp:377-397): every texel of the next level = 0.25f * (upper left + lower left + upper right + lower right)
+        size_t src = (size_t)table[k].x;
+        for (int level = 1, w = textures[k].width; level < table[k].w; level++, w /= 2) {
+            const size_t dst = src + (size_t)w * w;
+            const int rw = w / 2;
+            for (int y = 0; y < rw; y++)
+                for (int x = 0; x < rw; x++) {
+                    const float4 lu = texels[src + (size_t)(2 * y) * w + 2 * x], ll = texels[src + (size_t)(2 * y + 1) * w + 2 * x];
+                    const float4 ru = texels[src + (size_t)(2 * y) * w + 2 * x + 1], rl = texels[src + (size_t)(2 * y + 1) * w + 2 * x + 1];
+                    texels[dst + (size_t)y * rw + x] = make_float4(0.25f * (((lu.x + ll.x) + ru.x) + rl.x), 0.25f * (((lu.y + ll.y) + ru.y) + rl.y),
+                        0.25f * (((lu.z + ll.z) + ru.z) + rl.z), 0.0f);
+                }
+            src = dst;
+        }
     }
     CK(cudaStreamSynchronize(ctx->stream)); // an earlier frame may still sample the old texels
     CK(ctx->d_tex_texels.ensure(total));

@@ -197,7 +197,30 @@ __device__ __forceinline__ f3 tex_lerp(float low, float high, const f3& cl, cons
     return xadd(xmul(cl, xsub(1.0f, c)), xmul(ch, c));
 }
 
-__device__ __forceinline__ f3 sample_texture(const SceneDev& s, const FrameParams& fp, int tex, float u, float v)
+__device__ __forceinline__ f3 tex_nearest(const float4* px, unsigned w, unsigned h, float ix, float iy) // nearestNeighbor, image.cpp:201-228
+{
+    unsigned x = (unsigned)roundf(ix), y = (unsigned)roundf(iy);
+    if (x >= w)
+        x = w - 1u;
+    if (y >= h)
+        y = h - 1u;
+    return mk3(__ldg(&px[(size_t)y * w + x]));
+}
+
+__device__ __forceinline__ f3 tex_bilinear(const float4* px, unsigned w, float ix, float iy) // bilinearInterpolation, image.cpp:231-251
+{
+    const float xl = floorf(ix), xh = ceilf(ix), yl = floorf(iy), yh = ceilf(iy);
+    const f3 ll = mk3(__ldg(&px[(size_t)(unsigned)yl * w + (unsigned)xl])), lr = mk3(__ldg(&px[(size_t)(unsigned)yl * w + (unsigned)xh]));
+    const f3 hl = mk3(__ldg(&px[(size_t)(unsigned)yh * w + (unsigned)xl])), hr = mk3(__ldg(&px[(size_t)(unsigned)yh * w + (unsigned)xh]));
+    const f3 low = tex_lerp(xl, xh, ll, lr, ix), high = tex_lerp(xl, xh, hl, hr, ix);
+    return tex_lerp(yl, yh, low, high, iy);
+}
+
+// First texel of pyramid level `level` of a w x w texture whose levels lie back to back: sum of (w >> i)^2 for i < level.
+__device__ __forceinline__ unsigned mip_offset(unsigned w, unsigned level) { return (4u * (w * w - (w >> level) * (w >> level))) / 3u; }
+
+// Image::getPixel (src/image.cpp:75-112) with the out-of-bounds rules (110-198) and all five filters; lod: computeLevelOfDetails.
+__device__ __forceinline__ f3 sample_texture(const SceneDev& s, const FrameParams& fp, int tex, float u, float v, float lod)
 {
     const f3 border = mk3(fp.tex_border_r, fp.tex_border_g, fp.tex_border_b);
     if (fp.tex_oob_x == 0 && tex_out_of_bounds(u))
@@ -209,28 +232,91 @@ __device__ __forceinline__ f3 sample_texture(const SceneDev& s, const FrameParam
     const int4 tb = __ldg(&s.tex_table[tex]);
     const unsigned w = (unsigned)tb.y, h = (unsigned)tb.z;
     const float4* px = s.tex_texels + tb.x;
-    // Mip-mapped filters (2, 3, 4) at level of detail 0, see rt_b200.h: no pyramid (the texture is not a square power of two,
-    // src/image.cpp:411-413) -> white, Trilinear black (270-330); otherwise level 0 with the nearest / bilinear sample.
-    if (fp.tex_filter >= 2 && tb.w == 0)
-        return fp.tex_filter == 4 ? mk3(0.0f, 0.0f, 0.0f) : mk3(1.0f, 1.0f, 1.0f);
-    const float ix = xmul(u, (float)(w - 1u)), iy = xmul(xsub(1.0f, v), (float)(h - 1u));
-    if (fp.tex_filter == 0 || fp.tex_filter == 2) {
-        unsigned x = (unsigned)roundf(ix), y = (unsigned)roundf(iy);
-        if (x >= w)
-            x = w - 1u;
-        if (y >= h)
-            y = h - 1u;
-        return mk3(__ldg(&px[(size_t)y * w + x]));
+    if (fp.tex_filter < 2) { // level 0 of the image itself; toImageCoordinates (118-131): rows start at the top
+        const float ix = xmul(u, (float)(w - 1u)), iy = xmul(xsub(1.0f, v), (float)(h - 1u));
+        return fp.tex_filter == 0 ? tex_nearest(px, w, h, ix, iy) : tex_bilinear(px, w, ix, iy);
     }
-    const float xl = floorf(ix), xh = ceilf(ix), yl = floorf(iy), yh = ceilf(iy);
-    const f3 ll = mk3(__ldg(&px[(size_t)(unsigned)yl * w + (unsigned)xl])), lr = mk3(__ldg(&px[(size_t)(unsigned)yl * w + (unsigned)xh]));
-    const f3 hl = mk3(__ldg(&px[(size_t)(unsigned)yh * w + (unsigned)xl])), hr = mk3(__ldg(&px[(size_t)(unsigned)yh * w + (unsigned)xh]));
-    const f3 low = tex_lerp(xl, xh, ll, lr, ix), high = tex_lerp(xl, xh, hl, hr, ix);
-    return tex_lerp(yl, yh, low, high, iy);
+    // The mip-mapped filters: nearestLevelMipmapping (255-277), nearestLevelBilinear (280-302), trilinearInterpolation (305-363) with
+    // getBestLevelMipmap (506-541).  tb.w = number of pyramid levels; 0: the texture is not a square power of two and has none
+    // (canUseMipmapping, 400-402), the filters then answer white, Trilinear black.
+    const int n = tb.w;
+    if (n == 0)
+        return fp.tex_filter == 4 ? mk3(0.0f, 0.0f, 0.0f) : mk3(1.0f, 1.0f, 1.0f);
+    if (fp.tex_filter != 4) {
+        unsigned level;
+        if (xsub(lod, floorf(lod)) < xsub(ceilf(lod), lod))
+            level = (unsigned)(int)fmaxf(0.0f, floorf(lod));
+        else
+            level = (unsigned)(int)fminf((float)n - 1.0f, ceilf(lod));
+        const unsigned wl = w >> level;
+        const float ix = xmul(u, (float)(wl - 1u)), iy = xmul(xsub(1.0f, v), (float)(wl - 1u));
+        const float4* pl = px + mip_offset(w, level);
+        return fp.tex_filter == 2 ? tex_nearest(pl, wl, wl, ix, iy) : tex_bilinear(pl, wl, ix, iy);
+    }
+    const unsigned high = (unsigned)(int)fminf((float)n - 1.0f, ceilf(lod)), low = (unsigned)(int)fmaxf(0.0f, floorf(lod));
+    if (low >= (unsigned)n || high >= (unsigned)n) // getWidthHeightForLevel fails
+        return mk3(0.0f, 0.0f, 0.0f);
+    const unsigned wlo = w >> low, whi = w >> high;
+    const f3 cl = tex_bilinear(px + mip_offset(w, low), wlo, xmul(u, (float)(wlo - 1u)), xmul(xsub(1.0f, v), (float)(wlo - 1u)));
+    const f3 ch = tex_bilinear(px + mip_offset(w, high), whi, xmul(u, (float)(whi - 1u)), xmul(xsub(1.0f, v), (float)(whi - 1u)));
+    return tex_lerp((float)low, (float)high, cl, ch, lod);
+}
+
+// computeDerivativeOfBarycentricCoordinate, src/ray_differentials.cpp:38-48
+__device__ __forceinline__ float bary_derivative(const f3& a, const f3& b, const f3& p, const f3& pd, float area)
+{
+    const f3 term1 = xadd(xcross(pd, xsub(p, b)), xcross(xsub(p, a), pd));
+    const f3 term2 = xcross(xsub(a, p), xsub(b, p));
+    const float nominator = xadd(xdot(term1, term2), xdot(term2, term1));
+    const float denominator = xmul(xmul(2.0f, area), xsqrt(xdot(term2, term2)));
+    return xdiv(nominator, denominator);
+}
+
+// Level of detail of a textured triangle hit: the ray differentials of framework/include/ray.h:19-28 (their initial state DEFINED
+// as in oracle/ref_harness.cpp: right = (1,0,0), up = (0,-1,0), evaluated on (0,0,-1) for camera rays — Trackball::generateRay fills
+// a default-constructed Ray — and on the ray's own direction for reflection / refraction / glossy rays, which are fresh objects and
+// inherit nothing), transfer_ray_differentials (src/ray_differentials.cpp:5-16) and computeLevelOfDetails (121-139) with
+// computeTexturePartialDerivativeInInterpolatedTrianglePoint (73-88).  d, t: the ray as traced and its hit parameter.
+// std::pow / std::log2 of the reference are evaluated in double and rounded (glibc's float versions can differ from that in the last place).
+__device__ __forceinline__ float level_of_detail(const SceneDev& s, const Shading& sh, int ti, const f3& d, float t, bool camera_ray)
+{
+    const f3 right = mk3(1.0f, 0.0f, 0.0f), up = mk3(0.0f, -1.0f, 0.0f);
+    const f3 dir0 = camera_ray ? mk3(0.0f, 0.0f, -1.0f) : d;
+    const float dd = xdot(dir0, dir0);
+    const float p15 = (float)pow((double)dd, 1.5);
+    const f3 dDx = xdiv(xsub(xmul(right, dd), xmul(dir0, xdot(dir0, right))), p15);
+    const f3 dDy = xdiv(xsub(xmul(up, dd), xmul(dir0, xdot(dir0, up))), p15);
+    const f3 N = xnormalize(sh.N), D = xnormalize(d);
+    const f3 zero = mk3(0.0f, 0.0f, 0.0f);
+    const f3 ax = xadd(zero, xmul(dDx, t)), ay = xadd(zero, xmul(dDy, t)); // dP + t * dD with dP = 0
+    const float dn = xdot(D, N);
+    const float dt_dx = xdiv(-xdot(ax, N), dn), dt_dy = xdiv(-xdot(ay, N), dn);
+    const f3 dPx = xadd(ax, xmul(D, dt_dx)), dPy = xadd(ay, xmul(D, dt_dy));
+    const f3 v0 = mk3(__ldg(&s.tri_v0[kTriStride * ti])), v1 = mk3(__ldg(&s.tri_v1[kTriStride * ti])), v2 = mk3(__ldg(&s.tri_v2[kTriStride * ti]));
+    float2 t0 = make_float2(0.0f, 0.0f), t1 = t0, t2 = t0;
+    if (s.tri_uv) {
+        t0 = __ldg(&s.tri_uv[3 * (size_t)sh.gid]);
+        t1 = __ldg(&s.tri_uv[3 * (size_t)sh.gid + 1]);
+        t2 = __ldg(&s.tri_uv[3 * (size_t)sh.gid + 2]);
+    }
+    const float area = xlength(xcross(xsub(v2, v0), xsub(v1, v0)));
+    float len[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const f3 pd = k == 0 ? dPx : dPy;
+        const float a = bary_derivative(v2, v1, sh.p, pd, area), b = bary_derivative(v0, v2, sh.p, pd, area), c = bary_derivative(v1, v0, sh.p, pd, area);
+        const float tx = xmul(1.0f, xadd(xadd(xmul(a, t0.x), xmul(b, t1.x)), xmul(c, t2.x)));
+        const float ty = xmul(1.0f, xadd(xadd(xmul(a, t0.y), xmul(b, t1.y)), xmul(c, t2.y)));
+        len[k] = xsqrt(xadd(xmul(tx, tx), xmul(ty, ty)));
+    }
+    const float m = (len[0] < len[1]) ? len[1] : len[0]; // glm::max(a, b) = (a < b) ? b : a
+    const float l = (float)log2((double)m);
+    return (0.0f < l) ? l : 0.0f;
 }
 
 // kd of a hit: the material's, or its texture at the interpolated texture coordinate (getFinalColor, src/main.cpp:155-171)
-__device__ __forceinline__ f3 diffuse_colour(const SceneDev& s, const FrameParams& fp, const Shading& sh, bool force = false)
+__device__ __forceinline__ f3 diffuse_colour(const SceneDev& s, const FrameParams& fp, const Shading& sh, int ti, const f3& d, float t, bool camera_ray,
+    bool force = false)
 {
     if ((fp.tex_on || force) && sh.mesh >= 0) {
         const int tex = __ldg(&s.mat_tex[sh.mesh]);
@@ -243,7 +329,8 @@ __device__ __forceinline__ f3 diffuse_colour(const SceneDev& s, const FrameParam
             }
             const float u = xadd(xadd(xmul(t0.x, sh.c0), xmul(t1.x, sh.c1)), xmul(t2.x, sh.c2));
             const float v = xadd(xadd(xmul(t0.y, sh.c0), xmul(t1.y, sh.c1)), xmul(t2.y, sh.c2));
-            return sample_texture(s, fp, tex, u, v);
+            const float lod = fp.tex_filter >= 2 ? level_of_detail(s, sh, ti, d, t, camera_ray) : 0.0f;
+            return sample_texture(s, fp, tex, u, v, lod);
         }
     }
     return mk3(sh.m0);
@@ -400,6 +487,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
         int pix = 0;
         unsigned path = 0; // path id of the ray (glossy random stream; 0 and unused when glossy_ray_count is 1)
         f3 w = mk3(0, 0, 0), refl = mk3(0, 0, 0), refr = mk3(0, 0, 0), dn = mk3(0, 0, 0), Nn = mk3(0, 0, 0);
+        f3 d_ray = mk3(0, 0, 0); // the ray as traced (EXTRAS: the mip-mapped texture filters take their level of detail from it)
         Shading sh;
         sh.p = mk3(0, 0, 0);
         sh.N = mk3(0, 0, 0);
@@ -443,6 +531,8 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
                 }
                 pix = tag >> 1;
                 sh = shading_at(s, h.y, o, d, __int_as_float(h.x));
+                if (EXTRAS)
+                    d_ray = d;
                 dn = xnormalize(d);
                 Nn = xnormalize(sh.N);
                 refl = xreflect(dn, Nn); // main.cpp:141
@@ -452,12 +542,12 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
             if (hit) {
                 f3 c = mk3(1.0f, 1.0f, 1.0f);
                 if (fp.tex_available && sh.mesh >= 0 && __ldg(&s.mat_tex[sh.mesh]) >= 0)
-                    c = diffuse_colour(s, fp, sh, true);
+                    c = diffuse_colour(s, fp, sh, h.y, d_ray, __int_as_float(h.x), LEVEL0, true);
                 accumulate(b.accum, pix, c.x, c.y, c.z);
             }
             continue;
         }
-        const f3 kd = (EXTRAS && hit) ? diffuse_colour(s, fp, sh) : mk3(sh.m0), ks = mk3(sh.m1);
+        const f3 kd = (EXTRAS && hit) ? diffuse_colour(s, fp, sh, h.y, d_ray, __int_as_float(h.x), LEVEL0) : mk3(sh.m0), ks = mk3(sh.m1);
         const float shininess = sh.m0.w, transparency = sh.m1.w;
 
         // children

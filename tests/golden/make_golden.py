@@ -27,12 +27,15 @@ from rtb200 import standin  # noqa: E402
 DATA = "/root/reference/data/"
 OUT = os.path.dirname(os.path.abspath(__file__))
 
+ONLY = sys.argv[1:]
 CAM = dict(look_at=(0.0, 0.0, 0.0), euler_deg=(20.0, 20.0, 0.0), dist=3.0, fovy_deg=50.0)  # src/main.cpp:413-414
 
 
 def mint(name, sc, w, h, *, max_level, sphere_rays=10, sample_mode=0, sample_size=4, colour_from="reference", cam=CAM, plane_rays_1d=3, tex=None, texture_debug=False):
     """tex: dict(filtering, oob_x, oob_y, border) = useTextures on with these knobs (the scene carries uv / textures / mesh_tex);
     texture_debug: renderRayTracing's textureDebugging view (main.cpp:355-356), useTextures off, the knobs of `tex` still apply."""
+    if ONLY and not any(k in name for k in ONLY):   # `python make_golden.py tex_mip tex_tri`: mint only the fixtures whose names contain one of the words
+        return
     c = rtb200.make_camera(**cam)
     ref, port = oracle.Oracle("reference"), oracle.Oracle("port")
     for o in (ref, port):
@@ -87,7 +90,8 @@ def with_lights(sc, point=None, sphere=None):
     return sc
 
 
-def textured_scene():
+def textured_scene(mip_floor=False):
+    """mip_floor: the floor gets a 64x64 texture (square power of two: it has a mip pyramid, and the level of detail varies over it)."""
     quad = np.array([[-1.5, -0.6, -1.5, 1.5, -0.6, -1.5, 1.5, -0.6, 1.5], [-1.5, -0.6, -1.5, 1.5, -0.6, 1.5, -1.5, -0.6, 1.5]], np.float32)
     quv = np.array([[-0.5, -0.5, 1.5, -0.5, 1.5, 1.5], [-0.5, -0.5, 1.5, 1.5, -0.5, 1.5]], np.float32)
     cube = rtb200.load_obj(DATA + "cube.obj", False)
@@ -103,6 +107,11 @@ def textured_scene():
     sc.textures = [np.linspace(0, 255, 7 * 5 * 3).reshape(5, 7, 3).astype(np.uint8),
                    ((np.indices((16, 16)).sum(0) % 2)[..., None] * np.array([245, 190, 30]) + 10).astype(np.uint8)]
     sc.mesh_tex = np.array([0, 1, -1, 1, -1, 0, 1], np.int32)
+    if mip_floor:
+        yy, xx = np.indices((64, 64))
+        pat = np.stack([(xx * 4) % 256, (yy * 4 + xx * 2) % 256, ((xx // 8 + yy // 8) % 2) * 200 + 30], -1)
+        sc.textures.append((pat ^ rng.integers(0, 64, pat.shape)).astype(np.uint8))
+        sc.mesh_tex[0] = 2
     return sc
 
 
@@ -165,10 +174,16 @@ def main():
     # with random coordinates; a 7x5 gradient and a 16x16 checker; both filters that need no mip level, four rule pairs
     for nm, filt, ox, oy in (("tex_nearest_border_96x80", 0, 0, 0), ("tex_bilinear_clamp_repeat_96x80", 1, 1, 2), ("tex_nearest_repeat_clamp_96x80", 0, 2, 1),
                              ("tex_bilinear_repeat_96x80", 1, 2, 2),
-                             # the mip-mapped filters at the defined level of detail 0 (oracle_api.h): the 16x16 checker has a
-                             # pyramid and is sampled at level 0, the 7x5 gradient has none and answers white / black
+                             # the mip-mapped filters; their level of detail comes from the ray differentials (src/ray_differentials.cpp,
+                             # initial state defined in oracle/ref_harness.cpp): the 16x16 checker has a pyramid, the 7x5 gradient has
+                             # none and answers white / black
                              ("tex_mipnearest_repeat_96x80", 2, 2, 2), ("tex_mipbilinear_clamp_96x80", 3, 1, 1), ("tex_trilinear_repeat_clamp_96x80", 4, 2, 1)):
         mint(nm, textured_scene(), 96, 80, max_level=2, tex=dict(filtering=filt, oob_x=ox, oob_y=oy, border=(0.2, 0.1, 0.4)))
+    # the same with a 64x64 texture on the floor: the level of detail runs over several pyramid levels across the floor, for camera
+    # rays (differentials of a default-constructed Ray) and for the rays mirrored by the floor and the cube (differentials from their direction)
+    for nm, filt, ox, oy in (("tex_trilinear_floor64_96x80", 4, 2, 2), ("tex_mipnearest_floor64_96x80", 2, 2, 1), ("tex_mipbilinear_floor64_96x80", 3, 1, 2)):
+        mint(nm, textured_scene(mip_floor=True), 96, 80, max_level=2, tex=dict(filtering=filt, oob_x=ox, oob_y=oy, border=(0.2, 0.1, 0.4)))
+    mint("texdebug_trilinear_floor64_96x80", textured_scene(mip_floor=True), 96, 80, max_level=2, tex=dict(filtering=4, oob_x=2, oob_y=2, border=(0.2, 0.1, 0.4)), texture_debug=True)
     # renderRayTracing(..., textureDebugging = true) (main.cpp:355-356): texel of the corner ray's hit, white without a texture
     mint("texdebug_bilinear_repeat_clamp_96x80", textured_scene(), 96, 80, max_level=2, tex=dict(filtering=1, oob_x=2, oob_y=1, border=(0.2, 0.1, 0.4)), texture_debug=True)
     # Monkey preset: two point lights (scene.cpp:52-57), mirror-ish material
@@ -190,6 +205,8 @@ def main():
     # drop the 6 MB of geometry from that fixture again: the tests regenerate it and check a checksum instead
     path = os.path.join(OUT, "dragon_standin_c3_160x90.npz")
     d = dict(np.load(path))
+    if "pos" not in d:   # not minted in this run (name filter)
+        return
     d["pos_sum"] = np.float64(d["pos"].astype(np.float64).sum())
     d["pos_sha"] = np.frombuffer(__import__("hashlib").sha256(d["pos"].tobytes()).digest(), np.uint8)
     d["n_tris"] = d["pos"].shape[0]

@@ -8,7 +8,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 GOLDEN_NAMES = ["cornell_planelight_160", "cornell_planelight_inside_96", "cube_preset_spot_128", "monkey_spots_128", "cornell_preset_sphere_192", "spheres_preset_160", "cornell_c1_256", "cornell_c4_96", "cornell_sph10_aa_80x48", "cornell_ms16_70x45", "cornell_inside_128", "monkey_192",
-                "cube_96", "zfight_96", "tex_nearest_border_96x80", "tex_bilinear_clamp_repeat_96x80", "tex_nearest_repeat_clamp_96x80", "tex_bilinear_repeat_96x80", "tex_mipnearest_repeat_96x80", "tex_mipbilinear_clamp_96x80", "tex_trilinear_repeat_clamp_96x80", "texdebug_bilinear_repeat_clamp_96x80", "andreas_160x120", "catalin_128x96", "mike_128x96", "tr_def_96", "teapot_c2_256x144", "teapot_d3_128x72", "dragon_standin_c3_160x90"]
+                "cube_96", "zfight_96", "tex_nearest_border_96x80", "tex_bilinear_clamp_repeat_96x80", "tex_nearest_repeat_clamp_96x80", "tex_bilinear_repeat_96x80", "tex_mipnearest_repeat_96x80", "tex_mipbilinear_clamp_96x80", "tex_trilinear_repeat_clamp_96x80", "tex_trilinear_floor64_96x80", "tex_mipnearest_floor64_96x80", "tex_mipbilinear_floor64_96x80",
+                "texdebug_trilinear_floor64_96x80", "texdebug_bilinear_repeat_clamp_96x80", "andreas_160x120", "catalin_128x96", "mike_128x96", "tr_def_96", "teapot_c2_256x144", "teapot_d3_128x72", "dragon_standin_c3_160x90"]
 
 
 # Screen settings exercised by the post-processing fixture (tests/golden/make_golden_post.py) and the GPU tests; keyword
