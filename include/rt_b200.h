@@ -124,13 +124,17 @@ int rt_set_lights(rt_ctx* ctx, const rt_point_light* point, int n_point, const r
  * getFinalColor (src/main.cpp:155-171) with Image::getPixel (src/image.cpp:75-108). */
 #define RT_TEX_NEAREST 0   /* TextureFiltering (src/image.h:24-31): NearestNeighbor                                   */
 #define RT_TEX_BILINEAR 1  /* Bilinear                                                                                 */
-#define RT_TEX_MIP_NEAREST 2    /* MipMappingNearestLevelNearestNeighbor | The level of detail of these three comes    */
-#define RT_TEX_MIP_BILINEAR 3   /* MipMappingNearestLevelBilinear        | from Ray::dD_dx / dD_dy, which the reference */
-#define RT_TEX_TRILINEAR 4      /* Trilinear                             | initialises from members constructed later  */
-                           /* (framework/include/ray.h:19-28): whatever the stack held.  Here it is DEFINED as 0, the     */
-                           /* value of that expression when those members read as zero: textures with a mip pyramid       */
-                           /* (square, power of two) are sampled at level 0, the others answer white (Trilinear: black),  */
-                           /* exactly as Image::getPixel does for lod = 0 (src/image.cpp:270-330, 506-538).               */
+#define RT_TEX_MIP_NEAREST 2    /* MipMappingNearestLevelNearestNeighbor */
+#define RT_TEX_MIP_BILINEAR 3   /* MipMappingNearestLevelBilinear        */
+#define RT_TEX_TRILINEAR 4      /* Trilinear                             */
+/* The three mip-mapped filters sample the pyramid Image::initMipmap builds for square power-of-two textures (src/image.cpp:377-430;
+ * built by rt_set_textures; textures without one answer white, Trilinear black) at the level of detail computeLevelOfDetails
+ * derives from the ray differentials at the hit (src/ray_differentials.cpp:5-16, 38-88, 121-139; main.cpp:137, 168).  One thing is
+ * DEFINED: Ray's default member initialisers of dD_dx / dD_dy read the members `right` and `up` before these are constructed
+ * (framework/include/ray.h:19-28) — undefined behaviour in the reference; here they have the values their declarations give them,
+ * right = (1,0,0), up = (0,-1,0).  Everything else follows the reference to the letter, including that camera rays evaluate those
+ * defaults on the default direction (0,0,-1) (Trackball::generateRay fills a default-constructed Ray) and that reflection /
+ * refraction rays are fresh Ray objects that inherit no differentials. */
 #define RT_OOB_BORDER 0    /* OutOfBoundsRule, src/image.h:18-22 */
 #define RT_OOB_CLAMP 1
 #define RT_OOB_REPEAT 2

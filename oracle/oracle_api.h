@@ -103,7 +103,8 @@ void oracle_set_extra_lights(const float* spot, int n_spot, const float* plane, 
  * filtering: TextureFiltering (src/image.h:24-31) 0 NearestNeighbor, 1 Bilinear, 2 MipMappingNearestLevelNearestNeighbor,
  * 3 MipMappingNearestLevelBilinear, 4 Trilinear.  The mip-mapped modes take their level from ray differentials that the reference
  * initialises from not-yet-constructed members (framework/include/ray.h:19-28), i.e. from whatever the stack held; both checkers
- * sample them at level of detail 0, the value that expression has when those members read as zero.  oob_x / oob_y: OutOfBoundsRule (src/image.h:18-22) 0 Border, 1 Clamp, 2 Repeat.  use_textures is main.cpp's useTextures (the
+ * give those members the values of their declarations, right = (1,0,0) and up = (0,-1,0) (ref_harness.cpp: defineDifferentials;
+ * oracle_port.cpp: initialDifferentials), and run the reference's src/ray_differentials.cpp from there.  oob_x / oob_y: OutOfBoundsRule (src/image.h:18-22) 0 Border, 1 Clamp, 2 Repeat.  use_textures is main.cpp's useTextures (the
  * materials keep their textures either way, the texture-debug view reads them regardless); n_textures = 0 removes them. */
 typedef struct {
     int width, height;

@@ -1,8 +1,8 @@
 // Image — the reference's texture class (src/image.h:33-47) as far as the rebuilt path needs it: the texels, decoded
 // like Image::Image does (8-bit RGB through the image reader, each byte / 255.0f, src/image.cpp:36-59), and the knobs
-// main.cpp sets on a texture before sampling it (src/main.cpp:159-162).  Sampling itself — Image::getPixel for the
-// NearestNeighbor and Bilinear filters — runs on the device (csrc/rt_kernels.cu sample_texture); the mip-mapped
-// filters are not offered (see include/rt_b200.h).  stb_image is not vendored by the reference; PNG files (every
+// main.cpp sets on a texture before sampling it (src/main.cpp:159-162).  Sampling itself — Image::getPixel with all five
+// filters, the mip pyramid and the level of detail from the ray differentials — runs on the device (csrc/rt_kernels.cu:
+// sample_texture, level_of_detail; the pyramid is built by rt_set_textures).  stb_image is not vendored by the reference; PNG files (every
 // texture the reference ships) are decoded here with zlib.
 #pragma once
 #include <exception>
