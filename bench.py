@@ -46,7 +46,7 @@ def load_workload(name):
     desc, w, h, depth, srays = WORKLOADS[name]
     if name == "c3":
         sc = standin.dragon_standin_scene()
-    elif name == "c5":  # BASELINE.json configs[4]; device LBVH (a host SAH build of 44.5 M triangles takes half a minute)
+    elif name == "c5":  # BASELINE.json configs[4]
         return desc, standin.dragon_lattice_scene(), rtb200.make_camera(), rtb200.make_params(w, h, depth, srays, sample_mode=2, sample_size=16)
     else:  # geometry of the reference's assets travels inside the golden fixtures (tests/golden/make_golden.py)
         d = np.load(os.path.join(ROOT, "tests", "golden", GOLDEN_OF[name] + ".npz"))
@@ -79,9 +79,15 @@ def load_workload_reference(name):
     return desc, sc, cam, _Params(w, h, depth, srays)
 
 
+def BVH_MODES(rtb200):
+    """--bvh: ploc = built on the device (Morton order, locally-ordered clustering below, binned SAH on top; rt_ploc.cu; the default),
+    lbvh = Karras' Morton hierarchy on the device, sah = binned SAH on the host."""
+    return {"ploc": rtb200.BVH_PLOC_DEVICE, "lbvh": rtb200.BVH_LBVH_DEVICE, "sah": rtb200.BVH_SAH_HOST}
+
+
 def job_config(args, desc, world, gather=None):
     """`config` of the JSON line: the job, identical for both arms (the reference arm runs on the GPU arm's config)."""
-    return {"workload": desc, "bvh": "lbvh" if args.workload == "c5" else args.bvh,
+    return {"workload": desc, "bvh": args.bvh,
             "sharding": f"interleaved 32x16 tiles over {world} GPU(s), scene replicated",
             "gather": gather or ("none (single GPU)" if world == 1 else "peer_store"),
             "l2": "flushed between timed steps (512 MiB memset outside the event pair)"}
@@ -253,8 +259,10 @@ def run_gpu(args):
     ctx = rtb200.Context(local_rank)
     ctx.set_stream(stream.cuda_stream)
     if args.workload == "c5":
-        args.bvh, args.no_cpu_baseline = "lbvh", True   # the CPU reference needs ~10 GB and seconds per ray on this mesh
-    bvh_mode = rtb200.BVH_SAH_HOST if args.bvh == "sah" else rtb200.BVH_LBVH_DEVICE
+        args.no_cpu_baseline = True   # the CPU reference needs ~10 GB and seconds per ray on this mesh
+        if args.bvh == "sah":
+            args.bvh = "ploc"         # (a host SAH build of 44.5 M triangles takes half a minute)
+    bvh_mode = BVH_MODES(rtb200)[args.bvh]
     t0 = time.perf_counter()
     ctx.upload_scene(sc, bvh_mode)
     build_ms = 1e3 * (time.perf_counter() - t0)
@@ -583,7 +591,7 @@ def measure_config(ctx, name, flush, fp32_peak, mg):
     t0 = time.perf_counter()
     try:
         desc, sc, cam, prm = load_workload(name)
-        ctx.upload_scene(sc, rtb200.BVH_LBVH_DEVICE if name == "c5" else rtb200.BVH_SAH_HOST)
+        ctx.upload_scene(sc, rtb200.BVH_PLOC_DEVICE)
         del sc
         target = None
         if mg:
@@ -714,7 +722,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--bvh", default="sah", choices=["sah", "lbvh"])
+    ap.add_argument("--bvh", default="ploc", choices=["ploc", "sah", "lbvh"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the side measurements of C1 / C2 / C4 (one GPU) and C5 (eight GPUs)")
     args = ap.parse_args()

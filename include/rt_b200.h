@@ -100,7 +100,9 @@ typedef struct {
 
 #define RT_BVH_LBVH_DEVICE 0      /* Morton codes -> radix sort -> Karras hierarchy -> refit, all on the GPU */
 #define RT_BVH_SAH_HOST 1         /* binned SAH built by the host and uploaded                               */
-#define RT_BVH_AUTO 2             /* SAH_HOST up to 2^22 triangles, LBVH_DEVICE beyond                        */
+#define RT_BVH_AUTO 2             /* PLOC_DEVICE                                                              */
+#define RT_BVH_PLOC_DEVICE 3      /* Morton order -> parallel locally-ordered clustering (nearest neighbours by merged
+                                     surface area) -> leaf collapse, all on the GPU: SAH quality at device speed      */
 
 /* ---- lifetime ---- */
 int rt_create(int device, rt_ctx** out);

@@ -1336,8 +1336,8 @@ int rt_build_bvh(rt_ctx* ctx, int mode)
         CK(ctx->d_n2.ensure(n));
     }
     const int* perm = nullptr;
-    if (mode == RT_BVH_AUTO) // the host SAH tree traces ~15 % faster but takes ~0.6 us per triangle to build
-        mode = ctx->n_tris <= (1ll << 22) ? RT_BVH_SAH_HOST : RT_BVH_LBVH_DEVICE;
+    if (mode == RT_BVH_AUTO)
+        mode = RT_BVH_PLOC_DEVICE;
     if (mode == RT_BVH_SAH_HOST) {
         HostBvh h = build_bvh_sah_host(ctx->h_pos.data(), ctx->n_tris, pad);
         if (h.depth >= kStackDepth)
@@ -1352,7 +1352,7 @@ int rt_build_bvh(rt_ctx* ctx, int mode)
         ctx->root_entry = h.root_entry;
         ctx->bvh_depth = h.depth;
         perm = ctx->d_perm.p;
-    } else if (mode == RT_BVH_LBVH_DEVICE) {
+    } else if (mode == RT_BVH_LBVH_DEVICE || mode == RT_BVH_PLOC_DEVICE) {
         if (ctx->lbvh_nodes)
             cudaFree(ctx->lbvh_nodes);
         if (ctx->lbvh_perm)
@@ -1361,7 +1361,19 @@ int rt_build_bvh(rt_ctx* ctx, int mode)
         ctx->lbvh_perm = nullptr;
         DeviceBvh d;
         const char* err = nullptr;
-        if (build_bvh_lbvh_device(ctx->stream, ctx->d_pos.p, ctx->n_tris, pad, &d, &err) != 0)
+        int built = 2;
+        if (mode == RT_BVH_PLOC_DEVICE) {
+            built = build_bvh_ploc_device(ctx->stream, ctx->d_pos.p, ctx->n_tris, pad, &d, &err);
+            if (built == 1)
+                return fail(RT_ERR_CUDA, std::string("rt_build_bvh (PLOC): ") + (err ? err : "failed"));
+            if (built == 0 && d.depth >= kStackDepth) { // agglomeration does not bound the depth; the Morton hierarchy does (64-bit keys)
+                cudaFree(d.nodes);
+                cudaFree(d.perm);
+                d = DeviceBvh();
+                built = 2;
+            }
+        }
+        if (built == 2 && build_bvh_lbvh_device(ctx->stream, ctx->d_pos.p, ctx->n_tris, pad, &d, &err) != 0)
             return fail(RT_ERR_CUDA, std::string("rt_build_bvh (LBVH): ") + (err ? err : "failed"));
         if (d.depth >= kStackDepth) {
             cudaFree(d.nodes);

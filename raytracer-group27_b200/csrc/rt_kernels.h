@@ -51,6 +51,10 @@ struct DeviceBvh {
     int depth = 0;
 };
 int build_bvh_lbvh_device(cudaStream_t st, const float* d_pos, long long n_tris, float pad, DeviceBvh* out, const char** err);
+// Device builder of SAH quality (rt_ploc.cu): Morton order -> parallel locally-ordered clustering (mutual nearest neighbours by
+// merged surface area) -> depth-first leaf order -> leaf collapse.  Same outputs.  Returns 2 for scenes of at most 4 triangles
+// (use the LBVH path, which emits the single leaf).
+int build_bvh_ploc_device(cudaStream_t st, const float* d_pos, long long n_tris, float pad, DeviceBvh* out, const char** err);
 
 // Screen post-processing (rt_post.cu): float4 images in the Screen layout.  option / gauss follow rt_b200.h's RT_FILTER_* / RT_KERNEL_*.
 void launch_post_light(cudaStream_t st, int sm_count, const float4* img, float4* light, size_t n);

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RTB200_LIB") or os.path.join(os.path.dirname(_HERE), "librtb200.so")  # override: kernel-variant experiments
 
 RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_OVERFLOW, RT_ERR_IO = 0, 1, 2, 3, 4
-BVH_LBVH_DEVICE, BVH_SAH_HOST, BVH_AUTO = 0, 1, 2
+BVH_LBVH_DEVICE, BVH_SAH_HOST, BVH_AUTO, BVH_PLOC_DEVICE = 0, 1, 2, 3
 
 
 class RtError(RuntimeError):

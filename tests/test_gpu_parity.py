@@ -40,12 +40,12 @@ def _check_against_golden(g, rgb, ids, t, st, what, by_id=False):
 
 
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
-@pytest.mark.parametrize("bvh", ["lbvh", "sah"])
+@pytest.mark.parametrize("bvh", ["ploc", "lbvh", "sah"])
 def test_golden(rtb, gpu_ctx, name, bvh):
     g = Golden(name)
     if not g.geometry_ok:
         pytest.skip("stand-in geometry differs on this host's numpy; covered by test_dragon_live_oracle")
-    gpu_ctx.upload_scene(g.scene, rtb.BVH_LBVH_DEVICE if bvh == "lbvh" else rtb.BVH_SAH_HOST)
+    gpu_ctx.upload_scene(g.scene, {"ploc": rtb.BVH_PLOC_DEVICE, "lbvh": rtb.BVH_LBVH_DEVICE, "sah": rtb.BVH_SAH_HOST}[bvh])
     gpu_ctx.set_texturing(**g.tex) if g.tex else gpu_ctx.set_texturing(None)
     try:
         rgb, ids, t, st = gpu_ctx.render(g.camera(), g.params(), want_ids=True)
@@ -71,7 +71,7 @@ def test_tie_order_without_bvh(rtb, gpu_ctx):
     g = Golden("zfight_96")
     o_rgb, o_ids, o_t, o_st = g.oracle_render("port", use_bvh=False, shadow_exhaustive=True)
     assert np.array_equal(o_ids, g.ids) and (o_ids != g.ids_x).sum() > 500
-    for mode in (rtb.BVH_SAH_HOST, rtb.BVH_LBVH_DEVICE):
+    for mode in (rtb.BVH_PLOC_DEVICE, rtb.BVH_SAH_HOST, rtb.BVH_LBVH_DEVICE):
         gpu_ctx.upload_scene(g.scene, mode)
         for exhaustive in (False, True):
             rgb, ids, t, st = gpu_ctx.render(g.camera(), g.params(exhaustive=exhaustive, use_bvh=False), want_ids=True)
@@ -99,7 +99,7 @@ def test_glossy_rays_match_the_port(rtb, gpu_ctx, glossy, sample_mode, size):
     plain = o.render(s.pos, s.nrm, s.mesh_id, s.mats, s.point_lights, None, g.camera(), w, h, max_level=2, sample_mode=sample_mode, sample_size=16,
                      shadow_exhaustive=True)
     assert want[3].secondary_rays > 1.2 * plain[3].secondary_rays and np.abs(want[0] - plain[0]).max() > 0.01   # the glossy rays are there
-    for mode in (rtb.BVH_SAH_HOST, rtb.BVH_LBVH_DEVICE):
+    for mode in (rtb.BVH_PLOC_DEVICE, rtb.BVH_SAH_HOST, rtb.BVH_LBVH_DEVICE):
         gpu_ctx.upload_scene(s, mode)
         rgb, ids, t, st = gpu_ctx.render(g.camera(), rtb.make_params(w, h, 2, sample_mode=sample_mode, sample_size=16, glossy_rays=glossy), want_ids=True)
         assert np.array_equal(ids, want[1]) and bits_equal(t, want[2])
@@ -116,7 +116,7 @@ def test_dragon_live_oracle(rtb, gpu_ctx):
     w, h = 96, 54
     o = oracle.Oracle("port")
     o_rgb, o_ids, o_t, o_st = o.render(sc.pos, sc.nrm, sc.mesh_id, sc.mats, sc.point_lights, None, cam, w, h, max_level=3, shadow_exhaustive=True)
-    for mode in (rtb.BVH_LBVH_DEVICE, rtb.BVH_SAH_HOST):
+    for mode in (rtb.BVH_PLOC_DEVICE, rtb.BVH_LBVH_DEVICE, rtb.BVH_SAH_HOST):
         gpu_ctx.upload_scene(sc, mode)
         rgb, ids, t, st = gpu_ctx.render(cam, rtb.make_params(w, h, 3), want_ids=True)
         assert np.array_equal(ids, o_ids)
@@ -143,7 +143,7 @@ def test_intersect_matches_oracle(rtb, gpu_ctx):
         rays = np.concatenate([o, dirs], 1).astype(np.float32)
         o_ids, o_t = oracle.Oracle("port").closest_hit(g.scene.pos, g.scene.nrm, g.scene.mesh_id, rays, use_bvh=False)
         assert (o_ids >= 0).sum() > 1000
-        for mode in (rtb.BVH_LBVH_DEVICE, rtb.BVH_SAH_HOST):
+        for mode in (rtb.BVH_PLOC_DEVICE, rtb.BVH_LBVH_DEVICE, rtb.BVH_SAH_HOST):
             gpu_ctx.upload_scene(g.scene, mode)
             for use_bvh in bvh_modes:
                 ids, t = gpu_ctx.intersect(rays, use_bvh)
@@ -176,7 +176,7 @@ def test_axis_parallel_and_in_plane_rays(rtb, gpu_ctx):
         for use_bvh, order in ((True, 2), (False, 0)):
             o_ids, o_t = oracle.Oracle("port").closest_hit(g.scene.pos, g.scene.nrm, g.scene.mesh_id, rays, use_bvh=order)
             assert (o_ids >= 0).sum() > 100
-            for mode in (rtb.BVH_LBVH_DEVICE, rtb.BVH_SAH_HOST):
+            for mode in (rtb.BVH_PLOC_DEVICE, rtb.BVH_LBVH_DEVICE, rtb.BVH_SAH_HOST):
                 gpu_ctx.upload_scene(g.scene, mode)
                 ids, t = gpu_ctx.intersect(rays, use_bvh)
                 assert np.array_equal(ids, o_ids), f"{name} mode {mode} bvh {use_bvh}: {(ids != o_ids).sum()} of {len(ids)} ids differ"
@@ -194,7 +194,7 @@ def test_far_and_near_cameras(rtb, gpu_ctx):
         cam = rtb.make_camera(dist=dist, fovy_deg=fov, euler_deg=(35.0, -50.0, 0.0))
         o_rgb, o_ids, o_t, o_st = o.render(s.pos, s.nrm, s.mesh_id, s.mats, s.point_lights, None, cam, 160, 120, max_level=2, shadow_exhaustive=True)
         assert (o_ids >= 0).mean() > 0.05
-        for mode in (rtb.BVH_LBVH_DEVICE, rtb.BVH_SAH_HOST):
+        for mode in (rtb.BVH_PLOC_DEVICE, rtb.BVH_LBVH_DEVICE, rtb.BVH_SAH_HOST):
             gpu_ctx.upload_scene(s, mode)
             rgb, ids, t, st = gpu_ctx.render(cam, rtb.make_params(160, 120, 2), want_ids=True)
             assert np.array_equal(ids, o_ids), f"dist {dist}: {(ids != o_ids).sum()} ids differ"
@@ -359,21 +359,22 @@ def test_errors_are_loud(rtb, gpu_ctx):
 
 
 def test_full_size_two_bvhs_agree_c3(rtb, gpu_ctx):
-    """C3 at BASELINE size (3840x2160, depth 3) on the dragon stand-in: two unrelated hierarchies (device LBVH, host SAH)
+    """C3 at BASELINE size (3840x2160, depth 3) on the dragon stand-in: three unrelated hierarchies (device PLOC + SAH, device LBVH, host SAH)
     must produce the same frame — closest-hit ids and t bit for bit, identical ray counts, colour to accumulation
     round-off.  Any box test that culled a triangle the exact test accepts would show up as a difference."""
     from rtb200 import standin
     sc = standin.dragon_standin_scene()
     cam, prm = rtb.make_camera(), rtb.make_params(3840, 2160, 3)
     out = []
-    for mode in (rtb.BVH_LBVH_DEVICE, rtb.BVH_SAH_HOST):
+    for mode in (rtb.BVH_PLOC_DEVICE, rtb.BVH_LBVH_DEVICE, rtb.BVH_SAH_HOST):
         gpu_ctx.upload_scene(sc, mode)
         out.append(gpu_ctx.render(cam, prm, want_ids=True))
-    (a_rgb, a_ids, a_t, a_st), (b_rgb, b_ids, b_t, b_st) = out
-    assert np.array_equal(a_ids, b_ids) and bits_equal(a_t, b_t)
-    assert (a_st.primary_rays, a_st.shadow_queries, a_st.secondary_rays) == (b_st.primary_rays, b_st.shadow_queries, b_st.secondary_rays)
+    a_rgb, a_ids, a_t, a_st = out[0]
+    for b_rgb, b_ids, b_t, b_st in out[1:]:
+        assert np.array_equal(a_ids, b_ids) and bits_equal(a_t, b_t)
+        assert (a_st.primary_rays, a_st.shadow_queries, a_st.secondary_rays) == (b_st.primary_rays, b_st.shadow_queries, b_st.secondary_rays)
+        assert np.abs(a_rgb - b_rgb).max() <= 1e-6
     assert a_st.primary_rays == 3840 * 2160
-    assert np.abs(a_rgb - b_rgb).max() <= 1e-6
     assert (a_ids >= 0).mean() > 0.1
     # strided agreement with the golden minted at 160x90 (every 24th pixel corner coincides)
     g = Golden("dragon_standin_c3_160x90")
@@ -416,7 +417,7 @@ def test_c5_lattice_small(rtb, gpu_ctx):
     o_rgb, o_ids, o_t, o_st = o.render(sc.pos, sc.nrm, sc.mesh_id, sc.mats, sc.point_lights, None, cam, w, h, max_level=3, sample_mode=2, sample_size=16,
                                        shadow_exhaustive=True)
     assert o_st.primary_rays == w * h * 16 and (o_ids >= 0).mean() > 0.03 and o_st.secondary_rays > 1000
-    for mode in (rtb.BVH_LBVH_DEVICE, rtb.BVH_SAH_HOST):
+    for mode in (rtb.BVH_PLOC_DEVICE, rtb.BVH_LBVH_DEVICE, rtb.BVH_SAH_HOST):
         gpu_ctx.upload_scene(sc, mode)
         rgb, ids, t, st = gpu_ctx.render(cam, rtb.make_params(w, h, 3, sample_mode=2, sample_size=16), want_ids=True)
         assert np.array_equal(ids, o_ids) and bits_equal(t, o_t)
@@ -425,13 +426,13 @@ def test_c5_lattice_small(rtb, gpu_ctx):
 
 
 def test_c5_lattice_full_mesh_subset_equals_exhaustive(rtb, gpu_ctx):
-    """C5's own mesh — the 8x8x8 lattice, 44.5 M triangles, device LBVH — at a size the exhaustive search can afford: a 32x18 frame with
+    """C5's own mesh — the 8x8x8 lattice, 44.5 M triangles, the default device builder (PLOC + SAH, rt_ploc.cu) — at a size the exhaustive search can afford: a 32x18 frame with
     16 samples per pixel, depth 1.  The BVH frame must equal the exhaustive frame (every object tested for every ray) in ids, t, ray
     counts and colour; a box of the 44.5 M-triangle tree that culled a triangle the exact test accepts would show up here."""
     from rtb200 import standin
     sc = standin.dragon_lattice_scene(8)
     assert sc.n_tris == 512 * 86880
-    gpu_ctx.upload_scene(sc, rtb.BVH_LBVH_DEVICE)
+    gpu_ctx.upload_scene(sc, rtb.BVH_PLOC_DEVICE)
     del sc
     cam = rtb.make_camera()
     a = gpu_ctx.render(cam, rtb.make_params(32, 18, 1, sample_mode=2, sample_size=16), want_ids=True)
@@ -449,13 +450,14 @@ def test_full_size_c4_soft_shadow_sums(rtb, gpu_ctx):
     g = Golden("cornell_c4_96")
     cam, prm = g.camera(), rtb.make_params(2048, 2048, 5, sphere_rays=64)
     out = []
-    for mode in (rtb.BVH_LBVH_DEVICE, rtb.BVH_SAH_HOST):
+    for mode in (rtb.BVH_PLOC_DEVICE, rtb.BVH_LBVH_DEVICE, rtb.BVH_SAH_HOST):
         gpu_ctx.upload_scene(g.scene, mode)
         out.append(gpu_ctx.render(cam, prm, want_ids=True))
-    a, b = out
-    assert np.array_equal(a[1], b[1]) and bits_equal(a[2], b[2])
-    assert np.abs(a[0] - b[0]).max() <= 2e-6
-    assert a[3].rays == b[3].rays
+    a = out[0]
+    for b in out[1:]:
+        assert np.array_equal(a[1], b[1]) and bits_equal(a[2], b[2])
+        assert np.abs(a[0] - b[0]).max() <= 2e-6
+        assert a[3].rays == b[3].rays
     hits = int((a[1] >= 0).sum()) + int(a[3].secondary_rays)  # an upper bound of shaded hits: primary hits + all children
     assert a[3].shadow_queries >= 64 * int((a[1] >= 0).sum())
     assert a[3].shadow_queries <= 64 * hits * 3

@@ -26,7 +26,7 @@ def main():
     ctx = rtb200.Context(0)
     cam = rtb200.make_camera()
     out = [os.path.basename(os.environ.get("RTB200_LIB", "default"))]
-    bvh = rtb200.BVH_LBVH_DEVICE if os.environ.get("AB_BVH") == "lbvh" else rtb200.BVH_SAH_HOST
+    bvh = {"lbvh": rtb200.BVH_LBVH_DEVICE, "ploc": rtb200.BVH_PLOC_DEVICE}.get(os.environ.get("AB_BVH"), rtb200.BVH_SAH_HOST)
     if "c3" in which:
         ctx.upload_scene(standin.dragon_standin_scene(), bvh)
         prm = rtb200.make_params(3840, 2160, 3)
