@@ -150,6 +150,7 @@ struct rt_ctx {
     DevBuf<float> prim_t, out_t, rgb;
     DevBuf<unsigned char> row_flags;    // per 32-pixel tile row: some camera ray hit (k_row_flags)
     double store_gbs = 0.0;             // rate the paced background stores hold: 85 % of the measured device-to-host copy rate
+    int paths_mode = -1;                // rt_set_paths: -1 automatic, 0 never, 1 whenever legal
     double queue_scale = 1.0;           // RTB200_QUEUE_SCALE (tests): shrinks the queues' head-room to provoke the overflow path
     unsigned headroom_shift = 0;        // doublings of the head-room asked for by the overflow retry of rt_render / rt_render_shard
     double shared_store_gbs = 0.0;      // rt_set_host_store_rate: what this rank's link carries while every rank of the job stores into host memory
@@ -668,6 +669,7 @@ struct HostTarget {
 // Enqueue one frame.  `out`: float4 framebuffer (Screen layout), maybe on a peer GPU.  The frame starts and ends on the
 // context's stream; in between, its batches run on the lanes' own streams.
 constexpr int kBandGridMult = 4;
+constexpr long long kPathsMaxPrimaryRays = 3 << 19; // batches of up to 1.5 M primary rays trace their bounce levels as whole paths
 
 int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_ids, unsigned batch_rays, const HostTarget* host)
 {
@@ -738,6 +740,27 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
         }
         plan.swap(outer);
     }
+    // Bounce levels as whole paths (k_paths) instead of per-level kernels: legal when a path never splits and a shadow query never
+    // continues (every material opaque, glossy_ray_count 1), all lights are point-like and no texture is sampled; worth it when the
+    // batch is small — the per-level kernels of a small wavefront each wait for their longest ray (rt_kernels.cu).  Measured on C3
+    // (tools/ab_probe.py, one rank's share of the 4K frame, per-level kernels -> paths): 1/8 0.750 -> 0.707 ms, 1/64 0.475 -> 0.421 ms; 1/4 1.04 -> 1.16 ms,
+    // whole frame 2.04 -> 2.54 ms.  rt_set_paths / RTB200_PATHS=0 / 1: never / whenever legal.
+    static const int paths_env_default = [] {
+        const char* e = std::getenv("RTB200_PATHS");
+        return e ? std::atoi(e) : -1;
+    }();
+    const int paths_env = ctx->paths_mode >= 0 ? ctx->paths_mode : paths_env_default;
+    static const long long paths_max_rays = [] {
+        const char* e = std::getenv("RTB200_PATHS_MAX_RAYS");
+        return e ? std::atoll(e) : (long long)kPathsMaxPrimaryRays;
+    }();
+    const bool paths_legal = ctx->overlap && fp.max_level >= 1 && !fp.any_transparent && fp.glossy == 1 && fp.n_sphere == 0 && fp.n_plane == 0 && !fp.tex_on
+        && !fp.tex_debug && !fp.exhaustive;
+    static const int paths_from = [] {
+        const char* e = std::getenv("RTB200_PATHS_FROM");
+        return e ? std::max(1, std::atoi(e)) : 1;
+    }();
+    const bool use_paths = paths_legal && paths_env != 0 && (paths_env == 1 || (long long)batch_pixels * fp.spp <= paths_max_rays);
     const size_t n_batches = plan.size();
     const int n_lanes = (int)std::min<size_t>(lanes_wanted, std::max<size_t>(n_batches, 1));
 
@@ -805,6 +828,21 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
         n_primary *= (unsigned long long)fp.spp;
         traced_primary += n_traced * (unsigned long long)fp.spp;
         for (int level = 0; level <= fp.max_level; level++) {
+            if (level == paths_from && use_paths) {
+                // small wavefront of an opaque scene lit by point-like lights: the remaining levels as whole paths, one launch
+                // (k_paths), next to the shadow queries of the level before on the side stream
+                if (ctx->overlap && level >= 2)
+                    CK(cudaStreamWaitEvent(st, ln.ev_shadow[level & 1], 0));
+                launch_level_reset(st, b.counters, (level & 1) ^ 1, -1, 0, level & 1);
+                {
+                    StageScope sc(ctx, RT_STAGE_EXTEND, st);
+                    SceneDev s_ext = s;
+                    s_ext.tie_by_id = fp.tie_by_id; // for the closest-hit queries; the any-hit shadow queries do not look at tie keys
+                    launch_paths(st, ctx->sm_count, s_ext, ctx->root_entry, fp, b, level & 1, level, ctx->counters_enabled);
+                }
+                launches += 2;
+                break;
+            }
             const int qi = level & 1, par = level & 1;
             set_parity(ln, b, par);
             // the shadow queues of this parity were last read by the shadow kernels of level - 2
@@ -1193,6 +1231,14 @@ int rt_stage_times(rt_ctx* ctx, float* ms, int* launches)
         ms[k] = ctx->stage_ms[k];
         launches[k] = ctx->stage_launches[k];
     }
+    return RT_OK;
+}
+
+int rt_set_paths(rt_ctx* ctx, int mode)
+{
+    if (!ctx || mode < -1 || mode > 1)
+        return fail(RT_ERR_INVALID, "rt_set_paths: mode must be -1 (automatic), 0 (never) or 1 (whenever legal)");
+    ctx->paths_mode = mode;
     return RT_OK;
 }
 

@@ -461,6 +461,34 @@ __device__ __forceinline__ float path_uniform(unsigned path, unsigned child, uns
     return (float)(path_mix(path_mix(path_mix(path, child), attempt), j) >> 8) * (1.0f / 16777216.0f);
 }
 
+// A point-like light (point or spot, getPointLights / getSpotLichts, src/shadow.cpp:106-131, 229-252) seen from a hit.
+// light_reaches: false for a spot light whose cone does not contain the hit.  light_terms: the coefficients of calcColor
+// (src/main.cpp:112-121) folded with the path throughput w: the light adds A * intensity + B when it is visible.
+__device__ __forceinline__ bool light_reaches(const SceneDev& s, int li, const f3& p)
+{
+    const float4 L0 = __ldg(s.point_lights + 3 * li);
+    if (L0.w == 0.0f)
+        return true;
+    const float4 L1 = __ldg(s.point_lights + 3 * li + 1); // spot: dot(normalize(direction), normalize(p - position)) > cos(radians(angle))
+    const f3 sd = mk3(__ldg(s.point_lights + 3 * li + 2));
+    return xdot(xnormalize(sd), xnormalize(xsub(p, mk3(L0)))) > L1.w;
+}
+
+__device__ __forceinline__ void light_terms(const SceneDev& s, int li, const f3& p, const f3& Nn, const f3& reflN, const f3& w, const f3& kd, const f3& ks,
+    float shininess, f3& A, f3& B)
+{
+    const f3 lp = mk3(__ldg(s.point_lights + 3 * li)), lc = mk3(__ldg(s.point_lights + 3 * li + 1));
+    const f3 ldir = xnormalize(xsub(lp, p));
+    const float cosNL = fabsf(xdot(Nn, ldir));                 // shadow.cpp:125 / 245
+    const float cosRL = fmaxf(0.0f, xdot(reflN, ldir));         // shadow.cpp:126 / 246
+    A = mk3(w.x * kd.x * lc.x * cosNL, w.y * kd.y * lc.y * cosNL, w.z * kd.z * lc.z * cosNL);
+    B = mk3(0, 0, 0);
+    if (shininess > 0.0f) {
+        const float sp = powf(cosRL, shininess);
+        B = mk3(w.x * lc.x * ks.x * sp, w.y * lc.y * ks.y * sp, w.z * lc.z * ks.z * sp);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // K3 shade: getFinalColor without the recursion (src/main.cpp:129-190), light set-up of getPointLights /
 // getSpherelights (src/shadow.cpp:106-131, 139-226: everything except the cansee calls), calcColor
@@ -669,13 +697,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
         // record per light, for a spot light only if the hit lies inside its cone; the shadow kernel adds
         // A * intensity + B when the light is visible (calcColor, main.cpp:112-121).
         for (int li = 0; li < fp.n_point; li++) {
-            const float4 L0 = __ldg(s.point_lights + 3 * li), L1 = __ldg(s.point_lights + 3 * li + 1);
-            const f3 lp = mk3(L0), lc = mk3(L1);
-            bool lit = hit;
-            if (hit && L0.w != 0.0f) { // spot: dot(normalize(direction), normalize(p - position)) > cos(radians(angle))
-                const f3 sd = mk3(__ldg(s.point_lights + 3 * li + 2));
-                lit = xdot(xnormalize(sd), xnormalize(xsub(sh.p, lp))) > L1.w;
-            }
+            const bool lit = hit && light_reaches(s, li, sh.p);
             unsigned* const cl[1] = { &b.counters->sh[b.par].n_pt };
             const bool wl[1] = { lit };
             const unsigned capl[1] = { b.shadow_pt_capacity };
@@ -683,15 +705,8 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
             block_alloc<1>(cl, wl, capl, &b.counters->overflow, sl1, smem);
             if (sl1[0] == 0xffffffffu)
                 continue;
-            const f3 ldir = xnormalize(xsub(lp, sh.p));
-            const float cosNL = fabsf(xdot(Nn, ldir));                 // shadow.cpp:125 / 245
-            const float cosRL = fmaxf(0.0f, xdot(reflN, ldir));         // shadow.cpp:126 / 246
-            const f3 A = mk3(w.x * kd.x * lc.x * cosNL, w.y * kd.y * lc.y * cosNL, w.z * kd.z * lc.z * cosNL);
-            f3 B = mk3(0, 0, 0);
-            if (shininess > 0.0f) {
-                const float sp = powf(cosRL, shininess);
-                B = mk3(w.x * lc.x * ks.x * sp, w.y * lc.y * ks.y * sp, w.z * lc.z * ks.z * sp);
-            }
+            f3 A, B;
+            light_terms(s, li, sh.p, Nn, reflN, w, kd, ks, shininess, A, B);
             b.sq_point.p_pix[sl1[0]] = make_float4(sh.p.x, sh.p.y, sh.p.z, __int_as_float(pix));
             b.sq_point.a_light[sl1[0]] = make_float4(A.x, A.y, A.z, __int_as_float(li));
             b.sq_point.b[sl1[0]] = make_float4(B.x, B.y, B.z, 0.0f);
@@ -863,6 +878,117 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_shadow_
             const float4 bb = b.sq_point.b[i];
             accumulate(b.accum, __float_as_int(pp.w), al.x * intensity + bb.x, al.y * intensity + bb.y, al.z * intensity + bb.z);
         });
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2-4 fused, for the bounce levels of SMALL wavefronts: one lane follows one path from its level-`first_level` ray to the
+// end — closest hit (BoundingVolumeHierarchy::intersect), the hit's shading terms (getFinalColor, main.cpp:129-190), one
+// any-hit shadow query per point-like light (getPointLights / getSpotLichts with cansee, shadow.cpp:32-69, 106-131, 229-252),
+// then the mirror ray (main.cpp:191-203) — instead of one kernel per level and ray kind.  A level's kernel cannot end before its
+// longest ray has (a chain of ~200 dependent node fetches at L2 latency: 50-100 us however few rays there are), and the
+// per-level form pays that once per level and ray kind: 8 times for depth 3.  Here the longest PATH counts once.  For
+// wavefronts that fill the machine the per-level kernels are faster (coherent batches, all lanes in the same phase), so
+// enqueue_frame picks this kernel for small batches only (one GPU's share of a frame split over several).  Conditions (host):
+// every material opaque, glossy_ray_count 1, no spherical / plane lights, no textures — a path then never splits and a shadow
+// query never continues.  Queries of both kinds share the engine (kAnyHitPerQuery); the path state lives in shared memory.
+struct PathState {
+    float p[3], Nn[3], reflN[3], refl[3], w[3], kd[3], ks[3];
+    float shininess;
+    int pix, level, li;   // li: light of the shadow query in flight; -1: the closest-hit query is
+};
+
+constexpr int kPathBlocksPerSm = 4; // 128 registers: no spills; this kernel runs where latency, not occupancy, sets the time
+template <bool COUNT>
+__global__ void __launch_bounds__(RT_TRACE_BLOCK, kPathBlocksPerSm) k_paths(SceneDev s, int root_entry, FrameParams fp, BatchDev b, int qi, int first_level)
+{
+    __shared__ PathState ps_all[RT_TRACE_BLOCK];
+    if (batch_overflowed(b))
+        return;
+    PathState& ps = ps_all[threadIdx.x];
+    const unsigned n = min(b.counters->n_rays[qi], b.ray_capacity);
+    TraceStats st;
+    unsigned queries = 0, n_secondary = 0;
+    auto ld3 = [](const float* a) { return mk3(a[0], a[1], a[2]); };
+    auto st3 = [](float* a, const f3& v) { a[0] = v.x; a[1] = v.y; a[2] = v.z; };
+    // After the closest hit has been shaded, or a shadow query answered: the next shadow query of the hit, else the mirror ray, else the end.
+    auto next_query = [&](f3& o, f3& d, HitRec& q) -> bool {
+        const f3 p = ld3(ps.p);
+        for (int li = ps.li + 1; li < fp.n_point; li++) {
+            if (!light_reaches(s, li, p))
+                continue;
+            CanSee cs;
+            if (!cansee_begin(cs, p, mk3(__ldg(&s.point_lights[3 * li])))) { // the light sits on the hit: visible without a query (shadow.cpp:41,67)
+                f3 A, B;
+                light_terms(s, li, p, ld3(ps.Nn), ld3(ps.reflN), ld3(ps.w), ld3(ps.kd), ld3(ps.ks), ps.shininess, A, B);
+                accumulate(b.accum, ps.pix, A.x + B.x, A.y + B.y, A.z + B.z);
+                continue;
+            }
+            queries++;
+            ps.li = li;
+            o = cs.o;
+            d = cs.d;
+            q = cansee_query(cs);
+            return true;
+        }
+        const f3 ks = ld3(ps.ks);
+        if (ps.level < fp.max_level && (ks.x > 0.0f || ks.y > 0.0f || ks.z > 0.0f)) { // main.cpp:187, 194: the mirror ray, weight ks * ks
+            const f3 w = ld3(ps.w), refl = ld3(ps.refl);
+            st3(ps.w, mk3(w.x * ks.x * ks.x, w.y * ks.y * ks.y, w.z * ks.z * ks.z));
+            ps.level++;
+            ps.li = -1;
+            n_secondary++;
+            o = xadd(p, xmul(refl, 0.01f)); // main.cpp:199
+            d = refl;
+            q = fresh_query();
+            return true;
+        }
+        return false;
+    };
+    trace_queue<kAnyHitPerQuery, COUNT>(
+        s, root_entry, false, &b.counters->work[0], n, st,
+        [&](unsigned item, f3& o, f3& d, HitRec& q) {
+            const float4 op = b.q[qi].o_pix[item];
+            o = mk3(op);
+            d = mk3(b.q[qi].d[item]);
+            st3(ps.w, mk3(b.q[qi].w[item]));
+            ps.pix = __float_as_int(op.w) >> 1;
+            ps.level = first_level;
+            ps.li = -1;
+            q = fresh_query();
+            return true;
+        },
+        [&](unsigned, const HitRec& best, f3& o, f3& d, HitRec& q) {
+            if (ps.li >= 0) { // a shadow query came back
+                if (best.ti == -1) {
+                    f3 A, B;
+                    light_terms(s, ps.li, ld3(ps.p), ld3(ps.Nn), ld3(ps.reflN), ld3(ps.w), ld3(ps.kd), ld3(ps.ks), ps.shininess, A, B);
+                    accumulate(b.accum, ps.pix, A.x * 1.0f + B.x, A.y * 1.0f + B.y, A.z * 1.0f + B.z);
+                }
+                return next_query(o, d, q);
+            }
+            if (best.ti == -1) // the ray left the scene: black (main.cpp:295-301)
+                return false;
+            const Shading sh = shading_at(s, best.ti, o, d, best.t);
+            const f3 dn = xnormalize(d), Nn = xnormalize(sh.N), refl = xreflect(dn, Nn); // main.cpp:141
+            st3(ps.p, sh.p);
+            st3(ps.Nn, Nn);
+            st3(ps.refl, refl);
+            st3(ps.reflN, xnormalize(refl));
+            st3(ps.kd, mk3(sh.m0));
+            st3(ps.ks, mk3(sh.m1));
+            ps.shininess = sh.m0.w;
+            return next_query(o, d, q);
+        },
+        RT_MAX_QUOTA, max(fp.min_quota, 1));
+    warp_add_u64(&b.counters->shadow_queries, queries);
+    warp_add_u64(&b.counters->secondary_rays, n_secondary);
+    if (COUNT) {
+        warp_add_u64(&b.counters->node_visits, st.nodes);
+        warp_add_u64(&b.counters->tri_tests, st.tris);
+        warp_add_u64(&b.counters->tri_tests_full, st.tris_full);
+        atomicMax(&b.counters->max_ray_nodes, st.max_ray_nodes);
+        atomicMax(&b.counters->max_ray_tris, st.max_ray_tris);
+    }
 }
 
 // K4b spherical lights (getSpherelights, src/shadow.cpp:139-226).  Work item = (record, sample): sample 0 is the
@@ -1322,6 +1448,15 @@ void launch_shadow_point(cudaStream_t st, int sm_count, const SceneDev& s, int r
         k_shadow_point<false, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b);
     else
         k_shadow_point<false, false><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b);
+}
+
+void launch_paths(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, int qi, int first_level, bool count)
+{
+    const int grid = sm_count * kPathBlocksPerSm;
+    if (count)
+        k_paths<true><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b, qi, first_level);
+    else
+        k_paths<false><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b, qi, first_level);
 }
 
 void launch_shadow_sphere(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count)

@@ -14,6 +14,8 @@ void launch_extend(cudaStream_t st, int sm_count, const SceneDev& s, int root_en
     int level, unsigned first_lp, bool count);
 void launch_shade(cudaStream_t st, int sm_count, const SceneDev& s, const FrameParams& fp, const BatchDev& b, int qi, int level, unsigned first_lp);
 void launch_shadow_point(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count);
+// Bounce levels >= first_level of the rays in queue qi as whole paths (k_paths): small wavefronts of opaque scenes with point-like lights only.
+void launch_paths(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, int qi, int first_level, bool count);
 void launch_shadow_sphere(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count);
 void launch_shadow_plane(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count);
 void launch_resolve(cudaStream_t st, int sm_count, const FrameParams& fp, unsigned first_lp, unsigned n_lp, const float4* accum,

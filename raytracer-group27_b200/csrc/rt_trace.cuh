@@ -146,14 +146,14 @@ __device__ __forceinline__ int global_id(const SceneDev& s, const HitRec& best)
 }
 
 // Exhaustive search: every object (order irrelevant thanks to the tie rule).
-template <bool ANYHIT, bool COUNT>
+template <int ANYHIT, bool COUNT>
 __device__ __forceinline__ void trace_exhaustive(const SceneDev& s, const f3& o, const f3& d, HitRec& best, TraceStats& st)
 {
     const f3 dn = xnormalize(d);
-    if (test_spheres(s, o, d, best) && ANYHIT)
+    if (test_spheres(s, o, d, best) && ANYHIT == 1)
         return;
     for (int ti = 0; ti < s.n_tris; ti++) {
-        if (test_triangle<COUNT>(s, ti, o, d, dn, best, st) && ANYHIT)
+        if (test_triangle<COUNT>(s, ti, o, d, dn, best, st) && ANYHIT == 1)
             return;
     }
 }
@@ -163,6 +163,9 @@ __device__ __forceinline__ void trace_exhaustive(const SceneDev& s, const f3& o,
 // < 0 -> ~((first << 3) | (count - 1)), a leaf.  The builders keep the tree depth below kStackDepth (rt_build_bvh
 // fails otherwise), so the per-lane stack cannot overflow.
 constexpr int kTravDone = INT_MIN;      // not a valid leaf encoding (triangle count is limited to 2^28 - 2)
+// ANYHIT template modes of the engine: 0 = closest hit, 1 = any hit (the first blocker found ends the query), 2 = decided per
+// query by what it asks for: a bounded_query() is an any-hit query, a fresh_query() a closest-hit one (k_paths mixes both).
+constexpr int kAnyHitPerQuery = 2;
 #ifndef RT_REFILL_THRESHOLD
 #define RT_REFILL_THRESHOLD 0 // measured on B200: refilling only when the whole warp is done beats mid-traversal refills (profiles/README.md)
 #endif
@@ -183,6 +186,7 @@ struct Trav {
     float tlimit;
     int cur;                // current entry, kTravDone when the traversal is complete
     int sp;
+    bool anyhit;            // engines in kAnyHitPerQuery mode: this query ends with the first blocker
 };
 
 __device__ __forceinline__ void trav_begin(Trav& tv, const f3& o, const f3& d, const HitRec& query, int root_entry)
@@ -208,11 +212,13 @@ __device__ __forceinline__ void trav_begin(Trav& tv, const f3& o, const f3& d, c
 }
 
 // Start a query: the (few) sphere primitives first — their hit bounds the BVH walk, or ends an any-hit query outright.
-template <bool ANYHIT>
+template <int ANYHIT>
 __device__ __forceinline__ void trav_start(const SceneDev& s, Trav& tv, const f3& o, const f3& d, const HitRec& query, int root_entry)
 {
     trav_begin(tv, o, d, query, root_entry);
-    if (s.n_spheres > 0 && test_spheres(s, o, d, tv.best) && ANYHIT)
+    if (ANYHIT == kAnyHitPerQuery)
+        tv.anyhit = query.key == INT_MAX; // bounded_query()
+    if (s.n_spheres > 0 && test_spheres(s, o, d, tv.best) && (ANYHIT == 1 || (ANYHIT == kAnyHitPerQuery && tv.anyhit)))
         tv.cur = kTravDone;
     tv.tlimit = prune_limit(tv.best.t);
 }
@@ -297,7 +303,7 @@ __device__ __forceinline__ int trav_pop(Trav& tv, const TravStack& stack)
 #if RT_BVH_WIDE
 // One node step of the 4-wide tree (rt_wide.cu): fetch the 128-byte node `tv.cur`, slab-test its four boxes, go on with the
 // nearest hit child and push the others, farthest first; or pop.  An any-hit query does not care about the order.
-template <bool ANYHIT, bool COUNT>
+template <int ANYHIT, bool COUNT>
 __device__ __forceinline__ void trav_node_step(const SceneDev& s, Trav& tv, TravStack& stack, TraceStats& st)
 {
     const float4* np = s.nodes + 8 * (size_t)tv.cur;
@@ -355,7 +361,7 @@ __device__ __forceinline__ void trav_node_step(const SceneDev& s, Trav& tv, Trav
 #else
 // One node step: fetch the sibling pair `tv.cur` (one aligned 64-byte read), slab-test both boxes, descend into the
 // nearer hit child and push the other one, or pop.
-template <bool ANYHIT, bool COUNT>
+template <int ANYHIT, bool COUNT>
 __device__ __forceinline__ void trav_node_step(const SceneDev& s, Trav& tv, TravStack& stack, TraceStats& st)
 {
     const float4* np = s.nodes + 2 * (size_t)tv.cur;
@@ -397,7 +403,7 @@ __device__ __forceinline__ void trav_node_step(const SceneDev& s, Trav& tv, Trav
 
 // Test the triangles of leaf entry `leaf`; the walk state (tv.cur, stack) is untouched unless an any-hit query is
 // satisfied, which drops all remaining work.
-template <bool ANYHIT, bool COUNT>
+template <int ANYHIT, bool COUNT>
 __device__ __forceinline__ void trav_leaf_test(const SceneDev& s, Trav& tv, int leaf, TraceStats& st)
 {
     const int enc = ~leaf;
@@ -417,7 +423,7 @@ __device__ __forceinline__ void trav_leaf_test(const SceneDev& s, Trav& tv, int 
 #endif
     if (any) {
         tv.tlimit = prune_limit(tv.best.t);
-        if (ANYHIT) { // the first blocker decides
+        if (ANYHIT == 1 || (ANYHIT == kAnyHitPerQuery && tv.anyhit)) { // the first blocker decides
             tv.cur = kTravDone;
             tv.sp = 0;
         }
@@ -429,11 +435,12 @@ __device__ __forceinline__ void trav_leaf_test(const SceneDev& s, Trav& tv, int 
 // leaf, then tests the leaf's triangles, and repeats; when kRefillThreshold > 0 and fewer lanes than that are still inside
 // the loop, the warp leaves it and the idle lanes pull new items (one atomicAdd per warp per refill).
 // fetch(item, o, d, query) -> false if the item needs no ray;  finish(item, best, o, d, query) -> true to continue the
-// same item with a new segment (shadow rays passing a transparent surface).
+// same item with a new segment (shadow rays passing a transparent surface; the next query of a path, k_paths); o, d hold the
+// finished query's ray on entry.
 // STATIC: no work cursor — warp w takes items [(k * total_warps + w) * 32, + 32) for k = 0, 1, ...; only for queues whose items never
 // continue (finish() returns false), so that a warp refills with all 32 lanes idle.  Level-0 extend uses it: a 4K frame would
 // otherwise issue 260 K same-address atomics, which L2 serialises at about 1 ns each.
-template <bool ANYHIT, bool COUNT, bool STATIC = false, typename Fetch, typename Finish>
+template <int ANYHIT, bool COUNT, bool STATIC = false, typename Fetch, typename Finish>
 __device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, bool exhaustive, unsigned* cursor, unsigned n_items,
     TraceStats& st, Fetch fetch, Finish finish, int max_quota = 32, int min_quota = 1)
 {
@@ -454,6 +461,14 @@ __device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, b
 #define RT_MAX_QUOTA 32
 #endif
     const int quota = STATIC ? 32 : (int)min((unsigned)max_quota, max((unsigned)min_quota, (n_items + total_warps - 1) / total_warps));
+    // RT_LANE_DEPTH > 1: when the queue holds plenty of work a warp claims that many items per lane at once; a lane whose query
+    // ends starts on its next item at once instead of idling until the slowest lane of the warp is done.
+#ifndef RT_LANE_DEPTH
+#define RT_LANE_DEPTH 1
+#endif
+    constexpr int kLaneDepth = STATIC ? 1 : RT_LANE_DEPTH;
+    const bool deep_claims = kLaneDepth > 1 && !exhaustive && n_items >= (unsigned)kLaneDepth * 32u * total_warps;
+    unsigned nxt = 0, nxt_end = 0, nxt_stride = 0; // the lane's next claimed item, end of the warp's claim, distance between a lane's items
     unsigned static_next = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u;
     if (STATIC)
         more = static_next < n_items;
@@ -472,10 +487,16 @@ __device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, b
                 static_next += total_warps * 32u;
                 more = static_next < n_items;
             } else {
+                const unsigned claim = deep_claims && cnt == 32u ? cnt * (unsigned)kLaneDepth : cnt;
                 if (lane == leader)
-                    base = atomicAdd(cursor, cnt);
+                    base = atomicAdd(cursor, claim);
                 base = __shfl_sync(kFullMask, base, leader);
-                more = base + cnt < n_items;
+                more = base + claim < n_items;
+                if (kLaneDepth > 1) {
+                    nxt_stride = cnt;
+                    nxt_end = min(base + claim, n_items);
+                    nxt = base + cnt + (unsigned)__popc(idle & ((1u << lane) - 1u));
+                }
             }
             if (!active && ((idle >> lane) & 1u)) {
                 const unsigned item = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
@@ -509,6 +530,34 @@ __device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, b
             continue;
         }
         // ---- traverse ----
+        // the lane's query is complete: hand it in; true if the lane goes on (its item continues with another segment, or the next
+        // item of its claim starts)
+        auto complete = [&]() -> bool {
+            f3 o = tv.o, d = tv.d; // in: the ray of the finished query; out: the next segment when finish() asks for one
+            HitRec q;
+            if (COUNT)
+                st.query_ends();
+            if (finish(my, tv.best, o, d, q)) {
+                if (COUNT)
+                    st.query_begins();
+                trav_start<ANYHIT>(s, tv, o, d, q, root_entry);
+                return true;
+            }
+            if (kLaneDepth > 1) {
+                while (nxt < nxt_end) {
+                    const unsigned item = nxt;
+                    nxt += nxt_stride;
+                    if (fetch(item, o, d, q)) {
+                        my = item;
+                        if (COUNT)
+                            st.query_begins();
+                        trav_start<ANYHIT>(s, tv, o, d, q, root_entry);
+                        return true;
+                    }
+                }
+            }
+            return false;
+        };
         if (active) {
             const int min_active = more ? kRefillThreshold : 0;
             // Speculative while-while (Aila & Laine): a lane that reaches a leaf parks it and keeps walking nodes until
@@ -539,28 +588,22 @@ __device__ __forceinline__ void trace_queue(const SceneDev& s, int root_entry, b
                         tv.cur = trav_pop(tv, stack);
                     }
                 }
+                if (kLaneDepth > 1 && tv.cur == kTravDone && !complete()) {
+                    active = false;
+                    break;
+                }
                 if (min_active > 0 && __popc(__activemask()) < min_active)
                     break;
             }
-            if (tv.cur == kTravDone) {
-                f3 o, d;
-                HitRec q;
-                if (COUNT)
-                    st.query_ends();
-                if (finish(my, tv.best, o, d, q)) {
-                    if (COUNT)
-                        st.query_begins();
-                    trav_start<ANYHIT>(s, tv, o, d, q, root_entry);
-                } else
-                    active = false;
-            }
+            if (active && tv.cur == kTravDone && !complete())
+                active = false;
         }
         __syncwarp();
     }
 }
 
 // One-shot traversal of a single ray per thread (rt_intersect); lanes are independent here.
-template <bool ANYHIT, bool COUNT>
+template <int ANYHIT, bool COUNT>
 __device__ __forceinline__ void trace_bvh(const SceneDev& s, int root_entry, const f3& o, const f3& d, HitRec& best, TraceStats& st)
 {
     TravStack stack;

@@ -119,6 +119,7 @@ SYMBOLS = [
     ("rt_set_batch_rays", _I, [_P, C.c_uint]),
     ("rt_set_overlap", _I, [_P, _I]),
     ("rt_measure_fp32_peak", _I, [_P, C.POINTER(C.c_double)]),
+    ("rt_set_paths", _I, [_P, _I]),
     ("rt_set_pipeline", _I, [_P, _I, _I, C.c_uint]),
     ("rt_set_stage_timing", _I, [_P, _I]),
     ("rt_stage_times", _I, [_P, _P, _P]),
@@ -397,6 +398,10 @@ class Context:
 
     def set_pipeline(self, lanes: int, batches_per_frame: int, min_batch_pixels: int = 1 << 18):
         _check(self._l.rt_set_pipeline(self._h, lanes, batches_per_frame, min_batch_pixels))
+
+    def set_paths(self, mode: int):
+        """Bounce levels as whole paths (k_paths): -1 automatic, 0 never, 1 whenever legal."""
+        _check(self._l.rt_set_paths(self._h, int(mode)))
 
     def measure_fp32_peak(self) -> float:
         """Un-fused FMUL / FADD issue rate of this device in 1e9 lane-instructions per second (microbenchmark)."""

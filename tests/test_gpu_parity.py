@@ -304,6 +304,28 @@ def test_gather_frames_store_only_rows_with_hits(rtb, gpu_ctx):
     assert np.abs(gpu_ctx.download_rgb(ptr, w, h) - want["a"]).max() <= 1e-6
 
 
+@pytest.mark.parametrize("name", ["monkey_192", "monkey_spots_128", "teapot_d3_128x72", "spheres_preset_160", "cornell_c1_256"])
+def test_paths_and_levels_give_the_same_frame(rtb, gpu_ctx, name):
+    """The bounce levels traced per level (extend / shade / shadow kernels) and as whole paths (k_paths, rt_set_paths) are the same
+    computation: equal ray counts, colours to summation order.  Scenes with a transparent material or other light kinds are not legal for
+    paths and must silently take the per-level kernels (cornell_c1_256: the short box is a dielectric)."""
+    g = Golden(name)
+    gpu_ctx.upload_scene(g.scene)
+    out = []
+    try:
+        for mode in (0, 1):
+            gpu_ctx.set_paths(mode)
+            rgb, ids, t, st = gpu_ctx.render(g.camera(), g.params(), want_ids=True)
+            _check_against_golden(g, rgb, ids, t, st, f"{name}/paths={mode}")
+            out.append((rgb, st))
+    finally:
+        gpu_ctx.set_paths(-1)
+    assert np.abs(out[0][0] - out[1][0]).max() <= 1e-6
+    assert out[0][1].rays == out[1][1].rays
+    legal = name != "cornell_c1_256"
+    assert (out[1][1].kernel_launches < out[0][1].kernel_launches) == legal   # fewer launches exactly when the path kernel ran
+
+
 def test_queue_overflow_is_clean_and_retried(rtb, gpu_ctx):
     """A wavefront queue that overflows (views dominated by dielectrics or glossy surfaces can outgrow any fixed head-room) must end
     the frame with RT_ERR_OVERFLOW and nothing else: consumers clamp their item counts to the queues' capacities and the rest of
