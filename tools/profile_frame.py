@@ -8,7 +8,7 @@ import rtb200  # noqa: E402
 from rtb200 import standin  # noqa: E402
 
 frames = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-mode = rtb200.BVH_SAH_HOST if (len(sys.argv) < 3 or sys.argv[2] == "sah") else rtb200.BVH_LBVH_DEVICE
+mode = {"sah": rtb200.BVH_SAH_HOST, "lbvh": rtb200.BVH_LBVH_DEVICE}.get(sys.argv[2] if len(sys.argv) > 2 else "", rtb200.BVH_PLOC_DEVICE)  # default: the device builder
 ctx = rtb200.Context(0)
 ctx.upload_scene(standin.dragon_standin_scene(), mode)
 cam, prm = rtb200.make_camera(), rtb200.make_params(3840, 2160, 3)
