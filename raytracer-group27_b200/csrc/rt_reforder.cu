@@ -94,24 +94,29 @@ int reference_visit_rank(cudaStream_t st, const float* d_pos, long long n_tris, 
     int *perm = nullptr, *perm_out = nullptr;
     void* tmp = nullptr;
     size_t tmp_bytes = 0;
+    char* arena_to_free = nullptr;
     auto fail = [&](const char* what) {
         if (err)
             *err = what;
-        cudaFree(keys);
-        cudaFree(keys_out);
-        cudaFree(perm);
-        cudaFree(perm_out);
-        cudaFree(tmp);
+        cudaFree(arena_to_free);
         return 1;
     };
     if (n >= (1ll << 31))
         return fail("too many objects");
-    if (cudaMalloc(&keys, n * sizeof(*keys)) != cudaSuccess || cudaMalloc(&keys_out, n * sizeof(*keys)) != cudaSuccess
-        || cudaMalloc(&perm, n * sizeof(int)) != cudaSuccess || cudaMalloc(&perm_out, n * sizeof(int)) != cudaSuccess)
+    // one allocation for all scratch (a cudaMalloc / cudaFree pair per array costs milliseconds)
+    if (cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, perm, perm_out, (int)n, 0, 32 + kRefMaxLevel, st) != cudaSuccess)
+        return fail("radix sort set-up failed (reference visiting order)");
+    auto align = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t kb = align((size_t)n * sizeof(*keys)), pb = align((size_t)n * sizeof(int));
+    char* arena = nullptr;
+    if (cudaMalloc(&arena, 2 * kb + 2 * pb + align(tmp_bytes)) != cudaSuccess)
         return fail("out of device memory (reference visiting order)");
-    if (cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, perm, perm_out, (int)n, 0, 32 + kRefMaxLevel, st) != cudaSuccess
-        || cudaMalloc(&tmp, tmp_bytes) != cudaSuccess)
-        return fail("out of device memory (reference visiting order, sort)");
+    keys = reinterpret_cast<unsigned long long*>(arena);
+    keys_out = reinterpret_cast<unsigned long long*>(arena + kb);
+    perm = reinterpret_cast<int*>(arena + 2 * kb);
+    perm_out = reinterpret_cast<int*>(arena + 2 * kb + pb);
+    tmp = arena + 2 * kb + 2 * pb;
+    arena_to_free = arena;
     const unsigned grid = (unsigned)((n + 255) / 256);
     k_order_init<<<grid, 256, 0, st>>>(perm, n);
     for (int level = 1; level <= kRefMaxLevel; level++) {
@@ -124,11 +129,7 @@ int reference_visit_rank(cudaStream_t st, const float* d_pos, long long n_tris, 
     k_order_rank<<<grid, 256, 0, st>>>(perm, n, d_rank);
     if (cudaStreamSynchronize(st) != cudaSuccess)
         return fail("kernel failure (reference visiting order)");
-    cudaFree(keys);
-    cudaFree(keys_out);
-    cudaFree(perm);
-    cudaFree(perm_out);
-    cudaFree(tmp);
+    cudaFree(arena);
     return 0;
 }
 
