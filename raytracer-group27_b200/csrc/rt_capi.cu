@@ -817,7 +817,9 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
         unsigned long long n_primary = 0, n_traced = 0;
         for (size_t j = first / kTilePixels; j < (first + n_lp) / kTilePixels; j++) {
             const long long g = (long long)fp.rank + (long long)j * fp.world;
-            const int tx = (int)(g % fp.tiles_x), ty = (int)(g / fp.tiles_x);
+            unsigned utx, uty;
+            tile_xy((unsigned)g, (unsigned)fp.tiles_x, utx, uty);
+            const int tx = (int)utx, ty = (int)uty;
             n_primary += (unsigned long long)std::min(kTileW, fp.W - tx * kTileW) * std::min(kTileH, fp.H - ty * kTileH);
             // the ones that walk the BVH: pixels of the tile inside the scene's projection (pixel_sees_scene)
             const int x0 = std::max(tx * kTileW, fp.vis_x0), x1 = std::min(std::min((tx + 1) * kTileW, fp.W), fp.vis_x1);

@@ -85,7 +85,8 @@ __device__ __forceinline__ void local_to_pixel(const FrameParams& fp, unsigned l
 {
     const unsigned j = lp / kTilePixels, k = lp % kTilePixels;
     const unsigned g = (unsigned)fp.rank + j * (unsigned)fp.world; // global tile id
-    const unsigned tx = g % (unsigned)fp.tiles_x, ty = g / (unsigned)fp.tiles_x;
+    unsigned tx, ty;
+    tile_xy(g, (unsigned)fp.tiles_x, tx, ty);
     const unsigned w = k >> 5, l = k & 31;
     px = (int)(tx * kTileW + (w & 3) * 8 + (l & 7));
     py = (int)(ty * kTileH + (w >> 2) * 4 + (l >> 3));
@@ -1157,7 +1158,9 @@ __global__ void __launch_bounds__(256) k_resolve(FrameParams fp, unsigned first_
         if (row_flags && !row_flags[(size_t)j * kTileH + y])
             continue;
         const unsigned g = (unsigned)fp.rank + j * (unsigned)fp.world;
-        const int px = (int)((g % (unsigned)fp.tiles_x) * kTileW + x), py = (int)((g / (unsigned)fp.tiles_x) * kTileH + y);
+        unsigned tx, ty;
+        tile_xy(g, (unsigned)fp.tiles_x, tx, ty);
+        const int px = (int)(tx * kTileW + x), py = (int)(ty * kTileH + y);
         if (px >= fp.W || py >= fp.H)
             continue;
         const unsigned lp = j * kTilePixels + (((y >> 2) * 4 + (x >> 3)) << 5) + ((y & 3) << 3) + (x & 7);
@@ -1213,7 +1216,9 @@ __global__ void __launch_bounds__(256) k_pack_rgb_tiles(FrameParams fp, unsigned
         if (flags && !flags[(size_t)j * kTileH + y]) // rt_render, rows of background: already on the host (k_host_background)
             continue;
         const unsigned g = (unsigned)fp.rank + j * (unsigned)fp.world;
-        const int px0 = (int)((g % (unsigned)fp.tiles_x) * kTileW), py = (int)((g / (unsigned)fp.tiles_x) * kTileH + y);
+        unsigned tx, ty;
+        tile_xy(g, (unsigned)fp.tiles_x, tx, ty);
+        const int px0 = (int)(tx * kTileW), py = (int)(ty * kTileH + y);
         if (py >= fp.H)
             continue;
         const size_t p0 = (size_t)(fp.H - 1 - py) * fp.W + px0;
@@ -1252,7 +1257,9 @@ __global__ void __launch_bounds__(256) k_row_flags(FrameParams fp, unsigned firs
     for (size_t r = (size_t)blockIdx.x * 8 + wib; r < n_rows; r += (size_t)gridDim.x * 8) {
         const unsigned jl = (unsigned)(r / kTileH), y = (unsigned)(r % kTileH);
         const unsigned g = (unsigned)fp.rank + (tile0 + jl) * (unsigned)fp.world;
-        const int px = (int)((g % (unsigned)fp.tiles_x) * kTileW) + lane, py = (int)((g / (unsigned)fp.tiles_x) * kTileH + y);
+        unsigned tx, ty;
+        tile_xy(g, (unsigned)fp.tiles_x, tx, ty);
+        const int px = (int)(tx * kTileW) + lane, py = (int)(ty * kTileH + y);
         const unsigned k = ((((y >> 2) * 4 + ((unsigned)lane >> 3)) << 5) + ((y & 3) << 3) + ((unsigned)lane & 7)); // slot of pixel (lane, y) in its tile
         bool was_hit = false;
         if (pixel_sees_scene(fp, px, py)) {
@@ -1293,7 +1300,9 @@ __global__ void __launch_bounds__(256) k_host_background(FrameParams fp, unsigne
         if (flags && flags[(size_t)j * kTileH + y])
             continue;
         const unsigned g = (unsigned)fp.rank + j * (unsigned)fp.world;
-        const int px0 = (int)((g % (unsigned)fp.tiles_x) * kTileW), py = (int)((g / (unsigned)fp.tiles_x) * kTileH + y);
+        unsigned tx, ty;
+        tile_xy(g, (unsigned)fp.tiles_x, tx, ty);
+        const int px0 = (int)(tx * kTileW), py = (int)(ty * kTileH + y);
         if (py >= fp.H)
             continue;
         const bool outside = py < fp.vis_y0 || py >= fp.vis_y1 || px0 + (int)kTileW <= fp.vis_x0 || px0 >= fp.vis_x1;

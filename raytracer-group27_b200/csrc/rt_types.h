@@ -26,6 +26,22 @@ constexpr int kMaxPointLights = 16;
 constexpr int kMaxSphereLights = 8;
 constexpr int kMaxSpheres = 64;
 
+// Tile g of the image (0 <= g < tiles_x * tiles_y; rank r of a sharded job owns the tiles with g % world == r) lies in tile row
+// g / tiles_x, and inside that row the tiles are rotated by 3 columns per row.  Plain row-major numbering would hand every rank
+// whole tile COLUMNS whenever tiles_x is a multiple of the world size (a 3840-wide frame has 120 tile columns: with 8 ranks, rank r
+// would own the columns r, r + 8, ...), and columns that cross the object more often make their rank the slowest (measured on C3, 8
+// ranks: 0.70-0.79 ms on seven ranks, 0.96 ms on the eighth).  With the rotation a rank's tiles form a diagonal lattice.
+#if defined(__CUDACC__)
+#define RT_HD __host__ __device__
+#else
+#define RT_HD
+#endif
+RT_HD inline void tile_xy(unsigned g, unsigned tiles_x, unsigned& tx, unsigned& ty)
+{
+    ty = g / tiles_x;
+    tx = (g % tiles_x + 3u * ty) % tiles_x;
+}
+
 // Flattened BVH in HBM: 32-byte nodes {lo.xyz, entry}{hi.xyz, count}, read as 2 x float4.
 // Sibling nodes are adjacent (2k, 2k+1) so visiting an inner node is one aligned 64-byte fetch of both children.
 // count == 0: inner node, entry = index of the left child (even, >= 0); count > 0: leaf over triangles

@@ -507,9 +507,12 @@ def tile_grid(width: int, height: int):
 
 
 def owner_map(width: int, height: int, world: int) -> np.ndarray:
-    """(H, W) array in the Screen layout (row 0 = top): which rank renders each pixel (tile_id % world)."""
+    """(H, W) array in the Screen layout (row 0 = top): which rank renders each pixel.  Tile g (owner g % world) lies in tile row
+    g // tiles_x at column (g % tiles_x + 3 * row) % tiles_x (csrc/rt_types.h: tile_xy), so the tile at (column, row) is
+    g = row * tiles_x + (column - 3 * row) % tiles_x."""
     tx, ty = tile_grid(width, height)
-    tiles = (np.arange(ty)[:, None] * tx + np.arange(tx)[None, :]) % world
+    rows, cols = np.arange(ty)[:, None], np.arange(tx)[None, :]
+    tiles = (rows * tx + (cols - 3 * rows) % tx) % world
     full = np.repeat(np.repeat(tiles, TILE_H, 0), TILE_W, 1)[:height, :width]  # indexed [py, px], py = 0 at the bottom
     return full[::-1].copy()                                                     # Screen::setPixel flips y
 

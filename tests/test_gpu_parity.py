@@ -692,8 +692,7 @@ def test_render_shard_fills_a_shared_host_image(rtb):
             changed = (after != before).any(axis=2)
             # only pixels of this rank's 32x16 tiles may change (Screen rows are flipped: row r holds y = h - 1 - r)
             ys, xs = np.nonzero(changed)
-            tiles = ((h - 1 - ys) // 16) * ((w + 31) // 32) + xs // 32
-            assert len(ys) > 0 and (tiles % world == rank).all()
+            assert len(ys) > 0 and (rtb.owner_map(w, h, world)[ys, xs] == rank).all()
             for k, v in enumerate((st.primary_rays, st.shadow_queries, st.secondary_rays)):
                 counts[k] += v
             with pytest.raises(rtb.RtError):
