@@ -222,8 +222,8 @@ int rt_stage_times(rt_ctx* ctx, float* ms /* [RT_STAGE_COUNT] */, int* launches 
 /* How the bounce levels >= 1 are traced.  Per level (the default for wavefronts that fill the GPU): one extend, one shade and one
  * shadow kernel per level, coherent batches.  As whole paths (k_paths): one launch follows every level-1 ray to the end of its
  * path — legal when no material is transparent, glossy_ray_count is 1, all lights are point or spot lights and no texture is
- * sampled; faster for small wavefronts (one GPU's share of a frame split 8 ways), whose per-level kernels each wait for their
- * longest ray.  mode: -1 automatic (paths for batches of up to 1.5 M primary rays), 0 never, 1 whenever legal.  Same image either
+ * sampled; faster for very small wavefronts (frames of a few hundred pixels a side), whose per-level kernels each wait for their
+ * longest ray.  mode: -1 automatic (paths for batches of up to 128 K primary rays), 0 never, 1 whenever legal.  Same image either
  * way (per-pixel sums in a different order). */
 int rt_set_paths(rt_ctx* ctx, int mode);
 /* Measurement aid (bench.py's roofline): the rate at which this device issues un-fused FP32 multiplies and adds — the instruction

@@ -353,6 +353,8 @@ void visible_pixel_rect(const rt_ctx* ctx, FrameParams& fp)
     box_pixel_rect(lo, hi, fp);
 }
 
+constexpr int kTileRotation = 3; // see tile_xy (rt_types.h)
+
 int make_frame_params(const rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, FrameParams& fp)
 {
     if (!cam || !prm)
@@ -451,6 +453,11 @@ int make_frame_params(const rt_ctx* ctx, const rt_camera* cam, const rt_params* 
         return e ? std::max(1, std::min(32, std::atoi(e))) : 0;
     }();
     fp.min_quota = min_quota_env > 0 ? min_quota_env : 1;
+    static const int tile_rot_env = [] { // developer knob for A/B timing
+        const char* e = std::getenv("RTB200_TILE_ROT");
+        return e ? std::max(0, std::atoi(e)) : -1;
+    }();
+    fp.tile_rot = tile_rot_env >= 0 ? tile_rot_env : kTileRotation;
     return RT_OK;
 }
 
@@ -669,7 +676,7 @@ struct HostTarget {
 // Enqueue one frame.  `out`: float4 framebuffer (Screen layout), maybe on a peer GPU.  The frame starts and ends on the
 // context's stream; in between, its batches run on the lanes' own streams.
 constexpr int kBandGridMult = 4;
-constexpr long long kPathsMaxPrimaryRays = 3 << 19; // batches of up to 1.5 M primary rays trace their bounce levels as whole paths
+constexpr long long kPathsMaxPrimaryRays = 1 << 17; // batches of up to 128 K primary rays trace their bounce levels as whole paths
 
 int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_ids, unsigned batch_rays, const HostTarget* host)
 {
@@ -741,10 +748,13 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
         plan.swap(outer);
     }
     // Bounce levels as whole paths (k_paths) instead of per-level kernels: legal when a path never splits and a shadow query never
-    // continues (every material opaque, glossy_ray_count 1), all lights are point-like and no texture is sampled; worth it when the
-    // batch is small — the per-level kernels of a small wavefront each wait for their longest ray (rt_kernels.cu).  Measured on C3
-    // (tools/ab_probe.py, one rank's share of the 4K frame, per-level kernels -> paths): 1/8 0.750 -> 0.707 ms, 1/64 0.475 -> 0.421 ms; 1/4 1.04 -> 1.16 ms,
-    // whole frame 2.04 -> 2.54 ms.  rt_set_paths / RTB200_PATHS=0 / 1: never / whenever legal.
+    // continues (every material opaque, glossy_ray_count 1), all lights are point-like and no texture is sampled.  The per-level
+    // kernels of a small wavefront each wait for their longest ray (rt_kernels.cu), the path kernel waits once for the longest PATH —
+    // which, measured, is made of the long rays of every level.  One GPU, depth 3, per level -> paths (tools/small_frame_probe.py):
+    // 256x256 0.499 -> 0.476 (dragon stand-in), 0.256 -> 0.240 (monkey), 0.294 -> 0.224 ms (teapot); 512x512 0.717 -> 0.779, 0.300 -> 0.320,
+    // 0.339 -> 0.278 ms; 1024x1024 and up: slower or equal.  A rank's share of the 4K frame split 8 ways (tools/rank_probe.py): 0.70-0.79 ms on
+    // seven ranks instead of 0.75-0.81, but 0.95 instead of 0.83 ms on the slowest, which is the one that counts.  Hence: automatic only
+    // for batches of up to 128 K primary rays.  rt_set_paths / RTB200_PATHS=0 / 1: never / whenever legal.
     static const int paths_env_default = [] {
         const char* e = std::getenv("RTB200_PATHS");
         return e ? std::atoi(e) : -1;
@@ -818,7 +828,7 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
         for (size_t j = first / kTilePixels; j < (first + n_lp) / kTilePixels; j++) {
             const long long g = (long long)fp.rank + (long long)j * fp.world;
             unsigned utx, uty;
-            tile_xy((unsigned)g, (unsigned)fp.tiles_x, utx, uty);
+            tile_xy((unsigned)g, (unsigned)fp.tiles_x, (unsigned)fp.tile_rot, utx, uty);
             const int tx = (int)utx, ty = (int)uty;
             n_primary += (unsigned long long)std::min(kTileW, fp.W - tx * kTileW) * std::min(kTileH, fp.H - ty * kTileH);
             // the ones that walk the BVH: pixels of the tile inside the scene's projection (pixel_sees_scene)

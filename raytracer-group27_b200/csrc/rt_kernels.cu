@@ -86,7 +86,7 @@ __device__ __forceinline__ void local_to_pixel(const FrameParams& fp, unsigned l
     const unsigned j = lp / kTilePixels, k = lp % kTilePixels;
     const unsigned g = (unsigned)fp.rank + j * (unsigned)fp.world; // global tile id
     unsigned tx, ty;
-    tile_xy(g, (unsigned)fp.tiles_x, tx, ty);
+    tile_xy(g, (unsigned)fp.tiles_x, (unsigned)fp.tile_rot, tx, ty);
     const unsigned w = k >> 5, l = k & 31;
     px = (int)(tx * kTileW + (w & 3) * 8 + (l & 7));
     py = (int)(ty * kTileH + (w >> 2) * 4 + (l >> 3));
@@ -1159,7 +1159,7 @@ __global__ void __launch_bounds__(256) k_resolve(FrameParams fp, unsigned first_
             continue;
         const unsigned g = (unsigned)fp.rank + j * (unsigned)fp.world;
         unsigned tx, ty;
-        tile_xy(g, (unsigned)fp.tiles_x, tx, ty);
+        tile_xy(g, (unsigned)fp.tiles_x, (unsigned)fp.tile_rot, tx, ty);
         const int px = (int)(tx * kTileW + x), py = (int)(ty * kTileH + y);
         if (px >= fp.W || py >= fp.H)
             continue;
@@ -1217,7 +1217,7 @@ __global__ void __launch_bounds__(256) k_pack_rgb_tiles(FrameParams fp, unsigned
             continue;
         const unsigned g = (unsigned)fp.rank + j * (unsigned)fp.world;
         unsigned tx, ty;
-        tile_xy(g, (unsigned)fp.tiles_x, tx, ty);
+        tile_xy(g, (unsigned)fp.tiles_x, (unsigned)fp.tile_rot, tx, ty);
         const int px0 = (int)(tx * kTileW), py = (int)(ty * kTileH + y);
         if (py >= fp.H)
             continue;
@@ -1258,7 +1258,7 @@ __global__ void __launch_bounds__(256) k_row_flags(FrameParams fp, unsigned firs
         const unsigned jl = (unsigned)(r / kTileH), y = (unsigned)(r % kTileH);
         const unsigned g = (unsigned)fp.rank + (tile0 + jl) * (unsigned)fp.world;
         unsigned tx, ty;
-        tile_xy(g, (unsigned)fp.tiles_x, tx, ty);
+        tile_xy(g, (unsigned)fp.tiles_x, (unsigned)fp.tile_rot, tx, ty);
         const int px = (int)(tx * kTileW) + lane, py = (int)(ty * kTileH + y);
         const unsigned k = ((((y >> 2) * 4 + ((unsigned)lane >> 3)) << 5) + ((y & 3) << 3) + ((unsigned)lane & 7)); // slot of pixel (lane, y) in its tile
         bool was_hit = false;
@@ -1301,7 +1301,7 @@ __global__ void __launch_bounds__(256) k_host_background(FrameParams fp, unsigne
             continue;
         const unsigned g = (unsigned)fp.rank + j * (unsigned)fp.world;
         unsigned tx, ty;
-        tile_xy(g, (unsigned)fp.tiles_x, tx, ty);
+        tile_xy(g, (unsigned)fp.tiles_x, (unsigned)fp.tile_rot, tx, ty);
         const int px0 = (int)(tx * kTileW), py = (int)(ty * kTileH + y);
         if (py >= fp.H)
             continue;

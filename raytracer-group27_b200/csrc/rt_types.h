@@ -36,10 +36,10 @@ constexpr int kMaxSpheres = 64;
 #else
 #define RT_HD
 #endif
-RT_HD inline void tile_xy(unsigned g, unsigned tiles_x, unsigned& tx, unsigned& ty)
+RT_HD inline void tile_xy(unsigned g, unsigned tiles_x, unsigned rot, unsigned& tx, unsigned& ty)
 {
     ty = g / tiles_x;
-    tx = (g % tiles_x + 3u * ty) % tiles_x;
+    tx = (g % tiles_x + rot * ty) % tiles_x;
 }
 
 // Flattened BVH in HBM: 32-byte nodes {lo.xyz, entry}{hi.xyz, count}, read as 2 x float4.
@@ -118,6 +118,7 @@ struct FrameParams {
     // Pixels [vis_x0, vis_x1) x [vis_y0, vis_y1) are the only ones whose camera rays can meet the scene (projection of its
     // bounding box, rt_capi.cu); the other primary rays are misses without being traced.  Whole image when unknown.
     int vis_x0, vis_x1, vis_y0, vis_y1;
+    int tile_rot;        // columns by which the tiles of a tile row are rotated per row (tile_xy)
     int min_quota;       // fewest rays a warp of the traversal kernels takes per refill (small queues: fewer, fuller warps)
     int trace_grid_mult; // host side only: blocks per SM of the traversal kernels of this frame (0: the default, rt_kernels.cu)
 };

@@ -512,7 +512,8 @@ def owner_map(width: int, height: int, world: int) -> np.ndarray:
     g = row * tiles_x + (column - 3 * row) % tiles_x."""
     tx, ty = tile_grid(width, height)
     rows, cols = np.arange(ty)[:, None], np.arange(tx)[None, :]
-    tiles = (rows * tx + (cols - 3 * rows) % tx) % world
+    rot = int(os.environ.get("RTB200_TILE_ROT", "3"))   # developer knob mirrored from the library
+    tiles = (rows * tx + (cols - rot * rows) % tx) % world
     full = np.repeat(np.repeat(tiles, TILE_H, 0), TILE_W, 1)[:height, :width]  # indexed [py, px], py = 0 at the bottom
     return full[::-1].copy()                                                     # Screen::setPixel flips y
 
