@@ -593,17 +593,28 @@ def measure_config(ctx, name, flush, fp32_peak, mg):
     import rtb200
     t0 = time.perf_counter()
     try:
-        desc, sc, cam, prm = load_workload(name)
-        ctx.upload_scene(sc, rtb200.BVH_PLOC_DEVICE)
-        del sc
-        target = None
+        # set-up: the part that can fail on one rank alone (44.5 M triangles: 3 GB of host arrays and 12 GB of build scratch per rank).
+        # The ranks agree on the outcome before any of them enters a collective of the measurement itself.
+        target, setup_error = None, None
+        try:
+            desc, sc, cam, prm = load_workload(name)
+            ctx.upload_scene(sc, rtb200.BVH_PLOC_DEVICE)
+            del sc
+        except Exception as e:
+            setup_error = f"{type(e).__name__}: {e}"
         if mg:
             dist, torch = mg["dist"], mg["torch"]
+            ok = torch.tensor([0.0 if setup_error else 1.0], device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() == 0:
+                return {"error": setup_error or "set-up failed on another rank"}
             handle = [ctx.framebuffer_ipc_handle(prm.width, prm.height) if mg["rank"] == 0 else None]
             dist.broadcast_object_list(handle, src=0)
             if mg["rank"] != 0:
                 target = ctx.open_peer_framebuffer(handle[0])
             dist.barrier()
+        elif setup_error:
+            return {"error": setup_error}
 
         def frame():
             ctx.render_device(cam, prm, target)
