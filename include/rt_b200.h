@@ -226,6 +226,13 @@ int rt_stage_times(rt_ctx* ctx, float* ms /* [RT_STAGE_COUNT] */, int* launches 
  * longest ray.  mode: -1 automatic (paths for batches of up to 128 K primary rays), 0 never, 1 whenever legal.  Same image either
  * way (per-pixel sums in a different order). */
 int rt_set_paths(rt_ctx* ctx, int mode);
+/* Traversal form of the extend and (opaque scenes) point-light shadow kernels of the levels >= 1.  One lane per ray through the
+ * binary tree: best throughput, what a full queue wants.  Eight lanes per ray through an 8-wide tree (collapsed from the binary one
+ * at rt_build_bvh for scenes of up to 2^22 triangles): 2.3 times shorter a chain for the longest ray, which is what the kernel of a
+ * SMALL queue waits for (deep bounce levels, one GPU's share of a sharded frame), at half the throughput.  Same hits bit for bit.
+ * mode: -1 automatic (per level: eight lanes when that level's queue held at most 40 000 rays in the previous frame of the same
+ * shape), 0 never, 1 for every level >= 1. */
+int rt_set_wide(rt_ctx* ctx, int mode);
 /* Measurement aid (bench.py's roofline): the rate at which this device issues un-fused FP32 multiplies and adds — the instruction
  * mix of the path's parity-critical geometry code — in 1e9 lane-instructions per second, from a microbenchmark kernel (best of 3). */
 int rt_measure_fp32_peak(rt_ctx* ctx, double* ginst_per_s);
@@ -308,6 +315,8 @@ int rt_visible_rect(const rt_camera* cam, int width, int height, const float lo[
  *      bool useBVH), bounding_volume_hierarchy.cpp:49-78) ----
  * rays: 6 floats each (origin, direction).  tri_id: global triangle index or -1; t: ray.t or FLT_MAX. */
 int rt_intersect(rt_ctx* ctx, const float* rays, int64_t n_rays, int use_bvh, int* tri_id, float* t);
+/* Device time of the traversal kernel of the last rt_intersect (developer aid). */
+float rt_last_intersect_ms(rt_ctx* ctx);
 
 /* ---- OBJ/MTL loading (replaces loadMesh, src/mesh.cpp:58-188; host-only, no GPU needed) ---- */
 typedef struct rt_mesh_soup rt_mesh_soup;

@@ -86,6 +86,15 @@ struct rt_ctx {
     float4* lbvh_nodes = nullptr; // owned when the device builder allocated them
     int* lbvh_perm = nullptr;
     float4* wide_nodes = nullptr; // 4-wide tree collapsed from the builder's binary one (RT_BVH_WIDE builds)
+    DevBuf<float4> d_wide8;       // 8-wide tree for the eight-lanes-per-ray kernels of small queues (rt_wide8.cu); built for scenes of up to 2^22 triangles
+    int wide8_root = 0, wide8_depth = 0;
+    bool wide8_built = false;
+    int wide_mode = -1;           // rt_set_wide: -1 automatic (levels whose queues were small in the previous frame), 0 never, 1 every level >= 1
+    // queue fills per lane and bounce level of the previous frame (Counters::level_ext / level_sh) and what that frame looked like
+    unsigned hist_ext[kMaxLanes][kLevelHistory] = {}, hist_sh[kMaxLanes][kLevelHistory] = {};
+    unsigned long long hist_signature = 0, frame_signature = 0;
+    bool hist_valid = false;
+    float last_intersect_ms = 0.0f;
     const float4* nodes = nullptr;
     int n_nodes = 0, root_entry = 0, bvh_depth = 0;
     bool bvh_built = false;
@@ -676,6 +685,7 @@ struct HostTarget {
 // Enqueue one frame.  `out`: float4 framebuffer (Screen layout), maybe on a peer GPU.  The frame starts and ends on the
 // context's stream; in between, its batches run on the lanes' own streams.
 constexpr int kBandGridMult = 4;
+constexpr long long kWideMaxRays = 40000; // queues of up to this many rays (in the previous frame) are traced with eight lanes per ray
 constexpr long long kPathsMaxPrimaryRays = 1 << 17; // batches of up to 128 K primary rays trace their bounce levels as whole paths
 
 int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_ids, unsigned batch_rays, const HostTarget* host)
@@ -771,6 +781,30 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
         return e ? std::max(1, std::atoi(e)) : 1;
     }();
     const bool use_paths = paths_legal && paths_env != 0 && (paths_env == 1 || (long long)batch_pixels * fp.spp <= paths_max_rays);
+    // Which traversal form the levels >= 1 take: eight lanes per ray through the 8-wide tree for queues that were small in the
+    // previous frame (rt_kernels.cu: k_extend_wide), one lane per ray otherwise.  The previous frame's fills are a hint, not a
+    // contract: both forms are correct for any queue, the choice only decides the speed.  Frames are compared by a signature.
+    static const long long wide_max_rays = [] {
+        const char* e = std::getenv("RTB200_WIDE_MAX_RAYS");
+        return e ? std::atoll(e) : (long long)kWideMaxRays;
+    }();
+    const unsigned long long signature = ((unsigned long long)fp.W << 44) ^ ((unsigned long long)fp.H << 28) ^ ((unsigned long long)fp.spp << 20)
+        ^ ((unsigned long long)fp.world << 12) ^ ((unsigned long long)fp.rank << 4) ^ (unsigned long long)fp.max_level ^ ((unsigned long long)plan.size() << 56)
+        ^ ((unsigned long long)fp.n_point << 50);
+    const bool wide_usable = ctx->wide8_built && ctx->wide_mode != 0 && !ctx->counters_enabled && !fp.exhaustive && ctx->overlap;
+    const bool wide_hist = wide_usable && ctx->hist_valid && ctx->hist_signature == signature && plan.size() <= (size_t)lanes_wanted;
+    auto wide_for = [&](int lane, int level, bool shadow) {
+        if (!wide_usable || level < (shadow ? 0 : 1))
+            return false;
+        if (shadow && (fp.any_transparent || fp.n_point == 0))
+            return false;
+        if (ctx->wide_mode == 1)
+            return true;
+        if (!wide_hist || level >= kLevelHistory)
+            return false;
+        return (long long)(shadow ? ctx->hist_sh[lane][level] : ctx->hist_ext[lane][level]) <= wide_max_rays;
+    };
+    ctx->frame_signature = signature;
     const size_t n_batches = plan.size();
     const int n_lanes = (int)std::min<size_t>(lanes_wanted, std::max<size_t>(n_batches, 1));
 
@@ -869,7 +903,10 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
                 StageScope sc(ctx, RT_STAGE_EXTEND, st);
                 SceneDev s_ext = s;
                 s_ext.tie_by_id = fp.tie_by_id; // shadow queries keep the BVH order (shadow.cpp:42)
-                launch_extend(st, ctx->sm_count, s_ext, ctx->root_entry, fp, b, qi, level, (unsigned)first, ctx->counters_enabled);
+                if (wide_for(li, level, false))
+                    launch_extend_wide(st, ctx->sm_count, s_ext, ctx->d_wide8.p, ctx->wide8_root, b, qi, level);
+                else
+                    launch_extend(st, ctx->sm_count, s_ext, ctx->root_entry, fp, b, qi, level, (unsigned)first, ctx->counters_enabled);
             }
             if (sparse && level == 0) { // which tile rows of this batch hold a hit: the others are not stored (k_resolve)
                 launch_row_flags(st, ctx->sm_count, fp, (unsigned)first, n_lp, b.q[0].hit, ctx->row_flags.p, &b.counters->flagged_rows);
@@ -898,7 +935,10 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
             }
             if (fp.n_point > 0) {
                 StageScope sc(ctx, RT_STAGE_SHADOW_POINT, ss);
-                launch_shadow_point(ss, ctx->sm_count, s, ctx->root_entry, fp, b, ctx->counters_enabled);
+                if (wide_for(li, level, true))
+                    launch_shadow_point_wide(ss, ctx->sm_count, s, ctx->d_wide8.p, ctx->wide8_root, b, level);
+                else
+                    launch_shadow_point(ss, ctx->sm_count, s, ctx->root_entry, fp, b, level, ctx->counters_enabled);
                 launches++;
             }
             if (fp.n_sphere > 0) {
@@ -1095,6 +1135,8 @@ int rt_create(int device, rt_ctx** out)
         ctx->cull_primary = e[0] != '0';
     if (const char* e = std::getenv("RTB200_TRACE_BANDS"))
         ctx->trace_bands = e[0] == '1';
+    if (const char* e = std::getenv("RTB200_WIDE")) // developer knob: rt_set_wide's mode for new contexts
+        ctx->wide_mode = std::max(-1, std::min(1, std::atoi(e)));
     if (const char* e = std::getenv("RTB200_QUEUE_SCALE")) {
         const double v = std::atof(e);
         if (v > 0.0 && v <= 1.0)
@@ -1186,6 +1228,7 @@ int rt_destroy(rt_ctx* ctx)
     ctx->flag.release();
     ctx->row_flags.release();
     ctx->fb_plain.release();
+    ctx->d_wide8.release();
     if (ctx->lbvh_nodes)
         cudaFree(ctx->lbvh_nodes);
     if (ctx->lbvh_perm)
@@ -1243,6 +1286,14 @@ int rt_stage_times(rt_ctx* ctx, float* ms, int* launches)
         ms[k] = ctx->stage_ms[k];
         launches[k] = ctx->stage_launches[k];
     }
+    return RT_OK;
+}
+
+int rt_set_wide(rt_ctx* ctx, int mode)
+{
+    if (!ctx || mode < -1 || mode > 1)
+        return fail(RT_ERR_INVALID, "rt_set_wide: mode must be -1 (automatic), 0 (never) or 1 (every level >= 1)");
+    ctx->wide_mode = mode;
     return RT_OK;
 }
 
@@ -1478,6 +1529,26 @@ int rt_build_bvh(rt_ctx* ctx, int mode)
         }
     }
 #endif
+    ctx->wide8_built = false;
+    ctx->hist_valid = false;
+    const double t_wide0 = build_ms();
+    static const bool wide8_off = [] {
+        const char* e = std::getenv("RTB200_WIDE8");
+        return e && e[0] == '0';
+    }();
+    if (!wide8_off && ctx->n_tris <= (1ll << 22) && !RT_BVH_WIDE) { // the 8-wide tree beside the binary one: collapsed on the host (a few ms for 10^5 triangles)
+        std::vector<float4> h2(2 * (size_t)ctx->n_nodes), h8;
+        CK(cudaMemcpyAsync(h2.data(), ctx->nodes, h2.size() * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        build_wide8_host(h2.data(), ctx->n_nodes, ctx->root_entry, h8, ctx->wide8_root, ctx->wide8_depth);
+        CK(ctx->d_wide8.ensure(std::max<size_t>(h8.size(), 16)));
+        if (!h8.empty())
+            CK(cudaMemcpyAsync(ctx->d_wide8.p, h8.data(), h8.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->wide8_built = !h8.empty() && 7 * ctx->wide8_depth + 1 < 64; // (a step pushes up to 7 entries on the 64-entry group stack)
+        if (trace_build)
+            std::fprintf(stderr, "[build] 8-wide tree: %zu nodes, depth %d, %.2f ms (copy back, collapse on the host, upload)\n", h8.size() / 16, ctx->wide8_depth, build_ms() - t_wide0);
+    }
     const double t_tree = build_ms();
     {
         const SceneDev sd = ctx->scene_dev();
@@ -1862,6 +1933,13 @@ int rt_sync(rt_ctx* ctx, rt_stats* stats)
             ctx->trace_ev.clear();
             ctx->trace_what.clear();
         }
+        for (int l = 0; l < kMaxLanes; l++) // the queue fills of this frame are the next frame's expectations
+            if (ctx->lanes[l].used) {
+                std::memcpy(ctx->hist_ext[l], ctx->h_counters[l].level_ext, sizeof(ctx->hist_ext[l]));
+                std::memcpy(ctx->hist_sh[l], ctx->h_counters[l].level_sh, sizeof(ctx->hist_sh[l]));
+            }
+        ctx->hist_signature = ctx->frame_signature;
+        ctx->hist_valid = true;
         Counters c; // totals over the lanes used by the frame
         std::memset(&c, 0, sizeof(c));
         for (int l = 0; l < kMaxLanes; l++) {
@@ -2297,18 +2375,28 @@ int rt_intersect(rt_ctx* ctx, const float* rays, int64_t n_rays, int use_bvh, in
     CK(cudaMemcpyAsync(ctx->rays_in.p, rays, 6 * (size_t)n_rays * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     SceneDev s_int = ctx->scene_dev();
     s_int.tie_by_id = use_bvh ? 0 : 1;
-    launch_intersect(ctx->stream, ctx->sm_count, s_int, ctx->root_entry, ctx->rays_in.p, (long long)n_rays, use_bvh, ctx->out_id.p,
-        ctx->out_t.p, ctx->flag.p);
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (use_bvh == 2) { // experiment: the 8-wide tree, eight lanes per ray
+        if (!ctx->wide8_built)
+            return fail(RT_ERR_INVALID, "rt_intersect: no 8-wide tree for this scene");
+        launch_intersect_wide(ctx->stream, ctx->sm_count, s_int, ctx->d_wide8.p, ctx->wide8_root, ctx->rays_in.p, (long long)n_rays, ctx->out_id.p, ctx->out_t.p);
+    } else
+        launch_intersect(ctx->stream, ctx->sm_count, s_int, ctx->root_entry, ctx->rays_in.p, (long long)n_rays, use_bvh, ctx->out_id.p,
+            ctx->out_t.p, ctx->flag.p);
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaGetLastError());
     unsigned flag = 0;
     CK(cudaMemcpyAsync(tri_id, ctx->out_id.p, (size_t)n_rays * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(t, ctx->out_t.p, (size_t)n_rays * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(&flag, ctx->flag.p, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last_intersect_ms, ctx->ev0, ctx->ev1);
     if (flag)
         return fail(RT_ERR_OVERFLOW, "traversal stack overflow");
     return RT_OK;
 }
+
+float rt_last_intersect_ms(rt_ctx* ctx) { return ctx ? ctx->last_intersect_ms : 0.0f; }
 
 // ---- OBJ loading: host only ----
 struct rt_mesh_soup {

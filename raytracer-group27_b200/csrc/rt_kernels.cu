@@ -3,6 +3,7 @@
 // kernel cites the reference lines it replaces.
 #include "rt_kernels.h"
 #include "rt_trace.cuh"
+#include "rt_wide8.cuh"
 #include <algorithm>
 #include <cstdlib>
 
@@ -399,13 +400,15 @@ __global__ void k_level_reset(Counters* c, int next_q, long long n_current, unsi
 // src/bounding_volume_hierarchy.cpp:49-78) through the warp-synchronous engine of rt_trace.cuh.  At level 0 the ray is
 // generated from the pixel index when a lane picks the item up (K1 fused).  Result: hit[i] = {bits(t), BVH-order triangle}.
 template <bool LEVEL0, bool COUNT>
-__global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_extend(SceneDev s, int root_entry, FrameParams fp, BatchDev b, int qi, unsigned first_lp)
+__global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_extend(SceneDev s, int root_entry, FrameParams fp, BatchDev b, int qi, unsigned first_lp, int level)
 {
     // a queue that overflowed holds `capacity` items (block_alloc rejects the rest but still counts them); once the flag is up
     // the rest of the batch is skipped, rt_sync reports RT_ERR_OVERFLOW and the caller renders again with more head-room
     if (batch_overflowed(b))
         return;
     const unsigned n = LEVEL0 ? b.counters->n_rays[qi] : min(b.counters->n_rays[qi], b.ray_capacity); // (level 0: the batch's primary rays, set by the host)
+    if (blockIdx.x == 0 && threadIdx.x == 0 && level < kLevelHistory)
+        b.counters->level_ext[level] = n;
     TraceStats st;
     int tag = 0;
     trace_queue<false, COUNT, LEVEL0 && RT_STATIC_L0>(
@@ -858,11 +861,13 @@ __device__ __forceinline__ void shadow_loop(const SceneDev& s, int root_entry, c
 // K4a shadow rays to point lights (getPointLights' cansee call, src/shadow.cpp:120).
 // ANYHIT: every material is opaque, so the first blocker found decides; otherwise the closest hit does.
 template <bool ANYHIT, bool COUNT>
-__global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_shadow_point(SceneDev s, int root_entry, FrameParams fp, BatchDev b)
+__global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_shadow_point(SceneDev s, int root_entry, FrameParams fp, BatchDev b, int level)
 {
     if (batch_overflowed(b))
         return;
     const unsigned n = min(b.counters->sh[b.par].n_pt, b.shadow_pt_capacity);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && level < kLevelHistory)
+        b.counters->level_sh[level] = n;
     shadow_loop<ANYHIT, COUNT>(
         s, root_entry, fp, b, &b.counters->sh[b.par].work_pt, n,
         [&](unsigned i, f3& p1, f3& p2) {
@@ -879,6 +884,60 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_shadow_
             const float4 bb = b.sq_point.b[i];
             accumulate(b.accum, __float_as_int(pp.w), al.x * intensity + bb.x, al.y * intensity + bb.y, al.z * intensity + bb.z);
         });
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2w / K4w: extend and opaque point-light shadow queries of a SMALL queue through the 8-wide tree with eight lanes per ray
+// (rt_wide8.cuh): same inputs, same outputs, bit for bit the same hits — the triangle test and the tie rule are the binary
+// engine's — at 2.3 times shorter a chain for the longest ray (tools/wide8_probe.py: 1 K / 16 K / 64 K / 256 K incoherent rays:
+// 48 / 81 / 145 / 444 us against 111 / 139 / 161 / 257 us), which is what a small queue's kernel waits for.  Group g of the
+// grid takes items g, g + groups, ...: a small queue needs no work cursor.  enqueue_frame picks these kernels for the levels whose
+// queues held at most kWideMaxRays items in the previous frame.
+__global__ void __launch_bounds__(kWideBlock, 8) k_extend_wide(SceneDev s, const float4* __restrict__ wide, int wide_root, BatchDev b, int qi, int level)
+{
+    __shared__ int s_stack[kWideBlock / kGroup][kWideStack];
+    if (batch_overflowed(b))
+        return;
+    const unsigned n = min(b.counters->n_rays[qi], b.ray_capacity);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && level < kLevelHistory)
+        b.counters->level_ext[level] = n;
+    const unsigned groups = gridDim.x * (kWideBlock / kGroup);
+    for (unsigned item = blockIdx.x * (kWideBlock / kGroup) + threadIdx.x / kGroup; item < n; item += groups) {
+        const f3 o = mk3(b.q[qi].o_pix[item]), d = mk3(b.q[qi].d[item]);
+        HitRec best = fresh_query();
+        trace_wide<false>(s, wide, wide_root, o, d, best, s_stack[threadIdx.x / kGroup]);
+        if ((threadIdx.x & (kGroup - 1)) == 0)
+            b.q[qi].hit[item] = make_int2(__float_as_int(best.t), best.ti);
+    }
+}
+
+__global__ void __launch_bounds__(kWideBlock, 8) k_shadow_point_wide(SceneDev s, const float4* __restrict__ wide, int wide_root, BatchDev b, int level)
+{
+    __shared__ int s_stack[kWideBlock / kGroup][kWideStack];
+    if (batch_overflowed(b))
+        return;
+    const unsigned n = min(b.counters->sh[b.par].n_pt, b.shadow_pt_capacity);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && level < kLevelHistory)
+        b.counters->level_sh[level] = n;
+    const bool leader = (threadIdx.x & (kGroup - 1)) == 0;
+    const unsigned groups = gridDim.x * (kWideBlock / kGroup);
+    unsigned queries = 0;
+    for (unsigned item = blockIdx.x * (kWideBlock / kGroup) + threadIdx.x / kGroup; item < n; item += groups) {
+        const float4 pp = b.sq_point.p_pix[item], al = b.sq_point.a_light[item];
+        CanSee cs;
+        bool visible = true;
+        if (cansee_begin(cs, mk3(pp), mk3(__ldg(&s.point_lights[3 * __float_as_int(al.w)])))) {
+            queries += leader ? 1u : 0u;
+            HitRec best = cansee_query(cs);
+            trace_wide<true>(s, wide, wide_root, cs.o, cs.d, best, s_stack[threadIdx.x / kGroup]);
+            visible = best.ti == -1;
+        }
+        if (leader && visible) {
+            const float4 bb = b.sq_point.b[item];
+            accumulate(b.accum, __float_as_int(pp.w), al.x * 1.0f + bb.x, al.y * 1.0f + bb.y, al.z * 1.0f + bb.z);
+        }
+    }
+    warp_add_u64(&b.counters->shadow_queries, queries);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1417,14 +1476,14 @@ void launch_extend(cudaStream_t st, int sm_count, const SceneDev& s, int root_en
     const int grid = sm_count * trace_grid_mult(fp);
     if (level == 0) {
         if (count)
-            k_extend<true, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b, qi, first_lp);
+            k_extend<true, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b, qi, first_lp, level);
         else
-            k_extend<true, false><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b, qi, first_lp);
+            k_extend<true, false><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b, qi, first_lp, level);
     } else {
         if (count)
-            k_extend<false, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b, qi, first_lp);
+            k_extend<false, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b, qi, first_lp, level);
         else
-            k_extend<false, false><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b, qi, first_lp);
+            k_extend<false, false><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b, qi, first_lp, level);
     }
 }
 
@@ -1445,18 +1504,28 @@ void launch_shade(cudaStream_t st, int sm_count, const SceneDev& s, const FrameP
     }
 }
 
-void launch_shadow_point(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count)
+void launch_shadow_point(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, int level, bool count)
 {
     const int grid = sm_count * trace_grid_mult(fp);
     const bool anyhit = !fp.any_transparent;
     if (anyhit && count)
-        k_shadow_point<true, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b);
+        k_shadow_point<true, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b, level);
     else if (anyhit)
-        k_shadow_point<true, false><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b);
+        k_shadow_point<true, false><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b, level);
     else if (count)
-        k_shadow_point<false, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b);
+        k_shadow_point<false, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b, level);
     else
-        k_shadow_point<false, false><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b);
+        k_shadow_point<false, false><<<grid, RT_TRACE_BLOCK, 0, st>>>(s, root_entry, fp, b, level);
+}
+
+void launch_extend_wide(cudaStream_t st, int sm_count, const SceneDev& s, const float4* wide, int wide_root, const BatchDev& b, int qi, int level)
+{
+    k_extend_wide<<<sm_count * 8, kWideBlock, 0, st>>>(s, wide, wide_root, b, qi, level);
+}
+
+void launch_shadow_point_wide(cudaStream_t st, int sm_count, const SceneDev& s, const float4* wide, int wide_root, const BatchDev& b, int level)
+{
+    k_shadow_point_wide<<<sm_count * 8, kWideBlock, 0, st>>>(s, wide, wide_root, b, level);
 }
 
 void launch_paths(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, int qi, int first_level, bool count)

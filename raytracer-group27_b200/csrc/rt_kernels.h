@@ -13,7 +13,10 @@ void launch_level_reset(cudaStream_t st, Counters* c, int next_q, long long n_cu
 void launch_extend(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, int qi,
     int level, unsigned first_lp, bool count);
 void launch_shade(cudaStream_t st, int sm_count, const SceneDev& s, const FrameParams& fp, const BatchDev& b, int qi, int level, unsigned first_lp);
-void launch_shadow_point(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count);
+void launch_shadow_point(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, int level, bool count);
+// The same two queues through the 8-wide tree with eight lanes per ray (small queues; extend: levels >= 1; shadow: every material opaque).
+void launch_extend_wide(cudaStream_t st, int sm_count, const SceneDev& s, const float4* wide, int wide_root, const BatchDev& b, int qi, int level);
+void launch_shadow_point_wide(cudaStream_t st, int sm_count, const SceneDev& s, const float4* wide, int wide_root, const BatchDev& b, int level);
 // Bounce levels >= first_level of the rays in queue qi as whole paths (k_paths): small wavefronts of opaque scenes with point-like lights only.
 void launch_paths(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, int qi, int first_level, bool count);
 void launch_shadow_sphere(cudaStream_t st, int sm_count, const SceneDev& s, int root_entry, const FrameParams& fp, const BatchDev& b, bool count);
@@ -74,6 +77,12 @@ struct WideBvh {
     int depth = 0;
 };
 int collapse_bvh_wide_device(cudaStream_t st, const float4* d_nodes2, int n_nodes2, int root_entry2, WideBvh* out, const char** err);
+
+// EXPERIMENT (rt_wide8.cu): 8-wide tree collapsed on the host from the binary one (16 float4 per node), and rt_intersect through it
+// with eight lanes per ray.
+int build_wide8_host(const float4* nodes2, int n_nodes2, int root_entry2, std::vector<float4>& out, int& root_entry8, int& depth8);
+void launch_intersect_wide(cudaStream_t st, int sm_count, const SceneDev& s, const float4* wide, int root_entry, const float* rays, long long n, int* tri_id,
+    float* t_out);
 
 // Visiting rank of every object (triangles 0..n_tris-1, then spheres) in the reference's own BVH (rt_reforder.cu): the tie key
 // of the traversal kernels.  d_spheres: 3 x float4 per sphere ({centre, radius} first).  d_rank: n_tris + n_spheres ints.

@@ -21,6 +21,7 @@ constexpr int kTriStride = RT_TRI_AOS ? 4 : 1;
 
 constexpr int kMaxLeafTris = 8;   // leaf size must fit the 3-bit count of a packed stack entry
 constexpr int kStackDepth = 64;   // per-thread traversal stack (ints); builders guarantee depth < kStackDepth
+constexpr int kLevelHistory = 8;  // bounce levels whose queue fills are remembered from frame to frame (Counters::level_ext / level_sh)
 constexpr int kMaxLanes = 4;       // batches of one frame in flight at once (rt_set_pipeline)
 constexpr int kMaxPointLights = 16;
 constexpr int kMaxSphereLights = 8;
@@ -149,6 +150,10 @@ struct Counters {
     unsigned long long ext_tri_tests;
     unsigned long long ext_tri_tests_full;
     unsigned int max_ray_nodes, max_ray_tris; // instrumented builds: most boxes / triangles one query touched
+    // Queue fills of the batch the lane rendered last, by bounce level (levels past the table are not recorded): extend rays and
+    // point-like shadow records.  The host reads them with the counters and uses them as the expected sizes of the NEXT frame's
+    // queues, to pick the traversal form (one lane per ray / eight lanes per ray, rt_wide8.cuh) of every level.
+    unsigned int level_ext[kLevelHistory], level_sh[kLevelHistory];
 };
 
 struct RayQueue {

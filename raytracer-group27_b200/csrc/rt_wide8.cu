@@ -1,0 +1,165 @@
+// EXPERIMENT (round 2): an 8-wide tree walked by EIGHT LANES PER RAY, for small wavefronts.
+//
+// The per-level kernels of a small wavefront wait for their longest ray: a chain of ~200 dependent node-pair fetches at L2
+// latency plus up to ~90 triangle tests one after the other (profiles/README.md, round 2).  Eight lanes per ray shorten that
+// chain instead of hiding it: one step fetches and slab-tests the eight children of a node at once (2.5 times fewer steps than
+// pairs), a leaf's triangles (up to eight) are tested side by side, and the four rays of a warp diverge only as groups.  The
+// price is throughput — eight lanes do what one lane did — so this form is for the queues that cannot fill the GPU anyway.
+//
+// The 8-wide tree is collapsed from the binary one the builders emit (boxes copied, never recomputed: the conservative padding
+// carries over): a node takes the two children of a binary node and keeps replacing its largest inner child by that child's two
+// until it has eight; binary subtrees of at most eight triangles become one leaf (their triangles are contiguous in leaf order).
+// Node layout: child k at float4 [2k] = {lo.xyz, entry}, [2k + 1] = {hi.xyz, -}; 256 bytes per node; entry >= 0: node index,
+// < 0: leaf ~((first << 3) | (count - 1)) like the binary tree's; a missing child is a box turned inside out.
+#include "rt_kernels.h"
+#include "rt_wide8.cuh"
+
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+#include <cstring>
+#include <vector>
+
+namespace rtb {
+
+namespace {
+
+struct Bin2 { // host view of the binary tree
+    const float4* n;
+    int entry(int i) const
+    {
+        int e;
+        std::memcpy(&e, &n[2 * (size_t)i].w, 4);
+        return e;
+    }
+    float area(int i) const
+    {
+        const float4 lo = n[2 * (size_t)i], hi = n[2 * (size_t)i + 1];
+        const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+        return dx * dy + dy * dz + dz * dx;
+    }
+};
+
+// triangles below binary node i and the first of them (leaf order is depth first, so a subtree's triangles are contiguous)
+void subtree_span(const Bin2& b, int i, std::vector<int>& count, std::vector<int>& first)
+{
+    // iterative post-order
+    std::vector<std::pair<int, int>> st { { i, 0 } };
+    while (!st.empty()) {
+        auto [v, phase] = st.back();
+        st.pop_back();
+        const int e = b.entry(v);
+        if (e < 0) {
+            const int enc = ~e;
+            count[v] = (enc & 7) + 1;
+            first[v] = enc >> 3;
+        } else if (phase == 0) {
+            st.push_back({ v, 1 });
+            st.push_back({ e, 0 });
+            st.push_back({ e + 1, 0 });
+        } else {
+            count[v] = count[e] + count[e + 1];
+            first[v] = std::min(first[e], first[e + 1]);
+        }
+    }
+}
+
+} // namespace
+
+int build_wide8_host(const float4* nodes2, int n_nodes2, int root_entry2, std::vector<float4>& out, int& root_entry8, int& depth8)
+{
+    Bin2 b { nodes2 };
+    std::vector<int> count((size_t)n_nodes2, 0), first((size_t)n_nodes2, 0);
+    subtree_span(b, 0, count, first);
+    auto leaf_entry = [&](int v) { return ~((first[v] << 3) | (count[v] - 1)); };
+    out.clear();
+    depth8 = 1;
+    if (count[0] <= 8) { // the whole scene is one leaf
+        root_entry8 = leaf_entry(0);
+        return 0;
+    }
+    struct Item {
+        int bin, dst, depth;
+    };
+    std::vector<Item> work { { 0, 0, 1 } };
+    out.resize(16);
+    root_entry8 = 0;
+    while (!work.empty()) {
+        const Item it = work.back();
+        work.pop_back();
+        depth8 = std::max(depth8, it.depth + 1);
+        std::vector<int> kids { b.entry(it.bin), b.entry(it.bin) + 1 };
+        for (;;) { // open the largest child that is still a subtree of more than 8 triangles
+            if ((int)kids.size() >= 8)
+                break;
+            int best = -1;
+            float ba = -1.0f;
+            for (int k = 0; k < (int)kids.size(); k++)
+                if (count[kids[k]] > 8 && b.area(kids[k]) > ba) {
+                    ba = b.area(kids[k]);
+                    best = k;
+                }
+            if (best < 0)
+                break;
+            const int e = b.entry(kids[best]);
+            kids[best] = e;
+            kids.push_back(e + 1);
+        }
+        for (int k = 0; k < 8; k++) {
+            float4 lo = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, 0.0f), hi = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, 0.0f);
+            int entry = INT_MIN;
+            if (k < (int)kids.size()) {
+                const int v = kids[k];
+                lo = nodes2[2 * (size_t)v];
+                hi = nodes2[2 * (size_t)v + 1];
+                if (count[v] <= 8) {
+                    entry = leaf_entry(v);
+                } else {
+                    entry = (int)(out.size() / 16);
+                    out.resize(out.size() + 16);
+                    work.push_back({ v, entry, it.depth + 1 });
+                }
+            }
+            std::memcpy(&lo.w, &entry, 4);
+            out[16 * (size_t)it.dst + 2 * k] = lo;
+            out[16 * (size_t)it.dst + 2 * k + 1] = hi;
+        }
+    }
+    (void)root_entry2;
+    return 0;
+}
+
+namespace {
+
+// rt_intersect through the 8-wide tree: group g takes rays g, g + groups, ...
+__global__ void __launch_bounds__(kWideBlock) k_intersect_wide(SceneDev s, const float4* __restrict__ wide, int root_entry, const float* __restrict__ rays,
+    long long n, int* tri_id, float* t_out)
+{
+    __shared__ int s_stack[kWideBlock / kGroup][kWideStack];
+    int* stack = s_stack[threadIdx.x / kGroup];
+    const long long groups = (long long)gridDim.x * (kWideBlock / kGroup);
+    for (long long i = (long long)blockIdx.x * (kWideBlock / kGroup) + threadIdx.x / kGroup; i < n; i += groups) {
+        const f3 o = mk3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]);
+        const f3 d = mk3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
+        HitRec best = fresh_query();
+        trace_wide<false>(s, wide, root_entry, o, d, best, stack);
+        if ((threadIdx.x & (kGroup - 1)) == 0) {
+            tri_id[i] = global_id(s, best);
+            t_out[i] = best.t;
+        }
+    }
+}
+
+} // namespace
+
+void launch_intersect_wide(cudaStream_t st, int sm_count, const SceneDev& s, const float4* wide, int root_entry, const float* rays, long long n, int* tri_id,
+    float* t_out)
+{
+    if (n <= 0)
+        return;
+    const long long want = (n + (kWideBlock / kGroup) - 1) / (kWideBlock / kGroup);
+    const int grid = (int)std::min<long long>(want, (long long)sm_count * 16);
+    k_intersect_wide<<<grid, kWideBlock, 0, st>>>(s, wide, root_entry, rays, n, tri_id, t_out);
+}
+
+} // namespace rtb

@@ -120,6 +120,7 @@ SYMBOLS = [
     ("rt_set_overlap", _I, [_P, _I]),
     ("rt_measure_fp32_peak", _I, [_P, C.POINTER(C.c_double)]),
     ("rt_set_paths", _I, [_P, _I]),
+    ("rt_set_wide", _I, [_P, _I]),
     ("rt_set_pipeline", _I, [_P, _I, _I, C.c_uint]),
     ("rt_set_stage_timing", _I, [_P, _I]),
     ("rt_stage_times", _I, [_P, _P, _P]),
@@ -140,6 +141,7 @@ SYMBOLS = [
     ("rt_close_peer_framebuffer", _I, [_P, _P]),
     ("rt_download_rgb", _I, [_P, _P, _I, _I, _P]),
     ("rt_intersect", _I, [_P, _P, C.c_int64, _I, _P, _P]),
+    ("rt_last_intersect_ms", C.c_float, [_P]),
     ("rt_load_obj", _I, [C.c_char_p, _I, C.POINTER(_P)]),
     ("rt_soup_num_triangles", C.c_int64, [_P]),
     ("rt_soup_num_meshes", _I, [_P]),
@@ -402,6 +404,10 @@ class Context:
     def set_paths(self, mode: int):
         """Bounce levels as whole paths (k_paths): -1 automatic, 0 never, 1 whenever legal."""
         _check(self._l.rt_set_paths(self._h, int(mode)))
+
+    def set_wide(self, mode: int):
+        """Eight lanes per ray through the 8-wide tree for the levels >= 1: -1 automatic (small queues), 0 never, 1 always."""
+        _check(self._l.rt_set_wide(self._h, int(mode)))
 
     def measure_fp32_peak(self) -> float:
         """Un-fused FMUL / FADD issue rate of this device in 1e9 lane-instructions per second (microbenchmark)."""

@@ -326,6 +326,52 @@ def test_paths_and_levels_give_the_same_frame(rtb, gpu_ctx, name):
     assert (out[1][1].kernel_launches < out[0][1].kernel_launches) == legal   # fewer launches exactly when the path kernel ran
 
 
+@pytest.mark.parametrize("name", ["monkey_192", "monkey_spots_128", "teapot_d3_128x72", "cornell_c1_256", "cornell_preset_sphere_192", "zfight_96", "dragon_standin_c3_160x90",
+                                  "cornell_inside_128"])
+def test_eight_lanes_per_ray_give_the_same_frame(rtb, gpu_ctx, name):
+    """The bounce levels traced with one lane per ray through the binary tree and with eight lanes per ray through the 8-wide tree
+    (rt_set_wide; k_extend_wide, k_shadow_point_wide) find the same hits bit for bit — same triangle arithmetic, same tie rule (zfight_96:
+    coplanar triangles) — so ray counts are equal and colours agree to summation order; both against the golden frame.  Forced on for every
+    level >= 1 here; on its own the library picks it per level for queues that were small in the previous frame."""
+    g = Golden(name)
+    if not g.geometry_ok:
+        pytest.skip("stand-in geometry differs on this host's numpy")
+    gpu_ctx.upload_scene(g.scene)
+    out = []
+    try:
+        gpu_ctx.set_paths(0)
+        for mode in (0, 1):
+            gpu_ctx.set_wide(mode)
+            rgb, ids, t, st = gpu_ctx.render(g.camera(), g.params(), want_ids=True)
+            _check_against_golden(g, rgb, ids, t, st, f"{name}/wide={mode}")
+            out.append((rgb, st))
+    finally:
+        gpu_ctx.set_wide(-1)
+        gpu_ctx.set_paths(-1)
+    assert np.abs(out[0][0] - out[1][0]).max() <= 1e-6
+    assert (out[0][1].primary_rays, out[0][1].shadow_queries, out[0][1].secondary_rays) == (out[1][1].primary_rays, out[1][1].shadow_queries, out[1][1].secondary_rays)
+
+
+def test_wide_tree_answers_like_the_binary_one(rtb, gpu_ctx):
+    """rt_intersect through the 8-wide tree (use_bvh = 2, eight lanes per ray) against the binary tree on incoherent rays that start on the
+    surface: ids and t bit for bit."""
+    from rtb200 import standin
+    sc = standin.dragon_standin_scene()
+    gpu_ctx.upload_scene(sc)
+    rng = np.random.default_rng(11)
+    n = 50000
+    tri = rng.integers(0, sc.n_tris, n)
+    w = rng.dirichlet((1, 1, 1), n).astype(np.float32)
+    p = (sc.pos.reshape(-1, 3, 3)[tri] * w[..., None]).sum(1)
+    d = rng.standard_normal((n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([p + 0.01 * d, d], 1).astype(np.float32)
+    ids2, t2 = gpu_ctx.intersect(rays, use_bvh=True)
+    ids8, t8 = np.empty(n, np.int32), np.empty(n, np.float32)
+    assert rtb.lib().rt_intersect(gpu_ctx._h, rays.ctypes.data, n, 2, ids8.ctypes.data, t8.ctypes.data) == 0
+    assert np.array_equal(ids2, ids8) and bits_equal(t2, t8) and (ids2 >= 0).mean() > 0.3
+
+
 def test_queue_overflow_is_clean_and_retried(rtb, gpu_ctx):
     """A wavefront queue that overflows (views dominated by dielectrics or glossy surfaces can outgrow any fixed head-room) must end
     the frame with RT_ERR_OVERFLOW and nothing else: consumers clamp their item counts to the queues' capacities and the rest of

@@ -24,6 +24,8 @@ def frames(ctx, cam, prm, n=12):
 def main():
     which = sys.argv[1:] or ["c3"]
     ctx = rtb200.Context(0)
+    if os.environ.get("AB_WIDE"):
+        ctx.set_wide(int(os.environ["AB_WIDE"]))
     cam = rtb200.make_camera()
     out = [os.path.basename(os.environ.get("RTB200_LIB", "default"))]
     bvh = {"lbvh": rtb200.BVH_LBVH_DEVICE, "ploc": rtb200.BVH_PLOC_DEVICE}.get(os.environ.get("AB_BVH"), rtb200.BVH_SAH_HOST)
