@@ -88,7 +88,7 @@ struct rt_ctx {
     float4* wide_nodes = nullptr; // 4-wide tree collapsed from the builder's binary one (RT_BVH_WIDE builds)
     DevBuf<float4> d_wide8;       // 8-wide tree for the eight-lanes-per-ray kernels of small queues (rt_wide8.cu); built for scenes of up to 2^22 triangles
     int wide8_root = 0, wide8_depth = 0;
-    bool wide8_built = false;
+    bool wide8_built = false, wide8_tried = false;
     int wide_mode = -1;           // rt_set_wide: -1 automatic (levels whose queues were small in the previous frame), 0 never, 1 every level >= 1
     // queue fills per lane and bounce level of the previous frame (Counters::level_ext / level_sh) and what that frame looked like
     unsigned hist_ext[kMaxLanes][kLevelHistory] = {}, hist_sh[kMaxLanes][kLevelHistory] = {};
@@ -682,6 +682,36 @@ struct HostTarget {
     bool early_background = false;
 };
 
+// The 8-wide tree beside the binary one (rt_wide8.cu), collapsed on the host from a copy of the binary nodes: 4.6 ms for the 87 K-triangle
+// stand-in.  Built when a frame first asks for the eight-lanes-per-ray kernels, for scenes of up to 2^22 triangles (larger scenes do not
+// have small queues at the frame sizes they are rendered at, and a host pass over their nodes would take seconds).
+int ensure_wide8(rt_ctx* ctx)
+{
+    if (ctx->wide8_tried)
+        return RT_OK;
+    ctx->wide8_tried = true;
+    static const bool wide8_off = [] {
+        const char* e = std::getenv("RTB200_WIDE8");
+        return e && e[0] == '0';
+    }();
+    if (wide8_off || ctx->n_tris > (1ll << 22) || RT_BVH_WIDE || !ctx->bvh_built)
+        return RT_OK;
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<float4> h2(2 * (size_t)ctx->n_nodes), h8;
+    CK(cudaMemcpyAsync(h2.data(), ctx->nodes, h2.size() * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    build_wide8_host(h2.data(), ctx->n_nodes, ctx->root_entry, h8, ctx->wide8_root, ctx->wide8_depth);
+    CK(ctx->d_wide8.ensure(std::max<size_t>(h8.size(), 16)));
+    if (!h8.empty())
+        CK(cudaMemcpyAsync(ctx->d_wide8.p, h8.data(), h8.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->wide8_built = !h8.empty() && 7 * ctx->wide8_depth + 1 < 64; // (a step pushes up to 7 entries on the 64-entry group stack)
+    if (std::getenv("RTB200_TRACE_BUILD"))
+        std::fprintf(stderr, "[build] 8-wide tree: %zu nodes, depth %d, %.2f ms (copy back, collapse on the host, upload)\n", h8.size() / 16, ctx->wide8_depth,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    return RT_OK;
+}
+
 // Enqueue one frame.  `out`: float4 framebuffer (Screen layout), maybe on a peer GPU.  The frame starts and ends on the
 // context's stream; in between, its batches run on the lanes' own streams.
 constexpr int kBandGridMult = 4;
@@ -791,8 +821,20 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
     const unsigned long long signature = ((unsigned long long)fp.W << 44) ^ ((unsigned long long)fp.H << 28) ^ ((unsigned long long)fp.spp << 20)
         ^ ((unsigned long long)fp.world << 12) ^ ((unsigned long long)fp.rank << 4) ^ (unsigned long long)fp.max_level ^ ((unsigned long long)plan.size() << 56)
         ^ ((unsigned long long)fp.n_point << 50);
-    const bool wide_usable = ctx->wide8_built && ctx->wide_mode != 0 && !ctx->counters_enabled && !fp.exhaustive && ctx->overlap;
+    bool wide_usable = ctx->wide_mode != 0 && !ctx->counters_enabled && !fp.exhaustive && ctx->overlap && fp.max_level >= 1;
     const bool wide_hist = wide_usable && ctx->hist_valid && ctx->hist_signature == signature && plan.size() <= (size_t)lanes_wanted;
+    if (wide_usable && !ctx->wide8_tried) { // the first frame that could use the 8-wide tree builds it
+        bool wanted = ctx->wide_mode == 1;
+        for (int l = 0; wide_hist && l < lanes_wanted && !wanted; l++)
+            for (int lv = 1; lv < kLevelHistory && lv <= fp.max_level; lv++)
+                wanted = wanted || (long long)ctx->hist_ext[l][lv] <= wide_max_rays;
+        if (wanted) {
+            int rc = ensure_wide8(ctx);
+            if (rc)
+                return rc;
+        }
+    }
+    wide_usable = wide_usable && ctx->wide8_built;
     auto wide_for = [&](int lane, int level, bool shadow) {
         if (!wide_usable || level < (shadow ? 0 : 1))
             return false;
@@ -1529,26 +1571,9 @@ int rt_build_bvh(rt_ctx* ctx, int mode)
         }
     }
 #endif
-    ctx->wide8_built = false;
+    ctx->wide8_built = false; // the 8-wide tree of this scene is collapsed when a frame first wants it (ensure_wide8)
+    ctx->wide8_tried = false;
     ctx->hist_valid = false;
-    const double t_wide0 = build_ms();
-    static const bool wide8_off = [] {
-        const char* e = std::getenv("RTB200_WIDE8");
-        return e && e[0] == '0';
-    }();
-    if (!wide8_off && ctx->n_tris <= (1ll << 22) && !RT_BVH_WIDE) { // the 8-wide tree beside the binary one: collapsed on the host (a few ms for 10^5 triangles)
-        std::vector<float4> h2(2 * (size_t)ctx->n_nodes), h8;
-        CK(cudaMemcpyAsync(h2.data(), ctx->nodes, h2.size() * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        build_wide8_host(h2.data(), ctx->n_nodes, ctx->root_entry, h8, ctx->wide8_root, ctx->wide8_depth);
-        CK(ctx->d_wide8.ensure(std::max<size_t>(h8.size(), 16)));
-        if (!h8.empty())
-            CK(cudaMemcpyAsync(ctx->d_wide8.p, h8.data(), h8.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        ctx->wide8_built = !h8.empty() && 7 * ctx->wide8_depth + 1 < 64; // (a step pushes up to 7 entries on the 64-entry group stack)
-        if (trace_build)
-            std::fprintf(stderr, "[build] 8-wide tree: %zu nodes, depth %d, %.2f ms (copy back, collapse on the host, upload)\n", h8.size() / 16, ctx->wide8_depth, build_ms() - t_wide0);
-    }
     const double t_tree = build_ms();
     {
         const SceneDev sd = ctx->scene_dev();
@@ -2377,6 +2402,9 @@ int rt_intersect(rt_ctx* ctx, const float* rays, int64_t n_rays, int use_bvh, in
     s_int.tie_by_id = use_bvh ? 0 : 1;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     if (use_bvh == 2) { // experiment: the 8-wide tree, eight lanes per ray
+        rc = ensure_wide8(ctx);
+        if (rc)
+            return rc;
         if (!ctx->wide8_built)
             return fail(RT_ERR_INVALID, "rt_intersect: no 8-wide tree for this scene");
         launch_intersect_wide(ctx->stream, ctx->sm_count, s_int, ctx->d_wide8.p, ctx->wide8_root, ctx->rays_in.p, (long long)n_rays, ctx->out_id.p, ctx->out_t.p);
