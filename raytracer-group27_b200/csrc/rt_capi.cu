@@ -89,6 +89,7 @@ struct rt_ctx {
     DevBuf<float4> d_wide8;       // 8-wide tree for the eight-lanes-per-ray kernels of small queues (rt_wide8.cu); built for scenes of up to 2^22 triangles
     int wide8_root = 0, wide8_depth = 0;
     bool wide8_built = false, wide8_tried = false;
+    BuildScratch build_scratch;   // arena of the device builder, kept between builds (up to 1 GB)
     int wide_mode = -1;           // rt_set_wide: -1 automatic (levels whose queues were small in the previous frame), 0 never, 1 every level >= 1
     // queue fills per lane and bounce level of the previous frame (Counters::level_ext / level_sh) and what that frame looked like
     unsigned hist_ext[kMaxLanes][kLevelHistory] = {}, hist_sh[kMaxLanes][kLevelHistory] = {};
@@ -1271,6 +1272,9 @@ int rt_destroy(rt_ctx* ctx)
     ctx->row_flags.release();
     ctx->fb_plain.release();
     ctx->d_wide8.release();
+    cudaFree(ctx->build_scratch.base);
+    if (ctx->build_scratch.host_word)
+        cudaFreeHost(ctx->build_scratch.host_word);
     if (ctx->lbvh_nodes)
         cudaFree(ctx->lbvh_nodes);
     if (ctx->lbvh_perm)
@@ -1517,7 +1521,14 @@ int rt_build_bvh(rt_ctx* ctx, int mode)
         const char* err = nullptr;
         int built = 2;
         if (mode == RT_BVH_PLOC_DEVICE) {
-            built = build_bvh_ploc_device(ctx->stream, ctx->d_pos.p, ctx->n_tris, pad, &d, &err);
+            if (!ctx->build_scratch.host_word)
+                CK(cudaMallocHost(&ctx->build_scratch.host_word, sizeof(unsigned long long)));
+            built = build_bvh_ploc_device(ctx->stream, ctx->d_pos.p, ctx->n_tris, pad, &d, &err, &ctx->build_scratch);
+            if (ctx->build_scratch.capacity > ((size_t)1 << 30)) { // a 44 M-triangle scene's 12 GB of scratch are not kept
+                cudaFree(ctx->build_scratch.base);
+                ctx->build_scratch.base = nullptr;
+                ctx->build_scratch.capacity = 0;
+            }
             if (built == 1)
                 return fail(RT_ERR_CUDA, std::string("rt_build_bvh (PLOC): ") + (err ? err : "failed"));
             if (built == 0 && d.depth >= kStackDepth) { // agglomeration does not bound the depth; the Morton hierarchy does (64-bit keys)

@@ -59,7 +59,13 @@ int build_bvh_lbvh_device(cudaStream_t st, const float* d_pos, long long n_tris,
 // Device builder of SAH quality (rt_ploc.cu): Morton order -> parallel locally-ordered clustering (mutual nearest neighbours by
 // merged surface area) -> depth-first leaf order -> leaf collapse.  Same outputs.  Returns 2 for scenes of at most 4 triangles
 // (use the LBVH path, which emits the single leaf).
-int build_bvh_ploc_device(cudaStream_t st, const float* d_pos, long long n_tris, float pad, DeviceBvh* out, const char** err);
+// scratch: the caller's reusable build arena (grown when too small) and one pinned host word, so that a rebuild allocates nothing but its outputs.
+struct BuildScratch {
+    char* base = nullptr;
+    size_t capacity = 0;
+    unsigned long long* host_word = nullptr; // pinned
+};
+int build_bvh_ploc_device(cudaStream_t st, const float* d_pos, long long n_tris, float pad, DeviceBvh* out, const char** err, BuildScratch* scratch);
 
 // Screen post-processing (rt_post.cu): float4 images in the Screen layout.  option / gauss follow rt_b200.h's RT_FILTER_* / RT_KERNEL_*.
 void launch_post_light(cudaStream_t st, int sm_count, const float4* img, float4* light, size_t n);

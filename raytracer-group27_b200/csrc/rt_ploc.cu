@@ -505,11 +505,20 @@ __global__ void k_ploc_emit(int n, const int* __restrict__ left, const int* __re
 struct Scratch {
     char* base = nullptr;
     size_t capacity = 0, used = 0;
-    ~Scratch() { cudaFree(base); }
-    cudaError_t reserve(size_t bytes)
+    cudaError_t reserve(size_t bytes, BuildScratch* keep) // the caller's arena, grown if it is too small
     {
-        capacity = bytes;
-        return cudaMalloc(&base, bytes);
+        if (keep->capacity < bytes) {
+            cudaFree(keep->base);
+            keep->base = nullptr;
+            keep->capacity = 0;
+            const cudaError_t e = cudaMalloc(&keep->base, bytes);
+            if (e != cudaSuccess)
+                return e;
+            keep->capacity = bytes;
+        }
+        base = keep->base;
+        capacity = keep->capacity;
+        return cudaSuccess;
     }
     template <typename T> T* alloc(size_t n, cudaError_t& e)
     {
@@ -530,7 +539,7 @@ struct Scratch {
 
 // Returns 0 on success, 1 on a CUDA error (*err set), 2 when the scene is too small for this builder (the caller uses the LBVH
 // path, which handles single-leaf scenes).
-int build_bvh_ploc_device(cudaStream_t st, const float* d_pos, long long n_tris, float pad, DeviceBvh* out, const char** err)
+int build_bvh_ploc_device(cudaStream_t st, const float* d_pos, long long n_tris, float pad, DeviceBvh* out, const char** err, BuildScratch* keep)
 {
     const int n = (int)n_tris;
     if (n <= kLeafCollapse)
@@ -550,7 +559,7 @@ int build_bvh_ploc_device(cudaStream_t st, const float* d_pos, long long n_tris,
     tmp_scan = std::max(tmp_scan, tmp_scan2);
     Scratch sc;
     if (e == cudaSuccess) // 292 bytes of arrays per triangle (listed below) + the library's temporaries + alignment slack
-        e = sc.reserve((size_t)n * 300 + std::max(tmp_sort, tmp_scan) + (64 << 10));
+        e = sc.reserve((size_t)n * 300 + std::max(tmp_sort, tmp_scan) + (64 << 10), keep);
     float4* tlo = sc.alloc<float4>(n, e);
     float4* thi = sc.alloc<float4>(n, e);
     Bounds* bounds = sc.alloc<Bounds>(1, e);
@@ -605,9 +614,7 @@ int build_bvh_ploc_device(cudaStream_t st, const float* d_pos, long long n_tris,
         t_sorted = since();
     }
     int m = n, next_id = n - 2, cur = 0, iterations = 0;
-    unsigned long long* h_totals = nullptr; // pinned: one 8-byte read-back per iteration
-    if (cudaMallocHost(&h_totals, sizeof(unsigned long long)) != cudaSuccess)
-        return fail(cudaGetLastError());
+    unsigned long long* h_totals = keep->host_word; // pinned: one 8-byte read-back per iteration
     while (m > kTopClusters) {
         const int g = (m + 1 + blk - 1) / blk;
         k_ploc_nearest<<<(m + kNnBlock - 1) / kNnBlock, kNnBlock, 0, st>>>(clo[cur], chi[cur], m, nn);
@@ -617,13 +624,10 @@ int build_bvh_ploc_device(cudaStream_t st, const float* d_pos, long long n_tris,
             right, parent, count, height, blo, bhi);
         cudaMemcpyAsync(h_totals, ranks + m, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
         e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) {
-            cudaFreeHost(h_totals);
+        if (e != cudaSuccess)
             return fail(e);
-        }
         const int merged = (int)(*h_totals >> 32), stayed = (int)(*h_totals & 0xffffffffull);
         if (merged <= 0 || stayed != m - merged) { // the closest pair of the whole array is always mutual
-            cudaFreeHost(h_totals);
             cudaFree(perm);
             *err = "PLOC iteration made no progress";
             return 1;
@@ -633,7 +637,6 @@ int build_bvh_ploc_device(cudaStream_t st, const float* d_pos, long long n_tris,
         cur ^= 1;
         iterations++;
     }
-    cudaFreeHost(h_totals);
     t_clustered = since();
     // ---- top levels over the m clusters that are left: internal nodes 0 .. m-2 remain to be made (next_id == m - 2) ----
     if (next_id != m - 2) {
@@ -714,7 +717,7 @@ int build_bvh_ploc_device(cudaStream_t st, const float* d_pos, long long n_tris,
         return fail(e);
     }
     if (trace)
-        std::fprintf(stderr, "[ploc] order + emit %.2f ms, total %.2f ms (scratch is freed after this)\n", since() - t_top, since());
+        std::fprintf(stderr, "[ploc] order + emit %.2f ms, total %.2f ms (the scratch arena is kept by the caller)\n", since() - t_top, since());
     out->nodes = nodes;
     out->perm = perm;
     out->n_nodes = n_nodes;
