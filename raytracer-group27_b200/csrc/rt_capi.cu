@@ -716,7 +716,8 @@ int ensure_wide8(rt_ctx* ctx)
 // Enqueue one frame.  `out`: float4 framebuffer (Screen layout), maybe on a peer GPU.  The frame starts and ends on the
 // context's stream; in between, its batches run on the lanes' own streams.
 constexpr int kBandGridMult = 4;
-constexpr long long kWideMaxRays = 40000; // queues of up to this many rays (in the previous frame) are traced with eight lanes per ray
+constexpr long long kWideMaxRays = 40000;       // extend queues of up to this many rays (in the previous frame) are traced with eight lanes per ray
+constexpr long long kWideMaxShadowRays = 80000; // the same for the point-light shadow queues
 constexpr long long kPathsMaxPrimaryRays = 1 << 17; // batches of up to 128 K primary rays trace their bounce levels as whole paths
 
 int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_ids, unsigned batch_rays, const HostTarget* host)
@@ -819,6 +820,10 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
         const char* e = std::getenv("RTB200_WIDE_MAX_RAYS");
         return e ? std::atoll(e) : (long long)kWideMaxRays;
     }();
+    static const long long wide_max_shadow = [] { // any-hit queries need no ordering of the children: the wide form stays ahead for larger queues
+        const char* e = std::getenv("RTB200_WIDE_MAX_SHADOW");
+        return e ? std::atoll(e) : (long long)kWideMaxShadowRays;
+    }();
     const unsigned long long signature = ((unsigned long long)fp.W << 44) ^ ((unsigned long long)fp.H << 28) ^ ((unsigned long long)fp.spp << 20)
         ^ ((unsigned long long)fp.world << 12) ^ ((unsigned long long)fp.rank << 4) ^ (unsigned long long)fp.max_level ^ ((unsigned long long)plan.size() << 56)
         ^ ((unsigned long long)fp.n_point << 50);
@@ -845,7 +850,7 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
             return true;
         if (!wide_hist || level >= kLevelHistory)
             return false;
-        return (long long)(shadow ? ctx->hist_sh[lane][level] : ctx->hist_ext[lane][level]) <= wide_max_rays;
+        return shadow ? (long long)ctx->hist_sh[lane][level] <= wide_max_shadow : (long long)ctx->hist_ext[lane][level] <= wide_max_rays;
     };
     ctx->frame_signature = signature;
     const size_t n_batches = plan.size();

@@ -33,7 +33,10 @@ __device__ __forceinline__ void trace_wide(const SceneDev& s, const float4* __re
     while (cur != kTravDone) {
         if (cur >= 0) { // node: every lane tests one child
             const float4* np = wide + 16 * (size_t)cur + 2 * sub;
-            const float4 a0 = __ldg(np), a1 = __ldg(np + 1);
+            float4 a0, a1; // this lane's child: one 32-byte load
+            asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=f"(a0.x), "=f"(a0.y), "=f"(a0.z), "=f"(a0.w), "=f"(a1.x), "=f"(a1.y), "=f"(a1.z), "=f"(a1.w)
+                         : "l"(np));
             const float nx = fmaf(a0.x, nlx, fmaf(a1.x, nhx, -oix)), fx = fmaf(a0.x, nhx, fmaf(a1.x, nlx, -oix));
             const float ny = fmaf(a0.y, nly, fmaf(a1.y, nhy, -oiy)), fy = fmaf(a0.y, nhy, fmaf(a1.y, nly, -oiy));
             const float nz = fmaf(a0.z, nlz, fmaf(a1.z, nhz, -oiz)), fz = fmaf(a0.z, nhz, fmaf(a1.z, nlz, -oiz));
@@ -45,11 +48,16 @@ __device__ __forceinline__ void trace_wide(const SceneDev& s, const float4* __re
                 continue;
             }
             const int n = __popc(hm);
-            int rank = 0; // position of this child among the hit ones, nearest first (ties: lower child index)
+            int rank; // position of this child among the hit ones: nearest first (ties: lower child index); any order will do for an any-hit query
+            if (ANYHIT) {
+                rank = __popc(hm & ((1u << sub) - 1u));
+            } else {
+                rank = 0;
 #pragma unroll
-            for (int j = 0; j < kGroup; j++) {
-                const float tj = __shfl_sync(gmask, tn, (int)gbase + j);
-                rank += (((hm >> j) & 1u) && (tj < tn || (tj == tn && j < sub))) ? 1 : 0;
+                for (int j = 0; j < kGroup; j++) {
+                    const float tj = __shfl_sync(gmask, tn, (int)gbase + j);
+                    rank += (((hm >> j) & 1u) && (tj < tn || (tj == tn && j < sub))) ? 1 : 0;
+                }
             }
             const int entry = __float_as_int(a0.w);
             const unsigned first = (__ballot_sync(gmask, hit && rank == 0) >> gbase) & 0xffu;
