@@ -716,7 +716,8 @@ int ensure_wide8(rt_ctx* ctx)
 // Enqueue one frame.  `out`: float4 framebuffer (Screen layout), maybe on a peer GPU.  The frame starts and ends on the
 // context's stream; in between, its batches run on the lanes' own streams.
 constexpr int kBandGridMult = 4;
-constexpr long long kWideMaxRays = 40000;       // extend queues of up to this many rays (in the previous frame) are traced with eight lanes per ray
+constexpr long long kWideMaxRays = 130000;      // extend queues of up to this many rays (in the previous frame) are traced with eight lanes per ray ...
+constexpr long long kWideMaxRaysAlone = 60000;  // ... and only up to this many when the shadow kernel running beside them is a one-lane-per-ray one
 constexpr long long kWideMaxShadowRays = 80000; // the same for the point-light shadow queues
 constexpr long long kPathsMaxPrimaryRays = 1 << 17; // batches of up to 128 K primary rays trace their bounce levels as whole paths
 
@@ -820,6 +821,10 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
         const char* e = std::getenv("RTB200_WIDE_MAX_RAYS");
         return e ? std::atoll(e) : (long long)kWideMaxRays;
     }();
+    static const long long wide_max_rays_alone = [] {
+        const char* e = std::getenv("RTB200_WIDE_MAX_RAYS_ALONE");
+        return e ? std::atoll(e) : (long long)kWideMaxRaysAlone;
+    }();
     static const long long wide_max_shadow = [] { // any-hit queries need no ordering of the children: the wide form stays ahead for larger queues
         const char* e = std::getenv("RTB200_WIDE_MAX_SHADOW");
         return e ? std::atoll(e) : (long long)kWideMaxShadowRays;
@@ -850,7 +855,14 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
             return true;
         if (!wide_hist || level >= kLevelHistory)
             return false;
-        return shadow ? (long long)ctx->hist_sh[lane][level] <= wide_max_shadow : (long long)ctx->hist_ext[lane][level] <= wide_max_rays;
+        if (shadow)
+            return (long long)ctx->hist_sh[lane][level] <= wide_max_shadow;
+        // An extend kernel runs beside the shadow kernel of the level before.  Next to a one-lane-per-ray shadow kernel, whose persistent
+        // blocks fill the SMs until its queue is drained, the eight-lane form only pays for really small queues; next to an eight-lane one
+        // it pays up to the size where its throughput loses (1/4 share of C3, level 2: 88 K rays each, shadow one lane per ray: 0.89 ms
+        // with the extend kernel one lane per ray, 0.97 with eight).
+        const bool beside_wide_shadow = fp.n_point == 0 || (!fp.any_transparent && (long long)ctx->hist_sh[lane][level - 1] <= wide_max_shadow);
+        return (long long)ctx->hist_ext[lane][level] <= (beside_wide_shadow ? wide_max_rays : wide_max_rays_alone);
     };
     ctx->frame_signature = signature;
     const size_t n_batches = plan.size();

@@ -4,6 +4,9 @@
 
 namespace rtb {
 
+#ifndef RT_WIDE_NEAREST_ONLY
+#define RT_WIDE_NEAREST_ONLY 1
+#endif
 constexpr int kGroup = 8;                 // lanes per ray
 constexpr int kWideBlock = 128;           // 16 groups per block
 constexpr int kWideStack = 64;            // entries per group (shared memory); a step pushes at most 7, the tree is at most 8 levels deep for 2^22 triangles
@@ -51,6 +54,15 @@ __device__ __forceinline__ void trace_wide(const SceneDev& s, const float4* __re
             int rank; // position of this child among the hit ones: nearest first (ties: lower child index); any order will do for an any-hit query
             if (ANYHIT) {
                 rank = __popc(hm & ((1u << sub) - 1u));
+#if RT_WIDE_NEAREST_ONLY
+            } else if (true) { // only the nearest child is singled out (one REDUX on (entry distance, child index) keys), the others keep child order:
+                               // 18 % faster than ranking all hit children through eight shuffles (tools/wide8_probe.py: 16 K rays 81 -> 67 us, 1 M 1640 -> 1344 us)
+                const unsigned key = hit ? ((__float_as_uint(tn) & ~7u) | (unsigned)sub) : 0xffffffffu;
+                const unsigned kmin = __reduce_min_sync(gmask, key);
+                const int nearest = (int)(kmin & 7u);
+                const int below = __popc(hm & ((1u << sub) - 1u)); // hit children with a lower index
+                rank = sub == nearest ? 0 : below + (sub < nearest ? 1 : 0);
+#endif
             } else {
                 rank = 0;
 #pragma unroll
