@@ -230,8 +230,8 @@ int rt_set_paths(rt_ctx* ctx, int mode);
  * binary tree: best throughput, what a full queue wants.  Eight lanes per ray through an 8-wide tree (collapsed from the binary one
  * at rt_build_bvh for scenes of up to 2^22 triangles): 2.3 times shorter a chain for the longest ray, which is what the kernel of a
  * SMALL queue waits for (deep bounce levels, one GPU's share of a sharded frame), at half the throughput.  Same hits bit for bit.
- * mode: -1 automatic (per level: eight lanes when that level's queue held at most 40 000 rays — 80 000 shadow records — in the
- * previous frame of the same shape), 0 never, 1 for every level >= 1. */
+ * mode: -1 automatic (per level: eight lanes when that level's queue held at most 80 000 shadow records / 130 000 rays — 60 000
+ * beside a one-lane-per-ray shadow kernel — in the previous frame of the same shape), 0 never, 1 for every level >= 1. */
 int rt_set_wide(rt_ctx* ctx, int mode);
 /* Measurement aid (bench.py's roofline): the rate at which this device issues un-fused FP32 multiplies and adds — the instruction
  * mix of the path's parity-critical geometry code — in 1e9 lane-instructions per second, from a microbenchmark kernel (best of 3). */
