@@ -227,8 +227,8 @@ int rt_stage_times(rt_ctx* ctx, float* ms /* [RT_STAGE_COUNT] */, int* launches 
  * way (per-pixel sums in a different order). */
 int rt_set_paths(rt_ctx* ctx, int mode);
 /* Traversal form of the extend and (opaque scenes) point-light shadow kernels of the levels >= 1.  One lane per ray through the
- * binary tree: best throughput, what a full queue wants.  Eight lanes per ray through an 8-wide tree (collapsed from the binary one
- * at rt_build_bvh for scenes of up to 2^22 triangles): 2.3 times shorter a chain for the longest ray, which is what the kernel of a
+ * binary tree: best throughput, what a full queue wants.  Eight lanes per ray through an 8-wide tree (collapsed from the binary one,
+ * on the device, when a frame first needs it, for scenes of up to 2^22 triangles): 2.3 times shorter a chain for the longest ray, which is what the kernel of a
  * SMALL queue waits for (deep bounce levels, one GPU's share of a sharded frame), at half the throughput.  Same hits bit for bit.
  * mode: -1 automatic (per level: eight lanes when that level's queue held at most 80 000 shadow records / 130 000 rays — 60 000
  * beside a one-lane-per-ray shadow kernel — in the previous frame of the same shape), 0 never, 1 for every level >= 1. */

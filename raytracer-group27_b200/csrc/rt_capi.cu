@@ -86,7 +86,7 @@ struct rt_ctx {
     float4* lbvh_nodes = nullptr; // owned when the device builder allocated them
     int* lbvh_perm = nullptr;
     float4* wide_nodes = nullptr; // 4-wide tree collapsed from the builder's binary one (RT_BVH_WIDE builds)
-    DevBuf<float4> d_wide8;       // 8-wide tree for the eight-lanes-per-ray kernels of small queues (rt_wide8.cu); built for scenes of up to 2^22 triangles
+    float4* wide8_nodes = nullptr; // 8-wide tree for the eight-lanes-per-ray kernels of small queues (rt_wide8.cu), collapsed from the binary one at first need
     int wide8_root = 0, wide8_depth = 0;
     bool wide8_built = false, wide8_tried = false;
     BuildScratch build_scratch;   // arena of the device builder, kept between builds (up to 1 GB)
@@ -683,9 +683,9 @@ struct HostTarget {
     bool early_background = false;
 };
 
-// The 8-wide tree beside the binary one (rt_wide8.cu), collapsed on the host from a copy of the binary nodes: 4.6 ms for the 87 K-triangle
-// stand-in.  Built when a frame first asks for the eight-lanes-per-ray kernels, for scenes of up to 2^22 triangles (larger scenes do not
-// have small queues at the frame sizes they are rendered at, and a host pass over their nodes would take seconds).
+// The 8-wide tree beside the binary one (rt_wide8.cu), collapsed from it on the device (two span walks per binary node, then one launch
+// per level of the wide tree).  Built when a frame first asks for the eight-lanes-per-ray kernels, for scenes of up to 2^22 triangles
+// (larger scenes do not have small queues at the frame sizes they are rendered at).
 int ensure_wide8(rt_ctx* ctx)
 {
     if (ctx->wide8_tried)
@@ -698,17 +698,16 @@ int ensure_wide8(rt_ctx* ctx)
     if (wide8_off || ctx->n_tris > (1ll << 22) || RT_BVH_WIDE || !ctx->bvh_built)
         return RT_OK;
     const auto t0 = std::chrono::steady_clock::now();
-    std::vector<float4> h2(2 * (size_t)ctx->n_nodes), h8;
-    CK(cudaMemcpyAsync(h2.data(), ctx->nodes, h2.size() * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    build_wide8_host(h2.data(), ctx->n_nodes, ctx->root_entry, h8, ctx->wide8_root, ctx->wide8_depth);
-    CK(ctx->d_wide8.ensure(std::max<size_t>(h8.size(), 16)));
-    if (!h8.empty())
-        CK(cudaMemcpyAsync(ctx->d_wide8.p, h8.data(), h8.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    ctx->wide8_built = !h8.empty() && 7 * ctx->wide8_depth + 1 < 64; // (a step pushes up to 7 entries on the 64-entry group stack)
+    if (ctx->wide8_nodes)
+        cudaFree(ctx->wide8_nodes);
+    ctx->wide8_nodes = nullptr;
+    int n8 = 0;
+    const char* err = nullptr;
+    if (collapse_bvh_wide8_device(ctx->stream, ctx->nodes, ctx->n_nodes, &ctx->wide8_nodes, &n8, &ctx->wide8_root, &ctx->wide8_depth, &err) != 0)
+        return fail(RT_ERR_CUDA, std::string("8-wide tree: ") + (err ? err : "failed"));
+    ctx->wide8_built = n8 > 0 && 7 * ctx->wide8_depth + 1 < 64; // (a step pushes up to 7 entries on the 64-entry group stack)
     if (std::getenv("RTB200_TRACE_BUILD"))
-        std::fprintf(stderr, "[build] 8-wide tree: %zu nodes, depth %d, %.2f ms (copy back, collapse on the host, upload)\n", h8.size() / 16, ctx->wide8_depth,
+        std::fprintf(stderr, "[build] 8-wide tree: %d nodes, depth %d, %.2f ms (collapsed on the device)\n", n8, ctx->wide8_depth,
             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     return RT_OK;
 }
@@ -964,7 +963,7 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
                 SceneDev s_ext = s;
                 s_ext.tie_by_id = fp.tie_by_id; // shadow queries keep the BVH order (shadow.cpp:42)
                 if (wide_for(li, level, false))
-                    launch_extend_wide(st, ctx->sm_count, s_ext, ctx->d_wide8.p, ctx->wide8_root, b, qi, level);
+                    launch_extend_wide(st, ctx->sm_count, s_ext, ctx->wide8_nodes, ctx->wide8_root, b, qi, level);
                 else
                     launch_extend(st, ctx->sm_count, s_ext, ctx->root_entry, fp, b, qi, level, (unsigned)first, ctx->counters_enabled);
             }
@@ -996,7 +995,7 @@ int enqueue_frame(rt_ctx* ctx, const FrameParams& fp_in, float4* out, bool want_
             if (fp.n_point > 0) {
                 StageScope sc(ctx, RT_STAGE_SHADOW_POINT, ss);
                 if (wide_for(li, level, true))
-                    launch_shadow_point_wide(ss, ctx->sm_count, s, ctx->d_wide8.p, ctx->wide8_root, b, level);
+                    launch_shadow_point_wide(ss, ctx->sm_count, s, ctx->wide8_nodes, ctx->wide8_root, b, level);
                 else
                     launch_shadow_point(ss, ctx->sm_count, s, ctx->root_entry, fp, b, level, ctx->counters_enabled);
                 launches++;
@@ -1288,7 +1287,8 @@ int rt_destroy(rt_ctx* ctx)
     ctx->flag.release();
     ctx->row_flags.release();
     ctx->fb_plain.release();
-    ctx->d_wide8.release();
+    if (ctx->wide8_nodes)
+        cudaFree(ctx->wide8_nodes);
     cudaFree(ctx->build_scratch.base);
     if (ctx->build_scratch.host_word)
         cudaFreeHost(ctx->build_scratch.host_word);
@@ -2435,7 +2435,7 @@ int rt_intersect(rt_ctx* ctx, const float* rays, int64_t n_rays, int use_bvh, in
             return rc;
         if (!ctx->wide8_built)
             return fail(RT_ERR_INVALID, "rt_intersect: no 8-wide tree for this scene");
-        launch_intersect_wide(ctx->stream, ctx->sm_count, s_int, ctx->d_wide8.p, ctx->wide8_root, ctx->rays_in.p, (long long)n_rays, ctx->out_id.p, ctx->out_t.p);
+        launch_intersect_wide(ctx->stream, ctx->sm_count, s_int, ctx->wide8_nodes, ctx->wide8_root, ctx->rays_in.p, (long long)n_rays, ctx->out_id.p, ctx->out_t.p);
     } else
         launch_intersect(ctx->stream, ctx->sm_count, s_int, ctx->root_entry, ctx->rays_in.p, (long long)n_rays, use_bvh, ctx->out_id.p,
             ctx->out_t.p, ctx->flag.p);
