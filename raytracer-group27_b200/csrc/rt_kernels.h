@@ -84,9 +84,8 @@ struct WideBvh {
 };
 int collapse_bvh_wide_device(cudaStream_t st, const float4* d_nodes2, int n_nodes2, int root_entry2, WideBvh* out, const char** err);
 
-// EXPERIMENT (rt_wide8.cu): 8-wide tree collapsed on the host from the binary one (16 float4 per node), and rt_intersect through it
-// with eight lanes per ray.
-int build_wide8_host(const float4* nodes2, int n_nodes2, int root_entry2, std::vector<float4>& out, int& root_entry8, int& depth8);
+// rt_wide8.cu: the 8-wide tree (16 float4 per node) collapsed on the device from the binary one, and rt_intersect through it with eight
+// lanes per ray.
 int collapse_bvh_wide8_device(cudaStream_t st, const float4* d_nodes2, int n_nodes2, float4** nodes8, int* n_nodes8, int* root_entry8, int* depth8, const char** err);
 void launch_intersect_wide(cudaStream_t st, int sm_count, const SceneDev& s, const float4* wide, int root_entry, const float* rays, long long n, int* tri_id,
     float* t_out);

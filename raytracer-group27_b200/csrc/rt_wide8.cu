@@ -1,4 +1,4 @@
-// EXPERIMENT (round 2): an 8-wide tree walked by EIGHT LANES PER RAY, for small wavefronts.
+// An 8-wide tree walked by EIGHT LANES PER RAY, for small wavefronts (added in round 2; measurements in profiles/README.md).
 //
 // The per-level kernels of a small wavefront wait for their longest ray: a chain of ~200 dependent node-pair fetches at L2
 // latency plus up to ~90 triangle tests one after the other (profiles/README.md, round 2).  Eight lanes per ray shorten that
@@ -6,9 +6,8 @@
 // pairs), a leaf's triangles (up to eight) are tested side by side, and the four rays of a warp diverge only as groups.  The
 // price is throughput — eight lanes do what one lane did — so this form is for the queues that cannot fill the GPU anyway.
 //
-// The 8-wide tree is collapsed, on the device (collapse_bvh_wide8_device; build_wide8_host is the same procedure on the host, kept as
-// the reference the device version was checked against), from the binary one the builders emit (boxes copied, never recomputed: the
-// conservative padding carries over): a node takes the two children of a binary node and keeps replacing its largest inner child by that child's two
+// The 8-wide tree is collapsed, on the device (collapse_bvh_wide8_device), from the binary one the builders emit (boxes copied, never
+// recomputed: the conservative padding carries over): a node takes the two children of a binary node and keeps replacing its largest inner child by that child's two
 // until it has eight; binary subtrees of at most eight triangles become one leaf (their triangles are contiguous in leaf order).
 // Node layout: child k at float4 [2k] = {lo.xyz, entry}, [2k + 1] = {hi.xyz, -}; 256 bytes per node; entry >= 0: node index,
 // < 0: leaf ~((first << 3) | (count - 1)) like the binary tree's; a missing child is a box turned inside out.
@@ -18,117 +17,9 @@
 #include <algorithm>
 #include <cfloat>
 #include <climits>
-#include <cstring>
-#include <vector>
+#include <utility>
 
 namespace rtb {
-
-namespace {
-
-struct Bin2 { // host view of the binary tree
-    const float4* n;
-    int entry(int i) const
-    {
-        int e;
-        std::memcpy(&e, &n[2 * (size_t)i].w, 4);
-        return e;
-    }
-    float area(int i) const
-    {
-        const float4 lo = n[2 * (size_t)i], hi = n[2 * (size_t)i + 1];
-        const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
-        return dx * dy + dy * dz + dz * dx;
-    }
-};
-
-// triangles below binary node i and the first of them (leaf order is depth first, so a subtree's triangles are contiguous)
-void subtree_span(const Bin2& b, int i, std::vector<int>& count, std::vector<int>& first)
-{
-    // iterative post-order
-    std::vector<std::pair<int, int>> st { { i, 0 } };
-    while (!st.empty()) {
-        auto [v, phase] = st.back();
-        st.pop_back();
-        const int e = b.entry(v);
-        if (e < 0) {
-            const int enc = ~e;
-            count[v] = (enc & 7) + 1;
-            first[v] = enc >> 3;
-        } else if (phase == 0) {
-            st.push_back({ v, 1 });
-            st.push_back({ e, 0 });
-            st.push_back({ e + 1, 0 });
-        } else {
-            count[v] = count[e] + count[e + 1];
-            first[v] = std::min(first[e], first[e + 1]);
-        }
-    }
-}
-
-} // namespace
-
-int build_wide8_host(const float4* nodes2, int n_nodes2, int root_entry2, std::vector<float4>& out, int& root_entry8, int& depth8)
-{
-    Bin2 b { nodes2 };
-    std::vector<int> count((size_t)n_nodes2, 0), first((size_t)n_nodes2, 0);
-    subtree_span(b, 0, count, first);
-    auto leaf_entry = [&](int v) { return ~((first[v] << 3) | (count[v] - 1)); };
-    out.clear();
-    depth8 = 1;
-    if (count[0] <= 8) { // the whole scene is one leaf
-        root_entry8 = leaf_entry(0);
-        return 0;
-    }
-    struct Item {
-        int bin, dst, depth;
-    };
-    std::vector<Item> work { { 0, 0, 1 } };
-    out.resize(16);
-    root_entry8 = 0;
-    while (!work.empty()) {
-        const Item it = work.back();
-        work.pop_back();
-        depth8 = std::max(depth8, it.depth + 1);
-        std::vector<int> kids { b.entry(it.bin), b.entry(it.bin) + 1 };
-        for (;;) { // open the largest child that is still a subtree of more than 8 triangles
-            if ((int)kids.size() >= 8)
-                break;
-            int best = -1;
-            float ba = -1.0f;
-            for (int k = 0; k < (int)kids.size(); k++)
-                if (count[kids[k]] > 8 && b.area(kids[k]) > ba) {
-                    ba = b.area(kids[k]);
-                    best = k;
-                }
-            if (best < 0)
-                break;
-            const int e = b.entry(kids[best]);
-            kids[best] = e;
-            kids.push_back(e + 1);
-        }
-        for (int k = 0; k < 8; k++) {
-            float4 lo = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, 0.0f), hi = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, 0.0f);
-            int entry = INT_MIN;
-            if (k < (int)kids.size()) {
-                const int v = kids[k];
-                lo = nodes2[2 * (size_t)v];
-                hi = nodes2[2 * (size_t)v + 1];
-                if (count[v] <= 8) {
-                    entry = leaf_entry(v);
-                } else {
-                    entry = (int)(out.size() / 16);
-                    out.resize(out.size() + 16);
-                    work.push_back({ v, entry, it.depth + 1 });
-                }
-            }
-            std::memcpy(&lo.w, &entry, 4);
-            out[16 * (size_t)it.dst + 2 * k] = lo;
-            out[16 * (size_t)it.dst + 2 * k + 1] = hi;
-        }
-    }
-    (void)root_entry2;
-    return 0;
-}
 
 namespace {
 
