@@ -318,6 +318,19 @@ int rt_intersect(rt_ctx* ctx, const float* rays, int64_t n_rays, int use_bvh, in
 /* Device time of the traversal kernel of the last rt_intersect (developer aid). */
 float rt_last_intersect_ms(rt_ctx* ctx);
 
+/* ---- the checked build (the GPU counterpart of the reference's sanitizer options, framework/cmake/Sanitizers.cmake:7-37) ----
+ * `make EXTRA=-DRT_CHECKED=1 OUT=librtb200_checked.so BUILD=build_checked` compiles the same kernels with every data-derived index
+ * (BVH node, triangle, traversal-stack slot, 8-wide node and group-stack slot, accumulator / id pixel, framebuffer pixel, texel,
+ * material / light / sphere table entry, ray / shadow / hit queue slot) tested against its bound before the access; a violation is counted and the access goes to
+ * element 0.  rt_checked_build: 1 for such a library, 0 for the default one (RT_GUARD is then the identity, same SASS as without it).
+ * rt_violations: violations since the library was loaded on the context's device, per site in the order above plus queue slots (10 sites; further
+ * entries are zero); all zero from the default build.  Synchronises the device.
+ * rt_violations_selftest: one deliberate violation from each translation unit that counts (site 8, table entry, and site 4, group-stack
+ * slot), so that a test can tell a working counter from a dead one; does nothing in the default build. */
+int rt_checked_build(void);
+int rt_violations(rt_ctx* ctx, unsigned int* counts, int n_counts);
+int rt_violations_selftest(rt_ctx* ctx);
+
 /* ---- OBJ/MTL loading (replaces loadMesh, src/mesh.cpp:58-188; host-only, no GPU needed) ---- */
 typedef struct rt_mesh_soup rt_mesh_soup;
 int rt_load_obj(const char* path, int center_and_normalize, rt_mesh_soup** out);

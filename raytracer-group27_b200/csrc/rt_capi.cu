@@ -87,7 +87,7 @@ struct rt_ctx {
     int* lbvh_perm = nullptr;
     float4* wide_nodes = nullptr; // 4-wide tree collapsed from the builder's binary one (RT_BVH_WIDE builds)
     float4* wide8_nodes = nullptr; // 8-wide tree for the eight-lanes-per-ray kernels of small queues (rt_wide8.cu), collapsed from the binary one at first need
-    int wide8_root = 0, wide8_depth = 0;
+    int wide8_root = 0, wide8_depth = 0, wide8_count = 0;
     bool wide8_built = false, wide8_tried = false;
     BuildScratch build_scratch;   // arena of the device builder, kept between builds (up to 1 GB)
     int wide_mode = -1;           // rt_set_wide: -1 automatic (levels whose queues were small in the previous frame), 0 never, 1 every level >= 1
@@ -231,6 +231,11 @@ struct rt_ctx {
         s.sphere_id_base = (int)user_tris;
         s.n_tris = (int)n_tris;
         s.n_nodes = n_nodes;
+#if RT_CHECKED
+        s.n_wide_nodes = wide8_count;
+        s.n_mats = n_mats;
+        s.n_point_like = n_point;
+#endif
         return s;
     }
 };
@@ -537,6 +542,10 @@ int ensure_lane(rt_ctx* ctx, rt_ctx::Lane& ln, const FrameParams& fp, unsigned b
     b.accum = ctx->accum.p;
     b.prim_id = want_ids ? ctx->prim_id.p : nullptr;
     b.prim_t = want_ids ? ctx->prim_t.p : nullptr;
+#if RT_CHECKED
+    b.accum_pixels = (unsigned)std::max<size_t>((size_t)fp.n_local_tiles * kTilePixels, 1); // what the frame uses of accum / prim_id / prim_t
+    b.hit_capacity = (unsigned)std::min<size_t>(std::max(cap, prim), 0xfffffff0u);
+#endif
     return RT_OK;
 }
 
@@ -705,6 +714,7 @@ int ensure_wide8(rt_ctx* ctx)
     const char* err = nullptr;
     if (collapse_bvh_wide8_device(ctx->stream, ctx->nodes, ctx->n_nodes, &ctx->wide8_nodes, &n8, &ctx->wide8_root, &ctx->wide8_depth, &err) != 0)
         return fail(RT_ERR_CUDA, std::string("8-wide tree: ") + (err ? err : "failed"));
+    ctx->wide8_count = n8;
     ctx->wide8_built = n8 > 0 && 7 * ctx->wide8_depth + 1 < 64; // (a step pushes up to 7 entries on the 64-entry group stack)
     if (std::getenv("RTB200_TRACE_BUILD"))
         std::fprintf(stderr, "[build] 8-wide tree: %d nodes, depth %d, %.2f ms (collapsed on the device)\n", n8, ctx->wide8_depth,
@@ -2435,6 +2445,9 @@ int rt_intersect(rt_ctx* ctx, const float* rays, int64_t n_rays, int use_bvh, in
             return rc;
         if (!ctx->wide8_built)
             return fail(RT_ERR_INVALID, "rt_intersect: no 8-wide tree for this scene");
+#if RT_CHECKED
+        s_int.n_wide_nodes = ctx->wide8_count;
+#endif
         launch_intersect_wide(ctx->stream, ctx->sm_count, s_int, ctx->wide8_nodes, ctx->wide8_root, ctx->rays_in.p, (long long)n_rays, ctx->out_id.p, ctx->out_t.p);
     } else
         launch_intersect(ctx->stream, ctx->sm_count, s_int, ctx->root_entry, ctx->rays_in.p, (long long)n_rays, use_bvh, ctx->out_id.p,
@@ -2453,6 +2466,36 @@ int rt_intersect(rt_ctx* ctx, const float* rays, int64_t n_rays, int use_bvh, in
 }
 
 float rt_last_intersect_ms(rt_ctx* ctx) { return ctx ? ctx->last_intersect_ms : 0.0f; }
+
+int rt_checked_build(void) { return RT_CHECKED ? 1 : 0; }
+
+int rt_violations_selftest(rt_ctx* ctx)
+{
+    int rc = use_device(ctx);
+    if (rc)
+        return rc;
+    provoke_violation_kernels(ctx->stream);
+    provoke_violation_wide8(ctx->stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_violations(rt_ctx* ctx, unsigned int* counts, int n_counts)
+{
+    int rc = use_device(ctx);
+    if (rc)
+        return rc;
+    if (!counts || n_counts < 0)
+        return fail(RT_ERR_INVALID, "rt_violations: bad arguments");
+    CK(cudaDeviceSynchronize());
+    unsigned int all[kChkSites] = {};
+    add_violations_kernels(all);
+    add_violations_wide8(all);
+    for (int k = 0; k < n_counts; k++)
+        counts[k] = k < kChkSites ? all[k] : 0u;
+    return RT_OK;
+}
 
 // ---- OBJ loading: host only ----
 struct rt_mesh_soup {

@@ -146,7 +146,7 @@ __device__ __forceinline__ Shading shading_at(const SceneDev& s, int ti, const f
     Shading sh;
     sh.p = xadd(o, xmul(d, t));
     if (ti <= -2) { // sphere primitive (src/ray_tracing.cpp:199-204)
-        const int k = -2 - ti;
+        const int k = RT_GUARD(-2 - ti, s.n_spheres, kChkTable);
         sh.N = xnormalize(xsub(sh.p, mk3(__ldg(&s.spheres[3 * k]))));
         sh.m0 = __ldg(&s.spheres[3 * k + 1]);
         sh.m1 = __ldg(&s.spheres[3 * k + 2]);
@@ -154,10 +154,11 @@ __device__ __forceinline__ Shading shading_at(const SceneDev& s, int ti, const f
         sh.mesh = sh.gid = -1;
         return sh;
     }
+    ti = RT_GUARD(ti, s.n_tris, kChkTri);
     const float4 pl = __ldg(&s.tri_plane[kTriStride * ti]);
     const float4 a = __ldg(&s.tri_v0[kTriStride * ti]), b = __ldg(&s.tri_v1[kTriStride * ti]), c = __ldg(&s.tri_v2[kTriStride * ti]);
     const f3 v0 = mk3(a), v1 = mk3(b), v2 = mk3(c), fn = mk3(pl);
-    const int mesh = __float_as_int(b.w);
+    const int mesh = RT_GUARD(__float_as_int(b.w), s.n_mats, kChkTable);
     sh.m0 = __ldg(&s.mats[2 * mesh]);
     sh.m1 = __ldg(&s.mats[2 * mesh + 1]);
     const float total = xlength(xcross(xsub(v1, v0), xsub(v2, v0)));
@@ -206,14 +207,16 @@ __device__ __forceinline__ f3 tex_nearest(const float4* px, unsigned w, unsigned
         x = w - 1u;
     if (y >= h)
         y = h - 1u;
-    return mk3(__ldg(&px[(size_t)y * w + x]));
+    return mk3(__ldg(&px[RT_GUARD((size_t)y * w + x, (size_t)w * h, kChkTexel)]));
 }
 
-__device__ __forceinline__ f3 tex_bilinear(const float4* px, unsigned w, float ix, float iy) // bilinearInterpolation, image.cpp:231-251
+__device__ __forceinline__ f3 tex_bilinear(const float4* px, unsigned w, unsigned h, float ix, float iy) // bilinearInterpolation, image.cpp:231-251
 {
     const float xl = floorf(ix), xh = ceilf(ix), yl = floorf(iy), yh = ceilf(iy);
-    const f3 ll = mk3(__ldg(&px[(size_t)(unsigned)yl * w + (unsigned)xl])), lr = mk3(__ldg(&px[(size_t)(unsigned)yl * w + (unsigned)xh]));
-    const f3 hl = mk3(__ldg(&px[(size_t)(unsigned)yh * w + (unsigned)xl])), hr = mk3(__ldg(&px[(size_t)(unsigned)yh * w + (unsigned)xh]));
+    const size_t n = (size_t)w * h; // (bound of the checked build)
+    (void)n;
+    const f3 ll = mk3(__ldg(&px[RT_GUARD((size_t)(unsigned)yl * w + (unsigned)xl, n, kChkTexel)])), lr = mk3(__ldg(&px[RT_GUARD((size_t)(unsigned)yl * w + (unsigned)xh, n, kChkTexel)]));
+    const f3 hl = mk3(__ldg(&px[RT_GUARD((size_t)(unsigned)yh * w + (unsigned)xl, n, kChkTexel)])), hr = mk3(__ldg(&px[RT_GUARD((size_t)(unsigned)yh * w + (unsigned)xh, n, kChkTexel)]));
     const f3 low = tex_lerp(xl, xh, ll, lr, ix), high = tex_lerp(xl, xh, hl, hr, ix);
     return tex_lerp(yl, yh, low, high, iy);
 }
@@ -236,7 +239,7 @@ __device__ __forceinline__ f3 sample_texture(const SceneDev& s, const FrameParam
     const float4* px = s.tex_texels + tb.x;
     if (fp.tex_filter < 2) { // level 0 of the image itself; toImageCoordinates (118-131): rows start at the top
         const float ix = xmul(u, (float)(w - 1u)), iy = xmul(xsub(1.0f, v), (float)(h - 1u));
-        return fp.tex_filter == 0 ? tex_nearest(px, w, h, ix, iy) : tex_bilinear(px, w, ix, iy);
+        return fp.tex_filter == 0 ? tex_nearest(px, w, h, ix, iy) : tex_bilinear(px, w, h, ix, iy);
     }
     // The mip-mapped filters: nearestLevelMipmapping (255-277), nearestLevelBilinear (280-302), trilinearInterpolation (305-363) with
     // getBestLevelMipmap (506-541).  tb.w = number of pyramid levels; 0: the texture is not a square power of two and has none
@@ -253,14 +256,14 @@ __device__ __forceinline__ f3 sample_texture(const SceneDev& s, const FrameParam
         const unsigned wl = w >> level;
         const float ix = xmul(u, (float)(wl - 1u)), iy = xmul(xsub(1.0f, v), (float)(wl - 1u));
         const float4* pl = px + mip_offset(w, level);
-        return fp.tex_filter == 2 ? tex_nearest(pl, wl, wl, ix, iy) : tex_bilinear(pl, wl, ix, iy);
+        return fp.tex_filter == 2 ? tex_nearest(pl, wl, wl, ix, iy) : tex_bilinear(pl, wl, wl, ix, iy);
     }
     const unsigned high = (unsigned)(int)fminf((float)n - 1.0f, ceilf(lod)), low = (unsigned)(int)fmaxf(0.0f, floorf(lod));
     if (low >= (unsigned)n || high >= (unsigned)n) // getWidthHeightForLevel fails
         return mk3(0.0f, 0.0f, 0.0f);
     const unsigned wlo = w >> low, whi = w >> high;
-    const f3 cl = tex_bilinear(px + mip_offset(w, low), wlo, xmul(u, (float)(wlo - 1u)), xmul(xsub(1.0f, v), (float)(wlo - 1u)));
-    const f3 ch = tex_bilinear(px + mip_offset(w, high), whi, xmul(u, (float)(whi - 1u)), xmul(xsub(1.0f, v), (float)(whi - 1u)));
+    const f3 cl = tex_bilinear(px + mip_offset(w, low), wlo, wlo, xmul(u, (float)(wlo - 1u)), xmul(xsub(1.0f, v), (float)(wlo - 1u)));
+    const f3 ch = tex_bilinear(px + mip_offset(w, high), whi, whi, xmul(u, (float)(whi - 1u)), xmul(xsub(1.0f, v), (float)(whi - 1u)));
     return tex_lerp((float)low, (float)high, cl, ch, lod);
 }
 
@@ -347,9 +350,12 @@ __device__ __forceinline__ double schlick(float R0, float c)
     return (double)R0 + (double)(1.0f - R0) * p5;
 }
 
-__device__ __forceinline__ void accumulate(float4* accum, int pix, float r, float g, float bl)
+__device__ __forceinline__ void accumulate(const BatchDev& b, int pix, float r, float g, float bl)
 {
-    float* acc = reinterpret_cast<float*>(&accum[pix]);
+#if RT_CHECKED
+    pix = RT_GUARD(pix, b.accum_pixels, kChkAccum);
+#endif
+    float* acc = reinterpret_cast<float*>(&b.accum[pix]);
     atomicAdd(acc + 0, r);
     atomicAdd(acc + 1, g);
     atomicAdd(acc + 2, bl);
@@ -417,6 +423,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_extend(
             q = fresh_query();
             if (LEVEL0)
                 return generate_ray(fp, first_lp, item, o, d, tag);
+            item = RT_GUARD(item, b.ray_capacity, kChkQueue);
             const float4 op = b.q[qi].o_pix[item];
             o = mk3(op);
             d = mk3(b.q[qi].d[item]);
@@ -424,10 +431,10 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_extend(
             return true;
         },
         [&](unsigned item, const HitRec& best, f3&, f3&, HitRec&) {
-            b.q[qi].hit[item] = make_int2(__float_as_int(best.t), best.ti);
+            b.q[qi].hit[RT_GUARD(item, b.hit_capacity, kChkQueue)] = make_int2(__float_as_int(best.t), best.ti);
             if (LEVEL0 && b.prim_id && (tag & 1)) { // first sample of the pixel
-                b.prim_id[tag >> 1] = global_id(s, best);
-                b.prim_t[tag >> 1] = best.t;
+                b.prim_id[RT_GUARD(tag >> 1, b.accum_pixels, kChkAccum)] = global_id(s, best);
+                b.prim_t[RT_GUARD(tag >> 1, b.accum_pixels, kChkAccum)] = best.t;
             }
             return false;
         },
@@ -470,6 +477,7 @@ __device__ __forceinline__ float path_uniform(unsigned path, unsigned child, uns
 // (src/main.cpp:112-121) folded with the path throughput w: the light adds A * intensity + B when it is visible.
 __device__ __forceinline__ bool light_reaches(const SceneDev& s, int li, const f3& p)
 {
+    li = RT_GUARD(li, s.n_point_like, kChkTable);
     const float4 L0 = __ldg(s.point_lights + 3 * li);
     if (L0.w == 0.0f)
         return true;
@@ -481,6 +489,7 @@ __device__ __forceinline__ bool light_reaches(const SceneDev& s, int li, const f
 __device__ __forceinline__ void light_terms(const SceneDev& s, int li, const f3& p, const f3& Nn, const f3& reflN, const f3& w, const f3& kd, const f3& ks,
     float shininess, f3& A, f3& B)
 {
+    li = RT_GUARD(li, s.n_point_like, kChkTable);
     const f3 lp = mk3(__ldg(s.point_lights + 3 * li)), lc = mk3(__ldg(s.point_lights + 3 * li + 1));
     const f3 ldir = xnormalize(xsub(lp, p));
     const float cosNL = fabsf(xdot(Nn, ldir));                 // shadow.cpp:125 / 245
@@ -534,7 +543,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
                 valid = pixel_sees_scene(fp, px, py);
             }
             if (valid)
-                h = b.q[qi].hit[i];
+                h = b.q[qi].hit[RT_GUARD(i, b.hit_capacity, kChkQueue)];
         }
         // most slots of a level-0 frame are misses: a block without any hit has nothing to allocate
         if (!__syncthreads_or(h.y != -1))
@@ -553,6 +562,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
                         path = path_mix((unsigned)(py * fp.W + px), i % (unsigned)fp.spp);
                     }
                 } else {
+                    (void)RT_GUARD(i, b.ray_capacity, kChkQueue);
                     const float4 op = b.q[qi].o_pix[i];
                     const float4 dq = b.q[qi].d[i];
                     o = mk3(op);
@@ -575,7 +585,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
                 f3 c = mk3(1.0f, 1.0f, 1.0f);
                 if (fp.tex_available && sh.mesh >= 0 && __ldg(&s.mat_tex[sh.mesh]) >= 0)
                     c = diffuse_colour(s, fp, sh, h.y, d_ray, __int_as_float(h.x), LEVEL0, true);
-                accumulate(b.accum, pix, c.x, c.y, c.z);
+                accumulate(b, pix, c.x, c.y, c.z);
             }
             continue;
         }
@@ -631,12 +641,14 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
             slot1 = s1[0];
         }
         if (slot[0] != 0xffffffffu) {
+            (void)RT_GUARD(slot[0], b.ray_capacity, kChkQueue);
             const f3 o2 = xadd(sh.p, xmul(refl, 0.01f)); // main.cpp:199,286
             b.q[qo].o_pix[slot[0]] = make_float4(o2.x, o2.y, o2.z, __int_as_float(pix << 1));
             b.q[qo].d[slot[0]] = make_float4(refl.x, refl.y, refl.z, __int_as_float((int)path_mix(path, 0u)));
             b.q[qo].w[slot[0]] = make_float4(w0.x, w0.y, w0.z, 0.0f);
         }
         if (slot1 != 0xffffffffu) {
+            (void)RT_GUARD(slot1, b.ray_capacity, kChkQueue);
             const f3 o2 = xadd(sh.p, xmul(refr, 0.01f)); // main.cpp:288
             b.q[qo].o_pix[slot1] = make_float4(o2.x, o2.y, o2.z, __int_as_float(pix << 1));
             b.q[qo].d[slot1] = make_float4(refr.x, refr.y, refr.z, __int_as_float((int)path_mix(path, 0x4000u)));
@@ -689,6 +701,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
                     n_secondary++;
                 if (sg[0] == 0xffffffffu)
                     continue;
+                (void)RT_GUARD(sg[0], b.ray_capacity, kChkQueue);
                 const float wgt = fmaxf(powf(xdot(refl, shine), shininess), 0.0f) / (float)fp.glossy; // main.cpp:245,250
                 const f3 o2 = xadd(sh.p, xmul(shine, 0.01f));
                 b.q[qo].o_pix[sg[0]] = make_float4(o2.x, o2.y, o2.z, __int_as_float(pix << 1));
@@ -709,6 +722,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
             block_alloc<1>(cl, wl, capl, &b.counters->overflow, sl1, smem);
             if (sl1[0] == 0xffffffffu)
                 continue;
+            (void)RT_GUARD(sl1[0], b.shadow_pt_capacity, kChkQueue);
             f3 A, B;
             light_terms(s, li, sh.p, Nn, reflN, w, kd, ks, shininess, A, B);
             b.sq_point.p_pix[sl1[0]] = make_float4(sh.p.x, sh.p.y, sh.p.z, __int_as_float(pix));
@@ -729,7 +743,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
                     const float sp = powf(cosRL, shininess);
                     B = mk3(w.x * lc.x * ks.x * sp, w.y * lc.y * ks.y * sp, w.z * lc.z * ks.z * sp);
                 }
-                const unsigned sl = slot[1] * (unsigned)fp.n_sphere + (unsigned)lj;
+                const unsigned sl = RT_GUARD(slot[1] * (unsigned)fp.n_sphere + (unsigned)lj, b.shadow_sp_capacity, kChkQueue);
                 b.sq_sphere.p_pix[sl] = make_float4(sh.p.x, sh.p.y, sh.p.z, __int_as_float(pix));
                 b.sq_sphere.a_light[sl] = make_float4(A.x, A.y, A.z, __int_as_float(lj));
                 b.sq_sphere.b[sl] = make_float4(B.x, B.y, B.z, 0.0f);
@@ -754,6 +768,7 @@ __global__ void __launch_bounds__(kShadeBlock) k_shade(SceneDev s, FrameParams f
             block_alloc<1>(cl, wl, capl, &b.counters->overflow, sl1, smem);
             if (sl1[0] == 0xffffffffu)
                 continue;
+            (void)RT_GUARD(sl1[0], b.plane_capacity, kChkQueue);
             b.sq_plane.p_pix[sl1[0]] = make_float4(sh.p.x, sh.p.y, sh.p.z, __int_as_float(pix));
             b.sq_plane.a_light[sl1[0]] = make_float4(w.x * kd.x * pc.x, w.y * kd.y * pc.y, w.z * kd.z * pc.z, __int_as_float(lj));
             b.sq_plane.b_shin[sl1[0]] = make_float4(w.x * pc.x * ks.x, w.y * pc.y * ks.y, w.z * pc.z * ks.z, shininess);
@@ -871,10 +886,11 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_shadow_
     shadow_loop<ANYHIT, COUNT>(
         s, root_entry, fp, b, &b.counters->sh[b.par].work_pt, n,
         [&](unsigned i, f3& p1, f3& p2) {
+            i = RT_GUARD(i, b.shadow_pt_capacity, kChkQueue);
             const float4 pp = b.sq_point.p_pix[i];
             const float4 al = b.sq_point.a_light[i];
             p1 = mk3(pp);
-            p2 = mk3(__ldg(&s.point_lights[3 * __float_as_int(al.w)]));
+            p2 = mk3(__ldg(&s.point_lights[3 * RT_GUARD(__float_as_int(al.w), s.n_point_like, kChkTable)]));
         },
         [&](unsigned i, bool visible, float intensity) {
             if (!visible)
@@ -882,7 +898,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_shadow_
             const float4 pp = b.sq_point.p_pix[i];
             const float4 al = b.sq_point.a_light[i];
             const float4 bb = b.sq_point.b[i];
-            accumulate(b.accum, __float_as_int(pp.w), al.x * intensity + bb.x, al.y * intensity + bb.y, al.z * intensity + bb.z);
+            accumulate(b, __float_as_int(pp.w), al.x * intensity + bb.x, al.y * intensity + bb.y, al.z * intensity + bb.z);
         });
 }
 
@@ -903,6 +919,7 @@ __global__ void __launch_bounds__(kWideBlock, 8) k_extend_wide(SceneDev s, const
         b.counters->level_ext[level] = n;
     const unsigned groups = gridDim.x * (kWideBlock / kGroup);
     for (unsigned item = blockIdx.x * (kWideBlock / kGroup) + threadIdx.x / kGroup; item < n; item += groups) {
+        (void)RT_GUARD(item, b.ray_capacity, kChkQueue);
         const f3 o = mk3(b.q[qi].o_pix[item]), d = mk3(b.q[qi].d[item]);
         HitRec best = fresh_query();
         trace_wide<false>(s, wide, wide_root, o, d, best, s_stack[threadIdx.x / kGroup]);
@@ -923,10 +940,11 @@ __global__ void __launch_bounds__(kWideBlock, 8) k_shadow_point_wide(SceneDev s,
     const unsigned groups = gridDim.x * (kWideBlock / kGroup);
     unsigned queries = 0;
     for (unsigned item = blockIdx.x * (kWideBlock / kGroup) + threadIdx.x / kGroup; item < n; item += groups) {
+        (void)RT_GUARD(item, b.shadow_pt_capacity, kChkQueue);
         const float4 pp = b.sq_point.p_pix[item], al = b.sq_point.a_light[item];
         CanSee cs;
         bool visible = true;
-        if (cansee_begin(cs, mk3(pp), mk3(__ldg(&s.point_lights[3 * __float_as_int(al.w)])))) {
+        if (cansee_begin(cs, mk3(pp), mk3(__ldg(&s.point_lights[3 * RT_GUARD(__float_as_int(al.w), s.n_point_like, kChkTable)])))) {
             queries += leader ? 1u : 0u;
             HitRec best = cansee_query(cs);
             trace_wide<true>(s, wide, wide_root, cs.o, cs.d, best, s_stack[threadIdx.x / kGroup]);
@@ -934,7 +952,7 @@ __global__ void __launch_bounds__(kWideBlock, 8) k_shadow_point_wide(SceneDev s,
         }
         if (leader && visible) {
             const float4 bb = b.sq_point.b[item];
-            accumulate(b.accum, __float_as_int(pp.w), al.x * 1.0f + bb.x, al.y * 1.0f + bb.y, al.z * 1.0f + bb.z);
+            accumulate(b, __float_as_int(pp.w), al.x * 1.0f + bb.x, al.y * 1.0f + bb.y, al.z * 1.0f + bb.z);
         }
     }
     warp_add_u64(&b.counters->shadow_queries, queries);
@@ -980,7 +998,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, kPathBlocksPerSm) k_paths(Scen
             if (!cansee_begin(cs, p, mk3(__ldg(&s.point_lights[3 * li])))) { // the light sits on the hit: visible without a query (shadow.cpp:41,67)
                 f3 A, B;
                 light_terms(s, li, p, ld3(ps.Nn), ld3(ps.reflN), ld3(ps.w), ld3(ps.kd), ld3(ps.ks), ps.shininess, A, B);
-                accumulate(b.accum, ps.pix, A.x + B.x, A.y + B.y, A.z + B.z);
+                accumulate(b, ps.pix, A.x + B.x, A.y + B.y, A.z + B.z);
                 continue;
             }
             queries++;
@@ -1007,6 +1025,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, kPathBlocksPerSm) k_paths(Scen
     trace_queue<kAnyHitPerQuery, COUNT>(
         s, root_entry, false, &b.counters->work[0], n, st,
         [&](unsigned item, f3& o, f3& d, HitRec& q) {
+            item = RT_GUARD(item, b.ray_capacity, kChkQueue);
             const float4 op = b.q[qi].o_pix[item];
             o = mk3(op);
             d = mk3(b.q[qi].d[item]);
@@ -1022,7 +1041,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, kPathBlocksPerSm) k_paths(Scen
                 if (best.ti == -1) {
                     f3 A, B;
                     light_terms(s, ps.li, ld3(ps.p), ld3(ps.Nn), ld3(ps.reflN), ld3(ps.w), ld3(ps.kd), ld3(ps.ks), ps.shininess, A, B);
-                    accumulate(b.accum, ps.pix, A.x * 1.0f + B.x, A.y * 1.0f + B.y, A.z * 1.0f + B.z);
+                    accumulate(b, ps.pix, A.x * 1.0f + B.x, A.y * 1.0f + B.y, A.z * 1.0f + B.z);
                 }
                 return next_query(o, d, q);
             }
@@ -1064,7 +1083,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_shadow_
     shadow_loop<ANYHIT, COUNT>(
         s, root_entry, fp, b, &b.counters->sh[b.par].work_sp, n,
         [&](unsigned j, f3& p1, f3& p2) {
-            const unsigned rec = j / rc;
+            const unsigned rec = RT_GUARD(j / rc, b.shadow_sp_capacity, kChkQueue);
             const int k = (int)(j % rc);
             const float4 pp = b.sq_sphere.p_pix[rec];
             const float4 al = b.sq_sphere.a_light[rec];
@@ -1131,7 +1150,7 @@ __global__ void __launch_bounds__(256) k_sphere_finalize(FrameParams fp, BatchDe
             const float4 pp = b.sq_sphere.p_pix[i];
             const float4 al = b.sq_sphere.a_light[i];
             const float4 bb = b.sq_sphere.b[i];
-            accumulate(b.accum, __float_as_int(pp.w), al.x * intensity + bb.x, al.y * intensity + bb.y, al.z * intensity + bb.z);
+            accumulate(b, __float_as_int(pp.w), al.x * intensity + bb.x, al.y * intensity + bb.y, al.z * intensity + bb.z);
         }
     }
 }
@@ -1151,7 +1170,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_shadow_
     shadow_loop<ANYHIT, COUNT>(
         s, root_entry, fp, b, &b.counters->sh[b.par].work_pl, n,
         [&](unsigned j, f3& p1, f3& p2) {
-            const unsigned rec = j / per, k = j % per;
+            const unsigned rec = RT_GUARD(j / per, b.plane_capacity, kChkQueue), k = j % per;
             const int lj = __float_as_int(b.sq_plane.a_light[rec].w);
             const f3 ppos = mk3(__ldg(s.plane_lights + 4 * lj)), pw = mk3(__ldg(s.plane_lights + 4 * lj + 1)), ph = mk3(__ldg(s.plane_lights + 4 * lj + 2));
             const float step = xdiv(1.0f, (float)(fp.pl_rc - 1)); // 1.0f / (rayCount1D - 1)
@@ -1197,7 +1216,7 @@ __global__ void __launch_bounds__(256) k_plane_finalize(FrameParams fp, BatchDev
             const float4 al = b.sq_plane.a_light[i];
             const float4 bs = b.sq_plane.b_shin[i];
             const float sp = bs.w > 0.0f ? powf(acc.w, bs.w) : 0.0f;
-            accumulate(b.accum, __float_as_int(pp.w), al.x * intensity + bs.x * sp, al.y * intensity + bs.y * sp, al.z * intensity + bs.z * sp);
+            accumulate(b, __float_as_int(pp.w), al.x * intensity + bs.x * sp, al.y * intensity + bs.y * sp, al.z * intensity + bs.z * sp);
         }
     }
 }
@@ -1224,7 +1243,7 @@ __global__ void __launch_bounds__(256) k_resolve(FrameParams fp, unsigned first_
             continue;
         const unsigned lp = j * kTilePixels + (((y >> 2) * 4 + (x >> 3)) << 5) + ((y & 3) << 3) + (x & 7);
         const float4 a = accum[lp];
-        const size_t o = (size_t)(fp.H - 1 - py) * fp.W + px;
+        const size_t o = RT_GUARD((size_t)(fp.H - 1 - py) * fp.W + px, (size_t)fp.W * fp.H, kChkPixel);
         out[o] = make_float4(a.x * fp.sample_scale, a.y * fp.sample_scale, a.z * fp.sample_scale, 1.0f);
         if (out_id) {
             const bool traced = pixel_sees_scene(fp, px, py);
@@ -1280,7 +1299,7 @@ __global__ void __launch_bounds__(256) k_pack_rgb_tiles(FrameParams fp, unsigned
         const int px0 = (int)(tx * kTileW), py = (int)(ty * kTileH + y);
         if (py >= fp.H)
             continue;
-        const size_t p0 = (size_t)(fp.H - 1 - py) * fp.W + px0;
+        const size_t p0 = RT_GUARD((size_t)(fp.H - 1 - py) * fp.W + px0, (size_t)fp.W * fp.H, kChkPixel);
         const bool inside = px0 + lane < fp.W;
         const float4 a = inside ? in[p0 + lane] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         if (px0 + (int)kTileW <= fp.W && ((3 * p0) & 3) == 0) {
@@ -1376,7 +1395,7 @@ __global__ void __launch_bounds__(256) k_host_background(FrameParams fp, unsigne
             __nanosleep((unsigned)min(wait, 20000ll));
         }
         sent++;
-        const size_t p0 = (size_t)(fp.H - 1 - py) * fp.W + px0;
+        const size_t p0 = RT_GUARD((size_t)(fp.H - 1 - py) * fp.W + px0, (size_t)fp.W * fp.H, kChkPixel);
         if (px0 + (int)kTileW <= fp.W && ((3 * p0) & 3) == 0) {
             if (lane < 3 * (int)kTileW / 4)
                 reinterpret_cast<float4*>(out + 3 * p0)[lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -1650,6 +1669,35 @@ void launch_intersect(cudaStream_t st, int sm_count, const SceneDev& s, int root
     if (n <= 0)
         return;
     k_intersect<<<grid_for(n, 128, sm_count * 16), 128, 0, st>>>(s, root_entry, rays, n, use_bvh, tri_id, t_out, overflow);
+}
+
+#if RT_CHECKED
+namespace {
+__global__ void k_provoke_violation(int site) { (void)RT_GUARD(-1, 1, site); }
+} // namespace
+#endif
+
+// One deliberate violation at site kChkTable from this translation unit (rt_violations_selftest): proves that what the kernels count is
+// what add_violations_kernels reads.
+void provoke_violation_kernels(cudaStream_t st)
+{
+#if RT_CHECKED
+    k_provoke_violation<<<1, 1, 0, st>>>(kChkTable);
+#else
+    (void)st;
+#endif
+}
+
+void add_violations_kernels(unsigned int* out)
+{
+#if RT_CHECKED
+    unsigned int h[kChkSites] = {};
+    if (cudaMemcpyFromSymbol(h, g_rt_violations, sizeof(h)) == cudaSuccess)
+        for (int k = 0; k < kChkSites; k++)
+            out[k] += h[k];
+#else
+    (void)out;
+#endif
 }
 
 } // namespace rtb

@@ -90,6 +90,14 @@ int collapse_bvh_wide8_device(cudaStream_t st, const float4* d_nodes2, int n_nod
 void launch_intersect_wide(cudaStream_t st, int sm_count, const SceneDev& s, const float4* wide, int root_entry, const float* rays, long long n, int* tri_id,
     float* t_out);
 
+// Checked build (RT_CHECKED, rt_types.h): violations counted so far by the kernels of rt_kernels.cu / rt_wide8.cu on the current
+// device are ADDED to out[kChkSites].  The default build counts nothing and leaves `out` alone.
+void add_violations_kernels(unsigned int* out);
+void add_violations_wide8(unsigned int* out);
+// one deliberate violation each (site kChkTable / kChkWideStack), for rt_violations_selftest; nothing in the default build
+void provoke_violation_kernels(cudaStream_t st);
+void provoke_violation_wide8(cudaStream_t st);
+
 // Visiting rank of every object (triangles 0..n_tris-1, then spheres) in the reference's own BVH (rt_reforder.cu): the tie key
 // of the traversal kernels.  d_spheres: 3 x float4 per sphere ({centre, radius} first).  d_rank: n_tris + n_spheres ints.
 int reference_visit_rank(cudaStream_t st, const float* d_pos, long long n_tris, const float4* d_spheres, int n_spheres, int* d_rank, const char** err);

@@ -22,6 +22,24 @@
 
 namespace rtb {
 
+// Checked build (RT_CHECKED, rt_types.h): RT_GUARD(i, n, site) is i when 0 <= i < n; otherwise the violation is counted and the
+// access goes to element 0.  One counter table per translation unit that includes this header (rt_kernels.cu, rt_wide8.cu), read
+// back by add_violations_*() (rt_kernels.h).  Default build: the identity.
+#if RT_CHECKED
+static __device__ unsigned int g_rt_violations[kChkSites];
+template <typename T> __device__ __forceinline__ T rt_guard(T i, long long n, int site)
+{
+    if ((long long)i < 0 || (long long)i >= n) {
+        atomicAdd(&g_rt_violations[site], 1u);
+        return (T)0;
+    }
+    return i;
+}
+#define RT_GUARD(i, n, site) rtb::rt_guard((i), (long long)(n), (site))
+#else
+#define RT_GUARD(i, n, site) (i)
+#endif
+
 struct TraceStats {
     unsigned int nodes = 0, tris = 0, tris_full = 0;
     unsigned int ray_start_nodes = 0, ray_start_tris = 0; // counters when the lane's current query began (instrumented builds)
@@ -50,6 +68,7 @@ struct HitRec {
 template <bool COUNT>
 __device__ __forceinline__ bool test_triangle(const SceneDev& s, int ti, const float4& pl, const f3& o, const f3& d, const f3& dn, HitRec& best, TraceStats& st)
 {
+    ti = RT_GUARD(ti, s.n_tris, kChkTri);
     const f3 n = mk3(pl);
     if (COUNT)
         st.tris++;
@@ -88,6 +107,7 @@ __device__ __forceinline__ bool test_triangle(const SceneDev& s, int ti, const f
 template <bool COUNT>
 __device__ __forceinline__ bool test_triangle(const SceneDev& s, int ti, const f3& o, const f3& d, const f3& dn, HitRec& best, TraceStats& st)
 {
+    ti = RT_GUARD(ti, s.n_tris, kChkTri);
     return test_triangle<COUNT>(s, ti, __ldg(&s.tri_plane[kTriStride * ti]), o, d, dn, best, st);
 }
 
@@ -141,7 +161,7 @@ __device__ __forceinline__ HitRec bounded_query(float limit) { return HitRec { l
 __device__ __forceinline__ int global_id(const SceneDev& s, const HitRec& best)
 {
     if (best.ti >= 0)
-        return __float_as_int(__ldg(&s.tri_v2[kTriStride * best.ti]).w);
+        return __float_as_int(__ldg(&s.tri_v2[kTriStride * RT_GUARD(best.ti, s.n_tris, kChkTri)]).w);
     return best.ti == -1 ? -1 : s.sphere_id_base + (-2 - best.ti);
 }
 
@@ -246,8 +266,8 @@ struct TravStack {
     }
 #else
     int lo[kStackWords];
-    __device__ __forceinline__ int operator[](int i) const { return lo[i]; }
-    __device__ __forceinline__ void put(int i, int v) { lo[i] = v; }
+    __device__ __forceinline__ int operator[](int i) const { return lo[RT_GUARD(i, kStackWords, kChkStack)]; }
+    __device__ __forceinline__ void put(int i, int v) { lo[RT_GUARD(i, kStackWords, kChkStack)] = v; }
 #endif
 };
 // Binds the shared part of the stack; must be called by every thread of a block of at most RT_TRACE_BLOCK threads.
@@ -364,7 +384,7 @@ __device__ __forceinline__ void trav_node_step(const SceneDev& s, Trav& tv, Trav
 template <int ANYHIT, bool COUNT>
 __device__ __forceinline__ void trav_node_step(const SceneDev& s, Trav& tv, TravStack& stack, TraceStats& st)
 {
-    const float4* np = s.nodes + 2 * (size_t)tv.cur;
+    const float4* np = s.nodes + 2 * (size_t)RT_GUARD(tv.cur, s.n_nodes - 1, kChkNode); // (a fetch reads nodes cur and cur + 1)
     float4 a0, a1, b0, b1;
     load_node_pair(np, a0, a1, b0, b1);
     if (COUNT)

@@ -27,6 +27,16 @@ constexpr int kMaxPointLights = 16;
 constexpr int kMaxSphereLights = 8;
 constexpr int kMaxSpheres = 64;
 
+// RT_CHECKED = 1 (make EXTRA=-DRT_CHECKED=1 OUT=librtb200_checked.so BUILD=build_checked): the "checked build".  Every index the
+// kernels form from data — BVH node and triangle indices, traversal stack slots (per-lane and per-group), accumulator and framebuffer
+// pixels, texel addresses, queue slots — is tested against its bound first; a violation is counted per site (rt_violations) and the access goes to
+// element 0 instead.  The pool these kernels are developed on has no compute-sanitizer; the GPU test-suite run against this build
+// (RTB200_LIB) is its stand-in.  In the default build RT_GUARD is the identity and the SASS is unchanged.
+#ifndef RT_CHECKED
+#define RT_CHECKED 0
+#endif
+enum CheckSite { kChkNode = 0, kChkTri, kChkStack, kChkWideNode, kChkWideStack, kChkAccum, kChkPixel, kChkTexel, kChkTable, kChkQueue, kChkSites };
+
 // Tile g of the image (0 <= g < tiles_x * tiles_y; rank r of a sharded job owns the tiles with g % world == r) lies in tile row
 // g / tiles_x, and inside that row the tiles are rotated by 3 columns per row.  Plain row-major numbering would hand every rank
 // whole tile COLUMNS whenever tiles_x is a multiple of the world size (a 3840-wide frame has 120 tile columns: with 8 ranks, rank r
@@ -78,6 +88,10 @@ struct SceneDev {
     int sphere_id_base;          // global id of sphere 0 = number of triangles the caller uploaded
     int n_tris;
     int n_nodes;
+#if RT_CHECKED
+    int n_wide_nodes;            // nodes of the 8-wide tree (rt_wide8.cu)
+    int n_mats, n_point_like;    // entries of the material and point-like light tables
+#endif
 };
 
 struct FrameParams {
@@ -191,6 +205,10 @@ struct BatchDev {
     float4* accum;    // per local padded pixel, summed radiance
     int* prim_id;     // nullable: closest-hit global triangle id of the first primary ray of each local pixel
     float* prim_t;    // nullable
+#if RT_CHECKED
+    unsigned int accum_pixels; // entries of accum / prim_id / prim_t
+    unsigned int hit_capacity; // entries of q[].hit (level 0 keeps a slot per primary ray whatever ray_capacity is)
+#endif
 };
 
 } // namespace rtb

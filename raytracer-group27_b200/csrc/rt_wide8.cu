@@ -211,4 +211,33 @@ void launch_intersect_wide(cudaStream_t st, int sm_count, const SceneDev& s, con
     k_intersect_wide<<<grid, kWideBlock, 0, st>>>(s, wide, root_entry, rays, n, tri_id, t_out);
 }
 
+#if RT_CHECKED
+namespace {
+__global__ void k_provoke_violation(int site) { (void)RT_GUARD(-1, 1, site); }
+} // namespace
+#endif
+
+// One deliberate violation at site kChkWideStack from this translation unit (rt_violations_selftest): proves that what the kernels count is
+// what add_violations_wide8 reads.
+void provoke_violation_wide8(cudaStream_t st)
+{
+#if RT_CHECKED
+    k_provoke_violation<<<1, 1, 0, st>>>(kChkWideStack);
+#else
+    (void)st;
+#endif
+}
+
+void add_violations_wide8(unsigned int* out)
+{
+#if RT_CHECKED
+    unsigned int h[kChkSites] = {};
+    if (cudaMemcpyFromSymbol(h, g_rt_violations, sizeof(h)) == cudaSuccess)
+        for (int k = 0; k < kChkSites; k++)
+            out[k] += h[k];
+#else
+    (void)out;
+#endif
+}
+
 } // namespace rtb

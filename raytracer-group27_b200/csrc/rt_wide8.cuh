@@ -35,7 +35,7 @@ __device__ __forceinline__ void trace_wide(const SceneDev& s, const float4* __re
     }
     while (cur != kTravDone) {
         if (cur >= 0) { // node: every lane tests one child
-            const float4* np = wide + 16 * (size_t)cur + 2 * sub;
+            const float4* np = wide + 16 * (size_t)RT_GUARD(cur, s.n_wide_nodes, kChkWideNode) + 2 * sub;
             float4 a0, a1; // this lane's child: one 32-byte load
             asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                          : "=f"(a0.x), "=f"(a0.y), "=f"(a0.z), "=f"(a0.w), "=f"(a1.x), "=f"(a1.y), "=f"(a1.z), "=f"(a1.w)
@@ -75,7 +75,7 @@ __device__ __forceinline__ void trace_wide(const SceneDev& s, const float4* __re
             const unsigned first = (__ballot_sync(gmask, hit && rank == 0) >> gbase) & 0xffu;
             const int next = __shfl_sync(gmask, entry, (int)gbase + __ffs(first) - 1);
             if (hit && rank > 0)
-                stack[sp + (n - 1 - rank)] = entry; // the farthest lowest, the second nearest on top
+                stack[RT_GUARD(sp + (n - 1 - rank), kWideStack, kChkWideStack)] = entry; // the farthest lowest, the second nearest on top
             sp += n - 1;
             __syncwarp(gmask);
             cur = next;

@@ -142,6 +142,9 @@ SYMBOLS = [
     ("rt_download_rgb", _I, [_P, _P, _I, _I, _P]),
     ("rt_intersect", _I, [_P, _P, C.c_int64, _I, _P, _P]),
     ("rt_last_intersect_ms", C.c_float, [_P]),
+    ("rt_checked_build", _I, []),
+    ("rt_violations", _I, [_P, C.POINTER(C.c_uint), _I]),
+    ("rt_violations_selftest", _I, [_P]),
     ("rt_load_obj", _I, [C.c_char_p, _I, C.POINTER(_P)]),
     ("rt_soup_num_triangles", C.c_int64, [_P]),
     ("rt_soup_num_meshes", _I, [_P]),
@@ -502,6 +505,24 @@ class Context:
         t = np.empty(n, np.float32)
         _check(self._l.rt_intersect(self._h, rays.ctypes.data, n, 1 if use_bvh else 0, ids.ctypes.data, t.ctypes.data))
         return ids, t
+
+    def violations(self) -> dict:
+        """Checked build (rt_checked_build): indices the kernels found out of range so far, per site; all zero from the default build."""
+        counts = (C.c_uint * len(CHECK_SITES))()
+        _check(self._l.rt_violations(self._h, counts, len(CHECK_SITES)))
+        return dict(zip(CHECK_SITES, (int(v) for v in counts)))
+
+    def violations_selftest(self):
+        """Checked build: one deliberate violation at "table_entry" and one at "wide_stack_slot" (a live counter shows them)."""
+        _check(self._l.rt_violations_selftest(self._h))
+
+
+# sites of the checked build's bounds tests, in the order of rt_violations (csrc/rt_types.h: CheckSite)
+CHECK_SITES = ("bvh_node", "triangle", "stack_slot", "wide_node", "wide_stack_slot", "accumulator_pixel", "framebuffer_pixel", "texel", "table_entry", "queue_slot")
+
+
+def checked_build() -> bool:
+    return bool(lib().rt_checked_build())
 
 
 # ---- image sharding (host-side mirror of the device mapping in csrc/rt_kernels.cu: local_to_pixel) ----

@@ -29,4 +29,17 @@ def rtb():
 def gpu_ctx(rtb):
     ctx = rtb.Context(0)  # raises without a GPU: no fallback
     yield ctx
+    # The checked build (RTB200_LIB=.../librtb200_checked.so, include/rt_b200.h: rt_violations) counts every index its kernels found
+    # out of range, in all contexts of this process: a session run against it ends with the verdict.  The default build reports zeros.
+    verdict = {"checked": rtb.checked_build(), "violations": ctx.violations()}
+    ctx.violations_selftest()  # the counters are alive: two deliberate violations show up (checked build), nothing changes (default build)
+    after = ctx.violations()
+    verdict["selftest"] = {k: after[k] - verdict["violations"][k] for k in after if after[k] != verdict["violations"][k]}
     ctx.close()
+    out = os.environ.get("RTB200_VIOLATIONS_OUT")
+    if out:
+        import json
+        with open(out, "w") as f:
+            json.dump(verdict, f)
+    assert verdict["selftest"] == ({"table_entry": 1, "wide_stack_slot": 1} if verdict["checked"] else {}), verdict
+    assert not any(verdict["violations"].values()), f"out-of-range indices in the kernels: {verdict}"
