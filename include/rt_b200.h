@@ -275,6 +275,10 @@ int rt_render_shard(rt_ctx* ctx, const rt_camera* cam, const rt_params* prm, flo
  * without the permission to lock pages; the caller then simply keeps pageable memory.  rt_current_device: the calling thread's
  * current CUDA device (0 when there is none). */
 int rt_host_register(void* p, size_t bytes);
+/* The same kind of memory from the CUDA allocator itself (cudaHostAlloc, portable + mapped), for callers that can choose where their
+ * image lives; release with rt_host_free. */
+int rt_host_alloc(size_t bytes, void** p);
+int rt_host_free(void* p);
 int rt_host_unregister(void* p);
 int rt_current_device(void);
 /* The rows of background leave for the host while the frame is still traced, paced to just under what the link carries (stores that

@@ -1888,6 +1888,27 @@ int rt_host_register(void* p, size_t bytes)
     return RT_OK;
 }
 
+int rt_host_alloc(size_t bytes, void** p)
+{
+    if (!p || !bytes)
+        return fail(RT_ERR_INVALID, "rt_host_alloc: empty request");
+    *p = nullptr;
+    const cudaError_t e = cudaHostAlloc(p, bytes, cudaHostAllocPortable | cudaHostAllocMapped);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *p = nullptr;
+        return fail(RT_ERR_CUDA, std::string("rt_host_alloc: ") + cudaGetErrorString(e));
+    }
+    return RT_OK;
+}
+
+int rt_host_free(void* p)
+{
+    if (p && cudaFreeHost(p) != cudaSuccess)
+        cudaGetLastError();
+    return RT_OK;
+}
+
 int rt_host_unregister(void* p)
 {
     if (p && cudaHostUnregister(p) != cudaSuccess)

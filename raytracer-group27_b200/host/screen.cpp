@@ -8,17 +8,6 @@
 Screen::Screen(const glm::ivec2& resolution)
     : m_resolution(resolution), m_textureData(size_t(resolution.x) * size_t(resolution.y), glm::vec3(0.0f))
 {
-    if (!m_textureData.empty()) {
-        // page-locked and device-mapped pixels are rt_render's fast path; without a device (or the permission to lock pages) the
-        // frame arrives through staged copies instead
-        m_pageLocked = rt_host_register(m_textureData.data(), m_textureData.size() * sizeof(glm::vec3)) == RT_OK;
-    }
-}
-
-Screen::~Screen()
-{
-    if (m_pageLocked)
-        rt_host_unregister(m_textureData.data());
 }
 
 void Screen::clear(const glm::vec3& color) { std::fill(m_textureData.begin(), m_textureData.end(), color); }

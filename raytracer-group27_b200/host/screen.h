@@ -5,16 +5,53 @@
 // the Screen's own pixels when postprocessImage() / writeBitmapToFile() are called directly.
 #pragma once
 #include "rt_b200.h"
+#include <cstddef>
+#include <cstdlib>
 #include <filesystem>
 #include <glm/vec2.hpp>
 #include <glm/vec3.hpp>
+#include <new>
 #include <vector>
 
 enum class FilteringOption { None, Bloom, BloomWithReinhardHdr, BloomWithExposureHdr, OnlyLight, OnlyLightWithKernel };
 enum class Kernel { BoxKernel, GaussianKernel };
 
+// Allocator of the Screen's pixels: page-locked, device-mapped memory from the CUDA allocator (rt_host_alloc) when there is a device,
+// so that renderRayTracing's kernels can store the frame into it themselves (rt_render's fast path, rt_b200.h) at the link's full rate —
+// ordinary pages registered afterwards (rt_host_register on a std::vector's storage, the first version) take the same path 4 % slower
+// (tools/host_mem_probe.py: 2.66 against 2.56 ms for the 4K frame) — and plain memory where there is none (the frame then arrives through
+// staged copies).  A 64-byte header in front of the pixels remembers which of the two it was.
+template <typename T> struct ScreenAllocator {
+    using value_type = T;
+    ScreenAllocator() = default;
+    template <typename U> ScreenAllocator(const ScreenAllocator<U>&) {}
+    static constexpr std::size_t kHeader = 64;
+    T* allocate(std::size_t n)
+    {
+        const std::size_t bytes = kHeader + n * sizeof(T);
+        void* p = nullptr;
+        const bool pinned = rt_host_alloc(bytes, &p) == RT_OK;
+        if (!pinned && !(p = std::malloc(bytes)))
+            throw std::bad_alloc();
+        *static_cast<int*>(p) = pinned ? 1 : 0;
+        return reinterpret_cast<T*>(static_cast<char*>(p) + kHeader);
+    }
+    void deallocate(T* q, std::size_t) noexcept
+    {
+        void* p = reinterpret_cast<char*>(q) - kHeader;
+        if (*static_cast<int*>(p))
+            rt_host_free(p);
+        else
+            std::free(p);
+    }
+    template <typename U> bool operator==(const ScreenAllocator<U>&) const { return true; }
+    template <typename U> bool operator!=(const ScreenAllocator<U>&) const { return false; }
+};
+
 class Screen {
 public:
+    using Pixels = std::vector<glm::vec3, ScreenAllocator<glm::vec3>>;
+
     explicit Screen(const glm::ivec2& resolution);
 
     void clear(const glm::vec3& color);
@@ -39,19 +76,16 @@ public:
     [[nodiscard]] const rt_post_params& postSettings() const { return m_post; }
 
     [[nodiscard]] glm::ivec2 resolution() const { return m_resolution; }
-    [[nodiscard]] std::vector<glm::vec3>& pixels() { return m_textureData; }
-    [[nodiscard]] const std::vector<glm::vec3>& pixels() const { return m_textureData; }
+    [[nodiscard]] Pixels& pixels() { return m_textureData; }
+    [[nodiscard]] const Pixels& pixels() const { return m_textureData; }
 
-    // The pixel storage is page-locked and mapped into the CUDA devices while the Screen lives (when there is a device), so that
-    // renderRayTracing's kernels can store the frame into it themselves (rt_render, rt_b200.h); hence no copies of a Screen.
-    ~Screen();
+    // (the pixels are page-locked memory, a scarce resource: no accidental copies of a Screen)
     Screen(const Screen&) = delete;
     Screen& operator=(const Screen&) = delete;
 
 private:
     glm::ivec2 m_resolution;
-    std::vector<glm::vec3> m_textureData;
-    bool m_pageLocked = false;
+    Pixels m_textureData; // src/screen.h:85, in ScreenAllocator's memory
     // defaults of src/screen.h:84-101: no bloom, box kernel applied once, size 5, sigma 2, exposure 0.5, gamma 2.2 off
     rt_post_params m_post { RT_FILTER_NONE, RT_KERNEL_BOX, 1, 5, 2.0f, 0.5f, 0, 2.2f, 0 };
 };

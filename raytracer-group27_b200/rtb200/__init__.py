@@ -137,6 +137,8 @@ SYMBOLS = [
     ("rt_set_host_store_rate", _I, [_P, C.c_double]),
     ("rt_host_register", _I, [_P, C.c_size_t]),
     ("rt_host_unregister", _I, [_P]),
+    ("rt_host_alloc", _I, [C.c_size_t, C.POINTER(_P)]),
+    ("rt_host_free", _I, [_P]),
     ("rt_current_device", _I, []),
     ("rt_close_peer_framebuffer", _I, [_P, _P]),
     ("rt_download_rgb", _I, [_P, _P, _I, _I, _P]),
