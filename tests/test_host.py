@@ -28,6 +28,19 @@ def test_library_exports_every_declared_symbol(rtb):
     assert lib.rt_version().decode().startswith("rt_b200")
 
 
+def test_checked_library_has_the_same_abi(rtb):
+    """librtb200_checked.so (csrc/rt_types.h: RT_CHECKED; built by __graft_entry__.build()) is the same library with the kernels'
+    bounds checks live: every function of the header, and it says which of the two it is."""
+    import ctypes
+    path = os.path.join(ROOT, "raytracer-group27_b200", "librtb200_checked.so")
+    assert os.path.exists(path), "missing: __graft_entry__.build() makes it"
+    chk = ctypes.CDLL(path)
+    for n in declared_functions():
+        assert hasattr(chk, n), f"{n} is declared in include/rt_b200.h but not exported by the checked build"
+    assert chk.rt_checked_build() == 1 and rtb.lib().rt_checked_build() == 0
+    assert len(rtb.CHECK_SITES) == 10
+
+
 def test_no_cpu_fallback_without_gpu(rtb):
     import torch
     if torch.cuda.is_available():
