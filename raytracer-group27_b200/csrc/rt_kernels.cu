@@ -253,6 +253,8 @@ __device__ __forceinline__ f3 sample_texture(const SceneDev& s, const FrameParam
             level = (unsigned)(int)fmaxf(0.0f, floorf(lod));
         else
             level = (unsigned)(int)fminf((float)n - 1.0f, ceilf(lod));
+        if (level >= (unsigned)n) // a level of detail beyond the pyramid rounded DOWN: getWidthHeightForLevel fails and the filters answer white (image.cpp:268-271, 293-296)
+            return mk3(1.0f, 1.0f, 1.0f);
         const unsigned wl = w >> level;
         const float ix = xmul(u, (float)(wl - 1u)), iy = xmul(xsub(1.0f, v), (float)(wl - 1u));
         const float4* pl = px + mip_offset(w, level);

@@ -203,6 +203,42 @@ def test_far_and_near_cameras(rtb, gpu_ctx):
             assert st.rays == o_st.rays
 
 
+def test_level_of_detail_beyond_the_mip_pyramid(rtb, gpu_ctx):
+    """A level of detail past the last level of a texture's pyramid: getBestLevelMipmap rounds it DOWN when that is nearer (to a level
+    that does not exist: the two nearest-level filters then answer white, src/image.cpp:268-271, 293-296) and UP to the last level
+    otherwise (the 1 x 1 texel); Trilinear answers black (image.cpp:334-341).  Texture coordinates scaled by 150 put every hit of the
+    fixture's 16 x 16 and 64 x 64 textures there.  (Found by comparing the port with the reference's own translation units on random
+    scenes, tests/test_oracle.py; the port indexed the missing level, the device read past the pyramid.)"""
+    import oracle
+    g = Golden("tex_mipnearest_floor64_96x80")
+    s = g.scene
+    uv = (np.asarray(s.uv, np.float32) * np.float32(150.0)).astype(np.float32)
+    o = oracle.Oracle("port")
+    o.set_spheres(s.spheres)
+    o.set_extra_lights(s.spot_lights, s.plane_lights, g.plane_rays_1d)
+    gpu_ctx.upload_scene(s, rtb.BVH_PLOC_DEVICE)
+    gpu_ctx.set_texcoords(uv)
+    try:
+        for filtering, debug in ((2, True), (3, True), (2, False), (3, False), (4, False)):
+            o.set_textures(uv, s.textures, s.mesh_tex, filtering, 2, 2, (0, 0, 0), use_textures=not debug)
+            o_rgb, o_ids, o_t, o_st = o.render(s.pos, s.nrm, s.mesh_id, s.mats, s.point_lights, s.sphere_lights, g.camera(), g.w, g.h, max_level=g.max_level,
+                                               sphere_rays=g.sphere_rays, shadow_exhaustive=True, texture_debug=debug)
+            if debug:  # the view shows the texel itself: both outcomes occur on the textures that have a pyramid
+                hit = o_ids >= 0
+                on_pyramid = hit & np.isin(np.asarray(s.mesh_tex)[np.asarray(s.mesh_id)[np.clip(o_ids, 0, None)]], (1, 2))
+                white = (o_rgb == 1.0).all(axis=-1)
+                assert (white & on_pyramid).sum() > 500 and (~white & on_pyramid).sum() > 500
+            gpu_ctx.set_texturing(filtering, 2, 2, (0.0, 0.0, 0.0))
+            prm = rtb.make_params(g.w, g.h, g.max_level, g.sphere_rays, 0.8, g.sample_mode, g.sample_size, False, g.plane_rays_1d, True, texture_debug=debug)
+            rgb, ids, t, st = gpu_ctx.render(g.camera(), prm, want_ids=True)
+            assert np.array_equal(ids, o_ids) and bits_equal(t, o_t), f"filter {filtering}, debug view {debug}"
+            assert np.abs(rgb - o_rgb).max() <= COLOUR_TOL, f"filter {filtering}, debug view {debug}: {np.abs(rgb - o_rgb).max()}"
+            assert st.rays == o_st.rays
+    finally:
+        gpu_ctx.set_texturing(None)
+        o.set_textures()
+
+
 def test_full_size_bvh_equals_exhaustive(rtb, gpu_ctx):
     """Size-independent property at C1's full size (1024x1024, depth 3): the BVH frame equals the exhaustive frame
     bit for bit (ids, t) and to round-off in colour — both use the reference's triangle arithmetic."""

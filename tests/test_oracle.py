@@ -129,3 +129,105 @@ def test_port_postprocessing_against_reference_library_live():
         assert bits_equal(ref.postprocess(img, **cfg), port.postprocess(img, **cfg)), cfg
         (a, ra), (b, rb) = ref.postprocess(img, via_write_bitmap=True, **cfg), port.postprocess(img, via_write_bitmap=True, **cfg)
         assert bits_equal(a, b) and np.array_equal(ra, rb), cfg
+
+
+# ---- the port against the reference's own translation units on RANDOM scenes (only where oracle/_ref exists) ----
+def _random_scene(seed):
+    """20-120 random triangles of 1-4 materials (some shiny, some transparent), 1-2 point lights, sometimes a spherical light, a
+    random camera.  Triangles are large (area >> 1e-4), so the reference's epsilon early-outs (deviation 1) stay out of it."""
+    from oracle import MATERIAL_DTYPE
+    rng = np.random.default_rng(seed)
+    n, nm = int(rng.integers(20, 120)), int(rng.integers(1, 5))
+    pos = (rng.uniform(-0.8, 0.8, (n, 1, 3)) + rng.uniform(-0.35, 0.35, (n, 3, 3))).astype(np.float32)
+    fn = np.cross(pos[:, 1] - pos[:, 0], pos[:, 2] - pos[:, 0])
+    fn /= np.linalg.norm(fn, axis=1, keepdims=True)
+    nrm = (fn[:, None, :] + rng.normal(0, 0.15, (n, 3, 3))).astype(np.float32)
+    mesh = np.sort(rng.integers(0, nm, n)).astype(np.int32)
+    mats = np.zeros(nm, MATERIAL_DTYPE)
+    for m in range(nm):
+        mats[m]["kd"] = rng.uniform(0.1, 0.9, 3)
+        mats[m]["ks"] = rng.uniform(0, 0.8, 3) * (rng.random() < 0.7)
+        mats[m]["shininess"] = rng.choice([0.0, 8.0, 40.0])
+        mats[m]["transparency"] = rng.choice([1.0, 1.0, 0.4])
+    npl = int(rng.integers(1, 3))
+    pl = np.concatenate([rng.uniform(-2, 2, (npl, 3)), rng.uniform(0.3, 1, (npl, 3))], 1).astype(np.float32)
+    sl = np.concatenate([rng.uniform(-2, 2, (1, 3)), [[0.2]], rng.uniform(0.3, 1, (1, 3))], 1).astype(np.float32) if rng.random() < 0.5 else None
+    cam = dict(look_at=tuple(rng.uniform(-0.2, 0.2, 3)), euler=tuple(np.radians(rng.uniform(-60, 60, 3))), dist=float(rng.uniform(2, 4)),
+               fovy=float(np.radians(rng.uniform(35, 65))))
+    return (pos.reshape(n, 9), nrm.reshape(n, 9), mesh, mats, pl, sl, cam), rng
+
+
+def _same_frame(a, b):
+    return np.array_equal(a[1], b[1]) and bits_equal(a[2], b[2]) and bits_equal(a[0], b[0]) and a[3].rays == b[3].rays
+
+
+def _both_oracles():
+    import oracle
+    if not oracle.available("reference"):
+        pytest.skip("oracle/_ref not built here (needs /root/reference)")
+    return oracle.Oracle("reference"), oracle.Oracle("port")
+
+
+def test_port_equals_reference_on_random_scenes():
+    """Bit for bit (ids, t, colours, ray counts) on 40 random scenes: through the reference's BVH, through its brute-force loop, and
+    with the four-tap anti-aliasing; then on 30 more with sphere primitives, a spot light and a plane light thrown in."""
+    R, P = _both_oracles()
+    for seed in range(40):
+        s, _ = _random_scene(seed)
+        for kw in (dict(use_bvh=True), dict(use_bvh=False), dict(use_bvh=True, sample_mode=1)):
+            assert _same_frame(R.render(*s, 56, 40, max_level=3, sphere_rays=6, **kw), P.render(*s, 56, 40, max_level=3, sphere_rays=6, **kw)), (seed, kw)
+    try:
+        for seed in range(100, 130):
+            s, rng = _random_scene(seed)
+            sph = spot = plane = None
+            if rng.random() < 0.6:
+                k = int(rng.integers(1, 3))
+                sph = np.concatenate([rng.uniform(-0.7, 0.7, (k, 3)), rng.uniform(0.1, 0.3, (k, 1)), rng.uniform(0.1, 0.9, (k, 3)), rng.uniform(0, 0.7, (k, 3)),
+                                      rng.choice([0.0, 20.0], (k, 1)), rng.choice([1.0, 0.5], (k, 1))], 1).astype(np.float32)
+            if rng.random() < 0.5:
+                spot = np.concatenate([rng.uniform(-2, 2, (1, 3)), rng.uniform(-1, 1, (1, 3)), [[float(rng.uniform(20, 70))]], rng.uniform(0.3, 1, (1, 3))], 1).astype(np.float32)
+            if rng.random() < 0.5:
+                plane = np.concatenate([rng.uniform(-2, 2, (1, 3)), rng.uniform(-0.5, 0.5, (1, 3)), rng.uniform(-0.5, 0.5, (1, 3)), rng.uniform(0.3, 1, (1, 3))], 1).astype(np.float32)
+            for O in (R, P):
+                O.set_spheres(sph)
+                O.set_extra_lights(spot, plane, 3)
+            assert _same_frame(R.render(*s, 48, 36, max_level=3, sphere_rays=6), P.render(*s, 48, 36, max_level=3, sphere_rays=6)), seed
+    finally:
+        for O in (R, P):
+            O.set_spheres(None)
+            O.set_extra_lights(None, None, 3)
+
+
+def test_port_equals_reference_on_random_textures(capfd):
+    """60 random scenes with random textures (square powers of two WITH a mip pyramid, odd sizes without), texture coordinates from
+    -0.6 to 1.6, every filter and out-of-bounds rule, the texture-debug view now and then.  This is the test that found the level of
+    detail beyond the pyramid (the reference prints "toImageCoordinates: Invalid level" and answers white; tests/test_gpu_parity.py:
+    test_level_of_detail_beyond_the_mip_pyramid)."""
+    R, P = _both_oracles()
+    beyond = 0
+    try:
+        for seed in range(200, 260):
+            s, _ = _random_scene(seed)
+            rng = np.random.default_rng(seed + 11)
+            n, nm = len(s[0]), len(s[3])
+            uv = rng.uniform(-0.6, 1.6, (n, 6)).astype(np.float32)
+            texs = []
+            for _k in range(int(rng.integers(1, 3))):
+                if rng.random() < 0.7:
+                    w = int(2 ** rng.integers(2, 6))
+                    texs.append(rng.integers(0, 256, (w, w, 3), dtype=np.uint8))
+                else:
+                    texs.append(rng.integers(0, 256, (int(rng.integers(3, 20)), int(rng.integers(3, 20)), 3), dtype=np.uint8))
+            mt = rng.integers(-1, len(texs), nm).astype(np.int32)
+            filt, ox, oy, border = int(rng.integers(0, 5)), int(rng.integers(0, 3)), int(rng.integers(0, 3)), tuple(rng.uniform(0, 1, 3))
+            dbg = bool(rng.random() < 0.2)
+            for O in (R, P):
+                O.set_textures(uv, texs, mt, filt, ox, oy, border, use_textures=not dbg)
+            a = R.render(*s, 48, 36, max_level=2, sphere_rays=4, texture_debug=dbg)
+            beyond += "Invalid level" in capfd.readouterr().err
+            b = P.render(*s, 48, 36, max_level=2, sphere_rays=4, texture_debug=dbg)
+            assert _same_frame(a, b), (seed, filt, ox, oy, dbg, [t.shape for t in texs])
+    finally:
+        for O in (R, P):
+            O.set_textures()
+    assert beyond >= 5  # the case occurs in the sample
