@@ -266,7 +266,10 @@ void addSpheres(Scene& scene)
 Scene sceneFromSoup(const float* pos, const float* nrm, const int* mesh_id, int n_tris, const orc_material* mats, int n_mats)
 {
     Scene scene;
-    scene.meshes.resize(n_mats > 0 ? n_mats : 1);
+    int n_meshes = n_mats > 0 ? n_mats : 1;
+    for (int i = 0; mesh_id && i < n_tris; i++) // (oracle_closest_hit passes no materials: one mesh per id that occurs)
+        n_meshes = std::max(n_meshes, mesh_id[i] + 1);
+    scene.meshes.resize(n_meshes);
     for (int m = 0; m < (int)scene.meshes.size(); m++) {
         Material& mat = scene.meshes[m].material;
         if (m < n_mats && mats) {

@@ -231,3 +231,103 @@ def test_port_equals_reference_on_random_textures(capfd):
         for O in (R, P):
             O.set_textures()
     assert beyond >= 5  # the case occurs in the sample
+
+
+def test_port_equals_reference_on_random_settings():
+    """60 random scenes under random knobs: recursion depth 0-5, spherical-light ray counts 1-33, refraction factors, the three sampling
+    modes with 4-64 samples, BVH or brute force."""
+    R, P = _both_oracles()
+    for seed in range(300, 360):
+        s, rng = _random_scene(seed)
+        kw = dict(max_level=int(rng.integers(0, 6)), sphere_rays=int(rng.choice([1, 2, 3, 7, 10, 20, 33])), refraction=float(rng.choice([0.8, 0.5, 1.0, 1.3])),
+                  sample_mode=int(rng.choice([0, 1, 2])), sample_size=int(rng.choice([4, 9, 16, 25, 64])), use_bvh=bool(rng.random() < 0.7))
+        assert _same_frame(R.render(*s, 40, 28, **kw), P.render(*s, 40, 28, **kw)), (seed, kw)
+
+
+def _box_scene(seed):
+    """Axis-aligned boxes (flat bounding boxes of their faces: where the reference's slab test culls what its triangle test accepts),
+    a ground quad that is sometimes there twice (exact ties), lights and views that are sometimes axis-aligned (zero direction components)."""
+    from oracle import MATERIAL_DTYPE
+    rng = np.random.default_rng(seed)
+    tris = []
+    for _k in range(int(rng.integers(1, 5))):
+        c, h = rng.uniform(-0.6, 0.6, 3), rng.uniform(0.1, 0.4, 3)
+        if rng.random() < 0.5:
+            c, h = np.round(c * 4) / 4, np.round(h * 8) / 8 + 0.125
+        lo, hi = c - h, c + h
+        v = np.array([[x, y, z] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])])
+        for q in ((0, 1, 3, 2), (4, 6, 7, 5), (0, 4, 5, 1), (2, 3, 7, 6), (0, 2, 6, 4), (1, 5, 7, 3)):
+            tris += [[v[q[0]], v[q[1]], v[q[2]]], [v[q[0]], v[q[2]], v[q[3]]]]
+    y = -0.7
+    ground = [[[-1.5, y, -1.5], [1.5, y, -1.5], [1.5, y, 1.5]], [[-1.5, y, -1.5], [1.5, y, 1.5], [-1.5, y, 1.5]]]
+    tris += ground * (2 if rng.random() < 0.5 else 1)
+    pos = np.array(tris, np.float32)
+    n = len(pos)
+    fn = np.cross(pos[:, 1] - pos[:, 0], pos[:, 2] - pos[:, 0])
+    fn /= np.linalg.norm(fn, axis=1, keepdims=True)
+    nrm = np.repeat(fn[:, None, :], 3, 1).astype(np.float32)
+    nm = int(rng.integers(1, 4))
+    mesh = np.sort(rng.integers(0, nm, n)).astype(np.int32)
+    mats = np.zeros(nm, MATERIAL_DTYPE)
+    for m in range(nm):
+        mats[m]["kd"] = rng.uniform(0.1, 0.9, 3)
+        mats[m]["ks"] = rng.uniform(0, 0.8, 3) * (rng.random() < 0.7)
+        mats[m]["shininess"] = rng.choice([0.0, 8.0])
+        mats[m]["transparency"] = rng.choice([1.0, 1.0, 0.4])
+    pl = np.concatenate([rng.uniform(-2, 2, (1, 3)), rng.uniform(0.3, 1, (1, 3))], 1).astype(np.float32)
+    if rng.random() < 0.4:
+        pl[0, :3] = np.round(pl[0, :3])
+    eul = rng.uniform(-60, 60, 3)
+    if rng.random() < 0.5:
+        eul = np.round(eul / 45) * 45
+    cam = dict(look_at=(0.0, 0.0, 0.0), euler=tuple(np.radians(eul)), dist=float(rng.choice([2.0, 3.0, rng.uniform(2, 4)])), fovy=float(np.radians(50)))
+    return pos.reshape(n, 9), nrm.reshape(n, 9), mesh, mats, pl, None, cam
+
+
+def test_port_equals_reference_on_axis_aligned_scenes():
+    """The port restates the reference's BVH WITH its slab test, so it must cull exactly what the reference culls: 60 scenes of
+    axis-aligned boxes, coplanar duplicates, axis-aligned lights and views, as run (BVH) and through the brute-force loop."""
+    R, P = _both_oracles()
+    for seed in range(400, 460):
+        s = _box_scene(seed)
+        for kw in (dict(use_bvh=True), dict(use_bvh=False)):
+            assert _same_frame(R.render(*s, 41, 29, max_level=3, **kw), P.render(*s, 41, 29, max_level=3, **kw)), (seed, kw)
+
+
+def test_port_closest_hit_equals_reference_on_random_rays():
+    """BoundingVolumeHierarchy::intersect for caller-supplied rays: 3 000 rays per scene, a quarter with an exactly-zero direction
+    component, a quarter with directions of length 0.2-5 (t is measured along normalize(d), the hit point uses d itself)."""
+    R, P = _both_oracles()
+    hits = 0
+    for seed in range(500, 530):
+        s, rng = _random_scene(seed)
+        m = 3000
+        o, d = rng.uniform(-2, 2, (m, 3)), rng.normal(0, 1, (m, 3))
+        d[: m // 4, rng.integers(0, 3)] = 0.0
+        d[m // 4: m // 2] *= rng.uniform(0.2, 5, (m // 4, 1))
+        rays = np.concatenate([o, d], 1).astype(np.float32)
+        for use_bvh in (False, True):
+            ia, ta = R.closest_hit(s[0], s[1], s[2], rays, use_bvh=use_bvh)
+            ib, tb = P.closest_hit(s[0], s[1], s[2], rays, use_bvh=use_bvh)
+            assert np.array_equal(ia, ib) and bits_equal(ta, tb), (seed, use_bvh)
+            hits += int((ia >= 0).sum())
+    assert hits > 5000
+
+
+def test_port_postprocessing_equals_reference_on_random_settings():
+    """Screen::postprocessImage and the bloom + 8-bit conversion of writeBitmapToFile: 120 random images (1 x 1 up to 39 x 49, some with a
+    very bright pixel) under random settings, filters wider than the image and sigma 0 included — bit for bit."""
+    R, P = _both_oracles()
+    for seed in range(600, 720):
+        rng = np.random.default_rng(seed)
+        h, w = int(rng.integers(1, 40)), int(rng.integers(1, 50))
+        img = (rng.uniform(0, 1, (h, w, 3)) ** 2 * rng.choice([1.0, 2.5, 6.0])).astype(np.float32)
+        if rng.random() < 0.2:
+            img[rng.integers(0, h), rng.integers(0, w)] = np.float32(50.0)
+        kw = dict(filtering_option=int(rng.integers(0, 6)), kernel=int(rng.integers(0, 2)), kernel_repetitions=int(rng.integers(0, 4)),
+                  filter_size=int(rng.choice([0, 1, 2, 3, 5, 8, 13])), sigma=float(rng.choice([0.0, 0.5, 2.0, 5.0])), exposure=float(rng.choice([0.2, 0.5, 1.5])),
+                  gamma_correction=bool(rng.random() < 0.5), gamma=float(rng.choice([1.0, 1.8, 2.2])), bloom_live=bool(rng.random() < 0.7))
+        a, b = R.postprocess(img, **kw), P.postprocess(img, **kw)
+        assert bits_equal(a, b), (seed, kw)
+        a, b = R.postprocess(img, via_write_bitmap=True, **kw), P.postprocess(img, via_write_bitmap=True, **kw)
+        assert bits_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (seed, kw)
