@@ -239,6 +239,29 @@ def test_level_of_detail_beyond_the_mip_pyramid(rtb, gpu_ctx):
         o.set_textures()
 
 
+def test_random_scenes_match_the_port(rtb, gpu_ctx):
+    """Device against the port on the random scenes the port itself is pinned on (tests/test_oracle.py: bit-identical to the reference's own
+    translation units there): random triangle soups with shiny and transparent materials, one or two point lights, sometimes a spherical
+    light, a random camera, depth 3."""
+    import oracle
+    from test_oracle import _random_scene
+    o = oracle.Oracle("port")
+    o.set_spheres(None)
+    o.set_extra_lights(None, None, 3)
+    o.set_textures()
+    for seed in range(1000, 1012):
+        (pos, nrm, mesh, mats, pl, sl, c), rng = _random_scene(seed)
+        cam = rtb.make_camera(look_at=c["look_at"], euler_deg=tuple(float(v) for v in rng.uniform(-60, 60, 3)), dist=c["dist"], fovy_deg=float(rng.uniform(35, 65)))
+        sc = rtb.SceneData(pos, nrm, mesh, mats, pl, sl if sl is not None else np.zeros((0, 7), np.float32))
+        o_rgb, o_ids, o_t, o_st = o.render(pos, nrm, mesh, mats, pl, sl, cam, 64, 48, max_level=3, sphere_rays=6, shadow_exhaustive=True)
+        assert (o_ids >= 0).mean() > 0.02
+        gpu_ctx.upload_scene(sc, rtb.BVH_PLOC_DEVICE)
+        rgb, ids, t, st = gpu_ctx.render(cam, rtb.make_params(64, 48, 3, 6), want_ids=True)
+        assert np.array_equal(ids, o_ids) and bits_equal(t, o_t), f"seed {seed}: {(ids != o_ids).sum()} ids differ"
+        assert np.abs(rgb - o_rgb).max() <= COLOUR_TOL, f"seed {seed}: colour differs by {np.abs(rgb - o_rgb).max()}"
+        assert (st.primary_rays, st.shadow_queries, st.secondary_rays) == (o_st.primary_rays, o_st.shadow_queries, o_st.secondary_rays), f"seed {seed}"
+
+
 def test_full_size_bvh_equals_exhaustive(rtb, gpu_ctx):
     """Size-independent property at C1's full size (1024x1024, depth 3): the BVH frame equals the exhaustive frame
     bit for bit (ids, t) and to round-off in colour — both use the reference's triangle arithmetic."""
